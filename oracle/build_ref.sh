@@ -1,0 +1,49 @@
+#!/usr/bin/env bash
+# Build the UNMODIFIED reference hot path (hmc.c + mersenne_inline.c) from where it lies under
+# /root/reference into oracle/_ref/ as shared objects the tests/bench can dlopen.  TEST INFRASTRUCTURE ONLY.
+#
+#   libhmcref_<NT>x<NX>_<flavour>[_nsN].so
+#
+# * No reference source is copied into the repo: the two unguarded lattice #defines (hmc.c:14-15) are
+#   rewritten by sed in a pipe that feeds gcc on stdin.
+# * flavour "compat"  = verbatim source (fm_conjugate_mul == fm_mul).
+# * flavour "adjoint" = verbatim + the one-hunk correction inside fm_conjugate_mul only (hmc.c:197-248):
+#   every hop sign flipped and exp(mu) <-> exp(-mu), i.e. the true M^dagger.
+# * "-Dmain=hmc_main" turns the driver into a callable; -fPIC (semantic interposition left on) keeps every
+#   internal call to fm_mul/fm_conjugate_mul/fmdm_invert_cg going through the PLT, so a library loaded
+#   earlier can interpose them.
+# * optional _nsN: 'int nsteps = 10;' (hmc.c:708) rewritten to N leapfrog steps.
+set -euo pipefail
+REF=${TB_REFERENCE_DIR:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+OUT=$HERE/_ref
+OPT=${TB_REF_OPT:--O3 -march=x86-64-v3}
+mkdir -p "$OUT"
+if [ ! -f "$REF/hmc.c" ]; then
+  echo "build_ref.sh: $REF/hmc.c not present; keeping prebuilt files in $OUT" >&2
+  exit 0
+fi
+
+build_one() { # NT NX flavour [nsteps]
+  local nt=$1 nx=$2 fl=$3 ns=${4:-10}
+  local name="libhmcref_${nt}x${nx}_${fl}"
+  [ "$ns" != 10 ] && name="${name}_ns${ns}"
+  local sedprog="s/^#define NT 32/#define NT ${nt}/; s/^#define NX 32/#define NX ${nx}/; s/int nsteps = 10;/int nsteps = ${ns};/"
+  if [ "$fl" = adjoint ]; then
+    sedprog="$sedprog; 197,248{s/v += 0\\.5/v @@ 0.5/; s/v -= 0\\.5/v += 0.5/; s/v @@ 0\\.5/v -= 0.5/; s/expmmu/EXPTMP/; s/expmu/expmmu/; s/EXPTMP/expmu/}"
+  fi
+  sed "$sedprog" "$REF/hmc.c" | gcc $OPT -std=c99 -w -fPIC -shared -Dmain=hmc_main \
+      -I"$HERE/shim" -I"$REF" -x c - -x none "$REF/mersenne_inline.c" "$HERE/shim/lapack_stub.c" \
+      -o "$OUT/$name.so" -lm
+}
+
+SIZES=${TB_REF_SIZES:-"8x8 16x16 16x32 32x32 64x64 128x128 256x256"}
+for s in $SIZES; do
+  nt=${s%x*}; nx=${s#*x}
+  build_one "$nt" "$nx" compat
+  build_one "$nt" "$nx" adjoint
+done
+# light-mass trajectory oracle: 40 leapfrog steps
+build_one 32 32 adjoint 40
+build_one 64 64 adjoint 40
+ls "$OUT" | sed 's/^/  built oracle\/_ref\//'

@@ -1,0 +1,202 @@
+/* thirring_oracle.c — CPU restatement of the Thirring2D HMC fermion hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (thirring2d_b200/, include/, the C-ABI
+ * libraries) may include, link or execute this file; it is the checker for tests/,
+ * __graft_entry__.smoke() and the cpu_baseline / --impl reference legs of bench.py.
+ *
+ * Parity status: PINNED.  tests/test_oracle_pinned.py checks every function below
+ *   (i)  bit-for-bit against the reference itself (/root/reference/hmc.c compiled unmodified into
+ *        oracle/_ref/libhmcref_*.so by oracle/build_ref.sh) whenever oracle/_ref is present, and
+ *   (ii) against the committed fixtures tests/golden/ (npz) that tests/golden/make_golden.py generated
+ *        from those reference builds (the reference ships no golden vectors of its own).
+ *
+ * Conventions (all from /root/reference/hmc.c):
+ *   vectors   complex FP64, flat [t][x], interleaved (re,im)             (hmc.c:105-112 row-pointer arrays)
+ *   gauge     real FP64 angles, flat [t][x][dir], dir 0 = t, 1 = x      (hmc.c:47, 889-897)
+ *   eta       eta[t][x][0] = +1 for even x, -1 for odd x; eta[..][1]=1  (hmc.c:914-921)
+ *   boundary  antiperiodic in BOTH directions: the wrap-around hop enters with the opposite sign
+ *             ("if (t2 > t) += else -=", hmc.c:143-148,154-158,165-170,175-180)
+ *   mode 0    REF_COMPAT: fm_conjugate_mul is a verbatim copy of fm_mul (hmc.c:188-249)
+ *   mode 1    ADJOINT   : fm_conjugate_mul applies the true M^dagger (all hop signs flipped,
+ *                         exp(mu) <-> exp(-mu)); equals the one-hunk corrected reference build.
+ *
+ * Every floating-point expression keeps the reference's evaluation order; compile with
+ * -ffp-contract=off (as gcc does for the reference under -std=c99) and results are bit-identical.
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_CG_ACCURACY 1e-30      /* hmc.c:34 */
+#define ORC_CG_MAX_ITER 100000     /* hmc.c:35 */
+
+enum { ORC_MODE_REF_COMPAT = 0, ORC_MODE_ADJOINT = 1 };
+enum { ORC_CG_CONVERGED = 0, ORC_CG_MAXITER = 1, ORC_CG_DIVERGED = 2, ORC_CG_ZERO_SOURCE = 3 };
+
+typedef struct { double re, im; } cplx;
+
+static inline int eta0(int x) { return (x % 2 == 0) ? 1 : -1; }   /* hmc.c:917-921 */
+
+/* one hop term:  +-( 0.5*(cA + s*sA*I) * eta * ex * w ), evaluated left to right as the reference does
+ * (hmc.c:144).  conj_link selects (cA - sA*I). */
+static inline void hop(cplx *v, double cA, double sA, int conj_link, int eta, double ex, int use_ex,
+                       cplx w, int add)
+{
+  double lr = 0.5 * cA, li = 0.5 * (conj_link ? -sA : sA);
+  lr = lr * (double)eta;  li = li * (double)eta;
+  if (use_ex) { lr = lr * ex; li = li * ex; }
+  double pr = lr * w.re - li * w.im;
+  double pi = lr * w.im + li * w.re;
+  if (add) { v->re += pr; v->im += pi; } else { v->re -= pr; v->im -= pi; }
+}
+
+/* Shared body of fm_mul (hmc.c:132-183) and of the corrected fm_conjugate_mul.
+ * dagger = 0: M.   dagger = 1: M^dagger = every "+=" <-> "-=" on the hops and expmu <-> expmmu. */
+static void apply(int nt, int nx, double m, double mu, int dagger,
+                  const cplx *in, cplx *out, const double *A)
+{
+  const double expmu = exp(mu), expmmu = exp(-mu);                 /* hmc.c:127-128 */
+  const double e_fwd = dagger ? expmmu : expmu;                    /* factor on the +t hop */
+  const double e_bwd = dagger ? expmu : expmmu;                    /* factor on the -t hop */
+  for (int t = 0; t < nt; t++) for (int x = 0; x < nx; x++) {
+    cplx v;
+    const cplx c = in[t * nx + x];
+    v.re = m * c.re;  v.im = m * c.im;                             /* hmc.c:137 */
+
+    /* positive time direction, hmc.c:140-148 */
+    int t2 = (t + 1) % nt;
+    double a = A[(t * nx + x) * 2 + 0];
+    int add = (t2 > t);
+    hop(&v, cos(a), sin(a), 0, eta0(x), e_fwd, 1, in[t2 * nx + x], dagger ? !add : add);
+
+    /* negative time direction, hmc.c:151-159: link and eta taken at (t2,x) */
+    t2 = (t - 1 + nt) % nt;
+    a = A[(t2 * nx + x) * 2 + 0];
+    add = (t2 > t);
+    hop(&v, cos(a), sin(a), 1, eta0(x), e_bwd, 1, in[t2 * nx + x], dagger ? !add : add);
+
+    /* positive x direction, hmc.c:162-170 */
+    int x2 = (x + 1) % nx;
+    a = A[(t * nx + x) * 2 + 1];
+    add = (x2 > x);
+    hop(&v, cos(a), sin(a), 0, 1, 1.0, 0, in[t * nx + x2], dagger ? !add : add);
+
+    /* negative x direction, hmc.c:172-180: link taken at (t,x2) */
+    x2 = (x - 1 + nx) % nx;
+    a = A[(t * nx + x2) * 2 + 1];
+    add = (x2 > x);
+    hop(&v, cos(a), sin(a), 1, 1, 1.0, 0, in[t * nx + x2], dagger ? !add : add);
+
+    out[t * nx + x] = v;                                           /* hmc.c:182 */
+  }
+}
+
+/* fm_mul, hmc.c:123-184 */
+void orc_fm_mul(int nt, int nx, double m, double mu, const double *in, double *out, const double *A)
+{ apply(nt, nx, m, mu, 0, (const cplx *)in, (cplx *)out, A); }
+
+/* true adjoint M^dagger (what the corrected fm_conjugate_mul applies) */
+void orc_fm_dagger_mul(int nt, int nx, double m, double mu, const double *in, double *out, const double *A)
+{ apply(nt, nx, m, mu, 1, (const cplx *)in, (cplx *)out, A); }
+
+/* fm_conjugate_mul, hmc.c:188-249: identical to fm_mul as shipped (mode 0), M^dagger in mode 1 */
+void orc_fm_conjugate_mul(int nt, int nx, double m, double mu, int mode,
+                          const double *in, double *out, const double *A)
+{ apply(nt, nx, m, mu, mode == ORC_MODE_ADJOINT, (const cplx *)in, (cplx *)out, A); }
+
+/* fmdm_invert_cg, hmc.c:341-404.  Returns a status code and, through the optional pointers, the
+ * number of loop passes executed (k at exit; 0 for the zero-source early return) and the last ||r||^2.
+ * The reference prints "Cannot invert fermion matrix" and exit(1)s on divergence (hmc.c:383-388); the
+ * oracle returns ORC_CG_DIVERGED instead so a test can observe it. */
+int orc_fmdm_invert_cg(int nt, int nx, double m, double mu, int mode, const double *b_, double *x_,
+                       const double *A, int max_iter, int *iters, double *rr_final)
+{
+  const int V = nt * nx;
+  const cplx *b = (const cplx *)b_;
+  cplx *xo = (cplx *)x_;
+  cplx *r = malloc(sizeof(cplx) * V), *p = malloc(sizeof(cplx) * V);
+  cplx *Mp = malloc(sizeof(cplx) * V), *MMp = malloc(sizeof(cplx) * V);
+  double rr = 0, rr_old = 0, rr_init, pMp, a;
+  int status = ORC_CG_MAXITER, k = 0;
+  if (max_iter <= 0) max_iter = ORC_CG_MAX_ITER;
+
+  for (int i = 0; i < V; i++) {                                    /* hmc.c:350-356 */
+    xo[i].re = 0; xo[i].im = 0;
+    r[i] = b[i];
+    p[i] = r[i];
+    rr_old += r[i].re * r[i].re + r[i].im * r[i].im;
+  }
+  rr_init = rr_old;
+  rr = rr_old;
+  if (rr_old < ORC_CG_ACCURACY) { status = ORC_CG_ZERO_SOURCE; goto done; }   /* hmc.c:359-361 */
+
+  for (k = 1; k < max_iter; k++) {                                 /* hmc.c:364 */
+    apply(nt, nx, m, mu, 0, p, Mp, A);                             /* hmc.c:366 */
+    apply(nt, nx, m, mu, mode == ORC_MODE_ADJOINT, Mp, MMp, A);    /* hmc.c:367 */
+    pMp = 0;
+    for (int i = 0; i < V; i++) pMp += p[i].re * MMp[i].re + p[i].im * MMp[i].im;   /* hmc.c:369-370 */
+    a = rr_old / pMp;
+    for (int i = 0; i < V; i++) { xo[i].re += a * p[i].re; xo[i].im += a * p[i].im; }     /* :372-373 */
+    for (int i = 0; i < V; i++) { r[i].re -= a * MMp[i].re; r[i].im -= a * MMp[i].im; }   /* :374-375 */
+    rr = 0;
+    for (int i = 0; i < V; i++) rr += r[i].re * r[i].re + r[i].im * r[i].im;              /* :377-379 */
+    if (rr < ORC_CG_ACCURACY) { status = ORC_CG_CONVERGED; break; }                       /* :381 */
+    if (rr / rr_init > 1e10) { status = ORC_CG_DIVERGED; break; }                         /* :383 */
+    double beta = rr / rr_old;                                                            /* :390 */
+    for (int i = 0; i < V; i++) { p[i].re = r[i].re + beta * p[i].re; p[i].im = r[i].im + beta * p[i].im; }
+    rr_old = rr;
+  }
+done:
+  if (iters) *iters = k;
+  if (rr_final) *rr_final = rr;
+  free(r); free(p); free(Mp); free(MMp);
+  return status;
+}
+
+/* fm_invert_cg, hmc.c:408-414:  x = (M~ M)^-1 M~ v */
+int orc_fm_invert_cg(int nt, int nx, double m, double mu, int mode, const double *v, double *x,
+                     const double *A, int max_iter, int *iters, double *rr_final)
+{
+  double *tmp = malloc(sizeof(double) * 2 * nt * nx);
+  orc_fm_conjugate_mul(nt, nx, m, mu, mode, v, tmp, A);
+  int st = orc_fmdm_invert_cg(nt, nx, m, mu, mode, tmp, x, A, max_iter, iters, rr_final);
+  free(tmp);
+  return st;
+}
+
+/* fermion_matrix, hmc.c:269-310: dense V x V, column-major M[row + col*V], interleaved complex */
+void orc_fermion_matrix(int nt, int nx, double m, double mu, const double *A, double *M_)
+{
+  const int V = nt * nx;
+  cplx *M = (cplx *)M_;
+  const double expmu = exp(mu), expmmu = exp(-mu);
+  memset(M, 0, sizeof(cplx) * (size_t)V * V);
+  for (int t = 0; t < nt; t++) for (int x = 0; x < nx; x++) {
+    const int row = nx * t + x;
+    M[row + (size_t)row * V].re = m;
+    int t2 = (t + 1) % nt;
+    double a = A[(t * nx + x) * 2], s = (t2 > t) ? 0.5 : -0.5;
+    cplx *e = &M[row + (size_t)(nx * t2 + x) * V];
+    e->re = s * cos(a) * eta0(x) * expmu;  e->im = s * sin(a) * eta0(x) * expmu;
+    t2 = (t - 1 + nt) % nt;
+    a = A[(t2 * nx + x) * 2];  s = (t2 > t) ? 0.5 : -0.5;
+    e = &M[row + (size_t)(nx * t2 + x) * V];
+    e->re = s * cos(a) * eta0(x) * expmmu;  e->im = -(s * sin(a)) * eta0(x) * expmmu;
+    int x2 = (x + 1) % nx;
+    a = A[(t * nx + x) * 2 + 1];  s = (x2 > x) ? 0.5 : -0.5;
+    e = &M[row + (size_t)(nx * t + x2) * V];
+    e->re = s * cos(a);  e->im = s * sin(a);
+    x2 = (x - 1 + nx) % nx;
+    a = A[(t * nx + x2) * 2 + 1];  s = (x2 > x) ? 0.5 : -0.5;
+    e = &M[row + (size_t)(nx * t + x2) * V];
+    e->re = s * cos(a);  e->im = -(s * sin(a));
+  }
+}
+
+/* Re<a,b> summed sequentially in (t,x) order, as every action in hmc.c does (e.g. :456-459) */
+double orc_re_dot(int n, const double *a, const double *b)
+{
+  double s = 0;
+  for (int i = 0; i < n; i++) s += a[2 * i] * b[2 * i] + a[2 * i + 1] * b[2 * i + 1];
+  return s;
+}
