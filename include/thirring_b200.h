@@ -1,0 +1,124 @@
+/* thirring_b200.h — C-ABI of the B200-native Thirring2D fermion hot path.
+ *
+ * Scope: the staggered Dirac apply with U(1) auxiliary-field links (M, M^dagger, M~M), the CG inverter on
+ * M~M and the BLAS-1 reductions it needs, FP64, batched over independent Markov chains / sources.
+ * Each entry point cites the reference interface it replaces (file:line under rantahar/Thirring2D).
+ * The reference-signature symbols themselves (fm_mul, fm_conjugate_mul, fmdm_invert_cg, ...) live in
+ * thirring_hmc_abi.h and are implemented on top of this handle API.
+ *
+ * Plain C: pointers and sizes only.  Every function returns TB_OK (0) or a negative TB_E* code;
+ * tb_last_error() gives the message.  There is NO CPU fallback: without a CUDA device tb_create fails.
+ *
+ * Host ("canonical") layouts — what the reference's row-pointer arrays flatten to:
+ *   vector  double[nchains][NT][NX][2]   (re,im) of the reference's _Complex double v[t][x]  (hmc.c:105-112)
+ *   gauge   double[nchains][NT][NX][2]   A[t][x][dir], dir 0 = t-link, 1 = x-link            (hmc.c:47,889-897)
+ * Device layout (tb_*_dev entry points): site-major, chain-minor structure of arrays,
+ *   vector  double2[NT][NX][nchains]     so neighbouring lanes are neighbouring chains of the same site.
+ */
+#ifndef THIRRING_B200_H
+#define THIRRING_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tb_ctx tb_ctx;
+
+/* operator modes: what "fm_conjugate_mul" means */
+#define TB_MODE_REF_COMPAT 0 /* M~ == M, as shipped (hmc.c:188-249 is a copy of hmc.c:123-184) */
+#define TB_MODE_ADJOINT    1 /* M~ == M^dagger, the mathematically intended operator            */
+
+/* operators for tb_apply* */
+#define TB_OP_M     0 /* fm_mul            hmc.c:123-184 */
+#define TB_OP_MDAG  1 /* true adjoint of fm_mul (all hop signs flipped, e^{mu} <-> e^{-mu}) */
+#define TB_OP_MCONJ 2 /* fm_conjugate_mul  hmc.c:188-249: M in REF_COMPAT, M^dagger in ADJOINT */
+#define TB_OP_MDM   3 /* M~ (M v): what fmdm_mul (hmc.c:259-264) intends; the CG matrix */
+
+/* return codes */
+#define TB_OK          0
+#define TB_EINVAL     -1
+#define TB_ECUDA      -2
+#define TB_ENODEVICE  -3
+#define TB_ENOMEM     -4
+
+/* per-chain CG status (hmc.c:341-404) */
+#define TB_CG_CONVERGED   0 /* rr < accuracy                      hmc.c:381 */
+#define TB_CG_MAXITER     1 /* loop ran to CG_MAX_ITER-1 passes   hmc.c:364 (silent in the reference) */
+#define TB_CG_DIVERGED    2 /* rr/rr_init > 1e10                  hmc.c:383-388 (reference: print + exit(1)) */
+#define TB_CG_ZERO_SOURCE 3 /* ||b||^2 < accuracy, x = 0 returned hmc.c:359-361 */
+
+const char *tb_last_error(void);
+int tb_device_count(void);
+
+/* Create a context for nchains independent NT x NX lattices on CUDA device `device`.
+ * Replaces the compile-time NT/NX (hmc.c:14-15) and the file-scope globals (hmc.c:38-50). */
+int tb_create(tb_ctx **out, int nt, int nx, int nchains, int mode, int device);
+int tb_destroy(tb_ctx *ctx);
+
+/* Use an existing CUDA stream (cudaStream_t passed as void*), e.g. torch's current stream. */
+int tb_set_stream(tb_ctx *ctx, void *cuda_stream);
+int tb_synchronize(tb_ctx *ctx);
+
+/* Mass m and chemical potential mu (globals hmc.c:38,40).  n == 1 broadcasts one value to every chain,
+ * n == nchains sets them per chain.  exp(+-mu) is evaluated on the host with libm, as hmc.c:127-128 does. */
+int tb_set_params(tb_ctx *ctx, const double *m, const double *mu, int n);
+
+/* CG stopping rule: absolute ||r||^2 < accuracy (CG_ACCURACY 1e-30, hmc.c:34) and at most max_iter-1
+ * passes (CG_MAX_ITER 100000, hmc.c:35).  Defaults are the reference's. */
+int tb_set_cg(tb_ctx *ctx, double accuracy, int max_iter);
+
+/* Tuning knobs (0 = automatic): rows marched per thread in the stencil, CG iterations per graph launch,
+ * solver selection (0 auto, 1 streaming multi-kernel, 2 on-chip resident). */
+int tb_set_tuning(tb_ctx *ctx, int rows_per_thread, int iters_per_launch, int solver);
+
+/* ---- host-buffer entry points (copies inside; this is what the reference-facing shim calls) ---------- */
+
+/* Upload angles A and build the link fields W_mu = s * 1/2 * eta_mu * exp(iA_mu) once (replaces the
+ * sin/cos re-evaluated inside every apply, hmc.c:140-141,152-153,163-164,173-174). */
+int tb_set_gauge(tb_ctx *ctx, const double *A_host);
+
+/* out = Op in, Op one of TB_OP_* (fm_mul hmc.c:123, fm_conjugate_mul hmc.c:188, fmdm_mul hmc.c:259). */
+int tb_apply(tb_ctx *ctx, int op, const double *in_host, double *out_host);
+
+/* fmdm_invert_cg (hmc.c:341-404), batched: solve (M~ M) x = b for every chain from x0 = 0.
+ * status / iters / rr may be NULL, else arrays of nchains. */
+int tb_cg(tb_ctx *ctx, const double *b_host, double *x_host, int *status, int *iters, double *rr);
+
+/* fm_invert_cg (hmc.c:408-414), batched: x = (M~ M)^-1 M~ v. */
+int tb_invert(tb_ctx *ctx, const double *v_host, double *x_host, int *status, int *iters, double *rr);
+
+/* ---- device-resident entry points (no PCIe traffic; device layout unless stated) -------------------- */
+
+size_t tb_vec_doubles(const tb_ctx *ctx); /* doubles in one device vector = 2*NT*NX*nchains */
+
+/* canonical [chain][t][x] <-> device [t][x][chain] re-layout, both buffers on the device */
+int tb_pack_dev(tb_ctx *ctx, const double *d_canonical, double *d_vec);
+int tb_unpack_dev(tb_ctx *ctx, const double *d_vec, double *d_canonical);
+
+/* links from angles already on the device, canonical gauge layout */
+int tb_set_gauge_dev(tb_ctx *ctx, const double *d_A_canonical);
+
+int tb_apply_dev(tb_ctx *ctx, int op, const double *d_in, double *d_out);
+
+/* Batched CG on device vectors; results of the last solve are read with tb_cg_result. */
+int tb_cg_dev(tb_ctx *ctx, const double *d_b, double *d_x);
+int tb_invert_dev(tb_ctx *ctx, const double *d_v, double *d_x);
+int tb_cg_result(tb_ctx *ctx, int *status, int *iters, double *rr);
+
+/* Re<a,b> per chain, summed in a fixed (run-to-run deterministic) tree; out = nchains doubles on the HOST.
+ * Replaces the sequential action sums, e.g. hmc.c:456-459, 472-475. */
+int tb_re_dot_dev(tb_ctx *ctx, const double *d_a, const double *d_b, double *out_host);
+
+/* Counters for bench.py: kernels launched by this context since creation / since the last reset. */
+long long tb_launch_count(const tb_ctx *ctx);
+int tb_reset_launch_count(tb_ctx *ctx);
+
+/* Milliseconds the device spent in the last tb_cg_dev/tb_invert_dev call (CUDA events on the context stream). */
+double tb_last_solve_ms(const tb_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* THIRRING_B200_H */

@@ -46,4 +46,5 @@ done
 # light-mass trajectory oracle: 40 leapfrog steps
 build_one 32 32 adjoint 40
 build_one 64 64 adjoint 40
+gcc -O2 -o "$OUT/ref_hmc" "$HERE/ref_launcher.c" -ldl
 ls "$OUT" | sed 's/^/  built oracle\/_ref\//'

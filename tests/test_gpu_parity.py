@@ -1,0 +1,206 @@
+"""GPU parity tests proper: the CUDA path through the C-ABI against the CPU oracle on the same seeded inputs.
+
+T-numbers refer to SURVEY.md section 8(c).  Tolerances: apply 1e-13 (l2 and max-norm relative), CG iteration
+count within +-1 of the oracle and solution within 1e-12 l2-relative.
+"""
+import numpy as np
+import pytest
+
+from tests.util import APPLY_TOL, CG_SOL_TOL, assert_close, random_gauge, random_vector, smooth_gauge
+
+pytestmark = pytest.mark.gpu
+
+tb = pytest.importorskip("thirring2d_b200")
+
+
+def oracle_apply(oracle, op, v, A, m, mu, mode):
+    out = np.empty_like(v)
+    for c in range(v.shape[0]):
+        mc = m[c] if np.ndim(m) else m
+        muc = mu[c] if np.ndim(mu) else mu
+        if op == tb.OP_M:
+            out[c] = oracle.fm_mul(v[c], A[c], mc, muc)
+        elif op == tb.OP_MDAG:
+            out[c] = oracle.fm_dagger_mul(v[c], A[c], mc, muc)
+        elif op == tb.OP_MCONJ:
+            out[c] = oracle.fm_conjugate_mul(v[c], A[c], mc, muc, mode)
+        else:
+            out[c] = oracle.fm_conjugate_mul(oracle.fm_mul(v[c], A[c], mc, muc), A[c], mc, muc, mode)
+    return out
+
+
+@pytest.mark.parametrize("nt,nx,nchains", [(8, 8, 1), (16, 32, 1), (32, 32, 1), (64, 64, 1), (6, 10, 1),
+                                           (8, 8, 3), (16, 16, 8), (32, 32, 32), (16, 16, 40), (64, 64, 64),
+                                           (12, 20, 33)])
+@pytest.mark.parametrize("mode", [tb.MODE_REF_COMPAT, tb.MODE_ADJOINT])
+def test_T1_apply_matches_oracle(oracle, nt, nx, nchains, mode):
+    rng = np.random.default_rng(1000 + nt * 7 + nx * 3 + nchains)
+    A = random_gauge(rng, nchains, nt, nx)
+    v = random_vector(rng, nchains, nt, nx)
+    m = rng.uniform(0.05, 2.0, size=nchains)
+    mu = rng.uniform(-0.3, 0.3, size=nchains)
+    with tb.Context(nt, nx, nchains, mode) as ctx:
+        ctx.set_params(m, mu)
+        ctx.set_gauge(A)
+        for rows in (0, 1, 4):
+            ctx.set_tuning(rows_per_thread=rows)
+            for op in (tb.OP_M, tb.OP_MDAG, tb.OP_MCONJ, tb.OP_MDM):
+                got = ctx.apply(op, v)
+                ref = oracle_apply(oracle, op, v, A, m, mu, mode)
+                assert_close(got, ref, APPLY_TOL, f"op {op} rows {rows}")
+
+
+def test_T1_compat_conjugate_is_bitwise_fm_mul():
+    """REF_COMPAT: fm_conjugate_mul == fm_mul exactly."""
+    rng = np.random.default_rng(5)
+    A = random_gauge(rng, 4, 16, 16)
+    v = random_vector(rng, 4, 16, 16)
+    with tb.Context(16, 16, 4, tb.MODE_REF_COMPAT, m=0.7, mu=0.1) as ctx:
+        ctx.set_gauge(A)
+        assert np.array_equal(ctx.fm_mul(v), ctx.fm_conjugate_mul(v))
+
+
+def test_T2_apply_matches_dense_matrix(oracle):
+    """Independent of the matrix-free oracle: dense fermion_matrix() (hmc.c:269-310) times v."""
+    rng = np.random.default_rng(7)
+    nt = nx = 16
+    A = random_gauge(rng, 2, nt, nx)
+    v = random_vector(rng, 2, nt, nx)
+    with tb.Context(nt, nx, 2, tb.MODE_ADJOINT, m=0.3, mu=0.2) as ctx:
+        ctx.set_gauge(A)
+        Mv, Mdv = ctx.fm_mul(v), ctx.fm_dagger_mul(v)
+    for c in range(2):
+        Md = oracle.fermion_matrix(A[c], 0.3, 0.2)
+        assert_close(Mv[c].ravel(), Md @ v[c].ravel(), APPLY_TOL, "dense M")
+        assert_close(Mdv[c].ravel(), Md.conj().T @ v[c].ravel(), APPLY_TOL, "dense M^dagger")
+
+
+@pytest.mark.parametrize("nt,nx,nchains", [(32, 32, 5), (64, 64, 32)])
+def test_T3_adjointness(nt, nx, nchains):
+    """<a, M b> = <M^dagger a, b> to 1e-13 (the corrected identity of SURVEY Appendix A.13)."""
+    rng = np.random.default_rng(11)
+    A = random_gauge(rng, nchains, nt, nx)
+    a = random_vector(rng, nchains, nt, nx)
+    b = random_vector(rng, nchains, nt, nx)
+    with tb.Context(nt, nx, nchains, tb.MODE_ADJOINT, m=0.2, mu=0.15) as ctx:
+        ctx.set_gauge(A)
+        Mb, Mda = ctx.fm_mul(b), ctx.fm_dagger_mul(a)
+    for c in range(nchains):
+        lhs = np.vdot(a[c], Mb[c])
+        rhs = np.vdot(Mda[c], b[c])
+        assert abs(lhs - rhs) <= 1e-13 * abs(lhs) + 1e-10
+
+
+CG_CASES = [
+    # nt, nx, nchains, mode, m, mu, gauge width (None = uniform [-pi,pi))
+    (32, 32, 1, tb.MODE_REF_COMPAT, 100.0, 0.1, None),   # the shipped parameter file regime
+    (16, 16, 8, tb.MODE_ADJOINT, 1.0, 0.0, None),
+    (32, 32, 4, tb.MODE_ADJOINT, 0.1, 0.0, None),
+    (32, 32, 3, tb.MODE_ADJOINT, 0.1, 0.1, None),
+    (64, 64, 32, tb.MODE_ADJOINT, 0.5, 0.0, None),
+    (16, 32, 33, tb.MODE_ADJOINT, 0.3, 0.05, 0.5),
+]
+
+
+@pytest.mark.parametrize("nt,nx,nchains,mode,m,mu,width", CG_CASES)
+def test_T4_cg_matches_oracle(oracle, nt, nx, nchains, mode, m, mu, width):
+    rng = np.random.default_rng(nt + nx + nchains)
+    A = random_gauge(rng, nchains, nt, nx) if width is None else smooth_gauge(rng, nchains, nt, nx, width)
+    xi = random_vector(rng, nchains, nt, nx)
+    with tb.Context(nt, nx, nchains, mode, m=m, mu=mu) as ctx:
+        ctx.set_gauge(A)
+        b = ctx.fm_conjugate_mul(xi)  # as random_pseudofermion does (hmc.c:418-436)
+        for rows, chunk in ((0, 0), (2, 5)):
+            ctx.set_tuning(rows_per_thread=rows, iters_per_launch=chunk)
+            x, info = ctx.fmdm_invert_cg(b)
+            for c in range(nchains):
+                xo, st, it, rr = oracle.fmdm_invert_cg(b[c], A[c], m, mu, mode)
+                assert info.status[c] == st == tb.CG_CONVERGED
+                assert abs(int(info.iters[c]) - it) <= 1, (c, info.iters[c], it)
+                assert_close(x[c], xo, CG_SOL_TOL, f"chain {c}")
+                assert info.rr[c] < 1e-30
+
+
+def test_T4_per_chain_counts_equal_single_chain_counts(oracle):
+    """Chains with different masses converge at different iterations inside one batch; each chain's count
+    equals (+-1) what the oracle needs for that chain alone.  Sources are pseudofermions b = M~ xi, as in
+    random_pseudofermion (hmc.c:418-436)."""
+    rng = np.random.default_rng(3)
+    nt = nx = 32
+    masses = np.array([2.0, 0.5, 0.2, 1.0, 0.1, 5.0])
+    n = len(masses)
+    A = random_gauge(rng, n, nt, nx)
+    xi = random_vector(rng, n, nt, nx)
+    with tb.Context(nt, nx, n, tb.MODE_ADJOINT) as ctx:
+        ctx.set_params(masses, 0.0)
+        ctx.set_gauge(A)
+        b = ctx.fm_conjugate_mul(xi)
+        x, info = ctx.fmdm_invert_cg(b)
+    its = []
+    for c in range(n):
+        xo, st, it, rr = oracle.fmdm_invert_cg(b[c], A[c], masses[c], 0.0, tb.MODE_ADJOINT)
+        its.append(it)
+        assert abs(int(info.iters[c]) - it) <= 1, (c, info.iters[c], it)
+        assert_close(x[c], xo, CG_SOL_TOL, f"chain {c}")
+    assert len(set(its)) > 2  # the batch really had ragged convergence
+
+
+def test_T5_zero_source_and_divergence(oracle):
+    rng = np.random.default_rng(9)
+    nt = nx = 16
+    A = random_gauge(rng, 3, nt, nx)
+    b = random_vector(rng, 3, nt, nx)
+    b[1] = 0.0  # hmc.c:359-361: returns x = 0 without iterating
+    with tb.Context(nt, nx, 3, tb.MODE_ADJOINT, m=0.5) as ctx:
+        ctx.set_gauge(A)
+        x, info = ctx.fmdm_invert_cg(b)
+        assert info.status.tolist() == [tb.CG_CONVERGED, tb.CG_ZERO_SOURCE, tb.CG_CONVERGED]
+        assert info.iters[1] == 0 and np.all(x[1] == 0)
+    # REF_COMPAT at light mass: M.M is not positive definite -> the reference bails (hmc.c:383-388)
+    with tb.Context(nt, nx, 3, tb.MODE_REF_COMPAT, m=0.1) as ctx:
+        ctx.set_gauge(A)
+        b[1] = b[0]
+        x, info = ctx.fmdm_invert_cg(b)
+        for c in range(3):
+            xo, st, it, rr = oracle.fmdm_invert_cg(b[c], A[c], 0.1, 0.0, tb.MODE_REF_COMPAT)
+            assert st == tb.CG_DIVERGED
+            assert info.status[c] == tb.CG_DIVERGED
+            assert abs(int(info.iters[c]) - it) <= 2
+
+
+def test_max_iter_is_reported():
+    rng = np.random.default_rng(2)
+    A = random_gauge(rng, 2, 16, 16)
+    b = random_vector(rng, 2, 16, 16)
+    with tb.Context(16, 16, 2, tb.MODE_ADJOINT, m=0.05) as ctx:
+        ctx.set_gauge(A)
+        ctx.set_cg(1e-30, 20)
+        x, info = ctx.fmdm_invert_cg(b)
+        assert info.status.tolist() == [tb.CG_MAXITER] * 2
+        assert info.iters.tolist() == [19, 19]  # k = 1 .. max_iter-1, hmc.c:364
+
+
+def test_fm_invert_cg_inverts_M(oracle):
+    """fm_invert_cg (hmc.c:408-414): M x = v to solver accuracy in ADJOINT mode."""
+    rng = np.random.default_rng(4)
+    nt, nx, n = 32, 32, 4
+    A = random_gauge(rng, n, nt, nx)
+    v = random_vector(rng, n, nt, nx)
+    with tb.Context(nt, nx, n, tb.MODE_ADJOINT, m=0.4, mu=0.1) as ctx:
+        ctx.set_gauge(A)
+        x, info = ctx.fm_invert_cg(v)
+        assert np.all(info.status == tb.CG_CONVERGED)
+        assert_close(ctx.fm_mul(x), v, 1e-11, "M M^-1 v")
+    xo, st, it, rr = oracle.fm_invert_cg(v[0], A[0], 0.4, 0.1, tb.MODE_ADJOINT)
+    assert_close(x[0], xo, CG_SOL_TOL, "vs oracle")
+
+
+def test_runs_are_deterministic():
+    rng = np.random.default_rng(8)
+    A = random_gauge(rng, 16, 32, 32)
+    b = random_vector(rng, 16, 32, 32)
+    with tb.Context(32, 32, 16, tb.MODE_ADJOINT, m=0.2) as ctx:
+        ctx.set_gauge(A)
+        x1, i1 = ctx.fmdm_invert_cg(b)
+        x2, i2 = ctx.fmdm_invert_cg(b)
+    assert np.array_equal(x1, x2) and np.array_equal(i1.iters, i2.iters)

@@ -1,0 +1,195 @@
+"""Host-side mirror of the reference interface for the hot path (hmc.c:123-414), batched over chains.
+
+``Context`` owns one tb_ctx.  Methods carry the reference's names and argument meaning:
+
+    fm_mul(v)            hmc.c:123   M v
+    fm_conjugate_mul(v)  hmc.c:188   M~ v  (== M v in REF_COMPAT, M^dagger v in ADJOINT)
+    fmdm_invert_cg(b)    hmc.c:341   (M~ M)^-1 b by CG from x0 = 0, absolute stop ||r||^2 < 1e-30
+    fm_invert_cg(v)      hmc.c:408   (M~ M)^-1 M~ v
+
+Host arrays: vectors complex128 (nchains, NT, NX) (a single (NT, NX) array is accepted for nchains == 1),
+gauge fields float64 (nchains, NT, NX, 2).  The ``*_dev`` methods take raw device pointers (e.g.
+``torch.Tensor.data_ptr()``) in the library's device layout and move no data across PCIe.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from .lib import check, load_library
+
+MODE_REF_COMPAT, MODE_ADJOINT = 0, 1
+OP_M, OP_MDAG, OP_MCONJ, OP_MDM = 0, 1, 2, 3
+CG_CONVERGED, CG_MAXITER, CG_DIVERGED, CG_ZERO_SOURCE = 0, 1, 2, 3
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+class CGInfo:
+    """Per-chain outcome of a batched solve."""
+
+    def __init__(self, status, iters, rr):
+        self.status, self.iters, self.rr = status, iters, rr
+
+    def __repr__(self):
+        return f"CGInfo(status={self.status.tolist()}, iters={self.iters.tolist()})"
+
+
+class Context:
+    def __init__(self, nt, nx, nchains=1, mode=MODE_ADJOINT, device=0, m=1.0, mu=0.0, stream=None):
+        self.lib = load_library()
+        self.nt, self.nx, self.nchains, self.mode, self.device = nt, nx, nchains, mode, device
+        h = C.c_void_p()
+        check(self.lib.tb_create(C.byref(h), nt, nx, nchains, mode, device), "tb_create")
+        self._h = h
+        if stream is not None:
+            self.set_stream(stream)
+        self.set_params(m, mu)
+
+    # -- life cycle ----------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.tb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- configuration ---------------------------------------------------------------------------------
+    def set_stream(self, stream_ptr: int):
+        check(self.lib.tb_set_stream(self._h, C.c_void_p(stream_ptr)), "tb_set_stream")
+
+    def synchronize(self):
+        check(self.lib.tb_synchronize(self._h), "tb_synchronize")
+
+    def set_params(self, m, mu):
+        m = np.atleast_1d(np.asarray(m, dtype=np.float64))
+        mu = np.atleast_1d(np.asarray(mu, dtype=np.float64))
+        n = max(m.size, mu.size)
+        if n > 1:
+            m = np.ascontiguousarray(np.broadcast_to(m, (n,)))
+            mu = np.ascontiguousarray(np.broadcast_to(mu, (n,)))
+        check(self.lib.tb_set_params(self._h, m.ctypes.data_as(_dp), mu.ctypes.data_as(_dp), n), "tb_set_params")
+
+    def set_cg(self, accuracy=1e-30, max_iter=100000):
+        check(self.lib.tb_set_cg(self._h, accuracy, max_iter), "tb_set_cg")
+
+    def set_tuning(self, rows_per_thread=0, iters_per_launch=0, solver=0):
+        check(self.lib.tb_set_tuning(self._h, rows_per_thread, iters_per_launch, solver), "tb_set_tuning")
+
+    # -- host-buffer path (reference-facing) -----------------------------------------------------------------
+    def _vec(self, v):
+        v = np.ascontiguousarray(v, dtype=np.complex128)
+        if v.ndim == 2:
+            v = v[None]
+        assert v.shape == (self.nchains, self.nt, self.nx), (v.shape, (self.nchains, self.nt, self.nx))
+        return v
+
+    def set_gauge(self, A):
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        if A.ndim == 3:
+            A = A[None]
+        assert A.shape == (self.nchains, self.nt, self.nx, 2), A.shape
+        check(self.lib.tb_set_gauge(self._h, A.ctypes.data), "tb_set_gauge")
+
+    def apply(self, op, v):
+        squeeze = np.ndim(v) == 2
+        v = self._vec(v)
+        out = np.empty_like(v)
+        check(self.lib.tb_apply(self._h, op, v.ctypes.data, out.ctypes.data), "tb_apply")
+        return out[0] if squeeze else out
+
+    def fm_mul(self, v):
+        return self.apply(OP_M, v)
+
+    def fm_conjugate_mul(self, v):
+        return self.apply(OP_MCONJ, v)
+
+    def fm_dagger_mul(self, v):
+        return self.apply(OP_MDAG, v)
+
+    def fmdm_mul(self, v):
+        return self.apply(OP_MDM, v)
+
+    def _solve(self, fn, name, b):
+        squeeze = np.ndim(b) == 2
+        b = self._vec(b)
+        x = np.empty_like(b)
+        st = np.empty(self.nchains, dtype=np.int32)
+        it = np.empty(self.nchains, dtype=np.int32)
+        rr = np.empty(self.nchains, dtype=np.float64)
+        check(fn(self._h, b.ctypes.data, x.ctypes.data, st.ctypes.data_as(_ip), it.ctypes.data_as(_ip),
+                 rr.ctypes.data_as(_dp)), name)
+        return (x[0] if squeeze else x), CGInfo(st, it, rr)
+
+    def fmdm_invert_cg(self, b):
+        return self._solve(self.lib.tb_cg, "tb_cg", b)
+
+    def fm_invert_cg(self, v):
+        return self._solve(self.lib.tb_invert, "tb_invert", v)
+
+    # raw host pointers (e.g. pinned torch tensors) — used by bench.py's e2e leg
+    def cg_host_ptr(self, b_ptr: int, x_ptr: int):
+        check(self.lib.tb_cg(self._h, C.c_void_p(b_ptr), C.c_void_p(x_ptr), None, None, None), "tb_cg")
+
+    def set_gauge_host_ptr(self, a_ptr: int):
+        check(self.lib.tb_set_gauge(self._h, C.c_void_p(a_ptr)), "tb_set_gauge")
+
+    # -- device-resident path ------------------------------------------------------------------------
+    @property
+    def vec_doubles(self):
+        return int(self.lib.tb_vec_doubles(self._h))
+
+    def pack_dev(self, d_canonical: int, d_vec: int):
+        check(self.lib.tb_pack_dev(self._h, C.c_void_p(d_canonical), C.c_void_p(d_vec)), "tb_pack_dev")
+
+    def unpack_dev(self, d_vec: int, d_canonical: int):
+        check(self.lib.tb_unpack_dev(self._h, C.c_void_p(d_vec), C.c_void_p(d_canonical)), "tb_unpack_dev")
+
+    def set_gauge_dev(self, d_A_canonical: int):
+        check(self.lib.tb_set_gauge_dev(self._h, C.c_void_p(d_A_canonical)), "tb_set_gauge_dev")
+
+    def apply_dev(self, op, d_in: int, d_out: int):
+        check(self.lib.tb_apply_dev(self._h, op, C.c_void_p(d_in), C.c_void_p(d_out)), "tb_apply_dev")
+
+    def cg_dev(self, d_b: int, d_x: int):
+        check(self.lib.tb_cg_dev(self._h, C.c_void_p(d_b), C.c_void_p(d_x)), "tb_cg_dev")
+
+    def invert_dev(self, d_v: int, d_x: int):
+        check(self.lib.tb_invert_dev(self._h, C.c_void_p(d_v), C.c_void_p(d_x)), "tb_invert_dev")
+
+    def cg_result(self):
+        st = np.empty(self.nchains, dtype=np.int32)
+        it = np.empty(self.nchains, dtype=np.int32)
+        rr = np.empty(self.nchains, dtype=np.float64)
+        check(self.lib.tb_cg_result(self._h, st.ctypes.data_as(_ip), it.ctypes.data_as(_ip),
+                                    rr.ctypes.data_as(_dp)), "tb_cg_result")
+        return CGInfo(st, it, rr)
+
+    def re_dot_dev(self, d_a: int, d_b: int):
+        out = np.empty(self.nchains, dtype=np.float64)
+        check(self.lib.tb_re_dot_dev(self._h, C.c_void_p(d_a), C.c_void_p(d_b), out.ctypes.data_as(_dp)),
+              "tb_re_dot_dev")
+        return out
+
+    @property
+    def launch_count(self):
+        return int(self.lib.tb_launch_count(self._h))
+
+    def reset_launch_count(self):
+        self.lib.tb_reset_launch_count(self._h)
+
+    @property
+    def last_solve_ms(self):
+        return float(self.lib.tb_last_solve_ms(self._h))

@@ -1,0 +1,187 @@
+/* hmc_interpose.c — libthirring_hmc.so: the reference's family-A symbols (hmc.c:105-414) implemented on the
+ * B200 through the handle C-ABI.  Plain C host code; see include/thirring_hmc_abi.h for the contract. */
+#define _GNU_SOURCE
+#include <complex.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/thirring_b200.h"
+#include "../../include/thirring_hmc_abi.h"
+
+static struct {
+  tb_ctx *ctx;
+  int nt, nx, mode, device;
+  double *A_flat;      /* last uploaded angles [t][x][2] */
+  double *A_tmp;
+  double *vin, *vout;  /* contiguous staging [t][x] complex */
+  int have_A;
+  int mu_frozen;
+  double mu_at_first_call;
+  double *p_m, *p_mu;  /* the driver's globals, hmc.c:38,40 */
+  long cg_calls, apply_calls;
+} S;
+
+static void die(const char *what) {
+  fprintf(stderr, "libthirring_hmc: %s: %s\n", what, tb_last_error());
+  abort(); /* a void ABI has no channel to report device errors */
+}
+
+int tb_hmc_configure(int nt, int nx, int mode, int device) {
+  if (S.ctx) tb_hmc_shutdown();
+  memset(&S, 0, sizeof(S));
+  S.nt = nt; S.nx = nx; S.mode = mode; S.device = device;
+  if (tb_create(&S.ctx, nt, nx, 1, mode, device) != TB_OK) die("tb_create");
+  size_t v = (size_t)nt * nx;
+  S.A_flat = malloc(v * 2 * sizeof(double));
+  S.A_tmp = malloc(v * 2 * sizeof(double));
+  S.vin = malloc(v * 2 * sizeof(double));
+  S.vout = malloc(v * 2 * sizeof(double));
+  return 0;
+}
+
+void tb_hmc_shutdown(void) {
+  if (S.ctx) tb_destroy(S.ctx);
+  free(S.A_flat); free(S.A_tmp); free(S.vin); free(S.vout);
+  memset(&S, 0, sizeof(S));
+}
+
+long tb_hmc_cg_calls(void) { return S.cg_calls; }
+long tb_hmc_apply_calls(void) { return S.apply_calls; }
+
+static void lazy_init(void) {
+  if (S.ctx) return;
+  const char *nt = getenv("THIRRING_NT"), *nx = getenv("THIRRING_NX");
+  const char *mode = getenv("THIRRING_MODE"), *dev = getenv("THIRRING_DEVICE");
+  if (!nt || !nx) {
+    fprintf(stderr, "libthirring_hmc: lattice size unknown: call tb_hmc_configure() or set THIRRING_NT/THIRRING_NX\n");
+    abort();
+  }
+  tb_hmc_configure(atoi(nt), atoi(nx), (mode && !strcmp(mode, "adjoint")) ? TB_MODE_ADJOINT : TB_MODE_REF_COMPAT,
+                   dev ? atoi(dev) : 0);
+}
+
+/* m is read at every call, exp(+-mu) is frozen at the first one (hmc.c:124-130) */
+static void sync_params(void) {
+  if (!S.p_m) {
+    S.p_m = (double *)dlsym(RTLD_DEFAULT, "m");
+    S.p_mu = (double *)dlsym(RTLD_DEFAULT, "mu");
+    if (!S.p_m || !S.p_mu) {
+      fprintf(stderr, "libthirring_hmc: the driver's globals `m` and `mu` (hmc.c:38,40) are not visible\n");
+      abort();
+    }
+  }
+  if (!S.mu_frozen) { S.mu_at_first_call = *S.p_mu; S.mu_frozen = 1; }
+  double m = *S.p_m, mu = S.mu_at_first_call;
+  if (tb_set_params(S.ctx, &m, &mu, 1) != TB_OK) die("tb_set_params");
+}
+
+static void sync_gauge(double ***A) {
+  double *d = S.A_tmp;
+  for (int t = 0; t < S.nt; t++) for (int x = 0; x < S.nx; x++) {
+    *d++ = A[t][x][0];
+    *d++ = A[t][x][1];
+  }
+  size_t bytes = (size_t)S.nt * S.nx * 2 * sizeof(double);
+  if (S.have_A && memcmp(S.A_tmp, S.A_flat, bytes) == 0) return; /* links already on the device */
+  memcpy(S.A_flat, S.A_tmp, bytes);
+  if (tb_set_gauge(S.ctx, S.A_flat) != TB_OK) die("tb_set_gauge");
+  S.have_A = 1;
+}
+
+static const double *gather(_Complex double **v) {
+  /* rows handed out by our alloc_vector are contiguous: no copy */
+  if (v[S.nt - 1] == v[0] + (size_t)(S.nt - 1) * S.nx) return (const double *)v[0];
+  for (int t = 0; t < S.nt; t++) memcpy(S.vin + (size_t)t * S.nx * 2, v[t], (size_t)S.nx * 2 * sizeof(double));
+  return S.vin;
+}
+
+static double *out_buffer(_Complex double **v) {
+  if (v[S.nt - 1] == v[0] + (size_t)(S.nt - 1) * S.nx) return (double *)v[0];
+  return S.vout;
+}
+
+static void scatter(_Complex double **v, const double *buf) {
+  if ((const double *)v[0] == buf) return;
+  for (int t = 0; t < S.nt; t++) memcpy(v[t], buf + (size_t)t * S.nx * 2, (size_t)S.nx * 2 * sizeof(double));
+}
+
+static void apply(int op, _Complex double **v_in, _Complex double **v_out, double ***A) {
+  lazy_init();
+  sync_params();
+  sync_gauge(A);
+  const double *in = gather(v_in);
+  double *out = out_buffer(v_out);
+  if (tb_apply(S.ctx, op, in, out) != TB_OK) die("tb_apply");
+  scatter(v_out, out);
+  S.apply_calls++;
+}
+
+_Complex double **alloc_vector(void) {
+  lazy_init();
+  size_t table = ((size_t)S.nt * sizeof(_Complex double *) + 63) & ~(size_t)63;
+  char *blk = malloc(table + (size_t)S.nt * S.nx * sizeof(_Complex double));
+  _Complex double **v = (_Complex double **)blk;
+  for (int t = 0; t < S.nt; t++) v[t] = (_Complex double *)(blk + table) + (size_t)t * S.nx;
+  return v;
+}
+
+void free_vector(_Complex double **v) { free(v); }
+
+void fm_mul(_Complex double **v_in, _Complex double **v_out, double ***A) { apply(TB_OP_M, v_in, v_out, A); }
+
+void fm_conjugate_mul(_Complex double **v_in, _Complex double **v_out, double ***A) {
+  apply(TB_OP_MCONJ, v_in, v_out, A);
+}
+
+void fmdm_mul(_Complex double **v_in, _Complex double **v_out, double ***A) { apply(TB_OP_MDM, v_in, v_out, A); }
+
+static void solve(int with_conj, _Complex double **v_in, _Complex double **v_out, double ***A) {
+  lazy_init();
+  sync_params();
+  sync_gauge(A);
+  const double *in = gather(v_in);
+  double *out = out_buffer(v_out);
+  int status = 0, iters = 0;
+  double rr = 0;
+  int rc = with_conj ? tb_invert(S.ctx, in, out, &status, &iters, &rr) : tb_cg(S.ctx, in, out, &status, &iters, &rr);
+  if (rc != TB_OK) die("tb_cg");
+  S.cg_calls++;
+  if (status == TB_CG_DIVERGED) { /* hmc.c:383-388 */
+    printf("Cannot invert fermion matrix\n");
+    exit(1);
+  }
+  scatter(v_out, out);
+}
+
+void fmdm_invert_cg(_Complex double **v_in, _Complex double **v_out, double ***A) { solve(0, v_in, v_out, A); }
+
+void fm_invert_cg(_Complex double **v_in, _Complex double **v_out, double ***A) { solve(1, v_in, v_out, A); }
+
+void test_conjugate(double ***A) {
+  /* hmc.c:759-789; the random vector must come from the driver's own stochastic_vector so the
+   * Mersenne stream stays in step with an un-interposed run */
+  static void (*stoch)(_Complex double **) = NULL;
+  lazy_init();
+  if (!stoch) stoch = (void (*)(_Complex double **))dlsym(RTLD_DEFAULT, "stochastic_vector");
+  if (!stoch) { fprintf(stderr, "libthirring_hmc: stochastic_vector (hmc.c:439) not visible\n"); abort(); }
+  _Complex double **c = alloc_vector(), **mc = alloc_vector(), **mdc = alloc_vector();
+  stoch(c);
+  fm_mul(c, mc, A);
+  fm_conjugate_mul(c, mdc, A);
+  _Complex double cmdc = 0, cmc = 0;
+  for (int t = 0; t < S.nt; t++) for (int x = 0; x < S.nx; x++) {
+    cmdc += conj(c[t][x]) * mdc[t][x];
+    cmc += conj(mc[t][x]) * c[t][x];
+  }
+  _Complex double cdiff = (S.mode == TB_MODE_ADJOINT) ? cmdc - cmc : cmdc - conj(cmc);
+  double diff = creal(cdiff) * creal(cdiff) + cimag(cdiff) * cimag(cdiff);
+  if (diff > 0.001) {
+    printf("ERROR fm_conjugate_mul is not the conjugate of fm_mul\n");
+    printf("Difference = %g\n", diff);
+    exit(1);
+  }
+  free_vector(c); free_vector(mc); free_vector(mdc);
+}

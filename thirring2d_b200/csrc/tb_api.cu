@@ -1,0 +1,412 @@
+// tb_api.cu — the C-ABI of include/thirring_b200.h: context life cycle, host-buffer entry points and the
+// dispatch of the batched CG.  No CPU fallback: every entry point runs CUDA kernels or fails.
+#include <cmath>
+
+#include "tb_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void tb_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char *tb_last_error(void) { return g_err; }
+
+extern "C" int tb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+  return n;
+}
+
+template <typename T>
+static int dev_alloc(T **p, size_t n) {
+  cudaError_t e = cudaMalloc((void **)p, n * sizeof(T));
+  if (e != cudaSuccess) {
+    tb_set_error("cudaMalloc(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    return TB_ENOMEM;
+  }
+  return TB_OK;
+}
+
+static void invalidate_graph(tb_ctx *ctx) {
+  if (ctx->cg_graph) {
+    cudaGraphExecDestroy(ctx->cg_graph);
+    ctx->cg_graph = nullptr;
+  }
+}
+
+static int alloc_cg_state(tb_ctx *ctx) {
+  // sized for the finest geometry any tuning can choose: tt = 1
+  const TbGeom &g = ctx->g;
+  const size_t cp = g.Cpad;
+  const size_t max_slots = (size_t)g.nxtiles * ctx->nt;
+  TbCgState &s = ctx->cg;
+  double *dbl = nullptr;
+  TB_CHECK(dev_alloc(&dbl, 7 * cp));
+  s.rr_old = dbl;
+  s.rr_init = dbl + cp;
+  s.rr = dbl + 2 * cp;
+  s.pq = dbl + 3 * cp;
+  s.alpha = dbl + 4 * cp;
+  s.beta = dbl + 5 * cp;
+  s.dot = dbl + 6 * cp;
+  int *ints = nullptr;
+  TB_CHECK(dev_alloc(&ints, 3 * cp + g.nctiles + 1));
+  s.active = ints;
+  s.status = ints + cp;
+  s.iters = ints + 2 * cp;
+  s.tile_active = ints + 3 * cp;
+  s.n_active = ints + 3 * cp + g.nctiles;
+  TB_CHECK(dev_alloc(&s.partial, max_slots * cp));
+  TB_CHECK(dev_alloc(&s.ticket, (size_t)g.nctiles));
+  TB_CUDA(cudaMemset(dbl, 0, 7 * cp * sizeof(double)));
+  TB_CUDA(cudaMemset(ints, 0, (3 * cp + g.nctiles + 1) * sizeof(int)));
+  TB_CUDA(cudaMemset(s.ticket, 0, g.nctiles * sizeof(unsigned int)));
+  s.accuracy = 1e-30;   // CG_ACCURACY, hmc.c:34
+  s.max_iter = 100000;  // CG_MAX_ITER, hmc.c:35
+  return TB_OK;
+}
+
+extern "C" int tb_create(tb_ctx **out, int nt, int nx, int nchains, int mode, int device) {
+  if (!out || nt < 2 || nx < 2 || nchains < 1 || (mode != TB_MODE_REF_COMPAT && mode != TB_MODE_ADJOINT)) {
+    tb_set_error("tb_create: invalid arguments (nt=%d nx=%d nchains=%d mode=%d)", nt, nx, nchains, mode);
+    return TB_EINVAL;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    tb_set_error("tb_create: no CUDA device available (this library has no CPU path)");
+    return TB_ENODEVICE;
+  }
+  if (device < 0 || device >= ndev) {
+    tb_set_error("tb_create: device %d out of range (have %d)", device, ndev);
+    return TB_EINVAL;
+  }
+  TB_CUDA(cudaSetDevice(device));
+  tb_ctx *ctx = (tb_ctx *)calloc(1, sizeof(tb_ctx));
+  if (!ctx) return TB_ENOMEM;
+  ctx->nt = nt;
+  ctx->nx = nx;
+  ctx->C = nchains;
+  ctx->mode = mode;
+  ctx->device = device;
+  ctx->V = (size_t)nt * nx;
+  ctx->nsite = ctx->V * nchains;
+  const char *e;
+  ctx->tune_tt = (e = getenv("TB_ROWS_PER_THREAD")) ? atoi(e) : 0;
+  ctx->tune_chunk = (e = getenv("TB_ITERS_PER_LAUNCH")) ? atoi(e) : 0;
+  ctx->tune_solver = (e = getenv("TB_SOLVER")) ? atoi(e) : 0;
+  tb_choose_geom(ctx);
+  int rc = TB_OK;
+  cudaError_t ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (ce != cudaSuccess) {
+    tb_set_error("cudaStreamCreate: %s", cudaGetErrorString(ce));
+    free(ctx);
+    return TB_ECUDA;
+  }
+  ctx->own_stream = true;
+  const size_t n = ctx->nsite;
+  const size_t cp = ctx->g.Cpad;
+#define A_(ptr, cnt)                              \
+  if (rc == TB_OK) rc = dev_alloc(&(ptr), (cnt));
+  A_(ctx->d_mass, cp) A_(ctx->d_emu, cp) A_(ctx->d_emmu, cp)
+  A_(ctx->W0, n) A_(ctx->W1, n) A_(ctx->Adev, n)
+  A_(ctx->r, n) A_(ctx->p, n) A_(ctx->Mp, n) A_(ctx->q, n) A_(ctx->xw, n) A_(ctx->tmp, n)
+  A_(ctx->vin, n) A_(ctx->vout, n)
+  A_(ctx->stage, 2 * n)
+#undef A_
+  if (rc == TB_OK) rc = alloc_cg_state(ctx);
+  if (rc == TB_OK) {
+    ctx->h_mass = (double *)malloc(cp * sizeof(double));
+    ctx->h_mu = (double *)malloc(cp * sizeof(double));
+    if (cudaHostAlloc((void **)&ctx->h_flag, 4 * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&ctx->h_status, cp * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&ctx->h_iters, cp * sizeof(int), cudaHostAllocDefault) != cudaSuccess ||
+        cudaHostAlloc((void **)&ctx->h_rr, cp * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+      tb_set_error("cudaHostAlloc failed");
+      rc = TB_ENOMEM;
+    }
+  }
+  if (rc == TB_OK) {
+    cudaEventCreate(&ctx->ev0);
+    cudaEventCreate(&ctx->ev1);
+    cudaEventCreateWithFlags(&ctx->ev_flag[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ctx->ev_flag[1], cudaEventDisableTiming);
+    const double one = 1.0, zero = 0.0;
+    rc = tb_set_params(ctx, &one, &zero, 1);
+  }
+  if (rc != TB_OK) {
+    tb_destroy(ctx);
+    return rc;
+  }
+  *out = ctx;
+  return TB_OK;
+}
+
+extern "C" int tb_destroy(tb_ctx *ctx) {
+  if (!ctx) return TB_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  invalidate_graph(ctx);
+  void *dev[] = {ctx->d_mass, ctx->d_emu, ctx->d_emmu, ctx->W0, ctx->W1, ctx->Adev, ctx->r, ctx->p, ctx->Mp,
+                 ctx->q, ctx->xw, ctx->tmp, ctx->vin, ctx->vout, ctx->stage, ctx->cg.rr_old, ctx->cg.active,
+                 ctx->cg.partial, ctx->cg.ticket};
+  for (void *p : dev)
+    if (p) cudaFree(p);
+  if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+  if (ctx->h_status) cudaFreeHost(ctx->h_status);
+  if (ctx->h_iters) cudaFreeHost(ctx->h_iters);
+  if (ctx->h_rr) cudaFreeHost(ctx->h_rr);
+  free(ctx->h_mass);
+  free(ctx->h_mu);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev_flag[0]) cudaEventDestroy(ctx->ev_flag[0]);
+  if (ctx->ev_flag[1]) cudaEventDestroy(ctx->ev_flag[1]);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  free(ctx);
+  return TB_OK;
+}
+
+extern "C" int tb_set_stream(tb_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return TB_OK;
+}
+
+extern "C" int tb_synchronize(tb_ctx *ctx) {
+  if (!ctx) return TB_EINVAL;
+  TB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TB_OK;
+}
+
+extern "C" int tb_set_params(tb_ctx *ctx, const double *m, const double *mu, int n) {
+  if (!ctx || !m || !mu || (n != 1 && n != ctx->C)) {
+    tb_set_error("tb_set_params: n must be 1 or nchains");
+    return TB_EINVAL;
+  }
+  TB_CUDA(cudaSetDevice(ctx->device));
+  const int cp = ctx->g.Cpad;
+  double *buf = (double *)malloc(3 * (size_t)cp * sizeof(double));
+  for (int c = 0; c < cp; c++) {
+    const int k = (n == 1 || c >= ctx->C) ? 0 : c;
+    ctx->h_mass[c] = m[k];
+    ctx->h_mu[c] = mu[k];
+    buf[c] = m[k];
+    buf[cp + c] = exp(mu[k]);       // hmc.c:127
+    buf[2 * cp + c] = exp(-mu[k]);  // hmc.c:128
+  }
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_mass, buf, cp * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_emu, buf + cp, cp * sizeof(double), cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(ctx->d_emmu, buf + 2 * cp, cp * sizeof(double), cudaMemcpyHostToDevice);
+  free(buf);
+  TB_CUDA(e);
+  return TB_OK;
+}
+
+extern "C" int tb_set_cg(tb_ctx *ctx, double accuracy, int max_iter) {
+  if (!ctx || !(accuracy >= 0) || max_iter < 2) {
+    tb_set_error("tb_set_cg: invalid arguments");
+    return TB_EINVAL;
+  }
+  ctx->cg.accuracy = accuracy;
+  ctx->cg.max_iter = max_iter;
+  invalidate_graph(ctx);
+  return TB_OK;
+}
+
+extern "C" int tb_set_tuning(tb_ctx *ctx, int rows_per_thread, int iters_per_launch, int solver) {
+  if (!ctx) return TB_EINVAL;
+  TB_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->tune_tt = rows_per_thread;
+  ctx->tune_chunk = iters_per_launch;
+  ctx->tune_solver = solver;
+  tb_choose_geom(ctx);
+  invalidate_graph(ctx);
+  return TB_OK;
+}
+
+extern "C" size_t tb_vec_doubles(const tb_ctx *ctx) { return ctx ? 2 * ctx->nsite : 0; }
+
+extern "C" long long tb_launch_count(const tb_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int tb_reset_launch_count(tb_ctx *ctx) {
+  if (!ctx) return TB_EINVAL;
+  ctx->launches = 0;
+  return TB_OK;
+}
+extern "C" double tb_last_solve_ms(const tb_ctx *ctx) { return ctx ? ctx->last_solve_ms : 0.0; }
+
+// ---- device-resident entry points -----------------------------------------------------------------------
+
+extern "C" int tb_pack_dev(tb_ctx *ctx, const double *d_canonical, double *d_vec) {
+  if (!ctx || !d_canonical || !d_vec) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  return tb_launch_pack(ctx, d_canonical, (double2 *)d_vec);
+}
+
+extern "C" int tb_unpack_dev(tb_ctx *ctx, const double *d_vec, double *d_canonical) {
+  if (!ctx || !d_canonical || !d_vec) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  return tb_launch_unpack(ctx, (const double2 *)d_vec, d_canonical);
+}
+
+extern "C" int tb_set_gauge_dev(tb_ctx *ctx, const double *d_A_canonical) {
+  if (!ctx || !d_A_canonical) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(tb_launch_pack(ctx, d_A_canonical, ctx->Adev));
+  TB_CHECK(tb_launch_links(ctx, (const double *)ctx->Adev));
+  ctx->have_gauge = true;
+  return TB_OK;
+}
+
+static int need_gauge(tb_ctx *ctx) {
+  if (!ctx->have_gauge) {
+    tb_set_error("no gauge field set (call tb_set_gauge / tb_set_gauge_dev first)");
+    return TB_EINVAL;
+  }
+  return TB_OK;
+}
+
+extern "C" int tb_apply_dev(tb_ctx *ctx, int op, const double *d_in, double *d_out) {
+  if (!ctx || !d_in || !d_out || d_in == d_out) {
+    tb_set_error("tb_apply_dev: invalid arguments (in-place apply is not supported)");
+    return TB_EINVAL;
+  }
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(need_gauge(ctx));
+  const double2 *in = (const double2 *)d_in;
+  double2 *out = (double2 *)d_out;
+  switch (op) {
+    case TB_OP_M: return tb_launch_dslash(ctx, false, in, out, false);
+    case TB_OP_MDAG: return tb_launch_dslash(ctx, true, in, out, false);
+    case TB_OP_MCONJ: return tb_launch_dslash(ctx, tb_conj_is_dagger(ctx), in, out, false);
+    case TB_OP_MDM:
+      TB_CHECK(tb_launch_dslash(ctx, false, in, ctx->tmp, false));
+      return tb_launch_dslash(ctx, tb_conj_is_dagger(ctx), ctx->tmp, out, false);
+    default: tb_set_error("tb_apply_dev: unknown op %d", op); return TB_EINVAL;
+  }
+}
+
+static int run_cg(tb_ctx *ctx, const double2 *b, double2 *x) {
+  TB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  TB_CHECK(tb_run_cg_stream(ctx, b, x));
+  TB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  TB_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  TB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_solve_ms = ms;
+  return TB_OK;
+}
+
+extern "C" int tb_cg_dev(tb_ctx *ctx, const double *d_b, double *d_x) {
+  if (!ctx || !d_b || !d_x) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(need_gauge(ctx));
+  return run_cg(ctx, (const double2 *)d_b, (double2 *)d_x);
+}
+
+extern "C" int tb_invert_dev(tb_ctx *ctx, const double *d_v, double *d_x) {
+  if (!ctx || !d_v || !d_x) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(need_gauge(ctx));
+  // fm_invert_cg, hmc.c:408-414
+  TB_CHECK(tb_launch_dslash(ctx, tb_conj_is_dagger(ctx), (const double2 *)d_v, ctx->tmp, false));
+  return run_cg(ctx, ctx->tmp, (double2 *)d_x);
+}
+
+extern "C" int tb_cg_result(tb_ctx *ctx, int *status, int *iters, double *rr) {
+  if (!ctx) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  const size_t c = ctx->C;
+  cudaStream_t st = ctx->stream;
+  TB_CUDA(cudaMemcpyAsync(ctx->h_status, ctx->cg.status, c * sizeof(int), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(ctx->h_iters, ctx->cg.iters, c * sizeof(int), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaMemcpyAsync(ctx->h_rr, ctx->cg.rr, c * sizeof(double), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  if (status) memcpy(status, ctx->h_status, c * sizeof(int));
+  if (iters) memcpy(iters, ctx->h_iters, c * sizeof(int));
+  if (rr) memcpy(rr, ctx->h_rr, c * sizeof(double));
+  return TB_OK;
+}
+
+extern "C" int tb_re_dot_dev(tb_ctx *ctx, const double *d_a, const double *d_b, double *out_host) {
+  if (!ctx || !d_a || !d_b || !out_host) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(tb_launch_dot(ctx, (const double2 *)d_a, (const double2 *)d_b, ctx->cg.dot));
+  TB_CUDA(cudaMemcpyAsync(ctx->h_rr, ctx->cg.dot, ctx->C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  TB_CUDA(cudaStreamSynchronize(ctx->stream));
+  memcpy(out_host, ctx->h_rr, ctx->C * sizeof(double));
+  return TB_OK;
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------------------
+
+static int upload_vec(tb_ctx *ctx, const double *host, double2 *d_vec) {
+  const size_t bytes = ctx->nsite * sizeof(double2);
+  if (ctx->C == 1) {
+    TB_CUDA(cudaMemcpyAsync(d_vec, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return TB_OK;
+  }
+  TB_CUDA(cudaMemcpyAsync(ctx->stage, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return tb_launch_pack(ctx, ctx->stage, d_vec);
+}
+
+static int download_vec(tb_ctx *ctx, const double2 *d_vec, double *host) {
+  const size_t bytes = ctx->nsite * sizeof(double2);
+  if (ctx->C == 1) {
+    TB_CUDA(cudaMemcpyAsync(host, d_vec, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    TB_CHECK(tb_launch_unpack(ctx, d_vec, ctx->stage));
+    TB_CUDA(cudaMemcpyAsync(host, ctx->stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  TB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TB_OK;
+}
+
+extern "C" int tb_set_gauge(tb_ctx *ctx, const double *A_host) {
+  if (!ctx || !A_host) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(upload_vec(ctx, A_host, ctx->Adev));
+  TB_CHECK(tb_launch_links(ctx, (const double *)ctx->Adev));
+  ctx->have_gauge = true;
+  return TB_OK;
+}
+
+extern "C" int tb_apply(tb_ctx *ctx, int op, const double *in_host, double *out_host) {
+  if (!ctx || !in_host || !out_host) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(need_gauge(ctx));
+  TB_CHECK(upload_vec(ctx, in_host, ctx->vin));
+  TB_CHECK(tb_apply_dev(ctx, op, (const double *)ctx->vin, (double *)ctx->vout));
+  return download_vec(ctx, ctx->vout, out_host);
+}
+
+extern "C" int tb_cg(tb_ctx *ctx, const double *b_host, double *x_host, int *status, int *iters, double *rr) {
+  if (!ctx || !b_host || !x_host) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(need_gauge(ctx));
+  TB_CHECK(upload_vec(ctx, b_host, ctx->vin));
+  TB_CHECK(run_cg(ctx, ctx->vin, ctx->vout));
+  TB_CHECK(download_vec(ctx, ctx->vout, x_host));
+  if (status || iters || rr) TB_CHECK(tb_cg_result(ctx, status, iters, rr));
+  return TB_OK;
+}
+
+extern "C" int tb_invert(tb_ctx *ctx, const double *v_host, double *x_host, int *status, int *iters,
+                         double *rr) {
+  if (!ctx || !v_host || !x_host) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(need_gauge(ctx));
+  TB_CHECK(upload_vec(ctx, v_host, ctx->vin));
+  TB_CHECK(tb_invert_dev(ctx, (const double *)ctx->vin, (double *)ctx->vout));
+  TB_CHECK(download_vec(ctx, ctx->vout, x_host));
+  if (status || iters || rr) TB_CHECK(tb_cg_result(ctx, status, iters, rr));
+  return TB_OK;
+}

@@ -1,0 +1,564 @@
+// tb_stream.cu — streaming (HBM/L2-bound) kernels of the batched fermion solve, sm_100a, FP64.
+//
+//   links      A -> W_mu = s * 1/2 * eta_mu * exp(iA_mu)            replaces hmc.c:140-141,152-153,163-164,173-174
+//   dslash     out = M in | M^dagger in, optional fused Re<aux,out>  replaces fm_mul hmc.c:132-183,
+//                                                                    fm_conjugate_mul hmc.c:197-248, dot hmc.c:368-370
+//   axpy_norm  x += a p ; r -= a q ; ||r||^2                          replaces hmc.c:372-379
+//   xpay       p = r + b p                                            replaces hmc.c:390-392
+//   cg_init    x = 0 ; r = p = b ; ||b||^2                            replaces hmc.c:349-361
+//
+// Layout: double2 field[t][x][c], chain index c fastest.  A thread owns one (x,c) column position and
+// marches over TT rows in t keeping psi(t-1), psi(t), psi(t+1) and W0(t-1) in registers, so the t-neighbours
+// and the backward t-link cost no extra traffic; x-neighbours are the centre loads of the neighbouring
+// threads of the same block (L1) or of the neighbouring block (L2).
+//
+// Reductions are per chain and deterministic: fixed-shape tree inside the block, one partial per
+// (block, chain), and the LAST block of each chain tile (atomic ticket) sums the partials in slot order and
+// evaluates the CG scalar update, so alpha/beta/convergence never leave the device and no FP64 atomics in
+// arbitrary order are used.
+#include "tb_common.cuh"
+
+namespace {
+
+enum { FIN_DOT = 0, FIN_INIT = 1, FIN_PQ = 2, FIN_RR = 3 };
+
+struct BlockPos {
+  int ctile, xtile, ttile;
+  int c_local, x_local;
+  int c, x;
+  bool valid;
+};
+
+__device__ __forceinline__ BlockPos block_pos(const TbGeom &g) {
+  BlockPos b;
+  b.ctile = blockIdx.x;
+  b.xtile = blockIdx.y;
+  b.ttile = blockIdx.z;
+  b.c_local = threadIdx.x & (g.bc - 1);
+  b.x_local = threadIdx.x >> g.bc_shift;
+  b.c = b.ctile * g.bc + b.c_local;
+  b.x = b.xtile * g.bx + b.x_local;
+  b.valid = (b.c < g.C) && (b.x < g.nx);
+  return b;
+}
+
+// Block-level deterministic reduction of `acc` over the x_local index for every chain of the tile, then
+// ticket-based cross-block finalisation.  `red` is shared memory for blockDim.x doubles.
+template <int FIN>
+__device__ __forceinline__ void reduce_finalize(double acc, const TbGeom &g, const TbCgState &s,
+                                                const BlockPos &b, double *red) {
+  __shared__ unsigned int s_last;
+  const int idx = b.x_local * g.bc + b.c_local;
+  red[idx] = acc;
+  __syncthreads();
+  for (int st = g.bx >> 1; st > 0; st >>= 1) {
+    if (b.x_local < st) red[idx] += red[idx + st * g.bc];
+    __syncthreads();
+  }
+  const int slot = b.ttile * g.nxtiles + b.xtile;
+  const int cp = b.ctile * g.bc + b.c_local;  // < Cpad
+  if (b.x_local == 0) {
+    s.partial[(size_t)slot * g.Cpad + cp] = red[b.c_local];
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int tk = atomicAdd(&s.ticket[b.ctile], 1u);
+    s_last = (tk == (unsigned int)(g.nslots - 1));
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  double sum = 0.0;
+  for (int sl = b.x_local; sl < g.nslots; sl += g.bx) sum += __ldcg(&s.partial[(size_t)sl * g.Cpad + cp]);
+  red[idx] = sum;
+  __syncthreads();
+  for (int st = g.bx >> 1; st > 0; st >>= 1) {
+    if (b.x_local < st) red[idx] += red[idx + st * g.bc];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) s.ticket[b.ctile] = 0u;
+  if (b.x_local != 0 || b.c >= g.C) return;
+  const double total = red[b.c_local];
+  const int c = b.c;
+  if (FIN == FIN_DOT) {
+    s.dot[c] = total;
+  } else if (FIN == FIN_INIT) {
+    s.rr[c] = total;
+    s.rr_old[c] = total;
+    s.rr_init[c] = total;
+    if (total < s.accuracy) {  // hmc.c:359-361, x is already zero
+      s.status[c] = TB_CG_ZERO_SOURCE;
+      s.active[c] = 0;
+      atomicSub(&s.tile_active[b.ctile], 1);
+      atomicSub(s.n_active, 1);
+    }
+  } else if (FIN == FIN_PQ) {
+    if (s.active[c]) {
+      s.pq[c] = total;
+      s.alpha[c] = s.rr_old[c] / total;  // hmc.c:371
+    }
+  } else if (FIN == FIN_RR) {
+    if (s.active[c]) {
+      const int it = s.iters[c] + 1;
+      s.iters[c] = it;
+      s.rr[c] = total;
+      int st = -1;
+      if (total < s.accuracy) st = TB_CG_CONVERGED;                                    // hmc.c:381
+      else if (!(total == total) || total / s.rr_init[c] > TB_DIVERGENCE_RATIO) st = TB_CG_DIVERGED;  // hmc.c:383
+      else if (it >= s.max_iter - 1) st = TB_CG_MAXITER;                               // hmc.c:364
+      if (st >= 0) {
+        s.status[c] = st;
+        s.active[c] = 0;
+        atomicSub(&s.tile_active[b.ctile], 1);
+        atomicSub(s.n_active, 1);
+      } else {
+        s.beta[c] = total / s.rr_old[c];  // hmc.c:390
+        s.rr_old[c] = total;              // hmc.c:394
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Dirac apply.  DAG: M^dagger instead of M.  DOT: accumulate Re<aux,out> and finalise alpha (FIN_PQ) or a
+// plain dot (FIN_DOT when !MASKED).  MASKED: skip chains whose CG has finished.
+template <int TT, bool DAG, bool DOT, bool MASKED>
+__global__ void __launch_bounds__(TB_MAX_BLOCK)
+dslash_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ W0,
+              const double2 *__restrict__ W1, const double *__restrict__ mass,
+              const double *__restrict__ emu, const double *__restrict__ emmu,
+              const double2 *__restrict__ aux, const TbGeom g, const TbCgState s) {
+  __shared__ double red[TB_MAX_BLOCK];
+  const BlockPos b = block_pos(g);
+  if (MASKED && s.tile_active[b.ctile] == 0) return;
+  bool act = b.valid;
+  if (MASKED && act) act = s.active[b.c] != 0;
+  double acc = 0.0;
+  if (act) {
+    const double m = mass[b.c];
+    const double af = DAG ? emmu[b.c] : emu[b.c];  // factor on the +t hop (hmc.c:144 / adjoint)
+    const double ab = DAG ? emu[b.c] : emmu[b.c];  // factor on the -t hop (hmc.c:156 / adjoint)
+    const size_t R = (size_t)g.R;
+    const size_t j = (size_t)b.x * g.C + b.c;
+    const size_t jp = (size_t)((b.x + 1 == g.nx) ? 0 : b.x + 1) * g.C + b.c;
+    const size_t jm = (size_t)((b.x == 0) ? g.nx - 1 : b.x - 1) * g.C + b.c;
+    const int t0 = b.ttile * TT;
+    const int tm0 = (t0 == 0) ? g.nt - 1 : t0 - 1;
+    double2 pm = in[tm0 * R + j];
+    double2 pc = in[t0 * R + j];
+    double2 w0m = W0[tm0 * R + j];
+#pragma unroll
+    for (int i = 0; i < TT; i++) {
+      const int t = t0 + i;
+      if (t < g.nt) {
+        const int tp = (t + 1 == g.nt) ? 0 : t + 1;
+        const size_t row = t * R;
+        const double2 pp = in[tp * R + j];
+        const double2 pxp = in[row + jp];
+        const double2 pxm = in[row + jm];
+        const double2 w0c = W0[row + j];
+        const double2 w1c = W1[row + j];
+        const double2 w1m = W1[row + jm];
+        // hops: +af W0(n) psi(n+t) - ab conj(W0(n-t)) psi(n-t) + W1(n) psi(n+x) - conj(W1(n-x)) psi(n-x)
+        const double fr = w0c.x * af, fi = w0c.y * af;
+        const double br = w0m.x * ab, bi = w0m.y * ab;
+        double hr = fr * pp.x - fi * pp.y;
+        double hi = fr * pp.y + fi * pp.x;
+        hr -= br * pm.x + bi * pm.y;
+        hi -= br * pm.y - bi * pm.x;
+        hr += w1c.x * pxp.x - w1c.y * pxp.y;
+        hi += w1c.x * pxp.y + w1c.y * pxp.x;
+        hr -= w1m.x * pxm.x + w1m.y * pxm.y;
+        hi -= w1m.x * pxm.y - w1m.y * pxm.x;
+        double2 o;
+        if (DAG) {
+          o.x = m * pc.x - hr;
+          o.y = m * pc.y - hi;
+        } else {
+          o.x = m * pc.x + hr;
+          o.y = m * pc.y + hi;
+        }
+        out[row + j] = o;
+        if (DOT) {
+          const double2 a = aux[row + j];
+          acc += a.x * o.x + a.y * o.y;
+        }
+        pm = pc;
+        pc = pp;
+        w0m = w0c;
+      }
+    }
+  }
+  if (DOT) reduce_finalize<MASKED ? FIN_PQ : FIN_DOT>(acc, g, s, b, red);
+}
+
+// x += alpha p ; r -= alpha q ; rr = ||r||^2 ; then beta / convergence (hmc.c:372-394)
+template <int TT>
+__global__ void __launch_bounds__(TB_MAX_BLOCK)
+axpy_norm_kernel(double2 *__restrict__ x, double2 *__restrict__ r, const double2 *__restrict__ p,
+                 const double2 *__restrict__ q, const TbGeom g, const TbCgState s) {
+  __shared__ double red[TB_MAX_BLOCK];
+  const BlockPos b = block_pos(g);
+  if (s.tile_active[b.ctile] == 0) return;
+  const bool act = b.valid && s.active[b.c] != 0;
+  double acc = 0.0;
+  if (act) {
+    const double a = s.alpha[b.c];
+    const size_t R = (size_t)g.R;
+    const size_t j = (size_t)b.x * g.C + b.c;
+    const int t0 = b.ttile * TT;
+#pragma unroll
+    for (int i = 0; i < TT; i++) {
+      const int t = t0 + i;
+      if (t < g.nt) {
+        const size_t k = t * R + j;
+        double2 xv = x[k], rv = r[k];
+        const double2 pv = p[k], qv = q[k];
+        xv.x += a * pv.x;
+        xv.y += a * pv.y;
+        rv.x -= a * qv.x;
+        rv.y -= a * qv.y;
+        x[k] = xv;
+        r[k] = rv;
+        acc += rv.x * rv.x + rv.y * rv.y;
+      }
+    }
+  }
+  reduce_finalize<FIN_RR>(acc, g, s, b, red);
+}
+
+// p = r + beta p (hmc.c:391-392)
+template <int TT>
+__global__ void __launch_bounds__(TB_MAX_BLOCK)
+xpay_kernel(double2 *__restrict__ p, const double2 *__restrict__ r, const TbGeom g, const TbCgState s) {
+  const BlockPos b = block_pos(g);
+  if (s.tile_active[b.ctile] == 0) return;
+  if (!(b.valid && s.active[b.c] != 0)) return;
+  const double be = s.beta[b.c];
+  const size_t R = (size_t)g.R;
+  const size_t j = (size_t)b.x * g.C + b.c;
+  const int t0 = b.ttile * TT;
+#pragma unroll
+  for (int i = 0; i < TT; i++) {
+    const int t = t0 + i;
+    if (t < g.nt) {
+      const size_t k = t * R + j;
+      const double2 rv = r[k];
+      double2 pv = p[k];
+      pv.x = rv.x + be * pv.x;
+      pv.y = rv.y + be * pv.y;
+      p[k] = pv;
+    }
+  }
+}
+
+// x = 0 ; r = b ; p = b ; rr = ||b||^2 (hmc.c:349-361)
+template <int TT>
+__global__ void __launch_bounds__(TB_MAX_BLOCK)
+cg_init_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ x, double2 *__restrict__ r,
+               double2 *__restrict__ p, const TbGeom g, const TbCgState s) {
+  __shared__ double red[TB_MAX_BLOCK];
+  const BlockPos b = block_pos(g);
+  double acc = 0.0;
+  if (b.valid) {
+    const size_t R = (size_t)g.R;
+    const size_t j = (size_t)b.x * g.C + b.c;
+    const int t0 = b.ttile * TT;
+#pragma unroll
+    for (int i = 0; i < TT; i++) {
+      const int t = t0 + i;
+      if (t < g.nt) {
+        const size_t k = t * R + j;
+        const double2 v = bsrc[k];
+        x[k] = make_double2(0.0, 0.0);
+        r[k] = v;
+        p[k] = v;
+        acc += v.x * v.x + v.y * v.y;
+      }
+    }
+  }
+  reduce_finalize<FIN_INIT>(acc, g, s, b, red);
+}
+
+// plain per-chain Re<a,b>
+template <int TT>
+__global__ void __launch_bounds__(TB_MAX_BLOCK)
+dot_kernel(const double2 *__restrict__ a, const double2 *__restrict__ bb, const TbGeom g, const TbCgState s) {
+  __shared__ double red[TB_MAX_BLOCK];
+  const BlockPos b = block_pos(g);
+  double acc = 0.0;
+  if (b.valid) {
+    const size_t R = (size_t)g.R;
+    const size_t j = (size_t)b.x * g.C + b.c;
+    const int t0 = b.ttile * TT;
+#pragma unroll
+    for (int i = 0; i < TT; i++) {
+      const int t = t0 + i;
+      if (t < g.nt) {
+        const size_t k = t * R + j;
+        const double2 u = a[k], v = bb[k];
+        acc += u.x * v.x + u.y * v.y;
+      }
+    }
+  }
+  reduce_finalize<FIN_DOT>(acc, g, s, b, red);
+}
+
+__global__ void cg_reset_kernel(const TbGeom g, const TbCgState s) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < g.Cpad) {
+    const int valid = i < g.C;
+    s.active[i] = valid;
+    s.status[i] = TB_CG_MAXITER;
+    s.iters[i] = 0;
+    s.alpha[i] = 0.0;
+    s.beta[i] = 0.0;
+  }
+  if (i < g.nctiles) {
+    int n = g.C - i * g.bc;
+    s.tile_active[i] = n > g.bc ? g.bc : (n < 0 ? 0 : n);
+    s.ticket[i] = 0u;
+  }
+  if (i == 0) *s.n_active = g.C;
+}
+
+// W0 = s0(t) 1/2 eta0(x) (cos A0, sin A0) ; W1 = s1(x) 1/2 (cos A1, sin A1); device layout in and out.
+// eta0 = (-1)^x (hmc.c:917-921), s = -1 on the wrap link (hmc.c:143-148,165-170).
+__global__ void links_kernel(const double2 *__restrict__ A, double2 *__restrict__ W0, double2 *__restrict__ W1,
+                             int nt, int nx, int C) {
+  const size_t n = (size_t)nt * nx * C;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
+    const size_t site = k / C;
+    const int x = (int)(site % nx);
+    const int t = (int)(site / nx);
+    const double2 a = A[k];
+    double s0, c0, s1, c1;
+    sincos(a.x, &s0, &c0);
+    sincos(a.y, &s1, &c1);
+    double f0 = (x & 1) ? -0.5 : 0.5;
+    if (t == nt - 1) f0 = -f0;
+    const double f1 = (x == nx - 1) ? -0.5 : 0.5;
+    W0[k] = make_double2(f0 * c0, f0 * s0);
+    W1[k] = make_double2(f1 * c1, f1 * s1);
+  }
+}
+
+// (C x V) double2 -> (V x C) double2 tiled transpose and its inverse.
+__global__ void transpose_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, int rows, int cols) {
+  // src[rows][cols] -> dst[cols][rows]
+  __shared__ double2 tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = src[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
+dim3 grid_of(const TbGeom &g) { return dim3(g.nctiles, g.nxtiles, g.nttiles); }
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// host-side launch wrappers
+
+#define TB_DISPATCH_TT(tt, EXPR)            \
+  switch (tt) {                             \
+    case 1: { constexpr int TT = 1; EXPR; } break;   \
+    case 2: { constexpr int TT = 2; EXPR; } break;   \
+    case 4: { constexpr int TT = 4; EXPR; } break;   \
+    case 8: { constexpr int TT = 8; EXPR; } break;   \
+    default: { constexpr int TT = 16; EXPR; } break; \
+  }
+
+int tb_choose_geom(tb_ctx *ctx) {
+  TbGeom &g = ctx->g;
+  g.nt = ctx->nt;
+  g.nx = ctx->nx;
+  g.C = ctx->C;
+  g.R = ctx->nx * ctx->C;
+  int bc = 1;
+  while (bc < ctx->C && bc < 32) bc <<= 1;
+  int bx = TB_MAX_BLOCK / bc;
+  int nxp = 1;
+  while (nxp < ctx->nx) nxp <<= 1;
+  if (bx > nxp) bx = nxp;
+  if (bc * bx < 32) bx = 32 / bc;  // at least one warp
+  g.bc = bc;
+  g.bx = bx;
+  g.bc_shift = 0;
+  while ((1 << g.bc_shift) < bc) g.bc_shift++;
+  g.nctiles = (ctx->C + bc - 1) / bc;
+  g.nxtiles = (ctx->nx + bx - 1) / bx;
+  g.Cpad = g.nctiles * bc;
+  int tt = ctx->tune_tt;
+  if (tt != 1 && tt != 2 && tt != 4 && tt != 8 && tt != 16) {
+    tt = 16;
+    const long nb1 = (long)g.nctiles * g.nxtiles;
+    while (tt > 1 && nb1 * ((ctx->nt + tt - 1) / tt) < 6L * TB_NUM_SMS_B200) tt >>= 1;
+  }
+  g.tt = tt;
+  g.nttiles = (ctx->nt + tt - 1) / tt;
+  g.nslots = g.nxtiles * g.nttiles;
+  return TB_OK;
+}
+
+int tb_launch_links(tb_ctx *ctx, const double *d_A_dev_layout) {
+  const size_t n = ctx->nsite;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > TB_NUM_SMS_B200 * 16) blocks = TB_NUM_SMS_B200 * 16;
+  links_kernel<<<blocks, 256, 0, ctx->stream>>>((const double2 *)d_A_dev_layout, ctx->W0, ctx->W1, ctx->nt,
+                                                ctx->nx, ctx->C);
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
+int tb_launch_pack(tb_ctx *ctx, const double *d_canonical, double2 *d_vec) {
+  if (ctx->C == 1) {
+    if ((const void *)d_canonical != (const void *)d_vec)
+      TB_CUDA(cudaMemcpyAsync(d_vec, d_canonical, ctx->nsite * sizeof(double2), cudaMemcpyDeviceToDevice,
+                              ctx->stream));
+    return TB_OK;
+  }
+  const int rows = ctx->C, cols = (int)ctx->V;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, ctx->stream>>>((const double2 *)d_canonical, d_vec, rows, cols);
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
+int tb_launch_unpack(tb_ctx *ctx, const double2 *d_vec, double *d_canonical) {
+  if (ctx->C == 1) {
+    if ((const void *)d_canonical != (const void *)d_vec)
+      TB_CUDA(cudaMemcpyAsync(d_canonical, d_vec, ctx->nsite * sizeof(double2), cudaMemcpyDeviceToDevice,
+                              ctx->stream));
+    return TB_OK;
+  }
+  const int rows = (int)ctx->V, cols = ctx->C;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, ctx->stream>>>(d_vec, (double2 *)d_canonical, rows, cols);
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
+int tb_launch_dslash(tb_ctx *ctx, bool dagger, const double2 *in, double2 *out, bool masked) {
+  const TbGeom &g = ctx->g;
+  const dim3 grid = grid_of(g);
+  const int block = g.bc * g.bx;
+#define ARGS in, out, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu, nullptr, g, ctx->cg
+  if (masked) {
+    if (dagger) { TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, true, false, true><<<grid, block, 0, ctx->stream>>>(ARGS))) }
+    else { TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, false, false, true><<<grid, block, 0, ctx->stream>>>(ARGS))) }
+  } else {
+    if (dagger) { TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, true, false, false><<<grid, block, 0, ctx->stream>>>(ARGS))) }
+    else { TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, false, false, false><<<grid, block, 0, ctx->stream>>>(ARGS))) }
+  }
+#undef ARGS
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
+// q = M~ Mp with fused alpha = rr_old / Re<p,q>
+static int launch_dslash_pq(tb_ctx *ctx, bool dagger, const double2 *in, double2 *out, const double2 *aux) {
+  const TbGeom &g = ctx->g;
+  const dim3 grid = grid_of(g);
+  const int block = g.bc * g.bx;
+#define ARGS in, out, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu, aux, g, ctx->cg
+  if (dagger) { TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, true, true, true><<<grid, block, 0, ctx->stream>>>(ARGS))) }
+  else { TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, false, true, true><<<grid, block, 0, ctx->stream>>>(ARGS))) }
+#undef ARGS
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
+int tb_launch_dot(tb_ctx *ctx, const double2 *a, const double2 *b, double *d_out) {
+  const TbGeom &g = ctx->g;
+  TbCgState s = ctx->cg;
+  s.dot = d_out;
+  TB_DISPATCH_TT(g.tt, (dot_kernel<TT><<<grid_of(g), g.bc * g.bx, 0, ctx->stream>>>(a, b, g, s)))
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
+static int cg_iteration(tb_ctx *ctx, double2 *x) {
+  const TbGeom &g = ctx->g;
+  const dim3 grid = grid_of(g);
+  const int block = g.bc * g.bx;
+  TB_CHECK(tb_launch_dslash(ctx, false, ctx->p, ctx->Mp, true));                       // hmc.c:366
+  TB_CHECK(launch_dslash_pq(ctx, tb_conj_is_dagger(ctx), ctx->Mp, ctx->q, ctx->p));    // hmc.c:367-371
+  TB_DISPATCH_TT(g.tt, (axpy_norm_kernel<TT><<<grid, block, 0, ctx->stream>>>(x, ctx->r, ctx->p, ctx->q, g, ctx->cg)))
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  TB_DISPATCH_TT(g.tt, (xpay_kernel<TT><<<grid, block, 0, ctx->stream>>>(ctx->p, ctx->r, g, ctx->cg)))
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
+// Streaming CG driver: the whole solve stays on the device; the host only polls the number of chains
+// still iterating, one graph launch (tune_chunk iterations) behind the device.
+int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
+  const TbGeom &g = ctx->g;
+  const dim3 grid = grid_of(g);
+  const int block = g.bc * g.bx;
+  cudaStream_t st = ctx->stream;
+  cg_reset_kernel<<<(g.Cpad + 255) / 256, 256, 0, st>>>(g, ctx->cg);
+  ctx->launches++;
+  TB_DISPATCH_TT(g.tt, (cg_init_kernel<TT><<<grid, block, 0, st>>>(b, ctx->xw, ctx->r, ctx->p, g, ctx->cg)))
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+
+  int chunk = ctx->tune_chunk > 0 ? ctx->tune_chunk : 16;
+  const bool use_graph = getenv("TB_NO_GRAPH") == nullptr;
+  if (use_graph && (ctx->cg_graph == nullptr || ctx->cg_graph_chunk != chunk)) {
+    if (ctx->cg_graph) { cudaGraphExecDestroy(ctx->cg_graph); ctx->cg_graph = nullptr; }
+    cudaStream_t cap;
+    TB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    cudaStream_t saved = ctx->stream;
+    const long long saved_launches = ctx->launches;
+    ctx->stream = cap;
+    TB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed));
+    int rc = TB_OK;
+    for (int i = 0; i < chunk && rc == TB_OK; i++) rc = cg_iteration(ctx, ctx->xw);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cap, &graph);
+    ctx->stream = saved;
+    ctx->launches = saved_launches;
+    if (rc != TB_OK) { cudaStreamDestroy(cap); return rc; }
+    TB_CUDA(e);
+    TB_CUDA(cudaGraphInstantiate(&ctx->cg_graph, graph, 0));
+    cudaGraphDestroy(graph);
+    cudaStreamDestroy(cap);
+    ctx->cg_graph_chunk = chunk;
+  }
+
+  const long max_chunks = ((long)ctx->cg.max_iter + chunk - 1) / chunk + 1;
+  for (long i = 0; i < max_chunks; i++) {
+    if (use_graph) {
+      TB_CUDA(cudaGraphLaunch(ctx->cg_graph, st));
+      ctx->launches += 4LL * chunk;
+    } else {
+      for (int k = 0; k < chunk; k++) TB_CHECK(cg_iteration(ctx, ctx->xw));
+    }
+    const int slot = (int)(i & 1);
+    TB_CUDA(cudaMemcpyAsync(&ctx->h_flag[slot], ctx->cg.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaEventRecord(ctx->ev_flag[slot], st));
+    if (i > 0) {
+      TB_CUDA(cudaEventSynchronize(ctx->ev_flag[slot ^ 1]));
+      if (ctx->h_flag[slot ^ 1] == 0) break;
+    }
+  }
+  TB_CUDA(cudaMemcpyAsync(x, ctx->xw, ctx->nsite * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  return TB_OK;
+}

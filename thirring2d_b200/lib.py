@@ -1,0 +1,74 @@
+"""ctypes loader for libthirring_b200.so.  Fails loudly when the CUDA extension is missing."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class TBError(RuntimeError):
+    pass
+
+
+def library_path() -> str:
+    return os.path.join(_HERE, "libthirring_b200.so")
+
+
+# name -> (restype, argtypes); every symbol include/thirring_b200.h declares
+_vp, _i, _d = C.c_void_p, C.c_int, C.c_double
+_ip, _dp = C.POINTER(C.c_int), C.POINTER(C.c_double)
+SIGNATURES = {
+    "tb_last_error": (C.c_char_p, []),
+    "tb_device_count": (_i, []),
+    "tb_create": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i]),
+    "tb_destroy": (_i, [_vp]),
+    "tb_set_stream": (_i, [_vp, _vp]),
+    "tb_synchronize": (_i, [_vp]),
+    "tb_set_params": (_i, [_vp, _dp, _dp, _i]),
+    "tb_set_cg": (_i, [_vp, _d, _i]),
+    "tb_set_tuning": (_i, [_vp, _i, _i, _i]),
+    "tb_set_gauge": (_i, [_vp, _vp]),
+    "tb_apply": (_i, [_vp, _i, _vp, _vp]),
+    "tb_cg": (_i, [_vp, _vp, _vp, _ip, _ip, _dp]),
+    "tb_invert": (_i, [_vp, _vp, _vp, _ip, _ip, _dp]),
+    "tb_vec_doubles": (C.c_size_t, [_vp]),
+    "tb_pack_dev": (_i, [_vp, _vp, _vp]),
+    "tb_unpack_dev": (_i, [_vp, _vp, _vp]),
+    "tb_set_gauge_dev": (_i, [_vp, _vp]),
+    "tb_apply_dev": (_i, [_vp, _i, _vp, _vp]),
+    "tb_cg_dev": (_i, [_vp, _vp, _vp]),
+    "tb_invert_dev": (_i, [_vp, _vp, _vp]),
+    "tb_cg_result": (_i, [_vp, _ip, _ip, _dp]),
+    "tb_re_dot_dev": (_i, [_vp, _vp, _vp, _dp]),
+    "tb_launch_count": (C.c_longlong, [_vp]),
+    "tb_reset_launch_count": (_i, [_vp]),
+    "tb_last_solve_ms": (_d, [_vp]),
+}
+
+
+def load_library():
+    """dlopen the in-tree CUDA library and type every entry point.  No fallback of any kind."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise TBError(
+            f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C thirring2d_b200/csrc`).  thirring2d_b200 has no CPU fallback."
+        )
+    lib = C.CDLL(path)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load_library().tb_last_error()
+        raise TBError(f"{what} failed with code {rc}: {msg.decode() if msg else ''}")
