@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — Dirac applies/s of the batched HMC fermion solve on B200 (one JSON line on rank 0).
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run)
+    python bench.py --impl reference ...                     (the reference's CPU implementation, host cores)
+
+A "step" is one pass of the hot path over one batch: fmdm_invert_cg (hmc.c:341-404) for every chain of the
+workload from x0 = 0 to ||r||^2 < 1e-30, i.e. 2 Dirac applies (M, M^dagger) + the fused BLAS-1 per CG iteration
+per chain.  Workload = BASELINE.json configs[1]: 64x64 lattice, 256 independent chains per GPU, ADJOINT mode,
+m = 0.1, mu = 0, quenched-equilibrium links at g = 0.3.  Chains shard over ranks with no
+data-path collective (weak scaling: 256 chains per GPU).
+
+  value      whole-job applies/s, inputs resident in HBM, device time by CUDA events, max over ranks
+  e2e        the same metric through the reference-facing host-buffer C-ABI call (tb_set_gauge + tb_cg) with
+             pinned HOST buffers; H2D of links and sources and D2H of the solutions inside the timed region
+  roofline   CG iteration (the 4 fused streaming kernels, or the single resident kernel): algorithmic
+             288 B/site/iteration over the device time of the timed solves
+  cpu_baseline  the reference's own fmdm_invert_cg (oracle/_ref) on the host cores, bounded sample
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+NT = NX = 64
+CHAINS_PER_GPU = 256
+MASS, MU, G = 0.1, 0.0, 0.3
+BYTES_PER_SITE_ITER = 288  # K1 64 + K2 80 + K3 96 + K4 48
+BYTES_PER_SITE_APPLY = 64
+METRIC, UNIT = "dirac_applies_per_sec", "applies/s"
+
+
+def workload_name(chains):
+    return f"cg_solve_{NT}x{NX}_lattice_{chains}_chains_per_gpu_adjoint_m{MASS}_g{G}"
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def synthetic_batch(first_chain, nchains):
+    """Inputs of chain c depend only on c (so every rank count gives the same global ensemble).  Same
+    generator as oracle/cpu_baseline.py:synthetic_chain, restated here because the product side of the
+    bench must not import the oracle."""
+    A = np.empty((nchains, NT, NX, 2))
+    xi = np.empty((nchains, NT, NX), dtype=np.complex128)
+    for i in range(nchains):
+        rng = np.random.default_rng(1_000_003 * (first_chain + i + 1))
+        A[i] = rng.vonmises(0.0, 2.0 / G, size=(NT, NX, 2))
+        xi[i] = rng.normal(size=(NT, NX)) + 1j * rng.normal(size=(NT, NX))
+    return A, xi
+
+
+# ------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self.stop_flag = True
+        if self.nv is None or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml_unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max_mhz),
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_cpu_reference(chains_total, procs):
+    """Time the reference's fmdm_invert_cg on `procs` host processes (it is single-threaded: one chain per
+    process at a time).  Returns (applies/s, seconds wall, applies, kind)."""
+    per = max(1, chains_total // procs)
+    cmds = []
+    for p in range(procs):
+        cmds.append([sys.executable, "-m", "oracle.cpu_baseline", "--nt", str(NT), "--nx", str(NX), "--chains",
+                     str(per), "--first", str(p * per), "--m", str(MASS), "--mu", str(MU), "--g", str(G)])
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen(c, cwd=ROOT, stdout=subprocess.PIPE, text=True) for c in cmds]
+    outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in ps]
+    wall = time.perf_counter() - t0
+    applies = sum(o["applies"] for o in outs)
+    busy = max(o["seconds"] for o in outs)  # solver time of the slowest worker (excludes python start-up)
+    return applies / busy, busy, applies, outs[0]["kind"], per * procs, wall
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = cores * 2  # bounded sample: 2 chain solves per core per step (~0.5 s)
+    for _ in range(args.warmup):
+        run_cpu_reference(cores, cores)
+    t_busy, n_applies = 0.0, 0
+    for _ in range(args.steps):
+        v, busy, applies, kind, nchains, wall = run_cpu_reference(per_step, cores)
+        t_busy += busy
+        n_applies += applies
+    value = n_applies / t_busy
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_busy / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(CHAINS_PER_GPU), "sample": f"{per_step} of the chains per step"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": f"{per_step} chain solves per step ({NT}x{NX}, same inputs as the GPU arm), "
+                                   f"{cores} single-threaded processes of the reference's fmdm_invert_cg"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import thirring2d_b200 as tb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product has no CPU path; use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    chains = args.chains
+    first = rank * chains  # chain-parallel sharding: rank r owns chains [r*chains, (r+1)*chains)
+
+    stream = torch.cuda.current_stream()
+    ctx = tb.Context(NT, NX, chains, tb.MODE_ADJOINT, device=local, m=MASS, mu=MU, stream=stream.cuda_stream)
+    if args.solver or args.rows or args.chunk:
+        ctx.set_tuning(args.rows, args.chunk, args.solver)
+
+    # synthetic inputs: host (pinned) and device copies
+    A_np, xi_np = synthetic_batch(first, chains)
+    A_host = torch.from_numpy(A_np).pin_memory()
+    n = ctx.vec_doubles
+    A_dev = A_host.to(dev)
+    xi_canon = torch.from_numpy(xi_np.view(np.float64)).to(dev)
+    xi = torch.empty(n, dtype=torch.float64, device=dev)
+    b = torch.empty_like(xi)
+    x = torch.empty_like(xi)
+    ctx.set_gauge_dev(A_dev.data_ptr())
+    ctx.pack_dev(xi_canon.data_ptr(), xi.data_ptr())
+    ctx.apply_dev(tb.OP_MCONJ, xi.data_ptr(), b.data_ptr())  # b = M~ xi, hmc.c:432
+    # host copies of the sources for the e2e leg (canonical layout)
+    b_canon = torch.empty_like(xi_canon)
+    ctx.unpack_dev(b.data_ptr(), b_canon.data_ptr())
+    b_host = b_canon.cpu().pin_memory()
+    x_host = torch.empty_like(b_host).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        flush.zero_()  # evict the previous step's state from L2
+        ctx.cg_dev(b.data_ptr(), x.data_ptr())
+        return ctx.last_solve_ms
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    info = ctx.cg_result()
+    assert np.all(info.status == tb.CG_CONVERGED), info
+    iters = info.iters.astype(np.int64)
+    applies_per_step = int(2 * iters.sum())
+
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ctx.reset_launch_count()
+    solve_ms = 0.0
+    e0.record()
+    for _ in range(args.steps):
+        solve_ms += step()
+    e1.record()
+    barrier()
+    launches = ctx.launch_count
+    clocks = sampler.result()
+    ms_total = e0.elapsed_time(e1)
+
+    # e2e: the host-buffer C-ABI entry points a reference-side caller binds
+    def e2e_step():
+        ctx.set_gauge_host_ptr(A_host.data_ptr())
+        ctx.cg_host_ptr(b_host.data_ptr(), x_host.data_ptr())
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    x_dev_canon = torch.empty_like(xi_canon)
+    ctx.unpack_dev(x.data_ptr(), x_dev_canon.data_ptr())
+    assert torch.equal(x_dev_canon.cpu(), x_host), "e2e and device-resident solutions differ"
+
+    t = torch.tensor([ms_total, e2e_s * 1e3, solve_ms], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([applies_per_step, launches], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    ms_total, e2e_ms, solve_ms = t.tolist()
+    applies_all, launches_all = cnt.tolist()
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        sites = NT * NX * chains
+        max_it = int(iters.max())
+        # every chain of a tile streams until the tile's slowest chain converges -> bytes = sum over chains
+        alg_bytes_per_step = BYTES_PER_SITE_ITER * NT * NX * float(iters.sum())
+        achieved = alg_bytes_per_step * args.steps / (solve_ms * 1e-3) / 1e9
+        value = applies_all * args.steps / (ms_total * 1e-3)
+        e2e_value = applies_all * args.steps / (e2e_ms * 1e-3)
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(chains), "lattice": [NT, NX], "chains_per_gpu": chains,
+                       "mode": "ADJOINT", "m": MASS, "mu": MU, "g": G, "cg_accuracy": 1e-30,
+                       "cg_iters_mean": float(iters.mean()), "cg_iters_max": max_it,
+                       "l2": "256 MiB flush buffer written before every timed step"},
+            "site_applies_per_sec": value * NT * NX,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "CG iteration (dslash, dslash+dot, axpy+norm, xpay)",
+                         "algorithmic_bytes_per_site_iteration": BYTES_PER_SITE_ITER,
+                         "us_per_iteration": solve_ms * 1e3 / args.steps / max_it, "sites": sites},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(A_host.nbytes + b_host.nbytes),
+                    "d2h_bytes_per_step": int(x_host.nbytes), "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(launches_all),
+            "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            v, busy, applies, kind, nch, wall = run_cpu_reference(cores * 8, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
+                                    "sample": f"{nch} chain solves of the same workload ({NT}x{NX}, m={MASS}), "
+                                              f"{cores} single-threaded processes, {busy:.1f} s"}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU)
+    ap.add_argument("--rows", type=int, default=0)
+    ap.add_argument("--chunk", type=int, default=0)
+    ap.add_argument("--solver", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

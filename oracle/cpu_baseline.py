@@ -1,0 +1,64 @@
+"""CPU baseline worker: times the reference's own fmdm_invert_cg (oracle/_ref, hmc.c:341-404) or, when the
+reference build is absent, the oracle port, on synthetic chains of the bench workload.  TEST/BENCH
+INFRASTRUCTURE ONLY — executed only by bench.py's cpu_baseline / --impl reference legs.
+
+    python -m oracle.cpu_baseline --nt 64 --nx 64 --chains 4 --first 0 --m 0.1 --g 0.3
+
+prints one JSON line {"seconds", "chains", "iters", "applies", "kind"}.
+"""
+import argparse
+import json
+import time
+
+import numpy as np
+
+from oracle.pyoracle import MODE_ADJOINT, Oracle, RefLib, ref_available
+
+
+def synthetic_chain(chain, nt, nx, g):
+    """Same synthetic inputs as bench.py: quenched-equilibrium links P(A) ~ exp((Nf/g) cos A) (the fixed point
+    of update_puregauge_hb, hmc.c:82-93, Nf = 2) and a complex Gaussian xi (hmc.c:439-447)."""
+    rng = np.random.default_rng(1_000_003 * (chain + 1))
+    A = rng.vonmises(0.0, 2.0 / g, size=(nt, nx, 2))
+    xi = rng.normal(size=(nt, nx)) + 1j * rng.normal(size=(nt, nx))
+    return A, xi
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--nt", type=int, default=64)
+    ap.add_argument("--nx", type=int, default=64)
+    ap.add_argument("--chains", type=int, default=2)
+    ap.add_argument("--first", type=int, default=0)
+    ap.add_argument("--m", type=float, default=0.1)
+    ap.add_argument("--mu", type=float, default=0.0)
+    ap.add_argument("--g", type=float, default=0.3)
+    ap.add_argument("--max-iter", type=int, default=0)
+    a = ap.parse_args()
+    orc = Oracle()
+    use_ref = ref_available(a.nt, a.nx, "adjoint")
+    ref = RefLib(a.nt, a.nx, "adjoint", m=a.m, g=a.g, mu=a.mu) if use_ref else None
+    secs, iters = 0.0, 0
+    for c in range(a.first, a.first + a.chains):
+        A, xi = synthetic_chain(c, a.nt, a.nx, a.g)
+        if use_ref:
+            G = ref.gauge(A)
+            b = ref.fm_conjugate_mul(xi, G)
+            t0 = time.perf_counter()
+            x = ref.fmdm_invert_cg(b, G)
+            secs += time.perf_counter() - t0
+            # the reference does not return its iteration count; the bit-identical oracle port does
+            xo, st, it, rr = orc.fmdm_invert_cg(b, A, a.m, a.mu, MODE_ADJOINT, a.max_iter)
+            assert np.array_equal(x, xo)
+        else:
+            b = orc.fm_conjugate_mul(xi, A, a.m, a.mu, MODE_ADJOINT)
+            t0 = time.perf_counter()
+            xo, st, it, rr = orc.fmdm_invert_cg(b, A, a.m, a.mu, MODE_ADJOINT, a.max_iter)
+            secs += time.perf_counter() - t0
+        iters += it
+    print(json.dumps({"seconds": secs, "chains": a.chains, "iters": iters, "applies": 2 * iters,
+                      "kind": "reference" if use_ref else "port"}))
+
+
+if __name__ == "__main__":
+    main()

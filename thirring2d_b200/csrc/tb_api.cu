@@ -296,7 +296,14 @@ extern "C" int tb_apply_dev(tb_ctx *ctx, int op, const double *d_in, double *d_o
 
 static int run_cg(tb_ctx *ctx, const double2 *b, double2 *x) {
   TB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  TB_CHECK(tb_run_cg_stream(ctx, b, x));
+  // solver selection: 0 auto (resident when the lattice fits on chip), 1 streaming, 2 resident
+  const bool resident = ctx->tune_solver != 1 && tb_resident_supported(ctx);
+  if (ctx->tune_solver == 2 && !resident) {
+    tb_set_error("resident solver requested but %dx%d is not supported", ctx->nt, ctx->nx);
+    return TB_EINVAL;
+  }
+  if (resident) TB_CHECK(tb_run_cg_resident(ctx, b, x));
+  else TB_CHECK(tb_run_cg_stream(ctx, b, x));
   TB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   TB_CUDA(cudaEventSynchronize(ctx->ev1));
   float ms = 0.f;

@@ -95,6 +95,8 @@ int tb_launch_pack(tb_ctx *ctx, const double *d_canonical, double2 *d_vec);
 int tb_launch_unpack(tb_ctx *ctx, const double2 *d_vec, double *d_canonical);
 int tb_launch_dslash(tb_ctx *ctx, bool dagger, const double2 *in, double2 *out, bool masked);
 int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x);
+int tb_run_cg_resident(tb_ctx *ctx, const double2 *b, double2 *x);
+bool tb_resident_supported(const tb_ctx *ctx);
 int tb_launch_dot(tb_ctx *ctx, const double2 *a, const double2 *b, double *d_out);
 
 static inline bool tb_conj_is_dagger(const tb_ctx *ctx) { return ctx->mode == TB_MODE_ADJOINT; }
