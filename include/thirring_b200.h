@@ -69,8 +69,10 @@ int tb_set_params(tb_ctx *ctx, const double *m, const double *mu, int n);
  * passes (CG_MAX_ITER 100000, hmc.c:35).  Defaults are the reference's. */
 int tb_set_cg(tb_ctx *ctx, double accuracy, int max_iter);
 
-/* Tuning knobs (0 = automatic): rows marched per thread in the stencil, CG iterations per graph launch,
- * solver selection (0 auto, 1 streaming multi-kernel, 2 on-chip resident). */
+/* Tuning knobs (0 = automatic).  rows_per_thread: t-rows marched per thread by the streaming stencil
+ * (1,2,4,8,16); for the resident solver the same field selects the site tile per thread (44 = 4x4,
+ * 18 = 1x8, 28 = 2x8, 24 = 2x4).  iters_per_launch: CG iterations per CUDA-graph launch (streaming).
+ * solver: 0 auto (resident when the lattice is 16^2/32^2/64^2), 1 streaming multi-kernel, 2 resident. */
 int tb_set_tuning(tb_ctx *ctx, int rows_per_thread, int iters_per_launch, int solver);
 
 /* ---- host-buffer entry points (copies inside; this is what the reference-facing shim calls) ---------- */

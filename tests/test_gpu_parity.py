@@ -102,23 +102,46 @@ CG_CASES = [
 ]
 
 
+# (solver, rows_per_thread / resident tile shape, iterations per graph launch); solver 1 = streaming multi-kernel,
+# 2 = on-chip resident (16/32/64 square lattices only; tile 44 = 4x4, 18 = 1x8, 28 = 2x8 sites per thread)
+SOLVER_VARIANTS = [(1, 0, 0), (1, 2, 5), (2, 44, 0), (2, 18, 0), (2, 28, 0), (0, 0, 0)]
+
+
+def resident_ok(nt, nx):
+    return nt == nx and nt in (16, 32, 64)
+
+
 @pytest.mark.parametrize("nt,nx,nchains,mode,m,mu,width", CG_CASES)
 def test_T4_cg_matches_oracle(oracle, nt, nx, nchains, mode, m, mu, width):
     rng = np.random.default_rng(nt + nx + nchains)
     A = random_gauge(rng, nchains, nt, nx) if width is None else smooth_gauge(rng, nchains, nt, nx, width)
     xi = random_vector(rng, nchains, nt, nx)
+    ref = None
     with tb.Context(nt, nx, nchains, mode, m=m, mu=mu) as ctx:
         ctx.set_gauge(A)
         b = ctx.fm_conjugate_mul(xi)  # as random_pseudofermion does (hmc.c:418-436)
-        for rows, chunk in ((0, 0), (2, 5)):
-            ctx.set_tuning(rows_per_thread=rows, iters_per_launch=chunk)
+        for solver, rows, chunk in SOLVER_VARIANTS:
+            if solver == 2 and not resident_ok(nt, nx):
+                continue
+            ctx.set_tuning(rows_per_thread=rows, iters_per_launch=chunk, solver=solver)
             x, info = ctx.fmdm_invert_cg(b)
+            if ref is None:
+                ref = [oracle.fmdm_invert_cg(b[c], A[c], m, mu, mode) for c in range(nchains)]
             for c in range(nchains):
-                xo, st, it, rr = oracle.fmdm_invert_cg(b[c], A[c], m, mu, mode)
+                xo, st, it, rr = ref[c]
                 assert info.status[c] == st == tb.CG_CONVERGED
-                assert abs(int(info.iters[c]) - it) <= 1, (c, info.iters[c], it)
-                assert_close(x[c], xo, CG_SOL_TOL, f"chain {c}")
+                assert abs(int(info.iters[c]) - it) <= 1, (solver, rows, c, info.iters[c], it)
+                assert_close(x[c], xo, CG_SOL_TOL, f"solver {solver} rows {rows} chain {c}")
                 assert info.rr[c] < 1e-30
+
+
+def test_resident_solver_rejects_unsupported_lattice():
+    rng = np.random.default_rng(1)
+    with tb.Context(16, 32, 2, tb.MODE_ADJOINT, m=0.5) as ctx:
+        ctx.set_gauge(random_gauge(rng, 2, 16, 32))
+        ctx.set_tuning(solver=2)
+        with pytest.raises(tb.TBError, match="not supported"):
+            ctx.fmdm_invert_cg(random_vector(rng, 2, 16, 32))
 
 
 def test_T4_per_chain_counts_equal_single_chain_counts(oracle):
@@ -153,19 +176,23 @@ def test_T5_zero_source_and_divergence(oracle):
     b[1] = 0.0  # hmc.c:359-361: returns x = 0 without iterating
     with tb.Context(nt, nx, 3, tb.MODE_ADJOINT, m=0.5) as ctx:
         ctx.set_gauge(A)
-        x, info = ctx.fmdm_invert_cg(b)
-        assert info.status.tolist() == [tb.CG_CONVERGED, tb.CG_ZERO_SOURCE, tb.CG_CONVERGED]
-        assert info.iters[1] == 0 and np.all(x[1] == 0)
+        for solver in (1, 2):
+            ctx.set_tuning(solver=solver)
+            x, info = ctx.fmdm_invert_cg(b)
+            assert info.status.tolist() == [tb.CG_CONVERGED, tb.CG_ZERO_SOURCE, tb.CG_CONVERGED]
+            assert info.iters[1] == 0 and np.all(x[1] == 0)
     # REF_COMPAT at light mass: M.M is not positive definite -> the reference bails (hmc.c:383-388)
     with tb.Context(nt, nx, 3, tb.MODE_REF_COMPAT, m=0.1) as ctx:
         ctx.set_gauge(A)
         b[1] = b[0]
-        x, info = ctx.fmdm_invert_cg(b)
-        for c in range(3):
-            xo, st, it, rr = oracle.fmdm_invert_cg(b[c], A[c], 0.1, 0.0, tb.MODE_REF_COMPAT)
-            assert st == tb.CG_DIVERGED
-            assert info.status[c] == tb.CG_DIVERGED
-            assert abs(int(info.iters[c]) - it) <= 2
+        for solver in (1, 2):
+            ctx.set_tuning(solver=solver)
+            x, info = ctx.fmdm_invert_cg(b)
+            for c in range(3):
+                xo, st, it, rr = oracle.fmdm_invert_cg(b[c], A[c], 0.1, 0.0, tb.MODE_REF_COMPAT)
+                assert st == tb.CG_DIVERGED
+                assert info.status[c] == tb.CG_DIVERGED
+                assert abs(int(info.iters[c]) - it) <= 2
 
 
 def test_max_iter_is_reported():
@@ -175,9 +202,11 @@ def test_max_iter_is_reported():
     with tb.Context(16, 16, 2, tb.MODE_ADJOINT, m=0.05) as ctx:
         ctx.set_gauge(A)
         ctx.set_cg(1e-30, 20)
-        x, info = ctx.fmdm_invert_cg(b)
-        assert info.status.tolist() == [tb.CG_MAXITER] * 2
-        assert info.iters.tolist() == [19, 19]  # k = 1 .. max_iter-1, hmc.c:364
+        for solver in (1, 2):
+            ctx.set_tuning(solver=solver)
+            x, info = ctx.fmdm_invert_cg(b)
+            assert info.status.tolist() == [tb.CG_MAXITER] * 2
+            assert info.iters.tolist() == [19, 19]  # k = 1 .. max_iter-1, hmc.c:364
 
 
 def test_fm_invert_cg_inverts_M(oracle):
@@ -201,6 +230,8 @@ def test_runs_are_deterministic():
     b = random_vector(rng, 16, 32, 32)
     with tb.Context(32, 32, 16, tb.MODE_ADJOINT, m=0.2) as ctx:
         ctx.set_gauge(A)
-        x1, i1 = ctx.fmdm_invert_cg(b)
-        x2, i2 = ctx.fmdm_invert_cg(b)
-    assert np.array_equal(x1, x2) and np.array_equal(i1.iters, i2.iters)
+        for solver in (1, 2):
+            ctx.set_tuning(solver=solver)
+            x1, i1 = ctx.fmdm_invert_cg(b)
+            x2, i2 = ctx.fmdm_invert_cg(b)
+            assert np.array_equal(x1, x2) and np.array_equal(i1.iters, i2.iters)

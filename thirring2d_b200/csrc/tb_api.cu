@@ -194,10 +194,12 @@ extern "C" int tb_set_params(tb_ctx *ctx, const double *m, const double *mu, int
   TB_CUDA(cudaSetDevice(ctx->device));
   const int cp = ctx->g.Cpad;
   double *buf = (double *)malloc(3 * (size_t)cp * sizeof(double));
+  ctx->has_mu = false;
   for (int c = 0; c < cp; c++) {
     const int k = (n == 1 || c >= ctx->C) ? 0 : c;
     ctx->h_mass[c] = m[k];
     ctx->h_mu[c] = mu[k];
+    if (mu[k] != 0.0) ctx->has_mu = true;
     buf[c] = m[k];
     buf[cp + c] = exp(mu[k]);       // hmc.c:127
     buf[2 * cp + c] = exp(-mu[k]);  // hmc.c:128

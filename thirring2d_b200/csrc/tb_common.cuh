@@ -68,6 +68,7 @@ struct tb_ctx {
   // parameters
   double *d_mass, *d_emu, *d_emmu;  // [Cpad]
   double *h_mass, *h_mu;
+  bool has_mu;  // some chain has mu != 0
   // links, device layout [t][x][c]
   double2 *W0, *W1;
   bool have_gauge;

@@ -19,11 +19,26 @@
 
 namespace {
 
-__device__ __forceinline__ double2 cmul(const double2 w, const double2 p) {
-  return make_double2(w.x * p.x - w.y * p.y, w.x * p.y + w.y * p.x);
+// o += sgn * (w * f)  and  o += sgn * (conj(w) * f), as four FMAs each (operand negation is free in SASS)
+template <int SGN>
+__device__ __forceinline__ void hop_acc(double2 &o, const double2 w, const double2 f) {
+  if (SGN > 0) {
+    o.x = fma(w.x, f.x, o.x);  o.x = fma(-w.y, f.y, o.x);
+    o.y = fma(w.x, f.y, o.y);  o.y = fma(w.y, f.x, o.y);
+  } else {
+    o.x = fma(-w.x, f.x, o.x); o.x = fma(w.y, f.y, o.x);
+    o.y = fma(-w.x, f.y, o.y); o.y = fma(-w.y, f.x, o.y);
+  }
 }
-__device__ __forceinline__ double2 cmulc(const double2 w, const double2 p) {  // conj(w) * p
-  return make_double2(w.x * p.x + w.y * p.y, w.x * p.y - w.y * p.x);
+template <int SGN>
+__device__ __forceinline__ void hopc_acc(double2 &o, const double2 w, const double2 f) {
+  if (SGN > 0) {
+    o.x = fma(w.x, f.x, o.x);  o.x = fma(w.y, f.y, o.x);
+    o.y = fma(w.x, f.y, o.y);  o.y = fma(-w.y, f.x, o.y);
+  } else {
+    o.x = fma(-w.x, f.x, o.x); o.x = fma(-w.y, f.y, o.x);
+    o.y = fma(-w.x, f.y, o.y); o.y = fma(w.y, f.x, o.y);
+  }
 }
 
 template <int NWARPS>
@@ -38,49 +53,82 @@ __device__ __forceinline__ double block_sum(double v, double *scratch) {
   return s;
 }
 
-// out[i] = m f[i] +- hops, for the TS sites of this thread's column.  f: own column values (registers),
-// F: the same field in shared memory (neighbours), DAG: apply M^dagger instead of M.
-template <int NT, int NX, int TS, bool DAG>
-__device__ __forceinline__ void column_apply(const double2 (&f)[TS], double2 (&out)[TS], const double2 *F,
-                                             const double2 *W0s, const double2 *W1s, int t0, int x,
-                                             double m, double af, double ab) {
-  const int xp = (x + 1) & (NX - 1), xm = (x - 1) & (NX - 1);
-  const int tm = (t0 - 1) & (NT - 1), te = (t0 + TS) & (NT - 1);
-  const double2 fU = F[tm * NX + x];   // f(t0-1, x)
-  const double2 fD = F[te * NX + x];   // f(t0+TS, x)
-  double2 w0m = W0s[tm * NX + x];      // W0(t-1, x), slides down the column
+// Shared-memory site index: the TX x-sites of a thread's tile live in TX separate sub-planes of a row, so
+// that for a fixed tile column j consecutive threads (x-groups) touch consecutive double2 (conflict-free
+// LDS.128 / STS.128 whatever TX is).
+template <int NX, int TX>
+__device__ __forceinline__ int sidx(int t, int x) {
+  return t * NX + (x % TX) * (NX / TX) + x / TX;
+}
+
+// out = m f +- hops on the thread's TT x TX tile.  f: own tile (registers); F: the same field in shared memory
+// (only the tile's halo is read from it).  DAG: M^dagger instead of M.  HAS_MU: the t-links carry e^{+-mu}
+// (af on the +t hop, ab on the -t hop); otherwise both are 1 and the scaling is skipped.
+// Shared-memory traffic per site and apply: 16 B * (2 + 3/TX + 3/TT)  (halo of f, W0 rows, W1 columns).
+template <int NT, int NX, int TX, int TT, bool DAG, bool HAS_MU>
+__device__ __forceinline__ void tile_apply(const double2 (&f)[TT][TX], double2 (&out)[TT][TX], const double2 *F,
+                                           const double2 *W0s, const double2 *W1s, int t0, int g,
+                                           double m, double af, double ab) {
+  constexpr int SF = DAG ? -1 : 1;  // sign of the forward hops (hmc.c:144,166 / adjoint)
+  constexpr int SB = -SF;           // sign of the backward hops (hmc.c:158,179 / adjoint)
+  constexpr int NG = NX / TX;       // x-groups per row == stride between sub-planes
+  const int gl = (g + NG - 1) % NG, gr = (g + 1) % NG;
+  const int tm = (t0 + NT - 1) % NT, te = (t0 + TT) % NT;
+  double2 w0m[TX];                  // W0(t-1, x0+j): slides down the tile
 #pragma unroll
-  for (int i = 0; i < TS; i++) {
-    const int t = t0 + i;
-    const double2 w0c = W0s[t * NX + x];
-    const double2 w1c = W1s[t * NX + x];
-    const double2 w1m = W1s[t * NX + xm];
-    const double2 fxp = F[t * NX + xp];
-    const double2 fxm = F[t * NX + xm];
-    const double2 up = (i == TS - 1) ? fD : f[(i + 1) % TS];
-    const double2 dn = (i == 0) ? fU : f[(i + TS - 1) % TS];
-    // +af W0(n) f(n+t) - ab conj(W0(n-t)) f(n-t) + W1(n) f(n+x) - conj(W1(n-x)) f(n-x)   (hmc.c:140-180)
-    const double2 a = cmul(make_double2(w0c.x * af, w0c.y * af), up);
-    const double2 b = cmulc(make_double2(w0m.x * ab, w0m.y * ab), dn);
-    const double2 c = cmul(w1c, fxp);
-    const double2 d = cmulc(w1m, fxm);
-    const double hr = (a.x - b.x) + (c.x - d.x);
-    const double hi = (a.y - b.y) + (c.y - d.y);
-    if (DAG) out[i] = make_double2(m * f[i].x - hr, m * f[i].y - hi);
-    else out[i] = make_double2(m * f[i].x + hr, m * f[i].y + hi);
-    w0m = w0c;
+  for (int j = 0; j < TX; j++) w0m[j] = W0s[tm * NX + j * NG + g];
+#pragma unroll
+  for (int i = 0; i < TT; i++) {
+    const int row = (t0 + i) * NX;
+    const double2 fL = F[row + (TX - 1) * NG + gl];    // f(t, x0-1)
+    const double2 fR = F[row + gr];                    // f(t, x0+TX)
+    double2 w1m = W1s[row + (TX - 1) * NG + gl];       // W1(t, x0-1): slides along the row
+#pragma unroll
+    for (int j = 0; j < TX; j++) {
+      const double2 w0c = W0s[row + j * NG + g];
+      const double2 w1c = W1s[row + j * NG + g];
+      const double2 up = (i == TT - 1) ? F[te * NX + j * NG + g] : f[(i + 1) % TT][j];
+      const double2 dn = (i == 0) ? F[tm * NX + j * NG + g] : f[(i + TT - 1) % TT][j];
+      const double2 rt = (j == TX - 1) ? fR : f[i][(j + 1) % TX];
+      const double2 lf = (j == 0) ? fL : f[i][(j + TX - 1) % TX];
+      // m f(n) + af W0(n) f(n+t) - ab conj(W0(n-t)) f(n-t) + W1(n) f(n+x) - conj(W1(n-x)) f(n-x)  (hmc.c:137-180)
+      double2 o = make_double2(m * f[i][j].x, m * f[i][j].y);
+      if (HAS_MU) {
+        hop_acc<SF>(o, make_double2(w0c.x * af, w0c.y * af), up);
+        hopc_acc<SB>(o, make_double2(w0m[j].x * ab, w0m[j].y * ab), dn);
+      } else {
+        hop_acc<SF>(o, w0c, up);
+        hopc_acc<SB>(o, w0m[j], dn);
+      }
+      hop_acc<SF>(o, w1c, rt);
+      hopc_acc<SB>(o, w1m, lf);
+      out[i][j] = o;
+      w0m[j] = w0c;
+      w1m = w1c;
+    }
   }
 }
 
-template <int NT, int NX, int TS, bool DAG>
-__global__ void __launch_bounds__((NT / TS) * NX, (512 / ((NT / TS) * NX)) > 0 ? (512 / ((NT / TS) * NX)) : 1)
+template <int NT, int NX, int TX, int TT>
+struct ResidentCfg {
+  static constexpr int V = NT * NX;
+  static constexpr int NTHREADS = (NT / TT) * (NX / TX);
+  static constexpr int NWARPS = NTHREADS / 32;
+  static constexpr int REGS = (TX * TT >= 16) ? 255 : 128;
+  static constexpr int MINBLOCKS_RAW = 65536 / (NTHREADS * (REGS + 1));
+  static constexpr int MINBLOCKS = MINBLOCKS_RAW < 1 ? 1 : (MINBLOCKS_RAW > 16 ? 16 : MINBLOCKS_RAW);
+  static constexpr size_t SMEM = (size_t)V * 48 + 64 * sizeof(double);
+};
+
+template <int NT, int NX, int TX, int TT, bool DAG, bool HAS_MU>
+__global__ void __launch_bounds__(ResidentCfg<NT, NX, TX, TT>::NTHREADS, ResidentCfg<NT, NX, TX, TT>::MINBLOCKS)
 resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
                    const double2 *__restrict__ W0g, const double2 *__restrict__ W1g,
                    const double *__restrict__ mass, const double *__restrict__ emu,
                    const double *__restrict__ emmu, double2 *__restrict__ xw, const TbCgState s, const int C) {
-  constexpr int V = NT * NX;
-  constexpr int NTHREADS = (NT / TS) * NX;
-  constexpr int NWARPS = NTHREADS / 32;
+  using Cfg = ResidentCfg<NT, NX, TX, TT>;
+  constexpr int V = Cfg::V, NTHREADS = Cfg::NTHREADS, NWARPS = Cfg::NWARPS, NG = NX / TX;
+  static_assert(NTHREADS % 32 == 0, "a CTA must be whole warps");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *F = reinterpret_cast<double2 *>(smem_raw);
   double2 *W0s = F + V;
@@ -90,27 +138,33 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
 
   const int c = blockIdx.x;
   const int tid = threadIdx.x;
-  const int x = tid % NX;
-  const int t0 = (tid / NX) * TS;
+  const int g = tid % NG;            // x-group: the tile covers x in [g*TX, g*TX+TX)
+  const int t0 = (tid / NG) * TT;    // and t in [t0, t0+TT)
   const double m = mass[c];
   const double e_p = emu[c], e_m = emmu[c];
 
-  // links and source: device layout [site][chain] -> on-chip
+  // links: device layout [site][chain] -> shared memory
   for (int k = tid; k < V; k += NTHREADS) {
-    W0s[k] = W0g[(size_t)k * C + c];
-    W1s[k] = W1g[(size_t)k * C + c];
+    const int t = k / NX, x = k % NX;
+    W0s[sidx<NX, TX>(t, x)] = W0g[(size_t)k * C + c];
+    W1s[sidx<NX, TX>(t, x)] = W1g[(size_t)k * C + c];
   }
-  double2 r[TS], p[TS];
+  double2 r[TT][TX], p[TT][TX];
+  double2 *xwc = xw + (size_t)c * V;   // chain-major workspace, indexed like shared memory
   double rr = 0.0;
 #pragma unroll
-  for (int i = 0; i < TS; i++) {
-    const int k = (t0 + i) * NX + x;
-    r[i] = bsrc[(size_t)k * C + c];
-    p[i] = r[i];
-    rr += r[i].x * r[i].x + r[i].y * r[i].y;
-    F[k] = p[i];
-    xw[(size_t)c * V + k] = make_double2(0.0, 0.0);  // hmc.c:351
-  }
+  for (int i = 0; i < TT; i++)
+#pragma unroll
+    for (int j = 0; j < TX; j++) {
+      const int k = (t0 + i) * NX + g * TX + j;
+      const int ks = (t0 + i) * NX + j * NG + g;
+      r[i][j] = bsrc[(size_t)k * C + c];
+      p[i][j] = r[i][j];
+      rr = fma(r[i][j].x, r[i][j].x, rr);
+      rr = fma(r[i][j].y, r[i][j].y, rr);
+      F[ks] = p[i][j];
+      xwc[ks] = make_double2(0.0, 0.0);  // hmc.c:351
+    }
   rr = block_sum<NWARPS>(rr, scrA);   // hmc.c:354-356
   const double rr_init = rr;
   double rr_old = rr;
@@ -121,40 +175,52 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
     status = TB_CG_ZERO_SOURCE;
   } else {
     for (int k = 1; k < s.max_iter; k++) {  // hmc.c:364
-      double2 mp[TS], q[TS];
-      column_apply<NT, NX, TS, false>(p, mp, F, W0s, W1s, t0, x, m, e_p, e_m);   // Mp = M p, hmc.c:366
+      double2 mp[TT][TX], q[TT][TX];
+      tile_apply<NT, NX, TX, TT, false, HAS_MU>(p, mp, F, W0s, W1s, t0, g, m, e_p, e_m);   // Mp = M p, hmc.c:366
       __syncthreads();  // everyone has read p from F
 #pragma unroll
-      for (int i = 0; i < TS; i++) F[(t0 + i) * NX + x] = mp[i];
+      for (int i = 0; i < TT; i++)
+#pragma unroll
+        for (int j = 0; j < TX; j++) F[(t0 + i) * NX + j * NG + g] = mp[i][j];
       __syncthreads();
       // q = M~ Mp, hmc.c:367 (M^dagger swaps the roles of e^{mu} and e^{-mu})
-      column_apply<NT, NX, TS, DAG>(mp, q, F, W0s, W1s, t0, x, m, DAG ? e_m : e_p, DAG ? e_p : e_m);
+      tile_apply<NT, NX, TX, TT, DAG, HAS_MU>(mp, q, F, W0s, W1s, t0, g, m, DAG ? e_m : e_p, DAG ? e_p : e_m);
       double pq = 0.0;
 #pragma unroll
-      for (int i = 0; i < TS; i++) pq += p[i].x * q[i].x + p[i].y * q[i].y;   // hmc.c:368-370
+      for (int i = 0; i < TT; i++)
+#pragma unroll
+        for (int j = 0; j < TX; j++) {   // hmc.c:368-370
+          pq = fma(p[i][j].x, q[i][j].x, pq);
+          pq = fma(p[i][j].y, q[i][j].y, pq);
+        }
       pq = block_sum<NWARPS>(pq, scrB);
       const double a = rr_old / pq;   // hmc.c:371
       rr = 0.0;
 #pragma unroll
-      for (int i = 0; i < TS; i++) {
-        double2 *xk = &xw[(size_t)c * V + (t0 + i) * NX + x];
-        atomicAdd(&xk->x, a * p[i].x);   // x += a p, hmc.c:372-373 (RED.ADD at L2, one writer per address)
-        atomicAdd(&xk->y, a * p[i].y);
-        r[i].x -= a * q[i].x;            // hmc.c:374-375
-        r[i].y -= a * q[i].y;
-        rr += r[i].x * r[i].x + r[i].y * r[i].y;   // hmc.c:377-379
-      }
+      for (int i = 0; i < TT; i++)
+#pragma unroll
+        for (int j = 0; j < TX; j++) {
+          double2 *xk = &xwc[(t0 + i) * NX + j * NG + g];
+          atomicAdd(&xk->x, a * p[i][j].x);   // x += a p, hmc.c:372-373 (RED.ADD at L2, one writer per address)
+          atomicAdd(&xk->y, a * p[i][j].y);
+          r[i][j].x = fma(-a, q[i][j].x, r[i][j].x);   // hmc.c:374-375
+          r[i][j].y = fma(-a, q[i][j].y, r[i][j].y);
+          rr = fma(r[i][j].x, r[i][j].x, rr);          // hmc.c:377-379
+          rr = fma(r[i][j].y, r[i][j].y, rr);
+        }
       rr = block_sum<NWARPS>(rr, scrA);
       iters = k;
       if (rr < s.accuracy) { status = TB_CG_CONVERGED; break; }                                        // hmc.c:381
       if (!(rr == rr) || rr / rr_init > TB_DIVERGENCE_RATIO) { status = TB_CG_DIVERGED; break; }      // hmc.c:383
       const double be = rr / rr_old;   // hmc.c:390
 #pragma unroll
-      for (int i = 0; i < TS; i++) {
-        p[i].x = r[i].x + be * p[i].x;   // hmc.c:391-392
-        p[i].y = r[i].y + be * p[i].y;
-        F[(t0 + i) * NX + x] = p[i];     // all reads of Mp finished before the pq reduction's barrier
-      }
+      for (int i = 0; i < TT; i++)
+#pragma unroll
+        for (int j = 0; j < TX; j++) {
+          p[i][j].x = fma(be, p[i][j].x, r[i][j].x);   // hmc.c:391-392
+          p[i][j].y = fma(be, p[i][j].y, r[i][j].y);
+          F[(t0 + i) * NX + j * NG + g] = p[i][j];     // all reads of Mp finished before the pq reduction's barrier
+        }
       rr_old = rr;
       __syncthreads();
     }
@@ -163,10 +229,12 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
   __threadfence();
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < TS; i++) {
-    const int k = (t0 + i) * NX + x;
-    xout[(size_t)k * C + c] = __ldcg(&xw[(size_t)c * V + k]);
-  }
+  for (int i = 0; i < TT; i++)
+#pragma unroll
+    for (int j = 0; j < TX; j++) {
+      const int k = (t0 + i) * NX + g * TX + j;
+      xout[(size_t)k * C + c] = __ldcg(&xwc[(t0 + i) * NX + j * NG + g]);
+    }
   if (tid == 0) {
     s.status[c] = status;
     s.iters[c] = iters;
@@ -176,16 +244,17 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
   }
 }
 
-template <int NT, int NX, int TS>
+template <int NT, int NX, int TX, int TT>
 int launch_resident(tb_ctx *ctx, const double2 *b, double2 *x) {
-  constexpr int V = NT * NX;
-  constexpr int NTHREADS = (NT / TS) * NX;
-  const size_t smem = (size_t)V * 48 + 64 * sizeof(double);
+  using Cfg = ResidentCfg<NT, NX, TX, TT>;
   const bool dag = tb_conj_is_dagger(ctx);
-  auto kern = dag ? resident_cg_kernel<NT, NX, TS, true> : resident_cg_kernel<NT, NX, TS, false>;
-  TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<ctx->C, NTHREADS, smem, ctx->stream>>>(b, x, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu,
-                                                ctx->xw, ctx->cg, ctx->C);
+  auto kern = dag ? (ctx->has_mu ? resident_cg_kernel<NT, NX, TX, TT, true, true>
+                                 : resident_cg_kernel<NT, NX, TX, TT, true, false>)
+                  : (ctx->has_mu ? resident_cg_kernel<NT, NX, TX, TT, false, true>
+                                 : resident_cg_kernel<NT, NX, TX, TT, false, false>);
+  TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  kern<<<ctx->C, Cfg::NTHREADS, Cfg::SMEM, ctx->stream>>>(b, x, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu,
+                                                         ctx->d_emmu, ctx->xw, ctx->cg, ctx->C);
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
   return TB_OK;
@@ -197,16 +266,27 @@ bool tb_resident_supported(const tb_ctx *ctx) {
   return ctx->nt == ctx->nx && (ctx->nt == 16 || ctx->nt == 32 || ctx->nt == 64);
 }
 
-// One kernel launch per solve.
+// One kernel launch per solve.  The tile shape per thread is a tuning knob (tb_set_tuning rows_per_thread):
+// 0/44 = 4x4 sites (default), 18 = 1x8, 28 = 2x8, 24 = 2x4.
 int tb_run_cg_resident(tb_ctx *ctx, const double2 *b, double2 *x) {
   if (b == x) {
     tb_set_error("tb_run_cg_resident: in-place solve is not supported");
     return TB_EINVAL;
   }
+  const int shape = ctx->tune_tt;
   switch (ctx->nt) {
-    case 16: return launch_resident<16, 16, 8>(ctx, b, x);
-    case 32: return launch_resident<32, 32, 8>(ctx, b, x);
-    case 64: return launch_resident<64, 64, 8>(ctx, b, x);
+    case 16:
+      if (shape == 18) return launch_resident<16, 16, 1, 8>(ctx, b, x);
+      return launch_resident<16, 16, 2, 4>(ctx, b, x);
+    case 32:
+      if (shape == 18) return launch_resident<32, 32, 1, 8>(ctx, b, x);
+      if (shape == 28) return launch_resident<32, 32, 2, 8>(ctx, b, x);
+      return launch_resident<32, 32, 4, 4>(ctx, b, x);
+    case 64:
+      if (shape == 18) return launch_resident<64, 64, 1, 8>(ctx, b, x);
+      if (shape == 28) return launch_resident<64, 64, 2, 8>(ctx, b, x);
+      if (shape == 24) return launch_resident<64, 64, 2, 4>(ctx, b, x);
+      return launch_resident<64, 64, 4, 4>(ctx, b, x);
     default: tb_set_error("resident solver: unsupported lattice %dx%d", ctx->nt, ctx->nx); return TB_EINVAL;
   }
 }

@@ -49,10 +49,12 @@ def probe(nt, nx, C, m, rows=0, chunk=0, solver=0, reps=20, max_iter=100000):
     info = ctx.cg_result()
     ms = ctx.last_solve_ms
     its = float(info.iters.mean())
-    out.update({"cg_ms": round(ms, 3), "iters_mean": its, "iters_max": int(info.iters.max()),
-                "us_per_iter": round(ms * 1e3 / max(info.iters.max(), 1), 2),
-                "cg_GBs": round(288 * sites * info.iters.max() / ms / 1e6, 1),
-                "cg_frac": round(288 * sites * info.iters.max() / ms / 1e6 / PEAK, 3),
+    imax = int(info.iters.max())
+    isum = float(info.iters.astype(np.int64).sum())
+    out.update({"cg_ms": round(ms, 3), "iters_mean": its, "iters_max": imax,
+                "us_per_iter": round(ms * 1e3 / max(imax, 1), 2),
+                "cg_GBs": round(288.0 * nt * nx * isum / ms / 1e6, 1),
+                "cg_frac": round(288.0 * nt * nx * isum / ms / 1e6 / PEAK, 3),
                 "status": np.bincount(info.status, minlength=4).tolist()})
     ctx.close()
     return out
