@@ -116,6 +116,7 @@ extern "C" int tb_create(tb_ctx **out, int nt, int nx, int nchains, int mode, in
   A_(ctx->r, n) A_(ctx->p, n) A_(ctx->Mp, n) A_(ctx->q, n) A_(ctx->xw, n) A_(ctx->tmp, n)
   A_(ctx->vin, n) A_(ctx->vout, n)
   A_(ctx->stage, 2 * n)
+  A_(ctx->stage_x, n)
 #undef A_
   if (rc == TB_OK) rc = alloc_cg_state(ctx);
   if (rc == TB_OK) {
@@ -134,6 +135,17 @@ extern "C" int tb_create(tb_ctx **out, int nt, int nx, int nchains, int mode, in
     cudaEventCreate(&ctx->ev1);
     cudaEventCreateWithFlags(&ctx->ev_flag[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_flag[1], cudaEventDisableTiming);
+    // host-buffer pipeline: chains are processed in nsub sub-batches on their own streams
+    const char *es = getenv("TB_SUBBATCHES");
+    ctx->nsub = es ? atoi(es) : (ctx->C >= 128 ? 4 : (ctx->C >= 32 ? 2 : 1));
+    if (ctx->nsub < 1) ctx->nsub = 1;
+    if (ctx->nsub > TB_MAX_SUB) ctx->nsub = TB_MAX_SUB;
+    if (ctx->nsub > ctx->C) ctx->nsub = ctx->C;
+    cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
+    for (int s = 0; s < ctx->nsub; s++) {
+      cudaStreamCreateWithFlags(&ctx->sub_stream[s], cudaStreamNonBlocking);
+      cudaEventCreateWithFlags(&ctx->sub_done[s], cudaEventDisableTiming);
+    }
     const double one = 1.0, zero = 0.0;
     rc = tb_set_params(ctx, &one, &zero, 1);
   }
@@ -149,9 +161,14 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
   if (!ctx) return TB_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  for (int s = 0; s < ctx->nsub; s++) {
+    if (ctx->sub_stream[s]) { cudaStreamSynchronize(ctx->sub_stream[s]); cudaStreamDestroy(ctx->sub_stream[s]); }
+    if (ctx->sub_done[s]) cudaEventDestroy(ctx->sub_done[s]);
+  }
+  if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   invalidate_graph(ctx);
   void *dev[] = {ctx->d_mass, ctx->d_emu, ctx->d_emmu, ctx->W0, ctx->W1, ctx->Adev, ctx->r, ctx->p, ctx->Mp,
-                 ctx->q, ctx->xw, ctx->tmp, ctx->vin, ctx->vout, ctx->stage, ctx->cg.rr_old, ctx->cg.active,
+                 ctx->q, ctx->xw, ctx->tmp, ctx->vin, ctx->vout, ctx->stage, ctx->stage_x, ctx->cg.rr_old, ctx->cg.active,
                  ctx->cg.partial, ctx->cg.ticket};
   for (void *p : dev)
     if (p) cudaFree(p);
@@ -170,10 +187,43 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
   return TB_OK;
 }
 
+// ---- sub-batch streams (host-buffer pipeline) -----------------------------------------------------------
+static void sub_range(const tb_ctx *ctx, int s, int *c0, int *n) {
+  const int per = (ctx->C + ctx->nsub - 1) / ctx->nsub;
+  *c0 = s * per;
+  int m = ctx->C - *c0;
+  *n = m < 0 ? 0 : (m < per ? m : per);
+}
+
+// sub-streams start after everything already queued on the context stream
+static int fork_subs(tb_ctx *ctx) {
+  TB_CUDA(cudaEventRecord(ctx->fork_ev, ctx->stream));
+  for (int s = 0; s < ctx->nsub; s++) TB_CUDA(cudaStreamWaitEvent(ctx->sub_stream[s], ctx->fork_ev, 0));
+  ctx->sub_pending = true;
+  return TB_OK;
+}
+
+// the context stream continues after everything queued on the sub-streams (no-op when nothing is pending)
+static int join_subs(tb_ctx *ctx) {
+  if (!ctx->sub_pending) return TB_OK;
+  for (int s = 0; s < ctx->nsub; s++) {
+    TB_CUDA(cudaEventRecord(ctx->sub_done[s], ctx->sub_stream[s]));
+    TB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->sub_done[s], 0));
+  }
+  ctx->sub_pending = false;
+  return TB_OK;
+}
+
+static int sync_all(tb_ctx *ctx) {
+  TB_CHECK(join_subs(ctx));
+  TB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return TB_OK;
+}
+
 extern "C" int tb_set_stream(tb_ctx *ctx, void *cuda_stream) {
   if (!ctx) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
-  TB_CUDA(cudaStreamSynchronize(ctx->stream));
+  TB_CHECK(sync_all(ctx));
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   ctx->stream = (cudaStream_t)cuda_stream;
   ctx->own_stream = false;
@@ -182,8 +232,7 @@ extern "C" int tb_set_stream(tb_ctx *ctx, void *cuda_stream) {
 
 extern "C" int tb_synchronize(tb_ctx *ctx) {
   if (!ctx) return TB_EINVAL;
-  TB_CUDA(cudaStreamSynchronize(ctx->stream));
-  return TB_OK;
+  return sync_all(ctx);
 }
 
 extern "C" int tb_set_params(tb_ctx *ctx, const double *m, const double *mu, int n) {
@@ -204,6 +253,7 @@ extern "C" int tb_set_params(tb_ctx *ctx, const double *m, const double *mu, int
     buf[cp + c] = exp(mu[k]);       // hmc.c:127
     buf[2 * cp + c] = exp(-mu[k]);  // hmc.c:128
   }
+  join_subs(ctx);
   cudaError_t e = cudaStreamSynchronize(ctx->stream);
   if (e == cudaSuccess) e = cudaMemcpy(ctx->d_mass, buf, cp * sizeof(double), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) e = cudaMemcpy(ctx->d_emu, buf + cp, cp * sizeof(double), cudaMemcpyHostToDevice);
@@ -226,7 +276,7 @@ extern "C" int tb_set_cg(tb_ctx *ctx, double accuracy, int max_iter) {
 
 extern "C" int tb_set_tuning(tb_ctx *ctx, int rows_per_thread, int iters_per_launch, int solver) {
   if (!ctx) return TB_EINVAL;
-  TB_CUDA(cudaStreamSynchronize(ctx->stream));
+  TB_CHECK(sync_all(ctx));
   ctx->tune_tt = rows_per_thread;
   ctx->tune_chunk = iters_per_launch;
   ctx->tune_solver = solver;
@@ -250,18 +300,21 @@ extern "C" double tb_last_solve_ms(const tb_ctx *ctx) { return ctx ? ctx->last_s
 extern "C" int tb_pack_dev(tb_ctx *ctx, const double *d_canonical, double *d_vec) {
   if (!ctx || !d_canonical || !d_vec) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(join_subs(ctx));
   return tb_launch_pack(ctx, d_canonical, (double2 *)d_vec);
 }
 
 extern "C" int tb_unpack_dev(tb_ctx *ctx, const double *d_vec, double *d_canonical) {
   if (!ctx || !d_canonical || !d_vec) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(join_subs(ctx));
   return tb_launch_unpack(ctx, (const double2 *)d_vec, d_canonical);
 }
 
 extern "C" int tb_set_gauge_dev(tb_ctx *ctx, const double *d_A_canonical) {
   if (!ctx || !d_A_canonical) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(join_subs(ctx));
   TB_CHECK(tb_launch_pack(ctx, d_A_canonical, ctx->Adev));
   TB_CHECK(tb_launch_links(ctx, (const double *)ctx->Adev));
   ctx->have_gauge = true;
@@ -282,6 +335,7 @@ extern "C" int tb_apply_dev(tb_ctx *ctx, int op, const double *d_in, double *d_o
     return TB_EINVAL;
   }
   TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(join_subs(ctx));
   TB_CHECK(need_gauge(ctx));
   const double2 *in = (const double2 *)d_in;
   double2 *out = (double2 *)d_out;
@@ -317,6 +371,7 @@ static int run_cg(tb_ctx *ctx, const double2 *b, double2 *x) {
 extern "C" int tb_cg_dev(tb_ctx *ctx, const double *d_b, double *d_x) {
   if (!ctx || !d_b || !d_x) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(join_subs(ctx));
   TB_CHECK(need_gauge(ctx));
   return run_cg(ctx, (const double2 *)d_b, (double2 *)d_x);
 }
@@ -324,6 +379,7 @@ extern "C" int tb_cg_dev(tb_ctx *ctx, const double *d_b, double *d_x) {
 extern "C" int tb_invert_dev(tb_ctx *ctx, const double *d_v, double *d_x) {
   if (!ctx || !d_v || !d_x) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(join_subs(ctx));
   TB_CHECK(need_gauge(ctx));
   // fm_invert_cg, hmc.c:408-414
   TB_CHECK(tb_launch_dslash(ctx, tb_conj_is_dagger(ctx), (const double2 *)d_v, ctx->tmp, false));
@@ -333,6 +389,7 @@ extern "C" int tb_invert_dev(tb_ctx *ctx, const double *d_v, double *d_x) {
 extern "C" int tb_cg_result(tb_ctx *ctx, int *status, int *iters, double *rr) {
   if (!ctx) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(join_subs(ctx));
   const size_t c = ctx->C;
   cudaStream_t st = ctx->stream;
   TB_CUDA(cudaMemcpyAsync(ctx->h_status, ctx->cg.status, c * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -348,6 +405,7 @@ extern "C" int tb_cg_result(tb_ctx *ctx, int *status, int *iters, double *rr) {
 extern "C" int tb_re_dot_dev(tb_ctx *ctx, const double *d_a, const double *d_b, double *out_host) {
   if (!ctx || !d_a || !d_b || !out_host) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(join_subs(ctx));
   TB_CHECK(tb_launch_dot(ctx, (const double2 *)d_a, (const double2 *)d_b, ctx->cg.dot));
   TB_CUDA(cudaMemcpyAsync(ctx->h_rr, ctx->cg.dot, ctx->C * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   TB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -356,34 +414,54 @@ extern "C" int tb_re_dot_dev(tb_ctx *ctx, const double *d_a, const double *d_b, 
 }
 
 // ---- host-buffer entry points ---------------------------------------------------------------------------
+// Chains are processed in ctx->nsub sub-batches, each on its own stream: H2D -> re-layout -> kernels ->
+// re-layout -> D2H of one sub-batch overlap the copies and kernels of the others (pinned host buffers make the
+// copies asynchronous; pageable ones still work, without overlap).
 
 static int upload_vec(tb_ctx *ctx, const double *host, double2 *d_vec) {
-  const size_t bytes = ctx->nsite * sizeof(double2);
-  if (ctx->C == 1) {
-    TB_CUDA(cudaMemcpyAsync(d_vec, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    return TB_OK;
+  TB_CHECK(fork_subs(ctx));
+  for (int s = 0; s < ctx->nsub; s++) {
+    int c0, n;
+    sub_range(ctx, s, &c0, &n);
+    if (n == 0) continue;
+    const size_t off = (size_t)c0 * ctx->V;  // double2 elements
+    double2 *stg = (double2 *)ctx->stage + off;
+    double2 *dst = ctx->C == 1 ? d_vec : stg;
+    TB_CUDA(cudaMemcpyAsync(dst, (const double2 *)host + off, (size_t)n * ctx->V * sizeof(double2),
+                            cudaMemcpyHostToDevice, ctx->sub_stream[s]));
+    if (ctx->C > 1) TB_CHECK(tb_launch_pack_slice(ctx, stg, d_vec, c0, n, ctx->sub_stream[s]));
   }
-  TB_CUDA(cudaMemcpyAsync(ctx->stage, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
-  return tb_launch_pack(ctx, ctx->stage, d_vec);
+  return TB_OK;
 }
 
+// queue re-layout + D2H of every sub-batch behind whatever is queued on its stream, then wait for all
 static int download_vec(tb_ctx *ctx, const double2 *d_vec, double *host) {
-  const size_t bytes = ctx->nsite * sizeof(double2);
-  if (ctx->C == 1) {
-    TB_CUDA(cudaMemcpyAsync(host, d_vec, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  } else {
-    TB_CHECK(tb_launch_unpack(ctx, d_vec, ctx->stage));
-    TB_CUDA(cudaMemcpyAsync(host, ctx->stage, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  if (!ctx->sub_pending) TB_CHECK(fork_subs(ctx));
+  for (int s = 0; s < ctx->nsub; s++) {
+    int c0, n;
+    sub_range(ctx, s, &c0, &n);
+    if (n == 0) continue;
+    const size_t off = (size_t)c0 * ctx->V;
+    const double2 *src = d_vec;
+    if (ctx->C > 1) {
+      TB_CHECK(tb_launch_unpack_slice(ctx, d_vec, ctx->stage_x + off, c0, n, ctx->sub_stream[s]));
+      src = ctx->stage_x + off;
+    }
+    TB_CUDA(cudaMemcpyAsync((double2 *)host + off, src, (size_t)n * ctx->V * sizeof(double2),
+                            cudaMemcpyDeviceToHost, ctx->sub_stream[s]));
   }
-  TB_CUDA(cudaStreamSynchronize(ctx->stream));
-  return TB_OK;
+  return sync_all(ctx);
 }
 
 extern "C" int tb_set_gauge(tb_ctx *ctx, const double *A_host) {
   if (!ctx || !A_host) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
   TB_CHECK(upload_vec(ctx, A_host, ctx->Adev));
-  TB_CHECK(tb_launch_links(ctx, (const double *)ctx->Adev));
+  for (int s = 0; s < ctx->nsub; s++) {
+    int c0, n;
+    sub_range(ctx, s, &c0, &n);
+    if (n) TB_CHECK(tb_launch_links_slice(ctx, ctx->Adev, c0, n, ctx->sub_stream[s]));
+  }
   ctx->have_gauge = true;
   return TB_OK;
 }
@@ -393,29 +471,51 @@ extern "C" int tb_apply(tb_ctx *ctx, int op, const double *in_host, double *out_
   TB_CUDA(cudaSetDevice(ctx->device));
   TB_CHECK(need_gauge(ctx));
   TB_CHECK(upload_vec(ctx, in_host, ctx->vin));
-  TB_CHECK(tb_apply_dev(ctx, op, (const double *)ctx->vin, (double *)ctx->vout));
+  TB_CHECK(tb_apply_dev(ctx, op, (const double *)ctx->vin, (double *)ctx->vout));  // joins the sub-streams
   return download_vec(ctx, ctx->vout, out_host);
+}
+
+// the solve of a sub-batch starts as soon as ITS links and sources are on the device
+static int solve_host(tb_ctx *ctx, bool with_conj, const double *b_host, double *x_host, int *status, int *iters,
+                      double *rr) {
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(need_gauge(ctx));
+  const bool resident = ctx->tune_solver != 1 && tb_resident_supported(ctx);
+  if (ctx->tune_solver == 2 && !resident) {
+    tb_set_error("resident solver requested but %dx%d is not supported", ctx->nt, ctx->nx);
+    return TB_EINVAL;
+  }
+  if (!resident || with_conj) {
+    TB_CHECK(upload_vec(ctx, b_host, ctx->vin));
+    if (with_conj) TB_CHECK(tb_invert_dev(ctx, (const double *)ctx->vin, (double *)ctx->vout));
+    else TB_CHECK(tb_cg_dev(ctx, (const double *)ctx->vin, (double *)ctx->vout));
+    TB_CHECK(download_vec(ctx, ctx->vout, x_host));
+  } else {
+    TB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    TB_CHECK(upload_vec(ctx, b_host, ctx->vin));
+    for (int s = 0; s < ctx->nsub; s++) {
+      int c0, n;
+      sub_range(ctx, s, &c0, &n);
+      if (n) TB_CHECK(tb_run_cg_resident_slice(ctx, ctx->vin, ctx->vout, c0, n, ctx->sub_stream[s]));
+    }
+    TB_CHECK(download_vec(ctx, ctx->vout, x_host));
+    TB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    TB_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    TB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_solve_ms = ms;
+  }
+  if (status || iters || rr) TB_CHECK(tb_cg_result(ctx, status, iters, rr));
+  return TB_OK;
 }
 
 extern "C" int tb_cg(tb_ctx *ctx, const double *b_host, double *x_host, int *status, int *iters, double *rr) {
   if (!ctx || !b_host || !x_host) return TB_EINVAL;
-  TB_CUDA(cudaSetDevice(ctx->device));
-  TB_CHECK(need_gauge(ctx));
-  TB_CHECK(upload_vec(ctx, b_host, ctx->vin));
-  TB_CHECK(run_cg(ctx, ctx->vin, ctx->vout));
-  TB_CHECK(download_vec(ctx, ctx->vout, x_host));
-  if (status || iters || rr) TB_CHECK(tb_cg_result(ctx, status, iters, rr));
-  return TB_OK;
+  return solve_host(ctx, false, b_host, x_host, status, iters, rr);
 }
 
 extern "C" int tb_invert(tb_ctx *ctx, const double *v_host, double *x_host, int *status, int *iters,
                          double *rr) {
   if (!ctx || !v_host || !x_host) return TB_EINVAL;
-  TB_CUDA(cudaSetDevice(ctx->device));
-  TB_CHECK(need_gauge(ctx));
-  TB_CHECK(upload_vec(ctx, v_host, ctx->vin));
-  TB_CHECK(tb_invert_dev(ctx, (const double *)ctx->vin, (double *)ctx->vout));
-  TB_CHECK(download_vec(ctx, ctx->vout, x_host));
-  if (status || iters || rr) TB_CHECK(tb_cg_result(ctx, status, iters, rr));
-  return TB_OK;
+  return solve_host(ctx, true, v_host, x_host, status, iters, rr);
 }

@@ -12,6 +12,7 @@
 
 #define TB_NUM_SMS_B200 148
 #define TB_MAX_BLOCK 256
+#define TB_MAX_SUB 8
 #define TB_DIVERGENCE_RATIO 1e10 /* hmc.c:383 */
 
 void tb_set_error(const char *fmt, ...);
@@ -84,6 +85,12 @@ struct tb_ctx {
   cudaGraphExec_t cg_graph;
   int cg_graph_chunk;
   cudaEvent_t ev0, ev1, ev_flag[2];
+  // host-buffer pipeline: sub-batches of chains on their own streams (H2D -> pack -> solve -> unpack -> D2H)
+  cudaStream_t sub_stream[TB_MAX_SUB];
+  cudaEvent_t sub_done[TB_MAX_SUB], fork_ev;
+  int nsub;
+  bool sub_pending;  // work queued on the sub-streams that the context stream has not joined yet
+  double2 *stage_x;  // second canonical staging buffer (results)
   double last_solve_ms;
   long long launches;
 };
@@ -97,6 +104,10 @@ int tb_launch_unpack(tb_ctx *ctx, const double2 *d_vec, double *d_canonical);
 int tb_launch_dslash(tb_ctx *ctx, bool dagger, const double2 *in, double2 *out, bool masked);
 int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x);
 int tb_run_cg_resident(tb_ctx *ctx, const double2 *b, double2 *x);
+int tb_run_cg_resident_slice(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st);
+int tb_launch_links_slice(tb_ctx *ctx, const double2 *d_A_dev_layout, int c0, int n, cudaStream_t st);
+int tb_launch_pack_slice(tb_ctx *ctx, const double2 *d_canonical_slice, double2 *d_vec, int c0, int n, cudaStream_t st);
+int tb_launch_unpack_slice(tb_ctx *ctx, const double2 *d_vec, double2 *d_canonical_slice, int c0, int n, cudaStream_t st);
 bool tb_resident_supported(const tb_ctx *ctx);
 int tb_launch_dot(tb_ctx *ctx, const double2 *a, const double2 *b, double *d_out);
 

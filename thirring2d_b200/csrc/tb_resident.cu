@@ -7,7 +7,8 @@
 //   registers      r, p (persistent) and Mp, q (transient) for the TS sites of the thread's t-column
 //   shared memory  one exchange field F (p, then Mp: what the stencil neighbours read) 16 B/site
 //                  the two link fields W0, W1                                           32 B/site
-//   L2 (RED.ADD)   x += alpha p, fire-and-forget reductions into a chain-major workspace
+//   L2             x += alpha p as a 128-bit read-modify-write of a chain-major workspace (one owner thread per
+//                  element; loads issued ahead of the ||r||^2 barrier), 32 B/site/iteration
 //
 // 64^2: 48 B/site * 4096 = 192 KB of the 227 KB shared memory, one CTA of 512 threads per SM, 148 chains in
 // flight per B200.  HBM is touched only to load b and the links once and to store x once per solve.
@@ -125,7 +126,8 @@ __global__ void __launch_bounds__(ResidentCfg<NT, NX, TX, TT>::NTHREADS, Residen
 resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
                    const double2 *__restrict__ W0g, const double2 *__restrict__ W1g,
                    const double *__restrict__ mass, const double *__restrict__ emu,
-                   const double *__restrict__ emmu, double2 *__restrict__ xw, const TbCgState s, const int C) {
+                   const double *__restrict__ emmu, double2 *__restrict__ xw, const TbCgState s, const int C,
+                   const int c_first) {
   using Cfg = ResidentCfg<NT, NX, TX, TT>;
   constexpr int V = Cfg::V, NTHREADS = Cfg::NTHREADS, NWARPS = Cfg::NWARPS, NG = NX / TX;
   static_assert(NTHREADS % 32 == 0, "a CTA must be whole warps");
@@ -136,7 +138,7 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
   double *scrA = reinterpret_cast<double *>(W1s + V);
   double *scrB = scrA + 32;
 
-  const int c = blockIdx.x;
+  const int c = c_first + blockIdx.x;
   const int tid = threadIdx.x;
   const int g = tid % NG;            // x-group: the tile covers x in [g*TX, g*TX+TX)
   const int t0 = (tid / NG) * TT;    // and t in [t0, t0+TT)
@@ -163,13 +165,12 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
       rr = fma(r[i][j].x, r[i][j].x, rr);
       rr = fma(r[i][j].y, r[i][j].y, rr);
       F[ks] = p[i][j];
-      xwc[ks] = make_double2(0.0, 0.0);  // hmc.c:351
     }
   rr = block_sum<NWARPS>(rr, scrA);   // hmc.c:354-356
   const double rr_init = rr;
   double rr_old = rr;
   int status = TB_CG_MAXITER, iters = 0;
-  __syncthreads();  // F, links and the zeroed workspace are in place
+  __syncthreads();  // F and the links are in place
 
   if (rr_old < s.accuracy) {  // hmc.c:359-361
     status = TB_CG_ZERO_SOURCE;
@@ -200,15 +201,30 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
       for (int i = 0; i < TT; i++)
 #pragma unroll
         for (int j = 0; j < TX; j++) {
-          double2 *xk = &xwc[(t0 + i) * NX + j * NG + g];
-          atomicAdd(&xk->x, a * p[i][j].x);   // x += a p, hmc.c:372-373 (RED.ADD at L2, one writer per address)
-          atomicAdd(&xk->y, a * p[i][j].y);
           r[i][j].x = fma(-a, q[i][j].x, r[i][j].x);   // hmc.c:374-375
           r[i][j].y = fma(-a, q[i][j].y, r[i][j].y);
           rr = fma(r[i][j].x, r[i][j].x, rr);          // hmc.c:377-379
           rr = fma(r[i][j].y, r[i][j].y, rr);
         }
+      // x += a p (hmc.c:372-373): x lives in L2 (chain-major workspace, one owner thread per element); the
+      // loads are issued before the ||r||^2 reduction so that their latency hides behind its barrier
+      double2 xv[TT][TX];
+      if (k > 1) {
+#pragma unroll
+        for (int i = 0; i < TT; i++)
+#pragma unroll
+          for (int j = 0; j < TX; j++) xv[i][j] = __ldcg(&xwc[(t0 + i) * NX + j * NG + g]);
+      }
       rr = block_sum<NWARPS>(rr, scrA);
+#pragma unroll
+      for (int i = 0; i < TT; i++)
+#pragma unroll
+        for (int j = 0; j < TX; j++) {
+          double2 v = (k > 1) ? xv[i][j] : make_double2(0.0, 0.0);   // hmc.c:351: x0 = 0
+          v.x += a * p[i][j].x;
+          v.y += a * p[i][j].y;
+          __stcg(&xwc[(t0 + i) * NX + j * NG + g], v);
+        }
       iters = k;
       if (rr < s.accuracy) { status = TB_CG_CONVERGED; break; }                                        // hmc.c:381
       if (!(rr == rr) || rr / rr_init > TB_DIVERGENCE_RATIO) { status = TB_CG_DIVERGED; break; }      // hmc.c:383
@@ -225,15 +241,13 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
       __syncthreads();
     }
   }
-  // the RED.ADDs of this CTA must have landed before x is read back
-  __threadfence();
-  __syncthreads();
+  // every element of the workspace was written and is read back by the same thread
 #pragma unroll
   for (int i = 0; i < TT; i++)
 #pragma unroll
     for (int j = 0; j < TX; j++) {
       const int k = (t0 + i) * NX + g * TX + j;
-      xout[(size_t)k * C + c] = __ldcg(&xwc[(t0 + i) * NX + j * NG + g]);
+      xout[(size_t)k * C + c] = (iters > 0) ? __ldcg(&xwc[(t0 + i) * NX + j * NG + g]) : make_double2(0.0, 0.0);
     }
   if (tid == 0) {
     s.status[c] = status;
@@ -245,7 +259,7 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
 }
 
 template <int NT, int NX, int TX, int TT>
-int launch_resident(tb_ctx *ctx, const double2 *b, double2 *x) {
+int launch_resident(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st) {
   using Cfg = ResidentCfg<NT, NX, TX, TT>;
   const bool dag = tb_conj_is_dagger(ctx);
   auto kern = dag ? (ctx->has_mu ? resident_cg_kernel<NT, NX, TX, TT, true, true>
@@ -253,8 +267,8 @@ int launch_resident(tb_ctx *ctx, const double2 *b, double2 *x) {
                   : (ctx->has_mu ? resident_cg_kernel<NT, NX, TX, TT, false, true>
                                  : resident_cg_kernel<NT, NX, TX, TT, false, false>);
   TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-  kern<<<ctx->C, Cfg::NTHREADS, Cfg::SMEM, ctx->stream>>>(b, x, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu,
-                                                         ctx->d_emmu, ctx->xw, ctx->cg, ctx->C);
+  kern<<<n, Cfg::NTHREADS, Cfg::SMEM, st>>>(b, x, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu, ctx->xw,
+                                            ctx->cg, ctx->C, c0);
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
   return TB_OK;
@@ -266,9 +280,9 @@ bool tb_resident_supported(const tb_ctx *ctx) {
   return ctx->nt == ctx->nx && (ctx->nt == 16 || ctx->nt == 32 || ctx->nt == 64);
 }
 
-// One kernel launch per solve.  The tile shape per thread is a tuning knob (tb_set_tuning rows_per_thread):
-// 0/44 = 4x4 sites (default), 18 = 1x8, 28 = 2x8, 24 = 2x4.
-int tb_run_cg_resident(tb_ctx *ctx, const double2 *b, double2 *x) {
+// One kernel launch per (sub-)batch of chains [c0, c0+n).  The tile shape per thread is a tuning knob
+// (tb_set_tuning rows_per_thread): 0 = default (2x8 sites; 2x4 for 16^2), 44 = 4x4, 18 = 1x8, 28 = 2x8, 24 = 2x4.
+int tb_run_cg_resident_slice(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st) {
   if (b == x) {
     tb_set_error("tb_run_cg_resident: in-place solve is not supported");
     return TB_EINVAL;
@@ -276,17 +290,21 @@ int tb_run_cg_resident(tb_ctx *ctx, const double2 *b, double2 *x) {
   const int shape = ctx->tune_tt;
   switch (ctx->nt) {
     case 16:
-      if (shape == 18) return launch_resident<16, 16, 1, 8>(ctx, b, x);
-      return launch_resident<16, 16, 2, 4>(ctx, b, x);
+      if (shape == 18) return launch_resident<16, 16, 1, 8>(ctx, b, x, c0, n, st);
+      return launch_resident<16, 16, 2, 4>(ctx, b, x, c0, n, st);
     case 32:
-      if (shape == 18) return launch_resident<32, 32, 1, 8>(ctx, b, x);
-      if (shape == 28) return launch_resident<32, 32, 2, 8>(ctx, b, x);
-      return launch_resident<32, 32, 4, 4>(ctx, b, x);
+      if (shape == 18) return launch_resident<32, 32, 1, 8>(ctx, b, x, c0, n, st);
+      if (shape == 44) return launch_resident<32, 32, 4, 4>(ctx, b, x, c0, n, st);
+      return launch_resident<32, 32, 2, 8>(ctx, b, x, c0, n, st);
     case 64:
-      if (shape == 18) return launch_resident<64, 64, 1, 8>(ctx, b, x);
-      if (shape == 28) return launch_resident<64, 64, 2, 8>(ctx, b, x);
-      if (shape == 24) return launch_resident<64, 64, 2, 4>(ctx, b, x);
-      return launch_resident<64, 64, 4, 4>(ctx, b, x);
+      if (shape == 18) return launch_resident<64, 64, 1, 8>(ctx, b, x, c0, n, st);
+      if (shape == 44) return launch_resident<64, 64, 4, 4>(ctx, b, x, c0, n, st);
+      if (shape == 24) return launch_resident<64, 64, 2, 4>(ctx, b, x, c0, n, st);
+      return launch_resident<64, 64, 2, 8>(ctx, b, x, c0, n, st);
     default: tb_set_error("resident solver: unsupported lattice %dx%d", ctx->nt, ctx->nx); return TB_EINVAL;
   }
+}
+
+int tb_run_cg_resident(tb_ctx *ctx, const double2 *b, double2 *x) {
+  return tb_run_cg_resident_slice(ctx, b, x, 0, ctx->C, ctx->stream);
 }

@@ -326,37 +326,39 @@ __global__ void cg_reset_kernel(const TbGeom g, const TbCgState s) {
 // W0 = s0(t) 1/2 eta0(x) (cos A0, sin A0) ; W1 = s1(x) 1/2 (cos A1, sin A1); device layout in and out.
 // eta0 = (-1)^x (hmc.c:917-921), s = -1 on the wrap link (hmc.c:143-148,165-170).
 __global__ void links_kernel(const double2 *__restrict__ A, double2 *__restrict__ W0, double2 *__restrict__ W1,
-                             int nt, int nx, int C) {
-  const size_t n = (size_t)nt * nx * C;
-  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (size_t)gridDim.x * blockDim.x) {
-    const size_t site = k / C;
+                             int nt, int nx, int C, int c0, int n) {
+  const size_t total = (size_t)nt * nx * n;   // sites x chains of the slice [c0, c0+n)
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t site = i / n;
+    const size_t k = site * C + c0 + (i % n);
     const int x = (int)(site % nx);
     const int t = (int)(site / nx);
     const double2 a = A[k];
-    double s0, c0, s1, c1;
-    sincos(a.x, &s0, &c0);
+    double s0, c0v, s1, c1;
+    sincos(a.x, &s0, &c0v);
     sincos(a.y, &s1, &c1);
     double f0 = (x & 1) ? -0.5 : 0.5;
     if (t == nt - 1) f0 = -f0;
     const double f1 = (x == nx - 1) ? -0.5 : 0.5;
-    W0[k] = make_double2(f0 * c0, f0 * s0);
+    W0[k] = make_double2(f0 * c0v, f0 * s0);
     W1[k] = make_double2(f1 * c1, f1 * s1);
   }
 }
 
 // (C x V) double2 -> (V x C) double2 tiled transpose and its inverse.
-__global__ void transpose_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, int rows, int cols) {
-  // src[rows][cols] -> dst[cols][rows]
+__global__ void transpose_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, int rows, int cols,
+                                 size_t ld_src, size_t ld_dst) {
+  // src[r * ld_src + c], r < rows, c < cols   ->   dst[c * ld_dst + r]
   __shared__ double2 tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int r = r0 + i, c = c0 + threadIdx.x;
-    if (r < rows && c < cols) tile[i][threadIdx.x] = src[(size_t)r * cols + c];
+    if (r < rows && c < cols) tile[i][threadIdx.x] = src[(size_t)r * ld_src + c];
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int c = c0 + i, r = r0 + threadIdx.x;
-    if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][i];
+    if (r < rows && c < cols) dst[(size_t)c * ld_dst + r] = tile[threadIdx.x][i];
   }
 }
 
@@ -408,45 +410,59 @@ int tb_choose_geom(tb_ctx *ctx) {
   return TB_OK;
 }
 
-int tb_launch_links(tb_ctx *ctx, const double *d_A_dev_layout) {
-  const size_t n = ctx->nsite;
-  int blocks = (int)((n + 255) / 256);
+// Chain-slice variants: operate on chains [c0, c0+n) of the context on stream st (the host-buffer path
+// pipelines sub-batches of chains on separate streams).
+int tb_launch_links_slice(tb_ctx *ctx, const double2 *d_A_dev_layout, int c0, int n, cudaStream_t st) {
+  const size_t total = ctx->V * (size_t)n;
+  int blocks = (int)((total + 255) / 256);
   if (blocks > TB_NUM_SMS_B200 * 16) blocks = TB_NUM_SMS_B200 * 16;
-  links_kernel<<<blocks, 256, 0, ctx->stream>>>((const double2 *)d_A_dev_layout, ctx->W0, ctx->W1, ctx->nt,
-                                                ctx->nx, ctx->C);
+  links_kernel<<<blocks, 256, 0, st>>>(d_A_dev_layout, ctx->W0, ctx->W1, ctx->nt, ctx->nx, ctx->C, c0, n);
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
   return TB_OK;
+}
+
+// canonical slice [n chains][V] (contiguous) -> device layout columns [c0, c0+n) of d_vec[V][C]
+int tb_launch_pack_slice(tb_ctx *ctx, const double2 *d_canonical_slice, double2 *d_vec, int c0, int n,
+                         cudaStream_t st) {
+  if (ctx->C == 1) {
+    if ((const void *)d_canonical_slice != (const void *)d_vec)
+      TB_CUDA(cudaMemcpyAsync(d_vec, d_canonical_slice, ctx->nsite * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+    return TB_OK;
+  }
+  const int rows = n, cols = (int)ctx->V;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, st>>>(d_canonical_slice, d_vec + c0, rows, cols, ctx->V, (size_t)ctx->C);
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
+int tb_launch_unpack_slice(tb_ctx *ctx, const double2 *d_vec, double2 *d_canonical_slice, int c0, int n,
+                           cudaStream_t st) {
+  if (ctx->C == 1) {
+    if ((const void *)d_canonical_slice != (const void *)d_vec)
+      TB_CUDA(cudaMemcpyAsync(d_canonical_slice, d_vec, ctx->nsite * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+    return TB_OK;
+  }
+  const int rows = (int)ctx->V, cols = n;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
+  transpose_kernel<<<grid, block, 0, st>>>(d_vec + c0, d_canonical_slice, rows, cols, (size_t)ctx->C, ctx->V);
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
+int tb_launch_links(tb_ctx *ctx, const double *d_A_dev_layout) {
+  return tb_launch_links_slice(ctx, (const double2 *)d_A_dev_layout, 0, ctx->C, ctx->stream);
 }
 
 int tb_launch_pack(tb_ctx *ctx, const double *d_canonical, double2 *d_vec) {
-  if (ctx->C == 1) {
-    if ((const void *)d_canonical != (const void *)d_vec)
-      TB_CUDA(cudaMemcpyAsync(d_vec, d_canonical, ctx->nsite * sizeof(double2), cudaMemcpyDeviceToDevice,
-                              ctx->stream));
-    return TB_OK;
-  }
-  const int rows = ctx->C, cols = (int)ctx->V;
-  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-  transpose_kernel<<<grid, block, 0, ctx->stream>>>((const double2 *)d_canonical, d_vec, rows, cols);
-  ctx->launches++;
-  TB_CUDA(cudaGetLastError());
-  return TB_OK;
+  return tb_launch_pack_slice(ctx, (const double2 *)d_canonical, d_vec, 0, ctx->C, ctx->stream);
 }
 
 int tb_launch_unpack(tb_ctx *ctx, const double2 *d_vec, double *d_canonical) {
-  if (ctx->C == 1) {
-    if ((const void *)d_canonical != (const void *)d_vec)
-      TB_CUDA(cudaMemcpyAsync(d_canonical, d_vec, ctx->nsite * sizeof(double2), cudaMemcpyDeviceToDevice,
-                              ctx->stream));
-    return TB_OK;
-  }
-  const int rows = (int)ctx->V, cols = ctx->C;
-  dim3 grid((cols + 31) / 32, (rows + 31) / 32), block(32, 8);
-  transpose_kernel<<<grid, block, 0, ctx->stream>>>(d_vec, (double2 *)d_canonical, rows, cols);
-  ctx->launches++;
-  TB_CUDA(cudaGetLastError());
-  return TB_OK;
+  return tb_launch_unpack_slice(ctx, d_vec, (double2 *)d_canonical, 0, ctx->C, ctx->stream);
 }
 
 int tb_launch_dslash(tb_ctx *ctx, bool dagger, const double2 *in, double2 *out, bool masked) {
