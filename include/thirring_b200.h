@@ -113,6 +113,19 @@ int tb_cg_result(tb_ctx *ctx, int *status, int *iters, double *rr);
  * Replaces the sequential action sums, e.g. hmc.c:456-459, 472-475. */
 int tb_re_dot_dev(tb_ctx *ctx, const double *d_a, const double *d_b, double *out_host);
 
+/* ---- slab decomposition of ONE large lattice over the GPUs of a box --------------
+ * One process per GPU; rank r owns global rows [r*NT/nranks, (r+1)*NT/nranks) and passes only its slab
+ * (host layout double[nchains][NT/nranks][NX][2]) to every entry point above.  The stencil reads the
+ * neighbour ranks' boundary rows straight out of their HBM (CUDA-IPC peer mapping over NVLink, epoch flags),
+ * CG dot products are all-reduced by one-shot peer stores; no NCCL on the data path.  Every apply / solve /
+ * gauge update is COLLECTIVE: all ranks call it in the same order.  After tb_set_gauge* the caller must
+ * tb_synchronize and barrier across ranks (the neighbour reads the boundary row of the t-links).
+ * Set-up: every rank tb_create_slab -> tb_slab_export -> all-gather the handles -> tb_slab_connect -> barrier. */
+int tb_create_slab(tb_ctx **out, int nt_global, int nx, int nchains, int mode, int device, int rank, int nranks);
+int tb_slab_handle_bytes(void);
+int tb_slab_export(tb_ctx *ctx, void *handle_out);
+int tb_slab_connect(tb_ctx *ctx, const void *all_handles);
+
 /* Counters for bench.py: kernels launched by this context since creation / since the last reset. */
 long long tb_launch_count(const tb_ctx *ctx);
 int tb_reset_launch_count(tb_ctx *ctx);

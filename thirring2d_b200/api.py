@@ -38,11 +38,20 @@ class CGInfo:
 
 
 class Context:
-    def __init__(self, nt, nx, nchains=1, mode=MODE_ADJOINT, device=0, m=1.0, mu=0.0, stream=None):
+    def __init__(self, nt, nx, nchains=1, mode=MODE_ADJOINT, device=0, m=1.0, mu=0.0, stream=None,
+                 slab_rank=None, slab_nranks=1):
+        """nt is the GLOBAL number of t-rows; with slab_nranks > 1 this rank owns nt // slab_nranks of them
+        and every array passed to the methods is the local slab (nchains, nt_local, nx[, 2])."""
         self.lib = load_library()
-        self.nt, self.nx, self.nchains, self.mode, self.device = nt, nx, nchains, mode, device
+        self.nt_global, self.nranks, self.rank = nt, slab_nranks, slab_rank or 0
         h = C.c_void_p()
-        check(self.lib.tb_create(C.byref(h), nt, nx, nchains, mode, device), "tb_create")
+        if slab_nranks > 1:
+            check(self.lib.tb_create_slab(C.byref(h), nt, nx, nchains, mode, device, self.rank, slab_nranks),
+                  "tb_create_slab")
+            nt = nt // slab_nranks
+        else:
+            check(self.lib.tb_create(C.byref(h), nt, nx, nchains, mode, device), "tb_create")
+        self.nt, self.nx, self.nchains, self.mode, self.device = nt, nx, nchains, mode, device
         self._h = h
         if stream is not None:
             self.set_stream(stream)
@@ -65,6 +74,24 @@ class Context:
 
     def __exit__(self, *a):
         self.close()
+
+    # -- slab decomposition (one process per GPU) ---------------------------------------------------------
+    def slab_export(self) -> bytes:
+        buf = C.create_string_buffer(self.lib.tb_slab_handle_bytes())
+        check(self.lib.tb_slab_export(self._h, buf), "tb_slab_export")
+        return buf.raw
+
+    def slab_connect(self, handles):
+        """handles: list of the nranks exported handles in rank order."""
+        blob = b"".join(handles)
+        check(self.lib.tb_slab_connect(self._h, blob), "tb_slab_connect")
+
+    def slab_setup(self, dist):
+        """Exchange the IPC handles over an initialised torch.distributed group and connect."""
+        handles = [None] * self.nranks
+        dist.all_gather_object(handles, self.slab_export())
+        self.slab_connect(handles)
+        dist.barrier()
 
     # -- configuration ---------------------------------------------------------------------------------
     def set_stream(self, stream_ptr: int):

@@ -70,7 +70,14 @@ static int alloc_cg_state(tb_ctx *ctx) {
   return TB_OK;
 }
 
+void tb_slab_release(tb_ctx *ctx);
+
 extern "C" int tb_create(tb_ctx **out, int nt, int nx, int nchains, int mode, int device) {
+  return tb_create_common(out, nt, nx, nchains, mode, device, 0, 1, nt);
+}
+
+int tb_create_common(tb_ctx **out, int nt, int nx, int nchains, int mode, int device, int rank, int nranks,
+                     int nt_global) {
   if (!out || nt < 2 || nx < 2 || nchains < 1 || (mode != TB_MODE_REF_COMPAT && mode != TB_MODE_ADJOINT)) {
     tb_set_error("tb_create: invalid arguments (nt=%d nx=%d nchains=%d mode=%d)", nt, nx, nchains, mode);
     return TB_EINVAL;
@@ -94,6 +101,10 @@ extern "C" int tb_create(tb_ctx **out, int nt, int nx, int nchains, int mode, in
   ctx->device = device;
   ctx->V = (size_t)nt * nx;
   ctx->nsite = ctx->V * nchains;
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  ctx->nt_global = nt_global;
+  ctx->t_off = rank * nt;
   const char *e;
   ctx->tune_tt = (e = getenv("TB_ROWS_PER_THREAD")) ? atoi(e) : 0;
   ctx->tune_chunk = (e = getenv("TB_ITERS_PER_LAUNCH")) ? atoi(e) : 0;
@@ -112,8 +123,13 @@ extern "C" int tb_create(tb_ctx **out, int nt, int nx, int nchains, int mode, in
 #define A_(ptr, cnt)                              \
   if (rc == TB_OK) rc = dev_alloc(&(ptr), (cnt));
   A_(ctx->d_mass, cp) A_(ctx->d_emu, cp) A_(ctx->d_emmu, cp)
-  A_(ctx->W0, n) A_(ctx->W1, n) A_(ctx->Adev, n)
-  A_(ctx->r, n) A_(ctx->p, n) A_(ctx->Mp, n) A_(ctx->q, n) A_(ctx->xw, n) A_(ctx->tmp, n)
+  if (nranks > 1) {  // p, Mp and W0 live in the IPC-exported exchange block
+    if (rc == TB_OK) rc = tb_slab_layout(ctx);
+  } else {
+    A_(ctx->W0, n) A_(ctx->p, n) A_(ctx->Mp, n)
+  }
+  A_(ctx->W1, n) A_(ctx->Adev, n)
+  A_(ctx->r, n) A_(ctx->q, n) A_(ctx->xw, n) A_(ctx->tmp, n)
   A_(ctx->vin, n) A_(ctx->vout, n)
   A_(ctx->stage, 2 * n)
   A_(ctx->stage_x, n)
@@ -138,6 +154,7 @@ extern "C" int tb_create(tb_ctx **out, int nt, int nx, int nchains, int mode, in
     // host-buffer pipeline: chains are processed in nsub sub-batches on their own streams
     const char *es = getenv("TB_SUBBATCHES");
     ctx->nsub = es ? atoi(es) : (ctx->C >= 128 ? 4 : (ctx->C >= 32 ? 2 : 1));
+    if (nranks > 1) ctx->nsub = 1;
     if (ctx->nsub < 1) ctx->nsub = 1;
     if (ctx->nsub > TB_MAX_SUB) ctx->nsub = TB_MAX_SUB;
     if (ctx->nsub > ctx->C) ctx->nsub = ctx->C;
@@ -167,8 +184,10 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
   }
   if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
   invalidate_graph(ctx);
-  void *dev[] = {ctx->d_mass, ctx->d_emu, ctx->d_emmu, ctx->W0, ctx->W1, ctx->Adev, ctx->r, ctx->p, ctx->Mp,
-                 ctx->q, ctx->xw, ctx->tmp, ctx->vin, ctx->vout, ctx->stage, ctx->stage_x, ctx->cg.rr_old, ctx->cg.active,
+  const bool slab = ctx->nranks > 1;
+  tb_slab_release(ctx);
+  void *dev[] = {ctx->d_mass, ctx->d_emu, ctx->d_emmu, slab ? nullptr : (void *)ctx->W0, ctx->W1, ctx->Adev, ctx->r,
+                 slab ? nullptr : (void *)ctx->p, slab ? nullptr : (void *)ctx->Mp, ctx->q, ctx->xw, ctx->tmp, ctx->vin, ctx->vout, ctx->stage, ctx->stage_x, ctx->cg.rr_old, ctx->cg.active,
                  ctx->cg.partial, ctx->cg.ticket};
   for (void *p : dev)
     if (p) cudaFree(p);
@@ -217,6 +236,15 @@ static int join_subs(tb_ctx *ctx) {
 static int sync_all(tb_ctx *ctx) {
   TB_CHECK(join_subs(ctx));
   TB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ctx->nranks > 1) {  // a peer-flag wait that timed out is an error, never a hang
+    int err = 0;
+    TB_CUDA(cudaMemcpy(&err, ctx->slab.err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (err) {
+      tb_set_error("slab mode: wait on a neighbour's flag timed out (code %d): a rank died or the ranks issued "
+                   "collective calls in different orders", err);
+      return TB_ECUDA;
+    }
+  }
   return TB_OK;
 }
 
@@ -322,6 +350,10 @@ extern "C" int tb_set_gauge_dev(tb_ctx *ctx, const double *d_A_canonical) {
 }
 
 static int need_gauge(tb_ctx *ctx) {
+  if (ctx->nranks > 1 && !ctx->slab_connected) {
+    tb_set_error("slab context is not connected (call tb_slab_connect on every rank first)");
+    return TB_EINVAL;
+  }
   if (!ctx->have_gauge) {
     tb_set_error("no gauge field set (call tb_set_gauge / tb_set_gauge_dev first)");
     return TB_EINVAL;
@@ -339,6 +371,10 @@ extern "C" int tb_apply_dev(tb_ctx *ctx, int op, const double *d_in, double *d_o
   TB_CHECK(need_gauge(ctx));
   const double2 *in = (const double2 *)d_in;
   double2 *out = (double2 *)d_out;
+  if (ctx->nranks > 1) {
+    if (op < TB_OP_M || op > TB_OP_MDM) { tb_set_error("tb_apply_dev: unknown op %d", op); return TB_EINVAL; }
+    return tb_slab_apply(ctx, op, in, out);
+  }
   switch (op) {
     case TB_OP_M: return tb_launch_dslash(ctx, false, in, out, false);
     case TB_OP_MDAG: return tb_launch_dslash(ctx, true, in, out, false);
@@ -382,7 +418,8 @@ extern "C" int tb_invert_dev(tb_ctx *ctx, const double *d_v, double *d_x) {
   TB_CHECK(join_subs(ctx));
   TB_CHECK(need_gauge(ctx));
   // fm_invert_cg, hmc.c:408-414
-  TB_CHECK(tb_launch_dslash(ctx, tb_conj_is_dagger(ctx), (const double2 *)d_v, ctx->tmp, false));
+  if (ctx->nranks > 1) TB_CHECK(tb_slab_apply(ctx, TB_OP_MCONJ, (const double2 *)d_v, ctx->tmp));
+  else TB_CHECK(tb_launch_dslash(ctx, tb_conj_is_dagger(ctx), (const double2 *)d_v, ctx->tmp, false));
   return run_cg(ctx, ctx->tmp, (double2 *)d_x);
 }
 
@@ -395,7 +432,7 @@ extern "C" int tb_cg_result(tb_ctx *ctx, int *status, int *iters, double *rr) {
   TB_CUDA(cudaMemcpyAsync(ctx->h_status, ctx->cg.status, c * sizeof(int), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaMemcpyAsync(ctx->h_iters, ctx->cg.iters, c * sizeof(int), cudaMemcpyDeviceToHost, st));
   TB_CUDA(cudaMemcpyAsync(ctx->h_rr, ctx->cg.rr, c * sizeof(double), cudaMemcpyDeviceToHost, st));
-  TB_CUDA(cudaStreamSynchronize(st));
+  TB_CHECK(sync_all(ctx));
   if (status) memcpy(status, ctx->h_status, c * sizeof(int));
   if (iters) memcpy(iters, ctx->h_iters, c * sizeof(int));
   if (rr) memcpy(rr, ctx->h_rr, c * sizeof(double));

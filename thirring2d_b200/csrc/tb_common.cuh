@@ -58,6 +58,33 @@ struct TbCgState {
   int max_iter;
 };
 
+// Slab decomposition of ONE large lattice over P GPUs (1-D in t, rank r owns global rows [r*nt, (r+1)*nt)).
+// Nothing is copied for the halos: the stencil reads the neighbour rank's boundary row straight out of the
+// neighbour's HBM through an IPC-mapped peer pointer (NVLink), guarded by epoch flags that the producing
+// kernel's last block writes into the consumer's memory.  CG dot products are all-reduced by every rank
+// storing its partial into every peer's slot table (one-shot, P <= 8), summed in rank order => bitwise
+// identical scalars, hence identical convergence decisions, on all ranks.
+#define TB_SLAB_MAX_RANKS 8
+enum { TB_FLAG_PREADY = 0, TB_FLAG_MPREADY = 1, TB_FLAG_PDONE = 2, TB_FLAG_MPDONE = 3, TB_NFLAGS = 4 };
+enum { TB_RED_PQ = 0, TB_RED_RR = 1, TB_RED_INIT = 2, TB_NRED = 3 };
+struct TbSlab {
+  int P, rank;
+  // peer views of the two exchange vectors and of the t-links
+  const double2 *p_prev, *p_next, *mp_prev, *mp_next, *W0_prev;
+  // my flags: flags[kind*2 + side], side 0 = written by the previous rank, 1 = by the next rank
+  volatile int *flags;
+  int *sig_prev;  // previous rank's flags + 1 (its "from next" side):  sig_prev[kind*2]
+  int *sig_next;  // next rank's flags + 0 (its "from prev" side):      sig_next[kind*2]
+  // all-reduce slots in MY memory: red[(kind*P + q)*Cpad + c], red_flag[(kind*P + q)*nctiles + ctile]
+  double *red;
+  volatile int *red_flag;
+  double *peer_red[TB_SLAB_MAX_RANKS];
+  int *peer_red_flag[TB_SLAB_MAX_RANKS];
+  int *seq;                    // device epoch counter = generation of the exchange vector p
+  unsigned int *done_ticket;   // [TB_NFLAGS] completion counters of the signalling kernels
+  int *err;                    // set when a flag wait timed out
+};
+
 struct tb_ctx {
   int nt, nx, C, mode, device;
   size_t V;          // nt*nx
@@ -93,6 +120,15 @@ struct tb_ctx {
   double2 *stage_x;  // second canonical staging buffer (results)
   double last_solve_ms;
   long long launches;
+  // slab mode (nranks > 1): ctx->nt is the LOCAL number of rows
+  int nranks, rank, nt_global, t_off;
+  void *slab_block;                 // the IPC-exported allocation (p, Mp, W0, slots, flags)
+  size_t slab_bytes;
+  void *peer_block[TB_SLAB_MAX_RANKS];
+  bool slab_connected;
+  TbSlab slab;
+  cudaGraphExec_t slab_graph;
+  int slab_graph_chunk;
 };
 
 int tb_choose_geom(tb_ctx *ctx);
@@ -110,5 +146,9 @@ int tb_launch_pack_slice(tb_ctx *ctx, const double2 *d_canonical_slice, double2 
 int tb_launch_unpack_slice(tb_ctx *ctx, const double2 *d_vec, double2 *d_canonical_slice, int c0, int n, cudaStream_t st);
 bool tb_resident_supported(const tb_ctx *ctx);
 int tb_launch_dot(tb_ctx *ctx, const double2 *a, const double2 *b, double *d_out);
+int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out);
+int tb_slab_layout(tb_ctx *ctx);
+int tb_create_common(tb_ctx **out, int nt_local, int nx, int nchains, int mode, int device, int rank, int nranks,
+                     int nt_global);
 
 static inline bool tb_conj_is_dagger(const tb_ctx *ctx) { return ctx->mode == TB_MODE_ADJOINT; }

@@ -42,11 +42,103 @@ __device__ __forceinline__ BlockPos block_pos(const TbGeom &g) {
   return b;
 }
 
-// Block-level deterministic reduction of `acc` over the x_local index for every chain of the tile, then
-// ticket-based cross-block finalisation.  `red` is shared memory for blockDim.x doubles.
+// ---- slab-mode primitives (peer flags over NVLink) ------------------------------------------------------
+// spin until the flag written by the neighbour on `side` (0 = previous rank, 1 = next rank) reaches `need`
+// A wait that outlives TB_SLAB_SPIN_CYCLES (seconds: a peer died or the collective call order differs between
+// ranks) records an error instead of hanging the GPU; the host reports it at the next synchronisation.
+#define TB_SLAB_SPIN_CYCLES 6000000000LL
+__device__ __forceinline__ void slab_spin(volatile int *f, int need, int *err, int code) {
+  const long long t0 = clock64();
+  while (*f < need) {
+    __nanosleep(64);
+    if (clock64() - t0 > TB_SLAB_SPIN_CYCLES) {
+      atomicExch(err, code);
+      break;
+    }
+  }
+  __threadfence_system();
+}
+
+__device__ __forceinline__ void slab_wait(const TbSlab &sl, int kind, int side, int need) {
+  if (threadIdx.x == 0) slab_spin(sl.flags + kind * 2 + side, need, sl.err, 1 + kind);
+  __syncthreads();
+}
+
+// every block calls this after its last global store; the last block of the grid publishes `value` into
+// both neighbours' flag `kind`
+__device__ __forceinline__ void slab_signal_done(const TbSlab &sl, int kind0, int kind1, int value) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int tk = atomicAdd(&sl.done_ticket[kind0], 1u);
+    if (tk == nblocks - 1) {
+      sl.done_ticket[kind0] = 0u;
+      __threadfence_system();
+      *(volatile int *)(sl.sig_prev + kind0 * 2) = value;
+      *(volatile int *)(sl.sig_next + kind0 * 2) = value;
+      if (kind1 >= 0) {
+        *(volatile int *)(sl.sig_prev + kind1 * 2) = value;
+        *(volatile int *)(sl.sig_next + kind1 * 2) = value;
+      }
+      __threadfence_system();
+    }
+  }
+}
+
+template <bool SLAB>
+__device__ __forceinline__ double2 ld_halo(const double2 *p) {
+  return SLAB ? __ldcv(p) : *p;   // peer memory: never serve a halo row from a stale L1 line
+}
+
+// CG scalar update for chain c from the global sum `total` (shared by the local and the slab path)
 template <int FIN>
+__device__ __forceinline__ void finalize_scalar(double total, int c, int ctile, const TbCgState &s) {
+  if (FIN == FIN_DOT) {
+    s.dot[c] = total;
+  } else if (FIN == FIN_INIT) {
+    s.rr[c] = total;
+    s.rr_old[c] = total;
+    s.rr_init[c] = total;
+    if (total < s.accuracy) {  // hmc.c:359-361, x is already zero
+      s.status[c] = TB_CG_ZERO_SOURCE;
+      s.active[c] = 0;
+      atomicSub(&s.tile_active[ctile], 1);
+      atomicSub(s.n_active, 1);
+    }
+  } else if (FIN == FIN_PQ) {
+    if (s.active[c]) {
+      s.pq[c] = total;
+      s.alpha[c] = s.rr_old[c] / total;  // hmc.c:371
+    }
+  } else if (FIN == FIN_RR) {
+    if (s.active[c]) {
+      const int it = s.iters[c] + 1;
+      s.iters[c] = it;
+      s.rr[c] = total;
+      int st = -1;
+      if (total < s.accuracy) st = TB_CG_CONVERGED;                                                  // hmc.c:381
+      else if (!(total == total) || total / s.rr_init[c] > TB_DIVERGENCE_RATIO) st = TB_CG_DIVERGED;  // hmc.c:383
+      else if (it >= s.max_iter - 1) st = TB_CG_MAXITER;                                             // hmc.c:364
+      if (st >= 0) {
+        s.status[c] = st;
+        s.active[c] = 0;
+        atomicSub(&s.tile_active[ctile], 1);
+        atomicSub(s.n_active, 1);
+      } else {
+        s.beta[c] = total / s.rr_old[c];  // hmc.c:390
+        s.rr_old[c] = total;              // hmc.c:394
+      }
+    }
+  }
+}
+
+// Block-level deterministic reduction of `acc` over the x_local index for every chain of the tile, then
+// ticket-based cross-block reduction by the last block of the chain tile, which either evaluates the CG scalar
+// update (single GPU) or publishes this rank's partial to every rank's slot table (slab mode; RED = slot kind).
+template <int FIN, bool SLAB, int RED>
 __device__ __forceinline__ void reduce_finalize(double acc, const TbGeom &g, const TbCgState &s,
-                                                const BlockPos &b, double *red) {
+                                                const TbSlab &sl, const BlockPos &b, double *red) {
   __shared__ unsigned int s_last;
   const int idx = b.x_local * g.bc + b.c_local;
   red[idx] = acc;
@@ -70,7 +162,7 @@ __device__ __forceinline__ void reduce_finalize(double acc, const TbGeom &g, con
   if (!s_last) return;
   __threadfence();
   double sum = 0.0;
-  for (int sl = b.x_local; sl < g.nslots; sl += g.bx) sum += __ldcg(&s.partial[(size_t)sl * g.Cpad + cp]);
+  for (int sl_ = b.x_local; sl_ < g.nslots; sl_ += g.bx) sum += __ldcg(&s.partial[(size_t)sl_ * g.Cpad + cp]);
   red[idx] = sum;
   __syncthreads();
   for (int st = g.bx >> 1; st > 0; st >>= 1) {
@@ -78,60 +170,60 @@ __device__ __forceinline__ void reduce_finalize(double acc, const TbGeom &g, con
     __syncthreads();
   }
   if (threadIdx.x == 0) s.ticket[b.ctile] = 0u;
-  if (b.x_local != 0 || b.c >= g.C) return;
-  const double total = red[b.c_local];
-  const int c = b.c;
-  if (FIN == FIN_DOT) {
-    s.dot[c] = total;
-  } else if (FIN == FIN_INIT) {
-    s.rr[c] = total;
-    s.rr_old[c] = total;
-    s.rr_init[c] = total;
-    if (total < s.accuracy) {  // hmc.c:359-361, x is already zero
-      s.status[c] = TB_CG_ZERO_SOURCE;
-      s.active[c] = 0;
-      atomicSub(&s.tile_active[b.ctile], 1);
-      atomicSub(s.n_active, 1);
+  if (!SLAB) {
+    if (b.x_local == 0 && b.c < g.C) finalize_scalar<FIN>(red[b.c_local], b.c, b.ctile, s);
+  } else {
+    const int seq = *sl.seq;
+    if (b.x_local == 0) {
+      const double total = red[b.c_local];
+      for (int q = 0; q < sl.P; q++) sl.peer_red[q][(size_t)(RED * sl.P + sl.rank) * g.Cpad + cp] = total;
+      __threadfence_system();
     }
-  } else if (FIN == FIN_PQ) {
-    if (s.active[c]) {
-      s.pq[c] = total;
-      s.alpha[c] = s.rr_old[c] / total;  // hmc.c:371
-    }
-  } else if (FIN == FIN_RR) {
-    if (s.active[c]) {
-      const int it = s.iters[c] + 1;
-      s.iters[c] = it;
-      s.rr[c] = total;
-      int st = -1;
-      if (total < s.accuracy) st = TB_CG_CONVERGED;                                    // hmc.c:381
-      else if (!(total == total) || total / s.rr_init[c] > TB_DIVERGENCE_RATIO) st = TB_CG_DIVERGED;  // hmc.c:383
-      else if (it >= s.max_iter - 1) st = TB_CG_MAXITER;                               // hmc.c:364
-      if (st >= 0) {
-        s.status[c] = st;
-        s.active[c] = 0;
-        atomicSub(&s.tile_active[b.ctile], 1);
-        atomicSub(s.n_active, 1);
-      } else {
-        s.beta[c] = total / s.rr_old[c];  // hmc.c:390
-        s.rr_old[c] = total;              // hmc.c:394
-      }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      for (int q = 0; q < sl.P; q++)
+        *(volatile int *)(sl.peer_red_flag[q] + (RED * sl.P + sl.rank) * g.nctiles + b.ctile) = seq;
+      __threadfence_system();
     }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Dirac apply.  DAG: M^dagger instead of M.  DOT: accumulate Re<aux,out> and finalise alpha (FIN_PQ) or a
-// plain dot (FIN_DOT when !MASKED).  MASKED: skip chains whose CG has finished.
-template <int TT, bool DAG, bool DOT, bool MASKED>
+// Dirac apply.  DAG: M^dagger instead of M.  DOT: accumulate Re<aux,out> (alpha via FIN_PQ when MASKED, plain dot
+// otherwise).  MASKED: skip chains whose CG has finished.  SLAB: rows t-1 of the first local row and t+1 of the
+// last one live in the neighbour ranks' HBM (in_prev / in_next, W0_prev).  Without SLAB the same pointers
+// are the local arrays and the indexing is the periodic wrap.
+//   SLAB protocol (epoch E = *sl.seq): wait flag `wait_ready` >= E on the sides this block touches, and
+//   `wait_done` >= E-1 before overwriting `out` rows a neighbour may still be reading; when the whole grid
+//   is done, publish `sig0`/`sig1` = E to both neighbours.
+template <int TT, bool DAG, bool DOT, bool MASKED, bool SLAB>
 __global__ void __launch_bounds__(TB_MAX_BLOCK)
-dslash_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ W0,
+dslash_kernel(const double2 *__restrict__ in, const double2 *in_prev, const double2 *in_next,
+              double2 *__restrict__ out, const double2 *__restrict__ W0, const double2 *W0_prev,
               const double2 *__restrict__ W1, const double *__restrict__ mass,
               const double *__restrict__ emu, const double *__restrict__ emmu,
-              const double2 *__restrict__ aux, const TbGeom g, const TbCgState s) {
+              const double2 *__restrict__ aux, const TbGeom g, const TbCgState s, const TbSlab sl,
+              const int wait_ready, const int wait_done, const int sig0, const int sig1) {
   __shared__ double red[TB_MAX_BLOCK];
   const BlockPos b = block_pos(g);
-  if (MASKED && s.tile_active[b.ctile] == 0) return;
+  if (MASKED && s.tile_active[b.ctile] == 0) {
+    // a finished chain tile still takes part in the grid-completion ticket while other tiles iterate
+    if (SLAB && *s.n_active > 0) slab_signal_done(sl, sig0, sig1, *sl.seq);
+    return;
+  }
+  int seq = 0;
+  if (SLAB) {
+    seq = *sl.seq;
+    if (b.ttile == 0) {
+      slab_wait(sl, wait_ready, 0, seq);
+      if (wait_done >= 0) slab_wait(sl, wait_done, 0, seq - 1);
+    }
+    if (b.ttile == g.nttiles - 1) {
+      slab_wait(sl, wait_ready, 1, seq);
+      if (wait_done >= 0) slab_wait(sl, wait_done, 1, seq - 1);
+    }
+  }
   bool act = b.valid;
   if (MASKED && act) act = s.active[b.c] != 0;
   double acc = 0.0;
@@ -144,17 +236,21 @@ dslash_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, const d
     const size_t jp = (size_t)((b.x + 1 == g.nx) ? 0 : b.x + 1) * g.C + b.c;
     const size_t jm = (size_t)((b.x == 0) ? g.nx - 1 : b.x - 1) * g.C + b.c;
     const int t0 = b.ttile * TT;
-    const int tm0 = (t0 == 0) ? g.nt - 1 : t0 - 1;
-    double2 pm = in[tm0 * R + j];
+    double2 pm, w0m;
+    if (t0 == 0) {
+      pm = ld_halo<SLAB>(&in_prev[(size_t)(g.nt - 1) * R + j]);
+      w0m = ld_halo<SLAB>(&W0_prev[(size_t)(g.nt - 1) * R + j]);
+    } else {
+      pm = in[(size_t)(t0 - 1) * R + j];
+      w0m = W0[(size_t)(t0 - 1) * R + j];
+    }
     double2 pc = in[t0 * R + j];
-    double2 w0m = W0[tm0 * R + j];
 #pragma unroll
     for (int i = 0; i < TT; i++) {
       const int t = t0 + i;
       if (t < g.nt) {
-        const int tp = (t + 1 == g.nt) ? 0 : t + 1;
         const size_t row = t * R;
-        const double2 pp = in[tp * R + j];
+        const double2 pp = (t + 1 == g.nt) ? ld_halo<SLAB>(&in_next[j]) : in[row + R + j];
         const double2 pxp = in[row + jp];
         const double2 pxm = in[row + jm];
         const double2 w0c = W0[row + j];
@@ -190,14 +286,15 @@ dslash_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, const d
       }
     }
   }
-  if (DOT) reduce_finalize<MASKED ? FIN_PQ : FIN_DOT>(acc, g, s, b, red);
+  if (DOT) reduce_finalize<MASKED ? FIN_PQ : FIN_DOT, SLAB, TB_RED_PQ>(acc, g, s, sl, b, red);
+  if (SLAB) slab_signal_done(sl, sig0, sig1, seq);
 }
 
 // x += alpha p ; r -= alpha q ; rr = ||r||^2 ; then beta / convergence (hmc.c:372-394)
-template <int TT>
+template <int TT, bool SLAB>
 __global__ void __launch_bounds__(TB_MAX_BLOCK)
 axpy_norm_kernel(double2 *__restrict__ x, double2 *__restrict__ r, const double2 *__restrict__ p,
-                 const double2 *__restrict__ q, const TbGeom g, const TbCgState s) {
+                 const double2 *__restrict__ q, const TbGeom g, const TbCgState s, const TbSlab sl) {
   __shared__ double red[TB_MAX_BLOCK];
   const BlockPos b = block_pos(g);
   if (s.tile_active[b.ctile] == 0) return;
@@ -225,41 +322,60 @@ axpy_norm_kernel(double2 *__restrict__ x, double2 *__restrict__ r, const double2
       }
     }
   }
-  reduce_finalize<FIN_RR>(acc, g, s, b, red);
+  reduce_finalize<FIN_RR, SLAB, TB_RED_RR>(acc, g, s, sl, b, red);
 }
 
-// p = r + beta p (hmc.c:391-392)
-template <int TT>
+// p = r + beta p (hmc.c:391-392).  SLAB: p is an exchange vector: wait until the neighbours have finished
+// reading generation E-1 (PDONE), publish generation E (PREADY).
+template <int TT, bool SLAB>
 __global__ void __launch_bounds__(TB_MAX_BLOCK)
-xpay_kernel(double2 *__restrict__ p, const double2 *__restrict__ r, const TbGeom g, const TbCgState s) {
+xpay_kernel(double2 *__restrict__ p, const double2 *__restrict__ r, const TbGeom g, const TbCgState s,
+            const TbSlab sl) {
   const BlockPos b = block_pos(g);
-  if (s.tile_active[b.ctile] == 0) return;
-  if (!(b.valid && s.active[b.c] != 0)) return;
-  const double be = s.beta[b.c];
-  const size_t R = (size_t)g.R;
-  const size_t j = (size_t)b.x * g.C + b.c;
-  const int t0 = b.ttile * TT;
+  if (s.tile_active[b.ctile] == 0) {
+    if (SLAB && *s.n_active > 0) slab_signal_done(sl, TB_FLAG_PREADY, -1, *sl.seq);
+    return;
+  }
+  int seq = 0;
+  if (SLAB) {
+    seq = *sl.seq;
+    if (b.ttile == 0) slab_wait(sl, TB_FLAG_PDONE, 0, seq - 1);
+    if (b.ttile == g.nttiles - 1) slab_wait(sl, TB_FLAG_PDONE, 1, seq - 1);
+  }
+  if (b.valid && s.active[b.c] != 0) {
+    const double be = s.beta[b.c];
+    const size_t R = (size_t)g.R;
+    const size_t j = (size_t)b.x * g.C + b.c;
+    const int t0 = b.ttile * TT;
 #pragma unroll
-  for (int i = 0; i < TT; i++) {
-    const int t = t0 + i;
-    if (t < g.nt) {
-      const size_t k = t * R + j;
-      const double2 rv = r[k];
-      double2 pv = p[k];
-      pv.x = rv.x + be * pv.x;
-      pv.y = rv.y + be * pv.y;
-      p[k] = pv;
+    for (int i = 0; i < TT; i++) {
+      const int t = t0 + i;
+      if (t < g.nt) {
+        const size_t k = t * R + j;
+        const double2 rv = r[k];
+        double2 pv = p[k];
+        pv.x = rv.x + be * pv.x;
+        pv.y = rv.y + be * pv.y;
+        p[k] = pv;
+      }
     }
   }
+  if (SLAB) slab_signal_done(sl, TB_FLAG_PREADY, -1, seq);
 }
 
 // x = 0 ; r = b ; p = b ; rr = ||b||^2 (hmc.c:349-361)
-template <int TT>
+template <int TT, bool SLAB>
 __global__ void __launch_bounds__(TB_MAX_BLOCK)
 cg_init_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ x, double2 *__restrict__ r,
-               double2 *__restrict__ p, const TbGeom g, const TbCgState s) {
+               double2 *__restrict__ p, const TbGeom g, const TbCgState s, const TbSlab sl) {
   __shared__ double red[TB_MAX_BLOCK];
   const BlockPos b = block_pos(g);
+  int seq = 0;
+  if (SLAB) {
+    seq = *sl.seq;
+    if (b.ttile == 0) slab_wait(sl, TB_FLAG_PDONE, 0, seq - 1);
+    if (b.ttile == g.nttiles - 1) slab_wait(sl, TB_FLAG_PDONE, 1, seq - 1);
+  }
   double acc = 0.0;
   if (b.valid) {
     const size_t R = (size_t)g.R;
@@ -278,13 +394,77 @@ cg_init_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ x, double
       }
     }
   }
-  reduce_finalize<FIN_INIT>(acc, g, s, b, red);
+  reduce_finalize<FIN_INIT, SLAB, TB_RED_INIT>(acc, g, s, sl, b, red);
+  if (SLAB) slab_signal_done(sl, TB_FLAG_PREADY, -1, seq);
+}
+
+// slab mode: copy a user vector into the exchange vector p as generation E (standalone applies)
+template <int TT>
+__global__ void __launch_bounds__(TB_MAX_BLOCK)
+slab_stage_kernel(const double2 *__restrict__ src, double2 *__restrict__ p, const TbGeom g, const TbSlab sl) {
+  const BlockPos b = block_pos(g);
+  const int seq = *sl.seq;
+  if (b.ttile == 0) slab_wait(sl, TB_FLAG_PDONE, 0, seq - 1);
+  if (b.ttile == g.nttiles - 1) slab_wait(sl, TB_FLAG_PDONE, 1, seq - 1);
+  if (b.valid) {
+    const size_t R = (size_t)g.R;
+    const size_t j = (size_t)b.x * g.C + b.c;
+    const int t0 = b.ttile * TT;
+#pragma unroll
+    for (int i = 0; i < TT; i++) {
+      const int t = t0 + i;
+      if (t < g.nt) p[t * R + j] = src[t * R + j];
+    }
+  }
+  slab_signal_done(sl, TB_FLAG_PREADY, -1, seq);
+}
+
+// slab mode: advance the epoch (a new generation of p is about to be written)
+__global__ void slab_bump_kernel(const TbSlab sl) { *sl.seq += 1; }
+
+// slab mode: one block.  Waits for every rank's partial of reduction RED at epoch E, sums them in rank order
+// and evaluates the CG scalar update FIN for every chain.  After FIN_RR it opens the next epoch (unless every
+// chain has finished); after FIN_INIT with nothing left to solve it releases the neighbours, who will never be
+// asked to read this generation of p.
+template <int FIN, int RED>
+__global__ void __launch_bounds__(TB_MAX_BLOCK)
+slab_scalars_kernel(const TbGeom g, const TbCgState s, const TbSlab sl) {
+  if (FIN != FIN_INIT && *s.n_active == 0) return;
+  const int seq = *sl.seq;
+  for (int ctile = 0; ctile < g.nctiles; ctile++) {
+    if (FIN != FIN_INIT && s.tile_active[ctile] == 0) continue;   // uniform: nobody published for this tile
+    if ((int)threadIdx.x < sl.P)
+      slab_spin(sl.red_flag + (RED * sl.P + threadIdx.x) * g.nctiles + ctile, seq, sl.err, 10 + RED);
+    __syncthreads();
+    for (int cl = threadIdx.x; cl < g.bc; cl += blockDim.x) {
+      const int cp = ctile * g.bc + cl;
+      double total = 0.0;
+      for (int q = 0; q < sl.P; q++) total += __ldcv(&sl.red[(size_t)(RED * sl.P + q) * g.Cpad + cp]);
+      if (cp < g.C) finalize_scalar<FIN>(total, cp, ctile, s);
+    }
+    __syncthreads();
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int left = *(volatile int *)s.n_active;
+    if (FIN == FIN_RR && left > 0) *sl.seq = seq + 1;
+    if (FIN == FIN_INIT && left == 0) {
+      __threadfence_system();
+      *(volatile int *)(sl.sig_prev + TB_FLAG_PDONE * 2) = seq;
+      *(volatile int *)(sl.sig_next + TB_FLAG_PDONE * 2) = seq;
+      *(volatile int *)(sl.sig_prev + TB_FLAG_MPDONE * 2) = seq;
+      *(volatile int *)(sl.sig_next + TB_FLAG_MPDONE * 2) = seq;
+      __threadfence_system();
+    }
+  }
 }
 
 // plain per-chain Re<a,b>
 template <int TT>
 __global__ void __launch_bounds__(TB_MAX_BLOCK)
-dot_kernel(const double2 *__restrict__ a, const double2 *__restrict__ bb, const TbGeom g, const TbCgState s) {
+dot_kernel(const double2 *__restrict__ a, const double2 *__restrict__ bb, const TbGeom g, const TbCgState s,
+           const TbSlab sl) {
   __shared__ double red[TB_MAX_BLOCK];
   const BlockPos b = block_pos(g);
   double acc = 0.0;
@@ -302,7 +482,7 @@ dot_kernel(const double2 *__restrict__ a, const double2 *__restrict__ bb, const 
       }
     }
   }
-  reduce_finalize<FIN_DOT>(acc, g, s, b, red);
+  reduce_finalize<FIN_DOT, false, 0>(acc, g, s, sl, b, red);
 }
 
 __global__ void cg_reset_kernel(const TbGeom g, const TbCgState s) {
@@ -323,32 +503,32 @@ __global__ void cg_reset_kernel(const TbGeom g, const TbCgState s) {
   if (i == 0) *s.n_active = g.C;
 }
 
-// W0 = s0(t) 1/2 eta0(x) (cos A0, sin A0) ; W1 = s1(x) 1/2 (cos A1, sin A1); device layout in and out.
-// eta0 = (-1)^x (hmc.c:917-921), s = -1 on the wrap link (hmc.c:143-148,165-170).
+// W0 = s0(t) 1/2 eta0(x) (cos A0, sin A0) ; W1 = s1(x) 1/2 (cos A1, sin A1); device layout in and out, chains
+// [c0, c0+n).  eta0 = (-1)^x (hmc.c:917-921), s = -1 on the wrap link (hmc.c:143-148,165-170); t_off / nt_global
+// place a slab inside the global lattice.
 __global__ void links_kernel(const double2 *__restrict__ A, double2 *__restrict__ W0, double2 *__restrict__ W1,
-                             int nt, int nx, int C, int c0, int n) {
-  const size_t total = (size_t)nt * nx * n;   // sites x chains of the slice [c0, c0+n)
+                             int nt, int nx, int C, int c0, int n, int t_off, int nt_global) {
+  const size_t total = (size_t)nt * nx * n;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t site = i / n;
     const size_t k = site * C + c0 + (i % n);
     const int x = (int)(site % nx);
-    const int t = (int)(site / nx);
+    const int t = (int)(site / nx) + t_off;
     const double2 a = A[k];
     double s0, c0v, s1, c1;
     sincos(a.x, &s0, &c0v);
     sincos(a.y, &s1, &c1);
     double f0 = (x & 1) ? -0.5 : 0.5;
-    if (t == nt - 1) f0 = -f0;
+    if (t == nt_global - 1) f0 = -f0;
     const double f1 = (x == nx - 1) ? -0.5 : 0.5;
     W0[k] = make_double2(f0 * c0v, f0 * s0);
     W1[k] = make_double2(f1 * c1, f1 * s1);
   }
 }
 
-// (C x V) double2 -> (V x C) double2 tiled transpose and its inverse.
+// src[r * ld_src + c], r < rows, c < cols   ->   dst[c * ld_dst + r]   (tiled transpose of double2)
 __global__ void transpose_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, int rows, int cols,
                                  size_t ld_src, size_t ld_dst) {
-  // src[r * ld_src + c], r < rows, c < cols   ->   dst[c * ld_dst + r]
   __shared__ double2 tile[32][33];
   const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -416,7 +596,8 @@ int tb_launch_links_slice(tb_ctx *ctx, const double2 *d_A_dev_layout, int c0, in
   const size_t total = ctx->V * (size_t)n;
   int blocks = (int)((total + 255) / 256);
   if (blocks > TB_NUM_SMS_B200 * 16) blocks = TB_NUM_SMS_B200 * 16;
-  links_kernel<<<blocks, 256, 0, st>>>(d_A_dev_layout, ctx->W0, ctx->W1, ctx->nt, ctx->nx, ctx->C, c0, n);
+  links_kernel<<<blocks, 256, 0, st>>>(d_A_dev_layout, ctx->W0, ctx->W1, ctx->nt, ctx->nx, ctx->C, c0, n,
+                                       ctx->t_off, ctx->nt_global);
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
   return TB_OK;
@@ -465,61 +646,112 @@ int tb_launch_unpack(tb_ctx *ctx, const double2 *d_vec, double *d_canonical) {
   return tb_launch_unpack_slice(ctx, d_vec, (double2 *)d_canonical, 0, ctx->C, ctx->stream);
 }
 
-int tb_launch_dslash(tb_ctx *ctx, bool dagger, const double2 *in, double2 *out, bool masked) {
+// Generic dslash launch.  masked/dot select the CG variants; in slab mode the halo pointers and the flag protocol
+// (wait_ready, wait_done, sig0, sig1) come from the caller.
+struct DslashArgs {
+  const double2 *in, *in_prev, *in_next;
+  double2 *out;
+  const double2 *aux;
+  bool dagger, dot, masked;
+  int wait_ready, wait_done, sig0, sig1;
+};
+
+template <bool SLAB>
+static int launch_dslash_t(tb_ctx *ctx, const DslashArgs &a) {
   const TbGeom &g = ctx->g;
   const dim3 grid = grid_of(g);
   const int block = g.bc * g.bx;
-#define ARGS in, out, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu, nullptr, g, ctx->cg
-  if (masked) {
-    if (dagger) { TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, true, false, true><<<grid, block, 0, ctx->stream>>>(ARGS))) }
-    else { TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, false, false, true><<<grid, block, 0, ctx->stream>>>(ARGS))) }
+  const double2 *w0p = SLAB ? ctx->slab.W0_prev : ctx->W0;
+#define ARGS a.in, a.in_prev, a.in_next, a.out, ctx->W0, w0p, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu, a.aux, g, \
+             ctx->cg, ctx->slab, a.wait_ready, a.wait_done, a.sig0, a.sig1
+#define L(DAG, DOT, MASKED) \
+  TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, DAG, DOT, MASKED, SLAB><<<grid, block, 0, ctx->stream>>>(ARGS)))
+  if (a.dot) {
+    if (a.masked) { if (a.dagger) { L(true, true, true) } else { L(false, true, true) } }
+    else { if (a.dagger) { L(true, true, false) } else { L(false, true, false) } }
   } else {
-    if (dagger) { TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, true, false, false><<<grid, block, 0, ctx->stream>>>(ARGS))) }
-    else { TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, false, false, false><<<grid, block, 0, ctx->stream>>>(ARGS))) }
+    if (a.masked) { if (a.dagger) { L(true, false, true) } else { L(false, false, true) } }
+    else { if (a.dagger) { L(true, false, false) } else { L(false, false, false) } }
   }
+#undef L
 #undef ARGS
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
   return TB_OK;
 }
 
-// q = M~ Mp with fused alpha = rr_old / Re<p,q>
-static int launch_dslash_pq(tb_ctx *ctx, bool dagger, const double2 *in, double2 *out, const double2 *aux) {
-  const TbGeom &g = ctx->g;
-  const dim3 grid = grid_of(g);
-  const int block = g.bc * g.bx;
-#define ARGS in, out, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu, aux, g, ctx->cg
-  if (dagger) { TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, true, true, true><<<grid, block, 0, ctx->stream>>>(ARGS))) }
-  else { TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, false, true, true><<<grid, block, 0, ctx->stream>>>(ARGS))) }
-#undef ARGS
-  ctx->launches++;
-  TB_CUDA(cudaGetLastError());
-  return TB_OK;
+int tb_launch_dslash(tb_ctx *ctx, bool dagger, const double2 *in, double2 *out, bool masked) {
+  DslashArgs a = {in, in, in, out, nullptr, dagger, false, masked, 0, -1, 0, -1};
+  return launch_dslash_t<false>(ctx, a);
 }
 
 int tb_launch_dot(tb_ctx *ctx, const double2 *a, const double2 *b, double *d_out) {
   const TbGeom &g = ctx->g;
   TbCgState s = ctx->cg;
   s.dot = d_out;
-  TB_DISPATCH_TT(g.tt, (dot_kernel<TT><<<grid_of(g), g.bc * g.bx, 0, ctx->stream>>>(a, b, g, s)))
+  TB_DISPATCH_TT(g.tt, (dot_kernel<TT><<<grid_of(g), g.bc * g.bx, 0, ctx->stream>>>(a, b, g, s, ctx->slab)))
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
   return TB_OK;
 }
 
+template <bool SLAB>
 static int cg_iteration(tb_ctx *ctx, double2 *x) {
   const TbGeom &g = ctx->g;
   const dim3 grid = grid_of(g);
   const int block = g.bc * g.bx;
-  TB_CHECK(tb_launch_dslash(ctx, false, ctx->p, ctx->Mp, true));                       // hmc.c:366
-  TB_CHECK(launch_dslash_pq(ctx, tb_conj_is_dagger(ctx), ctx->Mp, ctx->q, ctx->p));    // hmc.c:367-371
-  TB_DISPATCH_TT(g.tt, (axpy_norm_kernel<TT><<<grid, block, 0, ctx->stream>>>(x, ctx->r, ctx->p, ctx->q, g, ctx->cg)))
+  const TbSlab &sl = ctx->slab;
+  cudaStream_t st = ctx->stream;
+  const bool dag = tb_conj_is_dagger(ctx);
+  // Mp = M p (hmc.c:366).  slab: needs generation E of the neighbours' p, overwrites Mp (neighbours must have
+  // finished reading generation E-1), then publishes Mp and releases p.
+  DslashArgs k1 = {ctx->p, SLAB ? sl.p_prev : ctx->p, SLAB ? sl.p_next : ctx->p, ctx->Mp, nullptr, false, false, true,
+                   TB_FLAG_PREADY, TB_FLAG_MPDONE, TB_FLAG_MPREADY, TB_FLAG_PDONE};
+  TB_CHECK(launch_dslash_t<SLAB>(ctx, k1));
+  // q = M~ Mp with the fused Re<p,q> (hmc.c:367-371)
+  DslashArgs k2 = {ctx->Mp, SLAB ? sl.mp_prev : ctx->Mp, SLAB ? sl.mp_next : ctx->Mp, ctx->q, ctx->p, dag, true, true,
+                   TB_FLAG_MPREADY, -1, TB_FLAG_MPDONE, -1};
+  TB_CHECK(launch_dslash_t<SLAB>(ctx, k2));
+  if (SLAB) {
+    slab_scalars_kernel<FIN_PQ, TB_RED_PQ><<<1, TB_MAX_BLOCK, 0, st>>>(g, ctx->cg, sl);
+    ctx->launches++;
+  }
+  TB_DISPATCH_TT(g.tt, (axpy_norm_kernel<TT, SLAB><<<grid, block, 0, st>>>(x, ctx->r, ctx->p, ctx->q, g, ctx->cg, sl)))
   ctx->launches++;
+  if (SLAB) {
+    slab_scalars_kernel<FIN_RR, TB_RED_RR><<<1, TB_MAX_BLOCK, 0, st>>>(g, ctx->cg, sl);
+    ctx->launches++;
+  }
   TB_CUDA(cudaGetLastError());
-  TB_DISPATCH_TT(g.tt, (xpay_kernel<TT><<<grid, block, 0, ctx->stream>>>(ctx->p, ctx->r, g, ctx->cg)))
+  TB_DISPATCH_TT(g.tt, (xpay_kernel<TT, SLAB><<<grid, block, 0, st>>>(ctx->p, ctx->r, g, ctx->cg, sl)))
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
   return TB_OK;
+}
+
+// slab mode: out = Op in on the distributed lattice (collective: every rank calls it with its slab)
+int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out) {
+  const TbGeom &g = ctx->g;
+  const TbSlab &sl = ctx->slab;
+  cudaStream_t st = ctx->stream;
+  const bool dag = tb_conj_is_dagger(ctx);
+  slab_bump_kernel<<<1, 1, 0, st>>>(sl);
+  TB_DISPATCH_TT(g.tt, (slab_stage_kernel<TT><<<grid_of(g), g.bc * g.bx, 0, st>>>(in, ctx->p, g, sl)))
+  ctx->launches += 2;
+  TB_CUDA(cudaGetLastError());
+  if (op == TB_OP_MDM) {
+    DslashArgs k1 = {ctx->p, sl.p_prev, sl.p_next, ctx->Mp, nullptr, false, false, false,
+                     TB_FLAG_PREADY, TB_FLAG_MPDONE, TB_FLAG_MPREADY, TB_FLAG_PDONE};
+    TB_CHECK(launch_dslash_t<true>(ctx, k1));
+    DslashArgs k2 = {ctx->Mp, sl.mp_prev, sl.mp_next, out, nullptr, dag, false, false,
+                     TB_FLAG_MPREADY, -1, TB_FLAG_MPDONE, -1};
+    return launch_dslash_t<true>(ctx, k2);
+  }
+  const bool d = (op == TB_OP_MDAG) || (op == TB_OP_MCONJ && dag);
+  // a single apply reads only p: release both exchange vectors for the next epoch
+  DslashArgs k = {ctx->p, sl.p_prev, sl.p_next, out, nullptr, d, false, false,
+                  TB_FLAG_PREADY, -1, TB_FLAG_PDONE, TB_FLAG_MPDONE};
+  return launch_dslash_t<true>(ctx, k);
 }
 
 // Streaming CG driver: the whole solve stays on the device; the host only polls the number of chains
@@ -529,10 +761,18 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
   const dim3 grid = grid_of(g);
   const int block = g.bc * g.bx;
   cudaStream_t st = ctx->stream;
+  const bool slab = ctx->nranks > 1;
   cg_reset_kernel<<<(g.Cpad + 255) / 256, 256, 0, st>>>(g, ctx->cg);
   ctx->launches++;
-  TB_DISPATCH_TT(g.tt, (cg_init_kernel<TT><<<grid, block, 0, st>>>(b, ctx->xw, ctx->r, ctx->p, g, ctx->cg)))
-  ctx->launches++;
+  if (slab) {
+    slab_bump_kernel<<<1, 1, 0, st>>>(ctx->slab);
+    TB_DISPATCH_TT(g.tt, (cg_init_kernel<TT, true><<<grid, block, 0, st>>>(b, ctx->xw, ctx->r, ctx->p, g, ctx->cg, ctx->slab)))
+    slab_scalars_kernel<FIN_INIT, TB_RED_INIT><<<1, TB_MAX_BLOCK, 0, st>>>(g, ctx->cg, ctx->slab);
+    ctx->launches += 3;
+  } else {
+    TB_DISPATCH_TT(g.tt, (cg_init_kernel<TT, false><<<grid, block, 0, st>>>(b, ctx->xw, ctx->r, ctx->p, g, ctx->cg, ctx->slab)))
+    ctx->launches++;
+  }
   TB_CUDA(cudaGetLastError());
 
   int chunk = ctx->tune_chunk > 0 ? ctx->tune_chunk : 16;
@@ -546,7 +786,7 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
     ctx->stream = cap;
     TB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed));
     int rc = TB_OK;
-    for (int i = 0; i < chunk && rc == TB_OK; i++) rc = cg_iteration(ctx, ctx->xw);
+    for (int i = 0; i < chunk && rc == TB_OK; i++) rc = slab ? cg_iteration<true>(ctx, ctx->xw) : cg_iteration<false>(ctx, ctx->xw);
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(cap, &graph);
     ctx->stream = saved;
@@ -563,9 +803,9 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
   for (long i = 0; i < max_chunks; i++) {
     if (use_graph) {
       TB_CUDA(cudaGraphLaunch(ctx->cg_graph, st));
-      ctx->launches += 4LL * chunk;
+      ctx->launches += (slab ? 6LL : 4LL) * chunk;
     } else {
-      for (int k = 0; k < chunk; k++) TB_CHECK(cg_iteration(ctx, ctx->xw));
+      for (int k = 0; k < chunk; k++) TB_CHECK(slab ? cg_iteration<true>(ctx, ctx->xw) : cg_iteration<false>(ctx, ctx->xw));
     }
     const int slot = (int)(i & 1);
     TB_CUDA(cudaMemcpyAsync(&ctx->h_flag[slot], ctx->cg.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));

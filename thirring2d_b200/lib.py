@@ -42,6 +42,10 @@ SIGNATURES = {
     "tb_invert_dev": (_i, [_vp, _vp, _vp]),
     "tb_cg_result": (_i, [_vp, _ip, _ip, _dp]),
     "tb_re_dot_dev": (_i, [_vp, _vp, _vp, _dp]),
+    "tb_create_slab": (_i, [C.POINTER(_vp), _i, _i, _i, _i, _i, _i, _i]),
+    "tb_slab_handle_bytes": (_i, []),
+    "tb_slab_export": (_i, [_vp, _vp]),
+    "tb_slab_connect": (_i, [_vp, _vp]),
     "tb_launch_count": (C.c_longlong, [_vp]),
     "tb_reset_launch_count": (_i, [_vp]),
     "tb_last_solve_ms": (_d, [_vp]),
