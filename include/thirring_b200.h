@@ -126,6 +126,39 @@ int tb_slab_handle_bytes(void);
 int tb_slab_export(tb_ctx *ctx, void *handle_out);
 int tb_slab_connect(tb_ctx *ctx, const void *all_handles);
 
+/* ---- device-resident batched HMC trajectory: the caller of the hot path -----------
+ * update_gauge (hmc.c:671-746) for every chain at once, as coded (leapfrog of hmc.c:708-716 with runtime nsteps
+ * and trajectory length instead of the hard-coded 10 and 1, forces of hmc.c:504-661, Metropolis test of
+ * hmc.c:738).  Nothing crosses PCIe during a trajectory except the per-chain observables at the end. */
+
+/* coupling g (global hmc.c:39): Nf/g with Nf = 2 (hmc.c:28); n == 1 broadcasts, n == nchains per chain */
+int tb_hmc_set_coupling(tb_ctx *ctx, const double *g, int n);
+
+/* `sweeps` quenched heat-bath sweeps of every link (update_puregauge_hb, hmc.c:82-93; main() does 100 from
+ * A = 0, hmc.c:927-929).  Random numbers: device Philox keyed by (seed, chain). */
+int tb_hmc_heatbath(tb_ctx *ctx, int sweeps, unsigned long long seed);
+
+/* One trajectory per chain.  The four random inputs are drawn on the device (Philox keyed by seed, chain,
+ * traj_index) when the pointer is NULL, or taken from the host for parity tests: xi_host / st_host complex
+ * [chain][t][x] (random_pseudofermion hmc.c:418, stochastic_vector hmc.c:439), mom_host real [chain][t][x][2]
+ * (random_momentum hmc.c:483), u_host [chain] (the Metropolis uniform, hmc.c:738).
+ * obs_host (may be NULL): 10 doubles per chain = Sg, Smdm, Smd, Smom at the start (hmc.c:701), the same four
+ * at the end (hmc.c:735), dS, accepted.  accepted_host[chain], cg_iters_host (sum over chains and solves)
+ * may be NULL.  A chain whose CG diverges or hits max-iter is rejected. */
+int tb_hmc_trajectory(tb_ctx *ctx, int nsteps, double traj_length, unsigned long long seed,
+                      unsigned int traj_index, const double *xi_host, const double *mom_host,
+                      const double *st_host, const double *u_host, double *obs_host, int *accepted_host,
+                      long long *cg_iters_host);
+
+/* measure() (hmc.c:823-842) per chain: Magnetisation = sum A / V and Phase = (1/nsrc) sum Im<c, M~ c> over nsrc
+ * stochastic vectors (fermion_phase hmc.c:794-815 uses 20).  sources_host (optional): complex
+ * [nsrc][chain][t][x]. */
+int tb_hmc_measure(tb_ctx *ctx, int nsrc, unsigned long long seed, unsigned int meas_index,
+                   const double *sources_host, double *magnetisation_host, double *phase_host);
+
+/* current gauge angles to the host, double[nchains][NT][NX][2] */
+int tb_get_gauge(tb_ctx *ctx, double *A_host);
+
 /* Counters for bench.py: kernels launched by this context since creation / since the last reset. */
 long long tb_launch_count(const tb_ctx *ctx);
 int tb_reset_launch_count(tb_ctx *ctx);

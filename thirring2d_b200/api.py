@@ -210,6 +210,55 @@ class Context:
               "tb_re_dot_dev")
         return out
 
+    # -- device-resident HMC trajectory (hmc.c:671-746, batched) ------------------------------------------
+    def hmc_set_coupling(self, g):
+        g = np.ascontiguousarray(np.atleast_1d(np.asarray(g, dtype=np.float64)))
+        check(self.lib.tb_hmc_set_coupling(self._h, g.ctypes.data_as(_dp), g.size), "tb_hmc_set_coupling")
+
+    def hmc_heatbath(self, sweeps=100, seed=1):
+        check(self.lib.tb_hmc_heatbath(self._h, sweeps, seed), "tb_hmc_heatbath")
+
+    def get_gauge(self):
+        A = np.empty((self.nchains, self.nt, self.nx, 2), dtype=np.float64)
+        check(self.lib.tb_get_gauge(self._h, A.ctypes.data), "tb_get_gauge")
+        return A
+
+    def hmc_trajectory(self, nsteps=10, traj_length=1.0, seed=1, traj_index=0, xi=None, mom=None, st=None, u=None):
+        """update_gauge for every chain.  Returns (obs, accepted, cg_iterations): obs[c] = Sg, Smdm, Smd, Smom,
+        Sg', Smdm', Smd', Smom', dS, accepted.  xi/mom/st/u: host random inputs for parity tests (else Philox)."""
+        keep = []
+
+        def ptr(arr, dtype, shape):
+            if arr is None:
+                return None
+            arr = np.ascontiguousarray(arr, dtype=dtype)
+            assert arr.shape == shape, (arr.shape, shape)
+            keep.append(arr)
+            return arr.ctypes.data
+
+        vs = (self.nchains, self.nt, self.nx)
+        obs = np.empty((self.nchains, 10), dtype=np.float64)
+        acc = np.empty(self.nchains, dtype=np.int32)
+        its = C.c_longlong(0)
+        check(self.lib.tb_hmc_trajectory(self._h, nsteps, traj_length, seed, traj_index,
+                                         ptr(xi, np.complex128, vs), ptr(mom, np.float64, vs + (2,)),
+                                         ptr(st, np.complex128, vs), ptr(u, np.float64, (self.nchains,)),
+                                         obs.ctypes.data, acc.ctypes.data_as(_ip), C.byref(its)),
+              "tb_hmc_trajectory")
+        return obs, acc, its.value
+
+    def hmc_measure(self, nsrc=20, seed=1, meas_index=0, sources=None):
+        mag = np.empty(self.nchains, dtype=np.float64)
+        ph = np.empty(self.nchains, dtype=np.float64)
+        src = None
+        if sources is not None:
+            sources = np.ascontiguousarray(sources, dtype=np.complex128)
+            assert sources.shape == (nsrc, self.nchains, self.nt, self.nx)
+            src = sources.ctypes.data
+        check(self.lib.tb_hmc_measure(self._h, nsrc, seed, meas_index, src, mag.ctypes.data_as(_dp),
+                                      ph.ctypes.data_as(_dp)), "tb_hmc_measure")
+        return mag, ph
+
     @property
     def launch_count(self):
         return int(self.lib.tb_launch_count(self._h))

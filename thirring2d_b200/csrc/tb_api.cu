@@ -186,6 +186,7 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
   invalidate_graph(ctx);
   const bool slab = ctx->nranks > 1;
   tb_slab_release(ctx);
+  tb_hmc_release(ctx);
   void *dev[] = {ctx->d_mass, ctx->d_emu, ctx->d_emmu, slab ? nullptr : (void *)ctx->W0, ctx->W1, ctx->Adev, ctx->r,
                  slab ? nullptr : (void *)ctx->p, slab ? nullptr : (void *)ctx->Mp, ctx->q, ctx->xw, ctx->tmp, ctx->vin, ctx->vout, ctx->stage, ctx->stage_x, ctx->cg.rr_old, ctx->cg.active,
                  ctx->cg.partial, ctx->cg.ticket};
@@ -386,7 +387,7 @@ extern "C" int tb_apply_dev(tb_ctx *ctx, int op, const double *d_in, double *d_o
   }
 }
 
-static int run_cg(tb_ctx *ctx, const double2 *b, double2 *x) {
+int tb_run_cg_any(tb_ctx *ctx, const double2 *b, double2 *x) {
   TB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   // solver selection: 0 auto (resident when the lattice fits on chip), 1 streaming, 2 resident
   const bool resident = ctx->tune_solver != 1 && tb_resident_supported(ctx);
@@ -409,7 +410,7 @@ extern "C" int tb_cg_dev(tb_ctx *ctx, const double *d_b, double *d_x) {
   TB_CUDA(cudaSetDevice(ctx->device));
   TB_CHECK(join_subs(ctx));
   TB_CHECK(need_gauge(ctx));
-  return run_cg(ctx, (const double2 *)d_b, (double2 *)d_x);
+  return tb_run_cg_any(ctx, (const double2 *)d_b, (double2 *)d_x);
 }
 
 extern "C" int tb_invert_dev(tb_ctx *ctx, const double *d_v, double *d_x) {
@@ -420,7 +421,7 @@ extern "C" int tb_invert_dev(tb_ctx *ctx, const double *d_v, double *d_x) {
   // fm_invert_cg, hmc.c:408-414
   if (ctx->nranks > 1) TB_CHECK(tb_slab_apply(ctx, TB_OP_MCONJ, (const double2 *)d_v, ctx->tmp));
   else TB_CHECK(tb_launch_dslash(ctx, tb_conj_is_dagger(ctx), (const double2 *)d_v, ctx->tmp, false));
-  return run_cg(ctx, ctx->tmp, (double2 *)d_x);
+  return tb_run_cg_any(ctx, ctx->tmp, (double2 *)d_x);
 }
 
 extern "C" int tb_cg_result(tb_ctx *ctx, int *status, int *iters, double *rr) {

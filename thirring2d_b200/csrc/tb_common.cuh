@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -85,6 +86,13 @@ struct TbSlab {
   int *err;                    // set when a flag wait timed out
 };
 
+// buffers of the device-resident HMC trajectory (tb_hmc.cu), allocated at first use
+struct TbHmc {
+  double2 *mom, *newA, *psi, *st, *chi, *phi, *gauss;
+  double *sums, *obs, *u, *nf_over_g;
+  int *accept, *failed;
+};
+
 struct tb_ctx {
   int nt, nx, C, mode, device;
   size_t V;          // nt*nx
@@ -129,6 +137,7 @@ struct tb_ctx {
   TbSlab slab;
   cudaGraphExec_t slab_graph;
   int slab_graph_chunk;
+  TbHmc hmc;
 };
 
 int tb_choose_geom(tb_ctx *ctx);
@@ -148,6 +157,8 @@ bool tb_resident_supported(const tb_ctx *ctx);
 int tb_launch_dot(tb_ctx *ctx, const double2 *a, const double2 *b, double *d_out);
 int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out);
 int tb_slab_layout(tb_ctx *ctx);
+int tb_run_cg_any(tb_ctx *ctx, const double2 *b, double2 *x);
+void tb_hmc_release(tb_ctx *ctx);
 int tb_create_common(tb_ctx **out, int nt_local, int nx, int nchains, int mode, int device, int rank, int nranks,
                      int nt_global);
 

@@ -46,6 +46,12 @@ SIGNATURES = {
     "tb_slab_handle_bytes": (_i, []),
     "tb_slab_export": (_i, [_vp, _vp]),
     "tb_slab_connect": (_i, [_vp, _vp]),
+    "tb_hmc_set_coupling": (_i, [_vp, _dp, _i]),
+    "tb_hmc_heatbath": (_i, [_vp, _i, C.c_ulonglong]),
+    "tb_hmc_trajectory": (_i, [_vp, _i, _d, C.c_ulonglong, C.c_uint, _vp, _vp, _vp, _vp, _vp, _ip,
+                               C.POINTER(C.c_longlong)]),
+    "tb_hmc_measure": (_i, [_vp, _i, C.c_ulonglong, C.c_uint, _vp, _dp, _dp]),
+    "tb_get_gauge": (_i, [_vp, _vp]),
     "tb_launch_count": (C.c_longlong, [_vp]),
     "tb_reset_launch_count": (_i, [_vp]),
     "tb_last_solve_ms": (_d, [_vp]),
