@@ -36,6 +36,7 @@ MASS, MU, G = 0.1, 0.0, 0.3
 BYTES_PER_SITE_ITER = 288  # K1 64 + K2 80 + K3 96 + K4 48
 BYTES_PER_SITE_APPLY = 64
 METRIC, UNIT = "dirac_applies_per_sec", "applies/s"
+HMC_NSTEPS = 40  # m = 0.1 needs 40 leapfrog steps (the reference hard-codes 10, hmc.c:708)
 
 
 def workload_name(chains):
@@ -101,7 +102,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02)
 
     def result(self):
         self.stop_flag = True
@@ -127,6 +128,23 @@ def run_cpu_reference(chains_total, procs):
     applies = sum(o["applies"] for o in outs)
     busy = max(o["seconds"] for o in outs)  # solver time of the slowest worker (excludes python start-up)
     return applies / busy, busy, applies, outs[0]["kind"], per * procs, wall
+
+
+def run_cpu_reference_hmc(procs):
+    """One full trajectory of the reference's own driver per host core (oracle/_ref/ref_hmc + the 40-step
+    ADJOINT build of hmc.c); returns trajectories/s over all cores, or None when the build is absent."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_hmc")
+    so = os.path.join(ROOT, "oracle", "_ref", f"libhmcref_{NT}x{NX}_adjoint_ns{HMC_NSTEPS}.so")
+    if not (os.path.exists(exe) and os.path.exists(so)):
+        return None
+    t0 = time.perf_counter()
+    ps = [subprocess.Popen([exe, so], stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, text=True) for _ in range(procs)]
+    for i, p in enumerate(ps):
+        p.stdin.write(f"1\n100\n{MASS}\n{G}\n{MU}\n{4354365264 + 2 * i}\n")
+        p.stdin.close()
+    for p in ps:
+        p.wait()
+    return procs / (time.perf_counter() - t0)
 
 
 def reference_arm(args):
@@ -210,6 +228,8 @@ def gpu_arm(args):
         ctx.cg_dev(b.data_ptr(), x.data_ptr())
         return ctx.last_solve_ms
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     info = ctx.cg_result()
@@ -217,8 +237,6 @@ def gpu_arm(args):
     iters = info.iters.astype(np.int64)
     applies_per_step = int(2 * iters.sum())
 
-    sampler = ClockSampler(local)
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ctx.reset_launch_count()
@@ -229,7 +247,6 @@ def gpu_arm(args):
     e1.record()
     barrier()
     launches = ctx.launch_count
-    clocks = sampler.result()
     ms_total = e0.elapsed_time(e1)
 
     # e2e: the host-buffer C-ABI entry points a reference-side caller binds
@@ -248,13 +265,31 @@ def gpu_arm(args):
     x_dev_canon = torch.empty_like(xi_canon)
     ctx.unpack_dev(x.data_ptr(), x_dev_canon.data_ptr())
     assert torch.equal(x_dev_canon.cpu(), x_host), "e2e and device-resident solutions differ"
+    clocks = sampler.result()  # sampled every 20 ms over warm-up, the timed region and the e2e region
 
-    t = torch.tensor([ms_total, e2e_s * 1e3, solve_ms], dtype=torch.float64, device=dev)
+    # HMC trajectories/s on the same workload (device-resident update_gauge, hmc.c:671-746, for all chains)
+    hmc = None
+    if not args.no_hmc:
+        ctx.hmc_set_coupling(G)
+        ctx.hmc_heatbath(100, seed=1000 + rank)           # main()'s quenched start, hmc.c:927-929
+        ctx.hmc_trajectory(HMC_NSTEPS, 1.0, seed=77 + rank, traj_index=0)
+        barrier()
+        t0 = time.perf_counter()
+        acc_sum, it_sum = 0.0, 0
+        for k in range(args.traj):
+            obs, acc, its = ctx.hmc_trajectory(HMC_NSTEPS, 1.0, seed=77 + rank, traj_index=1 + k)
+            acc_sum += float(acc.mean())
+            it_sum += its
+        torch.cuda.synchronize()
+        hmc_s = time.perf_counter() - t0
+        hmc = (hmc_s, acc_sum / args.traj, it_sum / (args.traj * chains * (HMC_NSTEPS + 1)))
+
+    t = torch.tensor([ms_total, e2e_s * 1e3, solve_ms, hmc[0] if hmc else 0.0], dtype=torch.float64, device=dev)
     cnt = torch.tensor([applies_per_step, launches], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_total, e2e_ms, solve_ms = t.tolist()
+    ms_total, e2e_ms, solve_ms, hmc_s = t.tolist()
     applies_all, launches_all = cnt.tolist()
 
     stream_roof = None
@@ -299,6 +334,13 @@ def gpu_arm(args):
             "gpu_launches": int(launches_all),
             "clocks": clocks,
         }
+        if hmc is not None:
+            line["hmc"] = {"traj_per_sec": world * chains * args.traj / hmc_s, "unit": "trajectories/s",
+                           "ms_per_batched_trajectory": 1e3 * hmc_s / args.traj, "nsteps": HMC_NSTEPS,
+                           "traj_length": 1.0, "acceptance": hmc[1], "cg_iters_per_solve": hmc[2],
+                           "note": "update_gauge as coded (hmc.c:671-746) for every chain, device-resident; "
+                                   "nsteps = 40 because the hard-coded 10 has zero acceptance at m = 0.1 "
+                                   "(SURVEY Appendix C)"}
         if stream_roof is not None:
             line["roofline_streaming"] = stream_roof
         if world == 1 and not args.no_cpu_baseline:
@@ -307,6 +349,12 @@ def gpu_arm(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"{nch} chain solves of the same workload ({NT}x{NX}, m={MASS}), "
                                               f"{cores} single-threaded processes, {busy:.1f} s"}
+            if hmc is not None:
+                tps = run_cpu_reference_hmc(cores)
+                if tps is not None:
+                    line["hmc"]["cpu_baseline"] = {"traj_per_sec": tps, "cores": cores, "kind": "reference",
+                                                   "sample": f"1 trajectory per core of the reference's own hmc.c "
+                                                             f"driver ({NT}x{NX}, m={MASS}, {HMC_NSTEPS} steps)"}
         print(json.dumps(line), flush=True)
     ctx.close()
     if world > 1:
@@ -356,6 +404,8 @@ def main():
     ap.add_argument("--solver", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the streaming-path roofline measurement")
+    ap.add_argument("--no-hmc", action="store_true", help="skip the trajectories/s measurement")
+    ap.add_argument("--traj", type=int, default=2, help="timed trajectories for the hmc figure")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -1,0 +1,95 @@
+"""Parity at BASELINE.json's full sizes through size-independent properties (the oracle would need minutes to
+hours there): adjointness, linearity, the CG residual checked by an independent apply, agreement of the two
+solvers, and a checksum of the batched result against single-chain solves of a few sampled chains."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+tb = pytest.importorskip("thirring2d_b200")
+
+
+def dev_vec(ctx, gen):
+    return torch.randn(ctx.vec_doubles, dtype=torch.float64, device="cuda", generator=gen)
+
+
+def cdot(a, b):
+    """<a,b> per whole batch for interleaved (re,im) device vectors."""
+    ar, ai, br, bi = a[0::2], a[1::2], b[0::2], b[1::2]
+    return complex(float((ar * br + ai * bi).sum()), float((ar * bi - ai * br).sum()))
+
+
+@pytest.mark.parametrize("nt,nx,nchains", [(64, 64, 256), (256, 256, 8), (2048, 2048, 1), (128, 128, 64)])
+def test_apply_adjointness_and_linearity_full_size(nt, nx, nchains):
+    gen = torch.Generator(device="cuda").manual_seed(nt + nchains)
+    with tb.Context(nt, nx, nchains, tb.MODE_ADJOINT, m=0.05, mu=0.1,
+                    stream=torch.cuda.current_stream().cuda_stream) as ctx:
+        A = (torch.rand(nchains * nt * nx * 2, dtype=torch.float64, device="cuda", generator=gen) - 0.5) * (2 * np.pi)
+        ctx.set_gauge_dev(A.data_ptr())
+        a, b = dev_vec(ctx, gen), dev_vec(ctx, gen)
+        Mb, Mda, Mab = torch.empty_like(a), torch.empty_like(a), torch.empty_like(a)
+        ctx.apply_dev(tb.OP_M, b.data_ptr(), Mb.data_ptr())
+        ctx.apply_dev(tb.OP_MDAG, a.data_ptr(), Mda.data_ptr())
+        lhs, rhs = cdot(a, Mb), cdot(Mda, b)
+        assert abs(lhs - rhs) <= 1e-12 * abs(lhs) + 1e-7, (lhs, rhs)       # <a, M b> = <M^dagger a, b>
+        # linearity: M(a + 2 b) = M a + 2 M b
+        ab = a + 2.0 * b
+        Ma = torch.empty_like(a)
+        ctx.apply_dev(tb.OP_M, a.data_ptr(), Ma.data_ptr())
+        ctx.apply_dev(tb.OP_M, ab.data_ptr(), Mab.data_ptr())
+        err = float((Mab - (Ma + 2.0 * Mb)).norm() / Mab.norm())
+        assert err <= 1e-14
+        # M~M is Hermitian positive: <b, M^dagger M b> = |M b|^2
+        MdMb = torch.empty_like(a)
+        ctx.apply_dev(tb.OP_MDM, b.data_ptr(), MdMb.data_ptr())
+        q = cdot(b, MdMb)
+        assert abs(q.imag) <= 1e-12 * q.real and abs(q.real - float((Mb * Mb).sum())) <= 1e-12 * q.real
+
+
+@pytest.mark.parametrize("nt,nx,nchains,m,solvers", [(64, 64, 256, 0.1, (2, 1)), (256, 256, 8, 0.05, (1,)),
+                                                      (1024, 1024, 1, 0.1, (1,))])
+def test_cg_residual_full_size(nt, nx, nchains, m, solvers):
+    """The true residual |b - M~M x| / |b| is at rounding level, checked with applies that are independent of
+    the solver's recursion; where both solvers exist they agree to 1e-12 and in iteration count +-1."""
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    sols, iters = [], []
+    with tb.Context(nt, nx, nchains, tb.MODE_ADJOINT, m=m, mu=0.0,
+                    stream=torch.cuda.current_stream().cuda_stream) as ctx:
+        A = torch.randn(nchains * nt * nx * 2, dtype=torch.float64, device="cuda", generator=gen) * 0.6
+        ctx.set_gauge_dev(A.data_ptr())
+        xi = dev_vec(ctx, gen)
+        b, x, chk = torch.empty_like(xi), torch.empty_like(xi), torch.empty_like(xi)
+        ctx.apply_dev(tb.OP_MCONJ, xi.data_ptr(), b.data_ptr())
+        for solver in solvers:
+            ctx.set_tuning(solver=solver)
+            ctx.cg_dev(b.data_ptr(), x.data_ptr())
+            info = ctx.cg_result()
+            assert np.all(info.status == tb.CG_CONVERGED)
+            ctx.apply_dev(tb.OP_MDM, x.data_ptr(), chk.data_ptr())
+            res = float((chk - b).norm() / b.norm())
+            assert res <= 5e-12, res
+            sols.append(x.clone())
+            iters.append(info.iters.copy())
+    if len(sols) == 2:
+        assert float((sols[0] - sols[1]).norm() / sols[1].norm()) <= 1e-12
+        assert np.all(np.abs(iters[0].astype(int) - iters[1].astype(int)) <= 1)
+
+
+def test_batched_solution_equals_single_chain_solutions():
+    """Chains are independent: chain c of the 256-chain batch equals the same chain solved alone (sampled)."""
+    nt = nx = 64
+    n = 256
+    rng = np.random.default_rng(0)
+    A = rng.vonmises(0.0, 2 / 0.3, size=(n, nt, nx, 2))
+    xi = rng.normal(size=(n, nt, nx)) + 1j * rng.normal(size=(n, nt, nx))
+    with tb.Context(nt, nx, n, tb.MODE_ADJOINT, m=0.1) as ctx:
+        ctx.set_gauge(A)
+        b = ctx.fm_conjugate_mul(xi)
+        x, info = ctx.fmdm_invert_cg(b)
+    for c in (0, 101, 255):
+        with tb.Context(nt, nx, 1, tb.MODE_ADJOINT, m=0.1) as one:
+            one.set_gauge(A[c])
+            x1, i1 = one.fmdm_invert_cg(b[c])
+        assert np.array_equal(x1, x[c])          # same kernel, same per-chain arithmetic: bitwise
+        assert i1.iters[0] == info.iters[c]

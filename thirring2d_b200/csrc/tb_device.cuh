@@ -145,8 +145,23 @@ __device__ __forceinline__ void reduce_finalize(double acc, const TbGeom &g, con
   __syncthreads();
   if (!s_last) return;
   __threadfence();
+  // slot order is fixed (deterministic); the loads of a batch are independent so their L2 latency overlaps
   double sum = 0.0;
-  for (int sl_ = b.x_local; sl_ < g.nslots; sl_ += g.bx) sum += __ldcg(&s.partial[(size_t)sl_ * g.Cpad + cp]);
+  {
+    constexpr int NB = 16;
+    const double *pp = s.partial + cp;
+    const size_t stride = (size_t)g.bx * g.Cpad;
+    int sl_ = b.x_local;
+    for (; sl_ + (NB - 1) * g.bx < g.nslots; sl_ += NB * g.bx) {
+      double v[NB];
+      const double *q = pp + (size_t)sl_ * g.Cpad;
+#pragma unroll
+      for (int u = 0; u < NB; u++) v[u] = __ldcg(q + u * stride);
+#pragma unroll
+      for (int u = 0; u < NB; u++) sum += v[u];
+    }
+    for (; sl_ < g.nslots; sl_ += g.bx) sum += __ldcg(pp + (size_t)sl_ * g.Cpad);
+  }
   red[idx] = sum;
   __syncthreads();
   for (int st = g.bx >> 1; st > 0; st >>= 1) {

@@ -63,7 +63,11 @@ def probe(nt, nx, C, m, rows=0, chunk=0, solver=0, reps=20, max_iter=100000):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cfg", nargs="*", default=None)
+    ap.add_argument("--one", nargs=3, type=int, default=None, help="NT NX C: one streaming-solver run, 60 iterations")
     args = ap.parse_args()
+    if args.one:
+        print(json.dumps(probe(args.one[0], args.one[1], args.one[2], 0.01, solver=1, reps=3, max_iter=61)))
+        sys.exit(0)
     cfgs = [(64, 64, 256, 0.1), (64, 64, 1024, 0.1), (256, 256, 64, 0.1), (2048, 2048, 1, 0.1), (32, 32, 1, 1.0),
             (128, 128, 512, 0.1)]
     for c in cfgs:
