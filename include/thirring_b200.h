@@ -81,6 +81,14 @@ int tb_set_tuning(tb_ctx *ctx, int rows_per_thread, int iters_per_launch, int so
  * sin/cos re-evaluated inside every apply, hmc.c:140-141,152-153,163-164,173-174). */
 int tb_set_gauge(tb_ctx *ctx, const double *A_host);
 
+/* Family B (vec_ops.c behind Thirring.h): occupation field int[nchains][NT][NX], 0 = free site (vec_ops.c:107).
+ * Replaces the gauge field: the links become the real constants s*1/2*eta masked by the field (a hop into or out
+ * of an occupied site is dropped, vec_ops.c:110-128) and occupied sites become identity rows (vec_ops.c:130).
+ * With it, TB_OP_M is fM (vec_ops.c:96), TB_OP_MDAG is fM_transpose (vec_ops.c:135), tb_cg is cg_MdM
+ * (vec_ops.c:261) and tb_invert is cg_propagator (vec_ops.c:311) on vectors whose imaginary parts are zero.
+ * Call tb_set_params first: the masses are baked into the per-site mass field. */
+int tb_set_occupancy(tb_ctx *ctx, const int *field_host);
+
 /* out = Op in, Op one of TB_OP_* (fm_mul hmc.c:123, fm_conjugate_mul hmc.c:188, fmdm_mul hmc.c:259). */
 int tb_apply(tb_ctx *ctx, int op, const double *in_host, double *out_host);
 

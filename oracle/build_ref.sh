@@ -46,5 +46,17 @@ done
 # light-mass trajectory oracle: 40 leapfrog steps
 build_one 32 32 adjoint 40
 build_one 64 64 adjoint 40
+# family B: vec_ops.c behind Thirring.h (sizes are unguarded #defines, Thirring.h:14-15).  The translation unit
+# is assembled on gcc's stdin: "#define MAIN" (so that the EXTERN globals of Thirring.h:54-76 are DEFINED here,
+# as the driver fermionbag.c does), the size-rewritten header, then vec_ops.c without its own #include.
+build_vecops() { # NT NX
+  local nt=$1 nx=$2
+  ( echo '#define MAIN'
+    sed "s/^#define NT 64/#define NT ${nt}/; s/^#define NX 64/#define NX ${nx}/" "$REF/Thirring.h"
+    sed '/#include "Thirring.h"/d' "$REF/vec_ops.c" ) | gcc $OPT -std=c99 -w -fPIC -shared \
+      -I"$HERE/shim" -I"$REF" -x c - -x none "$REF/mersenne_inline.c" -o "$OUT/libvecopsref_${nt}x${nx}.so" -lm
+}
+SIZES_B=${TB_REF_SIZES_B:-"16x16 32x32 64x64 16x32"}
+for s in $SIZES_B; do build_vecops "${s%x*}" "${s#*x}"; done
 gcc -O2 -o "$OUT/ref_hmc" "$HERE/ref_launcher.c" -ldl
 ls "$OUT" | sed 's/^/  built oracle\/_ref\//'

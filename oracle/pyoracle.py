@@ -64,6 +64,13 @@ class Oracle:
         L.orc_fermion_matrix.argtypes = [ii, ii, dd, dd, _dp, _dp]
         L.orc_re_dot.argtypes = [ii, _dp, _dp]
         L.orc_re_dot.restype = dd
+        ipp = C.POINTER(C.c_int)
+        L.orc_fM.argtypes = [ii, ii, dd, dd, ipp, _dp, _dp]
+        L.orc_fM_transpose.argtypes = [ii, ii, dd, dd, ipp, _dp, _dp]
+        L.orc_cg_MdM.argtypes = [ii, ii, dd, dd, ipp, _dp, _dp, ipp, _dp]
+        L.orc_cg_MdM.restype = ii
+        L.orc_cg_propagator.argtypes = [ii, ii, dd, dd, ipp, _dp, _dp, ipp, _dp]
+        L.orc_cg_propagator.restype = ii
 
     @staticmethod
     def _prep(v, A):
@@ -116,6 +123,30 @@ class Oracle:
         M = np.empty((V, V), dtype=np.complex128)  # column-major in the reference => transpose below
         self.lib.orc_fermion_matrix(nt, nx, m, mu, _p(A), _p(M))
         return M.T.copy()
+
+
+    # ---- family B (vec_ops.c): real vectors (NT, NX) float64, field (NT, NX) int32 --------------------------
+    @staticmethod
+    def _prep_b(v, field):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        field = np.ascontiguousarray(field, dtype=np.int32)
+        assert v.shape == field.shape
+        return v, field, v.shape[0], v.shape[1]
+
+    def fM(self, psi, field, m, mu, transpose=False):
+        psi, field, nt, nx = self._prep_b(psi, field)
+        chi = np.empty_like(psi)
+        fn = self.lib.orc_fM_transpose if transpose else self.lib.orc_fM
+        fn(nt, nx, m, mu, field.ctypes.data_as(C.POINTER(C.c_int)), _p(psi), _p(chi))
+        return chi
+
+    def cg_MdM(self, source, field, m, mu, propagator=False):
+        source, field, nt, nx = self._prep_b(source, field)
+        inv = np.empty_like(source)
+        it, rr = C.c_int(0), C.c_double(0)
+        fn = self.lib.orc_cg_propagator if propagator else self.lib.orc_cg_MdM
+        st = fn(nt, nx, m, mu, field.ctypes.data_as(C.POINTER(C.c_int)), _p(source), _p(inv), C.byref(it), C.byref(rr))
+        return inv, st, it.value, rr.value
 
 
 def ref_available(nt, nx, flavour="compat", nsteps=10):
@@ -268,3 +299,63 @@ class _Gauge:
     def A(self):
         """(NT, NX, 2) float64 view of the physical links."""
         return self.arr[:, : self.nx, :]
+
+
+def ref_b_available(nt, nx):
+    return os.path.exists(os.path.join(REF_DIR, f"libvecopsref_{nt}x{nx}.so"))
+
+
+class RefLibB:
+    """The reference's own vec_ops.c (family B), compiled unmodified with the EXTERN globals of Thirring.h
+    defined in the same object (oracle/build_ref.sh).  A private RTLD_DEEPBIND copy: its internal calls can
+    never be interposed, so it stays a pure CPU checker even when the GPU shim is loaded globally."""
+
+    def __init__(self, nt, nx, m=1.0, mu=0.0, deepbind=True):
+        src = os.path.join(REF_DIR, f"libvecopsref_{nt}x{nx}.so")
+        if not os.path.exists(src):
+            raise FileNotFoundError(src)
+        fd, tmp = tempfile.mkstemp(prefix="vecopsref_", suffix=".so")
+        os.close(fd)
+        shutil.copyfile(src, tmp)
+        mode = (os.RTLD_LOCAL | os.RTLD_DEEPBIND | os.RTLD_NOW) if deepbind else (os.RTLD_GLOBAL | os.RTLD_NOW)
+        self.lib = L = C.CDLL(tmp, mode=mode)
+        os.unlink(tmp)
+        self.nt, self.nx = nt, nx
+        C.c_double.in_dll(L, "m").value = m
+        C.c_double.in_dll(L, "mu").value = mu
+        self.m, self.mu = m, mu
+        self._tup = np.array([(i + 1) % nt for i in range(nt)], dtype=np.int32)
+        self._tdn = np.array([(i - 1 + nt) % nt for i in range(nt)], dtype=np.int32)
+        self._xup = np.array([(i + 1) % nx for i in range(nx + 1)], dtype=np.int32)
+        self._xdn = np.array([(i - 1 + nx) % nx for i in range(nx + 1)], dtype=np.int32)
+        for name, arr in (("tup", self._tup), ("tdn", self._tdn), ("xup", self._xup), ("xdn", self._xdn)):
+            C.c_void_p.in_dll(L, name).value = arr.ctypes.data
+        eta = np.zeros((nt, nx + 1, 2), dtype=np.int32)   # fermionbag.c:770-781
+        eta[:, :nx, 1] = 1
+        eta[:, 0:nx:2, 0] = 1
+        eta[:, 1:nx:2, 0] = -1
+        self._eta, self._eta_rows, self._eta_top = RefLib._triple(eta)
+        C.c_void_p.in_dll(L, "eta").value = self._eta_top.ctypes.data
+        self.field = np.zeros((nt, nx + 1), dtype=np.int32)   # fermionbag.c:697,710-712
+        self._field_rows = np.ascontiguousarray(
+            self.field.ctypes.data + np.arange(nt, dtype=np.uint64) * ((nx + 1) * 4), dtype=np.uint64)
+        C.c_void_p.in_dll(L, "field").value = self._field_rows.ctypes.data
+        vp = C.c_void_p
+        for f in ("fM", "fM_transpose", "cg_MdM", "cg_propagator"):
+            getattr(L, f).argtypes = [vp, vp]
+            getattr(L, f).restype = None
+
+    def set_field(self, field):
+        self.field[:, : self.nx] = field
+
+    def _rows(self, v):
+        assert v.dtype == np.float64 and v.flags.c_contiguous and v.shape == (self.nt, self.nx)
+        return np.ascontiguousarray(v.ctypes.data + np.arange(self.nt, dtype=np.uint64) * (self.nx * 8), dtype=np.uint64)
+
+    def call(self, fname, src):
+        """All four functions take (out, in) (vec_ops.c:96,135,261,311)."""
+        src = np.ascontiguousarray(src, dtype=np.float64)
+        out = np.zeros_like(src)
+        o, i = self._rows(out), self._rows(src)
+        getattr(self.lib, fname)(o.ctypes.data, i.ctypes.data)
+        return out

@@ -147,7 +147,7 @@ int orc_fmdm_invert_cg(int nt, int nx, double m, double mu, int mode, const doub
     rr_old = rr;
   }
 done:
-  if (iters) *iters = k;
+  if (iters) *iters = (status == ORC_CG_MAXITER) ? k - 1 : k;   /* loop passes executed */
   if (rr_final) *rr_final = rr;
   free(r); free(p); free(Mp); free(MMp);
   return status;
@@ -199,4 +199,101 @@ double orc_re_dot(int n, const double *a, const double *b)
   double s = 0;
   for (int i = 0; i < n; i++) s += a[2 * i] * b[2 * i] + a[2 * i + 1] * b[2 * i + 1];
   return s;
+}
+
+/* ====================================================================================================
+ * Family B: the real, occupation-masked operator of vec_ops.c behind Thirring.h (ANTISYMMETRIC boundaries,
+ * Thirring.h:27).  Vectors are real FP64 flat [t][x]; field[t][x] != 0 marks an occupied site (identity row,
+ * hops into it dropped).  Pinned bit-for-bit against oracle/_ref/libvecopsref_*.so (tests/test_oracle_pinned.py).
+ * ==================================================================================================== */
+#define ORC_B_CG_MAX_ITER 10000   /* Thirring.h:43 */
+
+/* fM (transpose = 0, vec_ops.c:96-133) and fM_transpose (transpose = 1, vec_ops.c:135-172) */
+static void apply_b(int nt, int nx, double m, double mu, int transpose, const int *field,
+                    const double *psi, double *chi)
+{
+  const double expmu = exp(mu), expmmu = exp(-mu);                /* vec_ops.c:101-102 */
+  const double e_up = transpose ? expmmu : expmu, e_dn = transpose ? expmu : expmmu;
+  for (int t = 0; t < nt; t++) for (int x = 0; x < nx; x++) {
+    const int k = t * nx + x;
+    double c = 0;
+    if (field[k] == 0) {
+      c = m * psi[k];
+      int t2 = (t + 1) % nt;
+      if (field[t2 * nx + x] == 0) {
+        double h = 0.5 * eta0(x) * e_up * psi[t2 * nx + x];
+        if ((t2 > t) != transpose) c += h; else c -= h;
+      }
+      t2 = (t - 1 + nt) % nt;
+      if (field[t2 * nx + x] == 0) {
+        double h = 0.5 * eta0(x) * e_dn * psi[t2 * nx + x];
+        if ((t2 > t) != transpose) c += h; else c -= h;
+      }
+      int x2 = (x + 1) % nx;
+      if (field[t * nx + x2] == 0) {
+        double h = 0.5 * 1 * psi[t * nx + x2];
+        if ((x2 > x) != transpose) c += h; else c -= h;
+      }
+      x2 = (x - 1 + nx) % nx;
+      if (field[t * nx + x2] == 0) {
+        double h = 0.5 * 1 * psi[t * nx + x2];
+        if ((x2 > x) != transpose) c += h; else c -= h;
+      }
+    } else {
+      c = psi[k];                                                   /* vec_ops.c:130 */
+    }
+    chi[k] = c;
+  }
+}
+
+void orc_fM(int nt, int nx, double m, double mu, const int *field, const double *psi, double *chi)
+{ apply_b(nt, nx, m, mu, 0, field, psi, chi); }
+
+void orc_fM_transpose(int nt, int nx, double m, double mu, const int *field, const double *psi, double *chi)
+{ apply_b(nt, nx, m, mu, 1, field, psi, chi); }
+
+static double dot_b(int n, const double *a, const double *b)      /* vec_dot, vec_ops.c:56-62 */
+{ double s = 0; for (int i = 0; i < n; i++) s += a[i] * b[i]; return s; }
+
+/* cg_MdM, vec_ops.c:261-307.  Divergence fills the solution with 1e50 (vec_ops.c:292-296). */
+int orc_cg_MdM(int nt, int nx, double m, double mu, const int *field, const double *source, double *inv,
+               int *iters, double *rr_final)
+{
+  const int V = nt * nx;
+  double *r = malloc(sizeof(double) * V), *p = malloc(sizeof(double) * V);
+  double *Mp = malloc(sizeof(double) * V), *MMp = malloc(sizeof(double) * V);
+  int status = ORC_CG_MAXITER, k = 0;
+  for (int i = 0; i < V; i++) { inv[i] = 0; r[i] = source[i]; p[i] = r[i]; }
+  double rr_old = dot_b(V, r, r), rr_init = rr_old, rr = rr_old;
+  if (rr_old < ORC_CG_ACCURACY) { status = ORC_CG_ZERO_SOURCE; goto done; }
+  for (k = 1; k < ORC_B_CG_MAX_ITER; k++) {
+    apply_b(nt, nx, m, mu, 0, field, p, Mp);
+    apply_b(nt, nx, m, mu, 1, field, Mp, MMp);
+    double pMp = dot_b(V, p, MMp);
+    double a = rr_old / pMp;
+    for (int i = 0; i < V; i++) inv[i] = inv[i] + a * p[i];          /* vec_dmul_add, vec_ops.c:286 */
+    for (int i = 0; i < V; i++) r[i] = r[i] + (-a) * MMp[i];         /* vec_ops.c:287 */
+    rr = dot_b(V, r, r);
+    if (rr < ORC_CG_ACCURACY) { status = ORC_CG_CONVERGED; break; }
+    if (rr / rr_init > 1e10) { for (int i = 0; i < V; i++) inv[i] = 1e50; status = ORC_CG_DIVERGED; break; }
+    double b = rr / rr_old;
+    for (int i = 0; i < V; i++) p[i] = r[i] + b * p[i];
+    rr_old = rr;
+  }
+done:
+  if (iters) *iters = (status == ORC_CG_MAXITER) ? k - 1 : k;
+  if (rr_final) *rr_final = rr;
+  free(r); free(p); free(Mp); free(MMp);
+  return status;
+}
+
+/* cg_propagator, vec_ops.c:311-321:  M^-1 source = (M^T M)^-1 M^T source */
+int orc_cg_propagator(int nt, int nx, double m, double mu, const int *field, const double *source, double *prop,
+                      int *iters, double *rr_final)
+{
+  double *tmp = malloc(sizeof(double) * nt * nx);
+  apply_b(nt, nx, m, mu, 1, field, source, tmp);
+  int st = orc_cg_MdM(nt, nx, m, mu, field, tmp, prop, iters, rr_final);
+  free(tmp);
+  return st;
 }

@@ -75,5 +75,22 @@ def main():
     print("wrote hmc_16x16_adjoint_m0.5_4traj.stdout")
 
 
+def family_b():
+    """vec_ops.c: fM, fM_transpose, cg_propagator on a 32x32 lattice with 15 % occupied sites."""
+    from oracle.pyoracle import RefLibB
+    rng = np.random.default_rng(2024)
+    nt = nx = 32
+    m, mu = 0.2, 0.1
+    ref = RefLibB(nt, nx, m=m, mu=mu)
+    field = (rng.random((nt, nx)) < 0.15).astype(np.int32)
+    ref.set_field(field)
+    psi = rng.normal(size=(nt, nx))
+    np.savez_compressed(os.path.join(OUT, "refB_32x32_m0.2_mu0.1.npz"), field=field, psi=psi, m=m, mu=mu,
+                        fM=ref.call("fM", psi), fMT=ref.call("fM_transpose", psi),
+                        prop=ref.call("cg_propagator", psi))
+    print("wrote refB_32x32_m0.2_mu0.1.npz")
+
+
 if __name__ == "__main__":
+    family_b()
     main()

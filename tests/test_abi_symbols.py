@@ -43,6 +43,16 @@ def test_reference_signature_shim_exports_family_A():
     assert not missing, missing
 
 
+def test_vec_ops_replacement_exports_family_B():
+    names = declared_functions("thirring_vecops_abi.h")
+    for n in ("fM", "fM_transpose", "cg_MdM", "cg_propagator", "vec_dot", "vec_dmul_add", "alloc_vector", "free_vector",
+              "vec_zero", "vec_one", "vec_add", "vec_d_mul", "vec_zero_occupied", "tb_vecops_configure"):
+        assert n in names
+    lib = ctypes.CDLL(os.path.join(PKG, "libthirring_vecops.so"))
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
 def test_no_cpu_fallback_without_device():
     """Creating a context on a host without a GPU must fail loudly, never fall back."""
     import thirring2d_b200 as tb

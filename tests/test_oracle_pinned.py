@@ -106,3 +106,38 @@ def test_reference_stdout_known_answer():
     assert "Start HMC: Sg 1042.01, Smdm 2199.41, Smd 203252, Smom 2015.63" in out
     assert "HMC End, dS -2.75473, Sg 1115.92, Smdm 2198.94, Smd 203250, Sm 1941.25" in out
     assert "Phase -20.0647" in out
+
+
+# ---- family B (vec_ops.c) --------------------------------------------------------------------------------
+from oracle.pyoracle import RefLibB, ref_b_available  # noqa: E402
+
+needs_ref_b = pytest.mark.skipif(not ref_b_available(16, 16), reason="oracle/_ref not built")
+
+
+@needs_ref_b
+@pytest.mark.parametrize("nt,nx", [(16, 16), (16, 32), (64, 64)])
+@pytest.mark.parametrize("m,mu,occ", [(0.3, 0.1, 0.1), (0.05, 0.0, 0.0), (1.0, 0.3, 0.3)])
+def test_family_b_oracle_bitwise_vs_compiled_vec_ops(oracle, nt, nx, m, mu, occ):
+    rng = np.random.default_rng(nt * nx + int(100 * m))
+    ref = RefLibB(nt, nx, m=m, mu=mu)
+    field = (rng.random((nt, nx)) < occ).astype(np.int32)
+    ref.set_field(field)
+    psi = rng.normal(size=(nt, nx))
+    assert np.array_equal(ref.call("fM", psi), oracle.fM(psi, field, m, mu))
+    assert np.array_equal(ref.call("fM_transpose", psi), oracle.fM(psi, field, m, mu, transpose=True))
+    x, st, it, rr = oracle.cg_MdM(psi, field, m, mu)
+    assert st == CG_CONVERGED and np.array_equal(ref.call("cg_MdM", psi), x)
+    xp, st, it, rr = oracle.cg_MdM(psi, field, m, mu, propagator=True)
+    assert np.array_equal(ref.call("cg_propagator", psi), xp)
+    # the reference's own sanity identities: <a, M b> = <M^T a, b>, M M^-1 b = b
+    a = rng.normal(size=(nt, nx))
+    assert abs(np.vdot(a, oracle.fM(psi, field, m, mu)) - np.vdot(oracle.fM(a, field, m, mu, transpose=True), psi)) < 1e-11
+    assert np.abs(oracle.fM(xp, field, m, mu) - psi).max() < 1e-12
+
+
+def test_family_b_golden_fixture(oracle):
+    d = np.load(os.path.join(GOLD, "refB_32x32_m0.2_mu0.1.npz"))
+    field, psi, m, mu = d["field"], d["psi"], float(d["m"]), float(d["mu"])
+    assert np.array_equal(oracle.fM(psi, field, m, mu), d["fM"])
+    assert np.array_equal(oracle.fM(psi, field, m, mu, transpose=True), d["fMT"])
+    assert np.array_equal(oracle.cg_MdM(psi, field, m, mu, propagator=True)[0], d["prop"])

@@ -130,6 +130,29 @@ class Context:
         assert A.shape == (self.nchains, self.nt, self.nx, 2), A.shape
         check(self.lib.tb_set_gauge(self._h, A.ctypes.data), "tb_set_gauge")
 
+    def set_occupancy(self, field):
+        """Family B (vec_ops.c): occupation field (nchains, NT, NX) ints, 0 = free.  Call set_params first."""
+        field = np.ascontiguousarray(field, dtype=np.int32)
+        if field.ndim == 2:
+            field = field[None]
+        assert field.shape == (self.nchains, self.nt, self.nx), field.shape
+        check(self.lib.tb_set_occupancy(self._h, field.ctypes.data), "tb_set_occupancy")
+
+    # family B names (vec_ops.c:96,135,261,311): real vectors in, real vectors out
+    def fM(self, psi):
+        return self.apply(OP_M, np.asarray(psi, dtype=np.float64).astype(np.complex128)).real
+
+    def fM_transpose(self, psi):
+        return self.apply(OP_MDAG, np.asarray(psi, dtype=np.float64).astype(np.complex128)).real
+
+    def cg_MdM(self, source):
+        x, info = self.fmdm_invert_cg(np.asarray(source, dtype=np.float64).astype(np.complex128))
+        return x.real, info
+
+    def cg_propagator(self, source):
+        x, info = self.fm_invert_cg(np.asarray(source, dtype=np.float64).astype(np.complex128))
+        return x.real, info
+
     def apply(self, op, v):
         squeeze = np.ndim(v) == 2
         v = self._vec(v)

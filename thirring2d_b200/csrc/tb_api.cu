@@ -346,6 +346,7 @@ extern "C" int tb_set_gauge_dev(tb_ctx *ctx, const double *d_A_canonical) {
   TB_CHECK(join_subs(ctx));
   TB_CHECK(tb_launch_pack(ctx, d_A_canonical, ctx->Adev));
   TB_CHECK(tb_launch_links(ctx, (const double *)ctx->Adev));
+  ctx->msite = nullptr;
   ctx->have_gauge = true;
   return TB_OK;
 }
@@ -500,6 +501,27 @@ extern "C" int tb_set_gauge(tb_ctx *ctx, const double *A_host) {
     sub_range(ctx, s, &c0, &n);
     if (n) TB_CHECK(tb_launch_links_slice(ctx, ctx->Adev, c0, n, ctx->sub_stream[s]));
   }
+  ctx->msite = nullptr;
+  ctx->have_gauge = true;
+  return TB_OK;
+}
+
+// Family B: occupation field `field` (ints, 0 = free site; vec_ops.c:107) in the canonical layout
+// int[nchains][NT][NX].  Replaces the gauge field: links become the real masked constants of fM / fM_transpose
+// and occupied sites identity rows.  The current tb_set_params masses are baked into the site masses.
+extern "C" int tb_set_occupancy(tb_ctx *ctx, const int *field_host) {
+  if (!ctx || !field_host) return TB_EINVAL;
+  if (ctx->nranks > 1) { tb_set_error("tb_set_occupancy: slab contexts are not supported"); return TB_EINVAL; }
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(sync_all(ctx));
+  if (!ctx->msite_buf) {
+    TB_CHECK(dev_alloc(&ctx->msite_buf, ctx->nsite));
+    TB_CHECK(dev_alloc(&ctx->occ_dev, ctx->nsite));
+    TB_CHECK(dev_alloc(&ctx->occ_stage, ctx->nsite));
+  }
+  TB_CUDA(cudaMemcpyAsync(ctx->occ_stage, field_host, ctx->nsite * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  TB_CHECK(tb_launch_occupancy(ctx, ctx->occ_stage));
+  ctx->msite = ctx->msite_buf;
   ctx->have_gauge = true;
   return TB_OK;
 }

@@ -108,6 +108,9 @@ struct tb_ctx {
   // links, device layout [t][x][c]
   double2 *W0, *W1;
   bool have_gauge;
+  // family B (vec_ops.c): per-site mass (occupied site = identity row); msite == nullptr for family A
+  double *msite, *msite_buf;
+  int *occ_dev, *occ_stage;
   // work vectors (device layout)
   double2 *r, *p, *Mp, *q, *xw, *tmp, *vin, *vout;
   double2 *Adev;  // angles (A0,A1) in device layout
@@ -155,6 +158,7 @@ int tb_launch_pack_slice(tb_ctx *ctx, const double2 *d_canonical_slice, double2 
 int tb_launch_unpack_slice(tb_ctx *ctx, const double2 *d_vec, double2 *d_canonical_slice, int c0, int n, cudaStream_t st);
 bool tb_resident_supported(const tb_ctx *ctx);
 int tb_launch_dot(tb_ctx *ctx, const double2 *a, const double2 *b, double *d_out);
+int tb_launch_occupancy(tb_ctx *ctx, const int *d_field_canonical);
 int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out);
 int tb_slab_layout(tb_ctx *ctx);
 int tb_run_cg_any(tb_ctx *ctx, const double2 *b, double2 *x);

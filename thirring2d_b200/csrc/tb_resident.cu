@@ -277,7 +277,7 @@ int launch_resident(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cu
 }  // namespace
 
 bool tb_resident_supported(const tb_ctx *ctx) {
-  return ctx->nranks == 1 && ctx->nt == ctx->nx && (ctx->nt == 16 || ctx->nt == 32 || ctx->nt == 64);
+  return ctx->nranks == 1 && ctx->msite == nullptr && ctx->nt == ctx->nx && (ctx->nt == 16 || ctx->nt == 32 || ctx->nt == 64);
 }
 
 // One kernel launch per (sub-)batch of chains [c0, c0+n).  The tile shape per thread is a tuning knob

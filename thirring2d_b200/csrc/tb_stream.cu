@@ -35,7 +35,7 @@ __global__ void __launch_bounds__(TB_MAX_BLOCK)
 dslash_kernel(const double2 *__restrict__ in, const double2 *in_prev, const double2 *in_next,
               double2 *__restrict__ out, const double2 *__restrict__ W0, const double2 *W0_prev,
               const double2 *__restrict__ W1, const double *__restrict__ mass,
-              const double *__restrict__ emu, const double *__restrict__ emmu,
+              const double *__restrict__ msite, const double *__restrict__ emu, const double *__restrict__ emmu,
               const double2 *__restrict__ aux, const TbGeom g, const TbCgState s, const TbSlab sl,
               const int wait_ready, const int wait_done, const int sig0, const int sig1) {
   __shared__ double red[TB_MAX_BLOCK];
@@ -100,13 +100,15 @@ dslash_kernel(const double2 *__restrict__ in, const double2 *in_prev, const doub
         hi += w1c.x * pxp.y + w1c.y * pxp.x;
         hr -= w1m.x * pxm.x + w1m.y * pxm.y;
         hi -= w1m.x * pxm.y - w1m.y * pxm.x;
+        // family B (vec_ops.c:107,130): an occupied site is an identity row -> per-site mass, links already masked
+        const double ms = msite ? msite[row + j] : m;
         double2 o;
         if (DAG) {
-          o.x = m * pc.x - hr;
-          o.y = m * pc.y - hi;
+          o.x = ms * pc.x - hr;
+          o.y = ms * pc.y - hi;
         } else {
-          o.x = m * pc.x + hr;
-          o.y = m * pc.y + hi;
+          o.x = ms * pc.x + hr;
+          o.y = ms * pc.y + hi;
         }
         out[row + j] = o;
         if (DOT) {
@@ -359,6 +361,46 @@ __global__ void links_kernel(const double2 *__restrict__ A, double2 *__restrict_
   }
 }
 
+// Family B (vec_ops.c:96-172): links are real constants masked by the occupation field, W_mu(n) = s 1/2 eta_mu
+// if both n and n+mu^ are free, else 0 (hops into or out of an occupied site are dropped, vec_ops.c:110-128); the
+// site mass is m on free sites and 1 on occupied ones (identity row, vec_ops.c:130).  occ: [t][x][c] ints.
+__global__ void occupancy_links_kernel(const int *__restrict__ occ, const double *__restrict__ mass,
+                                       double2 *__restrict__ W0, double2 *__restrict__ W1,
+                                       double *__restrict__ msite, int nt, int nx, int C) {
+  const size_t total = (size_t)nt * nx * C;
+  const size_t R = (size_t)nx * C;
+  for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(k % C);
+    const size_t site = k / C;
+    const int x = (int)(site % nx);
+    const int t = (int)(site / nx);
+    const size_t kt = (size_t)((t + 1 == nt) ? 0 : t + 1) * R + (size_t)x * C + c;
+    const size_t kx = (size_t)t * R + (size_t)((x + 1 == nx) ? 0 : x + 1) * C + c;
+    const bool free_n = occ[k] == 0;
+    double f0 = (x & 1) ? -0.5 : 0.5;
+    if (t == nt - 1) f0 = -f0;
+    const double f1 = (x == nx - 1) ? -0.5 : 0.5;
+    W0[k] = make_double2((free_n && occ[kt] == 0) ? f0 : 0.0, 0.0);
+    W1[k] = make_double2((free_n && occ[kx] == 0) ? f1 : 0.0, 0.0);
+    msite[k] = free_n ? mass[c] : 1.0;
+  }
+}
+
+__global__ void transpose_int_kernel(const int *__restrict__ src, int *__restrict__ dst, int rows, int cols) {
+  // src[rows][cols] -> dst[cols][rows]
+  __shared__ int tile[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    if (r < rows && c < cols) tile[i][threadIdx.x] = src[(size_t)r * cols + c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(size_t)c * rows + r] = tile[threadIdx.x][i];
+  }
+}
+
 // src[r * ld_src + c], r < rows, c < cols   ->   dst[c * ld_dst + r]   (tiled transpose of double2)
 __global__ void transpose_kernel(const double2 *__restrict__ src, double2 *__restrict__ dst, int rows, int cols,
                                  size_t ld_src, size_t ld_dst) {
@@ -416,6 +458,7 @@ int tb_choose_geom(tb_ctx *ctx) {
 // Chain-slice variants: operate on chains [c0, c0+n) of the context on stream st (the host-buffer path
 // pipelines sub-batches of chains on separate streams).
 int tb_launch_links_slice(tb_ctx *ctx, const double2 *d_A_dev_layout, int c0, int n, cudaStream_t st) {
+  ctx->msite = nullptr;  // complex U(1) links: family A, no occupation mask
   const size_t total = ctx->V * (size_t)n;
   int blocks = (int)((total + 255) / 256);
   if (blocks > TB_NUM_SMS_B200 * 16) blocks = TB_NUM_SMS_B200 * 16;
@@ -457,6 +500,25 @@ int tb_launch_unpack_slice(tb_ctx *ctx, const double2 *d_vec, double2 *d_canonic
   return TB_OK;
 }
 
+// occupation field in canonical layout [chain][t][x] (device ints) -> masked links + site masses
+int tb_launch_occupancy(tb_ctx *ctx, const int *d_field_canonical) {
+  cudaStream_t st = ctx->stream;
+  const int *occ = d_field_canonical;
+  if (ctx->C > 1) {
+    dim3 grid(((int)ctx->V + 31) / 32, (ctx->C + 31) / 32), block(32, 8);
+    transpose_int_kernel<<<grid, block, 0, st>>>(d_field_canonical, ctx->occ_dev, ctx->C, (int)ctx->V);
+    occ = ctx->occ_dev;
+    ctx->launches++;
+  }
+  int blocks = (int)((ctx->nsite + 255) / 256);
+  if (blocks > TB_NUM_SMS_B200 * 16) blocks = TB_NUM_SMS_B200 * 16;
+  occupancy_links_kernel<<<blocks, 256, 0, st>>>(occ, ctx->d_mass, ctx->W0, ctx->W1, ctx->msite_buf, ctx->nt,
+                                                 ctx->nx, ctx->C);
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
 int tb_launch_links(tb_ctx *ctx, const double *d_A_dev_layout) {
   return tb_launch_links_slice(ctx, (const double2 *)d_A_dev_layout, 0, ctx->C, ctx->stream);
 }
@@ -485,7 +547,7 @@ static int launch_dslash_t(tb_ctx *ctx, const DslashArgs &a) {
   const dim3 grid = grid_of(g);
   const int block = g.bc * g.bx;
   const double2 *w0p = SLAB ? ctx->slab.W0_prev : ctx->W0;
-#define ARGS a.in, a.in_prev, a.in_next, a.out, ctx->W0, w0p, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu, a.aux, g, \
+#define ARGS a.in, a.in_prev, a.in_next, a.out, ctx->W0, w0p, ctx->W1, ctx->d_mass, ctx->msite, ctx->d_emu, ctx->d_emmu, a.aux, g, \
              ctx->cg, ctx->slab, a.wait_ready, a.wait_done, a.sig0, a.sig1
 #define L(DAG, DOT, MASKED) \
   TB_DISPATCH_TT(g.tt, (dslash_kernel<TT, DAG, DOT, MASKED, SLAB><<<grid, block, 0, ctx->stream>>>(ARGS)))

@@ -1,0 +1,159 @@
+/* vecops_interpose.c — libthirring_vecops.so: the reference's family-B symbols (vec_ops.c) on the B200.
+ * Plain C host code over the handle C-ABI; contract in include/thirring_vecops_abi.h. */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/thirring_b200.h"
+#include "../../include/thirring_vecops_abi.h"
+
+#define VEC_CG_MAX_ITER 10000 /* Thirring.h:43 */
+
+static struct {
+  tb_ctx *ctx;
+  int nt, nx;
+  int *field_flat, *field_last;
+  double *cin, *cout;   /* complex staging (imaginary parts zero) */
+  int have_field, mu_frozen;
+  double mu0, m_last;
+  int ***p_field_dummy;
+  int ***p_field;       /* &field  (int **field, Thirring.h:76) */
+  double *p_m, *p_mu;
+  long gpu_calls;
+} S;
+
+static void die(const char *what) {
+  fprintf(stderr, "libthirring_vecops: %s: %s\n", what, tb_last_error());
+  abort();
+}
+
+int tb_vecops_configure(int nt, int nx, int device) {
+  if (S.ctx) tb_vecops_shutdown();
+  memset(&S, 0, sizeof(S));
+  S.nt = nt; S.nx = nx;
+  if (tb_create(&S.ctx, nt, nx, 1, TB_MODE_ADJOINT, device) != TB_OK) die("tb_create");
+  if (tb_set_cg(S.ctx, 1e-30, VEC_CG_MAX_ITER) != TB_OK) die("tb_set_cg");  /* Thirring.h:42-43 */
+  size_t v = (size_t)nt * nx;
+  S.field_flat = malloc(v * sizeof(int));
+  S.field_last = malloc(v * sizeof(int));
+  S.cin = calloc(2 * v, sizeof(double));
+  S.cout = calloc(2 * v, sizeof(double));
+  return 0;
+}
+
+void tb_vecops_shutdown(void) {
+  if (S.ctx) tb_destroy(S.ctx);
+  free(S.field_flat); free(S.field_last); free(S.cin); free(S.cout);
+  memset(&S, 0, sizeof(S));
+}
+
+long tb_vecops_gpu_calls(void) { return S.gpu_calls; }
+
+static void lazy_init(void) {
+  if (S.ctx) return;
+  const char *nt = getenv("THIRRING_NT"), *nx = getenv("THIRRING_NX"), *dev = getenv("THIRRING_DEVICE");
+  if (!nt || !nx) {
+    fprintf(stderr, "libthirring_vecops: call tb_vecops_configure() or set THIRRING_NT/THIRRING_NX\n");
+    abort();
+  }
+  tb_vecops_configure(atoi(nt), atoi(nx), dev ? atoi(dev) : 0);
+}
+
+/* mass, mu and the occupation field are the driver's globals; re-upload only what changed */
+static void sync_state(void) {
+  lazy_init();
+  if (!S.p_m) {
+    S.p_m = (double *)dlsym(RTLD_DEFAULT, "m");
+    S.p_mu = (double *)dlsym(RTLD_DEFAULT, "mu");
+    S.p_field = (int ***)dlsym(RTLD_DEFAULT, "field");
+    if (!S.p_m || !S.p_mu || !S.p_field) {
+      fprintf(stderr, "libthirring_vecops: the driver's globals m, mu, field (Thirring.h:63-76) are not visible\n");
+      abort();
+    }
+  }
+  if (!S.mu_frozen) { S.mu0 = *S.p_mu; S.mu_frozen = 1; }   /* vec_ops.c:98-104 */
+  int **field = *S.p_field;
+  int *d = S.field_flat;
+  for (int t = 0; t < S.nt; t++) for (int x = 0; x < S.nx; x++) *d++ = field[t][x];
+  size_t bytes = (size_t)S.nt * S.nx * sizeof(int);
+  int changed = !S.have_field || memcmp(S.field_flat, S.field_last, bytes) != 0 || S.m_last != *S.p_m;
+  if (changed) {
+    double m = *S.p_m, mu = S.mu0;
+    if (tb_set_params(S.ctx, &m, &mu, 1) != TB_OK) die("tb_set_params");
+    if (tb_set_occupancy(S.ctx, S.field_flat) != TB_OK) die("tb_set_occupancy");
+    memcpy(S.field_last, S.field_flat, bytes);
+    S.m_last = m;
+    S.have_field = 1;
+  }
+}
+
+static void to_complex(double **v) {
+  for (int t = 0; t < S.nt; t++) for (int x = 0; x < S.nx; x++) S.cin[2 * ((size_t)t * S.nx + x)] = v[t][x];
+}
+static void from_complex(double **v) {
+  for (int t = 0; t < S.nt; t++) for (int x = 0; x < S.nx; x++) v[t][x] = S.cout[2 * ((size_t)t * S.nx + x)];
+}
+
+/* ---- element-wise helpers: host rows, as in the reference ------------------------------------------------ */
+#define FORALL for (int t = 0; t < S.nt; t++) for (int x = 0; x < S.nx; x++)
+double **alloc_vector(void) {
+  lazy_init();
+  size_t table = ((size_t)S.nt * sizeof(double *) + 63) & ~(size_t)63;
+  char *blk = malloc(table + (size_t)S.nt * S.nx * sizeof(double));
+  double **a = (double **)blk;
+  for (int t = 0; t < S.nt; t++) a[t] = (double *)(blk + table) + (size_t)t * S.nx;
+  return a;
+}
+void free_vector(double **a) { free(a); }
+void vec_neg(double **a) { lazy_init(); FORALL a[t][x] = -a[t][x]; }
+void vec_zero(double **a) { lazy_init(); FORALL a[t][x] = 0; }
+void vec_one(double **a) { lazy_init(); FORALL a[t][x] = 1; }
+void vec_set(double **a, double d) { lazy_init(); FORALL a[t][x] = d; }
+void vec_d_mul(double **a, double d) { lazy_init(); FORALL a[t][x] = a[t][x] * d; }
+void vec_assign(double **a, double **b) { lazy_init(); FORALL a[t][x] = b[t][x]; }
+void vec_add(double **a, double **b) { lazy_init(); FORALL a[t][x] += b[t][x]; }
+void vec_dmul_add(double **a, double **b, double **d, double e) { lazy_init(); FORALL a[t][x] = b[t][x] + e * d[t][x]; }
+double vec_dot(double **a, double **b) { lazy_init(); double s = 0; FORALL s += a[t][x] * b[t][x]; return s; }
+void vec_zero_occupied(double **a) {
+  sync_state();
+  int **field = *S.p_field;
+  FORALL if (field[t][x] > 0) a[t][x] = 0;
+}
+void vec_print_lat(double **a) {
+  lazy_init();
+  for (int t = 0; t < S.nt; t++) { for (int x = 0; x < S.nx; x++) printf(" %8.2f ", a[t][x]); printf(" \n"); }
+  printf(" \n");
+}
+
+/* ---- the hot path: GPU ------------------------------------------------------------------------------------ */
+static void apply(int op, double **chi, double **psi) {
+  sync_state();
+  to_complex(psi);
+  if (tb_apply(S.ctx, op, S.cin, S.cout) != TB_OK) die("tb_apply");
+  from_complex(chi);
+  S.gpu_calls++;
+}
+
+void fM(double **chi, double **psi) { apply(TB_OP_M, chi, psi); }
+void fM_transpose(double **chi, double **psi) { apply(TB_OP_MDAG, chi, psi); }
+
+static void solve(int propagator, double **inv, double **source) {
+  sync_state();
+  to_complex(source);
+  int status = 0, iters = 0;
+  double rr = 0;
+  int rc = propagator ? tb_invert(S.ctx, S.cin, S.cout, &status, &iters, &rr)
+                      : tb_cg(S.ctx, S.cin, S.cout, &status, &iters, &rr);
+  if (rc != TB_OK) die("tb_cg");
+  S.gpu_calls++;
+  if (status == TB_CG_DIVERGED) {   /* vec_ops.c:292-296 */
+    vec_set(inv, 1e50);
+    return;
+  }
+  from_complex(inv);
+}
+
+void cg_MdM(double **inv, double **source) { solve(0, inv, source); }
+void cg_propagator(double **propagator, double **source) { solve(1, propagator, source); }
