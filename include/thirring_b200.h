@@ -167,6 +167,11 @@ int tb_hmc_measure(tb_ctx *ctx, int nsrc, unsigned long long seed, unsigned int 
 /* current gauge angles to the host, double[nchains][NT][NX][2] */
 int tb_get_gauge(tb_ctx *ctx, double *A_host);
 
+/* Gauge-field checkpoint (hmc.c has none; mirrors the raw dump of fermionbag.c:125-161): 64-byte header
+ * ("THIRRING2D-A-V1", NT, NX, nchains, mode) + raw FP64 A[chain][t][x][dir]. */
+int tb_checkpoint_write(tb_ctx *ctx, const char *path);
+int tb_checkpoint_read(tb_ctx *ctx, const char *path);
+
 /* Counters for bench.py: kernels launched by this context since creation / since the last reset. */
 long long tb_launch_count(const tb_ctx *ctx);
 int tb_reset_launch_count(tb_ctx *ctx);

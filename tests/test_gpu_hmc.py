@@ -136,3 +136,40 @@ def test_batched_trajectories_device_rng_statistics():
         assert np.array_equal(changed, acc.astype(bool))  # exactly the accepted chains moved
         obs2, acc2, _ = ctx.hmc_trajectory(nsteps=20, traj_length=0.5, seed=9, traj_index=1)
         assert not np.array_equal(obs[:, 1], obs2[:, 1])  # a new trajectory index draws new fields
+
+
+def test_checkpoint_round_trip_and_batched_driver(tmp_path):
+    """On-disk format: raw FP64 gauge dump with a header, and the batched driver printing the
+    reference's stdout keywords per chain; a resumed run continues from the stored fields."""
+    import subprocess
+    import sys
+
+    nt = nx = 16
+    ck = str(tmp_path / "gauge.ckpt")
+    with tb.Context(nt, nx, 6, tb.MODE_ADJOINT, m=0.5) as ctx:
+        ctx.hmc_set_coupling(0.3)
+        ctx.hmc_heatbath(20, seed=3)
+        A = ctx.get_gauge()
+        ctx.checkpoint_write(ck)
+    assert os.path.getsize(ck) == 64 + A.nbytes
+    with tb.Context(nt, nx, 6, tb.MODE_ADJOINT, m=0.5) as ctx:
+        ctx.checkpoint_read(ck)
+        assert np.array_equal(ctx.get_gauge(), A)
+    with tb.Context(nt, nx, 5, tb.MODE_ADJOINT, m=0.5) as ctx:
+        with pytest.raises(tb.TBError, match="holds 6 chains"):
+            ctx.checkpoint_read(ck)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "thirring2d_b200.hmc_driver", "--nt", "16", "--nx", "16", "--chains", "6",
+                        "--mode", "adjoint", "--nsteps", "10", "--resume", ck], input="2\n2\n0.5\n0.3\n0.0\n99\n",
+                       capture_output=True, text=True, cwd=root, timeout=300)
+    assert p.returncode == 0, p.stderr
+    out = p.stdout
+    assert " 2D quenched Thirring model, ( 16 , 16 ) lattice" in out
+    assert len(re.findall(r"^\[chain \d\] Start HMC: Sg \S+, Smdm \S+, Smd \S+, Smom \S+$", out, re.M)) == 12
+    assert len(re.findall(r"^\[chain \d\] HMC End, dS \S+, Sg \S+, Smdm \S+, Smd \S+, Sm \S+$", out, re.M)) == 12
+    assert len(re.findall(r"^\[chain \d\] HMC (ACCEPTED|REJECTED)$", out, re.M)) == 12
+    assert len(re.findall(r"^\[chain \d\] Magnetisation \S+$", out, re.M)) == 6
+    assert len(re.findall(r"^\[chain \d\] Phase \S+$", out, re.M)) == 6
+    # the first printed gauge action is the action of the checkpointed field: (Nf/g) sum (1 - cos A)
+    sg0 = float(re.search(r"^\[chain 0\] Start HMC: Sg (\S+),", out, re.M).group(1))
+    assert abs(sg0 - (2 / 0.3) * np.sum(1 - np.cos(A[0]))) <= 6e-6 * sg0

@@ -14,6 +14,7 @@ gauge fields float64 (nchains, NT, NX, 2).  The ``*_dev`` methods take raw devic
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -281,6 +282,12 @@ class Context:
         check(self.lib.tb_hmc_measure(self._h, nsrc, seed, meas_index, src, mag.ctypes.data_as(_dp),
                                       ph.ctypes.data_as(_dp)), "tb_hmc_measure")
         return mag, ph
+
+    def checkpoint_write(self, path):
+        check(self.lib.tb_checkpoint_write(self._h, os.fsencode(path)), "tb_checkpoint_write")
+
+    def checkpoint_read(self, path):
+        check(self.lib.tb_checkpoint_read(self._h, os.fsencode(path)), "tb_checkpoint_read")
 
     @property
     def launch_count(self):

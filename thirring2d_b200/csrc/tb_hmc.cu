@@ -534,3 +534,66 @@ extern "C" int tb_hmc_measure(tb_ctx *ctx, int nsrc, unsigned long long seed, un
   free(hm);
   return TB_OK;
 }
+
+// ---- on-disk format -----------------------------------------------------------------------
+// hmc.c never writes its configuration; the checkpoint mirrors fermionbag's raw dump idea (fermionbag.c:125-161):
+// a 64-byte header (magic, NT, NX, nchains, mode) followed by the raw FP64 angles A[chain][t][x][dir].
+struct TbCkptHeader {
+  char magic[16];
+  int nt, nx, nchains, mode;
+  char pad[32];
+};
+
+extern "C" int tb_checkpoint_write(tb_ctx *ctx, const char *path) {
+  if (!ctx || !path) return TB_EINVAL;
+  if (!ctx->have_gauge) { tb_set_error("tb_checkpoint_write: no gauge field"); return TB_EINVAL; }
+  double *A = (double *)malloc(ctx->nsite * 2 * sizeof(double));
+  if (!A) return TB_ENOMEM;
+  int rc = tb_get_gauge(ctx, A);
+  if (rc == TB_OK) {
+    FILE *f = fopen(path, "wb");
+    if (!f) { tb_set_error("tb_checkpoint_write: cannot open %s", path); rc = TB_EINVAL; }
+    else {
+      TbCkptHeader h;
+      memset(&h, 0, sizeof(h));
+      memcpy(h.magic, "THIRRING2D-A-V1", 15);
+      h.nt = ctx->nt; h.nx = ctx->nx; h.nchains = ctx->C; h.mode = ctx->mode;
+      if (fwrite(&h, sizeof(h), 1, f) != 1 || fwrite(A, sizeof(double), ctx->nsite * 2, f) != ctx->nsite * 2) {
+        tb_set_error("tb_checkpoint_write: short write to %s", path);
+        rc = TB_EINVAL;
+      }
+      fclose(f);
+    }
+  }
+  free(A);
+  return rc;
+}
+
+extern "C" int tb_checkpoint_read(tb_ctx *ctx, const char *path) {
+  if (!ctx || !path) return TB_EINVAL;
+  FILE *f = fopen(path, "rb");
+  if (!f) { tb_set_error("tb_checkpoint_read: cannot open %s", path); return TB_EINVAL; }
+  TbCkptHeader h;
+  int rc = TB_OK;
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "THIRRING2D-A-V1", 15) != 0) {
+    tb_set_error("tb_checkpoint_read: %s is not a Thirring2D gauge checkpoint", path);
+    rc = TB_EINVAL;
+  } else if (h.nt != ctx->nt || h.nx != ctx->nx || h.nchains != ctx->C) {
+    tb_set_error("tb_checkpoint_read: %s holds %d chains of %dx%d, the context %d of %dx%d", path, h.nchains, h.nt,
+                 h.nx, ctx->C, ctx->nt, ctx->nx);
+    rc = TB_EINVAL;
+  }
+  double *A = nullptr;
+  if (rc == TB_OK) {
+    A = (double *)malloc(ctx->nsite * 2 * sizeof(double));
+    if (fread(A, sizeof(double), ctx->nsite * 2, f) != ctx->nsite * 2) {
+      tb_set_error("tb_checkpoint_read: %s is truncated", path);
+      rc = TB_EINVAL;
+    }
+  }
+  fclose(f);
+  if (rc == TB_OK) rc = tb_set_gauge(ctx, A);
+  if (rc == TB_OK) rc = tb_synchronize(ctx);
+  free(A);
+  return rc;
+}

@@ -53,6 +53,8 @@ SIGNATURES = {
                                C.POINTER(C.c_longlong)]),
     "tb_hmc_measure": (_i, [_vp, _i, C.c_ulonglong, C.c_uint, _vp, _dp, _dp]),
     "tb_get_gauge": (_i, [_vp, _vp]),
+    "tb_checkpoint_write": (_i, [_vp, C.c_char_p]),
+    "tb_checkpoint_read": (_i, [_vp, C.c_char_p]),
     "tb_launch_count": (C.c_longlong, [_vp]),
     "tb_reset_launch_count": (_i, [_vp]),
     "tb_last_solve_ms": (_d, [_vp]),
