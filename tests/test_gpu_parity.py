@@ -102,9 +102,10 @@ CG_CASES = [
 ]
 
 
-# (solver, rows_per_thread / resident tile shape, iterations per graph launch); solver 1 = streaming multi-kernel,
+# (solver, rows_per_thread / resident tile shape, iterations per graph launch); solver 1 = streaming (fused 3-kernel
+# iteration in ADJOINT mode), 3 = streaming with the 4-kernel iteration always,
 # 2 = on-chip resident (16/32/64 square lattices only; tile 44 = 4x4, 18 = 1x8, 28 = 2x8 sites per thread)
-SOLVER_VARIANTS = [(1, 0, 0), (1, 2, 5), (2, 44, 0), (2, 18, 0), (2, 28, 0), (0, 0, 0)]
+SOLVER_VARIANTS = [(1, 0, 0), (1, 2, 5), (3, 0, 0), (3, 4, 3), (2, 44, 0), (2, 18, 0), (2, 28, 0), (0, 0, 0)]
 
 
 def resident_ok(nt, nx):

@@ -109,6 +109,7 @@ int tb_create_common(tb_ctx **out, int nt, int nx, int nchains, int mode, int de
   ctx->tune_tt = (e = getenv("TB_ROWS_PER_THREAD")) ? atoi(e) : 0;
   ctx->tune_chunk = (e = getenv("TB_ITERS_PER_LAUNCH")) ? atoi(e) : 0;
   ctx->tune_solver = (e = getenv("TB_SOLVER")) ? atoi(e) : 0;
+  ctx->cg_variant = (e = getenv("TB_CG_VARIANT")) ? atoi(e) : 0;
   tb_choose_geom(ctx);
   int rc = TB_OK;
   cudaError_t ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -308,7 +309,8 @@ extern "C" int tb_set_tuning(tb_ctx *ctx, int rows_per_thread, int iters_per_lau
   TB_CHECK(sync_all(ctx));
   ctx->tune_tt = rows_per_thread;
   ctx->tune_chunk = iters_per_launch;
-  ctx->tune_solver = solver;
+  ctx->tune_solver = solver == 3 ? 1 : solver;   // 3 = streaming solver, 4-kernel iteration
+  ctx->cg_variant = solver == 3 ? 4 : 0;
   tb_choose_geom(ctx);
   invalidate_graph(ctx);
   return TB_OK;

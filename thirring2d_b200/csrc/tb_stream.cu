@@ -112,8 +112,12 @@ dslash_kernel(const double2 *__restrict__ in, const double2 *in_prev, const doub
         }
         out[row + j] = o;
         if (DOT) {
-          const double2 a = aux[row + j];
-          acc += a.x * o.x + a.y * o.y;
+          if (aux) {
+            const double2 a = aux[row + j];
+            acc += a.x * o.x + a.y * o.y;
+          } else {
+            acc += o.x * o.x + o.y * o.y;   // |out|^2 (fused variant: <p, M^dagger M p> = |M p|^2)
+          }
         }
         pm = pc;
         pc = pp;
@@ -158,6 +162,77 @@ axpy_norm_kernel(double2 *__restrict__ x, double2 *__restrict__ r, const double2
     }
   }
   reduce_finalize<FIN_RR, SLAB, TB_RED_RR>(acc, g, s, sl, b, red);
+}
+
+// Fused variant for M~ = M^dagger: q = M^dagger (Mp) is consumed in registers, never written:
+//   x += alpha p ; r -= alpha q ; rr = ||r||^2 ; beta / convergence by the last block        (hmc.c:367-390)
+// alpha = rr_old / |Mp|^2 was finalised by the preceding dslash (<p, M^dagger M p> = |M p|^2 exactly when
+// M~ is the true adjoint).  One CG iteration = 240 B/site in 3 launches instead of 288 B/site in 4.
+template <int TT>
+__global__ void __launch_bounds__(TB_MAX_BLOCK)
+dslash_axpy_norm_kernel(const double2 *__restrict__ in, const double2 *__restrict__ W0,
+                        const double2 *__restrict__ W1, const double *__restrict__ mass,
+                        const double *__restrict__ msite, const double *__restrict__ emu,
+                        const double *__restrict__ emmu, const double2 *__restrict__ p, double2 *__restrict__ x,
+                        double2 *__restrict__ r, const TbGeom g, const TbCgState s, const TbSlab sl) {
+  __shared__ double red[TB_MAX_BLOCK];
+  const BlockPos b = block_pos(g);
+  if (s.tile_active[b.ctile] == 0) return;
+  const bool act = b.valid && s.active[b.c] != 0;
+  double acc = 0.0;
+  if (act) {
+    const double m = mass[b.c];
+    const double af = emmu[b.c], ab = emu[b.c];   // M^dagger: e^{-mu} on the +t hop, e^{+mu} on the -t hop
+    const double a = s.alpha[b.c];
+    const size_t R = (size_t)g.R;
+    const size_t j = (size_t)b.x * g.C + b.c;
+    const size_t jp = (size_t)((b.x + 1 == g.nx) ? 0 : b.x + 1) * g.C + b.c;
+    const size_t jm = (size_t)((b.x == 0) ? g.nx - 1 : b.x - 1) * g.C + b.c;
+    const int t0 = b.ttile * TT;
+    const int tm0 = (t0 == 0) ? g.nt - 1 : t0 - 1;
+    double2 pm = in[(size_t)tm0 * R + j];
+    double2 w0m = W0[(size_t)tm0 * R + j];
+    double2 pc = in[t0 * R + j];
+#pragma unroll
+    for (int i = 0; i < TT; i++) {
+      const int t = t0 + i;
+      if (t < g.nt) {
+        const size_t row = t * R;
+        const int tp = (t + 1 == g.nt) ? 0 : t + 1;
+        const double2 pp = in[(size_t)tp * R + j];
+        const double2 pxp = in[row + jp];
+        const double2 pxm = in[row + jm];
+        const double2 w0c = W0[row + j];
+        const double2 w1c = W1[row + j];
+        const double2 w1m = W1[row + jm];
+        const double2 pv = p[row + j];
+        double2 xv = x[row + j], rv = r[row + j];
+        const double fr = w0c.x * af, fi = w0c.y * af;
+        const double br = w0m.x * ab, bi = w0m.y * ab;
+        double hr = fr * pp.x - fi * pp.y;
+        double hi = fr * pp.y + fi * pp.x;
+        hr -= br * pm.x + bi * pm.y;
+        hi -= br * pm.y - bi * pm.x;
+        hr += w1c.x * pxp.x - w1c.y * pxp.y;
+        hi += w1c.x * pxp.y + w1c.y * pxp.x;
+        hr -= w1m.x * pxm.x + w1m.y * pxm.y;
+        hi -= w1m.x * pxm.y - w1m.y * pxm.x;
+        const double ms = msite ? msite[row + j] : m;
+        const double qx = ms * pc.x - hr, qy = ms * pc.y - hi;   // q = M^dagger Mp
+        xv.x += a * pv.x;
+        xv.y += a * pv.y;
+        rv.x -= a * qx;
+        rv.y -= a * qy;
+        x[row + j] = xv;
+        r[row + j] = rv;
+        acc += rv.x * rv.x + rv.y * rv.y;
+        pm = pc;
+        pc = pp;
+        w0m = w0c;
+      }
+    }
+  }
+  reduce_finalize<FIN_RR, false, TB_RED_RR>(acc, g, s, sl, b, red);
 }
 
 // p = r + beta p (hmc.c:391-392).  SLAB: p is an exchange vector: wait until the neighbours have finished
@@ -614,6 +689,24 @@ static int cg_iteration(tb_ctx *ctx, double2 *x) {
   return TB_OK;
 }
 
+// Fused ADJOINT iteration (single GPU): dslash + |Mp|^2 -> alpha ; dslash^dagger fused with the x/r update and
+// ||r||^2 -> beta ; xpay.
+static int cg_iteration_fused(tb_ctx *ctx, double2 *x) {
+  const TbGeom &g = ctx->g;
+  const dim3 grid = grid_of(g);
+  const int block = g.bc * g.bx;
+  cudaStream_t st = ctx->stream;
+  DslashArgs k1 = {ctx->p, ctx->p, ctx->p, ctx->Mp, nullptr, false, true, true, 0, -1, 0, -1};
+  TB_CHECK(launch_dslash_t<false>(ctx, k1));
+  TB_DISPATCH_TT(g.tt, (dslash_axpy_norm_kernel<TT><<<grid, block, 0, st>>>(ctx->Mp, ctx->W0, ctx->W1, ctx->d_mass,
+      ctx->msite, ctx->d_emu, ctx->d_emmu, ctx->p, x, ctx->r, g, ctx->cg, ctx->slab)))
+  ctx->launches++;
+  TB_DISPATCH_TT(g.tt, (xpay_kernel<TT, false><<<grid, block, 0, st>>>(ctx->p, ctx->r, g, ctx->cg, ctx->slab)))
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
 // slab mode: out = Op in on the distributed lattice (collective: every rank calls it with its slab)
 int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out) {
   const TbGeom &g = ctx->g;
@@ -647,6 +740,8 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
   const int block = g.bc * g.bx;
   cudaStream_t st = ctx->stream;
   const bool slab = ctx->nranks > 1;
+  // the fused 3-kernel iteration needs M~ = M^dagger; TB_CG_VARIANT=4 (or tune) forces the 4-kernel form
+  const bool fused = !slab && tb_conj_is_dagger(ctx) && ctx->cg_variant != 4;
   cg_reset_kernel<<<(g.Cpad + 255) / 256, 256, 0, st>>>(g, ctx->cg);
   ctx->launches++;
   if (slab) {
@@ -662,7 +757,7 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
 
   int chunk = ctx->tune_chunk > 0 ? ctx->tune_chunk : 16;
   const bool use_graph = getenv("TB_NO_GRAPH") == nullptr;
-  if (use_graph && (ctx->cg_graph == nullptr || ctx->cg_graph_chunk != chunk)) {
+  if (use_graph && (ctx->cg_graph == nullptr || ctx->cg_graph_chunk != chunk * 8 + (fused ? 1 : 0))) {
     if (ctx->cg_graph) { cudaGraphExecDestroy(ctx->cg_graph); ctx->cg_graph = nullptr; }
     cudaStream_t cap;
     TB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
@@ -671,7 +766,8 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
     ctx->stream = cap;
     TB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed));
     int rc = TB_OK;
-    for (int i = 0; i < chunk && rc == TB_OK; i++) rc = slab ? cg_iteration<true>(ctx, ctx->xw) : cg_iteration<false>(ctx, ctx->xw);
+    for (int i = 0; i < chunk && rc == TB_OK; i++)
+      rc = slab ? cg_iteration<true>(ctx, ctx->xw) : (fused ? cg_iteration_fused(ctx, ctx->xw) : cg_iteration<false>(ctx, ctx->xw));
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(cap, &graph);
     ctx->stream = saved;
@@ -681,16 +777,17 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
     TB_CUDA(cudaGraphInstantiate(&ctx->cg_graph, graph, 0));
     cudaGraphDestroy(graph);
     cudaStreamDestroy(cap);
-    ctx->cg_graph_chunk = chunk;
+    ctx->cg_graph_chunk = chunk * 8 + (fused ? 1 : 0);
   }
 
   const long max_chunks = ((long)ctx->cg.max_iter + chunk - 1) / chunk + 1;
   for (long i = 0; i < max_chunks; i++) {
     if (use_graph) {
       TB_CUDA(cudaGraphLaunch(ctx->cg_graph, st));
-      ctx->launches += (slab ? 6LL : 4LL) * chunk;
+      ctx->launches += (slab ? 6LL : (fused ? 3LL : 4LL)) * chunk;
     } else {
-      for (int k = 0; k < chunk; k++) TB_CHECK(slab ? cg_iteration<true>(ctx, ctx->xw) : cg_iteration<false>(ctx, ctx->xw));
+      for (int k = 0; k < chunk; k++)
+        TB_CHECK(slab ? cg_iteration<true>(ctx, ctx->xw) : (fused ? cg_iteration_fused(ctx, ctx->xw) : cg_iteration<false>(ctx, ctx->xw)));
     }
     const int slot = (int)(i & 1);
     TB_CUDA(cudaMemcpyAsync(&ctx->h_flag[slot], ctx->cg.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
