@@ -178,23 +178,37 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
     for (int k = 1; k < s.max_iter; k++) {  // hmc.c:364
       double2 mp[TT][TX], q[TT][TX];
       tile_apply<NT, NX, TX, TT, false, HAS_MU>(p, mp, F, W0s, W1s, t0, g, m, e_p, e_m);   // Mp = M p, hmc.c:366
+      double pq = 0.0;
+      if (DAG) {
+        // M~ = M^dagger: <p, M^dagger M p> = |M p|^2, so alpha is known before q exists and the pq reduction
+        // overlaps the barrier that publishes Mp
+#pragma unroll
+        for (int i = 0; i < TT; i++)
+#pragma unroll
+          for (int j = 0; j < TX; j++) {
+            pq = fma(mp[i][j].x, mp[i][j].x, pq);
+            pq = fma(mp[i][j].y, mp[i][j].y, pq);
+          }
+      }
       __syncthreads();  // everyone has read p from F
 #pragma unroll
       for (int i = 0; i < TT; i++)
 #pragma unroll
         for (int j = 0; j < TX; j++) F[(t0 + i) * NX + j * NG + g] = mp[i][j];
-      __syncthreads();
+      if (DAG) pq = block_sum<NWARPS>(pq, scrB);   // its barrier also publishes Mp
+      else __syncthreads();
       // q = M~ Mp, hmc.c:367 (M^dagger swaps the roles of e^{mu} and e^{-mu})
       tile_apply<NT, NX, TX, TT, DAG, HAS_MU>(mp, q, F, W0s, W1s, t0, g, m, DAG ? e_m : e_p, DAG ? e_p : e_m);
-      double pq = 0.0;
+      if (!DAG) {
 #pragma unroll
-      for (int i = 0; i < TT; i++)
+        for (int i = 0; i < TT; i++)
 #pragma unroll
-        for (int j = 0; j < TX; j++) {   // hmc.c:368-370
-          pq = fma(p[i][j].x, q[i][j].x, pq);
-          pq = fma(p[i][j].y, q[i][j].y, pq);
-        }
-      pq = block_sum<NWARPS>(pq, scrB);
+          for (int j = 0; j < TX; j++) {   // hmc.c:368-370
+            pq = fma(p[i][j].x, q[i][j].x, pq);
+            pq = fma(p[i][j].y, q[i][j].y, pq);
+          }
+        pq = block_sum<NWARPS>(pq, scrB);
+      }
       const double a = rr_old / pq;   // hmc.c:371
       rr = 0.0;
 #pragma unroll
