@@ -48,7 +48,10 @@ def _worker(rank, world, port, nt, nx, nchains, m, mu, q):
     x, info = ctx.fmdm_invert_cg(b)
     x2, info2 = ctx.fmdm_invert_cg(b)  # a second solve exercises the epoch hand-over between solves
     xi, infoi = ctx.fm_invert_cg(v[:, sl])
-    out.update(b=b, x=x, x2=x2, xi=xi, iters=info.iters, status=info.status, iters2=info2.iters)
+    ctx.set_tuning(solver=3)   # the 4-kernel iteration with separate scalar kernels (the form REF_COMPAT uses)
+    x4, info4 = ctx.fmdm_invert_cg(b)
+    out.update(b=b, x=x, x2=x2, xi=xi, x4=x4, iters=info.iters, status=info.status, iters2=info2.iters,
+               iters4=info4.iters)
     q.put((rank, out))
     dist.barrier()
     ctx.close()
@@ -92,5 +95,7 @@ def test_T7_slab_matches_single_gpu(nt, nx, nchains, m, mu):
         assert np.array_equal(res[r]["iters"], res[r]["iters2"])
     xs = cat("x")
     assert np.array_equal(xs, cat("x2"))
+    assert np.linalg.norm(cat("x4") - x) <= 1e-12 * np.linalg.norm(x)
+    assert np.all(np.abs(res[0]["iters4"].astype(int) - info.iters.astype(int)) <= 1)
     assert np.linalg.norm(xs - x) <= 1e-12 * np.linalg.norm(x)
     assert np.linalg.norm(cat("xi") - xi) <= 1e-12 * np.linalg.norm(xi)

@@ -168,38 +168,52 @@ axpy_norm_kernel(double2 *__restrict__ x, double2 *__restrict__ r, const double2
 //   x += alpha p ; r -= alpha q ; rr = ||r||^2 ; beta / convergence by the last block        (hmc.c:367-390)
 // alpha = rr_old / |Mp|^2 was finalised by the preceding dslash (<p, M^dagger M p> = |M p|^2 exactly when
 // M~ is the true adjoint).  One CG iteration = 240 B/site in 3 launches instead of 288 B/site in 4.
-template <int TT>
+template <int TT, bool SLAB>
 __global__ void __launch_bounds__(TB_MAX_BLOCK)
-dslash_axpy_norm_kernel(const double2 *__restrict__ in, const double2 *__restrict__ W0,
+dslash_axpy_norm_kernel(const double2 *__restrict__ in, const double2 *in_prev, const double2 *in_next,
+                        const double2 *__restrict__ W0, const double2 *W0_prev,
                         const double2 *__restrict__ W1, const double *__restrict__ mass,
                         const double *__restrict__ msite, const double *__restrict__ emu,
                         const double *__restrict__ emmu, const double2 *__restrict__ p, double2 *__restrict__ x,
                         double2 *__restrict__ r, const TbGeom g, const TbCgState s, const TbSlab sl) {
   __shared__ double red[TB_MAX_BLOCK];
   const BlockPos b = block_pos(g);
-  if (s.tile_active[b.ctile] == 0) return;
+  if (s.tile_active[b.ctile] == 0) {
+    if (SLAB && *s.n_active > 0) slab_signal_done(sl, TB_FLAG_MPDONE, -1, *sl.seq);
+    return;
+  }
+  int seq = 0;
+  if (SLAB) {
+    seq = *sl.seq;
+    if (b.ttile == 0) slab_wait(sl, TB_FLAG_MPREADY, 0, seq);
+    if (b.ttile == g.nttiles - 1) slab_wait(sl, TB_FLAG_MPREADY, 1, seq);
+  }
   const bool act = b.valid && s.active[b.c] != 0;
   double acc = 0.0;
   if (act) {
     const double m = mass[b.c];
     const double af = emmu[b.c], ab = emu[b.c];   // M^dagger: e^{-mu} on the +t hop, e^{+mu} on the -t hop
-    const double a = s.alpha[b.c];
+    const double a = s.alpha[b.c];   // single GPU: finalised by the preceding dslash; slab: by slab_scalars_kernel
     const size_t R = (size_t)g.R;
     const size_t j = (size_t)b.x * g.C + b.c;
     const size_t jp = (size_t)((b.x + 1 == g.nx) ? 0 : b.x + 1) * g.C + b.c;
     const size_t jm = (size_t)((b.x == 0) ? g.nx - 1 : b.x - 1) * g.C + b.c;
     const int t0 = b.ttile * TT;
-    const int tm0 = (t0 == 0) ? g.nt - 1 : t0 - 1;
-    double2 pm = in[(size_t)tm0 * R + j];
-    double2 w0m = W0[(size_t)tm0 * R + j];
+    double2 pm, w0m;
+    if (t0 == 0) {
+      pm = ld_halo<SLAB>(&in_prev[(size_t)(g.nt - 1) * R + j]);
+      w0m = ld_halo<SLAB>(&W0_prev[(size_t)(g.nt - 1) * R + j]);
+    } else {
+      pm = in[(size_t)(t0 - 1) * R + j];
+      w0m = W0[(size_t)(t0 - 1) * R + j];
+    }
     double2 pc = in[t0 * R + j];
 #pragma unroll
     for (int i = 0; i < TT; i++) {
       const int t = t0 + i;
       if (t < g.nt) {
         const size_t row = t * R;
-        const int tp = (t + 1 == g.nt) ? 0 : t + 1;
-        const double2 pp = in[(size_t)tp * R + j];
+        const double2 pp = (t + 1 == g.nt) ? ld_halo<SLAB>(&in_next[j]) : in[row + R + j];
         const double2 pxp = in[row + jp];
         const double2 pxm = in[row + jm];
         const double2 w0c = W0[row + j];
@@ -232,7 +246,8 @@ dslash_axpy_norm_kernel(const double2 *__restrict__ in, const double2 *__restric
       }
     }
   }
-  reduce_finalize<FIN_RR, false, TB_RED_RR>(acc, g, s, sl, b, red);
+  reduce_finalize<FIN_RR, SLAB, TB_RED_RR>(acc, g, s, sl, b, red);
+  if (SLAB) slab_signal_done(sl, TB_FLAG_MPDONE, -1, seq);
 }
 
 // p = r + beta p (hmc.c:391-392).  SLAB: p is an exchange vector: wait until the neighbours have finished
@@ -698,11 +713,33 @@ static int cg_iteration_fused(tb_ctx *ctx, double2 *x) {
   cudaStream_t st = ctx->stream;
   DslashArgs k1 = {ctx->p, ctx->p, ctx->p, ctx->Mp, nullptr, false, true, true, 0, -1, 0, -1};
   TB_CHECK(launch_dslash_t<false>(ctx, k1));
-  TB_DISPATCH_TT(g.tt, (dslash_axpy_norm_kernel<TT><<<grid, block, 0, st>>>(ctx->Mp, ctx->W0, ctx->W1, ctx->d_mass,
-      ctx->msite, ctx->d_emu, ctx->d_emmu, ctx->p, x, ctx->r, g, ctx->cg, ctx->slab)))
+  TB_DISPATCH_TT(g.tt, (dslash_axpy_norm_kernel<TT, false><<<grid, block, 0, st>>>(ctx->Mp, ctx->Mp, ctx->Mp, ctx->W0,
+      ctx->W0, ctx->W1, ctx->d_mass, ctx->msite, ctx->d_emu, ctx->d_emmu, ctx->p, x, ctx->r, g, ctx->cg, ctx->slab)))
   ctx->launches++;
   TB_DISPATCH_TT(g.tt, (xpay_kernel<TT, false><<<grid, block, 0, st>>>(ctx->p, ctx->r, g, ctx->cg, ctx->slab)))
   ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
+// Fused ADJOINT iteration in slab mode: 240 B/site; the all-reduced scalars are evaluated by the one-block
+// slab_scalars_kernel between the passes.  (Letting every block of the consumer kernel poll the peers' flags was
+// measured slower: thousands of pollers on one L2 line delay the NVLink store they are waiting for.)
+static int cg_iteration_fused_slab(tb_ctx *ctx, double2 *x) {
+  const TbGeom &g = ctx->g;
+  const dim3 grid = grid_of(g);
+  const int block = g.bc * g.bx;
+  const TbSlab &sl = ctx->slab;
+  cudaStream_t st = ctx->stream;
+  DslashArgs k1 = {ctx->p, sl.p_prev, sl.p_next, ctx->Mp, nullptr, false, true, true,
+                   TB_FLAG_PREADY, TB_FLAG_MPDONE, TB_FLAG_MPREADY, TB_FLAG_PDONE};
+  TB_CHECK(launch_dslash_t<true>(ctx, k1));
+  slab_scalars_kernel<FIN_PQ, TB_RED_PQ><<<1, TB_MAX_BLOCK, 0, st>>>(g, ctx->cg, sl);
+  TB_DISPATCH_TT(g.tt, (dslash_axpy_norm_kernel<TT, true><<<grid, block, 0, st>>>(ctx->Mp, sl.mp_prev, sl.mp_next, ctx->W0,
+      sl.W0_prev, ctx->W1, ctx->d_mass, ctx->msite, ctx->d_emu, ctx->d_emmu, ctx->p, x, ctx->r, g, ctx->cg, sl)))
+  slab_scalars_kernel<FIN_RR, TB_RED_RR><<<1, TB_MAX_BLOCK, 0, st>>>(g, ctx->cg, sl);
+  TB_DISPATCH_TT(g.tt, (xpay_kernel<TT, true><<<grid, block, 0, st>>>(ctx->p, ctx->r, g, ctx->cg, sl)))
+  ctx->launches += 4;
   TB_CUDA(cudaGetLastError());
   return TB_OK;
 }
@@ -741,7 +778,7 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
   cudaStream_t st = ctx->stream;
   const bool slab = ctx->nranks > 1;
   // the fused 3-kernel iteration needs M~ = M^dagger; TB_CG_VARIANT=4 (or tune) forces the 4-kernel form
-  const bool fused = !slab && tb_conj_is_dagger(ctx) && ctx->cg_variant != 4;
+  const bool fused = tb_conj_is_dagger(ctx) && ctx->cg_variant != 4;
   cg_reset_kernel<<<(g.Cpad + 255) / 256, 256, 0, st>>>(g, ctx->cg);
   ctx->launches++;
   if (slab) {
@@ -767,7 +804,8 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
     TB_CUDA(cudaStreamBeginCapture(cap, cudaStreamCaptureModeRelaxed));
     int rc = TB_OK;
     for (int i = 0; i < chunk && rc == TB_OK; i++)
-      rc = slab ? cg_iteration<true>(ctx, ctx->xw) : (fused ? cg_iteration_fused(ctx, ctx->xw) : cg_iteration<false>(ctx, ctx->xw));
+      rc = slab ? (fused ? cg_iteration_fused_slab(ctx, ctx->xw) : cg_iteration<true>(ctx, ctx->xw))
+                : (fused ? cg_iteration_fused(ctx, ctx->xw) : cg_iteration<false>(ctx, ctx->xw));
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(cap, &graph);
     ctx->stream = saved;
@@ -784,10 +822,11 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
   for (long i = 0; i < max_chunks; i++) {
     if (use_graph) {
       TB_CUDA(cudaGraphLaunch(ctx->cg_graph, st));
-      ctx->launches += (slab ? 6LL : (fused ? 3LL : 4LL)) * chunk;
+      ctx->launches += (slab ? (fused ? 5LL : 6LL) : (fused ? 3LL : 4LL)) * chunk;
     } else {
       for (int k = 0; k < chunk; k++)
-        TB_CHECK(slab ? cg_iteration<true>(ctx, ctx->xw) : (fused ? cg_iteration_fused(ctx, ctx->xw) : cg_iteration<false>(ctx, ctx->xw)));
+        TB_CHECK(slab ? (fused ? cg_iteration_fused_slab(ctx, ctx->xw) : cg_iteration<true>(ctx, ctx->xw))
+                      : (fused ? cg_iteration_fused(ctx, ctx->xw) : cg_iteration<false>(ctx, ctx->xw)));
     }
     const int slot = (int)(i & 1);
     TB_CUDA(cudaMemcpyAsync(&ctx->h_flag[slot], ctx->cg.n_active, sizeof(int), cudaMemcpyDeviceToHost, st));
