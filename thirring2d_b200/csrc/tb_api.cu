@@ -110,6 +110,7 @@ int tb_create_common(tb_ctx **out, int nt, int nx, int nchains, int mode, int de
   ctx->tune_chunk = (e = getenv("TB_ITERS_PER_LAUNCH")) ? atoi(e) : 0;
   ctx->tune_solver = (e = getenv("TB_SOLVER")) ? atoi(e) : 0;
   ctx->cg_variant = (e = getenv("TB_CG_VARIANT")) ? atoi(e) : 0;
+  ctx->resident_x_tmem = (e = getenv("TB_RESIDENT_X_TMEM")) ? atoi(e) : 1;
   tb_choose_geom(ctx);
   int rc = TB_OK;
   cudaError_t ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);

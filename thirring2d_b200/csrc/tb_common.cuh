@@ -101,6 +101,7 @@ struct tb_ctx {
   bool own_stream;
   TbGeom g;
   int tune_tt, tune_chunk, tune_solver;
+  int resident_x_tmem;  // resident solver: keep x in tensor memory (1, default) or in an L2 workspace (0)
   int cg_variant;  // 0 auto (fused 3-kernel iteration when M~ = M^dagger), 4 = always the 4-kernel form
   // parameters
   double *d_mass, *d_emu, *d_emmu;  // [Cpad]

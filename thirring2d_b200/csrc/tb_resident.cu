@@ -7,8 +7,8 @@
 //   registers      r, p (persistent) and Mp, q (transient) for the TS sites of the thread's t-column
 //   shared memory  one exchange field F (p, then Mp: what the stencil neighbours read) 16 B/site
 //                  the two link fields W0, W1                                           32 B/site
-//   L2             x += alpha p as a 128-bit read-modify-write of a chain-major workspace (one owner thread per
-//                  element; loads issued ahead of the ||r||^2 barrier), 32 B/site/iteration
+//   tensor memory  x, thread-private columns (tcgen05.ld/st 32x32b): x += alpha p costs no LSU wavefronts; the
+//                  fallback (TB_RESIDENT_X_TMEM=0) is a 128-bit L2 read-modify-write of a chain-major workspace
 //
 // 64^2: 48 B/site * 4096 = 192 KB of the 227 KB shared memory, one CTA of 512 threads per SM, 148 chains in
 // flight per B200.  HBM is touched only to load b and the links once and to store x once per solve.
@@ -16,6 +16,8 @@
 // A thread owns TS consecutive t-sites of one x column, so the t-neighbours of both stencils are its own
 // registers; x-neighbours and the column ends come from F.  Reductions are fixed-shape (shuffle tree, then
 // warp partials summed in warp order) => run-to-run deterministic.
+#include <cstdint>
+
 #include "tb_common.cuh"
 
 namespace {
@@ -41,6 +43,29 @@ __device__ __forceinline__ void hopc_acc(double2 &o, const double2 w, const doub
     o.y = fma(-w.x, f.y, o.y); o.y = fma(w.y, f.x, o.y);
   }
 }
+
+// ---- tensor memory (TMEM) as a thread-private home for the solution vector x ------------------------------
+// 256 KB per SM that nothing else on this path uses.  A warp can only reach the 32 TMEM lanes of its own quarter
+// (warp % 4); within them every thread owns its lane, so "32x32b" loads/stores are exactly a per-thread scratch
+// array: WORDS 32-bit columns per thread, warps that share a quarter stacked along the columns.  x += alpha p then
+// costs no LSU wavefronts and no L2 round trip.
+__device__ __forceinline__ void tmem_ld16(uint32_t (&v)[16], uint32_t taddr) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32"
+               "[%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
+               :
+               : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
 template <int NWARPS>
 __device__ __forceinline__ double block_sum(double v, double *scratch) {
@@ -119,9 +144,14 @@ struct ResidentCfg {
   static constexpr int MINBLOCKS_RAW = 65536 / (NTHREADS * (REGS + 1));
   static constexpr int MINBLOCKS = MINBLOCKS_RAW < 1 ? 1 : (MINBLOCKS_RAW > 16 ? 16 : MINBLOCKS_RAW);
   static constexpr size_t SMEM = (size_t)V * 48 + 64 * sizeof(double);
+  // TMEM: 4 words (one double2) per site of the thread's tile; warps of the same lane quarter stack in columns
+  static constexpr int TMEM_WORDS = TX * TT * 4;
+  static constexpr int TMEM_NEED = TMEM_WORDS * ((NWARPS + 3) / 4);
+  static constexpr int TMEM_COLS = TMEM_NEED <= 32 ? 32 : (TMEM_NEED <= 64 ? 64 : (TMEM_NEED <= 128 ? 128 : (TMEM_NEED <= 256 ? 256 : 512)));
+  static constexpr bool TMEM_OK = (TMEM_WORDS % 16 == 0) && TMEM_NEED <= 512;
 };
 
-template <int NT, int NX, int TX, int TT, bool DAG, bool HAS_MU>
+template <int NT, int NX, int TX, int TT, bool DAG, bool HAS_MU, bool XT>
 __global__ void __launch_bounds__(ResidentCfg<NT, NX, TX, TT>::NTHREADS, ResidentCfg<NT, NX, TX, TT>::MINBLOCKS)
 resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
                    const double2 *__restrict__ W0g, const double2 *__restrict__ W1g,
@@ -137,6 +167,20 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
   double2 *W1s = W0s + V;
   double *scrA = reinterpret_cast<double *>(W1s + V);
   double *scrB = scrA + 32;
+  __shared__ uint32_t tmem_base_s;
+  uint32_t xaddr = 0;   // this thread's x columns in tensor memory (XT)
+  if (XT) {
+    if (threadIdx.x < 32) {   // one fully active warp allocates (and later frees) the columns
+      const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst), "r"(Cfg::TMEM_COLS) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const uint32_t warp = threadIdx.x >> 5;
+    xaddr = tmem_base_s + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (uint32_t)Cfg::TMEM_WORDS;
+  }
 
   const int c = c_first + blockIdx.x;
   const int tid = threadIdx.x;
@@ -220,6 +264,29 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
           rr = fma(r[i][j].x, r[i][j].x, rr);          // hmc.c:377-379
           rr = fma(r[i][j].y, r[i][j].y, rr);
         }
+      if (XT) {
+        // x += a p (hmc.c:372-373) in tensor memory: 4 sites (16 words) per tcgen05.ld / tcgen05.st
+        rr = block_sum<NWARPS>(rr, scrA);
+#pragma unroll
+        for (int ch = 0; ch < Cfg::TMEM_WORDS / 16; ch++) {
+          uint32_t v[16];
+          if (k > 1) tmem_ld16(v, xaddr + ch * 16);
+#pragma unroll
+          for (int u = 0; u < 4; u++) {
+            const int f = ch * 4 + u, i = f / TX, j = f % TX;
+            double xr = (k > 1) ? __hiloint2double((int)v[4 * u + 1], (int)v[4 * u]) : 0.0;   // hmc.c:351: x0 = 0
+            double xi = (k > 1) ? __hiloint2double((int)v[4 * u + 3], (int)v[4 * u + 2]) : 0.0;
+            xr += a * p[i][j].x;
+            xi += a * p[i][j].y;
+            v[4 * u] = (uint32_t)__double2loint(xr);
+            v[4 * u + 1] = (uint32_t)__double2hiint(xr);
+            v[4 * u + 2] = (uint32_t)__double2loint(xi);
+            v[4 * u + 3] = (uint32_t)__double2hiint(xi);
+          }
+          tmem_st16(xaddr + ch * 16, v);
+        }
+        tmem_wait_st();
+      } else {
       // x += a p (hmc.c:372-373): x lives in L2 (chain-major workspace, one owner thread per element); the
       // loads are issued before the ||r||^2 reduction so that their latency hides behind its barrier
       double2 xv[TT][TX];
@@ -239,6 +306,7 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
           v.y += a * p[i][j].y;
           __stcg(&xwc[(t0 + i) * NX + j * NG + g], v);
         }
+      }
       iters = k;
       if (rr < s.accuracy) { status = TB_CG_CONVERGED; break; }                                        // hmc.c:381
       if (!(rr == rr) || rr / rr_init > TB_DIVERGENCE_RATIO) { status = TB_CG_DIVERGED; break; }      // hmc.c:383
@@ -255,6 +323,24 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
       __syncthreads();
     }
   }
+  if (XT) {
+#pragma unroll
+    for (int ch = 0; ch < Cfg::TMEM_WORDS / 16; ch++) {
+      uint32_t v[16];
+      if (iters > 0) tmem_ld16(v, xaddr + ch * 16);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int f = ch * 4 + u, i = f / TX, j = f % TX;
+        const int kk = (t0 + i) * NX + g * TX + j;
+        xout[(size_t)kk * C + c] = (iters > 0) ? make_double2(__hiloint2double((int)v[4 * u + 1], (int)v[4 * u]),
+                                                               __hiloint2double((int)v[4 * u + 3], (int)v[4 * u + 2]))
+                                                : make_double2(0.0, 0.0);
+      }
+    }
+    __syncthreads();   // every warp has read its columns
+    if (threadIdx.x < 32)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base_s), "r"(Cfg::TMEM_COLS) : "memory");
+  } else {
   // every element of the workspace was written and is read back by the same thread
 #pragma unroll
   for (int i = 0; i < TT; i++)
@@ -263,6 +349,7 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
       const int k = (t0 + i) * NX + g * TX + j;
       xout[(size_t)k * C + c] = (iters > 0) ? __ldcg(&xwc[(t0 + i) * NX + j * NG + g]) : make_double2(0.0, 0.0);
     }
+  }
   if (tid == 0) {
     s.status[c] = status;
     s.iters[c] = iters;
@@ -276,10 +363,14 @@ template <int NT, int NX, int TX, int TT>
 int launch_resident(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st) {
   using Cfg = ResidentCfg<NT, NX, TX, TT>;
   const bool dag = tb_conj_is_dagger(ctx);
-  auto kern = dag ? (ctx->has_mu ? resident_cg_kernel<NT, NX, TX, TT, true, true>
-                                 : resident_cg_kernel<NT, NX, TX, TT, true, false>)
-                  : (ctx->has_mu ? resident_cg_kernel<NT, NX, TX, TT, false, true>
-                                 : resident_cg_kernel<NT, NX, TX, TT, false, false>);
+  constexpr bool T = Cfg::TMEM_OK;
+  const bool xt = T && ctx->resident_x_tmem;
+  auto kern = resident_cg_kernel<NT, NX, TX, TT, false, false, false>;
+#define PICK(D, M)                                                                               \
+  kern = xt ? resident_cg_kernel<NT, NX, TX, TT, D, M, T> : resident_cg_kernel<NT, NX, TX, TT, D, M, false>;
+  if (dag) { if (ctx->has_mu) { PICK(true, true) } else { PICK(true, false) } }
+  else { if (ctx->has_mu) { PICK(false, true) } else { PICK(false, false) } }
+#undef PICK
   TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   kern<<<n, Cfg::NTHREADS, Cfg::SMEM, st>>>(b, x, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu, ctx->xw,
                                             ctx->cg, ctx->C, c0);
