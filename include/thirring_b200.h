@@ -165,6 +165,14 @@ int tb_hmc_trajectory(tb_ctx *ctx, int nsteps, double traj_length, unsigned long
 int tb_hmc_measure(tb_ctx *ctx, int nsrc, unsigned long long seed, unsigned int meas_index,
                    const double *sources_host, double *magnetisation_host, double *phase_host);
 
+/* Chiral condensate per chain (the reference's measure() lacks it):
+ * (1/V) Tr M^-1 estimated as (1/(2 V nsrc)) sum_i Re<eta_i, M^-1 eta_i> with M^-1 eta = fm_invert_cg(eta)
+ * (hmc.c:408-414) over nsrc stochastic vectors (stochastic_vector, hmc.c:439-447; E|eta|^2 = 2 per site).
+ * sources_host (optional): complex [nsrc][chain][t][x]; cg_iters_host (optional): iterations summed over
+ * chains and sources.  A chain whose solve does not converge gets NaN. */
+int tb_hmc_condensate(tb_ctx *ctx, int nsrc, unsigned long long seed, unsigned int meas_index,
+                      const double *sources_host, double *condensate_host, long long *cg_iters_host);
+
 /* current gauge angles to the host, double[nchains][NT][NX][2] */
 int tb_get_gauge(tb_ctx *ctx, double *A_host);
 

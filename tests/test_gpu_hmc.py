@@ -173,3 +173,95 @@ def test_checkpoint_round_trip_and_batched_driver(tmp_path):
     # the first printed gauge action is the action of the checkpointed field: (Nf/g) sum (1 - cos A)
     sg0 = float(re.search(r"^\[chain 0\] Start HMC: Sg (\S+),", out, re.M).group(1))
     assert abs(sg0 - (2 / 0.3) * np.sum(1 - np.cos(A[0]))) <= 6e-6 * sg0
+
+
+def free_field_condensate(L, m):
+    """(1/V) Tr M^-1 at A = 0, mu = 0: (1/V) sum_k m / (m^2 + sum_mu sin^2 k_mu), k antiperiodic."""
+    k = (2 * np.arange(L) + 1) * np.pi / L
+    s = np.sin(k) ** 2
+    return float((m / (m * m + s[:, None] + s[None, :])).mean())
+
+
+@pytest.mark.parametrize("L,solver", [(16, 0), (8, 1)])
+def test_condensate_free_field(L, solver):
+    """Stochastic estimator against the closed form on the free field, both solvers (resident 16^2, streaming 8^2)."""
+    m, n, nsrc = 0.5, 64, 20
+    with tb.Context(L, L, n, tb.MODE_ADJOINT, m=m, mu=0.0) as ctx:
+        ctx.set_tuning(solver=solver)
+        ctx.set_gauge(np.zeros((n, L, L, 2)))
+        cond, iters = ctx.hmc_condensate(nsrc=nsrc, seed=11)
+    want = free_field_condensate(L, m)
+    err = cond.std(ddof=1) / np.sqrt(n)
+    assert iters > 0 and np.all(np.isfinite(cond))
+    assert abs(cond.mean() - want) < 4 * err, (cond.mean(), want, err)
+    assert err < 0.01 * want   # the estimator is not trivially noisy: 64 x 20 sources pin it to < 1 %
+
+
+@pytest.mark.parametrize("flavour,m,mu", [("adjoint", 0.3, 0.0), ("adjoint", 0.5, 0.2), ("compat", 100.0, 0.1)])
+def test_condensate_matches_reference_fm_invert_cg(flavour, m, mu):
+    """Same sources through the reference's own fm_invert_cg (hmc.c:408-414) on a heat-bath field."""
+    nt = nx = 16
+    if not ref_available(nt, nx, flavour):
+        pytest.skip("oracle/_ref not built")
+    ref = RefLib(nt, nx, flavour, m=m, g=0.3, mu=mu, seed=SEED, nsteps=10)
+    G = ref.gauge()
+    ref.heatbath(G, 5)
+    nsrc, n = 4, 3
+    rng = np.random.default_rng(5)
+    src = rng.standard_normal((nsrc, n, nt, nx)) + 1j * rng.standard_normal((nsrc, n, nt, nx))
+    want = np.zeros(n)
+    for i in range(nsrc):
+        for c in range(n):
+            want[c] += np.vdot(src[i, c], ref.fm_invert_cg(src[i, c], G)).real
+    want /= 2 * nt * nx * nsrc
+    mode = tb.MODE_ADJOINT if flavour == "adjoint" else tb.MODE_REF_COMPAT
+    with tb.Context(nt, nx, n, mode, m=m, mu=mu) as ctx:
+        ctx.set_gauge(np.broadcast_to(G.A, (n, nt, nx, 2)))
+        cond, _ = ctx.hmc_condensate(nsrc=nsrc, sources=src)
+    assert np.allclose(cond, want, rtol=1e-10, atol=0), (cond, want)
+
+
+def test_ensemble_matches_reference_chains(capfd):
+    """T8: device-RNG chains on the GPU against independent chains of the reference's own driver
+    functions (different Mersenne seeds), compared at equal trajectory index — the run is not thermalised, so
+    equal index, not 'equilibrium' — within the combined statistical error."""
+    nt = nx = 16
+    m, g, mu, nsteps, ntraj, sweeps = 0.5, 0.3, 0.0, 10, 6, 20
+    if not ref_available(nt, nx, "adjoint"):
+        pytest.skip("oracle/_ref not built")
+    libc = ctypes.CDLL(None)
+    n_ref, n_gpu = 48, 512
+    # --- reference chains: heat-bath start, then update_gauge; observables parsed from its own stdout
+    ref_obs = np.zeros((n_ref, ntraj, 4))   # Sg at start, dS, accepted, Magnetisation after the trajectory
+    for c in range(n_ref):
+        r = RefLib(nt, nx, "adjoint", m=m, g=g, mu=mu, nsteps=nsteps)
+        r.seed(1000 + 7 * c, warmup=2000)
+        G = r.gauge()
+        r.heatbath(G, sweeps)
+        for t in range(ntraj):
+            capfd.readouterr()
+            r.lib.update_gauge(G.top.ctypes.data)
+            libc.fflush(None)
+            out = capfd.readouterr().out
+            sg = float(re.search(r"Start HMC: Sg (\S+),", out).group(1))
+            ds = float(re.search(r"HMC End, dS (\S+),", out).group(1))
+            ref_obs[c, t] = sg, ds, float("HMC ACCEPTED" in out), G.A.sum() / (nt * nx)
+    # --- GPU chains
+    gpu_obs = np.zeros((n_gpu, ntraj, 4))
+    with tb.Context(nt, nx, n_gpu, tb.MODE_ADJOINT, m=m, mu=mu) as ctx:
+        ctx.hmc_set_coupling(g)
+        ctx.hmc_heatbath(sweeps, seed=77)
+        for t in range(ntraj):
+            obs, acc, _ = ctx.hmc_trajectory(nsteps=nsteps, traj_length=1.0, seed=77, traj_index=t + 1)
+            mag, _ = ctx.hmc_measure(nsrc=0)
+            gpu_obs[:, t] = np.stack([obs[:, 0], obs[:, 8], acc, mag], axis=1)
+    for t in range(ntraj):
+        for k, name in enumerate(["Sg", "dS", "acceptance", "Magnetisation"]):
+            a, b = ref_obs[:, t, k], gpu_obs[:, t, k]
+            if name == "dS":   # heavy upper tail (SURVEY Appendix C: mean |dS| ~ 3): compare the medians' proxy
+                a, b = np.minimum(a, 20.0), np.minimum(b, 20.0)
+            err = np.sqrt(a.var(ddof=1) / a.size + b.var(ddof=1) / b.size)
+            assert abs(a.mean() - b.mean()) < 4.0 * err + 1e-12, (t, name, a.mean(), b.mean(), err)
+    # the comparison has teeth: the gauge action is pinned to better than 2 %
+    a, b = ref_obs[:, 0, 0], gpu_obs[:, 0, 0]
+    assert np.sqrt(a.var(ddof=1) / a.size + b.var(ddof=1) / b.size) < 0.02 * a.mean()

@@ -283,6 +283,19 @@ class Context:
                                       ph.ctypes.data_as(_dp)), "tb_hmc_measure")
         return mag, ph
 
+    def hmc_condensate(self, nsrc=20, seed=1, meas_index=0, sources=None):
+        """Per-chain stochastic estimate of (1/V) Tr M^-1 through fm_invert_cg.  Returns (condensate, cg_iterations)."""
+        cond = np.empty(self.nchains, dtype=np.float64)
+        src = None
+        if sources is not None:
+            sources = np.ascontiguousarray(sources, dtype=np.complex128)
+            assert sources.shape == (nsrc, self.nchains, self.nt, self.nx)
+            src = sources.ctypes.data
+        its = C.c_longlong(0)
+        check(self.lib.tb_hmc_condensate(self._h, nsrc, seed, meas_index, src, cond.ctypes.data_as(_dp),
+                                         C.byref(its)), "tb_hmc_condensate")
+        return cond, its.value
+
     def checkpoint_write(self, path):
         check(self.lib.tb_checkpoint_write(self._h, os.fsencode(path)), "tb_checkpoint_write")
 

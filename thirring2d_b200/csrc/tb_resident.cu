@@ -4,68 +4,26 @@
 // independent, every CG reduction is a block-level reduction and no grid-wide synchronisation or kernel
 // boundary is needed.  The CG state never leaves the SM between iterations:
 //
-//   registers      r, p (persistent) and Mp, q (transient) for the TS sites of the thread's t-column
+//   registers      r, p (persistent) and Mp, q (transient) for the TT x TX site tile of the thread
 //   shared memory  one exchange field F (p, then Mp: what the stencil neighbours read) 16 B/site
 //                  the two link fields W0, W1                                           32 B/site
 //   tensor memory  x, thread-private columns (tcgen05.ld/st 32x32b): x += alpha p costs no LSU wavefronts; the
 //                  fallback (TB_RESIDENT_X_TMEM=0) is a 128-bit L2 read-modify-write of a chain-major workspace
 //
-// 64^2: 48 B/site * 4096 = 192 KB of the 227 KB shared memory, one CTA of 512 threads per SM, 148 chains in
-// flight per B200.  HBM is touched only to load b and the links once and to store x once per solve.
+// 64^2: 48 B/site * 4096 = 192 KB of the 227 KB shared memory, one CTA of 256 threads (2 x 8 sites each, 255
+// registers) per SM, 148 chains in flight per B200.  HBM is touched only to load b and the links once and to
+// store x once per solve.  Larger lattices (128^2, 256^2) use one thread-block CLUSTER per chain: tb_cluster.cu.
 //
-// A thread owns TS consecutive t-sites of one x column, so the t-neighbours of both stencils are its own
-// registers; x-neighbours and the column ends come from F.  Reductions are fixed-shape (shuffle tree, then
-// warp partials summed in warp order) => run-to-run deterministic.
+// A thread owns a TT x TX tile of sites, so most stencil neighbours are its own registers; the tile's halo comes
+// from F.  Reductions are fixed-shape (shuffle tree, then warp partials summed in warp order) => run-to-run
+// deterministic.
 #include <cstdint>
 
 #include "tb_common.cuh"
 
 namespace {
 
-// o += sgn * (w * f)  and  o += sgn * (conj(w) * f), as four FMAs each (operand negation is free in SASS)
-template <int SGN>
-__device__ __forceinline__ void hop_acc(double2 &o, const double2 w, const double2 f) {
-  if (SGN > 0) {
-    o.x = fma(w.x, f.x, o.x);  o.x = fma(-w.y, f.y, o.x);
-    o.y = fma(w.x, f.y, o.y);  o.y = fma(w.y, f.x, o.y);
-  } else {
-    o.x = fma(-w.x, f.x, o.x); o.x = fma(w.y, f.y, o.x);
-    o.y = fma(-w.x, f.y, o.y); o.y = fma(-w.y, f.x, o.y);
-  }
-}
-template <int SGN>
-__device__ __forceinline__ void hopc_acc(double2 &o, const double2 w, const double2 f) {
-  if (SGN > 0) {
-    o.x = fma(w.x, f.x, o.x);  o.x = fma(w.y, f.y, o.x);
-    o.y = fma(w.x, f.y, o.y);  o.y = fma(-w.y, f.x, o.y);
-  } else {
-    o.x = fma(-w.x, f.x, o.x); o.x = fma(-w.y, f.y, o.x);
-    o.y = fma(-w.x, f.y, o.y); o.y = fma(w.y, f.x, o.y);
-  }
-}
-
-// ---- tensor memory (TMEM) as a thread-private home for the solution vector x ------------------------------
-// 256 KB per SM that nothing else on this path uses.  A warp can only reach the 32 TMEM lanes of its own quarter
-// (warp % 4); within them every thread owns its lane, so "32x32b" loads/stores are exactly a per-thread scratch
-// array: WORDS 32-bit columns per thread, warps that share a quarter stacked along the columns.  x += alpha p then
-// costs no LSU wavefronts and no L2 round trip.
-__device__ __forceinline__ void tmem_ld16(uint32_t (&v)[16], uint32_t taddr) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"
-               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-               : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32"
-               "[%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};\n"
-               :
-               : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
-                 "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
-               : "memory");
-}
-__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+#include "tb_onchip.cuh"
 
 template <int NWARPS>
 __device__ __forceinline__ double block_sum(double v, double *scratch) {

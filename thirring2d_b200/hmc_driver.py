@@ -59,6 +59,8 @@ def main(argv=None):
     ap.add_argument("--mode", choices=["compat", "adjoint"], default="compat")
     ap.add_argument("--nsteps", type=int, default=10, help="leapfrog steps (hard-coded 10 in hmc.c:708)")
     ap.add_argument("--traj-length", type=float, default=1.0, help="hard-coded 1 in hmc.c:709")
+    ap.add_argument("--condensate", type=int, default=0, metavar="NSRC",
+                    help="also print the chiral condensate from NSRC stochastic sources (not in the reference's measure())")
     ap.add_argument("--device", type=int, default=0)
     ap.add_argument("--checkpoint", default=None, help="write the gauge fields here at the end")
     ap.add_argument("--resume", default=None, help="start from this checkpoint instead of the heat bath")
@@ -82,6 +84,10 @@ def main(argv=None):
                 mag, ph = ctx.hmc_measure(20, seed=seed, meas_index=i)
                 for c in range(a.chains):
                     print("\n".join(measurement_lines(mag[c], ph[c], c)))
+                if a.condensate > 0:
+                    cond, _ = ctx.hmc_condensate(a.condensate, seed=seed, meas_index=i)
+                    for c in range(a.chains):
+                        print("[chain %d] Condensate %s" % (c, fmt_g(cond[c])))
         if a.checkpoint:
             ctx.checkpoint_write(a.checkpoint)
     return 0
