@@ -111,6 +111,7 @@ int tb_create_common(tb_ctx **out, int nt, int nx, int nchains, int mode, int de
   ctx->tune_solver = (e = getenv("TB_SOLVER")) ? atoi(e) : 0;
   ctx->cg_variant = (e = getenv("TB_CG_VARIANT")) ? atoi(e) : 0;
   ctx->resident_x_tmem = (e = getenv("TB_RESIDENT_X_TMEM")) ? atoi(e) : 1;
+  ctx->cluster_capacity = -1;
   tb_choose_geom(ctx);
   int rc = TB_OK;
   cudaError_t ce = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -391,15 +392,27 @@ extern "C" int tb_apply_dev(tb_ctx *ctx, int op, const double *d_in, double *d_o
   }
 }
 
+// 0 = streaming, 1 = one CTA per chain (tb_resident.cu), 2 = one thread-block cluster per chain (tb_cluster.cu)
+static int onchip_solver(tb_ctx *ctx) {
+  if (ctx->tune_solver == 1) return 0;
+  if (tb_resident_supported(ctx)) return 1;
+  if (tb_cluster_supported(ctx)) return 2;
+  return 0;
+}
+
+static int run_onchip_slice(tb_ctx *ctx, int kind, const double2 *b, double2 *x, int c0, int n, cudaStream_t st) {
+  return kind == 1 ? tb_run_cg_resident_slice(ctx, b, x, c0, n, st) : tb_run_cg_cluster_slice(ctx, b, x, c0, n, st);
+}
+
 int tb_run_cg_any(tb_ctx *ctx, const double2 *b, double2 *x) {
   TB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  // solver selection: 0 auto (resident when the lattice fits on chip), 1 streaming, 2 resident
-  const bool resident = ctx->tune_solver != 1 && tb_resident_supported(ctx);
-  if (ctx->tune_solver == 2 && !resident) {
-    tb_set_error("resident solver requested but %dx%d is not supported", ctx->nt, ctx->nx);
+  // solver selection: 0 auto (on-chip when the lattice has a resident or cluster shape), 1 streaming, 2 on-chip
+  const int onchip = onchip_solver(ctx);
+  if (ctx->tune_solver == 2 && !onchip) {
+    tb_set_error("on-chip solver requested but %dx%d is not supported", ctx->nt, ctx->nx);
     return TB_EINVAL;
   }
-  if (resident) TB_CHECK(tb_run_cg_resident(ctx, b, x));
+  if (onchip) TB_CHECK(run_onchip_slice(ctx, onchip, b, x, 0, ctx->C, ctx->stream));
   else TB_CHECK(tb_run_cg_stream(ctx, b, x));
   TB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   TB_CUDA(cudaEventSynchronize(ctx->ev1));
@@ -543,12 +556,12 @@ static int solve_host(tb_ctx *ctx, bool with_conj, const double *b_host, double 
                       double *rr) {
   TB_CUDA(cudaSetDevice(ctx->device));
   TB_CHECK(need_gauge(ctx));
-  const bool resident = ctx->tune_solver != 1 && tb_resident_supported(ctx);
-  if (ctx->tune_solver == 2 && !resident) {
-    tb_set_error("resident solver requested but %dx%d is not supported", ctx->nt, ctx->nx);
+  const int onchip = onchip_solver(ctx);
+  if (ctx->tune_solver == 2 && !onchip) {
+    tb_set_error("on-chip solver requested but %dx%d is not supported", ctx->nt, ctx->nx);
     return TB_EINVAL;
   }
-  if (!resident || with_conj) {
+  if (!onchip || with_conj) {
     TB_CHECK(upload_vec(ctx, b_host, ctx->vin));
     if (with_conj) TB_CHECK(tb_invert_dev(ctx, (const double *)ctx->vin, (double *)ctx->vout));
     else TB_CHECK(tb_cg_dev(ctx, (const double *)ctx->vin, (double *)ctx->vout));
@@ -559,7 +572,7 @@ static int solve_host(tb_ctx *ctx, bool with_conj, const double *b_host, double 
     for (int s = 0; s < ctx->nsub; s++) {
       int c0, n;
       sub_range(ctx, s, &c0, &n);
-      if (n) TB_CHECK(tb_run_cg_resident_slice(ctx, ctx->vin, ctx->vout, c0, n, ctx->sub_stream[s]));
+      if (n) TB_CHECK(run_onchip_slice(ctx, onchip, ctx->vin, ctx->vout, c0, n, ctx->sub_stream[s]));
     }
     TB_CHECK(download_vec(ctx, ctx->vout, x_host));
     TB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));

@@ -460,6 +460,7 @@ int tb_run_cg_cluster_slice(tb_ctx *ctx, const double2 *b, double2 *x, int c0, i
   return TB_EINVAL;
 }
 
+int tb_run_cg_cluster(tb_ctx *ctx, const double2 *b, double2 *x);
 int tb_run_cg_cluster(tb_ctx *ctx, const double2 *b, double2 *x) {
   return tb_run_cg_cluster_slice(ctx, b, x, 0, ctx->C, ctx->stream);
 }

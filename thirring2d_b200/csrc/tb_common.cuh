@@ -102,6 +102,7 @@ struct tb_ctx {
   TbGeom g;
   int tune_tt, tune_chunk, tune_solver;
   int resident_x_tmem;  // resident solver: keep x in tensor memory (1, default) or in an L2 workspace (0)
+  int cluster_capacity; // cluster solver: co-resident clusters of this lattice's shape (-1 = not queried yet)
   int cg_variant;  // 0 auto (fused 3-kernel iteration when M~ = M^dagger), 4 = always the 4-kernel form
   // parameters
   double *d_mass, *d_emu, *d_emmu;  // [Cpad]
@@ -159,6 +160,9 @@ int tb_launch_links_slice(tb_ctx *ctx, const double2 *d_A_dev_layout, int c0, in
 int tb_launch_pack_slice(tb_ctx *ctx, const double2 *d_canonical_slice, double2 *d_vec, int c0, int n, cudaStream_t st);
 int tb_launch_unpack_slice(tb_ctx *ctx, const double2 *d_vec, double2 *d_canonical_slice, int c0, int n, cudaStream_t st);
 bool tb_resident_supported(const tb_ctx *ctx);
+bool tb_cluster_supported(tb_ctx *ctx);
+int tb_cluster_capacity(tb_ctx *ctx);
+int tb_run_cg_cluster_slice(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st);
 int tb_launch_dot(tb_ctx *ctx, const double2 *a, const double2 *b, double *d_out);
 int tb_launch_occupancy(tb_ctx *ctx, const int *d_field_canonical);
 int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out);
