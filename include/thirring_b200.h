@@ -72,9 +72,16 @@ int tb_set_cg(tb_ctx *ctx, double accuracy, int max_iter);
 /* Tuning knobs (0 = automatic).  rows_per_thread: t-rows marched per thread by the streaming stencil
  * (1,2,4,8,16); for the resident solver the same field selects the site tile per thread (44 = 4x4,
  * 18 = 1x8, 28 = 2x8, 24 = 2x4).  iters_per_launch: CG iterations per CUDA-graph launch (streaming).
- * solver: 0 auto (resident when the lattice is 16^2/32^2/64^2), 1 streaming multi-kernel (3 fused kernels per
- * iteration when M~ = M^dagger, else 4), 2 resident, 3 streaming with the 4-kernel iteration always. */
+ * solver: 0 auto (on-chip when the lattice has a resident or cluster shape, see tb_solver_info), 1 streaming
+ * multi-kernel (3 fused kernels per iteration when M~ = M^dagger, else 4), 2 on-chip or fail, 3 streaming with
+ * the 4-kernel iteration always. */
 int tb_set_tuning(tb_ctx *ctx, int rows_per_thread, int iters_per_launch, int solver);
+
+/* Which CG solver the context will use with the current tuning: kind 0 = streaming kernels, 1 = on-chip, one CTA
+ * per chain (16^2/32^2/64^2), 2 = on-chip, one thread-block cluster per chain (lattices of CS * 4096/NX rows by
+ * NX in {64,128,256} sites, 2 <= CS <= 16: 128^2, 256^2, ...).  chains_in_flight: chains the on-chip solver
+ * runs concurrently on this device (0 for streaming).  Either pointer may be NULL. */
+int tb_solver_info(tb_ctx *ctx, int *kind, int *chains_in_flight);
 
 /* ---- host-buffer entry points (copies inside; this is what the reference-facing shim calls) ---------- */
 

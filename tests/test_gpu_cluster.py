@@ -1,4 +1,4 @@
-"""Thread-block-cluster CG (tb_cluster.cu: one cluster of 64x64 sub-lattices per chain, halos and reductions over
+"""Thread-block-cluster CG (tb_cluster.cu: one cluster of 4096-site t-slabs per chain, halos and reductions over
 distributed shared memory) against the CPU oracle and against the streaming solver, through the C-ABI.
 Tolerances as everywhere: iteration count +-1, solution 1e-12 l2/max relative."""
 import numpy as np
@@ -12,12 +12,14 @@ tb = pytest.importorskip("thirring2d_b200")
 
 CASES = [
     # nt, nx, nchains, mode, m, mu
-    (128, 128, 3, tb.MODE_ADJOINT, 0.3, 0.0),     # 2 x 2 CTAs
-    (64, 128, 2, tb.MODE_ADJOINT, 0.5, 0.1),      # 1 x 2
-    (128, 64, 2, tb.MODE_REF_COMPAT, 100.0, 0.1), # 2 x 1, the shipped parameter regime (M~ = M)
-    (256, 256, 2, tb.MODE_ADJOINT, 0.5, 0.0),     # 4 x 4 (non-portable cluster size 16)
-    (128, 256, 1, tb.MODE_ADJOINT, 0.4, -0.2),    # 2 x 4
-    (256, 128, 1, tb.MODE_ADJOINT, 0.4, 0.0),     # 4 x 2
+    (128, 128, 3, tb.MODE_ADJOINT, 0.3, 0.0),     # 4 CTAs of 32 rows
+    (64, 128, 2, tb.MODE_ADJOINT, 0.5, 0.1),      # 2 CTAs of 32 rows
+    (128, 64, 2, tb.MODE_REF_COMPAT, 100.0, 0.1), # 2 CTAs of 64 rows, the shipped parameter regime (M~ = M)
+    (256, 256, 2, tb.MODE_ADJOINT, 0.5, 0.0),     # 16 CTAs of 16 rows (non-portable cluster size)
+    (128, 256, 1, tb.MODE_ADJOINT, 0.4, -0.2),    # 8 CTAs of 16 rows
+    (256, 128, 1, tb.MODE_ADJOINT, 0.4, 0.0),     # 8 CTAs of 32 rows
+    (256, 64, 2, tb.MODE_ADJOINT, 0.6, 0.05),     # 4 CTAs of 64 rows
+    (64, 256, 2, tb.MODE_ADJOINT, 0.7, 0.1),      # 4 CTAs of 16 rows
 ]
 
 
@@ -30,6 +32,8 @@ def test_cluster_cg_matches_oracle_and_streaming(oracle, nt, nx, nchains, mode, 
         ctx.set_gauge(A)
         b = ctx.fm_conjugate_mul(xi)
         ctx.set_tuning(solver=2)   # on-chip: must be the cluster kernel for these shapes, or fail loudly
+        kind, in_flight = ctx.solver_info()
+        assert kind == 2 and in_flight >= 1
         x, info = ctx.fmdm_invert_cg(b)
         x2, info2 = ctx.fmdm_invert_cg(b)
         ctx.set_tuning(solver=1)

@@ -116,6 +116,12 @@ class Context:
     def set_tuning(self, rows_per_thread=0, iters_per_launch=0, solver=0):
         check(self.lib.tb_set_tuning(self._h, rows_per_thread, iters_per_launch, solver), "tb_set_tuning")
 
+    def solver_info(self):
+        """(kind, chains_in_flight): kind 0 streaming, 1 on-chip CTA per chain, 2 on-chip cluster per chain."""
+        k, n = C.c_int(0), C.c_int(0)
+        check(self.lib.tb_solver_info(self._h, C.byref(k), C.byref(n)), "tb_solver_info")
+        return k.value, n.value
+
     # -- host-buffer path (reference-facing) -----------------------------------------------------------------
     def _vec(self, v):
         v = np.ascontiguousarray(v, dtype=np.complex128)

@@ -422,6 +422,25 @@ int tb_run_cg_any(tb_ctx *ctx, const double2 *b, double2 *x) {
   return TB_OK;
 }
 
+extern "C" int tb_solver_info(tb_ctx *ctx, int *kind, int *chains_in_flight) {
+  if (!ctx) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  const int k = onchip_solver(ctx);
+  if (kind) *kind = k;
+  if (chains_in_flight) {
+    int n = 0;
+    if (k == 1) {
+      cudaDeviceProp prop;
+      TB_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+      n = prop.multiProcessorCount;   // one CTA per SM at 64^2; smaller lattices pack more
+    } else if (k == 2) {
+      n = tb_cluster_capacity(ctx);
+    }
+    *chains_in_flight = n;
+  }
+  return TB_OK;
+}
+
 extern "C" int tb_cg_dev(tb_ctx *ctx, const double *d_b, double *d_x) {
   if (!ctx || !d_b || !d_x) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));

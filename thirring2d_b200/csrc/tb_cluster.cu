@@ -1,24 +1,26 @@
 // tb_cluster.cu — on-chip resident batched CG for lattices that do not fit one SM: one THREAD-BLOCK CLUSTER per
-// Markov chain (128^2 = 2x2 CTAs, 256^2 = 4x4 CTAs, and the rectangles in between), sm_100a, FP64.
+// Markov chain (128^2 = 4 CTAs, 256^2 = 16 CTAs, and the rectangles in between), sm_100a, FP64.
 //
 // Same algorithm and per-thread arithmetic as tb_resident.cu (fmdm_invert_cg, hmc.c:341-404), with the lattice
-// cut into 64 x 64 sub-lattices, one per CTA of the cluster.  The CG state of a sub-lattice never leaves its SM:
+// cut into t-slabs of 4096 sites (LT = 4096/NX rows of NX sites), one per CTA of the cluster.  The CG state of a
+// slab never leaves its SM:
 //
 //   registers      r, p (persistent), Mp, q (transient): 8 x 2 sites per thread, 256 threads
-//   shared memory  exchange field F (p, then Mp), links W0, W1 of the sub-lattice       48 B/site = 192 KB
-//                  halo rows/columns of p and of Mp, pushed by the four neighbour CTAs  2 x 4 x 64 x 16 B
-//                  halo row of W0 and halo column of W1 (constant during the solve)     2 x 64 x 16 B
+//   shared memory  exchange field F (p, then Mp), links W0, W1 of the slab              48 B/site = 192 KB
+//                  halo rows t = -1 and t = LT of p and of Mp, pushed by the neighbours  4 x NX x 16 B
+//                  halo row of W0 (constant during the solve)                            NX x 16 B
 //   tensor memory  x, thread-private columns (tcgen05.ld/st 32x32b)
 //
 // Distributed shared memory carries everything that crosses a CTA boundary:
-//   * halos are PUSHED: the thread that produces a boundary site of p or Mp also stores it into the neighbour
-//     CTA's halo buffer (st.shared::cluster); the stencil itself only ever reads local shared memory;
+//   * halos are PUSHED: the warps that produce the first / last row of p or Mp also store it into the neighbour
+//     CTA's halo buffer (st.shared::cluster, 512 contiguous bytes per warp); the stencil reads local memory only;
 //   * both CG reductions are all-to-all over the cluster: every CTA stores its block sum into every CTA's slot
 //     table, and all CTAs add the slots in rank order => bitwise identical alpha, beta and stopping decisions on
 //     every CTA with no further communication (and run-to-run deterministic);
-//   * barrier.cluster (arrive.release / wait.acquire) publishes both; the x += alpha p update in tensor memory
-//     runs between the arrive and the wait of the ||r||^2 reduction.
-// Three cluster barriers and one CTA barrier per CG iteration.  HBM is touched once per solve.
+//   * barrier.cluster is split into arrive.release / wait.acquire and the latency is hidden: a stencil first does
+//     everything that needs only the CTA's own rows, waits, and then adds the one hop that comes from the halo row
+//     (first / last row of the slab); the x += alpha p update in tensor memory runs inside the ||r||^2 barrier.
+// Three split cluster barriers per CG iteration.  HBM is touched once per solve.
 #include <cstdint>
 
 #include "tb_common.cuh"
@@ -27,26 +29,29 @@ namespace {
 
 #include "tb_onchip.cuh"
 
-constexpr int LT = 64, LX = 64;            // sub-lattice of one CTA
 constexpr int TX = 2, TT = 8;              // sites per thread: TT rows (t) x TX columns (x)
-constexpr int NG = LX / TX;                // x-groups per row = lanes of a warp
-constexpr int NTHREADS = (LT / TT) * NG;   // 256
+constexpr int VL = 4096;                   // sites per CTA
+constexpr int NTHREADS = VL / (TX * TT);   // 256
 constexpr int NWARPS = NTHREADS / 32;      // 8
-constexpr int VL = LT * LX;
-static_assert(NG == 32, "a warp is one row of tiles");
-
-// shared-memory map, in double2 units from the start of dynamic shared memory
-constexpr int OFF_F = 0, OFF_W0 = VL, OFF_W1 = 2 * VL;
-constexpr int OFF_HP = 3 * VL;             // halos of p : [dn | up | left | right], 64 each
-constexpr int OFF_HM = OFF_HP + 4 * 64;    // halos of Mp
-constexpr int OFF_W0H = OFF_HM + 4 * 64;   // W0(t = -1, x)   row layout
-constexpr int OFF_W1H = OFF_W0H + 64;      // W1(t, x = -1)   indexed by t
-constexpr int OFF_END = OFF_W1H + 64;
-constexpr int H_DN = 0, H_UP = 64, H_L = 128, H_R = 192;
-// doubles after OFF_END: warp partials A, B [NWARPS each], cluster slots A, B [16 each]
-constexpr size_t CL_SMEM = (size_t)OFF_END * sizeof(double2) + (2 * NWARPS + 32) * sizeof(double);
 constexpr int TMEM_WORDS = TX * TT * 4;                    // 64 words of x per thread
 constexpr int TMEM_COLS = TMEM_WORDS * (NWARPS / 4);       // 128 columns
+
+// Geometry and shared-memory map (double2 units from the start of dynamic shared memory) of an NX-wide slab.
+template <int NX>
+struct Slab {
+  static constexpr int LT = VL / NX;         // rows per CTA
+  static constexpr int NGX = NX / TX;        // tiles per row; consecutive threads = consecutive tiles of a row
+  static_assert(LT % TT == 0 && LT * NX == VL && NGX % 32 == 0, "slab shape");
+  static constexpr int OFF_F = 0, OFF_W0 = VL, OFF_W1 = 2 * VL;
+  static constexpr int OFF_HP = 3 * VL;              // halo rows of p : [dn (t = -1) | up (t = LT)], row layout
+  static constexpr int OFF_HM = OFF_HP + 2 * NX;     // halo rows of Mp
+  static constexpr int OFF_W0H = OFF_HM + 2 * NX;    // W0(t = -1, x)
+  static constexpr int OFF_END = OFF_W0H + NX;
+  static constexpr int H_DN = 0, H_UP = NX;
+  // doubles after OFF_END: warp partials A, B [NWARPS each], cluster slots A, B [16 each]
+  static constexpr size_t SMEM = (size_t)OFF_END * sizeof(double2) + (2 * NWARPS + 32) * sizeof(double);
+  static_assert(SMEM <= 232448, "exceeds the 227 KB of shared memory per CTA");
+};
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -67,7 +72,9 @@ __device__ __forceinline__ void st_cluster(uint32_t addr, const double v) {
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
 
-// Block sum -> every CTA's slot table.  After the caller's cluster barrier, cluster_total adds the CS slots.
+// Block sum -> every CTA's slot table; ends with a CTA barrier BEFORE the remote stores, so the caller's shared-
+// memory writes that precede it are visible CTA-wide afterwards.  After the caller's cluster barrier,
+// cluster_total adds the CS slots in rank order.
 template <int CS>
 __device__ __forceinline__ void cluster_sum_post(double v, double *wscr, uint32_t slots_saddr, uint32_t my_rank) {
 #pragma unroll
@@ -89,66 +96,52 @@ __device__ __forceinline__ double cluster_total(const double *slots) {
   return s;
 }
 
-// The thread's boundary sites of v -> the halo buffers (set HSET) of the four neighbour CTAs.
-struct Nbr {
-  uint32_t tm, tp, xm, xp;   // cluster ranks of the CTAs at (ct-1), (ct+1), (cx-1), (cx+1), periodic
-};
-__device__ __forceinline__ void push_halos(const double2 (&v)[TT][TX], int hset, uint32_t smem_base, const Nbr nb,
-                                           int t0, int g) {
-  const uint32_t hb = smem_base + (uint32_t)hset * 16u;
-  if (t0 == 0) {             // my first row is the (t+1) halo of the CTA above
-    const uint32_t a = mapa_shared(hb + (H_UP + g) * 16u, nb.tm);
+// first row of the slab -> the "up" halo of the CTA that owns the rows before mine; last row -> the "dn" halo of
+// the CTA that owns the rows after mine (periodic in the cluster rank; the antiperiodic sign lives in the links)
+template <int NX>
+__device__ __forceinline__ void push_rows(const double2 (&v)[TT][TX], int hset, uint32_t smem_base, uint32_t rank_m,
+                                          uint32_t rank_p, bool top, bool bot, int g) {
+  using G = Slab<NX>;
+  if (top) {
+    const uint32_t a = mapa_shared(smem_base + (uint32_t)(hset + G::H_UP + g) * 16u, rank_m);
 #pragma unroll
-    for (int j = 0; j < TX; j++) st_cluster(a + j * NG * 16u, v[0][j]);
+    for (int j = 0; j < TX; j++) st_cluster(a + j * G::NGX * 16u, v[0][j]);
   }
-  if (t0 + TT == LT) {       // my last row is the (t-1) halo of the CTA below
-    const uint32_t a = mapa_shared(hb + (H_DN + g) * 16u, nb.tp);
+  if (bot) {
+    const uint32_t a = mapa_shared(smem_base + (uint32_t)(hset + G::H_DN + g) * 16u, rank_p);
 #pragma unroll
-    for (int j = 0; j < TX; j++) st_cluster(a + j * NG * 16u, v[TT - 1][j]);
-  }
-  if (g == 0) {              // my first column is the (x+1) halo of the CTA to the left
-    const uint32_t a = mapa_shared(hb + (H_R + t0) * 16u, nb.xm);
-#pragma unroll
-    for (int i = 0; i < TT; i++) st_cluster(a + i * 16u, v[i][0]);
-  }
-  if (g == NG - 1) {         // my last column is the (x-1) halo of the CTA to the right
-    const uint32_t a = mapa_shared(hb + (H_L + t0) * 16u, nb.xp);
-#pragma unroll
-    for (int i = 0; i < TT; i++) st_cluster(a + i * 16u, v[i][TX - 1]);
+    for (int j = 0; j < TX; j++) st_cluster(a + j * G::NGX * 16u, v[TT - 1][j]);
   }
 }
 
-// out = m f +- hops on the thread's tile of the 64 x 64 sub-lattice; S = shared memory as double2[], hset = the
-// halo set that belongs to the field in F.  Same arithmetic and order as tile_apply of tb_resident.cu.
-template <bool DAG, bool HAS_MU>
-__device__ __forceinline__ void tile_apply_cl(const double2 (&f)[TT][TX], double2 (&out)[TT][TX], const double2 *S,
-                                              int hset, int t0, int g, double m, double af, double ab) {
+// out = m f +- hops on the thread's tile, EXCEPT the hop from the halo row t = -1 (tiles with top) and from the
+// halo row t = LT (tiles with bot): those are added by tile_fixup once the neighbours' rows have arrived.
+// Same arithmetic and hop order as tile_apply of tb_resident.cu for every other site.
+template <int NX, bool DAG, bool HAS_MU>
+__device__ __forceinline__ void tile_apply_own(const double2 (&f)[TT][TX], double2 (&out)[TT][TX], const double2 *S,
+                                               int t0, int g, bool top, bool bot, double m, double af, double ab) {
+  using G = Slab<NX>;
   constexpr int SF = DAG ? -1 : 1;
   constexpr int SB = -SF;
-  // rows t0-1 and t0+TT of the field, and row t0-1 of W0: own F / W0 or the halo rows (warp-uniform selects)
-  const int rowm = (t0 == 0) ? hset + H_DN : OFF_F + (t0 - 1) * LX;
-  const int rowe = (t0 + TT == LT) ? hset + H_UP : OFF_F + (t0 + TT) * LX;
-  const int w0rm = (t0 == 0) ? OFF_W0H : OFF_W0 + (t0 - 1) * LX;
-  // columns x0-1 and x0+TX: own F (stride LX) or the halo columns (stride 1); same for W1(t, x0-1)
-  const int colL = (g == 0) ? hset + H_L + t0 : OFF_F + t0 * LX + (TX - 1) * NG + g - 1;
-  const int colR = (g == NG - 1) ? hset + H_R + t0 : OFF_F + t0 * LX + g + 1;
-  const int w1L = (g == 0) ? OFF_W1H + t0 : OFF_W1 + t0 * LX + (TX - 1) * NG + g - 1;
-  const int sL = (g == 0) ? 1 : LX, sR = (g == NG - 1) ? 1 : LX;
-  double2 w0m[TX];
+  constexpr int NGX = G::NGX;
+  const int gl = (g + NGX - 1) % NGX, gr = (g + 1) % NGX;
+  const double2 *F = S + G::OFF_F, *W0s = S + G::OFF_W0, *W1s = S + G::OFF_W1;
+  const double2 zero = make_double2(0.0, 0.0);
+  double2 w0m[TX];                  // W0(t-1, x0+j): slides down the tile
 #pragma unroll
-  for (int j = 0; j < TX; j++) w0m[j] = S[w0rm + j * NG + g];
+  for (int j = 0; j < TX; j++) w0m[j] = top ? zero : W0s[(t0 - 1) * NX + j * NGX + g];
 #pragma unroll
   for (int i = 0; i < TT; i++) {
-    const int row = (t0 + i) * LX;
-    const double2 fL = S[colL + i * sL];
-    const double2 fR = S[colR + i * sR];
-    double2 w1m = S[w1L + i * sL];
+    const int row = (t0 + i) * NX;
+    const double2 fL = F[row + (TX - 1) * NGX + gl];    // f(t, x0-1)
+    const double2 fR = F[row + gr];                     // f(t, x0+TX)
+    double2 w1m = W1s[row + (TX - 1) * NGX + gl];       // W1(t, x0-1): slides along the row
 #pragma unroll
     for (int j = 0; j < TX; j++) {
-      const double2 w0c = S[OFF_W0 + row + j * NG + g];
-      const double2 w1c = S[OFF_W1 + row + j * NG + g];
-      const double2 up = (i == TT - 1) ? S[rowe + j * NG + g] : f[(i + 1) % TT][j];
-      const double2 dn = (i == 0) ? S[rowm + j * NG + g] : f[(i + TT - 1) % TT][j];
+      const double2 w0c = W0s[row + j * NGX + g];
+      const double2 w1c = W1s[row + j * NGX + g];
+      const double2 up = (i == TT - 1) ? (bot ? zero : F[(t0 + TT) * NX + j * NGX + g]) : f[(i + 1) % TT][j];
+      const double2 dn = (i == 0) ? (top ? zero : F[(t0 - 1) * NX + j * NGX + g]) : f[(i + TT - 1) % TT][j];
       const double2 rt = (j == TX - 1) ? fR : f[i][(j + 1) % TX];
       const double2 lf = (j == 0) ? fL : f[i][(j + TX - 1) % TX];
       double2 o = make_double2(m * f[i][j].x, m * f[i][j].y);   // hmc.c:137-180
@@ -168,16 +161,42 @@ __device__ __forceinline__ void tile_apply_cl(const double2 (&f)[TT][TX], double
   }
 }
 
-template <int CT, int CX, bool DAG, bool HAS_MU>
+// the two hops tile_apply_own left out: -+ ab conj(W0(-1,x)) f(-1,x) into row 0, +- af W0(LT-1,x) f(LT,x) into row LT-1
+template <int NX, bool DAG, bool HAS_MU>
+__device__ __forceinline__ void tile_fixup(double2 (&out)[TT][TX], const double2 *S, int hset, int t0, int g, bool top,
+                                           bool bot, double af, double ab) {
+  using G = Slab<NX>;
+  constexpr int SF = DAG ? -1 : 1;
+  constexpr int SB = -SF;
+  if (top) {
+#pragma unroll
+    for (int j = 0; j < TX; j++) {
+      double2 w = S[G::OFF_W0H + j * G::NGX + g];
+      if (HAS_MU) w = make_double2(w.x * ab, w.y * ab);
+      hopc_acc<SB>(out[0][j], w, S[hset + G::H_DN + j * G::NGX + g]);
+    }
+  }
+  if (bot) {
+#pragma unroll
+    for (int j = 0; j < TX; j++) {
+      double2 w = S[G::OFF_W0 + (t0 + TT - 1) * NX + j * G::NGX + g];
+      if (HAS_MU) w = make_double2(w.x * af, w.y * af);
+      hop_acc<SF>(out[TT - 1][j], w, S[hset + G::H_UP + j * G::NGX + g]);
+    }
+  }
+}
+
+template <int NX, int CS, bool DAG, bool HAS_MU>
 __global__ void __launch_bounds__(NTHREADS, 1)
 cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, const double2 *__restrict__ W0g,
                   const double2 *__restrict__ W1g, const double *__restrict__ mass, const double *__restrict__ emu,
                   const double *__restrict__ emmu, const TbCgState s, const int C, const int c_first) {
-  constexpr int CS = CT * CX, NT = CT * LT, NX = CX * LX;
-  static_assert(CS <= 16, "slot tables hold 16 ranks");
+  using G = Slab<NX>;
+  constexpr int LT = G::LT, NGX = G::NGX, NT = CS * LT;
+  static_assert(CS >= 2 && CS <= 16, "slot tables hold 16 ranks");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *S = reinterpret_cast<double2 *>(smem_raw);
-  double *wscrA = reinterpret_cast<double *>(S + OFF_END);
+  double *wscrA = reinterpret_cast<double *>(S + G::OFF_END);
   double *wscrB = wscrA + NWARPS;
   double *slotA = wscrB + NWARPS;
   double *slotB = slotA + 16;
@@ -198,34 +217,27 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   const uint32_t xaddr = tmem_base_s + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (uint32_t)TMEM_WORDS;
 
   const uint32_t rank = cluster_ctarank();
-  const int ct = (int)rank / CX, cx = (int)rank % CX;
-  Nbr nb;
-  nb.tm = (uint32_t)(((ct + CT - 1) % CT) * CX + cx);
-  nb.tp = (uint32_t)(((ct + 1) % CT) * CX + cx);
-  nb.xm = (uint32_t)(ct * CX + (cx + CX - 1) % CX);
-  nb.xp = (uint32_t)(ct * CX + (cx + 1) % CX);
+  const uint32_t rank_m = (rank + CS - 1) % CS, rank_p = (rank + 1) % CS;
   const int c = c_first + (int)(blockIdx.x / CS);
   const int tid = threadIdx.x;
-  const int g = tid % NG;
-  const int t0 = (tid / NG) * TT;
+  const int g = tid % NGX;
+  const int t0 = (tid / NGX) * TT;
+  const bool top = t0 == 0, bot = t0 + TT == LT;   // warp-uniform
   const double m = mass[c];
   const double e_p = emu[c], e_m = emmu[c];
-  const int tg0 = ct * LT, xg0 = cx * LX;   // global origin of the sub-lattice
+  const int tg0 = (int)rank * LT;   // first global row of the slab
 
-  // links of the sub-lattice and their halos: device layout [site][chain] -> shared memory
+  // links of the slab and the W0 halo row: device layout [site][chain] -> shared memory
   for (int k = tid; k < VL; k += NTHREADS) {
-    const int t = k / LX, x = k % LX;
-    const size_t gs = (size_t)(tg0 + t) * NX + xg0 + x;
-    const int ks = t * LX + (x % TX) * NG + x / TX;
-    S[OFF_W0 + ks] = W0g[gs * C + c];
-    S[OFF_W1 + ks] = W1g[gs * C + c];
+    const int t = k / NX, x = k % NX;
+    const size_t gs = (size_t)(tg0 + t) * NX + x;
+    const int ks = t * NX + (x % TX) * NGX + x / TX;
+    S[G::OFF_W0 + ks] = W0g[gs * C + c];
+    S[G::OFF_W1 + ks] = W1g[gs * C + c];
   }
-  if (tid < LX) {
-    const int x = tid, tgm = (tg0 + NT - 1) % NT;
-    S[OFF_W0H + (x % TX) * NG + x / TX] = W0g[((size_t)tgm * NX + xg0 + x) * C + c];
-  } else if (tid < LX + LT) {
-    const int t = tid - LX, xgm = (xg0 + NX - 1) % NX;
-    S[OFF_W1H + t] = W1g[((size_t)(tg0 + t) * NX + xgm) * C + c];
+  for (int x = tid; x < NX; x += NTHREADS) {
+    const int tgm = (tg0 + NT - 1) % NT;
+    S[G::OFF_W0H + (x % TX) * NGX + x / TX] = W0g[((size_t)tgm * NX + x) * C + c];
   }
   double2 r[TT][TX], p[TT][TX];
   double rr = 0.0;
@@ -233,18 +245,18 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   for (int i = 0; i < TT; i++)
 #pragma unroll
     for (int j = 0; j < TX; j++) {
-      const size_t gs = (size_t)(tg0 + t0 + i) * NX + xg0 + g * TX + j;
+      const size_t gs = (size_t)(tg0 + t0 + i) * NX + g * TX + j;
       r[i][j] = bsrc[gs * C + c];
       p[i][j] = r[i][j];
       rr = fma(r[i][j].x, r[i][j].x, rr);
       rr = fma(r[i][j].y, r[i][j].y, rr);
-      S[OFF_F + (t0 + i) * LX + j * NG + g] = p[i][j];
+      S[G::OFF_F + (t0 + i) * NX + j * NGX + g] = p[i][j];
     }
   // every CTA of the cluster is running before anyone stores into a peer's shared memory
   cluster_arrive();
   cluster_wait();
-  push_halos(p, OFF_HP, smem_base, nb, t0, g);
-  cluster_sum_post<CS>(rr, wscrA, slotA_addr, rank);   // hmc.c:354-356
+  push_rows<NX>(p, G::OFF_HP, smem_base, rank_m, rank_p, top, bot, g);
+  cluster_sum_post<CS>(rr, wscrA, slotA_addr, rank);   // hmc.c:354-356; its CTA barrier publishes F and the links
   cluster_arrive();
   cluster_wait();
   rr = cluster_total<CS>(slotA);
@@ -255,9 +267,13 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   if (rr_old < s.accuracy) {  // hmc.c:359-361
     status = TB_CG_ZERO_SOURCE;
   } else {
+    cluster_arrive();   // pairs with the wait inside the first iteration (p and its halos are already published)
     for (int k = 1; k < s.max_iter; k++) {  // hmc.c:364
       double2 mp[TT][TX], q[TT][TX];
-      tile_apply_cl<false, HAS_MU>(p, mp, S, OFF_HP, t0, g, m, e_p, e_m);   // Mp = M p, hmc.c:366
+      // Mp = M p (hmc.c:366): own rows first, then the hop from the neighbours' rows
+      tile_apply_own<NX, false, HAS_MU>(p, mp, S, t0, g, top, bot, m, e_p, e_m);
+      cluster_wait();   // p halos of this iteration are in place
+      tile_fixup<NX, false, HAS_MU>(mp, S, G::OFF_HP, t0, g, top, bot, e_p, e_m);
       double pq = 0.0;
       if (DAG) {   // <p, M^dagger M p> = |M p|^2
 #pragma unroll
@@ -272,15 +288,18 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
 #pragma unroll
       for (int i = 0; i < TT; i++)
 #pragma unroll
-        for (int j = 0; j < TX; j++) S[OFF_F + (t0 + i) * LX + j * NG + g] = mp[i][j];
-      push_halos(mp, OFF_HM, smem_base, nb, t0, g);
-      if (DAG) cluster_sum_post<CS>(pq, wscrB, slotB_addr, rank);
-      cluster_arrive();   // publishes Mp, its halos and the |Mp|^2 partials
-      cluster_wait();
-      if (DAG) pq = cluster_total<CS>(slotB);
+        for (int j = 0; j < TX; j++) S[G::OFF_F + (t0 + i) * NX + j * NGX + g] = mp[i][j];
+      push_rows<NX>(mp, G::OFF_HM, smem_base, rank_m, rank_p, top, bot, g);
+      if (DAG) cluster_sum_post<CS>(pq, wscrB, slotB_addr, rank);   // its CTA barrier publishes Mp inside the CTA
+      else __syncthreads();
+      cluster_arrive();   // Mp halos and |Mp|^2 partials are on their way
       // q = M~ Mp, hmc.c:367
-      tile_apply_cl<DAG, HAS_MU>(mp, q, S, OFF_HM, t0, g, m, DAG ? e_m : e_p, DAG ? e_p : e_m);
-      if (!DAG) {
+      tile_apply_own<NX, DAG, HAS_MU>(mp, q, S, t0, g, top, bot, m, DAG ? e_m : e_p, DAG ? e_p : e_m);
+      cluster_wait();
+      tile_fixup<NX, DAG, HAS_MU>(q, S, G::OFF_HM, t0, g, top, bot, DAG ? e_m : e_p, DAG ? e_p : e_m);
+      if (DAG) {
+        pq = cluster_total<CS>(slotB);
+      } else {
 #pragma unroll
         for (int i = 0; i < TT; i++)
 #pragma unroll
@@ -304,7 +323,7 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
           rr = fma(r[i][j].x, r[i][j].x, rr);          // hmc.c:377-379
           rr = fma(r[i][j].y, r[i][j].y, rr);
         }
-      cluster_sum_post<CS>(rr, wscrA, slotA_addr, rank);
+      cluster_sum_post<CS>(rr, wscrA, slotA_addr, rank);   // its CTA barrier: every local read of Mp has finished
       cluster_arrive();
       // x += a p (hmc.c:372-373) in tensor memory while the ||r||^2 partials cross the cluster
 #pragma unroll
@@ -329,7 +348,7 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
       cluster_wait();
       rr = cluster_total<CS>(slotA);
       iters = k;
-      // identical rr on every CTA => the whole cluster leaves the loop together
+      // identical rr on every CTA => the whole cluster leaves the loop together, no barrier half-open
       if (rr < s.accuracy) { status = TB_CG_CONVERGED; break; }                                        // hmc.c:381
       if (!(rr == rr) || rr / rr_init > TB_DIVERGENCE_RATIO) { status = TB_CG_DIVERGED; break; }      // hmc.c:383
       const double be = rr / rr_old;   // hmc.c:390
@@ -339,12 +358,13 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
         for (int j = 0; j < TX; j++) {
           p[i][j].x = fma(be, p[i][j].x, r[i][j].x);   // hmc.c:391-392
           p[i][j].y = fma(be, p[i][j].y, r[i][j].y);
-          S[OFF_F + (t0 + i) * LX + j * NG + g] = p[i][j];   // local reads of Mp ended before the ||r||^2 barrier
+          S[G::OFF_F + (t0 + i) * NX + j * NGX + g] = p[i][j];
         }
-      push_halos(p, OFF_HP, smem_base, nb, t0, g);
+      push_rows<NX>(p, G::OFF_HP, smem_base, rank_m, rank_p, top, bot, g);
       rr_old = rr;
-      cluster_arrive();   // publishes p and its halos
-      cluster_wait();
+      __syncthreads();    // p is published inside the CTA
+      cluster_arrive();   // and its halos are on their way; the wait is after the own-rows stencil
+      if (k + 1 >= s.max_iter) cluster_wait();   // loop ends here: close the barrier
     }
   }
 #pragma unroll
@@ -354,7 +374,7 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int f = ch * 4 + u, i = f / TX, j = f % TX;
-      const size_t gs = (size_t)(tg0 + t0 + i) * NX + xg0 + g * TX + j;
+      const size_t gs = (size_t)(tg0 + t0 + i) * NX + g * TX + j;
       xout[gs * C + c] = (iters > 0) ? make_double2(__hiloint2double((int)v[4 * u + 1], (int)v[4 * u]),
                                                      __hiloint2double((int)v[4 * u + 3], (int)v[4 * u + 2]))
                                       : make_double2(0.0, 0.0);
@@ -372,22 +392,21 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   }
 }
 
-template <int CT, int CX>
+template <int NX, int CS>
 struct ClusterLaunch {
   using Kern = void (*)(const double2 *, double2 *, const double2 *, const double2 *, const double *, const double *,
                         const double *, const TbCgState, const int, const int);
   static Kern pick(bool dag, bool has_mu) {
-    if (dag) return has_mu ? cluster_cg_kernel<CT, CX, true, true> : cluster_cg_kernel<CT, CX, true, false>;
-    return has_mu ? cluster_cg_kernel<CT, CX, false, true> : cluster_cg_kernel<CT, CX, false, false>;
+    if (dag) return has_mu ? cluster_cg_kernel<NX, CS, true, true> : cluster_cg_kernel<NX, CS, true, false>;
+    return has_mu ? cluster_cg_kernel<NX, CS, false, true> : cluster_cg_kernel<NX, CS, false, false>;
   }
   static int config(Kern kern, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, int nclusters, cudaStream_t st) {
-    constexpr int CS = CT * CX;
-    TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CL_SMEM));
+    TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Slab<NX>::SMEM));
     if (CS > 8) TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     memset(cfg, 0, sizeof(*cfg));
     cfg->gridDim = dim3((unsigned)(nclusters * CS), 1, 1);
     cfg->blockDim = dim3(NTHREADS, 1, 1);
-    cfg->dynamicSmemBytes = CL_SMEM;
+    cfg->dynamicSmemBytes = Slab<NX>::SMEM;
     cfg->stream = st;
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CS;
@@ -423,8 +442,8 @@ struct ClusterLaunch {
   }
 };
 
-// lattice -> cluster shape (CT x CX sub-lattices of 64 x 64)
-#define TB_CLUSTER_SHAPES(X) X(1, 2) X(2, 1) X(2, 2) X(2, 4) X(4, 2) X(4, 4)
+// (row length NX, CTAs per cluster): lattices of CS * 4096/NX rows by NX sites
+#define TB_CLUSTER_SHAPES(X) X(64, 2) X(64, 4) X(128, 2) X(128, 4) X(128, 8) X(256, 4) X(256, 8) X(256, 16)
 
 }  // namespace
 
@@ -433,10 +452,10 @@ struct ClusterLaunch {
 int tb_cluster_capacity(tb_ctx *ctx) {
   if (ctx->cluster_capacity >= 0) return ctx->cluster_capacity;
   int cap = 0;
-  if (ctx->nranks == 1 && ctx->msite == nullptr && ctx->nt % LT == 0 && ctx->nx % LX == 0) {
-    const int ctn = ctx->nt / LT, cxn = ctx->nx / LX;
-#define X(CT_, CX_) \
-  if (ctn == CT_ && cxn == CX_) cap = ClusterLaunch<CT_, CX_>::max_active(tb_conj_is_dagger(ctx), ctx->has_mu);
+  if (ctx->nranks == 1 && ctx->nx >= 64 && VL % ctx->nx == 0 && ctx->nt % (VL / ctx->nx) == 0) {
+    const int cs = ctx->nt / (VL / ctx->nx);
+#define X(NX_, CS_) \
+  if (ctx->nx == NX_ && cs == CS_) cap = ClusterLaunch<NX_, CS_>::max_active(tb_conj_is_dagger(ctx), ctx->has_mu);
     TB_CLUSTER_SHAPES(X)
 #undef X
   }
@@ -451,16 +470,11 @@ int tb_run_cg_cluster_slice(tb_ctx *ctx, const double2 *b, double2 *x, int c0, i
     tb_set_error("tb_run_cg_cluster: in-place solve is not supported");
     return TB_EINVAL;
   }
-  const int ctn = ctx->nt / LT, cxn = ctx->nx / LX;
-#define X(CT_, CX_) \
-  if (ctn == CT_ && cxn == CX_) return ClusterLaunch<CT_, CX_>::launch(ctx, b, x, c0, n, st);
+  const int cs = ctx->nx >= 64 && VL % ctx->nx == 0 ? ctx->nt / (VL / ctx->nx) : 0;
+#define X(NX_, CS_) \
+  if (ctx->nx == NX_ && cs == CS_) return ClusterLaunch<NX_, CS_>::launch(ctx, b, x, c0, n, st);
   TB_CLUSTER_SHAPES(X)
 #undef X
   tb_set_error("cluster solver: unsupported lattice %dx%d", ctx->nt, ctx->nx);
   return TB_EINVAL;
-}
-
-int tb_run_cg_cluster(tb_ctx *ctx, const double2 *b, double2 *x);
-int tb_run_cg_cluster(tb_ctx *ctx, const double2 *b, double2 *x) {
-  return tb_run_cg_cluster_slice(ctx, b, x, 0, ctx->C, ctx->stream);
 }

@@ -29,6 +29,7 @@ SIGNATURES = {
     "tb_set_params": (_i, [_vp, _dp, _dp, _i]),
     "tb_set_cg": (_i, [_vp, _d, _i]),
     "tb_set_tuning": (_i, [_vp, _i, _i, _i]),
+    "tb_solver_info": (_i, [_vp, _ip, _ip]),
     "tb_set_gauge": (_i, [_vp, _vp]),
     "tb_set_occupancy": (_i, [_vp, _vp]),
     "tb_apply": (_i, [_vp, _i, _vp, _vp]),
