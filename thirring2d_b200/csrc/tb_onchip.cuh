@@ -47,3 +47,154 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
 
+
+// ---- links in tensor memory ------------------------------------------------------------------------------------
+// The link fields are read-only during a solve and every thread needs exactly the links of its own tile plus the
+// tile's backward halo (W0 of the row above, W1 of the column to the left): 42 double2 for an 8 x 2 tile.  Kept as
+// thread-private TMEM columns they cost no shared-memory bandwidth (the LSU data pipe is what bounds the on-chip
+// kernels).  Asynchronous variants: issue, compute on something else, then tmem_wait_ld on the destination
+// registers (the "+r" operands make every later use depend on the wait).
+__device__ __forceinline__ void tmem_ld16_async(uint32_t (&v)[20], uint32_t taddr) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"
+               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld4_async(uint32_t (&v)[20], uint32_t taddr) {   // fills v[16..19]
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8_async(uint32_t (&v)[8], uint32_t taddr) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[20]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[20], uint32_t (&h)[8]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(h[0]), "+r"(h[1]), "+r"(h[2]), "+r"(h[3]),
+                 "+r"(h[4]), "+r"(h[5]), "+r"(h[6]), "+r"(h[7])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_d2(uint32_t taddr, const double2 v) {
+  tmem_st4(taddr, (uint32_t)__double2loint(v.x), (uint32_t)__double2hiint(v.x), (uint32_t)__double2loint(v.y),
+           (uint32_t)__double2hiint(v.y));
+}
+__device__ __forceinline__ double2 d2_from_words(const uint32_t *w) {
+  return make_double2(__hiloint2double((int)w[1], (int)w[0]), __hiloint2double((int)w[3], (int)w[2]));
+}
+
+// Per-thread TMEM map of the 8 x 2 tile (32-bit columns): x, then the links.
+//   [0, 64)      x(i, j)                       4 words per site, site f = i*2 + j
+//   [64, 192)    row i: W0(i,0) W0(i,1) W1(i,0) W1(i,1)      16 words per row
+//   [192, 224)   W1(i, x0-1)                   4 words per row
+//   [224, 232)   W0(t0-1, x0+j)                4 words per column
+// 240 columns per thread (16-aligned); the two warps of a lane quarter stack along the columns: 480 of 512.
+constexpr int TM_X = 0, TM_ROW = 64, TM_W1M = 192, TM_W0M = 224, TM_SPAN = 240, TM_COLS_WT = 512;
+
+// out = m f +- hops on the thread's 8 x 2 tile with the links streamed from tensor memory (software-pipelined one
+// row ahead).  F: the field in shared memory (row-major NX, sub-plane layout), only the tile's halo is read.
+// Same arithmetic and hop order as tile_apply.  CLUSTER: the lattice continues in other CTAs, rows are not wrapped
+// and the hop from row t0-1 (top) / t0+8 (bot) is skipped; the caller adds it later from the halo rows.
+// Every finished site is handed to epi(i, j, value) (i, j compile-time after unrolling): the caller stores it,
+// publishes it or folds it into the CG update at once, so no output tile has to stay live in registers.
+template <int NT, int NX, bool DAG, bool HAS_MU, bool CLUSTER, typename Epi>
+__device__ __forceinline__ void tile_apply_wt(const double2 (&f)[8][2], const double2 *F, uint32_t wb, int t0, int g,
+                                              bool top, bool bot, double m, double af, double ab, Epi epi) {
+  constexpr int TX = 2, TT = 8;
+  constexpr int SF = DAG ? -1 : 1;
+  constexpr int SB = -SF;
+  constexpr int NG = NX / TX;
+  const int gl = (g + NG - 1) % NG, gr = (g + 1) % NG;
+  const int tm = CLUSTER ? t0 - 1 : (t0 + NT - 1) % NT, te = CLUSTER ? t0 + TT : (t0 + TT) % NT;
+  const double2 zero = make_double2(0.0, 0.0);
+  uint32_t h[8], buf[2][20];
+  tmem_ld8_async(h, wb + TM_W0M);
+  tmem_ld16_async(buf[0], wb + TM_ROW);
+  tmem_ld4_async(buf[0], wb + TM_W1M);
+  // halo of the field while the links are in flight
+  double2 fdn[TX], fup[TX];
+#pragma unroll
+  for (int j = 0; j < TX; j++) {
+    fdn[j] = (CLUSTER && top) ? zero : F[tm * NX + j * NG + g];
+    fup[j] = (CLUSTER && bot) ? zero : F[te * NX + j * NG + g];
+  }
+  tmem_wait_ld(buf[0], h);
+  double2 w0m[TX];
+#pragma unroll
+  for (int j = 0; j < TX; j++) w0m[j] = d2_from_words(&h[4 * j]);
+#pragma unroll
+  for (int i = 0; i < TT; i++) {
+    uint32_t(&cur)[20] = buf[i & 1];
+    if (i + 1 < TT) {
+      tmem_ld16_async(buf[(i + 1) & 1], wb + TM_ROW + 16 * (i + 1));
+      tmem_ld4_async(buf[(i + 1) & 1], wb + TM_W1M + 4 * (i + 1));
+    }
+    const int row = (t0 + i) * NX;
+    const double2 fL = F[row + (TX - 1) * NG + gl];    // f(t, x0-1)
+    const double2 fR = F[row + gr];                    // f(t, x0+TX)
+    double2 w1m = d2_from_words(&cur[16]);
+#pragma unroll
+    for (int j = 0; j < TX; j++) {
+      const double2 w0c = d2_from_words(&cur[4 * j]);
+      const double2 w1c = d2_from_words(&cur[8 + 4 * j]);
+      const double2 up = (i == TT - 1) ? fup[j] : f[(i + 1) % TT][j];
+      const double2 dn = (i == 0) ? fdn[j] : f[(i + TT - 1) % TT][j];
+      const double2 rt = (j == TX - 1) ? fR : f[i][(j + 1) % TX];
+      const double2 lf = (j == 0) ? fL : f[i][(j + TX - 1) % TX];
+      double2 o = make_double2(m * f[i][j].x, m * f[i][j].y);   // hmc.c:137-180
+      if (HAS_MU) {
+        hop_acc<SF>(o, make_double2(w0c.x * af, w0c.y * af), up);
+        hopc_acc<SB>(o, make_double2(w0m[j].x * ab, w0m[j].y * ab), dn);
+      } else {
+        hop_acc<SF>(o, w0c, up);
+        hopc_acc<SB>(o, w0m[j], dn);
+      }
+      hop_acc<SF>(o, w1c, rt);
+      hopc_acc<SB>(o, w1m, lf);
+      epi(i, j, o);
+      w0m[j] = w0c;
+      w1m = w1c;
+    }
+    if (i + 1 < TT) tmem_wait_ld(buf[(i + 1) & 1]);
+  }
+}
+
+// x += a p on the thread's tile in tensor memory (hmc.c:372-373); first = x is still the zero start vector
+__device__ __forceinline__ void tmem_x_axpy(uint32_t xaddr, const double2 (&p)[8][2], double a, bool first) {
+#pragma unroll
+  for (int ch = 0; ch < 4; ch++) {
+    uint32_t v[16];
+    if (!first) tmem_ld16(v, xaddr + ch * 16);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int f = ch * 4 + u, i = f / 2, j = f % 2;
+      double xr = first ? 0.0 : __hiloint2double((int)v[4 * u + 1], (int)v[4 * u]);   // hmc.c:351: x0 = 0
+      double xi = first ? 0.0 : __hiloint2double((int)v[4 * u + 3], (int)v[4 * u + 2]);
+      xr += a * p[i][j].x;
+      xi += a * p[i][j].y;
+      v[4 * u] = (uint32_t)__double2loint(xr);
+      v[4 * u + 1] = (uint32_t)__double2hiint(xr);
+      v[4 * u + 2] = (uint32_t)__double2loint(xi);
+      v[4 * u + 3] = (uint32_t)__double2hiint(xi);
+    }
+    tmem_st16(xaddr + ch * 16, v);
+  }
+  tmem_wait_st();
+}

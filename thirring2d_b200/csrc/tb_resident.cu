@@ -37,6 +37,18 @@ __device__ __forceinline__ double block_sum(double v, double *scratch) {
   return s;
 }
 
+// Same, with the warp partials added as a balanced tree (three dependent additions instead of NWARPS after the
+// barrier); NWARPS must be 8.  A different but equally fixed summation order.
+__device__ __forceinline__ double block_sum8(double v, double *scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  const double2 *s2 = reinterpret_cast<const double2 *>(scratch);
+  const double2 a = s2[0], b = s2[1], c = s2[2], d = s2[3];
+  return ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d.x + d.y));
+}
+
 // Shared-memory site index: the TX x-sites of a thread's tile live in TX separate sub-planes of a row, so
 // that for a fixed tile column j consecutive threads (x-groups) touch consecutive double2 (conflict-free
 // LDS.128 / STS.128 whatever TX is).
@@ -317,6 +329,196 @@ resident_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
   }
 }
 
+// ---- links in tensor memory (64^2) -------------------------------------------------------------------------------
+// The same solve with the two link fields kept as thread-private TMEM columns next to x (tb_onchip.cuh): the
+// stencil's shared-memory traffic drops from 62 to 20 B per site and apply (only the tile's field halo), and the
+// 128 KB of shared memory this frees hold p and Mp in SEPARATE exchange buffers, which removes the write-after-read
+// barrier: three CTA barriers per CG iteration instead of four.  8 x 2 sites per thread, 256 threads.
+template <int NT, int NX>
+struct ResidentWtCfg {
+  static constexpr int V = NT * NX, TX = 2, TT = 8;
+  static constexpr int NTHREADS = (NT / TT) * (NX / TX);
+  static constexpr int NWARPS = NTHREADS / 32;
+  static constexpr size_t SMEM = (size_t)V * 32 + 64 * sizeof(double);
+  static_assert(NWARPS == 8, "two warps per TMEM lane quarter; block_sum8");
+};
+
+template <int NT, int NX, bool DAG, bool HAS_MU>
+__global__ void __launch_bounds__(ResidentWtCfg<NT, NX>::NTHREADS, 1)
+resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, const double2 *__restrict__ W0g,
+                   const double2 *__restrict__ W1g, const double *__restrict__ mass, const double *__restrict__ emu,
+                   const double *__restrict__ emmu, const TbCgState s, const int C, const int c_first) {
+  using Cfg = ResidentWtCfg<NT, NX>;
+  constexpr int V = Cfg::V, NWARPS = Cfg::NWARPS, TX = 2, TT = 8, NG = NX / TX;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *Fp = reinterpret_cast<double2 *>(smem_raw);   // p, as the stencil neighbours read it
+  double2 *Fm = Fp + V;                                  // Mp
+  double *scrA = reinterpret_cast<double *>(Fm + V);
+  double *scrB = scrA + 32;
+  __shared__ uint32_t tmem_base_s;
+  if (threadIdx.x < 32) {
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst), "r"(TM_COLS_WT) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t xaddr = tmem_base_s + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (uint32_t)TM_SPAN;
+
+  const int c = c_first + blockIdx.x;
+  const int tid = threadIdx.x;
+  const int g = tid % NG;
+  const int t0 = (tid / NG) * TT;
+  const double m = mass[c];
+  const double e_p = emu[c], e_m = emmu[c];
+
+  // links of the tile and of its backward halo: device layout [site][chain] -> tensor memory
+  {
+    const int xm = (g * TX + NX - 1) % NX, tmr = (t0 + NT - 1) % NT;
+#pragma unroll
+    for (int i = 0; i < TT; i++) {
+      const size_t row = (size_t)(t0 + i) * NX;
+#pragma unroll
+      for (int j = 0; j < TX; j++) {
+        tmem_st_d2(xaddr + TM_ROW + 16 * i + 4 * j, W0g[(row + g * TX + j) * C + c]);
+        tmem_st_d2(xaddr + TM_ROW + 16 * i + 8 + 4 * j, W1g[(row + g * TX + j) * C + c]);
+      }
+      tmem_st_d2(xaddr + TM_W1M + 4 * i, W1g[(row + xm) * C + c]);
+    }
+#pragma unroll
+    for (int j = 0; j < TX; j++) tmem_st_d2(xaddr + TM_W0M + 4 * j, W0g[((size_t)tmr * NX + g * TX + j) * C + c]);
+    tmem_wait_st();
+  }
+  double2 r[TT][TX], p[TT][TX];
+  double rr = 0.0;
+#pragma unroll
+  for (int i = 0; i < TT; i++)
+#pragma unroll
+    for (int j = 0; j < TX; j++) {
+      const int k = (t0 + i) * NX + g * TX + j;
+      r[i][j] = bsrc[(size_t)k * C + c];
+      p[i][j] = r[i][j];
+      rr = fma(r[i][j].x, r[i][j].x, rr);
+      rr = fma(r[i][j].y, r[i][j].y, rr);
+      Fp[(t0 + i) * NX + j * NG + g] = p[i][j];
+    }
+  rr = block_sum8(rr, scrA);   // hmc.c:354-356; its barrier publishes p
+  const double rr_init = rr;
+  double rr_old = rr;
+  int status = TB_CG_MAXITER, iters = 0;
+
+  if (rr_old < s.accuracy) {  // hmc.c:359-361
+    status = TB_CG_ZERO_SOURCE;
+  } else {
+    for (int k = 1; k < s.max_iter; k++) {  // hmc.c:364
+      // Mp = M p (hmc.c:366): every site is published to Fm as soon as it is finished (the last readers of Fm
+      // passed the ||r||^2 barrier), and <p, M^dagger M p> = |M p|^2 is accumulated on the way
+      double2 mp[TT][TX];
+      double pq = 0.0;
+      tile_apply_wt<NT, NX, false, HAS_MU, false>(p, Fp, xaddr, t0, g, false, false, m, e_p, e_m,
+                                                  [&](int i, int j, const double2 o) {
+                                                    mp[i][j] = o;
+                                                    Fm[(t0 + i) * NX + j * NG + g] = o;
+                                                    if (DAG) {
+                                                      pq = fma(o.x, o.x, pq);
+                                                      pq = fma(o.y, o.y, pq);
+                                                    }
+                                                  });
+      if (DAG) pq = block_sum8(pq, scrB);   // its barrier also publishes Mp
+      else __syncthreads();
+      rr = 0.0;
+      double a;
+      if (DAG) {
+        // alpha is known before q = M^dagger Mp exists (hmc.c:367,371): q is consumed site by site,
+        // r -= alpha q and ||r||^2 (hmc.c:374-379), and never stored
+        a = rr_old / pq;
+        tile_apply_wt<NT, NX, true, HAS_MU, false>(mp, Fm, xaddr, t0, g, false, false, m, e_m, e_p,
+                                                   [&](int i, int j, const double2 o) {
+                                                     r[i][j].x = fma(-a, o.x, r[i][j].x);
+                                                     r[i][j].y = fma(-a, o.y, r[i][j].y);
+                                                     rr = fma(r[i][j].x, r[i][j].x, rr);
+                                                     rr = fma(r[i][j].y, r[i][j].y, rr);
+                                                   });
+      } else {
+        double2 q[TT][TX];
+        tile_apply_wt<NT, NX, false, HAS_MU, false>(mp, Fm, xaddr, t0, g, false, false, m, e_p, e_m,
+                                                    [&](int i, int j, const double2 o) {
+                                                      q[i][j] = o;
+                                                      pq = fma(p[i][j].x, o.x, pq);   // hmc.c:368-370
+                                                      pq = fma(p[i][j].y, o.y, pq);
+                                                    });
+        pq = block_sum8(pq, scrB);
+        a = rr_old / pq;   // hmc.c:371
+#pragma unroll
+        for (int i = 0; i < TT; i++)
+#pragma unroll
+          for (int j = 0; j < TX; j++) {
+            r[i][j].x = fma(-a, q[i][j].x, r[i][j].x);   // hmc.c:374-375
+            r[i][j].y = fma(-a, q[i][j].y, r[i][j].y);
+            rr = fma(r[i][j].x, r[i][j].x, rr);          // hmc.c:377-379
+            rr = fma(r[i][j].y, r[i][j].y, rr);
+          }
+      }
+      rr = block_sum8(rr, scrA);
+      tmem_x_axpy(xaddr + TM_X, p, a, k == 1);          // hmc.c:372-373
+      iters = k;
+      if (rr < s.accuracy) { status = TB_CG_CONVERGED; break; }                                        // hmc.c:381
+      if (!(rr == rr) || rr / rr_init > TB_DIVERGENCE_RATIO) { status = TB_CG_DIVERGED; break; }      // hmc.c:383
+      const double be = rr / rr_old;   // hmc.c:390
+#pragma unroll
+      for (int i = 0; i < TT; i++)
+#pragma unroll
+        for (int j = 0; j < TX; j++) {
+          p[i][j].x = fma(be, p[i][j].x, r[i][j].x);   // hmc.c:391-392
+          p[i][j].y = fma(be, p[i][j].y, r[i][j].y);
+          Fp[(t0 + i) * NX + j * NG + g] = p[i][j];    // the last readers of Fp passed the |Mp|^2 barrier
+        }
+      rr_old = rr;
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int ch = 0; ch < 4; ch++) {
+    uint32_t v[16];
+    if (iters > 0) tmem_ld16(v, xaddr + TM_X + ch * 16);
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int f = ch * 4 + u, i = f / TX, j = f % TX;
+      const int kk = (t0 + i) * NX + g * TX + j;
+      xout[(size_t)kk * C + c] = (iters > 0) ? make_double2(__hiloint2double((int)v[4 * u + 1], (int)v[4 * u]),
+                                                             __hiloint2double((int)v[4 * u + 3], (int)v[4 * u + 2]))
+                                              : make_double2(0.0, 0.0);
+    }
+  }
+  __syncthreads();   // every warp has read its columns
+  if (threadIdx.x < 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base_s), "r"(TM_COLS_WT) : "memory");
+  if (tid == 0) {
+    s.status[c] = status;
+    s.iters[c] = iters;
+    s.rr[c] = rr;
+    s.rr_init[c] = rr_init;
+    s.active[c] = 0;
+  }
+}
+
+template <int NT, int NX>
+int launch_resident_wt(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st) {
+  using Cfg = ResidentWtCfg<NT, NX>;
+  const bool dag = tb_conj_is_dagger(ctx);
+  auto kern = resident_wt_kernel<NT, NX, false, false>;
+  if (dag) kern = ctx->has_mu ? resident_wt_kernel<NT, NX, true, true> : resident_wt_kernel<NT, NX, true, false>;
+  else if (ctx->has_mu) kern = resident_wt_kernel<NT, NX, false, true>;
+  TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  kern<<<n, Cfg::NTHREADS, Cfg::SMEM, st>>>(b, x, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu, ctx->cg, ctx->C,
+                                            c0);
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
 template <int NT, int NX, int TX, int TT>
 int launch_resident(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st) {
   using Cfg = ResidentCfg<NT, NX, TX, TT>;
@@ -344,7 +546,8 @@ bool tb_resident_supported(const tb_ctx *ctx) {
 }
 
 // One kernel launch per (sub-)batch of chains [c0, c0+n).  The tile shape per thread is a tuning knob
-// (tb_set_tuning rows_per_thread): 0 = default (2x8 sites; 2x4 for 16^2), 44 = 4x4, 18 = 1x8, 28 = 2x8, 24 = 2x4.
+// (tb_set_tuning rows_per_thread): 0 = default (64^2: 2x8 sites with the links in tensor memory; 32^2: 2x8; 16^2: 2x4),
+// 44 = 4x4, 18 = 1x8, 28 = 2x8 with the links in shared memory, 24 = 2x4.
 int tb_run_cg_resident_slice(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st) {
   if (b == x) {
     tb_set_error("tb_run_cg_resident: in-place solve is not supported");
@@ -363,7 +566,8 @@ int tb_run_cg_resident_slice(tb_ctx *ctx, const double2 *b, double2 *x, int c0, 
       if (shape == 18) return launch_resident<64, 64, 1, 8>(ctx, b, x, c0, n, st);
       if (shape == 44) return launch_resident<64, 64, 4, 4>(ctx, b, x, c0, n, st);
       if (shape == 24) return launch_resident<64, 64, 2, 4>(ctx, b, x, c0, n, st);
-      return launch_resident<64, 64, 2, 8>(ctx, b, x, c0, n, st);
+      if (shape == 28 || !ctx->resident_x_tmem) return launch_resident<64, 64, 2, 8>(ctx, b, x, c0, n, st);
+      return launch_resident_wt<64, 64>(ctx, b, x, c0, n, st);   // default: links and x in tensor memory
     default: tb_set_error("resident solver: unsupported lattice %dx%d", ctx->nt, ctx->nx); return TB_EINVAL;
   }
 }
