@@ -1,15 +1,14 @@
 // tb_cluster.cu — on-chip resident batched CG for lattices that do not fit one SM: one THREAD-BLOCK CLUSTER per
 // Markov chain (128^2 = 4 CTAs, 256^2 = 16 CTAs, and the rectangles in between), sm_100a, FP64.
 //
-// Same algorithm and per-thread arithmetic as tb_resident.cu (fmdm_invert_cg, hmc.c:341-404), with the lattice
-// cut into t-slabs of 4096 sites (LT = 4096/NX rows of NX sites), one per CTA of the cluster.  The CG state of a
-// slab never leaves its SM:
+// Same algorithm and per-thread arithmetic as the 64^2 kernel of tb_resident.cu (fmdm_invert_cg, hmc.c:341-404),
+// with the lattice cut into t-slabs of 4096 sites (LT = 4096/NX rows of NX sites), one per CTA of the cluster.
+// The CG state of a slab never leaves its SM:
 //
-//   registers      r, p (persistent), Mp, q (transient): 8 x 2 sites per thread, 256 threads
-//   shared memory  exchange field F (p, then Mp), links W0, W1 of the slab              48 B/site = 192 KB
+//   registers      r, p (persistent), Mp (transient): 8 x 2 sites per thread, 256 threads
+//   shared memory  exchange fields Fp (p) and Fm (Mp) of the slab                       32 B/site = 128 KB
 //                  halo rows t = -1 and t = LT of p and of Mp, pushed by the neighbours  4 x NX x 16 B
-//                  halo row of W0 (constant during the solve)                            NX x 16 B
-//   tensor memory  x, thread-private columns (tcgen05.ld/st 32x32b)
+//   tensor memory  x and the links W0, W1 of the thread's tile, thread-private columns (tcgen05.ld/st 32x32b)
 //
 // Distributed shared memory carries everything that crosses a CTA boundary:
 //   * halos are PUSHED: the warps that produce the first / last row of p or Mp also store it into the neighbour
@@ -17,9 +16,10 @@
 //   * both CG reductions are all-to-all over the cluster: every CTA stores its block sum into every CTA's slot
 //     table, and all CTAs add the slots in rank order => bitwise identical alpha, beta and stopping decisions on
 //     every CTA with no further communication (and run-to-run deterministic);
-//   * barrier.cluster is split into arrive.release / wait.acquire and the latency is hidden: a stencil first does
-//     everything that needs only the CTA's own rows, waits, and then adds the one hop that comes from the halo row
-//     (first / last row of the slab); the x += alpha p update in tensor memory runs inside the ||r||^2 barrier.
+//   * barrier.cluster is split into arrive.release / wait.acquire and the latency is hidden: a stencil does the
+//     first four rows of every tile (which need only the CTA's own data, except one hop into the first row of the
+//     slab that is added afterwards), THEN waits, and finishes with the halo rows in place; the x += alpha p
+//     update in tensor memory runs inside the ||r||^2 barrier.
 // Three split cluster barriers per CG iteration.  HBM is touched once per solve.
 #include <cstdint>
 
@@ -33,24 +33,19 @@ constexpr int TX = 2, TT = 8;              // sites per thread: TT rows (t) x TX
 constexpr int VL = 4096;                   // sites per CTA
 constexpr int NTHREADS = VL / (TX * TT);   // 256
 constexpr int NWARPS = NTHREADS / 32;      // 8
-constexpr int TMEM_WORDS = TX * TT * 4;                    // 64 words of x per thread
-constexpr int TMEM_COLS = TMEM_WORDS * (NWARPS / 4);       // 128 columns
-
 // Geometry and shared-memory map (double2 units from the start of dynamic shared memory) of an NX-wide slab.
 template <int NX>
 struct Slab {
   static constexpr int LT = VL / NX;         // rows per CTA
   static constexpr int NGX = NX / TX;        // tiles per row; consecutive threads = consecutive tiles of a row
   static_assert(LT % TT == 0 && LT * NX == VL && NGX % 32 == 0, "slab shape");
-  static constexpr int OFF_F = 0, OFF_W0 = VL, OFF_W1 = 2 * VL;
-  static constexpr int OFF_HP = 3 * VL;              // halo rows of p : [dn (t = -1) | up (t = LT)], row layout
+  static constexpr int OFF_FP = 0, OFF_FM = VL;
+  static constexpr int OFF_HP = 2 * VL;              // halo rows of p : [dn (t = -1) | up (t = LT)], row layout
   static constexpr int OFF_HM = OFF_HP + 2 * NX;     // halo rows of Mp
-  static constexpr int OFF_W0H = OFF_HM + 2 * NX;    // W0(t = -1, x)
-  static constexpr int OFF_END = OFF_W0H + NX;
+  static constexpr int OFF_END = OFF_HM + 2 * NX;
   static constexpr int H_DN = 0, H_UP = NX;
   // doubles after OFF_END: warp partials A, B [NWARPS each], cluster slots A, B [16 each]
   static constexpr size_t SMEM = (size_t)OFF_END * sizeof(double2) + (2 * NWARPS + 32) * sizeof(double);
-  static_assert(SMEM <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -114,78 +109,6 @@ __device__ __forceinline__ void push_rows(const double2 (&v)[TT][TX], int hset, 
   }
 }
 
-// out = m f +- hops on the thread's tile, EXCEPT the hop from the halo row t = -1 (tiles with top) and from the
-// halo row t = LT (tiles with bot): those are added by tile_fixup once the neighbours' rows have arrived.
-// Same arithmetic and hop order as tile_apply of tb_resident.cu for every other site.
-template <int NX, bool DAG, bool HAS_MU>
-__device__ __forceinline__ void tile_apply_own(const double2 (&f)[TT][TX], double2 (&out)[TT][TX], const double2 *S,
-                                               int t0, int g, bool top, bool bot, double m, double af, double ab) {
-  using G = Slab<NX>;
-  constexpr int SF = DAG ? -1 : 1;
-  constexpr int SB = -SF;
-  constexpr int NGX = G::NGX;
-  const int gl = (g + NGX - 1) % NGX, gr = (g + 1) % NGX;
-  const double2 *F = S + G::OFF_F, *W0s = S + G::OFF_W0, *W1s = S + G::OFF_W1;
-  const double2 zero = make_double2(0.0, 0.0);
-  double2 w0m[TX];                  // W0(t-1, x0+j): slides down the tile
-#pragma unroll
-  for (int j = 0; j < TX; j++) w0m[j] = top ? zero : W0s[(t0 - 1) * NX + j * NGX + g];
-#pragma unroll
-  for (int i = 0; i < TT; i++) {
-    const int row = (t0 + i) * NX;
-    const double2 fL = F[row + (TX - 1) * NGX + gl];    // f(t, x0-1)
-    const double2 fR = F[row + gr];                     // f(t, x0+TX)
-    double2 w1m = W1s[row + (TX - 1) * NGX + gl];       // W1(t, x0-1): slides along the row
-#pragma unroll
-    for (int j = 0; j < TX; j++) {
-      const double2 w0c = W0s[row + j * NGX + g];
-      const double2 w1c = W1s[row + j * NGX + g];
-      const double2 up = (i == TT - 1) ? (bot ? zero : F[(t0 + TT) * NX + j * NGX + g]) : f[(i + 1) % TT][j];
-      const double2 dn = (i == 0) ? (top ? zero : F[(t0 - 1) * NX + j * NGX + g]) : f[(i + TT - 1) % TT][j];
-      const double2 rt = (j == TX - 1) ? fR : f[i][(j + 1) % TX];
-      const double2 lf = (j == 0) ? fL : f[i][(j + TX - 1) % TX];
-      double2 o = make_double2(m * f[i][j].x, m * f[i][j].y);   // hmc.c:137-180
-      if (HAS_MU) {
-        hop_acc<SF>(o, make_double2(w0c.x * af, w0c.y * af), up);
-        hopc_acc<SB>(o, make_double2(w0m[j].x * ab, w0m[j].y * ab), dn);
-      } else {
-        hop_acc<SF>(o, w0c, up);
-        hopc_acc<SB>(o, w0m[j], dn);
-      }
-      hop_acc<SF>(o, w1c, rt);
-      hopc_acc<SB>(o, w1m, lf);
-      out[i][j] = o;
-      w0m[j] = w0c;
-      w1m = w1c;
-    }
-  }
-}
-
-// the two hops tile_apply_own left out: -+ ab conj(W0(-1,x)) f(-1,x) into row 0, +- af W0(LT-1,x) f(LT,x) into row LT-1
-template <int NX, bool DAG, bool HAS_MU>
-__device__ __forceinline__ void tile_fixup(double2 (&out)[TT][TX], const double2 *S, int hset, int t0, int g, bool top,
-                                           bool bot, double af, double ab) {
-  using G = Slab<NX>;
-  constexpr int SF = DAG ? -1 : 1;
-  constexpr int SB = -SF;
-  if (top) {
-#pragma unroll
-    for (int j = 0; j < TX; j++) {
-      double2 w = S[G::OFF_W0H + j * G::NGX + g];
-      if (HAS_MU) w = make_double2(w.x * ab, w.y * ab);
-      hopc_acc<SB>(out[0][j], w, S[hset + G::H_DN + j * G::NGX + g]);
-    }
-  }
-  if (bot) {
-#pragma unroll
-    for (int j = 0; j < TX; j++) {
-      double2 w = S[G::OFF_W0 + (t0 + TT - 1) * NX + j * G::NGX + g];
-      if (HAS_MU) w = make_double2(w.x * af, w.y * af);
-      hop_acc<SF>(out[TT - 1][j], w, S[hset + G::H_UP + j * G::NGX + g]);
-    }
-  }
-}
-
 template <int NX, int CS, bool DAG, bool HAS_MU>
 __global__ void __launch_bounds__(NTHREADS, 1)
 cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, const double2 *__restrict__ W0g,
@@ -196,6 +119,7 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   static_assert(CS >= 2 && CS <= 16, "slot tables hold 16 ranks");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *S = reinterpret_cast<double2 *>(smem_raw);
+  double2 *Fp = S + G::OFF_FP, *Fm = S + G::OFF_FM;
   double *wscrA = reinterpret_cast<double *>(S + G::OFF_END);
   double *wscrB = wscrA + NWARPS;
   double *slotA = wscrB + NWARPS;
@@ -207,14 +131,14 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
 
   if (threadIdx.x < 32) {
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst), "r"(TM_COLS_WT) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t warp = threadIdx.x >> 5;
-  const uint32_t xaddr = tmem_base_s + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (uint32_t)TMEM_WORDS;
+  const uint32_t xaddr = tmem_base_s + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (uint32_t)TM_SPAN;
 
   const uint32_t rank = cluster_ctarank();
   const uint32_t rank_m = (rank + CS - 1) % CS, rank_p = (rank + 1) % CS;
@@ -226,18 +150,28 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   const double m = mass[c];
   const double e_p = emu[c], e_m = emmu[c];
   const int tg0 = (int)rank * LT;   // first global row of the slab
+  // rows above / below the tile: own exchange field, or the halo rows the neighbour CTAs push
+  const double2 *p_dn = top ? S + G::OFF_HP + G::H_DN : Fp + (t0 - 1) * NX;
+  const double2 *p_up = bot ? S + G::OFF_HP + G::H_UP : Fp + (t0 + TT) * NX;
+  const double2 *m_dn = top ? S + G::OFF_HM + G::H_DN : Fm + (t0 - 1) * NX;
+  const double2 *m_up = bot ? S + G::OFF_HM + G::H_UP : Fm + (t0 + TT) * NX;
 
-  // links of the slab and the W0 halo row: device layout [site][chain] -> shared memory
-  for (int k = tid; k < VL; k += NTHREADS) {
-    const int t = k / NX, x = k % NX;
-    const size_t gs = (size_t)(tg0 + t) * NX + x;
-    const int ks = t * NX + (x % TX) * NGX + x / TX;
-    S[G::OFF_W0 + ks] = W0g[gs * C + c];
-    S[G::OFF_W1 + ks] = W1g[gs * C + c];
-  }
-  for (int x = tid; x < NX; x += NTHREADS) {
-    const int tgm = (tg0 + NT - 1) % NT;
-    S[G::OFF_W0H + (x % TX) * NGX + x / TX] = W0g[((size_t)tgm * NX + x) * C + c];
+  // links of the tile and of its backward halo: device layout [site][chain] -> tensor memory
+  {
+    const int xm = (g * TX + NX - 1) % NX, tmr = (tg0 + t0 + NT - 1) % NT;
+#pragma unroll
+    for (int i = 0; i < TT; i++) {
+      const size_t row = (size_t)(tg0 + t0 + i) * NX;
+#pragma unroll
+      for (int j = 0; j < TX; j++) {
+        tmem_st_d2(xaddr + TM_ROW + 16 * i + 4 * j, W0g[(row + g * TX + j) * C + c]);
+        tmem_st_d2(xaddr + TM_ROW + 16 * i + 8 + 4 * j, W1g[(row + g * TX + j) * C + c]);
+      }
+      tmem_st_d2(xaddr + TM_W1M + 4 * i, W1g[(row + xm) * C + c]);
+    }
+#pragma unroll
+    for (int j = 0; j < TX; j++) tmem_st_d2(xaddr + TM_W0M + 4 * j, W0g[((size_t)tmr * NX + g * TX + j) * C + c]);
+    tmem_wait_st();
   }
   double2 r[TT][TX], p[TT][TX];
   double rr = 0.0;
@@ -250,13 +184,13 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
       p[i][j] = r[i][j];
       rr = fma(r[i][j].x, r[i][j].x, rr);
       rr = fma(r[i][j].y, r[i][j].y, rr);
-      S[G::OFF_F + (t0 + i) * NX + j * NGX + g] = p[i][j];
+      Fp[(t0 + i) * NX + j * NGX + g] = p[i][j];
     }
   // every CTA of the cluster is running before anyone stores into a peer's shared memory
   cluster_arrive();
   cluster_wait();
   push_rows<NX>(p, G::OFF_HP, smem_base, rank_m, rank_p, top, bot, g);
-  cluster_sum_post<CS>(rr, wscrA, slotA_addr, rank);   // hmc.c:354-356; its CTA barrier publishes F and the links
+  cluster_sum_post<CS>(rr, wscrA, slotA_addr, rank);   // hmc.c:354-356; its CTA barrier publishes Fp
   cluster_arrive();
   cluster_wait();
   rr = cluster_total<CS>(slotA);
@@ -267,39 +201,74 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   if (rr_old < s.accuracy) {  // hmc.c:359-361
     status = TB_CG_ZERO_SOURCE;
   } else {
-    cluster_arrive();   // pairs with the wait inside the first iteration (p and its halos are already published)
+    cluster_arrive();   // pairs with the wait inside the first stencil (p and its halos are already published)
     for (int k = 1; k < s.max_iter; k++) {  // hmc.c:364
-      double2 mp[TT][TX], q[TT][TX];
-      // Mp = M p (hmc.c:366): own rows first, then the hop from the neighbours' rows
-      tile_apply_own<NX, false, HAS_MU>(p, mp, S, t0, g, top, bot, m, e_p, e_m);
-      cluster_wait();   // p halos of this iteration are in place
-      tile_fixup<NX, false, HAS_MU>(mp, S, G::OFF_HP, t0, g, top, bot, e_p, e_m);
+      // ---- Mp = M p (hmc.c:366).  Finished sites go to Fm at once (its last readers passed the ||r||^2
+      // barrier); the first row of the slab waits for its hop from the halo row.
+      double2 mp[TT][TX];
       double pq = 0.0;
-      if (DAG) {   // <p, M^dagger M p> = |M p|^2
+      tile_apply_wt<NX, false, HAS_MU>(
+          p, Fp, p_dn, p_up, top, xaddr, t0, g, m, e_p, e_m,
+          [&](int i, int j, const double2 o) {
+            mp[i][j] = o;
+            if (!(i == 0 && top)) {
+              Fm[(t0 + i) * NX + j * NGX + g] = o;
+              if (DAG) {   // <p, M^dagger M p> = |M p|^2
+                pq = fma(o.x, o.x, pq);
+                pq = fma(o.y, o.y, pq);
+              }
+            }
+          },
+          [] { cluster_wait(); });   // the p halos of this iteration are in place
+      if (top) {
+        tile_fixup_dn<NX, false, HAS_MU>(mp[0], p_dn, xaddr, g, e_m);
 #pragma unroll
-        for (int i = 0; i < TT; i++)
-#pragma unroll
-          for (int j = 0; j < TX; j++) {
-            pq = fma(mp[i][j].x, mp[i][j].x, pq);
-            pq = fma(mp[i][j].y, mp[i][j].y, pq);
+        for (int j = 0; j < TX; j++) {
+          Fm[t0 * NX + j * NGX + g] = mp[0][j];
+          if (DAG) {
+            pq = fma(mp[0][j].x, mp[0][j].x, pq);
+            pq = fma(mp[0][j].y, mp[0][j].y, pq);
           }
+        }
       }
-      __syncthreads();  // this CTA has read p from F (peers read only their own halo copies)
-#pragma unroll
-      for (int i = 0; i < TT; i++)
-#pragma unroll
-        for (int j = 0; j < TX; j++) S[G::OFF_F + (t0 + i) * NX + j * NGX + g] = mp[i][j];
       push_rows<NX>(mp, G::OFF_HM, smem_base, rank_m, rank_p, top, bot, g);
-      if (DAG) cluster_sum_post<CS>(pq, wscrB, slotB_addr, rank);   // its CTA barrier publishes Mp inside the CTA
+      if (DAG) cluster_sum_post<CS>(pq, wscrB, slotB_addr, rank);   // its CTA barrier publishes Fm inside the CTA
       else __syncthreads();
       cluster_arrive();   // Mp halos and |Mp|^2 partials are on their way
-      // q = M~ Mp, hmc.c:367
-      tile_apply_own<NX, DAG, HAS_MU>(mp, q, S, t0, g, top, bot, m, DAG ? e_m : e_p, DAG ? e_p : e_m);
-      cluster_wait();
-      tile_fixup<NX, DAG, HAS_MU>(q, S, G::OFF_HM, t0, g, top, bot, DAG ? e_m : e_p, DAG ? e_p : e_m);
+      rr = 0.0;
+      double a = 0.0;
       if (DAG) {
-        pq = cluster_total<CS>(slotB);
+        // ---- q = M^dagger Mp (hmc.c:367) is consumed site by site: r -= alpha q, ||r||^2 (hmc.c:371-379).  alpha
+        // needs the cluster-wide |Mp|^2, so the first four rows of q are parked until the wait in the middle.
+        double2 qh[TT / 2][TX];
+        auto consume = [&](int i, int j, const double2 o) {
+          r[i][j].x = fma(-a, o.x, r[i][j].x);
+          r[i][j].y = fma(-a, o.y, r[i][j].y);
+          rr = fma(r[i][j].x, r[i][j].x, rr);
+          rr = fma(r[i][j].y, r[i][j].y, rr);
+        };
+        tile_apply_wt<NX, true, HAS_MU>(
+            mp, Fm, m_dn, m_up, top, xaddr, t0, g, m, e_m, e_p,
+            [&](int i, int j, const double2 o) {
+              if (i < TT / 2) qh[i % (TT / 2)][j] = o;
+              else consume(i, j, o);
+            },
+            [&] {
+              cluster_wait();
+              a = rr_old / cluster_total<CS>(slotB);   // hmc.c:371
+              if (top) tile_fixup_dn<NX, true, HAS_MU>(qh[0], m_dn, xaddr, g, e_p);
+#pragma unroll
+              for (int i = 0; i < TT / 2; i++)
+#pragma unroll
+                for (int j = 0; j < TX; j++) consume(i, j, qh[i][j]);
+            });
       } else {
+        // ---- M~ = M (REF_COMPAT): alpha needs <p, q> of the whole lattice, q is kept
+        double2 q[TT][TX];
+        tile_apply_wt<NX, false, HAS_MU>(
+            mp, Fm, m_dn, m_up, top, xaddr, t0, g, m, e_p, e_m, [&](int i, int j, const double2 o) { q[i][j] = o; },
+            [] { cluster_wait(); });
+        if (top) tile_fixup_dn<NX, false, HAS_MU>(q[0], m_dn, xaddr, g, e_m);
 #pragma unroll
         for (int i = 0; i < TT; i++)
 #pragma unroll
@@ -310,41 +279,20 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
         cluster_sum_post<CS>(pq, wscrB, slotB_addr, rank);
         cluster_arrive();
         cluster_wait();
-        pq = cluster_total<CS>(slotB);
+        a = rr_old / cluster_total<CS>(slotB);   // hmc.c:371
+#pragma unroll
+        for (int i = 0; i < TT; i++)
+#pragma unroll
+          for (int j = 0; j < TX; j++) {
+            r[i][j].x = fma(-a, q[i][j].x, r[i][j].x);   // hmc.c:374-375
+            r[i][j].y = fma(-a, q[i][j].y, r[i][j].y);
+            rr = fma(r[i][j].x, r[i][j].x, rr);          // hmc.c:377-379
+            rr = fma(r[i][j].y, r[i][j].y, rr);
+          }
       }
-      const double a = rr_old / pq;   // hmc.c:371
-      rr = 0.0;
-#pragma unroll
-      for (int i = 0; i < TT; i++)
-#pragma unroll
-        for (int j = 0; j < TX; j++) {
-          r[i][j].x = fma(-a, q[i][j].x, r[i][j].x);   // hmc.c:374-375
-          r[i][j].y = fma(-a, q[i][j].y, r[i][j].y);
-          rr = fma(r[i][j].x, r[i][j].x, rr);          // hmc.c:377-379
-          rr = fma(r[i][j].y, r[i][j].y, rr);
-        }
-      cluster_sum_post<CS>(rr, wscrA, slotA_addr, rank);   // its CTA barrier: every local read of Mp has finished
+      cluster_sum_post<CS>(rr, wscrA, slotA_addr, rank);   // its CTA barrier: every local read of Fm has finished
       cluster_arrive();
-      // x += a p (hmc.c:372-373) in tensor memory while the ||r||^2 partials cross the cluster
-#pragma unroll
-      for (int ch = 0; ch < TMEM_WORDS / 16; ch++) {
-        uint32_t v[16];
-        if (k > 1) tmem_ld16(v, xaddr + ch * 16);
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-          const int f = ch * 4 + u, i = f / TX, j = f % TX;
-          double xr = (k > 1) ? __hiloint2double((int)v[4 * u + 1], (int)v[4 * u]) : 0.0;   // hmc.c:351: x0 = 0
-          double xi = (k > 1) ? __hiloint2double((int)v[4 * u + 3], (int)v[4 * u + 2]) : 0.0;
-          xr += a * p[i][j].x;
-          xi += a * p[i][j].y;
-          v[4 * u] = (uint32_t)__double2loint(xr);
-          v[4 * u + 1] = (uint32_t)__double2hiint(xr);
-          v[4 * u + 2] = (uint32_t)__double2loint(xi);
-          v[4 * u + 3] = (uint32_t)__double2hiint(xi);
-        }
-        tmem_st16(xaddr + ch * 16, v);
-      }
-      tmem_wait_st();
+      tmem_x_axpy(xaddr + TM_X, p, a, k == 1);   // x += a p (hmc.c:372-373) while the partials cross the cluster
       cluster_wait();
       rr = cluster_total<CS>(slotA);
       iters = k;
@@ -358,19 +306,19 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
         for (int j = 0; j < TX; j++) {
           p[i][j].x = fma(be, p[i][j].x, r[i][j].x);   // hmc.c:391-392
           p[i][j].y = fma(be, p[i][j].y, r[i][j].y);
-          S[G::OFF_F + (t0 + i) * NX + j * NGX + g] = p[i][j];
+          Fp[(t0 + i) * NX + j * NGX + g] = p[i][j];   // the last readers of Fp passed the |Mp|^2 barrier
         }
       push_rows<NX>(p, G::OFF_HP, smem_base, rank_m, rank_p, top, bot, g);
       rr_old = rr;
       __syncthreads();    // p is published inside the CTA
-      cluster_arrive();   // and its halos are on their way; the wait is after the own-rows stencil
+      cluster_arrive();   // and its halos are on their way; the wait is in the middle of the next stencil
       if (k + 1 >= s.max_iter) cluster_wait();   // loop ends here: close the barrier
     }
   }
 #pragma unroll
-  for (int ch = 0; ch < TMEM_WORDS / 16; ch++) {
+  for (int ch = 0; ch < 4; ch++) {
     uint32_t v[16];
-    if (iters > 0) tmem_ld16(v, xaddr + ch * 16);
+    if (iters > 0) tmem_ld16(v, xaddr + TM_X + ch * 16);
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       const int f = ch * 4 + u, i = f / TX, j = f % TX;
@@ -382,7 +330,7 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   }
   __syncthreads();   // every warp has read its columns
   if (threadIdx.x < 32)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base_s), "r"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base_s), "r"(TM_COLS_WT) : "memory");
   if (tid == 0 && rank == 0) {
     s.status[c] = status;
     s.iters[c] = iters;

@@ -108,39 +108,39 @@ __device__ __forceinline__ double2 d2_from_words(const uint32_t *w) {
 // 240 columns per thread (16-aligned); the two warps of a lane quarter stack along the columns: 480 of 512.
 constexpr int TM_X = 0, TM_ROW = 64, TM_W1M = 192, TM_W0M = 224, TM_SPAN = 240, TM_COLS_WT = 512;
 
-// out = m f +- hops on the thread's 8 x 2 tile with the links streamed from tensor memory (software-pipelined one
-// row ahead).  F: the field in shared memory (row-major NX, sub-plane layout), only the tile's halo is read.
-// Same arithmetic and hop order as tile_apply.  CLUSTER: the lattice continues in other CTAs, rows are not wrapped
-// and the hop from row t0-1 (top) / t0+8 (bot) is skipped; the caller adds it later from the halo rows.
-// Every finished site is handed to epi(i, j, value) (i, j compile-time after unrolling): the caller stores it,
-// publishes it or folds it into the CG update at once, so no output tile has to stay live in registers.
-template <int NT, int NX, bool DAG, bool HAS_MU, bool CLUSTER, typename Epi>
-__device__ __forceinline__ void tile_apply_wt(const double2 (&f)[8][2], const double2 *F, uint32_t wb, int t0, int g,
-                                              bool top, bool bot, double m, double af, double ab, Epi epi) {
+// m f +- hops on the thread's 8 x 2 tile with the links streamed from tensor memory (software-pipelined one row
+// ahead).  F: the field in shared memory (rows of NX sites in sub-plane layout); only the tile's halo is read from
+// it: columns x0-1 and x0+2 of the tile's rows, and the rows above and below the tile, given as row pointers
+// rowdn (t0-1) and rowup (t0+8) so that a cluster kernel can point them at its halo buffers.  Same arithmetic and
+// hop order as tile_apply.
+//   skip_dn   the hop from row t0-1 is left out (its data is not there yet); the caller adds it afterwards
+//   epi(i, j, value)   receives every finished site (i, j compile-time after unrolling): the caller stores it,
+//                      publishes it or folds it into the CG update at once, so no output tile need stay live
+//   mid()     runs between rows 3 and 4; rowup is first read after it (a cluster kernel waits for its halos there)
+template <int NX, bool DAG, bool HAS_MU, typename Epi, typename Mid>
+__device__ __forceinline__ void tile_apply_wt(const double2 (&f)[8][2], const double2 *F, const double2 *rowdn,
+                                              const double2 *rowup, bool skip_dn, uint32_t wb, int t0, int g,
+                                              double m, double af, double ab, Epi epi, Mid mid) {
   constexpr int TX = 2, TT = 8;
   constexpr int SF = DAG ? -1 : 1;
   constexpr int SB = -SF;
   constexpr int NG = NX / TX;
   const int gl = (g + NG - 1) % NG, gr = (g + 1) % NG;
-  const int tm = CLUSTER ? t0 - 1 : (t0 + NT - 1) % NT, te = CLUSTER ? t0 + TT : (t0 + TT) % NT;
   const double2 zero = make_double2(0.0, 0.0);
   uint32_t h[8], buf[2][20];
   tmem_ld8_async(h, wb + TM_W0M);
   tmem_ld16_async(buf[0], wb + TM_ROW);
   tmem_ld4_async(buf[0], wb + TM_W1M);
-  // halo of the field while the links are in flight
-  double2 fdn[TX], fup[TX];
+  double2 fdn[TX];   // halo of the field while the links are in flight
 #pragma unroll
-  for (int j = 0; j < TX; j++) {
-    fdn[j] = (CLUSTER && top) ? zero : F[tm * NX + j * NG + g];
-    fup[j] = (CLUSTER && bot) ? zero : F[te * NX + j * NG + g];
-  }
+  for (int j = 0; j < TX; j++) fdn[j] = skip_dn ? zero : rowdn[j * NG + g];
   tmem_wait_ld(buf[0], h);
   double2 w0m[TX];
 #pragma unroll
   for (int j = 0; j < TX; j++) w0m[j] = d2_from_words(&h[4 * j]);
 #pragma unroll
   for (int i = 0; i < TT; i++) {
+    if (i == TT / 2) mid();
     uint32_t(&cur)[20] = buf[i & 1];
     if (i + 1 < TT) {
       tmem_ld16_async(buf[(i + 1) & 1], wb + TM_ROW + 16 * (i + 1));
@@ -154,7 +154,7 @@ __device__ __forceinline__ void tile_apply_wt(const double2 (&f)[8][2], const do
     for (int j = 0; j < TX; j++) {
       const double2 w0c = d2_from_words(&cur[4 * j]);
       const double2 w1c = d2_from_words(&cur[8 + 4 * j]);
-      const double2 up = (i == TT - 1) ? fup[j] : f[(i + 1) % TT][j];
+      const double2 up = (i == TT - 1) ? rowup[j * NG + g] : f[(i + 1) % TT][j];
       const double2 dn = (i == 0) ? fdn[j] : f[(i + TT - 1) % TT][j];
       const double2 rt = (j == TX - 1) ? fR : f[i][(j + 1) % TX];
       const double2 lf = (j == 0) ? fL : f[i][(j + TX - 1) % TX];
@@ -173,6 +173,24 @@ __device__ __forceinline__ void tile_apply_wt(const double2 (&f)[8][2], const do
       w1m = w1c;
     }
     if (i + 1 < TT) tmem_wait_ld(buf[(i + 1) & 1]);
+  }
+}
+
+// the hop tile_apply_wt left out with skip_dn: -+ ab conj(W0(t0-1, x)) f(t0-1, x) into the tile's first row
+template <int NX, bool DAG, bool HAS_MU>
+__device__ __forceinline__ void tile_fixup_dn(double2 (&row0)[2], const double2 *rowdn, uint32_t wb, int g, double ab) {
+  constexpr int SB = DAG ? 1 : -1;
+  uint32_t h[8];
+  tmem_ld8_async(h, wb + TM_W0M);
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+               : "+r"(h[0]), "+r"(h[1]), "+r"(h[2]), "+r"(h[3]), "+r"(h[4]), "+r"(h[5]), "+r"(h[6]), "+r"(h[7])
+               :
+               : "memory");
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    double2 w = d2_from_words(&h[4 * j]);
+    if (HAS_MU) w = make_double2(w.x * ab, w.y * ab);
+    hopc_acc<SB>(row0[j], w, rowdn[j * (NX / 2) + g]);
   }
 }
 

@@ -371,6 +371,7 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
   const int tid = threadIdx.x;
   const int g = tid % NG;
   const int t0 = (tid / NG) * TT;
+  const int tm = (t0 + NT - 1) % NT, te = (t0 + TT) % NT;   // rows above and below the tile (periodic)
   const double m = mass[c];
   const double e_p = emu[c], e_m = emmu[c];
 
@@ -417,15 +418,17 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
       // passed the ||r||^2 barrier), and <p, M^dagger M p> = |M p|^2 is accumulated on the way
       double2 mp[TT][TX];
       double pq = 0.0;
-      tile_apply_wt<NT, NX, false, HAS_MU, false>(p, Fp, xaddr, t0, g, false, false, m, e_p, e_m,
-                                                  [&](int i, int j, const double2 o) {
-                                                    mp[i][j] = o;
-                                                    Fm[(t0 + i) * NX + j * NG + g] = o;
-                                                    if (DAG) {
-                                                      pq = fma(o.x, o.x, pq);
-                                                      pq = fma(o.y, o.y, pq);
-                                                    }
-                                                  });
+      tile_apply_wt<NX, false, HAS_MU>(
+          p, Fp, Fp + tm * NX, Fp + te * NX, false, xaddr, t0, g, m, e_p, e_m,
+          [&](int i, int j, const double2 o) {
+            mp[i][j] = o;
+            Fm[(t0 + i) * NX + j * NG + g] = o;
+            if (DAG) {
+              pq = fma(o.x, o.x, pq);
+              pq = fma(o.y, o.y, pq);
+            }
+          },
+          [] {});
       if (DAG) pq = block_sum8(pq, scrB);   // its barrier also publishes Mp
       else __syncthreads();
       rr = 0.0;
@@ -434,21 +437,25 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
         // alpha is known before q = M^dagger Mp exists (hmc.c:367,371): q is consumed site by site,
         // r -= alpha q and ||r||^2 (hmc.c:374-379), and never stored
         a = rr_old / pq;
-        tile_apply_wt<NT, NX, true, HAS_MU, false>(mp, Fm, xaddr, t0, g, false, false, m, e_m, e_p,
-                                                   [&](int i, int j, const double2 o) {
-                                                     r[i][j].x = fma(-a, o.x, r[i][j].x);
-                                                     r[i][j].y = fma(-a, o.y, r[i][j].y);
-                                                     rr = fma(r[i][j].x, r[i][j].x, rr);
-                                                     rr = fma(r[i][j].y, r[i][j].y, rr);
-                                                   });
+        tile_apply_wt<NX, true, HAS_MU>(
+            mp, Fm, Fm + tm * NX, Fm + te * NX, false, xaddr, t0, g, m, e_m, e_p,
+            [&](int i, int j, const double2 o) {
+              r[i][j].x = fma(-a, o.x, r[i][j].x);
+              r[i][j].y = fma(-a, o.y, r[i][j].y);
+              rr = fma(r[i][j].x, r[i][j].x, rr);
+              rr = fma(r[i][j].y, r[i][j].y, rr);
+            },
+            [] {});
       } else {
         double2 q[TT][TX];
-        tile_apply_wt<NT, NX, false, HAS_MU, false>(mp, Fm, xaddr, t0, g, false, false, m, e_p, e_m,
-                                                    [&](int i, int j, const double2 o) {
-                                                      q[i][j] = o;
-                                                      pq = fma(p[i][j].x, o.x, pq);   // hmc.c:368-370
-                                                      pq = fma(p[i][j].y, o.y, pq);
-                                                    });
+        tile_apply_wt<NX, false, HAS_MU>(
+            mp, Fm, Fm + tm * NX, Fm + te * NX, false, xaddr, t0, g, m, e_p, e_m,
+            [&](int i, int j, const double2 o) {
+              q[i][j] = o;
+              pq = fma(p[i][j].x, o.x, pq);   // hmc.c:368-370
+              pq = fma(p[i][j].y, o.y, pq);
+            },
+            [] {});
         pq = block_sum8(pq, scrB);
         a = rr_old / pq;   // hmc.c:371
 #pragma unroll
