@@ -295,6 +295,9 @@ def gpu_arm(args):
     stream_roof = None
     if rank == 0 and world == 1 and not args.no_extra:
         stream_roof = streaming_roofline(tb, torch, dev, stream)
+    other = None
+    if not args.no_extra:
+        other = other_configs(tb, torch, dist if world > 1 else None, dev, stream, rank, world)
     if rank == 0:
         peak, peak_src = measured_peak()
         sites = NT * NX * chains
@@ -306,7 +309,8 @@ def gpu_arm(args):
         e2e_value = applies_all * args.steps / (e2e_ms * 1e-3)
         resident = launches <= 2 * args.steps  # one launch per solve => the on-chip resident kernel ran
         launches_per_step = max(launches / args.steps, 1)
-        kernel_name = ("resident_cg_kernel (whole batched solve in one launch; CG state in registers + shared memory)"
+        kernel_name = ("resident_wt_kernel (whole batched solve in one launch; r, p in registers, p/Mp exchange in "
+                       "shared memory, links and x in tensor memory)"
                        if resident else "CG iteration (dslash, dslash+dot, axpy+norm, xpay)")
         regime = ("cache-resident: state on chip, frac > 1 is expected; HBM traffic = `traffic`"
                   if resident else "streaming")
@@ -343,6 +347,8 @@ def gpu_arm(args):
                                    "(SURVEY Appendix C)"}
         if stream_roof is not None:
             line["roofline_streaming"] = stream_roof
+        if other is not None:
+            line["other_configs"] = other
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             v, busy, applies, kind, nch, wall = run_cpu_reference(cores * 8, cores)
@@ -390,6 +396,107 @@ def streaming_roofline(tb, torch, dev, stream):
             "workload": f"{nt}x{nx} x {chains} chains, {it} iterations, working set 470 MB > L2",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
             "us_per_iteration": t * 1e6 / it}
+
+
+def other_configs(tb, torch, dist, dev, stream, rank, world):
+    """The remaining BASELINE.json configurations, one bounded measurement each (not the headline; parity for
+    these shapes is in tests/).  Chains / parameter points shard over ranks like the headline workload: every
+    figure is whole-job units over the slowest rank's time."""
+    out = {}
+    local = dev.index or 0
+
+    def max_over_ranks(ms):
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def total_over_ranks(v):
+        t = torch.tensor([float(v)], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def solve_once(ctx, n, solver):
+        g = torch.Generator(device=dev).manual_seed(11 + rank)
+        xi = torch.randn(n, dtype=torch.float64, device=dev, generator=g)
+        b, x = torch.empty_like(xi), torch.empty_like(xi)
+        ctx.apply_dev(tb.OP_MCONJ, xi.data_ptr(), b.data_ptr())
+        ctx.set_tuning(0, 0, solver)
+        ctx.cg_dev(b.data_ptr(), x.data_ptr())  # warm-up (graph build for the streaming solver)
+        ctx.cg_dev(b.data_ptr(), x.data_ptr())
+        info = ctx.cg_result()
+        return ctx.last_solve_ms, info
+
+    # configs[2]: 256x256, light mass (ill-conditioned CG), chains sharded over the GPUs.  SURVEY 8(d): g = 1,
+    # m = 0.01 (about 3 100 iterations), 8 chains per GPU.
+    nt = nx = 256
+    chains = 8
+    ctx = tb.Context(nt, nx, chains, tb.MODE_ADJOINT, device=local, m=0.01, mu=0.0, stream=stream.cuda_stream)
+    ctx.hmc_set_coupling(1.0)
+    ctx.hmc_heatbath(100, seed=300 + rank)
+    kind, in_flight = ctx.solver_info()
+    ms, info = solve_once(ctx, ctx.vec_doubles, 0)
+    ms_stream, _ = solve_once(ctx, ctx.vec_doubles, 1)
+    ctx.close()
+    ms = max_over_ranks(ms)
+    applies = total_over_ranks(2 * int(info.iters.astype(np.int64).sum()))
+    out["256x256_m0.01_g1_8_chains_per_gpu"] = {
+        "dirac_applies_per_sec": applies / (ms * 1e-3), "site_applies_per_sec": applies * nt * nx / (ms * 1e-3),
+        "ms_per_batched_solve": ms, "cg_iters_mean": float(info.iters.mean()),
+        "converged": bool(np.all(info.status == tb.CG_CONVERGED)),
+        "solver": {0: "streaming", 1: "on-chip (CTA per chain)", 2: "on-chip (16-CTA cluster per chain)"}[kind],
+        "chains_in_flight": in_flight, "ms_streaming_solver": max_over_ranks(ms_stream)}
+
+    # configs[4]: coupling/mass scan, 32 (g, m) points x 64 chains on 128x128, chiral condensate measurement.
+    # 4 points (256 chains) per GPU; per-chain m and g; condensate from stochastic sources through fm_invert_cg.
+    nt = nx = 128
+    pts = [(g, m) for g in (0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 1.0) for m in (0.01, 0.03, 0.1, 0.3)]
+    mine = [pts[(4 * rank + k) % len(pts)] for k in range(4)]
+    chains = 64 * len(mine)
+    g_arr = np.repeat([p[0] for p in mine], 64)
+    m_arr = np.repeat([p[1] for p in mine], 64)
+    ctx = tb.Context(nt, nx, chains, tb.MODE_ADJOINT, device=local, stream=stream.cuda_stream)
+    ctx.set_params(m_arr, 0.0)
+    ctx.hmc_set_coupling(g_arr)
+    ctx.hmc_heatbath(100, seed=500 + rank)
+    kind, in_flight = ctx.solver_info()
+    nsrc = 2
+    ctx.hmc_condensate(nsrc=1, seed=1, meas_index=0)  # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    cond, its = ctx.hmc_condensate(nsrc=nsrc, seed=1, meas_index=1)
+    torch.cuda.synchronize()
+    sec = max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3
+    ctx.close()
+    applies = total_over_ranks(2 * its + chains * nsrc)
+    out["128x128_scan_4_points_x_64_chains_per_gpu_condensate"] = {
+        "condensate_sources_per_sec": world * chains * nsrc / sec, "dirac_applies_per_sec": applies / sec,
+        "ms_per_source_batch": 1e3 * sec / nsrc, "points_on_rank0": mine, "nsrc": nsrc,
+        "condensate_rank0_by_point": [float(np.mean(cond[64 * k:64 * (k + 1)])) for k in range(len(mine))],
+        "finite": bool(np.all(np.isfinite(cond))),
+        "solver": {0: "streaming", 1: "on-chip (CTA per chain)", 2: "on-chip (4-CTA cluster per chain)"}[kind],
+        "chains_in_flight": in_flight}
+
+    # configs[3] at N = 1: 2048x2048 single lattice, streaming CG, fixed 200 iterations (the slab-decomposed
+    # multi-GPU figures come from tools/slab_bench.py, profiles/scaling_*.txt)
+    if world == 1:
+        nt = nx = 2048
+        peak, _ = measured_peak()
+        ctx = tb.Context(nt, nx, 1, tb.MODE_ADJOINT, device=local, m=0.05, mu=0.0, stream=stream.cuda_stream)
+        ctx.set_cg(1e-30, 201)
+        g = torch.Generator(device=dev).manual_seed(5)
+        A = (torch.rand(nt * nx * 2, dtype=torch.float64, device=dev, generator=g) - 0.5) * (2 * np.pi)
+        ctx.set_gauge_dev(A.data_ptr())
+        ms, info = solve_once(ctx, ctx.vec_doubles, 1)
+        it = int(info.iters.max())
+        ctx.close()
+        out["2048x2048_single_lattice_1_gpu"] = {
+            "us_per_cg_iteration": ms * 1e3 / it, "dirac_applies_per_sec": 2 * it / (ms * 1e-3),
+            "site_applies_per_sec": 2 * it * nt * nx / (ms * 1e-3),
+            "hbm_frac_288B_definition": BYTES_PER_SITE_ITER * nt * nx * it / (ms * 1e-3) / 1e9 / peak,
+            "hbm_frac_real_traffic_240B": 240 * nt * nx * it / (ms * 1e-3) / 1e9 / peak, "iterations": it}
+    return out
 
 
 def main():

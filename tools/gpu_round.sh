@@ -19,6 +19,10 @@ echo "== ncu full: resident kernel"
 ncu --set full --clock-control none --import-source on -k regex:resident -s 2 -c 1 \
     -f -o $OUT/prof_${TAG}_resident python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-hmc --no-extra > $OUT/ncu_full_$TAG.log 2>&1
 tail -1 $OUT/ncu_full_$TAG.log | cut -c1-200
+echo "== ncu full: cluster kernel (128x128 x 33 chains = one wave of 4-CTA clusters)"
+ncu --set full --clock-control none --import-source on -k regex:cluster_cg -s 1 -c 1 \
+    -f -o $OUT/prof_${TAG}_cluster python tools/probe_cluster.py 128,128,33,0.1 > $OUT/ncu_full_cluster_$TAG.log 2>&1
+tail -1 $OUT/ncu_full_cluster_$TAG.log | cut -c1-200
 echo "== ncu full: streaming kernels on a working set > L2 (256x256 x 64 chains)"
 ncu --set full --clock-control none --import-source on -k regex:'dslash_kernel|axpy_norm|xpay' -s 40 -c 8 \
     -f -o $OUT/prof_${TAG}_stream python tools/probe.py --one 256 256 64 > $OUT/ncu_full_stream_$TAG.log 2>&1
