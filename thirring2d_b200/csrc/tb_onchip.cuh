@@ -52,42 +52,29 @@ __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.
 // The link fields are read-only during a solve and every thread needs exactly the links of its own tile plus the
 // tile's backward halo (W0 of the row above, W1 of the column to the left): 42 double2 for an 8 x 2 tile.  Kept as
 // thread-private TMEM columns they cost no shared-memory bandwidth (the LSU data pipe is what bounds the on-chip
-// kernels).  Asynchronous variants: issue, compute on something else, then tmem_wait_ld on the destination
-// registers (the "+r" operands make every later use depend on the wait).
-__device__ __forceinline__ void tmem_ld16_async(uint32_t (&v)[20], uint32_t taddr) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32"
-               "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                 "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-               : "r"(taddr));
-}
-__device__ __forceinline__ void tmem_ld4_async(uint32_t (&v)[20], uint32_t taddr) {   // fills v[16..19]
+// kernels).  Asynchronous variants: issue, compute on something else, then tmem_wait_ld before the first use.
+// A row of links (20 words) is fetched as five independent x4 loads: one x16 load needs a 16-register aligned
+// landing block, of which ptxas finds only one under this register pressure and then copies every value out of
+// it (a quarter of the stencil's instructions were those moves); x4 blocks can live anywhere.
+__device__ __forceinline__ void tmem_ld4_at(uint32_t (&v)[20], int k, uint32_t taddr) {   // fills v[4k .. 4k+3]
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
-               : "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19])
+               : "=r"(v[4 * k]), "=r"(v[4 * k + 1]), "=r"(v[4 * k + 2]), "=r"(v[4 * k + 3])
                : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16_async(uint32_t (&v)[20], uint32_t taddr) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) tmem_ld4_at(v, k, taddr + 4 * k);
+}
+__device__ __forceinline__ void tmem_ld4_async(uint32_t (&v)[20], uint32_t taddr) { tmem_ld4_at(v, 4, taddr); }
 __device__ __forceinline__ void tmem_ld8_async(uint32_t (&v)[8], uint32_t taddr) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                : "r"(taddr));
 }
-__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[20]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
-                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19])
-               :
-               : "memory");
-}
-__device__ __forceinline__ void tmem_wait_ld(uint32_t (&v)[20], uint32_t (&h)[8]) {
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
-                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(h[0]), "+r"(h[1]), "+r"(h[2]), "+r"(h[3]),
-                 "+r"(h[4]), "+r"(h[5]), "+r"(h[6]), "+r"(h[7])
-               :
-               : "memory");
-}
+// tcgen05.wait::ld is what PTX requires between a tensor-memory load and the first use of its registers; ptxas
+// turns it into scoreboard waits on exactly those registers (no instruction of its own in the SASS), so it is
+// stated once per stage without tying the registers to the asm (that forced a copy of every loaded value).
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d)
                : "memory");
@@ -134,7 +121,7 @@ __device__ __forceinline__ void tile_apply_wt(const double2 (&f)[8][2], const do
   double2 fdn[TX];   // halo of the field while the links are in flight
 #pragma unroll
   for (int j = 0; j < TX; j++) fdn[j] = skip_dn ? zero : rowdn[j * NG + g];
-  tmem_wait_ld(buf[0], h);
+  tmem_wait_ld();
   double2 w0m[TX];
 #pragma unroll
   for (int j = 0; j < TX; j++) w0m[j] = d2_from_words(&h[4 * j]);
@@ -172,7 +159,7 @@ __device__ __forceinline__ void tile_apply_wt(const double2 (&f)[8][2], const do
       w0m[j] = w0c;
       w1m = w1c;
     }
-    if (i + 1 < TT) tmem_wait_ld(buf[(i + 1) & 1]);
+    if (i + 1 < TT) tmem_wait_ld();
   }
 }
 
@@ -182,10 +169,7 @@ __device__ __forceinline__ void tile_fixup_dn(double2 (&row0)[2], const double2 
   constexpr int SB = DAG ? 1 : -1;
   uint32_t h[8];
   tmem_ld8_async(h, wb + TM_W0M);
-  asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-               : "+r"(h[0]), "+r"(h[1]), "+r"(h[2]), "+r"(h[3]), "+r"(h[4]), "+r"(h[5]), "+r"(h[6]), "+r"(h[7])
-               :
-               : "memory");
+  tmem_wait_ld();
 #pragma unroll
   for (int j = 0; j < 2; j++) {
     double2 w = d2_from_words(&h[4 * j]);
