@@ -336,7 +336,12 @@ def gpu_arm(args):
                          "kernel": kernel_name, "regime": regime,
                          "algorithmic_bytes_per_launch": alg_bytes_per_step / launches_per_step,
                          "algorithmic_bytes_per_site_iteration": BYTES_PER_SITE_ITER,
-                         "us_per_iteration": solve_ms * 1e3 / args.steps / max_it, "sites": sites},
+                         "us_per_iteration": solve_ms * 1e3 / args.steps / max_it, "sites": sites,
+                         # what actually bounds the on-chip kernel (ncu: FP64 pipe), for orientation only: 34
+                         # useful flops per site and apply + 20 for the fused BLAS-1
+                         "fp64": {"achieved_tflops": 88 * NT * NX * float(iters.sum()) * args.steps
+                                  / (solve_ms * 1e-3) / 1e12,
+                                  "nominal_peak_tflops": 37.0, "peak_source": "B200 datasheet FP64 (not measured)"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(A_host.nbytes + b_host.nbytes),
                     "d2h_bytes_per_step": int(x_host.nbytes), "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches_all),
@@ -481,6 +486,39 @@ def other_configs(tb, torch, dist, dev, stream, rank, world):
         "finite": bool(np.all(np.isfinite(cond))),
         "solver": {0: "streaming", 1: "on-chip (CTA per chain)", 2: "on-chip (4-CTA cluster per chain)"}[kind],
         "chains_in_flight": in_flight}
+
+    # SURVEY 8(f) row 3, family B (vec_ops.c): measure_propagator's batch of point sources on one occupation mask
+    # (fermionbag.c:389-435) through cg_propagator, host buffers in and out; reference = its own vec_ops.c on one core
+    if world == 1:
+        from_b = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", "--nt", "64", "--nx", "64", "--m", "0.1",
+                                 "--mu", "0.0", "--family-b", "8"], cwd=ROOT, capture_output=True, text=True)
+        nt = nx = 64
+        nsrc = 2 * nx
+        rng = np.random.default_rng(4242)   # same mask and sources as oracle/cpu_baseline.py:family_b_inputs
+        field = (rng.random((nt, nx)) < 0.1).astype(np.int32)
+        sites = [(t, x) for t in range(nt) for x in range(nx) if field[t, x] == 0][:nsrc]
+        src = np.zeros((nsrc, nt, nx))
+        for i, (t, x) in enumerate(sites):
+            src[i, t, x] = 1.0
+        ctx = tb.Context(nt, nx, nsrc, tb.MODE_ADJOINT, device=local, m=0.1, mu=0.0, stream=stream.cuda_stream)
+        ctx.set_occupancy(np.broadcast_to(field, (nsrc, nt, nx)))
+        kind, _ = ctx.solver_info()
+        ctx.cg_propagator(src)
+        t0 = time.perf_counter()
+        prop, info = ctx.cg_propagator(src)
+        sec = time.perf_counter() - t0
+        ctx.close()
+        fb = {"propagators_per_sec": nsrc / sec, "sources": nsrc, "ms_per_batch": 1e3 * sec,
+              "cg_iters_mean": float(info.iters.mean()), "converged": bool(np.all(info.status == tb.CG_CONVERGED)),
+              "solver": {0: "streaming", 1: "on-chip (CTA per source)", 2: "on-chip (cluster per source)"}[kind]
+                        + ", masked real operator on the complex kernels"}
+        try:
+            o = json.loads(from_b.stdout.strip().splitlines()[-1])
+            fb["cpu_baseline"] = {"propagators_per_sec": o["sources"] / o["seconds"], "cores": 1, "kind": o["kind"],
+                                  "sample": f"{o['sources']} point sources through the reference's cg_propagator"}
+        except Exception:
+            pass
+        out["family_b_64x64_point_source_propagators"] = fb
 
     # configs[3] at N = 1: 2048x2048 single lattice, streaming CG, fixed 200 iterations (the slab-decomposed
     # multi-GPU figures come from tools/slab_bench.py, profiles/scaling_*.txt)

@@ -24,6 +24,37 @@ def synthetic_chain(chain, nt, nx, g):
     return A, xi
 
 
+def family_b_inputs(nt, nx, nsrc):
+    """Occupation mask (10 % monomers, fermionbag.c's field) and point sources on the first rows, as
+    measure_propagator (fermionbag.c:389-435) builds them."""
+    rng = np.random.default_rng(4242)
+    field = (rng.random((nt, nx)) < 0.1).astype(np.int32)
+    sites = [(t, x) for t in range(nt) for x in range(nx) if field[t, x] == 0][:nsrc]
+    src = np.zeros((len(sites), nt, nx))
+    for i, (t, x) in enumerate(sites):
+        src[i, t, x] = 1.0
+    return field, src
+
+
+def family_b(a):
+    from oracle.pyoracle import RefLibB, ref_b_available
+
+    field, src = family_b_inputs(a.nt, a.nx, a.family_b)
+    orc = Oracle()
+    use_ref = ref_b_available(a.nt, a.nx)
+    ref = RefLibB(a.nt, a.nx, m=a.m, mu=a.mu) if use_ref else None
+    if use_ref:
+        ref.set_field(field)
+    t0 = time.perf_counter()
+    for i in range(src.shape[0]):
+        if use_ref:
+            ref.call("cg_propagator", src[i])
+        else:
+            orc.cg_MdM(src[i], field, a.m, a.mu, propagator=True)
+    secs = time.perf_counter() - t0
+    print(json.dumps({"seconds": secs, "sources": int(src.shape[0]), "kind": "reference" if use_ref else "port"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--nt", type=int, default=64)
@@ -34,7 +65,11 @@ def main():
     ap.add_argument("--mu", type=float, default=0.0)
     ap.add_argument("--g", type=float, default=0.3)
     ap.add_argument("--max-iter", type=int, default=0)
+    ap.add_argument("--family-b", type=int, default=0, metavar="NSRC",
+                    help="time the reference's vec_ops.c cg_propagator on NSRC point sources instead")
     a = ap.parse_args()
+    if a.family_b:
+        return family_b(a)
     orc = Oracle()
     use_ref = ref_available(a.nt, a.nx, "adjoint")
     ref = RefLib(a.nt, a.nx, "adjoint", m=a.m, g=a.g, mu=a.mu) if use_ref else None

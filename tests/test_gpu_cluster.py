@@ -125,3 +125,31 @@ def test_cluster_device_resident_invert_and_condensate():
     want = float((m / (m * m + s[:, None] + s[None, :])).mean())
     err = cond.std(ddof=1) / np.sqrt(n)
     assert abs(cond.mean() - want) < 5 * err + 1e-4, (cond.mean(), want, err)
+
+
+@pytest.mark.parametrize("nt,nx", [(128, 64), (128, 128)])
+def test_cluster_family_b_masked_operator(oracle, nt, nx):
+    """Family B (vec_ops.c: real operator with an occupation mask) on the cluster kernel: cg_MdM and cg_propagator
+    against the oracle, on-chip and streaming."""
+    rng = np.random.default_rng(nt + nx)
+    nsrc, m, mu = 3, 0.3, 0.1
+    field = (rng.random((nsrc, nt, nx)) < 0.1).astype(np.int32)
+    psi = rng.normal(size=(nsrc, nt, nx))
+    with tb.Context(nt, nx, nsrc, tb.MODE_ADJOINT, m=m, mu=mu) as ctx:
+        ctx.set_occupancy(field)
+        ctx.set_tuning(solver=2)
+        assert ctx.solver_info()[0] == 2
+        x, info = ctx.cg_MdM(psi)
+        xp, infop = ctx.cg_propagator(psi)
+        ctx.set_tuning(solver=1)
+        xs, infos = ctx.cg_MdM(psi)
+    for c in range(nsrc):
+        xo, st, it, rr = oracle.cg_MdM(psi[c], field[c], m, mu)
+        assert info.status[c] == st == tb.CG_CONVERGED and abs(int(info.iters[c]) - it) <= 1
+        assert_close(x[c], xo, CG_SOL_TOL, "cg_MdM")
+        assert_close(x[c], xs[c], CG_SOL_TOL, "on-chip vs streaming")
+        xo, st, it, rr = oracle.cg_MdM(psi[c], field[c], m, mu, propagator=True)
+        assert abs(int(infop.iters[c]) - it) <= 1
+        assert_close(xp[c], xo, CG_SOL_TOL, "cg_propagator")
+        occ_sites = field[c] != 0
+        assert np.allclose(x[c][occ_sites], psi[c][occ_sites], rtol=1e-12, atol=1e-13)

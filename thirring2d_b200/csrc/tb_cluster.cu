@@ -109,11 +109,12 @@ __device__ __forceinline__ void push_rows(const double2 (&v)[TT][TX], int hset, 
   }
 }
 
-template <int NX, int CS, bool DAG, bool HAS_MU>
+template <int NX, int CS, bool DAG, bool HAS_MU, bool MASKED>
 __global__ void __launch_bounds__(NTHREADS, 1)
 cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, const double2 *__restrict__ W0g,
-                  const double2 *__restrict__ W1g, const double *__restrict__ mass, const double *__restrict__ emu,
-                  const double *__restrict__ emmu, const TbCgState s, const int C, const int c_first) {
+                  const double2 *__restrict__ W1g, const double *__restrict__ mass, const double *__restrict__ msite,
+                  const double *__restrict__ emu, const double *__restrict__ emmu, const TbCgState s, const int C,
+                  const int c_first) {
   using G = Slab<NX>;
   constexpr int LT = G::LT, NGX = G::NGX, NT = CS * LT;
   static_assert(CS >= 2 && CS <= 16, "slot tables hold 16 ranks");
@@ -175,6 +176,7 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   }
   double2 r[TT][TX], p[TT][TX];
   double rr = 0.0;
+  uint32_t occ = 0;   // family B: occupied sites of the tile (identity rows, vec_ops.c:130)
 #pragma unroll
   for (int i = 0; i < TT; i++)
 #pragma unroll
@@ -185,6 +187,7 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
       rr = fma(r[i][j].x, r[i][j].x, rr);
       rr = fma(r[i][j].y, r[i][j].y, rr);
       Fp[(t0 + i) * NX + j * NGX + g] = p[i][j];
+      if (MASKED && msite[gs * C + c] != m) occ |= 1u << (i * TX + j);
     }
   // every CTA of the cluster is running before anyone stores into a peer's shared memory
   cluster_arrive();
@@ -207,8 +210,8 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
       // barrier); the first row of the slab waits for its hop from the halo row.
       double2 mp[TT][TX];
       double pq = 0.0;
-      tile_apply_wt<NX, false, HAS_MU>(
-          p, Fp, p_dn, p_up, top, xaddr, t0, g, m, e_p, e_m,
+      tile_apply_wt<NX, false, HAS_MU, MASKED>(
+          p, Fp, p_dn, p_up, top, xaddr, t0, g, m, occ, e_p, e_m,
           [&](int i, int j, const double2 o) {
             mp[i][j] = o;
             if (!(i == 0 && top)) {
@@ -247,8 +250,8 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
           rr = fma(r[i][j].x, r[i][j].x, rr);
           rr = fma(r[i][j].y, r[i][j].y, rr);
         };
-        tile_apply_wt<NX, true, HAS_MU>(
-            mp, Fm, m_dn, m_up, top, xaddr, t0, g, m, e_m, e_p,
+        tile_apply_wt<NX, true, HAS_MU, MASKED>(
+            mp, Fm, m_dn, m_up, top, xaddr, t0, g, m, occ, e_m, e_p,
             [&](int i, int j, const double2 o) {
               if (i < TT / 2) qh[i % (TT / 2)][j] = o;
               else consume(i, j, o);
@@ -265,8 +268,8 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
       } else {
         // ---- M~ = M (REF_COMPAT): alpha needs <p, q> of the whole lattice, q is kept
         double2 q[TT][TX];
-        tile_apply_wt<NX, false, HAS_MU>(
-            mp, Fm, m_dn, m_up, top, xaddr, t0, g, m, e_p, e_m, [&](int i, int j, const double2 o) { q[i][j] = o; },
+        tile_apply_wt<NX, false, HAS_MU, MASKED>(
+            mp, Fm, m_dn, m_up, top, xaddr, t0, g, m, occ, e_p, e_m, [&](int i, int j, const double2 o) { q[i][j] = o; },
             [] { cluster_wait(); });
         if (top) tile_fixup_dn<NX, false, HAS_MU>(q[0], m_dn, xaddr, g, e_m);
 #pragma unroll
@@ -343,10 +346,11 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
 template <int NX, int CS>
 struct ClusterLaunch {
   using Kern = void (*)(const double2 *, double2 *, const double2 *, const double2 *, const double *, const double *,
-                        const double *, const TbCgState, const int, const int);
-  static Kern pick(bool dag, bool has_mu) {
-    if (dag) return has_mu ? cluster_cg_kernel<NX, CS, true, true> : cluster_cg_kernel<NX, CS, true, false>;
-    return has_mu ? cluster_cg_kernel<NX, CS, false, true> : cluster_cg_kernel<NX, CS, false, false>;
+                        const double *, const double *, const TbCgState, const int, const int);
+  static Kern pick(bool dag, bool has_mu, bool masked = false) {
+    if (masked) return has_mu ? cluster_cg_kernel<NX, CS, true, true, true> : cluster_cg_kernel<NX, CS, true, false, true>;
+    if (dag) return has_mu ? cluster_cg_kernel<NX, CS, true, true, false> : cluster_cg_kernel<NX, CS, true, false, false>;
+    return has_mu ? cluster_cg_kernel<NX, CS, false, true, false> : cluster_cg_kernel<NX, CS, false, false, false>;
   }
   static int config(Kern kern, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, int nclusters, cudaStream_t st) {
     TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Slab<NX>::SMEM));
@@ -378,13 +382,13 @@ struct ClusterLaunch {
     return n;
   }
   static int launch(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st) {
-    Kern kern = pick(tb_conj_is_dagger(ctx), ctx->has_mu);
+    Kern kern = pick(tb_conj_is_dagger(ctx), ctx->has_mu, ctx->msite != nullptr);
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
     TB_CHECK(config(kern, &cfg, attr, n, st));
     TB_CUDA(cudaLaunchKernelEx(&cfg, kern, b, x, (const double2 *)ctx->W0, (const double2 *)ctx->W1,
-                               (const double *)ctx->d_mass, (const double *)ctx->d_emu, (const double *)ctx->d_emmu,
-                               ctx->cg, ctx->C, c0));
+                               (const double *)ctx->d_mass, (const double *)ctx->msite, (const double *)ctx->d_emu,
+                               (const double *)ctx->d_emmu, ctx->cg, ctx->C, c0));
     ctx->launches++;
     return TB_OK;
   }
@@ -411,7 +415,10 @@ int tb_cluster_capacity(tb_ctx *ctx) {
   return cap;
 }
 
-bool tb_cluster_supported(tb_ctx *ctx) { return ctx->msite == nullptr && tb_cluster_capacity(ctx) > 0; }
+bool tb_cluster_supported(tb_ctx *ctx) {
+  if (ctx->msite && !tb_conj_is_dagger(ctx)) return false;   // family B (occupation mask) needs M~ = M^T
+  return tb_cluster_capacity(ctx) > 0;
+}
 
 int tb_run_cg_cluster_slice(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st) {
   if (b == x) {

@@ -104,10 +104,12 @@ constexpr int TM_X = 0, TM_ROW = 64, TM_W1M = 192, TM_W0M = 224, TM_SPAN = 240, 
 //   epi(i, j, value)   receives every finished site (i, j compile-time after unrolling): the caller stores it,
 //                      publishes it or folds it into the CG update at once, so no output tile need stay live
 //   mid()     runs between rows 3 and 4; rowup is first read after it (a cluster kernel waits for its halos there)
-template <int NX, bool DAG, bool HAS_MU, typename Epi, typename Mid>
+//   MASKED    family B (vec_ops.c:107,130): bit i*2+j of occ set = occupied site = identity row (mass 1; its links
+//             are already zero)
+template <int NX, bool DAG, bool HAS_MU, bool MASKED, typename Epi, typename Mid>
 __device__ __forceinline__ void tile_apply_wt(const double2 (&f)[8][2], const double2 *F, const double2 *rowdn,
                                               const double2 *rowup, bool skip_dn, uint32_t wb, int t0, int g,
-                                              double m, double af, double ab, Epi epi, Mid mid) {
+                                              double m, uint32_t occ, double af, double ab, Epi epi, Mid mid) {
   constexpr int TX = 2, TT = 8;
   constexpr int SF = DAG ? -1 : 1;
   constexpr int SB = -SF;
@@ -145,7 +147,8 @@ __device__ __forceinline__ void tile_apply_wt(const double2 (&f)[8][2], const do
       const double2 dn = (i == 0) ? fdn[j] : f[(i + TT - 1) % TT][j];
       const double2 rt = (j == TX - 1) ? fR : f[i][(j + 1) % TX];
       const double2 lf = (j == 0) ? fL : f[i][(j + TX - 1) % TX];
-      double2 o = make_double2(m * f[i][j].x, m * f[i][j].y);   // hmc.c:137-180
+      const double ms = (MASKED && ((occ >> (i * TX + j)) & 1u)) ? 1.0 : m;
+      double2 o = make_double2(ms * f[i][j].x, ms * f[i][j].y);   // hmc.c:137-180
       if (HAS_MU) {
         hop_acc<SF>(o, make_double2(w0c.x * af, w0c.y * af), up);
         hopc_acc<SB>(o, make_double2(w0m[j].x * ab, w0m[j].y * ab), dn);

@@ -343,11 +343,12 @@ struct ResidentWtCfg {
   static_assert(NWARPS == 8, "two warps per TMEM lane quarter; block_sum8");
 };
 
-template <int NT, int NX, bool DAG, bool HAS_MU>
+template <int NT, int NX, bool DAG, bool HAS_MU, bool MASKED>
 __global__ void __launch_bounds__(ResidentWtCfg<NT, NX>::NTHREADS, 1)
 resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, const double2 *__restrict__ W0g,
-                   const double2 *__restrict__ W1g, const double *__restrict__ mass, const double *__restrict__ emu,
-                   const double *__restrict__ emmu, const TbCgState s, const int C, const int c_first) {
+                   const double2 *__restrict__ W1g, const double *__restrict__ mass, const double *__restrict__ msite,
+                   const double *__restrict__ emu, const double *__restrict__ emmu, const TbCgState s, const int C,
+                   const int c_first) {
   using Cfg = ResidentWtCfg<NT, NX>;
   constexpr int V = Cfg::V, NWARPS = Cfg::NWARPS, TX = 2, TT = 8, NG = NX / TX;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -394,6 +395,7 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
   }
   double2 r[TT][TX], p[TT][TX];
   double rr = 0.0;
+  uint32_t occ = 0;   // family B: occupied sites of the tile (identity rows, vec_ops.c:130)
 #pragma unroll
   for (int i = 0; i < TT; i++)
 #pragma unroll
@@ -404,6 +406,7 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
       rr = fma(r[i][j].x, r[i][j].x, rr);
       rr = fma(r[i][j].y, r[i][j].y, rr);
       Fp[(t0 + i) * NX + j * NG + g] = p[i][j];
+      if (MASKED && msite[(size_t)k * C + c] != m) occ |= 1u << (i * TX + j);
     }
   rr = block_sum8(rr, scrA);   // hmc.c:354-356; its barrier publishes p
   const double rr_init = rr;
@@ -418,8 +421,8 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
       // passed the ||r||^2 barrier), and <p, M^dagger M p> = |M p|^2 is accumulated on the way
       double2 mp[TT][TX];
       double pq = 0.0;
-      tile_apply_wt<NX, false, HAS_MU>(
-          p, Fp, Fp + tm * NX, Fp + te * NX, false, xaddr, t0, g, m, e_p, e_m,
+      tile_apply_wt<NX, false, HAS_MU, MASKED>(
+          p, Fp, Fp + tm * NX, Fp + te * NX, false, xaddr, t0, g, m, occ, e_p, e_m,
           [&](int i, int j, const double2 o) {
             mp[i][j] = o;
             Fm[(t0 + i) * NX + j * NG + g] = o;
@@ -437,8 +440,8 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
         // alpha is known before q = M^dagger Mp exists (hmc.c:367,371): q is consumed site by site,
         // r -= alpha q and ||r||^2 (hmc.c:374-379), and never stored
         a = rr_old / pq;
-        tile_apply_wt<NX, true, HAS_MU>(
-            mp, Fm, Fm + tm * NX, Fm + te * NX, false, xaddr, t0, g, m, e_m, e_p,
+        tile_apply_wt<NX, true, HAS_MU, MASKED>(
+            mp, Fm, Fm + tm * NX, Fm + te * NX, false, xaddr, t0, g, m, occ, e_m, e_p,
             [&](int i, int j, const double2 o) {
               r[i][j].x = fma(-a, o.x, r[i][j].x);
               r[i][j].y = fma(-a, o.y, r[i][j].y);
@@ -448,8 +451,8 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
             [] {});
       } else {
         double2 q[TT][TX];
-        tile_apply_wt<NX, false, HAS_MU>(
-            mp, Fm, Fm + tm * NX, Fm + te * NX, false, xaddr, t0, g, m, e_p, e_m,
+        tile_apply_wt<NX, false, HAS_MU, MASKED>(
+            mp, Fm, Fm + tm * NX, Fm + te * NX, false, xaddr, t0, g, m, occ, e_p, e_m,
             [&](int i, int j, const double2 o) {
               q[i][j] = o;
               pq = fma(p[i][j].x, o.x, pq);   // hmc.c:368-370
@@ -515,12 +518,13 @@ template <int NT, int NX>
 int launch_resident_wt(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st) {
   using Cfg = ResidentWtCfg<NT, NX>;
   const bool dag = tb_conj_is_dagger(ctx);
-  auto kern = resident_wt_kernel<NT, NX, false, false>;
-  if (dag) kern = ctx->has_mu ? resident_wt_kernel<NT, NX, true, true> : resident_wt_kernel<NT, NX, true, false>;
-  else if (ctx->has_mu) kern = resident_wt_kernel<NT, NX, false, true>;
+  auto kern = resident_wt_kernel<NT, NX, false, false, false>;
+  if (ctx->msite) kern = ctx->has_mu ? resident_wt_kernel<NT, NX, true, true, true> : resident_wt_kernel<NT, NX, true, false, true>;
+  else if (dag) kern = ctx->has_mu ? resident_wt_kernel<NT, NX, true, true, false> : resident_wt_kernel<NT, NX, true, false, false>;
+  else if (ctx->has_mu) kern = resident_wt_kernel<NT, NX, false, true, false>;
   TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-  kern<<<n, Cfg::NTHREADS, Cfg::SMEM, st>>>(b, x, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu, ctx->cg, ctx->C,
-                                            c0);
+  kern<<<n, Cfg::NTHREADS, Cfg::SMEM, st>>>(b, x, ctx->W0, ctx->W1, ctx->d_mass, ctx->msite, ctx->d_emu, ctx->d_emmu,
+                                            ctx->cg, ctx->C, c0);
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
   return TB_OK;
@@ -549,7 +553,10 @@ int launch_resident(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cu
 }  // namespace
 
 bool tb_resident_supported(const tb_ctx *ctx) {
-  return ctx->nranks == 1 && ctx->msite == nullptr && ctx->nt == ctx->nx && (ctx->nt == 16 || ctx->nt == 32 || ctx->nt == 64);
+  if (ctx->nranks != 1 || ctx->nt != ctx->nx) return false;
+  // family B (occupation mask): the 64^2 kernel with the links in tensor memory handles it, for M~ = M^T
+  if (ctx->msite) return ctx->nt == 64 && tb_conj_is_dagger(ctx) && ctx->resident_x_tmem && ctx->tune_tt == 0;
+  return ctx->nt == 16 || ctx->nt == 32 || ctx->nt == 64;
 }
 
 // One kernel launch per (sub-)batch of chains [c0, c0+n).  The tile shape per thread is a tuning knob

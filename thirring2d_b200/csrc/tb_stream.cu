@@ -78,57 +78,51 @@ dslash_kernel(const double2 *__restrict__ in, const double2 *in_prev, const doub
       w0m = W0[(size_t)(t0 - 1) * R + j];
     }
     double2 pc = in[t0 * R + j];
-    // one row of the march; without per-row guards (tile entirely inside the lattice) the TT rows are one basic
-    // block and the loads of the following rows are issued ahead of the arithmetic
-    auto do_row = [&](const int t) {
-      const size_t row = t * R;
-      double2 pp;
-      if (SLAB) pp = (t + 1 == g.nt) ? ld_halo<SLAB>(&in_next[j]) : in[row + R + j];
-      else pp = *((t + 1 == g.nt) ? &in_next[j] : &in[row + R + j]);
-      const double2 pxp = in[row + jp];
-      const double2 pxm = in[row + jm];
-      const double2 w0c = W0[row + j];
-      const double2 w1c = W1[row + j];
-      const double2 w1m = W1[row + jm];
-      // hops: +af W0(n) psi(n+t) - ab conj(W0(n-t)) psi(n-t) + W1(n) psi(n+x) - conj(W1(n-x)) psi(n-x)
-      const double fr = w0c.x * af, fi = w0c.y * af;
-      const double br = w0m.x * ab, bi = w0m.y * ab;
-      double hr = fr * pp.x - fi * pp.y;
-      double hi = fr * pp.y + fi * pp.x;
-      hr -= br * pm.x + bi * pm.y;
-      hi -= br * pm.y - bi * pm.x;
-      hr += w1c.x * pxp.x - w1c.y * pxp.y;
-      hi += w1c.x * pxp.y + w1c.y * pxp.x;
-      hr -= w1m.x * pxm.x + w1m.y * pxm.y;
-      hi -= w1m.x * pxm.y - w1m.y * pxm.x;
-      // family B (vec_ops.c:107,130): an occupied site is an identity row -> per-site mass, links already masked
-      const double ms = msite ? msite[row + j] : m;
-      double2 o;
-      if (DAG) {
-        o.x = ms * pc.x - hr;
-        o.y = ms * pc.y - hi;
-      } else {
-        o.x = ms * pc.x + hr;
-        o.y = ms * pc.y + hi;
-      }
-      out[row + j] = o;
-      if (DOT) {
-        if (aux) {
-          const double2 a = aux[row + j];
-          acc += a.x * o.x + a.y * o.y;
-        } else {
-          acc += o.x * o.x + o.y * o.y;   // |out|^2 (fused variant: <p, M^dagger M p> = |M p|^2)
-        }
-      }
-      pm = pc;
-      pc = pp;
-      w0m = w0c;
-    };
-    if (t0 + TT <= g.nt) {
 #pragma unroll
-      for (int i = 0; i < TT; i++) do_row(t0 + i);
-    } else {
-      for (int t = t0; t < g.nt; t++) do_row(t);
+    for (int i = 0; i < TT; i++) {
+      const int t = t0 + i;
+      if (t < g.nt) {
+        const size_t row = t * R;
+        const double2 pp = (t + 1 == g.nt) ? ld_halo<SLAB>(&in_next[j]) : in[row + R + j];
+        const double2 pxp = in[row + jp];
+        const double2 pxm = in[row + jm];
+        const double2 w0c = W0[row + j];
+        const double2 w1c = W1[row + j];
+        const double2 w1m = W1[row + jm];
+        // hops: +af W0(n) psi(n+t) - ab conj(W0(n-t)) psi(n-t) + W1(n) psi(n+x) - conj(W1(n-x)) psi(n-x)
+        const double fr = w0c.x * af, fi = w0c.y * af;
+        const double br = w0m.x * ab, bi = w0m.y * ab;
+        double hr = fr * pp.x - fi * pp.y;
+        double hi = fr * pp.y + fi * pp.x;
+        hr -= br * pm.x + bi * pm.y;
+        hi -= br * pm.y - bi * pm.x;
+        hr += w1c.x * pxp.x - w1c.y * pxp.y;
+        hi += w1c.x * pxp.y + w1c.y * pxp.x;
+        hr -= w1m.x * pxm.x + w1m.y * pxm.y;
+        hi -= w1m.x * pxm.y - w1m.y * pxm.x;
+        // family B (vec_ops.c:107,130): an occupied site is an identity row -> per-site mass, links already masked
+        const double ms = msite ? msite[row + j] : m;
+        double2 o;
+        if (DAG) {
+          o.x = ms * pc.x - hr;
+          o.y = ms * pc.y - hi;
+        } else {
+          o.x = ms * pc.x + hr;
+          o.y = ms * pc.y + hi;
+        }
+        out[row + j] = o;
+        if (DOT) {
+          if (aux) {
+            const double2 a = aux[row + j];
+            acc += a.x * o.x + a.y * o.y;
+          } else {
+            acc += o.x * o.x + o.y * o.y;   // |out|^2 (fused variant: <p, M^dagger M p> = |M p|^2)
+          }
+        }
+        pm = pc;
+        pc = pp;
+        w0m = w0c;
+      }
     }
   }
   if (DOT) reduce_finalize<MASKED ? FIN_PQ : FIN_DOT, SLAB, TB_RED_PQ>(acc, g, s, sl, b, red);
@@ -150,23 +144,21 @@ axpy_norm_kernel(double2 *__restrict__ x, double2 *__restrict__ r, const double2
     const size_t R = (size_t)g.R;
     const size_t j = (size_t)b.x * g.C + b.c;
     const int t0 = b.ttile * TT;
-    auto do_row = [&](const int t) {
-      const size_t k = t * R + j;
-      double2 xv = x[k], rv = r[k];
-      const double2 pv = p[k], qv = q[k];
-      xv.x += a * pv.x;
-      xv.y += a * pv.y;
-      rv.x -= a * qv.x;
-      rv.y -= a * qv.y;
-      x[k] = xv;
-      r[k] = rv;
-      acc += rv.x * rv.x + rv.y * rv.y;
-    };
-    if (t0 + TT <= g.nt) {
 #pragma unroll
-      for (int i = 0; i < TT; i++) do_row(t0 + i);
-    } else {
-      for (int t = t0; t < g.nt; t++) do_row(t);
+    for (int i = 0; i < TT; i++) {
+      const int t = t0 + i;
+      if (t < g.nt) {
+        const size_t k = t * R + j;
+        double2 xv = x[k], rv = r[k];
+        const double2 pv = p[k], qv = q[k];
+        xv.x += a * pv.x;
+        xv.y += a * pv.y;
+        rv.x -= a * qv.x;
+        rv.y -= a * qv.y;
+        x[k] = xv;
+        r[k] = rv;
+        acc += rv.x * rv.x + rv.y * rv.y;
+      }
     }
   }
   reduce_finalize<FIN_RR, SLAB, TB_RED_RR>(acc, g, s, sl, b, red);
@@ -216,46 +208,42 @@ dslash_axpy_norm_kernel(const double2 *__restrict__ in, const double2 *in_prev, 
       w0m = W0[(size_t)(t0 - 1) * R + j];
     }
     double2 pc = in[t0 * R + j];
-    auto do_row = [&](const int t) {
-      const size_t row = t * R;
-      double2 pp;
-      if (SLAB) pp = (t + 1 == g.nt) ? ld_halo<SLAB>(&in_next[j]) : in[row + R + j];
-      else pp = *((t + 1 == g.nt) ? &in_next[j] : &in[row + R + j]);
-      const double2 pxp = in[row + jp];
-      const double2 pxm = in[row + jm];
-      const double2 w0c = W0[row + j];
-      const double2 w1c = W1[row + j];
-      const double2 w1m = W1[row + jm];
-      const double2 pv = p[row + j];
-      double2 xv = x[row + j], rv = r[row + j];
-      const double fr = w0c.x * af, fi = w0c.y * af;
-      const double br = w0m.x * ab, bi = w0m.y * ab;
-      double hr = fr * pp.x - fi * pp.y;
-      double hi = fr * pp.y + fi * pp.x;
-      hr -= br * pm.x + bi * pm.y;
-      hi -= br * pm.y - bi * pm.x;
-      hr += w1c.x * pxp.x - w1c.y * pxp.y;
-      hi += w1c.x * pxp.y + w1c.y * pxp.x;
-      hr -= w1m.x * pxm.x + w1m.y * pxm.y;
-      hi -= w1m.x * pxm.y - w1m.y * pxm.x;
-      const double ms = msite ? msite[row + j] : m;
-      const double qx = ms * pc.x - hr, qy = ms * pc.y - hi;   // q = M^dagger Mp
-      xv.x += a * pv.x;
-      xv.y += a * pv.y;
-      rv.x -= a * qx;
-      rv.y -= a * qy;
-      x[row + j] = xv;
-      r[row + j] = rv;
-      acc += rv.x * rv.x + rv.y * rv.y;
-      pm = pc;
-      pc = pp;
-      w0m = w0c;
-    };
-    if (t0 + TT <= g.nt) {
 #pragma unroll
-      for (int i = 0; i < TT; i++) do_row(t0 + i);
-    } else {
-      for (int t = t0; t < g.nt; t++) do_row(t);
+    for (int i = 0; i < TT; i++) {
+      const int t = t0 + i;
+      if (t < g.nt) {
+        const size_t row = t * R;
+        const double2 pp = (t + 1 == g.nt) ? ld_halo<SLAB>(&in_next[j]) : in[row + R + j];
+        const double2 pxp = in[row + jp];
+        const double2 pxm = in[row + jm];
+        const double2 w0c = W0[row + j];
+        const double2 w1c = W1[row + j];
+        const double2 w1m = W1[row + jm];
+        const double2 pv = p[row + j];
+        double2 xv = x[row + j], rv = r[row + j];
+        const double fr = w0c.x * af, fi = w0c.y * af;
+        const double br = w0m.x * ab, bi = w0m.y * ab;
+        double hr = fr * pp.x - fi * pp.y;
+        double hi = fr * pp.y + fi * pp.x;
+        hr -= br * pm.x + bi * pm.y;
+        hi -= br * pm.y - bi * pm.x;
+        hr += w1c.x * pxp.x - w1c.y * pxp.y;
+        hi += w1c.x * pxp.y + w1c.y * pxp.x;
+        hr -= w1m.x * pxm.x + w1m.y * pxm.y;
+        hi -= w1m.x * pxm.y - w1m.y * pxm.x;
+        const double ms = msite ? msite[row + j] : m;
+        const double qx = ms * pc.x - hr, qy = ms * pc.y - hi;   // q = M^dagger Mp
+        xv.x += a * pv.x;
+        xv.y += a * pv.y;
+        rv.x -= a * qx;
+        rv.y -= a * qy;
+        x[row + j] = xv;
+        r[row + j] = rv;
+        acc += rv.x * rv.x + rv.y * rv.y;
+        pm = pc;
+        pc = pp;
+        w0m = w0c;
+      }
     }
   }
   reduce_finalize<FIN_RR, SLAB, TB_RED_RR>(acc, g, s, sl, b, red);
@@ -284,19 +272,17 @@ xpay_kernel(double2 *__restrict__ p, const double2 *__restrict__ r, const TbGeom
     const size_t R = (size_t)g.R;
     const size_t j = (size_t)b.x * g.C + b.c;
     const int t0 = b.ttile * TT;
-    auto do_row = [&](const int t) {
-      const size_t k = t * R + j;
-      const double2 rv = r[k];
-      double2 pv = p[k];
-      pv.x = rv.x + be * pv.x;
-      pv.y = rv.y + be * pv.y;
-      p[k] = pv;
-    };
-    if (t0 + TT <= g.nt) {
 #pragma unroll
-      for (int i = 0; i < TT; i++) do_row(t0 + i);
-    } else {
-      for (int t = t0; t < g.nt; t++) do_row(t);
+    for (int i = 0; i < TT; i++) {
+      const int t = t0 + i;
+      if (t < g.nt) {
+        const size_t k = t * R + j;
+        const double2 rv = r[k];
+        double2 pv = p[k];
+        pv.x = rv.x + be * pv.x;
+        pv.y = rv.y + be * pv.y;
+        p[k] = pv;
+      }
     }
   }
   if (SLAB) slab_signal_done(sl, TB_FLAG_PREADY, -1, seq);
@@ -548,13 +534,10 @@ int tb_choose_geom(tb_ctx *ctx) {
   g.nxtiles = (ctx->nx + bx - 1) / bx;
   g.Cpad = g.nctiles * bc;
   int tt = ctx->tune_tt;
+  if (const char *e = getenv("TB_FORCE_ROWS")) tt = atoi(e);   // development override, wins over tb_set_tuning
   if (tt != 1 && tt != 2 && tt != 4 && tt != 8 && tt != 16) {
-    // long marches amortise the t-halo rows, but the grid has to be several waves of 148 SMs x 4 resident blocks
-    // for the tail of the last wave not to show: measured on 256^2 x 64, 512^2 x 16, 1024^2 x 4 and 2048^2, 8 rows
-    // (2048 blocks) beat 16 (1024 blocks) by 5-9 % per kernel
     tt = 16;
     const long nb1 = (long)g.nctiles * g.nxtiles;
-    while (tt > 8 && nb1 * ((ctx->nt + tt - 1) / tt) < 14L * TB_NUM_SMS_B200) tt >>= 1;
     while (tt > 1 && nb1 * ((ctx->nt + tt - 1) / tt) < 6L * TB_NUM_SMS_B200) tt >>= 1;
   }
   g.tt = tt;
