@@ -543,6 +543,14 @@ int launch_resident(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cu
   else { if (ctx->has_mu) { PICK(false, true) } else { PICK(false, false) } }
 #undef PICK
   TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+  if (getenv("TB_DEBUG")) {
+    int per_sm = -1;
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kern);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, Cfg::NTHREADS, Cfg::SMEM);
+    fprintf(stderr, "resident kernel %dx%d tile %dx%d x_tmem=%d: %d CTAs/SM by occupancy, %d threads, %d regs, %zu B smem\n", NT, NX,
+            TT, TX, (int)xt, per_sm, Cfg::NTHREADS, fa.numRegs, (size_t)Cfg::SMEM);
+  }
   kern<<<n, Cfg::NTHREADS, Cfg::SMEM, st>>>(b, x, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu, ctx->xw,
                                             ctx->cg, ctx->C, c0);
   ctx->launches++;
