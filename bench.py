@@ -12,7 +12,7 @@ data-path collective (weak scaling: 256 chains per GPU).
 
   value      whole-job applies/s, inputs resident in HBM, device time of the K solves by CUDA events (the L2 flush
              between steps excluded), max over ranks
-  e2e        the same metric through the reference-facing host-buffer C-ABI call (tb_set_gauge + tb_cg) with
+  e2e        the same metric through the reference-facing host-buffer C-ABI call (tb_cg_gauge = tb_set_gauge + tb_cg) with
              pinned HOST buffers; H2D of links and sources and D2H of the solutions inside the timed region
   roofline   CG iteration (the 4 fused streaming kernels, or the single resident kernel): algorithmic
              288 B/site/iteration over the device time of the timed solves
@@ -251,9 +251,8 @@ def gpu_arm(args):
     ms_total = e0.elapsed_time(e1)
 
     # e2e: the host-buffer C-ABI entry points a reference-side caller binds
-    def e2e_step():
-        ctx.set_gauge_host_ptr(A_host.data_ptr())
-        ctx.cg_host_ptr(b_host.data_ptr(), x_host.data_ptr())
+    def e2e_step():   # new angles + solve, as at every leapfrog step of momentum_step (hmc.c:504-516)
+        ctx.cg_gauge_host_ptr(A_host.data_ptr(), b_host.data_ptr(), x_host.data_ptr())
 
     for _ in range(2):
         e2e_step()

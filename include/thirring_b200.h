@@ -104,6 +104,12 @@ int tb_apply(tb_ctx *ctx, int op, const double *in_host, double *out_host);
  * status / iters / rr may be NULL, else arrays of nchains. */
 int tb_cg(tb_ctx *ctx, const double *b_host, double *x_host, int *status, int *iters, double *rr);
 
+/* tb_set_gauge + tb_cg in one call (what momentum_step does at every leapfrog step: new angles, then the solve,
+ * hmc.c:504-516).  Links and sources travel per sub-batch of chains, so the first solves start while the rest
+ * of the input is still crossing PCIe. */
+int tb_cg_gauge(tb_ctx *ctx, const double *A_host, const double *b_host, double *x_host, int *status, int *iters,
+                double *rr);
+
 /* fm_invert_cg (hmc.c:408-414), batched: x = (M~ M)^-1 M~ v. */
 int tb_invert(tb_ctx *ctx, const double *v_host, double *x_host, int *status, int *iters, double *rr);
 

@@ -236,3 +236,22 @@ def test_runs_are_deterministic():
             x1, i1 = ctx.fmdm_invert_cg(b)
             x2, i2 = ctx.fmdm_invert_cg(b)
             assert np.array_equal(x1, x2) and np.array_equal(i1.iters, i2.iters)
+
+
+@pytest.mark.parametrize("nt,nx,n", [(64, 64, 150), (32, 32, 7), (128, 128, 5), (16, 32, 40)])
+def test_cg_gauge_equals_set_gauge_then_cg(nt, nx, n):
+    """tb_cg_gauge (gauge upload interleaved with the sources per sub-batch of chains) is bitwise tb_set_gauge + tb_cg,
+    on the on-chip solvers and on the streaming fallback (16 x 32)."""
+    rng = np.random.default_rng(nt + n)
+    A = random_gauge(rng, n, nt, nx)
+    A2 = random_gauge(rng, n, nt, nx)
+    b = random_vector(rng, n, nt, nx)
+    with tb.Context(nt, nx, n, tb.MODE_ADJOINT, m=0.4, mu=0.05) as ctx:
+        ctx.set_gauge(A2)                       # stale links that the combined call must replace
+        x1, i1 = ctx.fmdm_invert_cg_with_gauge(A, b)
+        ctx.set_gauge(A)
+        x2, i2 = ctx.fmdm_invert_cg(b)
+        x3 = ctx.fmdm_mul(x1)                   # the links the combined call left behind are A's
+    assert np.array_equal(x1, x2) and np.array_equal(i1.iters, i2.iters)
+    assert np.all(i1.status == tb.CG_CONVERGED)
+    assert_close(x3, b, 1e-11, "M~M x = b")

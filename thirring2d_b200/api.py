@@ -200,6 +200,26 @@ class Context:
     def cg_host_ptr(self, b_ptr: int, x_ptr: int):
         check(self.lib.tb_cg(self._h, C.c_void_p(b_ptr), C.c_void_p(x_ptr), None, None, None), "tb_cg")
 
+    def cg_gauge_host_ptr(self, a_ptr: int, b_ptr: int, x_ptr: int):
+        check(self.lib.tb_cg_gauge(self._h, C.c_void_p(a_ptr), C.c_void_p(b_ptr), C.c_void_p(x_ptr), None, None, None),
+              "tb_cg_gauge")
+
+    def fmdm_invert_cg_with_gauge(self, A, b):
+        """set_gauge(A) followed by fmdm_invert_cg(b), uploads interleaved per sub-batch of chains."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        if A.ndim == 3:
+            A = A[None]
+        assert A.shape == (self.nchains, self.nt, self.nx, 2), A.shape
+        squeeze = np.ndim(b) == 2
+        b = self._vec(b)
+        x = np.empty_like(b)
+        st = np.empty(self.nchains, dtype=np.int32)
+        it = np.empty(self.nchains, dtype=np.int32)
+        rr = np.empty(self.nchains, dtype=np.float64)
+        check(self.lib.tb_cg_gauge(self._h, A.ctypes.data, b.ctypes.data, x.ctypes.data, st.ctypes.data_as(_ip),
+                                   it.ctypes.data_as(_ip), rr.ctypes.data_as(_dp)), "tb_cg_gauge")
+        return (x[0] if squeeze else x), CGInfo(st, it, rr)
+
     def set_gauge_host_ptr(self, a_ptr: int):
         check(self.lib.tb_set_gauge(self._h, C.c_void_p(a_ptr)), "tb_set_gauge")
 

@@ -492,19 +492,23 @@ extern "C" int tb_re_dot_dev(tb_ctx *ctx, const double *d_a, const double *d_b, 
 // re-layout -> D2H of one sub-batch overlap the copies and kernels of the others (pinned host buffers make the
 // copies asynchronous; pageable ones still work, without overlap).
 
+// H2D + re-layout of the chains of sub-batch s on its stream
+static int upload_slice(tb_ctx *ctx, int s, const double *host, double2 *d_vec) {
+  int c0, n;
+  sub_range(ctx, s, &c0, &n);
+  if (n == 0) return TB_OK;
+  const size_t off = (size_t)c0 * ctx->V;  // double2 elements
+  double2 *stg = (double2 *)ctx->stage + off;
+  double2 *dst = ctx->C == 1 ? d_vec : stg;
+  TB_CUDA(cudaMemcpyAsync(dst, (const double2 *)host + off, (size_t)n * ctx->V * sizeof(double2),
+                          cudaMemcpyHostToDevice, ctx->sub_stream[s]));
+  if (ctx->C > 1) TB_CHECK(tb_launch_pack_slice(ctx, stg, d_vec, c0, n, ctx->sub_stream[s]));
+  return TB_OK;
+}
+
 static int upload_vec(tb_ctx *ctx, const double *host, double2 *d_vec) {
   TB_CHECK(fork_subs(ctx));
-  for (int s = 0; s < ctx->nsub; s++) {
-    int c0, n;
-    sub_range(ctx, s, &c0, &n);
-    if (n == 0) continue;
-    const size_t off = (size_t)c0 * ctx->V;  // double2 elements
-    double2 *stg = (double2 *)ctx->stage + off;
-    double2 *dst = ctx->C == 1 ? d_vec : stg;
-    TB_CUDA(cudaMemcpyAsync(dst, (const double2 *)host + off, (size_t)n * ctx->V * sizeof(double2),
-                            cudaMemcpyHostToDevice, ctx->sub_stream[s]));
-    if (ctx->C > 1) TB_CHECK(tb_launch_pack_slice(ctx, stg, d_vec, c0, n, ctx->sub_stream[s]));
-  }
+  for (int s = 0; s < ctx->nsub; s++) TB_CHECK(upload_slice(ctx, s, host, d_vec));
   return TB_OK;
 }
 
@@ -600,6 +604,43 @@ static int solve_host(tb_ctx *ctx, bool with_conj, const double *b_host, double 
     TB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->last_solve_ms = ms;
   }
+  if (status || iters || rr) TB_CHECK(tb_cg_result(ctx, status, iters, rr));
+  return TB_OK;
+}
+
+// tb_set_gauge + tb_cg in one call, interleaved per sub-batch: links and sources of sub-batch s travel back to back,
+// so its solve starts after 1/nsub of the input has crossed PCIe instead of after the whole gauge field.
+extern "C" int tb_cg_gauge(tb_ctx *ctx, const double *A_host, const double *b_host, double *x_host, int *status,
+                           int *iters, double *rr) {
+  if (!ctx || !A_host || !b_host || !x_host) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->nranks > 1) { tb_set_error("tb_cg_gauge: slab contexts use tb_set_gauge + tb_cg"); return TB_EINVAL; }
+  ctx->msite = nullptr;
+  ctx->have_gauge = true;
+  const int onchip = onchip_solver(ctx);
+  if (!onchip) {   // the streaming solver works on the whole batch at once: nothing to interleave
+    TB_CHECK(tb_set_gauge(ctx, A_host));
+    return solve_host(ctx, false, b_host, x_host, status, iters, rr);
+  }
+  TB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  TB_CHECK(fork_subs(ctx));
+  // stage is shared by the two uploads of a sub-batch: the copy of b into it is ordered behind the pack of A on
+  // the same stream
+  for (int s = 0; s < ctx->nsub; s++) {
+    int c0, n;
+    sub_range(ctx, s, &c0, &n);
+    if (n == 0) continue;
+    TB_CHECK(upload_slice(ctx, s, A_host, ctx->Adev));
+    TB_CHECK(tb_launch_links_slice(ctx, ctx->Adev, c0, n, ctx->sub_stream[s]));
+    TB_CHECK(upload_slice(ctx, s, b_host, ctx->vin));
+    TB_CHECK(run_onchip_slice(ctx, onchip, ctx->vin, ctx->vout, c0, n, ctx->sub_stream[s]));
+  }
+  TB_CHECK(download_vec(ctx, ctx->vout, x_host));
+  TB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  TB_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  TB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_solve_ms = ms;
   if (status || iters || rr) TB_CHECK(tb_cg_result(ctx, status, iters, rr));
   return TB_OK;
 }

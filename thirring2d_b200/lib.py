@@ -35,6 +35,7 @@ SIGNATURES = {
     "tb_apply": (_i, [_vp, _i, _vp, _vp]),
     "tb_cg": (_i, [_vp, _vp, _vp, _ip, _ip, _dp]),
     "tb_invert": (_i, [_vp, _vp, _vp, _ip, _ip, _dp]),
+    "tb_cg_gauge": (_i, [_vp, _vp, _vp, _vp, _ip, _ip, _dp]),
     "tb_vec_doubles": (C.c_size_t, [_vp]),
     "tb_pack_dev": (_i, [_vp, _vp, _vp]),
     "tb_unpack_dev": (_i, [_vp, _vp, _vp]),
