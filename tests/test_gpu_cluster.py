@@ -153,3 +153,30 @@ def test_cluster_family_b_masked_operator(oracle, nt, nx):
         assert_close(xp[c], xo, CG_SOL_TOL, "cg_propagator")
         occ_sites = field[c] != 0
         assert np.allclose(x[c][occ_sites], psi[c][occ_sites], rtol=1e-12, atol=1e-13)
+
+
+def test_cluster_hmc_trajectory_and_measurements():
+    """The device-resident trajectory (hmc.c:671-746) on a 128^2 lattice: its 11*(nsteps/10)+1 solves run on the
+    cluster kernel; observables are finite, exactly the accepted chains move, and a reversed-sign check of dS:
+    the same trajectory replayed with the streaming solver gives the same observables to solver accuracy."""
+    nt = nx = 128
+    n = 5
+    with tb.Context(nt, nx, n, tb.MODE_ADJOINT, m=0.5, mu=0.0) as ctx:
+        ctx.hmc_set_coupling(0.3)
+        ctx.hmc_heatbath(30, seed=21)
+        assert ctx.solver_info()[0] == 2
+        A0 = ctx.get_gauge()
+        obs, acc, iters = ctx.hmc_trajectory(nsteps=10, traj_length=0.5, seed=5, traj_index=1)
+        A1 = ctx.get_gauge()
+        mag, ph = ctx.hmc_measure(nsrc=2, seed=5, meas_index=1)
+        # replay from the same start with the streaming kernels
+        ctx.set_gauge(A0)
+        ctx.set_tuning(solver=1)
+        obs_s, acc_s, iters_s = ctx.hmc_trajectory(nsteps=10, traj_length=0.5, seed=5, traj_index=1)
+    assert np.all(np.isfinite(obs)) and iters > 0
+    changed = np.abs(A1 - A0).reshape(n, -1).max(axis=1) > 0
+    assert np.array_equal(changed, acc.astype(bool))
+    assert np.all(np.isfinite(mag)) and np.all(np.isfinite(ph))
+    assert np.array_equal(acc, acc_s)
+    assert np.allclose(obs[:, :8], obs_s[:, :8], rtol=1e-9, atol=0)          # actions
+    assert np.allclose(obs[:, 8], obs_s[:, 8], rtol=0, atol=1e-6 * np.abs(obs[:, :8]).max())   # dS (a difference)
