@@ -205,6 +205,7 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
     status = TB_CG_ZERO_SOURCE;
   } else {
     cluster_arrive();   // pairs with the wait inside the first stencil (p and its halos are already published)
+    if (s.max_iter <= 1) cluster_wait();   // no iteration will run: close the barrier
     for (int k = 1; k < s.max_iter; k++) {  // hmc.c:364
       // ---- Mp = M p (hmc.c:366).  Finished sites go to Fm at once (its last readers passed the ||r||^2
       // barrier); the first row of the slab waits for its hop from the halo row.
