@@ -93,3 +93,23 @@ def test_batched_solution_equals_single_chain_solutions():
             x1, i1 = one.fmdm_invert_cg(b[c])
         assert np.array_equal(x1, x[c])          # same kernel, same per-chain arithmetic: bitwise
         assert i1.iters[0] == info.iters[c]
+
+
+@pytest.mark.parametrize("nt,nx,nchains", [(256, 256, 2), (2048, 2048, 1)])
+def test_T1_apply_matches_oracle_at_full_size(oracle, nt, nx, nchains):
+    """T1 of SURVEY 8(c) at the large lattices of BASELINE.json directly against the C oracle (a 2048^2 apply takes it
+    under a second): M, M^dagger and M~ to 1e-13 in l2 and max norm, per-chain mu."""
+    from tests.util import APPLY_TOL, assert_close, random_gauge, random_vector
+
+    rng = np.random.default_rng(nt + nchains)
+    A = random_gauge(rng, nchains, nt, nx)
+    v = random_vector(rng, nchains, nt, nx)
+    m = rng.uniform(0.05, 1.0, size=nchains)
+    mu = rng.uniform(-0.2, 0.2, size=nchains)
+    with tb.Context(nt, nx, nchains, tb.MODE_ADJOINT) as ctx:
+        ctx.set_params(m, mu)
+        ctx.set_gauge(A)
+        got_m, got_d = ctx.fm_mul(v), ctx.fm_conjugate_mul(v)
+    for c in range(nchains):
+        assert_close(got_m[c], oracle.fm_mul(v[c], A[c], m[c], mu[c]), APPLY_TOL, "M")
+        assert_close(got_d[c], oracle.fm_conjugate_mul(v[c], A[c], m[c], mu[c], tb.MODE_ADJOINT), APPLY_TOL, "M^dagger")
