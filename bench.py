@@ -520,6 +520,44 @@ def other_configs(tb, torch, dist, dev, stream, rank, world):
             pass
         out["family_b_64x64_point_source_propagators"] = fb
 
+    # configs[0]: the reference's own driver (hmc.c UNMODIFIED) with the shipped parameters, once on the CPU and once
+    # on top of the library through symbol interposition: wall clock of the whole process
+    if world == 1:
+        launcher = os.path.join(ROOT, "thirring2d_b200", "hmc_b200")
+        ref_exe = os.path.join(ROOT, "oracle", "_ref", "ref_hmc")
+        drop = {}
+        for name, so, mode, params in (
+                ("32x32_shipped_parameter_file_m100", "libhmcref_32x32_compat.so", "compat",
+                 "40\n40\n100\n0.3\n0.1\n4354365264\n"),
+                ("32x32_adjoint_m0.1_40_steps", "libhmcref_32x32_adjoint_ns40.so", "adjoint",
+                 "6\n100\n0.1\n0.3\n0.0\n4354365264\n")):   # no measure(): its test_conjugate aborts a true adjoint
+            sop = os.path.join(ROOT, "oracle", "_ref", so)
+            if not (os.path.exists(launcher) and os.path.exists(ref_exe) and os.path.exists(sop)):
+                continue
+            ntraj = int(params.split("\n")[0])
+            zero = "0\n" + params.split("\n", 1)[1]   # same start (seeding, 100 heat-bath sweeps), no trajectory
+
+            def wall(cmd, inp):
+                t0 = time.perf_counter()
+                p = subprocess.run(cmd, input=inp, capture_output=True, text=True)
+                return time.perf_counter() - t0, p
+
+            gpu_cmd, cpu_cmd = [launcher, sop, "32", "32", mode], [ref_exe, sop]
+            wall(gpu_cmd, zero)   # warm the driver / page in the library
+            tg0 = min(wall(gpu_cmd, zero)[0] for _ in range(2))
+            tg, pg = wall(gpu_cmd, params)
+            tc0 = wall(cpu_cmd, zero)[0]
+            tc, pc = wall(cpu_cmd, params)
+            drop[name] = {"trajectories": ntraj,
+                          "ms_per_trajectory_on_the_library": 1e3 * max(tg - tg0, 0.0) / ntraj,
+                          "ms_per_trajectory_reference_cpu": 1e3 * max(tc - tc0, 0.0) / ntraj,
+                          "process_seconds_on_the_library": tg, "process_seconds_reference_cpu": tc,
+                          "stdout_identical": pg.stdout == pc.stdout, "served": pg.stderr.strip().splitlines()[-1:],
+                          "note": "one chain; per-trajectory = (N-trajectory process) - (0-trajectory process), which "
+                                  "removes CUDA start-up (0.3-2 s per process) and the common heat-bath start"}
+        if drop:
+            out["unmodified_reference_driver_single_chain"] = drop
+
     # configs[3] at N = 1: 2048x2048 single lattice, streaming CG, fixed 200 iterations (the slab-decomposed
     # multi-GPU figures come from tools/slab_bench.py, profiles/scaling_*.txt)
     if world == 1:

@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "../../include/thirring_b200.h"
 #include "../../include/thirring_hmc_abi.h"
@@ -138,10 +139,20 @@ void fm_conjugate_mul(_Complex double **v_in, _Complex double **v_out, double **
 
 void fmdm_mul(_Complex double **v_in, _Complex double **v_out, double ***A) { apply(TB_OP_MDM, v_in, v_out, A); }
 
+static double now_ms(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static void solve(int with_conj, _Complex double **v_in, _Complex double **v_out, double ***A) {
   lazy_init();
+  const int trace = getenv("TB_HMC_TRACE") != NULL;
+  const double t0 = trace ? now_ms() : 0.0;
   sync_params();
+  const double t1 = trace ? now_ms() : 0.0;
   sync_gauge(A);
+  const double t2 = trace ? now_ms() : 0.0;
   const double *in = gather(v_in);
   double *out = out_buffer(v_out);
   int status = 0, iters = 0;
@@ -149,6 +160,9 @@ static void solve(int with_conj, _Complex double **v_in, _Complex double **v_out
   int rc = with_conj ? tb_invert(S.ctx, in, out, &status, &iters, &rr) : tb_cg(S.ctx, in, out, &status, &iters, &rr);
   if (rc != TB_OK) die("tb_cg");
   S.cg_calls++;
+  if (trace)
+    fprintf(stderr, "libthirring_hmc: solve %ld: params %.3f ms, gauge %.3f ms, cg %.3f ms (%d iterations)\n", S.cg_calls,
+            t1 - t0, t2 - t1, now_ms() - t2, iters);
   if (status == TB_CG_DIVERGED) { /* hmc.c:383-388 */
     printf("Cannot invert fermion matrix\n");
     exit(1);
