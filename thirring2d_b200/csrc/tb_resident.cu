@@ -49,6 +49,19 @@ __device__ __forceinline__ double block_sum8(double v, double *scratch) {
   return ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d.x + d.y));
 }
 
+// block_sum8 split at its barrier, so that independent work can sit in front of it
+__device__ __forceinline__ void block_sum8_post(double v, double *scratch) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+}
+__device__ __forceinline__ double block_sum8_total(const double *scratch) {
+  __syncthreads();
+  const double2 *s2 = reinterpret_cast<const double2 *>(scratch);
+  const double2 a = s2[0], b = s2[1], c = s2[2], d = s2[3];
+  return ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d.x + d.y));
+}
+
 // Shared-memory site index: the TX x-sites of a thread's tile live in TX separate sub-planes of a row, so
 // that for a fixed tile column j consecutive threads (x-groups) touch consecutive double2 (conflict-free
 // LDS.128 / STS.128 whatever TX is).
@@ -471,8 +484,11 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
             rr = fma(r[i][j].y, r[i][j].y, rr);
           }
       }
-      rr = block_sum8(rr, scrA);
-      tmem_x_axpy(xaddr + TM_X, p, a, k == 1);          // hmc.c:372-373
+      // ||r||^2 with x += a p (hmc.c:372-373) between the posting of the warp partial and the barrier: warps that are
+      // ahead update their tensor-memory columns instead of waiting
+      block_sum8_post(rr, scrA);
+      tmem_x_axpy(xaddr + TM_X, p, a, k == 1);
+      rr = block_sum8_total(scrA);
       iters = k;
       if (rr < s.accuracy) { status = TB_CG_CONVERGED; break; }                                        // hmc.c:381
       if (!(rr == rr) || rr / rr_init > TB_DIVERGENCE_RATIO) { status = TB_CG_DIVERGED; break; }      // hmc.c:383
