@@ -156,6 +156,11 @@ int tb_slab_connect(tb_ctx *ctx, const void *all_handles);
 /* coupling g (global hmc.c:39): Nf/g with Nf = 2 (hmc.c:28); n == 1 broadcasts, n == nchains per chain */
 int tb_hmc_set_coupling(tb_ctx *ctx, const double *g, int n);
 
+/* Global index of this context's first chain.  It enters the key of the device random-number stream (Philox keyed
+ * by seed and GLOBAL chain index), so an ensemble sharded over several GPUs draws the same numbers per chain whatever
+ * the number of shards.  Default 0. */
+int tb_hmc_set_chain_offset(tb_ctx *ctx, unsigned int first_chain);
+
 /* `sweeps` quenched heat-bath sweeps of every link (update_puregauge_hb, hmc.c:82-93; main() does 100 from
  * A = 0, hmc.c:927-929).  Random numbers: device Philox keyed by (seed, chain). */
 int tb_hmc_heatbath(tb_ctx *ctx, int sweeps, unsigned long long seed);

@@ -4,6 +4,8 @@ import io
 import os
 import re
 
+import numpy as np
+
 from thirring2d_b200.hmc_driver import banner, measurement_lines, read_parameters, trajectory_lines
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -35,3 +37,16 @@ def test_banner_matches_reference():
     out = open(os.path.join(GOLD, "hmc_32x32_shipped_5traj.stdout")).read()
     for line in banner(32, 32, 1, 100.0, 0.3, 0.1, 4354365264)[1:]:
         assert line in out, line
+
+
+def test_scan_parsing_and_summary_lines():
+    from thirring2d_b200.hmc_driver import parse_scan, summary_lines
+
+    pts = parse_scan("0.2,0.4:0.01,0.1,0.3")
+    assert pts == [(0.2, 0.01), (0.2, 0.1), (0.2, 0.3), (0.4, 0.01), (0.4, 0.1), (0.4, 0.3)]
+    cnt = np.array([4.0] * 6)
+    mean = np.arange(12, dtype=float).reshape(6, 2)
+    err = np.full((6, 2), 0.5)
+    lines = summary_lines(pts, cnt, mean, err, ["acceptance", "Condensate"])
+    assert lines[0] == "[point 0 g 0.2 m 0.01] chains 4, acceptance 0 +- 0.5, Condensate 1 +- 0.5"
+    assert len(lines) == 6 and lines[5].startswith("[point 5 g 0.4 m 0.3] chains 4, acceptance 10 +- 0.5")

@@ -265,6 +265,10 @@ class Context:
         g = np.ascontiguousarray(np.atleast_1d(np.asarray(g, dtype=np.float64)))
         check(self.lib.tb_hmc_set_coupling(self._h, g.ctypes.data_as(_dp), g.size), "tb_hmc_set_coupling")
 
+    def hmc_set_chain_offset(self, first_chain: int):
+        """Global index of this context's first chain (enters the device RNG key; see shard.chain_range)."""
+        check(self.lib.tb_hmc_set_chain_offset(self._h, int(first_chain)), "tb_hmc_set_chain_offset")
+
     def hmc_heatbath(self, sweeps=100, seed=1):
         check(self.lib.tb_hmc_heatbath(self._h, sweeps, seed), "tb_hmc_heatbath")
 

@@ -144,6 +144,7 @@ struct tb_ctx {
   cudaGraphExec_t slab_graph;
   int slab_graph_chunk;
   TbHmc hmc;
+  unsigned int hmc_chain_offset;  // global index of chain 0 (RNG key), tb_hmc_set_chain_offset
 };
 
 int tb_choose_geom(tb_ctx *ctx);

@@ -38,12 +38,13 @@ __device__ __forceinline__ double u01(unsigned int r) { return ((double)r + 0.5)
 struct RngKey {
   unsigned long long seed;
   unsigned int traj, stream;
+  unsigned int chain0;   // global index of the context's first chain (tb_hmc_set_chain_offset)
 };
 
 // (sqrt(-2 ln x1) cos(2 pi x2), sqrt(-2 ln x1) sin(2 pi x2)), hmc.c:425-426 / 490-491
 __device__ __forceinline__ double2 box_muller(size_t site, int c, const RngKey k) {
   const uint4 r = philox(make_uint4((unsigned int)site, (unsigned int)(site >> 32), k.traj, k.stream),
-                         make_uint2((unsigned int)k.seed, (unsigned int)(k.seed >> 32) ^ (unsigned int)c));
+                         make_uint2((unsigned int)k.seed, (unsigned int)(k.seed >> 32) ^ ((unsigned int)c + k.chain0)));
   const double x1 = u01(r.x), x2 = u01(r.y);
   const double rad = sqrt(-2.0 * log(x1));
   double s, co;
@@ -60,7 +61,7 @@ __global__ void fill_uniform_kernel(double *__restrict__ u, int C, RngKey k) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
     const uint4 r = philox(make_uint4(0u, 0u, k.traj, k.stream),
-                           make_uint2((unsigned int)k.seed, (unsigned int)(k.seed >> 32) ^ (unsigned int)c));
+                           make_uint2((unsigned int)k.seed, (unsigned int)(k.seed >> 32) ^ ((unsigned int)c + k.chain0)));
     u[c] = u01(r.x);
   }
 }
@@ -216,7 +217,7 @@ __global__ void heatbath_kernel(double2 *__restrict__ A, const double *__restric
     double2 a = A[i];
     for (int s = 0; s < sweeps; s++) {
       const uint4 r = philox(make_uint4((unsigned int)site, (unsigned int)(site >> 32), (unsigned int)s, k.stream),
-                             make_uint2((unsigned int)k.seed, (unsigned int)(k.seed >> 32) ^ (unsigned int)c));
+                             make_uint2((unsigned int)k.seed, (unsigned int)(k.seed >> 32) ^ ((unsigned int)c + k.chain0)));
       const double n0 = 2.0 * M_PI * u01(r.x) - M_PI, n1 = 2.0 * M_PI * u01(r.z) - M_PI;
       if (u01(r.y) < exp(nfg * (cos(n0) - cos(a.x)))) a.x = n0;
       if (u01(r.w) < exp(nfg * (cos(n1) - cos(a.y)))) a.y = n1;
@@ -337,6 +338,14 @@ extern "C" int tb_hmc_set_coupling(tb_ctx *ctx, const double *g, int n) {
   return TB_OK;
 }
 
+// Global index of this context's first chain: enters the Philox key, so an ensemble sharded over several contexts
+// (GPUs) draws the same random numbers per chain whatever the number of shards.
+extern "C" int tb_hmc_set_chain_offset(tb_ctx *ctx, unsigned int first_chain) {
+  if (!ctx) return TB_EINVAL;
+  ctx->hmc_chain_offset = first_chain;
+  return TB_OK;
+}
+
 static int dot_to(tb_ctx *ctx, const double2 *a, const double2 *b, int slot) {
   return tb_launch_dot(ctx, a, b, ctx->hmc.sums + (size_t)slot * ctx->g.Cpad);
 }
@@ -358,7 +367,7 @@ extern "C" int tb_hmc_heatbath(tb_ctx *ctx, int sweeps, unsigned long long seed)
   TB_CUDA(cudaSetDevice(ctx->device));
   TB_CHECK(hmc_alloc(ctx));
   if (!ctx->have_gauge) TB_CUDA(cudaMemsetAsync(ctx->Adev, 0, ctx->nsite * sizeof(double2), ctx->stream));  // hmc.c:915
-  const RngKey k = {seed, 0u, 7u};
+  const RngKey k = {seed, 0u, 7u, ctx->hmc_chain_offset};
   heatbath_kernel<<<ew_blocks(ctx->nsite), 256, 0, ctx->stream>>>(ctx->Adev, ctx->hmc.nf_over_g, sweeps, ctx->nsite,
                                                                  ctx->C, k);
   ctx->launches++;
@@ -408,22 +417,22 @@ extern "C" int tb_hmc_trajectory(tb_ctx *ctx, int nsteps, double traj_length, un
   TB_CHECK(links_from(ctx, ctx->Adev));
   // random_pseudofermion, hmc.c:418-436: Smdm = |xi|^2, psi = M~ xi
   if (xi_host) TB_CHECK(upload(xi_host, H.gauss));
-  else { fill_gauss_kernel<<<eb, 256, 0, st>>>(H.gauss, n, C, RngKey{seed, traj_index, 1u}); ctx->launches++; }
+  else { fill_gauss_kernel<<<eb, 256, 0, st>>>(H.gauss, n, C, RngKey{seed, traj_index, 1u, ctx->hmc_chain_offset}); ctx->launches++; }
   TB_CHECK(dot_to(ctx, H.gauss, H.gauss, 1));
   TB_CHECK(tb_launch_dslash(ctx, dag, H.gauss, H.psi, false));
   // random_momentum, hmc.c:483-499: Smom = sum p^2
   if (mom_host) TB_CHECK(upload(mom_host, H.mom));
-  else { fill_gauss_kernel<<<eb, 256, 0, st>>>(H.mom, n, C, RngKey{seed, traj_index, 2u}); ctx->launches++; }
+  else { fill_gauss_kernel<<<eb, 256, 0, st>>>(H.mom, n, C, RngKey{seed, traj_index, 2u, ctx->hmc_chain_offset}); ctx->launches++; }
   TB_CHECK(dot_to(ctx, H.mom, H.mom, 3));
   // calc_gauge_action, hmc.c:697
   TB_CHECK(gauge_action_to(ctx, ctx->Adev, 0));
   // stochastic_vector + stochastic_md_action, hmc.c:698-699: Smd = Re<st, M~ st>
   if (st_host) TB_CHECK(upload(st_host, H.st));
-  else { fill_gauss_kernel<<<eb, 256, 0, st>>>(H.st, n, C, RngKey{seed, traj_index, 3u}); ctx->launches++; }
+  else { fill_gauss_kernel<<<eb, 256, 0, st>>>(H.st, n, C, RngKey{seed, traj_index, 3u, ctx->hmc_chain_offset}); ctx->launches++; }
   TB_CHECK(tb_launch_dslash(ctx, dag, H.st, ctx->tmp, false));
   TB_CHECK(dot_to(ctx, H.st, ctx->tmp, 2));
   if (u_host) TB_CUDA(cudaMemcpyAsync(H.u, u_host, C * sizeof(double), cudaMemcpyHostToDevice, st));
-  else { fill_uniform_kernel<<<(C + 255) / 256, 256, 0, st>>>(H.u, C, RngKey{seed, traj_index, 4u}); ctx->launches++; }
+  else { fill_uniform_kernel<<<(C + 255) / 256, 256, 0, st>>>(H.u, C, RngKey{seed, traj_index, 4u, ctx->hmc_chain_offset}); ctx->launches++; }
   // new_A = A, hmc.c:703-705
   TB_CUDA(cudaMemcpyAsync(H.newA, ctx->Adev, n * sizeof(double2), cudaMemcpyDeviceToDevice, st));
 
@@ -517,7 +526,7 @@ extern "C" int tb_hmc_measure(tb_ctx *ctx, int nsrc, unsigned long long seed, un
       TB_CUDA(cudaMemcpyAsync(ctx->stage, sources_host + (size_t)i * 2 * n, n * sizeof(double2), cudaMemcpyHostToDevice, st));
       TB_CHECK(tb_launch_pack(ctx, ctx->stage, H.gauss));
     } else {
-      fill_gauss_kernel<<<ew_blocks(n), 256, 0, st>>>(H.gauss, n, C, RngKey{seed, meas_index, 16u + (unsigned int)i});
+      fill_gauss_kernel<<<ew_blocks(n), 256, 0, st>>>(H.gauss, n, C, RngKey{seed, meas_index, 16u + (unsigned int)i, ctx->hmc_chain_offset});
       ctx->launches++;
     }
     TB_CHECK(tb_launch_dslash(ctx, tb_conj_is_dagger(ctx), H.gauss, ctx->tmp, false));
@@ -562,7 +571,7 @@ extern "C" int tb_hmc_condensate(tb_ctx *ctx, int nsrc, unsigned long long seed,
         TB_CUDA(cudaMemcpyAsync(ctx->stage, sources_host + (size_t)i * 2 * n, n * sizeof(double2), cudaMemcpyHostToDevice, st));
         TB_CHECK(tb_launch_pack(ctx, ctx->stage, H.gauss));
       } else {
-        fill_gauss_kernel<<<ew_blocks(n), 256, 0, st>>>(H.gauss, n, C, RngKey{seed, meas_index, 64u + (unsigned int)i});
+        fill_gauss_kernel<<<ew_blocks(n), 256, 0, st>>>(H.gauss, n, C, RngKey{seed, meas_index, 64u + (unsigned int)i, ctx->hmc_chain_offset});
         ctx->launches++;
       }
       TB_CHECK(tb_launch_dslash(ctx, tb_conj_is_dagger(ctx), H.gauss, ctx->tmp, false));   // hmc.c:410

@@ -50,6 +50,7 @@ SIGNATURES = {
     "tb_slab_export": (_i, [_vp, _vp]),
     "tb_slab_connect": (_i, [_vp, _vp]),
     "tb_hmc_set_coupling": (_i, [_vp, _dp, _i]),
+    "tb_hmc_set_chain_offset": (_i, [_vp, C.c_uint]),
     "tb_hmc_heatbath": (_i, [_vp, _i, C.c_ulonglong]),
     "tb_hmc_trajectory": (_i, [_vp, _i, _d, C.c_ulonglong, C.c_uint, _vp, _vp, _vp, _vp, _vp, _ip,
                                C.POINTER(C.c_longlong)]),
