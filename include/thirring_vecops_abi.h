@@ -40,6 +40,14 @@ void fM(double **chi, double **psi);                           /* vec_ops.c:96-1
 void fM_transpose(double **chi, double **psi);                 /* vec_ops.c:135-172 chi = M^T psi */
 void cg_MdM(double **inv, double **source);                    /* vec_ops.c:261-307; divergence -> 1e50 fill */
 void cg_propagator(double **propagator, double **source);      /* vec_ops.c:311-321 */
+/* flat-array family, double[NT*NX] indexed t*NX+x (Thirring.h:102-106; no caller in the reference).
+ * fM_occupied is fM_transpose without the mass term; on the GPU through a second context at mass 0. */
+double *alloc_field(void);                                     /* vec_ops.c:252-255 */
+void fM_occupied(double *chi, double *psi);                    /* vec_ops.c:345-380 */
+void fM_occupied_sq(double *chi, double *psi);                 /* vec_ops.c:384-390: fM_occupied twice */
+double action(double *psi);                                    /* vec_ops.c:392-397: 0.5 sum psi^2 */
+void vec_gaussian(double *a);                                  /* vec_ops.c:399-409: Box-Muller on the driver's mersenne() */
+int cg_MdM_occupied(double *psi, double *source);              /* vec_ops.c:413-461: 0 = converged, 1 = not */
 #endif
 
 #ifdef __cplusplus

@@ -71,6 +71,12 @@ class Oracle:
         L.orc_cg_MdM.restype = ii
         L.orc_cg_propagator.argtypes = [ii, ii, dd, dd, ipp, _dp, _dp, ipp, _dp]
         L.orc_cg_propagator.restype = ii
+        L.orc_fM_occupied.argtypes = [ii, ii, dd, ipp, _dp, _dp]
+        L.orc_fM_occupied_sq.argtypes = [ii, ii, dd, ipp, _dp, _dp]
+        L.orc_action.argtypes = [ii, _dp]
+        L.orc_action.restype = dd
+        L.orc_cg_MdM_occupied.argtypes = [ii, ii, dd, ipp, _dp, _dp, ipp]
+        L.orc_cg_MdM_occupied.restype = ii
 
     @staticmethod
     def _prep(v, A):
@@ -147,6 +153,28 @@ class Oracle:
         fn = self.lib.orc_cg_propagator if propagator else self.lib.orc_cg_MdM
         st = fn(nt, nx, m, mu, field.ctypes.data_as(C.POINTER(C.c_int)), _p(source), _p(inv), C.byref(it), C.byref(rr))
         return inv, st, it.value, rr.value
+
+
+    # flat-array family (vec_ops.c:345-461); vectors still passed as (NT, NX) arrays, flattened t*NX+x
+    def fM_occupied(self, psi, field, mu, sq=False):
+        psi, field, nt, nx = self._prep_b(psi, field)
+        chi = np.empty_like(psi)
+        fn = self.lib.orc_fM_occupied_sq if sq else self.lib.orc_fM_occupied
+        fn(nt, nx, mu, field.ctypes.data_as(C.POINTER(C.c_int)), _p(psi), _p(chi))
+        return chi
+
+    def action(self, psi):
+        psi = np.ascontiguousarray(psi, dtype=np.float64)
+        return self.lib.orc_action(psi.size, _p(psi))
+
+    def cg_MdM_occupied(self, source, field, mu):
+        """Returns (psi, ret, iterations); ret 0 = converged, 1 = not (psi is then None)."""
+        source, field, nt, nx = self._prep_b(source, field)
+        psi = np.full_like(source, np.nan)
+        it = C.c_int(0)
+        ret = self.lib.orc_cg_MdM_occupied(nt, nx, mu, field.ctypes.data_as(C.POINTER(C.c_int)),
+                                           _p(source), _p(psi), C.byref(it))
+        return (psi if ret == 0 else None), ret, it.value
 
 
 def ref_available(nt, nx, flavour="compat", nsteps=10):
@@ -359,3 +387,20 @@ class RefLibB:
         o, i = self._rows(out), self._rows(src)
         getattr(self.lib, fname)(o.ctypes.data, i.ctypes.data)
         return out
+
+    def call_flat(self, fname, src):
+        """The flat-array family (vec_ops.c:345-461): fM_occupied, fM_occupied_sq take (out, in) as double[NT*NX];
+        cg_MdM_occupied returns (psi or None, ret)."""
+        src = np.ascontiguousarray(src, dtype=np.float64)
+        out = np.full_like(src, np.nan)
+        fn = getattr(self.lib, fname)
+        fn.argtypes = [C.c_void_p, C.c_void_p]
+        fn.restype = C.c_int if fname == "cg_MdM_occupied" else None
+        ret = fn(out.ctypes.data, src.ctypes.data)
+        if fname == "cg_MdM_occupied":
+            return (out if ret == 0 else None), ret
+        return out
+
+    def set_mu(self, mu):
+        C.c_double.in_dll(self.lib, "mu").value = mu
+        self.mu = mu

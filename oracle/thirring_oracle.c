@@ -287,6 +287,59 @@ done:
   return status;
 }
 
+/* ---- flat-array family, vec_ops.c:345-461 (declared Thirring.h:102-106; no caller in the reference) ------------- */
+
+/* fM_occupied, vec_ops.c:345-380: the hop terms of fM_transpose without the mass term (chi starts from 0 and every
+ * hop is 0.5*exp*eta*psi; the factors 0.5 and eta = +-1 are exact, so the product order of vec_ops.c:355 and
+ * vec_ops.c:150 gives the same double) */
+void orc_fM_occupied(int nt, int nx, double mu, const int *field, const double *psi, double *chi)
+{ apply_b(nt, nx, 0.0, mu, 1, field, psi, chi); }
+
+/* fM_occupied_sq, vec_ops.c:384-390 */
+void orc_fM_occupied_sq(int nt, int nx, double mu, const int *field, const double *psi, double *chi)
+{
+  double *tmp = malloc(sizeof(double) * nt * nx);
+  orc_fM_occupied(nt, nx, mu, field, psi, tmp);
+  orc_fM_occupied(nt, nx, mu, field, tmp, chi);
+  free(tmp);
+}
+
+/* action, vec_ops.c:392-397 */
+double orc_action(int n, const double *psi)
+{ double s = 0; for (int i = 0; i < n; i++) s += psi[i] * psi[i]; return 0.5 * s; }
+
+/* cg_MdM_occupied, vec_ops.c:413-461: CG on fM_occupied_sq from inv = 0, then psi = fM_occupied(inv).
+ * Returns 0 (converged; psi written) or 1 (divergence, NaN, or CG_MAX_ITER passes; psi untouched). */
+int orc_cg_MdM_occupied(int nt, int nx, double mu, const int *field, const double *source, double *psi, int *iters)
+{
+  const int V = nt * nx;
+  double *r = malloc(sizeof(double) * V), *p = malloc(sizeof(double) * V);
+  double *MMp = malloc(sizeof(double) * V), *inv = malloc(sizeof(double) * V);
+  int ret = 1, k;
+  for (int i = 0; i < V; i++) inv[i] = 0;
+  for (int i = 0; i < V; i++) p[i] = r[i] = source[i];
+  double rr_old = 0;
+  for (int i = 0; i < V; i++) rr_old += r[i] * r[i];
+  const double rr_init = rr_old;
+  for (k = 1; k < ORC_B_CG_MAX_ITER; k++) {
+    orc_fM_occupied_sq(nt, nx, mu, field, p, MMp);
+    double pMp = 0;
+    for (int i = 0; i < V; i++) pMp += p[i] * MMp[i];
+    const double a = rr_old / pMp;
+    for (int i = 0; i < V; i++) { inv[i] = inv[i] + a * p[i]; r[i] = r[i] - a * MMp[i]; }
+    double rr = 0;
+    for (int i = 0; i < V; i++) rr += r[i] * r[i];
+    if (rr < ORC_CG_ACCURACY) { orc_fM_occupied(nt, nx, mu, field, inv, psi); ret = 0; break; }
+    if (rr / rr_init > 1e10 || isnan(rr)) break;                       /* vec_ops.c:448-451 */
+    const double b = rr / rr_old;
+    for (int i = 0; i < V; i++) p[i] = r[i] + b * p[i];
+    rr_old = rr;
+  }
+  if (iters) *iters = k < ORC_B_CG_MAX_ITER ? k : k - 1;
+  free(r); free(p); free(MMp); free(inv);
+  return ret;
+}
+
 /* cg_propagator, vec_ops.c:311-321:  M^-1 source = (M^T M)^-1 M^T source */
 int orc_cg_propagator(int nt, int nx, double m, double mu, const int *field, const double *source, double *prop,
                       int *iters, double *rr_final)

@@ -141,3 +141,54 @@ def test_family_b_golden_fixture(oracle):
     assert np.array_equal(oracle.fM(psi, field, m, mu), d["fM"])
     assert np.array_equal(oracle.fM(psi, field, m, mu, transpose=True), d["fMT"])
     assert np.array_equal(oracle.cg_MdM(psi, field, m, mu, propagator=True)[0], d["prop"])
+
+
+@needs_ref_b
+@pytest.mark.parametrize("nt,nx", [(16, 16), (16, 32), (32, 32)])
+@pytest.mark.parametrize("mu,occ", [(0.0, 0.0), (0.1, 0.0), (0.3, 0.2)])
+def test_flat_array_family_oracle_bitwise_vs_compiled_vec_ops(oracle, nt, nx, mu, occ):
+    """vec_ops.c:345-461 (fM_occupied, fM_occupied_sq, action, cg_MdM_occupied; no caller in the reference)."""
+    import ctypes as C
+
+    rng = np.random.default_rng(nt * nx + int(100 * mu))
+    ref = RefLibB(nt, nx, m=0.7, mu=mu)       # the mass must not enter (vec_ops.c:353 starts from chi = 0)
+    field = (rng.random((nt, nx)) < occ).astype(np.int32)
+    ref.set_field(field)
+    psi = rng.normal(size=(nt, nx))
+    assert np.array_equal(ref.call_flat("fM_occupied", psi), oracle.fM_occupied(psi, field, mu))
+    assert np.array_equal(ref.call_flat("fM_occupied_sq", psi), oracle.fM_occupied(psi, field, mu, sq=True))
+    ref.lib.action.restype = C.c_double
+    ref.lib.action.argtypes = [C.c_void_p]
+    assert ref.lib.action(psi.ctypes.data) == oracle.action(psi)
+    # F F is negative definite on the free sites and the identity on occupied ones: sources supported on the free
+    # sites keep the Krylov space inside one definite block
+    src = np.where(field == 0, psi, 0.0)
+    x_ref, ret_ref = ref.call_flat("cg_MdM_occupied", src)
+    x, ret, it = oracle.cg_MdM_occupied(src, field, mu)
+    assert ret == ret_ref
+    if ret == 0:
+        assert np.array_equal(x, x_ref)
+        # psi = F (F F)^-1 source  =>  F psi = source
+        assert np.abs(oracle.fM_occupied(x, field, mu) - src).max() < 1e-10
+    # zero source: a = 0/0, the NaN branch returns 1 (vec_ops.c:448-451)
+    assert ref.call_flat("cg_MdM_occupied", np.zeros((nt, nx)))[1] == 1
+    assert oracle.cg_MdM_occupied(np.zeros((nt, nx)), field, mu)[1] == 1
+
+
+@needs_ref_b
+def test_flat_array_cg_with_occupied_dimers_bitwise(oracle):
+    """Occupied nearest-neighbour pairs (what a fermion bag occupies) keep the two sublattices balanced: no zero
+    modes, cg_MdM_occupied converges at mu = 0."""
+    nt = nx = 32
+    rng = np.random.default_rng(4)
+    field = np.zeros((nt, nx), dtype=np.int32)
+    for _ in range(10):
+        t, x = rng.integers(nt), rng.integers(nx - 1)
+        field[t, x] = field[t, x + 1] = 1
+    ref = RefLibB(nt, nx, m=0.3, mu=0.0)
+    ref.set_field(field)
+    src = np.where(field == 0, rng.normal(size=(nt, nx)), 0.0)
+    x_ref, ret_ref = ref.call_flat("cg_MdM_occupied", src)
+    x, ret, it = oracle.cg_MdM_occupied(src, field, 0.0)
+    assert ret == ret_ref == 0 and it > 50
+    assert np.array_equal(x, x_ref)

@@ -2,6 +2,7 @@
  * Plain C host code over the handle C-ABI; contract in include/thirring_vecops_abi.h. */
 #define _GNU_SOURCE
 #include <dlfcn.h>
+#include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -13,7 +14,7 @@
 
 static struct {
   tb_ctx *ctx;
-  int nt, nx;
+  int nt, nx, device;
   int *field_flat, *field_last;
   double *cin, *cout;   /* complex staging (imaginary parts zero) */
   int have_field, mu_frozen;
@@ -22,6 +23,12 @@ static struct {
   int ***p_field;       /* &field  (int **field, Thirring.h:76) */
   double *p_m, *p_mu;
   long gpu_calls;
+  /* flat-array family (vec_ops.c:345-461): massless operator, see the section at the end of the file */
+  tb_ctx *ctx0;
+  int *field0_last;
+  int have_field0;
+  double mu_flat;
+  double *inv0;
 } S;
 
 static void die(const char *what) {
@@ -32,7 +39,7 @@ static void die(const char *what) {
 int tb_vecops_configure(int nt, int nx, int device) {
   if (S.ctx) tb_vecops_shutdown();
   memset(&S, 0, sizeof(S));
-  S.nt = nt; S.nx = nx;
+  S.nt = nt; S.nx = nx; S.device = device;
   if (tb_create(&S.ctx, nt, nx, 1, TB_MODE_ADJOINT, device) != TB_OK) die("tb_create");
   if (tb_set_cg(S.ctx, 1e-30, VEC_CG_MAX_ITER) != TB_OK) die("tb_set_cg");  /* Thirring.h:42-43 */
   size_t v = (size_t)nt * nx;
@@ -45,7 +52,8 @@ int tb_vecops_configure(int nt, int nx, int device) {
 
 void tb_vecops_shutdown(void) {
   if (S.ctx) tb_destroy(S.ctx);
-  free(S.field_flat); free(S.field_last); free(S.cin); free(S.cout);
+  if (S.ctx0) tb_destroy(S.ctx0);
+  free(S.field_flat); free(S.field_last); free(S.cin); free(S.cout); free(S.field0_last); free(S.inv0);
   memset(&S, 0, sizeof(S));
 }
 
@@ -157,3 +165,122 @@ static void solve(int propagator, double **inv, double **source) {
 
 void cg_MdM(double **inv, double **source) { solve(0, inv, source); }
 void cg_propagator(double **propagator, double **source) { solve(1, propagator, source); }
+
+/* ---- the flat-array family of vec_ops.c:345-461 (declared Thirring.h:102-106, no caller in the reference) -----------
+ * F = fM_occupied is fM_transpose without the mass term (vec_ops.c:345-380): F = T (+) 1 with T the hop matrix between
+ * free sites and 1 on the occupied ones.  The GPU context ctx0 holds M' = fM at mass 0 and chemical potential -mu,
+ * which is (-T) (+) 1 (transposing the hop matrix flips its sign and exchanges exp(mu) <-> exp(-mu)), so
+ *   F v = -M' v on free sites, v on occupied sites;  F F = M' M'  (what TB_OP_MDM and tb_cg apply in REF_COMPAT mode).
+ * Vectors are flat double[VOLUME], index t*NX+x. */
+static void sync_state0(void) {
+  sync_state();   /* globals, frozen mu, S.field_flat = the driver's current field */
+  size_t v = (size_t)S.nt * S.nx, bytes = v * sizeof(int);
+  if (!S.ctx0) {
+    if (tb_create(&S.ctx0, S.nt, S.nx, 1, TB_MODE_REF_COMPAT, S.device) != TB_OK) die("tb_create (flat-array family)");
+    if (tb_set_cg(S.ctx0, 1e-30, VEC_CG_MAX_ITER) != TB_OK) die("tb_set_cg");
+    S.field0_last = malloc(bytes);
+    S.inv0 = calloc(2 * v, sizeof(double));
+    S.have_field0 = 0;
+  }
+  /* fM_occupied never clears its `init` flag (vec_ops.c:347-352): exp(+-mu) follows the driver's current mu */
+  if (!S.have_field0 || S.mu_flat != *S.p_mu) {
+    double m0 = 0, mu0 = -*S.p_mu;
+    if (tb_set_params(S.ctx0, &m0, &mu0, 1) != TB_OK) die("tb_set_params");
+    S.mu_flat = *S.p_mu;
+    S.have_field0 = 0;
+  }
+  if (!S.have_field0 || memcmp(S.field_flat, S.field0_last, bytes) != 0) {
+    if (tb_set_occupancy(S.ctx0, S.field_flat) != TB_OK) die("tb_set_occupancy");
+    memcpy(S.field0_last, S.field_flat, bytes);
+    S.have_field0 = 1;
+  }
+}
+
+/* chi = F psi from M' psi (S.cout holds M' of S.cin) */
+static void f_from_mprime(double *chi) {
+  size_t v = (size_t)S.nt * S.nx;
+  for (size_t i = 0; i < v; i++) chi[i] = S.field_flat[i] == 0 ? -S.cout[2 * i] : S.cin[2 * i];
+}
+
+double *alloc_field(void) {   /* vec_ops.c:252-255 sizes it with sizeof(double *): the same 8 bytes per site */
+  lazy_init();
+  return malloc((size_t)S.nt * S.nx * sizeof(double *));
+}
+
+void fM_occupied(double *chi, double *psi) {
+  sync_state0();
+  size_t v = (size_t)S.nt * S.nx;
+  for (size_t i = 0; i < v; i++) S.cin[2 * i] = psi[i];
+  if (tb_apply(S.ctx0, TB_OP_M, S.cin, S.cout) != TB_OK) die("tb_apply");
+  f_from_mprime(chi);
+  S.gpu_calls++;
+}
+
+void fM_occupied_sq(double *chi, double *psi) {   /* vec_ops.c:384-390 */
+  sync_state0();
+  size_t v = (size_t)S.nt * S.nx;
+  for (size_t i = 0; i < v; i++) S.cin[2 * i] = psi[i];
+  if (tb_apply(S.ctx0, TB_OP_MDM, S.cin, S.cout) != TB_OK) die("tb_apply");
+  for (size_t i = 0; i < v; i++) chi[i] = S.cout[2 * i];
+  S.gpu_calls++;
+}
+
+double action(double *psi) {   /* vec_ops.c:392-397 */
+  lazy_init();
+  double s = 0;
+  size_t v = (size_t)S.nt * S.nx;
+  for (size_t i = 0; i < v; i++) s += psi[i] * psi[i];
+  return 0.5 * s;
+}
+
+/* vec_ops.c:399-409.  mersenne() is a macro over the generator's state (mersenne.h:8-14), which lives in the driver's
+ * mersenne_inline.o: the same state is used here, so the driver's random stream stays in step. */
+void vec_gaussian(double *a) {
+  lazy_init();
+  static int *p_i;
+  static double *p_arr;
+  static double (*p_gen)(void);
+  if (!p_gen) {
+    p_i = (int *)dlsym(RTLD_DEFAULT, "mersenne_i");
+    p_arr = (double *)dlsym(RTLD_DEFAULT, "mersenne_array");
+    p_gen = (double (*)(void))dlsym(RTLD_DEFAULT, "mersenne_generate");
+    if (!p_i || !p_arr || !p_gen) {
+      fprintf(stderr, "libthirring_vecops: the driver's Mersenne generator (mersenne.h:8-14) is not visible\n");
+      abort();
+    }
+  }
+#define MERSENNE() (*p_i > 0 ? p_arr[--*p_i] : p_gen())
+  int v = S.nt * S.nx;
+  for (int t = 0; t < v; t++) {
+    double x1 = MERSENNE();
+    double x2 = MERSENNE();
+    a[t] = sqrt(-2 * log(x1)) * cos(2 * M_PI * x2);
+    if (t < v - 1) a[++t] = sqrt(-2 * log(x1)) * sin(2 * M_PI * x2);
+  }
+#undef MERSENNE
+}
+
+/* vec_ops.c:413-461: CG on F F from x0 = 0, then psi = F inv.  Returns 0 when ||r||^2 < CG_ACCURACY, 1 on
+ * divergence, NaN or CG_MAX_ITER (psi is left untouched then, as in the reference). */
+int cg_MdM_occupied(double *psi, double *source) {
+  sync_state0();
+  size_t v = (size_t)S.nt * S.nx;
+  for (size_t i = 0; i < v; i++) S.cin[2 * i] = source[i];
+  int status = 0, iters = 0;
+  double rr = 0;
+  if (tb_cg(S.ctx0, S.cin, S.inv0, &status, &iters, &rr) != TB_OK) die("tb_cg");
+  S.gpu_calls++;
+  if (status == TB_CG_ZERO_SOURCE) {
+    /* no zero-source exit in vec_ops.c:413-461: rr_old = 0 gives a = 0/0 and the NaN branch returns 1; a source
+     * that is only tiny is solved by x = 0 to the requested accuracy */
+    double s = 0;
+    for (size_t i = 0; i < v; i++) s += source[i] * source[i];
+    if (s == 0) return 1;
+  } else if (status != TB_CG_CONVERGED) {
+    return 1;
+  }
+  memcpy(S.cin, S.inv0, 2 * v * sizeof(double));
+  if (tb_apply(S.ctx0, TB_OP_M, S.cin, S.cout) != TB_OK) die("tb_apply");
+  f_from_mprime(psi);
+  return 0;
+}
