@@ -114,14 +114,15 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------------
-def run_cpu_reference(chains_total, procs):
+def run_cpu_reference(chains_total, procs, flavour="adjoint"):
     """Time the reference's fmdm_invert_cg on `procs` host processes (it is single-threaded: one chain per
     process at a time).  Returns (applies/s, seconds wall, applies, kind)."""
     per = max(1, chains_total // procs)
     cmds = []
     for p in range(procs):
         cmds.append([sys.executable, "-m", "oracle.cpu_baseline", "--nt", str(NT), "--nx", str(NX), "--chains",
-                     str(per), "--first", str(p * per), "--m", str(MASS), "--mu", str(MU), "--g", str(G)])
+                     str(per), "--first", str(p * per), "--m", str(MASS), "--mu", str(MU), "--g", str(G),
+                     "--flavour", flavour])
     t0 = time.perf_counter()
     ps = [subprocess.Popen(c, cwd=ROOT, stdout=subprocess.PIPE, text=True) for c in cmds]
     outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in ps]
@@ -363,6 +364,13 @@ def gpu_arm(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"{nch} chain solves of the same workload ({NT}x{NX}, m={MASS}), "
                                               f"{cores} single-threaded processes, {busy:.1f} s"}
+            # also one core, and the flags the reference ships with (Makefile:2, no optimisation)
+            v1 = run_cpu_reference(4, 1)
+            line["cpu_baseline"]["one_core"] = {"value": v1[0], "sample": f"{v1[4]} chain solves, -O3"}
+            if os.path.exists(os.path.join(ROOT, "oracle", "_ref", f"libhmcref_{NT}x{NX}_adjoint_shipped.so")):
+                vs = run_cpu_reference(2, 1, "adjoint_shipped")
+                line["cpu_baseline"]["one_core_shipped_flags"] = {
+                    "value": vs[0], "sample": f"{vs[4]} chain solves, the reference's own CFLAGS (-std=c99 -g, no -O)"}
             if hmc is not None:
                 tps = run_cpu_reference_hmc(cores)
                 if tps is not None:
@@ -537,9 +545,11 @@ def other_configs(tb, torch, dist, dev, stream, rank, world):
             ntraj = int(params.split("\n")[0])
             zero = "0\n" + params.split("\n", 1)[1]   # same start (seeding, 100 heat-bath sweeps), no trajectory
 
+            nsteps_env = dict(os.environ, THIRRING_NSTEPS="40" if "ns40" in so else "10")
+
             def wall(cmd, inp):
                 t0 = time.perf_counter()
-                p = subprocess.run(cmd, input=inp, capture_output=True, text=True)
+                p = subprocess.run(cmd, input=inp, capture_output=True, text=True, env=nsteps_env)
                 return time.perf_counter() - t0, p
 
             gpu_cmd, cpu_cmd = [launcher, sop, "32", "32", mode], [ref_exe, sop]
@@ -548,10 +558,16 @@ def other_configs(tb, torch, dist, dev, stream, rank, world):
             tg, pg = wall(gpu_cmd, params)
             tc0 = wall(cpu_cmd, zero)[0]
             tc, pc = wall(cpu_cmd, params)
+            # optional coarse override (libthirring_hmc_coarse.so): update_gauge = one device-resident trajectory
+            co_cmd = gpu_cmd + ["0", "coarse"]
+            tk0 = min(wall(co_cmd, zero)[0] for _ in range(2))
+            tk, pk = wall(co_cmd, params)
             drop[name] = {"trajectories": ntraj,
                           "ms_per_trajectory_on_the_library": 1e3 * max(tg - tg0, 0.0) / ntraj,
                           "ms_per_trajectory_reference_cpu": 1e3 * max(tc - tc0, 0.0) / ntraj,
                           "process_seconds_on_the_library": tg, "process_seconds_reference_cpu": tc,
+                          "ms_per_trajectory_coarse_override": 1e3 * max(tk - tk0, 0.0) / ntraj,
+                          "stdout_identical_coarse_override": pk.stdout == pc.stdout,
                           "stdout_identical": pg.stdout == pc.stdout, "served": pg.stderr.strip().splitlines()[-1:],
                           "note": "one chain; per-trajectory = (N-trajectory process) - (0-trajectory process), which "
                                   "removes CUDA start-up (0.3-2 s per process) and the common heat-bath start"}

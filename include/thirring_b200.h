@@ -177,6 +177,11 @@ int tb_hmc_trajectory(tb_ctx *ctx, int nsteps, double traj_length, unsigned long
                       const double *st_host, const double *u_host, double *obs_host, int *accepted_host,
                       long long *cg_iters_host);
 
+/* Per chain, how the CG solves of the last tb_hmc_trajectory ended: bit (1 << TB_CG_MAXITER) and / or
+ * (1 << TB_CG_DIVERGED) set, 0 when every solve converged.  The reference exit(1)s on divergence (hmc.c:383-388)
+ * and is silent at max-iter; a batched trajectory rejects such a chain and reports it here. */
+int tb_hmc_cg_failures(tb_ctx *ctx, int *mask_host);
+
 /* measure() (hmc.c:823-842) per chain: Magnetisation = sum A / V and Phase = (1/nsrc) sum Im<c, M~ c> over nsrc
  * stochastic vectors (fermion_phase hmc.c:794-815 uses 20).  sources_host (optional): complex
  * [nsrc][chain][t][x]. */

@@ -28,6 +28,15 @@ void tb_hmc_shutdown(void);
 /* number of CG solves / Dirac applies served since configure (for tests) */
 long tb_hmc_cg_calls(void);
 long tb_hmc_apply_calls(void);
+long tb_hmc_trajectory_calls(void);
+
+/* update_gauge (hmc.c:671-746) as ONE device-resident trajectory of the context (tb_hmc_trajectory), drawing the
+ * random fields and the Metropolis uniform from the driver's own Mersenne state in the reference's order and printing
+ * the reference's stdout lines (hmc.c:701,735,739,743).  The leapfrog has 10 steps like hmc.c:708 unless
+ * THIRRING_NSTEPS is set.  libthirring_hmc_coarse.so exports the reference's symbol `update_gauge` bound to this
+ * function: the optional coarse override of SURVEY 8(b); without that library the driver's own update_gauge runs and
+ * only its solves and applies are interposed. */
+void tb_hmc_update_gauge(double ***A);
 
 #ifndef THIRRING_HMC_ABI_NO_PROTOTYPES
 /* replaces hmc.c:105-112 — one block holds the row table and the rows, so the stray free(tmp) of

@@ -24,15 +24,18 @@ if [ ! -f "$REF/hmc.c" ]; then
   exit 0
 fi
 
-build_one() { # NT NX flavour [nsteps]
-  local nt=$1 nx=$2 fl=$3 ns=${4:-10}
+build_one() { # NT NX flavour [nsteps] [shipped]
+  local nt=$1 nx=$2 fl=$3 ns=${4:-10} opt=$OPT
   local name="libhmcref_${nt}x${nx}_${fl}"
   [ "$ns" != 10 ] && name="${name}_ns${ns}"
+  # the reference's own CFLAGS (Makefile:5 "-march=native -std=c99 -g", i.e. no optimisation); x86-64-v3 instead of
+  # native so that the object also runs on the GPU box's host CPU
+  if [ "${5:-}" = shipped ]; then name="${name}_shipped"; opt="-march=x86-64-v3 -g"; fi
   local sedprog="s/^#define NT 32/#define NT ${nt}/; s/^#define NX 32/#define NX ${nx}/; s/int nsteps = 10;/int nsteps = ${ns};/"
   if [ "$fl" = adjoint ]; then
     sedprog="$sedprog; 197,248{s/v += 0\\.5/v @@ 0.5/; s/v -= 0\\.5/v += 0.5/; s/v @@ 0\\.5/v -= 0.5/; s/expmmu/EXPTMP/; s/expmu/expmmu/; s/EXPTMP/expmu/}"
   fi
-  sed "$sedprog" "$REF/hmc.c" | gcc $OPT -std=c99 -w -fPIC -shared -Dmain=hmc_main \
+  sed "$sedprog" "$REF/hmc.c" | gcc $opt -std=c99 -w -fPIC -shared -Dmain=hmc_main \
       -I"$HERE/shim" -I"$REF" -x c - -x none "$REF/mersenne_inline.c" "$HERE/shim/lapack_stub.c" \
       -o "$OUT/$name.so" -lm
 }
@@ -46,6 +49,8 @@ done
 # light-mass trajectory oracle: 40 leapfrog steps
 build_one 32 32 adjoint 40
 build_one 64 64 adjoint 40
+# CPU baseline at the flags the reference ships with
+build_one 64 64 adjoint 10 shipped
 # family B: vec_ops.c behind Thirring.h (sizes are unguarded #defines, Thirring.h:14-15).  The translation unit
 # is assembled on gcc's stdin: "#define MAIN" (so that the EXTERN globals of Thirring.h:54-76 are DEFINED here,
 # as the driver fermionbag.c does), the size-rewritten header, then vec_ops.c without its own #include.

@@ -65,14 +65,15 @@ def main():
     ap.add_argument("--mu", type=float, default=0.0)
     ap.add_argument("--g", type=float, default=0.3)
     ap.add_argument("--max-iter", type=int, default=0)
+    ap.add_argument("--flavour", default="adjoint", help="adjoint (-O3) or adjoint_shipped (the reference's own CFLAGS)")
     ap.add_argument("--family-b", type=int, default=0, metavar="NSRC",
                     help="time the reference's vec_ops.c cg_propagator on NSRC point sources instead")
     a = ap.parse_args()
     if a.family_b:
         return family_b(a)
     orc = Oracle()
-    use_ref = ref_available(a.nt, a.nx, "adjoint")
-    ref = RefLib(a.nt, a.nx, "adjoint", m=a.m, g=a.g, mu=a.mu) if use_ref else None
+    use_ref = ref_available(a.nt, a.nx, a.flavour)
+    ref = RefLib(a.nt, a.nx, a.flavour, m=a.m, g=a.g, mu=a.mu) if use_ref else None
     secs, iters = 0.0, 0
     for c in range(a.first, a.first + a.chains):
         A, xi = synthetic_chain(c, a.nt, a.nx, a.g)

@@ -206,7 +206,7 @@ class RefLib:
         self.lib = L = C.CDLL(self._tmp)
         os.unlink(self._tmp)
         self.nt, self.nx, self.flavour = nt, nx, flavour
-        self.mode = MODE_ADJOINT if flavour == "adjoint" else MODE_REF_COMPAT
+        self.mode = MODE_ADJOINT if flavour.startswith("adjoint") else MODE_REF_COMPAT
         for name, val in (("m", m), ("g", g), ("mu", mu)):
             C.c_double.in_dll(L, name).value = val
         self.m, self.g, self.mu = m, g, mu

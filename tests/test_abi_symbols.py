@@ -43,10 +43,17 @@ def test_reference_signature_shim_exports_family_A():
     assert not missing, missing
 
 
+def test_coarse_override_library_exports_update_gauge():
+    lib = ctypes.CDLL(os.path.join(PKG, "libthirring_hmc_coarse.so"))
+    assert hasattr(lib, "update_gauge")
+    assert os.path.exists(os.path.join(PKG, "libthirring_b200.a"))   # the static variant of the handle library
+
+
 def test_vec_ops_replacement_exports_family_B():
     names = declared_functions("thirring_vecops_abi.h")
     for n in ("fM", "fM_transpose", "cg_MdM", "cg_propagator", "vec_dot", "vec_dmul_add", "alloc_vector", "free_vector",
-              "vec_zero", "vec_one", "vec_add", "vec_d_mul", "vec_zero_occupied", "tb_vecops_configure"):
+              "vec_zero", "vec_one", "vec_add", "vec_d_mul", "vec_zero_occupied", "tb_vecops_configure",
+              "cg_MdM_occupied", "fM_occupied", "fM_occupied_sq", "action", "vec_gaussian", "alloc_field"):
         assert n in names
     lib = ctypes.CDLL(os.path.join(PKG, "libthirring_vecops.so"))
     missing = [n for n in names if not hasattr(lib, n)]

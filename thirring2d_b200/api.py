@@ -301,6 +301,12 @@ class Context:
               "tb_hmc_trajectory")
         return obs, acc, its.value
 
+    def hmc_cg_failures(self):
+        """Per chain: bit (1 << CG_MAXITER) / (1 << CG_DIVERGED) set if a solve of the last trajectory ended so."""
+        mask = np.empty(self.nchains, dtype=np.int32)
+        check(self.lib.tb_hmc_cg_failures(self._h, mask.ctypes.data_as(_ip)), "tb_hmc_cg_failures")
+        return mask
+
     def hmc_measure(self, nsrc=20, seed=1, meas_index=0, sources=None):
         mag = np.empty(self.nchains, dtype=np.float64)
         ph = np.empty(self.nchains, dtype=np.float64)

@@ -22,7 +22,14 @@ static struct {
   int mu_frozen;
   double mu_at_first_call;
   double *p_m, *p_mu;  /* the driver's globals, hmc.c:38,40 */
-  long cg_calls, apply_calls;
+  long cg_calls, apply_calls, traj_calls;
+  /* coarse override (update_gauge as one device-resident trajectory) */
+  double *p_g;          /* the driver's global g, hmc.c:39 */
+  int *p_mers_i;        /* the driver's Mersenne state, mersenne.h:8-14 */
+  double *p_mers_array;
+  double (*p_mers_generate)(void);
+  double *xi, *mom, *st;
+  unsigned int traj_index;
 } S;
 
 static void die(const char *what) {
@@ -45,12 +52,13 @@ int tb_hmc_configure(int nt, int nx, int mode, int device) {
 
 void tb_hmc_shutdown(void) {
   if (S.ctx) tb_destroy(S.ctx);
-  free(S.A_flat); free(S.A_tmp); free(S.vin); free(S.vout);
+  free(S.A_flat); free(S.A_tmp); free(S.vin); free(S.vout); free(S.xi); free(S.mom); free(S.st);
   memset(&S, 0, sizeof(S));
 }
 
 long tb_hmc_cg_calls(void) { return S.cg_calls; }
 long tb_hmc_apply_calls(void) { return S.apply_calls; }
+long tb_hmc_trajectory_calls(void) { return S.traj_calls; }
 
 static void lazy_init(void) {
   if (S.ctx) return;
@@ -198,4 +206,79 @@ void test_conjugate(double ***A) {
     exit(1);
   }
   free_vector(c); free_vector(mc); free_vector(mdc);
+}
+
+/* ---- coarse override: update_gauge (hmc.c:671-746) as ONE device-resident trajectory ------------------------------
+ * Exported under a tb_ name here; libthirring_hmc_coarse.so (hmc_coarse.c) binds the reference's symbol to it, so the
+ * fine-grained path above stays the default.  The random numbers are the DRIVER's: the Box-Muller fields of
+ * random_pseudofermion (hmc.c:418-430), random_momentum (hmc.c:483-499) and stochastic_vector (hmc.c:439-447) and the
+ * Metropolis uniform (hmc.c:738) are drawn here from the driver's Mersenne state in the reference's order (nothing
+ * else draws in between), so the stream stays in step with an un-interposed run.  The two stdout lines and the
+ * verdict are printed in the reference's format (hmc.c:701,735,739,743). */
+static double drv_mersenne(void) {   /* the mersenne() macro, mersenne.h:11 */
+  return *S.p_mers_i > 0 ? S.p_mers_array[--*S.p_mers_i] : S.p_mers_generate();
+}
+
+static void box_muller_pairs(double *out, size_t npairs) {
+  for (size_t i = 0; i < npairs; i++) {
+    double x1 = drv_mersenne();
+    double x2 = drv_mersenne();
+    out[2 * i] = sqrt(-2 * log(x1)) * cos(2 * M_PI * x2);
+    out[2 * i + 1] = sqrt(-2 * log(x1)) * sin(2 * M_PI * x2);
+  }
+}
+
+void tb_hmc_update_gauge(double ***A) {
+  lazy_init();
+  sync_params();
+  const size_t v = (size_t)S.nt * S.nx;
+  if (!S.p_g) {
+    S.p_g = (double *)dlsym(RTLD_DEFAULT, "g");
+    S.p_mers_i = (int *)dlsym(RTLD_DEFAULT, "mersenne_i");
+    S.p_mers_array = (double *)dlsym(RTLD_DEFAULT, "mersenne_array");
+    S.p_mers_generate = (double (*)(void))dlsym(RTLD_DEFAULT, "mersenne_generate");
+    if (!S.p_g || !S.p_mers_i || !S.p_mers_array || !S.p_mers_generate) {
+      fprintf(stderr, "libthirring_hmc: the driver's `g` (hmc.c:39) or its Mersenne generator is not visible\n");
+      abort();
+    }
+    S.xi = malloc(v * 2 * sizeof(double));
+    S.mom = malloc(v * 2 * sizeof(double));
+    S.st = malloc(v * 2 * sizeof(double));
+  }
+  const char *ns = getenv("THIRRING_NSTEPS");   /* hmc.c:708 hard-codes 10 */
+  const int nsteps = ns ? atoi(ns) : 10;
+  double g = *S.p_g;
+  if (tb_hmc_set_coupling(S.ctx, &g, 1) != TB_OK) die("tb_hmc_set_coupling");
+  sync_gauge(A);
+  box_muller_pairs(S.xi, v);    /* random_pseudofermion: re, im per site */
+  box_muller_pairs(S.mom, v);   /* random_momentum: mom[t][x][0], mom[t][x][1] */
+  box_muller_pairs(S.st, v);    /* stochastic_vector */
+  double obs[10];
+  int accepted = 0;
+  /* the trajectory needs the uniform before it starts; the reference draws it after the leapfrog, with nothing drawn
+   * in between, so the position in the stream is the same */
+  double u = drv_mersenne();
+  if (tb_hmc_trajectory(S.ctx, nsteps, 1.0, 0, S.traj_index++, S.xi, S.mom, S.st, &u, obs, &accepted, NULL) != TB_OK)
+    die("tb_hmc_trajectory");
+  S.traj_calls++;
+  printf("Start HMC: Sg %g, Smdm %g, Smd %g, Smom %g\n", obs[0], obs[1], obs[2], obs[3]);
+  int failed = 0;
+  if (tb_hmc_cg_failures(S.ctx, &failed) != TB_OK) die("tb_hmc_cg_failures");
+  if (failed & (1 << TB_CG_DIVERGED)) {   /* hmc.c:383-388 */
+    printf("Cannot invert fermion matrix\n");
+    exit(1);
+  }
+  printf("HMC End, dS %g, Sg %g, Smdm %g, Smd %g, Sm %g\n", obs[8], obs[4], obs[5], obs[6], obs[7]);
+  if (accepted) {
+    printf("HMC ACCEPTED\n");
+    if (tb_get_gauge(S.ctx, S.A_flat) != TB_OK) die("tb_get_gauge");
+    const double *d = S.A_flat;
+    for (int t = 0; t < S.nt; t++) for (int x = 0; x < S.nx; x++) {
+      A[t][x][0] = *d++;
+      A[t][x][1] = *d++;
+    }
+    S.have_A = 1;   /* the device already holds this field and its links */
+  } else {
+    printf("HMC REJECTED\n");
+  }
 }

@@ -203,7 +203,7 @@ __global__ void commit_kernel(double2 *__restrict__ A, const double2 *__restrict
 
 __global__ void or_failed_kernel(int *__restrict__ failed, const int *__restrict__ status, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < C && status[c] != TB_CG_CONVERGED && status[c] != TB_CG_ZERO_SOURCE) failed[c] = 1;
+  if (c < C && status[c] != TB_CG_CONVERGED && status[c] != TB_CG_ZERO_SOURCE) failed[c] |= 1 << status[c];
 }
 
 // update_puregauge_hb (hmc.c:82-93): links decouple in the quenched action, so every link runs its own
@@ -481,6 +481,16 @@ extern "C" int tb_hmc_trajectory(tb_ctx *ctx, int nsteps, double traj_length, un
     TB_CUDA(cudaStreamSynchronize(st));
   }
   if (cg_iters_host) *cg_iters_host = cg_iters;
+  return TB_OK;
+}
+
+// per chain: bit TB_CG_MAXITER / TB_CG_DIVERGED set when a solve of the last trajectory ended that way
+extern "C" int tb_hmc_cg_failures(tb_ctx *ctx, int *mask_host) {
+  if (!ctx || !mask_host) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->hmc.failed) { tb_set_error("tb_hmc_cg_failures: no trajectory has run"); return TB_EINVAL; }
+  TB_CUDA(cudaMemcpyAsync(mask_host, ctx->hmc.failed, ctx->C * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  TB_CUDA(cudaStreamSynchronize(ctx->stream));
   return TB_OK;
 }
 
