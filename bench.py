@@ -266,6 +266,18 @@ def gpu_arm(args):
     x_dev_canon = torch.empty_like(xi_canon)
     ctx.unpack_dev(x.data_ptr(), x_dev_canon.data_ptr())
     assert torch.equal(x_dev_canon.cpu(), x_host), "e2e and device-resident solutions differ"
+    # what bounds e2e: the pinned-memory copy rates of this box, measured with the step's own buffers
+    pcie = {}
+    for name, dst, src in (("h2d_gbs", b_canon, b_host), ("d2h_gbs", x_host, b_canon)):
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        c0.record()
+        for _ in range(5):
+            dst.copy_(src, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        pcie[name] = 5 * src.numel() * 8 / (c0.elapsed_time(c1) * 1e-3) / 1e9
     clocks = sampler.result()  # sampled every 20 ms over warm-up, the timed region and the e2e region
 
     # HMC trajectories/s on the same workload (device-resident update_gauge, hmc.c:671-746, for all chains)
@@ -298,7 +310,8 @@ def gpu_arm(args):
         stream_roof = streaming_roofline(tb, torch, dev, stream)
     other = None
     if not args.no_extra:
-        other = other_configs(tb, torch, dist if world > 1 else None, dev, stream, rank, world)
+        other = other_configs(tb, torch, dist if world > 1 else None, dev, stream, rank, world,
+                              cpu=not args.no_cpu_baseline)
     if rank == 0:
         peak, peak_src = measured_peak()
         sites = NT * NX * chains
@@ -343,7 +356,10 @@ def gpu_arm(args):
                                   / (solve_ms * 1e-3) / 1e12,
                                   "nominal_peak_tflops": 37.0, "peak_source": "B200 datasheet FP64 (not measured)"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(A_host.nbytes + b_host.nbytes),
-                    "d2h_bytes_per_step": int(x_host.nbytes), "ms_per_step": e2e_ms / args.steps},
+                    "d2h_bytes_per_step": int(x_host.nbytes), "ms_per_step": e2e_ms / args.steps,
+                    "pinned_copy_rates_measured": pcie,
+                    "note": "PCIe-bound: the last chain of the second wave (256 chains on 148 SMs) starts one solve "
+                            "after the data of chain 108 have arrived"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
         }
@@ -414,7 +430,24 @@ def streaming_roofline(tb, torch, dev, stream):
             "us_per_iteration": t * 1e6 / it}
 
 
-def other_configs(tb, torch, dist, dev, stream, rank, world):
+def cpu_port_apply_rate(nt, nx, m, iters):
+    """Dirac applies/s of the CPU path on ONE host core at a lattice size where a full reference solve would take
+    minutes to hours (SURVEY 8(c) caveat 4): `iters` CG iterations of the oracle port of fmdm_invert_cg (bit-identical
+    to the reference's, tests/test_oracle_pinned.py), which re-evaluates sin/cos in every apply like hmc.c:140-174."""
+    from oracle.pyoracle import MODE_ADJOINT, Oracle
+
+    orc = Oracle()
+    rng = np.random.default_rng(7)
+    A = rng.uniform(-np.pi, np.pi, size=(nt, nx, 2))
+    b = rng.normal(size=(nt, nx)) + 1j * rng.normal(size=(nt, nx))
+    t0 = time.perf_counter()
+    orc.fmdm_invert_cg(b, A, m, 0.0, MODE_ADJOINT, iters + 1)
+    dt = time.perf_counter() - t0
+    return {"dirac_applies_per_sec": 2 * iters / dt, "cores": 1, "kind": "port",
+            "sample": f"{iters} CG iterations of one {nt}x{nx} chain, {dt:.1f} s"}
+
+
+def other_configs(tb, torch, dist, dev, stream, rank, world, cpu=True):
     """The remaining BASELINE.json configurations, one bounded measurement each (not the headline; parity for
     these shapes is in tests/).  Chains / parameter points shard over ranks like the headline workload: every
     figure is whole-job units over the slowest rank's time."""
@@ -463,6 +496,8 @@ def other_configs(tb, torch, dist, dev, stream, rank, world):
         "converged": bool(np.all(info.status == tb.CG_CONVERGED)),
         "solver": {0: "streaming", 1: "on-chip (CTA per chain)", 2: "on-chip (16-CTA cluster per chain)"}[kind],
         "chains_in_flight": in_flight, "ms_streaming_solver": max_over_ranks(ms_stream)}
+    if world == 1 and cpu:
+        out["256x256_m0.01_g1_8_chains_per_gpu"]["cpu_baseline"] = cpu_port_apply_rate(256, 256, 0.01, 40)
 
     # configs[4]: coupling/mass scan, 32 (g, m) points x 64 chains on 128x128, chiral condensate measurement.
     # 4 points (256 chains) per GPU; per-chain m and g; condensate from stochastic sources through fm_invert_cg.
@@ -592,6 +627,8 @@ def other_configs(tb, torch, dist, dev, stream, rank, world):
             "site_applies_per_sec": 2 * it * nt * nx / (ms * 1e-3),
             "hbm_frac_288B_definition": BYTES_PER_SITE_ITER * nt * nx * it / (ms * 1e-3) / 1e9 / peak,
             "hbm_frac_real_traffic_240B": 240 * nt * nx * it / (ms * 1e-3) / 1e9 / peak, "iterations": it}
+        if cpu:
+            out["2048x2048_single_lattice_1_gpu"]["cpu_baseline"] = cpu_port_apply_rate(2048, 2048, 0.05, 2)
     return out
 
 
