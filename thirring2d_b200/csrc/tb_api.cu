@@ -195,6 +195,7 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
                  ctx->cg.partial, ctx->cg.ticket};
   for (void *p : dev)
     if (p) cudaFree(p);
+  if (ctx->plan_buf) cudaFree(ctx->plan_buf);
   if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   if (ctx->h_iters) cudaFreeHost(ctx->h_iters);

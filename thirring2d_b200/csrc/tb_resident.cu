@@ -356,12 +356,30 @@ struct ResidentWtCfg {
   static_assert(NWARPS == 8, "two warps per TMEM lane quarter; block_sum8");
 };
 
-template <int NT, int NX, bool DAG, bool HAS_MU, bool MASKED>
+// ---- planned launches: balancing a batch that is not a multiple of the SM count --------------------------------------
+// One CTA per chain leaves SMs idle in the last wave (256 chains on 148 SMs: 1.73 waves cost 2).  A solve cannot be
+// made faster by adding SMs, but it can be PAUSED: r, p (registers) and x (tensor memory) of a chain are 192 KB.
+// plan_kernel cuts the concatenated iteration ranges of all chains into one equal share per SM (McNaughton's wrap-
+// around rule for preemptive scheduling; the expected iteration counts are those of the previous solve of the
+// context): every CTA owns a list of segments (chain, first iteration, end iteration).  At most one chain per CTA is
+// split: the CTA that holds its head runs it FIRST (from iteration 1, then stores the state and raises hand[chain]);
+// the CTA that holds its tail runs it LAST, after a spin-wait on hand[chain] that normally finds the flag long set.
+// The head's CTA has the lower block index, so it is dispatched no later than the CTA that waits for it.  The
+// arithmetic of a chain is unaffected (the state round-trips bit for bit): x, the iteration count and the status are
+// those of the one-CTA-per-chain launch.
+struct TbPlan {
+  const int4 *segs;      // (chain, k_begin, k_end, -); k_begin == 1: fresh start; k_end == INT_MAX: to the end
+  const int *seg_lo, *seg_hi;   // [gridDim.x] segment range of a CTA
+  int *hand;             // [C] 0 = head not finished, k > 0 = state stored, resume at iteration k, -1 = chain finished
+  double2 *sr, *sp, *sx; // stored state, [chain][16 tile sites][256 threads]
+};
+
+template <int NT, int NX, bool DAG, bool HAS_MU, bool MASKED, bool PLAN>
 __global__ void __launch_bounds__(ResidentWtCfg<NT, NX>::NTHREADS, 1)
 resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, const double2 *__restrict__ W0g,
                    const double2 *__restrict__ W1g, const double *__restrict__ mass, const double *__restrict__ msite,
                    const double *__restrict__ emu, const double *__restrict__ emmu, const TbCgState s, const int C,
-                   const int c_first) {
+                   const int c_first, const TbPlan plan) {
   using Cfg = ResidentWtCfg<NT, NX>;
   constexpr int V = Cfg::V, NWARPS = Cfg::NWARPS, TX = 2, TT = 8, NG = NX / TX;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -381,11 +399,40 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
   const uint32_t warp = threadIdx.x >> 5;
   const uint32_t xaddr = tmem_base_s + (((warp & 3u) * 32u) << 16) + (warp >> 2) * (uint32_t)TM_SPAN;
 
-  const int c = c_first + blockIdx.x;
   const int tid = threadIdx.x;
   const int g = tid % NG;
   const int t0 = (tid / NG) * TT;
   const int tm = (t0 + NT - 1) % NT, te = (t0 + TT) % NT;   // rows above and below the tile (periodic)
+  // The segment bookkeeping of a planned launch lives in shared memory and is re-read (volatile) where it is needed:
+  // the CG loop has no register to spare (255), and four more live values cost it 16 spill instructions per
+  // iteration and 17 % of its speed.
+  __shared__ int seg_s[4];   // chain (-1: no more work), k_begin, k_end, index of the CTA's next segment
+  volatile int *const sv = seg_s;
+  if (PLAN && tid == 0) sv[3] = plan.seg_lo[blockIdx.x];
+  for (bool more = true; more; more = PLAN) {
+  int c = c_first + blockIdx.x, k_begin = 1;
+  if (PLAN) {
+    __syncthreads();
+    if (tid == 0) {
+      const int sg = sv[3];
+      int4 q = make_int4(-1, 1, 0, 0);
+      if (sg < plan.seg_hi[blockIdx.x]) {
+        q = plan.segs[sg];
+        if (q.y > 1) {   // the tail of a split chain: its head was the first job of a CTA with a lower index
+          int h;
+          while ((h = *(volatile int *)&plan.hand[q.x]) == 0) __nanosleep(200);
+          __threadfence();
+          if (h < 0) q.y = -1;   // the chain ended inside its head
+        }
+      }
+      sv[0] = q.x; sv[1] = q.y; sv[2] = q.z; sv[3] = sg + 1;
+    }
+    __syncthreads();
+    c = sv[0];
+    k_begin = sv[1];
+    if (c < 0) break;
+    if (k_begin < 0) continue;
+  }
   const double m = mass[c];
   const double e_p = emu[c], e_m = emmu[c];
 
@@ -407,8 +454,27 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
     tmem_wait_st();
   }
   double2 r[TT][TX], p[TT][TX];
-  double rr = 0.0;
+  double rr = 0.0, rr_init, rr_old;
   uint32_t occ = 0;   // family B: occupied sites of the tile (identity rows, vec_ops.c:130)
+  if (PLAN && k_begin > 1) {
+    // resume: r, p from the stored state, x back into tensor memory, p published for the stencil
+    const size_t sb = (size_t)c * V + tid;
+#pragma unroll
+    for (int i = 0; i < TT; i++)
+#pragma unroll
+      for (int j = 0; j < TX; j++) {
+        const int f = i * TX + j;
+        r[i][j] = __ldcg(&plan.sr[sb + (size_t)f * Cfg::NTHREADS]);
+        p[i][j] = __ldcg(&plan.sp[sb + (size_t)f * Cfg::NTHREADS]);
+        tmem_st_d2(xaddr + TM_X + 4 * f, __ldcg(&plan.sx[sb + (size_t)f * Cfg::NTHREADS]));
+        Fp[(t0 + i) * NX + j * NG + g] = p[i][j];
+      }
+    tmem_wait_st();
+    rr_old = __ldcg(&s.rr_old[c]);
+    rr_init = __ldcg(&s.rr_init[c]);
+    rr = rr_old;
+    __syncthreads();
+  } else {
 #pragma unroll
   for (int i = 0; i < TT; i++)
 #pragma unroll
@@ -422,14 +488,15 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
       if (MASKED && msite[(size_t)k * C + c] != m) occ |= 1u << (i * TX + j);
     }
   rr = block_sum8(rr, scrA);   // hmc.c:354-356; its barrier publishes p
-  const double rr_init = rr;
-  double rr_old = rr;
-  int status = TB_CG_MAXITER, iters = 0;
+  rr_init = rr;
+  rr_old = rr;
+  }
+  int status = TB_CG_MAXITER, iters = k_begin - 1;
 
-  if (rr_old < s.accuracy) {  // hmc.c:359-361
+  if (rr_old < s.accuracy && k_begin == 1) {  // hmc.c:359-361
     status = TB_CG_ZERO_SOURCE;
   } else {
-    for (int k = 1; k < s.max_iter; k++) {  // hmc.c:364
+    for (int k = k_begin; k < s.max_iter && (!PLAN || k < sv[2]); k++) {  // hmc.c:364
       // Mp = M p (hmc.c:366): every site is published to Fm as soon as it is finished (the last readers of Fm
       // passed the ||r||^2 barrier), and <p, M^dagger M p> = |M p|^2 is accumulated on the way
       double2 mp[TT][TX];
@@ -505,6 +572,36 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
       __syncthreads();
     }
   }
+  if (PLAN) c = sv[0];
+  if (PLAN && status == TB_CG_MAXITER && sv[2] < s.max_iter) {
+    // the head of a split chain ends here: store r, p, x and the two scalars, then raise the chain's flag
+    const size_t sb = (size_t)c * V + tid;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+      uint32_t v[16];
+      tmem_ld16(v, xaddr + TM_X + ch * 16);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int f = ch * 4 + u, i = f / TX, j = f % TX;
+        __stcg(&plan.sr[sb + (size_t)f * Cfg::NTHREADS], r[i][j]);
+        __stcg(&plan.sp[sb + (size_t)f * Cfg::NTHREADS], p[i][j]);
+        __stcg(&plan.sx[sb + (size_t)f * Cfg::NTHREADS],
+               make_double2(__hiloint2double((int)v[4 * u + 1], (int)v[4 * u]),
+                            __hiloint2double((int)v[4 * u + 3], (int)v[4 * u + 2])));
+      }
+    }
+    if (tid == 0) {
+      s.rr_old[c] = rr_old;
+      s.rr_init[c] = rr_init;
+    }
+    __threadfence();
+    __syncthreads();   // every thread's state is out (and every warp has read its tensor-memory columns)
+    if (tid == 0) {
+      __threadfence();
+      *(volatile int *)&plan.hand[c] = sv[2];
+    }
+    continue;
+  }
 #pragma unroll
   for (int ch = 0; ch < 4; ch++) {
     uint32_t v[16];
@@ -519,28 +616,131 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
     }
   }
   __syncthreads();   // every warp has read its columns
-  if (threadIdx.x < 32)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base_s), "r"(TM_COLS_WT) : "memory");
   if (tid == 0) {
     s.status[c] = status;
     s.iters[c] = iters;
     s.rr[c] = rr;
     s.rr_init[c] = rr_init;
     s.active[c] = 0;
+    if (PLAN && sv[2] != 0x7fffffff) {   // the chain ended inside its head: the CTA that holds the tail skips it
+      __threadfence();
+      *(volatile int *)&plan.hand[c] = -1;
+    }
   }
+  }   // segments
+  if (PLAN) __syncthreads();
+  if (threadIdx.x < 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base_s), "r"(TM_COLS_WT) : "memory");
+}
+
+// The schedule of a planned launch (one thread: C is a few hundred).  est = iteration counts of the context's previous
+// solve.  Machines are filled one after the other with T = ceil(sum est / M) iterations each; the chain that straddles
+// the boundary between machine j (its end) and j + 1 (its start) is split: head [1, 1 + first) FIRST on machine
+// j + 1, tail [1 + first, end) LAST on machine j.  Machine j is CTA M - 1 - j, so the head's CTA has the lower index.
+// Without usable estimates (first solve of a context, or a chain that did not converge) chains are dealt out whole,
+// round-robin, which is what the hardware does with one CTA per chain.
+__global__ void plan_kernel(const int *__restrict__ est, const int *__restrict__ status, int C, int M, int4 *segs,
+                            int *seg_lo, int *seg_hi, int *hand) {
+  extern __shared__ int est_s[];   // [C]: one thread walks the chains, out of shared memory
+  __shared__ long long W_s;
+  __shared__ int mx_s, bad_s;
+  if (threadIdx.x == 0) { W_s = 0; mx_s = 0; bad_s = 0; }
+  __syncthreads();
+  long long w = 0;
+  int mx = 0, bad = 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    hand[c] = 0;
+    const int n = est[c];
+    est_s[c] = n;
+    if (n <= 0 || status[c] != TB_CG_CONVERGED) bad = 1;
+    w += n;
+    mx = n > mx ? n : mx;
+  }
+  atomicAdd((unsigned long long *)&W_s, (unsigned long long)w);
+  atomicMax(&mx_s, mx);
+  if (bad) atomicOr(&bad_s, 1);
+  __syncthreads();
+  if (bad_s) {   // chains dealt out whole, round-robin
+    for (int b = threadIdx.x; b < M; b += blockDim.x) {
+      const int per = C / M, extra = C % M;   // CTA b gets chains b, b + M, ...
+      const int lo = b * per + (b < extra ? b : extra), cnt = per + (b < extra ? 1 : 0);
+      seg_lo[b] = lo;
+      seg_hi[b] = lo + cnt;
+      for (int i = 0; i < cnt; i++) segs[lo + i] = make_int4(b + i * M, 1, 0x7fffffff, 0);
+    }
+    return;
+  }
+  if (threadIdx.x != 0) return;
+  const int INF = 0x7fffffff, MINS = 8;
+  long long T = (W_s + M - 1) / M;
+  if (T < mx_s) T = mx_s;
+  int nseg = 0, j = 0;
+  long long rem = T;
+  seg_lo[M - 1] = 0;
+  for (int c = 0; c < C; c++) {
+    const int n = est_s[c];
+    if (rem < MINS && j < M - 1) {   // machine j is full
+      seg_hi[M - 1 - j] = nseg;
+      j++;
+      seg_lo[M - 1 - j] = nseg;
+      rem = T;
+    }
+    const long long first = n - rem;   // iterations that do not fit machine j
+    if (j == M - 1 || first < MINS) {  // whole (a few iterations over the share are cheaper than a hand-over)
+      segs[nseg++] = make_int4(c, 1, INF, 0);
+      rem = first > 0 ? 0 : rem - n;
+    } else {
+      segs[nseg++] = make_int4(c, 1 + (int)first, INF, 0);   // tail: last job of machine j
+      seg_hi[M - 1 - j] = nseg;
+      j++;
+      seg_lo[M - 1 - j] = nseg;
+      segs[nseg++] = make_int4(c, 1, 1 + (int)first, 0);     // head: first job of machine j + 1
+      rem = T - first;
+    }
+  }
+  seg_hi[M - 1 - j] = nseg;
+  for (j++; j < M; j++) seg_lo[M - 1 - j] = seg_hi[M - 1 - j] = nseg;
 }
 
 template <int NT, int NX>
 int launch_resident_wt(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st) {
   using Cfg = ResidentWtCfg<NT, NX>;
   const bool dag = tb_conj_is_dagger(ctx);
-  auto kern = resident_wt_kernel<NT, NX, false, false, false>;
-  if (ctx->msite) kern = ctx->has_mu ? resident_wt_kernel<NT, NX, true, true, true> : resident_wt_kernel<NT, NX, true, false, true>;
-  else if (dag) kern = ctx->has_mu ? resident_wt_kernel<NT, NX, true, true, false> : resident_wt_kernel<NT, NX, true, false, false>;
-  else if (ctx->has_mu) kern = resident_wt_kernel<NT, NX, false, true, false>;
+  // whole batches larger than the SM count are balanced over the SMs (see TbPlan)
+  int nsm = TB_NUM_SMS_B200;
+  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
+  // worth it when the last wave of a plain launch is less than ~3/4 full: a planned launch costs about 4 % (a third
+  // segment per CTA: links and state in and out once more), measured 256 chains +10 %, 200 +38 %, 296 -4 %, 1000 -1 %
+  const bool plan = c0 == 0 && n == ctx->C && n > nsm && n <= 40000 && !ctx->msite && !getenv("TB_NO_PLAN") &&
+                    (double)((n + nsm - 1) / nsm) * nsm >= 1.06 * n;
+  TbPlan pl = {};
+  if (plan) {
+    if (!ctx->plan_buf) TB_CUDA(cudaMalloc((void **)&ctx->plan_buf, ((size_t)(ctx->C + nsm) * 4 + 2 * nsm + ctx->C) * sizeof(int)));
+    int4 *segs = (int4 *)ctx->plan_buf;
+    int *lo = ctx->plan_buf + (size_t)(ctx->C + nsm) * 4, *hi = lo + nsm, *hand = hi + nsm;
+    if (ctx->C > 12000)
+      TB_CUDA(cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->C * (int)sizeof(int)));
+    plan_kernel<<<1, 256, ctx->C * sizeof(int), st>>>(ctx->cg.iters, ctx->cg.status, ctx->C, nsm, segs, lo, hi, hand);
+    ctx->launches++;
+    pl.segs = segs; pl.seg_lo = lo; pl.seg_hi = hi; pl.hand = hand;
+    pl.sr = ctx->r; pl.sp = ctx->p; pl.sx = ctx->q;
+    auto kern = resident_wt_kernel<NT, NX, false, false, false, true>;
+    if (dag) kern = ctx->has_mu ? resident_wt_kernel<NT, NX, true, true, false, true> : resident_wt_kernel<NT, NX, true, false, false, true>;
+    else if (ctx->has_mu) kern = resident_wt_kernel<NT, NX, false, true, false, true>;
+    TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
+    kern<<<nsm, Cfg::NTHREADS, Cfg::SMEM, st>>>(b, x, ctx->W0, ctx->W1, ctx->d_mass, ctx->msite, ctx->d_emu, ctx->d_emmu,
+                                                ctx->cg, ctx->C, 0, pl);
+    ctx->launches++;
+    TB_CUDA(cudaGetLastError());
+    return TB_OK;
+  }
+  auto kern = resident_wt_kernel<NT, NX, false, false, false, false>;
+  if (ctx->msite) kern = ctx->has_mu ? resident_wt_kernel<NT, NX, true, true, true, false> : resident_wt_kernel<NT, NX, true, false, true, false>;
+  else if (dag) kern = ctx->has_mu ? resident_wt_kernel<NT, NX, true, true, false, false> : resident_wt_kernel<NT, NX, true, false, false, false>;
+  else if (ctx->has_mu) kern = resident_wt_kernel<NT, NX, false, true, false, false>;
   TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   kern<<<n, Cfg::NTHREADS, Cfg::SMEM, st>>>(b, x, ctx->W0, ctx->W1, ctx->d_mass, ctx->msite, ctx->d_emu, ctx->d_emmu,
-                                            ctx->cg, ctx->C, c0);
+                                            ctx->cg, ctx->C, c0, pl);
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
   return TB_OK;
