@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 #include <unistd.h>
 
 #include "../../include/thirring_b200.h"
@@ -38,8 +39,12 @@ int main(int argc, char **argv) {
   if (!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 2; }
   int (*hmc_main)(void) = (int (*)(void))dlsym(h, "hmc_main");
   if (!hmc_main) { fprintf(stderr, "hmc_main not found: %s\n", dlerror()); return 2; }
+  struct timespec t0, t1;   /* wall clock of the driver alone: CUDA start-up happened in tb_hmc_configure */
+  clock_gettime(CLOCK_MONOTONIC, &t0);
   int rc = hmc_main();
+  clock_gettime(CLOCK_MONOTONIC, &t1);
   fflush(stdout);
+  fprintf(stderr, "hmc_main_seconds=%.6f\n", (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec));
   fprintf(stderr, "hmc_b200: %ld CG solves and %ld Dirac applies served by the GPU library, %ld whole trajectories\n",
           tb_hmc_cg_calls(), tb_hmc_apply_calls(), tb_hmc_trajectory_calls());
   tb_hmc_shutdown();

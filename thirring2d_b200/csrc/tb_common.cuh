@@ -134,6 +134,7 @@ struct tb_ctx {
   double2 *stage_x;  // second canonical staging buffer (results)
   double last_solve_ms;
   long long launches;
+  int plan_m;     // machines the plan buffer was sized for
   int *plan_buf;  // planned launches of the on-chip solver (tb_resident.cu: TbPlan): segments, ranges, hand-over flags
   // slab mode (nranks > 1): ctx->nt is the LOCAL number of rows
   int nranks, rank, nt_global, t_off;

@@ -203,3 +203,119 @@ __device__ __forceinline__ void tmem_x_axpy(uint32_t xaddr, const double2 (&p)[8
   }
   tmem_wait_st();
 }
+
+// ---- planned launches: balancing a batch that is not a multiple of the SM count --------------------------------------
+// One CTA (or cluster) per chain leaves SMs idle in the last wave (256 chains on 148 SMs: 1.73 waves cost 2).  A solve cannot be
+// made faster by adding SMs, but it can be PAUSED: r, p (registers) and x (tensor memory) of a chain are 192 KB.
+// plan_kernel cuts the concatenated iteration ranges of all chains into one equal share per SM (McNaughton's wrap-
+// around rule for preemptive scheduling; the expected iteration counts are those of the previous solve of the
+// context): every CTA owns a list of segments (chain, first iteration, end iteration).  At most one chain per CTA is
+// split: the CTA that holds its head runs it FIRST (from iteration 1, then stores the state and raises hand[chain]);
+// the CTA that holds its tail runs it LAST, after a spin-wait on hand[chain] that normally finds the flag long set.
+// The head's CTA has the lower block index, so it is dispatched no later than the CTA that waits for it.  The
+// arithmetic of a chain is unaffected (the state round-trips bit for bit): x, the iteration count and the status are
+// those of the one-CTA-per-chain launch.
+struct TbPlan {
+  const int4 *segs;      // (chain, k_begin, k_end, -); k_begin == 1: fresh start; k_end == INT_MAX: to the end
+  const int *seg_lo, *seg_hi;   // [gridDim.x] segment range of a CTA
+  int *hand;             // [C] 0 = head not finished, k > 0 = state stored, resume at iteration k, -1 = chain finished
+  double2 *sr, *sp, *sx; // stored state, [chain][16 tile sites][256 threads]
+};
+
+
+// The schedule of a planned launch (one thread: C is a few hundred).  est = iteration counts of the context's previous
+// solve.  Machines are filled one after the other with T = ceil(sum est / M) iterations each; the chain that straddles
+// the boundary between machine j (its end) and j + 1 (its start) is split: head [1, 1 + first) FIRST on machine
+// j + 1, tail [1 + first, end) LAST on machine j.  Machine j is CTA M - 1 - j, so the head's CTA has the lower index.
+// Without usable estimates (first solve of a context, or a chain that did not converge) chains are dealt out whole,
+// round-robin, which is what the hardware does with one CTA per chain.
+__global__ void plan_kernel(const int *__restrict__ est, const int *__restrict__ status, int C, int M, int4 *segs,
+                            int *seg_lo, int *seg_hi, int *hand) {
+  extern __shared__ int est_s[];   // [C]: one thread walks the chains, out of shared memory
+  __shared__ long long W_s;
+  __shared__ int mx_s, bad_s;
+  if (threadIdx.x == 0) { W_s = 0; mx_s = 0; bad_s = 0; }
+  __syncthreads();
+  long long w = 0;
+  int mx = 0, bad = 0;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    hand[c] = 0;
+    const int n = est[c];
+    est_s[c] = n;
+    if (n <= 0 || status[c] != TB_CG_CONVERGED) bad = 1;
+    w += n;
+    mx = n > mx ? n : mx;
+  }
+  atomicAdd((unsigned long long *)&W_s, (unsigned long long)w);
+  atomicMax(&mx_s, mx);
+  if (bad) atomicOr(&bad_s, 1);
+  __syncthreads();
+  if (bad_s) {   // chains dealt out whole, round-robin
+    for (int b = threadIdx.x; b < M; b += blockDim.x) {
+      const int per = C / M, extra = C % M;   // CTA b gets chains b, b + M, ...
+      const int lo = b * per + (b < extra ? b : extra), cnt = per + (b < extra ? 1 : 0);
+      seg_lo[b] = lo;
+      seg_hi[b] = lo + cnt;
+      for (int i = 0; i < cnt; i++) segs[lo + i] = make_int4(b + i * M, 1, 0x7fffffff, 0);
+    }
+    return;
+  }
+  if (threadIdx.x != 0) return;
+  const int INF = 0x7fffffff, MINS = 8;
+  long long T = (W_s + M - 1) / M;
+  if (T < mx_s) T = mx_s;
+  int nseg = 0, j = 0;
+  long long rem = T;
+  seg_lo[M - 1] = 0;
+  for (int c = 0; c < C; c++) {
+    const int n = est_s[c];
+    if (rem < MINS && j < M - 1) {   // machine j is full
+      seg_hi[M - 1 - j] = nseg;
+      j++;
+      seg_lo[M - 1 - j] = nseg;
+      rem = T;
+    }
+    const long long first = n - rem;   // iterations that do not fit machine j
+    if (j == M - 1 || first < MINS) {  // whole (a few iterations over the share are cheaper than a hand-over)
+      segs[nseg++] = make_int4(c, 1, INF, 0);
+      rem = first > 0 ? 0 : rem - n;
+    } else {
+      segs[nseg++] = make_int4(c, 1 + (int)first, INF, 0);   // tail: last job of machine j
+      seg_hi[M - 1 - j] = nseg;
+      j++;
+      seg_lo[M - 1 - j] = nseg;
+      segs[nseg++] = make_int4(c, 1, 1 + (int)first, 0);     // head: first job of machine j + 1
+      rem = T - first;
+    }
+  }
+  seg_hi[M - 1 - j] = nseg;
+  for (j++; j < M; j++) seg_lo[M - 1 - j] = seg_hi[M - 1 - j] = nseg;
+}
+
+
+// plan_kernel on the context's stream; M = CTAs (64^2) or clusters (128^2, 256^2) of the planned launch
+static int plan_prepare(tb_ctx *ctx, int M, cudaStream_t st, TbPlan *pl) {
+  const int C = ctx->C;
+  if (!ctx->plan_buf) {
+    const int mmax = TB_NUM_SMS_B200 > M ? TB_NUM_SMS_B200 : M;
+    TB_CUDA(cudaMalloc((void **)&ctx->plan_buf, ((size_t)(C + mmax) * 4 + 2 * mmax + C) * sizeof(int)));
+    ctx->plan_m = mmax;
+  }
+  if (M > ctx->plan_m) { tb_set_error("plan_prepare: %d machines, buffer holds %d", M, ctx->plan_m); return TB_EINVAL; }
+  int4 *segs = (int4 *)ctx->plan_buf;
+  int *lo = ctx->plan_buf + (size_t)(C + ctx->plan_m) * 4, *hi = lo + ctx->plan_m, *hand = hi + ctx->plan_m;
+  if (C > 12000) TB_CUDA(cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C * (int)sizeof(int)));
+  plan_kernel<<<1, 256, C * sizeof(int), st>>>(ctx->cg.iters, ctx->cg.status, C, M, segs, lo, hi, hand);
+  ctx->launches++;
+  pl->segs = segs; pl->seg_lo = lo; pl->seg_hi = hi; pl->hand = hand;
+  pl->sr = ctx->r; pl->sp = ctx->p; pl->sx = ctx->q;
+  return TB_OK;
+}
+
+// worth it when the last wave of a plain launch is less than ~3/4 full: a planned launch costs about 4 % (a third
+// segment per CTA: links and state in and out once more); measured at 64^2: 256 chains +10 %, 200 +38 %, 296 -4 %,
+// 1000 -1 %
+static bool plan_pays(const tb_ctx *ctx, int c0, int n, int M) {
+  return c0 == 0 && n == ctx->C && n > M && n <= 40000 && !ctx->msite && !getenv("TB_NO_PLAN") &&
+         (double)((n + M - 1) / M) * M >= 1.06 * n;
+}
