@@ -101,3 +101,52 @@ def test_planned_launch_with_max_iter_inside_a_head(whole_batch):
         assert np.all(short[1].status == tb.CG_MAXITER) and np.all(short[1].iters == 60)
         same(solve(ctx, b, planned=False), short)
         same(solve(ctx, b, planned=True), short)       # previous solve not converged: dealt out whole
+
+
+@pytest.mark.parametrize("nt,nx,C,mu", [(128, 128, 40, 0.0), (128, 128, 50, 0.1), (256, 256, 8, 0.0), (64, 128, 90, 0.0)])
+def test_planned_cluster_launch_is_bitwise_the_plain_launch(whole_batch, oracle, nt, nx, C, mu):
+    """The same for the cluster solver (tb_cluster.cu): a batch that fills its last wave of clusters badly (8 chains of
+    256^2 on 7 co-resident clusters of 16 CTAs) is cut into one share per cluster; the state of a split chain (r, p, x
+    of every slab) crosses from one cluster to another through HBM."""
+    rng = np.random.default_rng(29)
+    A = smooth_gauge(rng, C, nt, nx, 0.4)
+    xi = random_vector(rng, C, nt, nx)
+    xi[1] = 0.0
+    m = np.exp(rng.uniform(np.log(0.05), np.log(0.6), size=C))
+    with tb.Context(nt, nx, C, tb.MODE_ADJOINT, m=m, mu=mu) as ctx:
+        kind, capacity = ctx.solver_info()
+        if kind != 2 or C <= capacity:
+            pytest.skip(f"no cluster shape on this device, or one wave holds the batch: kind {kind}, {capacity} clusters")
+        ctx.set_gauge(A)
+        b = ctx.fm_conjugate_mul(xi)
+        n0 = ctx.launch_count
+        ref = solve(ctx, b, planned=False)
+        n1 = ctx.launch_count
+        solve(ctx, b, planned=True)
+        assert ctx.launch_count - n1 == n1 - n0 + 1, "the planned path (one more launch: the scheduler) did not run"
+        assert ref[1].status[1] == tb.CG_ZERO_SOURCE and np.all(np.delete(ref[1].status, 1) == tb.CG_CONVERGED)
+        same(solve(ctx, b, planned=True), ref)          # a chain without an estimate: dealt out whole
+        b2 = b.copy()
+        b2[1] = b[2]
+        ref2 = solve(ctx, b2, planned=False)
+        same(solve(ctx, b2, planned=True), ref2)        # split chains
+        same(solve(ctx, b2, planned=True), ref2)
+        ctx.set_params(m[::-1].copy(), mu)              # estimates that are badly wrong
+        ref3 = solve(ctx, b2, planned=False)
+        ctx.set_params(m, mu)
+        solve(ctx, b2, planned=False)
+        ctx.set_params(m[::-1].copy(), mu)
+        same(solve(ctx, b2, planned=True), ref3)
+        ctx.set_cg(1e-30, 31)                           # max_iter inside the heads
+        short = solve(ctx, b2, planned=True)
+        assert np.all(short[1].status == tb.CG_MAXITER) and np.all(short[1].iters == 30)
+        same(solve(ctx, b2, planned=False), short)
+        ctx.set_cg(1e-30, 100000)
+        ctx.set_params(m, mu)
+        solve(ctx, b2, planned=False)
+        x, info2 = solve(ctx, b2, planned=True)
+        if nt * nx <= 128 * 128:
+            c = C - 1
+            xo, st, it, rr = oracle.fmdm_invert_cg(b2[c], A[c], float(m[c]), mu, tb.MODE_ADJOINT)
+            assert st == info2.status[c] and abs(it - int(info2.iters[c])) <= 1
+            assert_close(x[c], xo, CG_SOL_TOL, "planned cluster launch vs oracle")

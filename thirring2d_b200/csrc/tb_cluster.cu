@@ -109,12 +109,16 @@ __device__ __forceinline__ void push_rows(const double2 (&v)[TT][TX], int hset, 
   }
 }
 
-template <int NX, int CS, bool DAG, bool HAS_MU, bool MASKED>
+// PLAN: the grid is one cluster per "machine" of a planned launch (tb_onchip.cuh: TbPlan) and every cluster works
+// through its list of segments; a chain that is split is stored by the cluster that ran its head (r, p, x of every
+// slab, the flag raised by rank 0 after a cluster barrier) and picked up by the cluster that runs its tail.  Every
+// CTA of a cluster reads the same segment list and the same flag, so the cluster takes every decision as one.
+template <int NX, int CS, bool DAG, bool HAS_MU, bool MASKED, bool PLAN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, const double2 *__restrict__ W0g,
                   const double2 *__restrict__ W1g, const double *__restrict__ mass, const double *__restrict__ msite,
                   const double *__restrict__ emu, const double *__restrict__ emmu, const TbCgState s, const int C,
-                  const int c_first) {
+                  const int c_first, const TbPlan plan) {
   using G = Slab<NX>;
   constexpr int LT = G::LT, NGX = G::NGX, NT = CS * LT;
   static_assert(CS >= 2 && CS <= 16, "slot tables hold 16 ranks");
@@ -143,19 +147,47 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
 
   const uint32_t rank = cluster_ctarank();
   const uint32_t rank_m = (rank + CS - 1) % CS, rank_p = (rank + 1) % CS;
-  const int c = c_first + (int)(blockIdx.x / CS);
   const int tid = threadIdx.x;
   const int g = tid % NGX;
   const int t0 = (tid / NGX) * TT;
   const bool top = t0 == 0, bot = t0 + TT == LT;   // warp-uniform
-  const double m = mass[c];
-  const double e_p = emu[c], e_m = emmu[c];
   const int tg0 = (int)rank * LT;   // first global row of the slab
   // rows above / below the tile: own exchange field, or the halo rows the neighbour CTAs push
   const double2 *p_dn = top ? S + G::OFF_HP + G::H_DN : Fp + (t0 - 1) * NX;
   const double2 *p_up = bot ? S + G::OFF_HP + G::H_UP : Fp + (t0 + TT) * NX;
   const double2 *m_dn = top ? S + G::OFF_HM + G::H_DN : Fm + (t0 - 1) * NX;
   const double2 *m_up = bot ? S + G::OFF_HM + G::H_UP : Fm + (t0 + TT) * NX;
+  // segment bookkeeping of a planned launch: in shared memory, re-read where needed (the CG loop has no register to
+  // spare, see resident_wt_kernel)
+  __shared__ int seg_s[4];   // chain (-1: no more work), k_begin, k_end, index of the cluster's next segment
+  volatile int *const sv = seg_s;
+  if (PLAN && tid == 0) sv[3] = plan.seg_lo[blockIdx.x / CS];
+  for (bool more = true; more; more = PLAN) {
+  int c = c_first + (int)(blockIdx.x / CS), k_begin = 1;
+  if (PLAN) {
+    __syncthreads();
+    if (tid == 0) {
+      const int sg = sv[3];
+      int4 q = make_int4(-1, 1, 0, 0);
+      if (sg < plan.seg_hi[blockIdx.x / CS]) {
+        q = plan.segs[sg];
+        if (q.y > 1) {   // the tail of a split chain: its head was the first job of a cluster with a lower index
+          int h;
+          while ((h = *(volatile int *)&plan.hand[q.x]) == 0) __nanosleep(200);
+          __threadfence();
+          if (h < 0) q.y = -1;   // the chain ended inside its head
+        }
+      }
+      sv[0] = q.x; sv[1] = q.y; sv[2] = q.z; sv[3] = sg + 1;
+    }
+    __syncthreads();
+    c = sv[0];
+    k_begin = sv[1];
+    if (c < 0) break;
+    if (k_begin < 0) continue;
+  }
+  const double m = mass[c];
+  const double e_p = emu[c], e_m = emmu[c];
 
   // links of the tile and of its backward halo: device layout [site][chain] -> tensor memory
   {
@@ -175,8 +207,31 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
     tmem_wait_st();
   }
   double2 r[TT][TX], p[TT][TX];
-  double rr = 0.0;
+  double rr = 0.0, rr_init, rr_old;
   uint32_t occ = 0;   // family B: occupied sites of the tile (identity rows, vec_ops.c:130)
+  if (PLAN && k_begin > 1) {
+    // resume: r, p from the stored state, x back into tensor memory, p published for the stencil
+    const size_t sb = ((size_t)c * CS + rank) * VL + tid;
+#pragma unroll
+    for (int i = 0; i < TT; i++)
+#pragma unroll
+      for (int j = 0; j < TX; j++) {
+        const int f = i * TX + j;
+        r[i][j] = __ldcg(&plan.sr[sb + (size_t)f * NTHREADS]);
+        p[i][j] = __ldcg(&plan.sp[sb + (size_t)f * NTHREADS]);
+        tmem_st_d2(xaddr + TM_X + 4 * f, __ldcg(&plan.sx[sb + (size_t)f * NTHREADS]));
+        Fp[(t0 + i) * NX + j * NGX + g] = p[i][j];
+      }
+    tmem_wait_st();
+    rr_old = __ldcg(&s.rr_old[c]);
+    rr_init = __ldcg(&s.rr_init[c]);
+    rr = rr_old;
+    // every CTA of the cluster has left its previous segment before anyone stores into a peer's shared memory
+    cluster_arrive();
+    cluster_wait();
+    push_rows<NX>(p, G::OFF_HP, smem_base, rank_m, rank_p, top, bot, g);
+    __syncthreads();   // p is published inside the CTA
+  } else {
 #pragma unroll
   for (int i = 0; i < TT; i++)
 #pragma unroll
@@ -189,7 +244,8 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
       Fp[(t0 + i) * NX + j * NGX + g] = p[i][j];
       if (MASKED && msite[gs * C + c] != m) occ |= 1u << (i * TX + j);
     }
-  // every CTA of the cluster is running before anyone stores into a peer's shared memory
+  // every CTA of the cluster is running (planned launch: has left its previous segment) before anyone stores into a
+  // peer's shared memory
   cluster_arrive();
   cluster_wait();
   push_rows<NX>(p, G::OFF_HP, smem_base, rank_m, rank_p, top, bot, g);
@@ -197,16 +253,17 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   cluster_arrive();
   cluster_wait();
   rr = cluster_total<CS>(slotA);
-  const double rr_init = rr;
-  double rr_old = rr;
-  int status = TB_CG_MAXITER, iters = 0;
+  rr_init = rr;
+  rr_old = rr;
+  }
+  int status = TB_CG_MAXITER, iters = k_begin - 1;
 
-  if (rr_old < s.accuracy) {  // hmc.c:359-361
+  if (rr_old < s.accuracy && k_begin == 1) {  // hmc.c:359-361
     status = TB_CG_ZERO_SOURCE;
   } else {
     cluster_arrive();   // pairs with the wait inside the first stencil (p and its halos are already published)
-    if (s.max_iter <= 1) cluster_wait();   // no iteration will run: close the barrier
-    for (int k = 1; k < s.max_iter; k++) {  // hmc.c:364
+    if (k_begin >= s.max_iter || (PLAN && k_begin >= sv[2])) cluster_wait();   // no iteration will run: close the barrier
+    for (int k = k_begin; k < s.max_iter && (!PLAN || k < sv[2]); k++) {  // hmc.c:364
       // ---- Mp = M p (hmc.c:366).  Finished sites go to Fm at once (its last readers passed the ||r||^2
       // barrier); the first row of the slab waits for its hop from the halo row.
       double2 mp[TT][TX];
@@ -316,8 +373,40 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
       rr_old = rr;
       __syncthreads();    // p is published inside the CTA
       cluster_arrive();   // and its halos are on their way; the wait is in the middle of the next stencil
-      if (k + 1 >= s.max_iter) cluster_wait();   // loop ends here: close the barrier
+      if (k + 1 >= s.max_iter || (PLAN && k + 1 >= sv[2])) cluster_wait();   // loop ends here: close the barrier
     }
+  }
+  if (PLAN) c = sv[0];
+  if (PLAN && status == TB_CG_MAXITER && sv[2] < s.max_iter) {
+    // the head of a split chain ends here: every slab stores r, p, x, rank 0 the two scalars; after a cluster
+    // barrier rank 0 raises the chain's flag
+    const size_t sb = ((size_t)c * CS + rank) * VL + tid;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) {
+      uint32_t v[16];
+      tmem_ld16(v, xaddr + TM_X + ch * 16);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int f = ch * 4 + u, i = f / TX, j = f % TX;
+        __stcg(&plan.sr[sb + (size_t)f * NTHREADS], r[i][j]);
+        __stcg(&plan.sp[sb + (size_t)f * NTHREADS], p[i][j]);
+        __stcg(&plan.sx[sb + (size_t)f * NTHREADS],
+               make_double2(__hiloint2double((int)v[4 * u + 1], (int)v[4 * u]),
+                            __hiloint2double((int)v[4 * u + 3], (int)v[4 * u + 2])));
+      }
+    }
+    if (tid == 0 && rank == 0) {
+      s.rr_old[c] = rr_old;
+      s.rr_init[c] = rr_init;
+    }
+    __threadfence();
+    cluster_arrive();   // every thread of every slab has its state out (and has read its tensor-memory columns)
+    cluster_wait();
+    if (tid == 0 && rank == 0) {
+      __threadfence();
+      *(volatile int *)&plan.hand[c] = sv[2];
+    }
+    continue;
   }
 #pragma unroll
   for (int ch = 0; ch < 4; ch++) {
@@ -333,25 +422,35 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
     }
   }
   __syncthreads();   // every warp has read its columns
-  if (threadIdx.x < 32)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base_s), "r"(TM_COLS_WT) : "memory");
   if (tid == 0 && rank == 0) {
     s.status[c] = status;
     s.iters[c] = iters;
     s.rr[c] = rr;
     s.rr_init[c] = rr_init;
     s.active[c] = 0;
+    if (PLAN && sv[2] != 0x7fffffff) {   // the chain ended inside its head: the cluster that holds the tail skips it
+      __threadfence();
+      *(volatile int *)&plan.hand[c] = -1;
+    }
   }
+  }   // segments
+  if (PLAN) __syncthreads();
+  if (threadIdx.x < 32)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base_s), "r"(TM_COLS_WT) : "memory");
 }
 
 template <int NX, int CS>
 struct ClusterLaunch {
   using Kern = void (*)(const double2 *, double2 *, const double2 *, const double2 *, const double *, const double *,
-                        const double *, const double *, const TbCgState, const int, const int);
+                        const double *, const double *, const TbCgState, const int, const int, const TbPlan);
   static Kern pick(bool dag, bool has_mu, bool masked = false) {
-    if (masked) return has_mu ? cluster_cg_kernel<NX, CS, true, true, true> : cluster_cg_kernel<NX, CS, true, false, true>;
-    if (dag) return has_mu ? cluster_cg_kernel<NX, CS, true, true, false> : cluster_cg_kernel<NX, CS, true, false, false>;
-    return has_mu ? cluster_cg_kernel<NX, CS, false, true, false> : cluster_cg_kernel<NX, CS, false, false, false>;
+    if (masked) return has_mu ? cluster_cg_kernel<NX, CS, true, true, true, false> : cluster_cg_kernel<NX, CS, true, false, true, false>;
+    if (dag) return has_mu ? cluster_cg_kernel<NX, CS, true, true, false, false> : cluster_cg_kernel<NX, CS, true, false, false, false>;
+    return has_mu ? cluster_cg_kernel<NX, CS, false, true, false, false> : cluster_cg_kernel<NX, CS, false, false, false, false>;
+  }
+  // planned launches exist for M~ = M^dagger without an occupation mask (the production mode of the HMC solve)
+  static Kern pick_planned(bool has_mu) {
+    return has_mu ? cluster_cg_kernel<NX, CS, true, true, false, true> : cluster_cg_kernel<NX, CS, true, false, false, true>;
   }
   static int config(Kern kern, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, int nclusters, cudaStream_t st) {
     TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Slab<NX>::SMEM));
@@ -370,8 +469,7 @@ struct ClusterLaunch {
     return TB_OK;
   }
   // how many clusters of this shape the device can hold at once (0 = cannot be scheduled at all)
-  static int max_active(bool dag, bool has_mu) {
-    Kern kern = pick(dag, has_mu);
+  static int max_active(Kern kern) {
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
     if (config(kern, &cfg, attr, 1, nullptr) != TB_OK) return 0;
@@ -382,14 +480,34 @@ struct ClusterLaunch {
     }
     return n;
   }
+  static int max_active(bool dag, bool has_mu) { return max_active(pick(dag, has_mu)); }
   static int launch(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st) {
-    Kern kern = pick(tb_conj_is_dagger(ctx), ctx->has_mu, ctx->msite != nullptr);
+    const bool dag = tb_conj_is_dagger(ctx);
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
+    TbPlan pl = {};
+    // a whole batch that fills its last wave of clusters badly (256^2: 8 chains on 7 clusters of 16) is cut into one
+    // equal share of CG iterations per co-resident cluster; the grid of a planned launch is exactly one wave, so the
+    // cluster that waits for a hand-over and the cluster that produces it are always on the device together
+    if (dag && plan_pays(ctx, c0, n, tb_cluster_capacity(ctx))) {
+      Kern kp = pick_planned(ctx->has_mu);
+      int cap = max_active(kp);
+      if (cap > tb_cluster_capacity(ctx)) cap = tb_cluster_capacity(ctx);
+      if (cap > 0 && plan_pays(ctx, c0, n, cap)) {
+        TB_CHECK(plan_prepare(ctx, cap, st, &pl));
+        TB_CHECK(config(kp, &cfg, attr, cap, st));
+        TB_CUDA(cudaLaunchKernelEx(&cfg, kp, b, x, (const double2 *)ctx->W0, (const double2 *)ctx->W1,
+                                   (const double *)ctx->d_mass, (const double *)ctx->msite, (const double *)ctx->d_emu,
+                                   (const double *)ctx->d_emmu, ctx->cg, ctx->C, 0, pl));
+        ctx->launches++;
+        return TB_OK;
+      }
+    }
+    Kern kern = pick(dag, ctx->has_mu, ctx->msite != nullptr);
     TB_CHECK(config(kern, &cfg, attr, n, st));
     TB_CUDA(cudaLaunchKernelEx(&cfg, kern, b, x, (const double2 *)ctx->W0, (const double2 *)ctx->W1,
                                (const double *)ctx->d_mass, (const double *)ctx->msite, (const double *)ctx->d_emu,
-                               (const double *)ctx->d_emmu, ctx->cg, ctx->C, c0));
+                               (const double *)ctx->d_emmu, ctx->cg, ctx->C, c0, pl));
     ctx->launches++;
     return TB_OK;
   }
