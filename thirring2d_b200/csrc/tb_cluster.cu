@@ -172,8 +172,7 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
       if (sg < plan.seg_hi[blockIdx.x / CS]) {
         q = plan.segs[sg];
         if (q.y > 1) {   // the tail of a split chain: its head was the first job of a cluster with a lower index
-          int h;
-          while ((h = *(volatile int *)&plan.hand[q.x]) == 0) __nanosleep(200);
+          const int h = plan_wait_hand(&plan.hand[q.x]);
           __threadfence();
           if (h < 0) q.y = -1;   // the chain ended inside its head
         }

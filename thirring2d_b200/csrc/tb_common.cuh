@@ -41,6 +41,7 @@ struct TbGeom {
   int R;              // row length in sites*chains = nx*C
   int bc, bx;         // block tile: chains x x-sites (powers of two), bc*bx threads
   int bc_shift;       // log2(bc)
+  int ta_shift;       // log2 of the chain-tile width that TbCgState::tile_active counts in (the marching kernels' bc)
   int nctiles, nxtiles, nttiles;
   int tt;             // rows marched per thread
   int nslots;         // partial sums per chain = nxtiles*nttiles
@@ -100,6 +101,8 @@ struct tb_ctx {
   cudaStream_t stream;
   bool own_stream;
   TbGeom g;
+  TbGeom gp;        // geometry of the TMA-staged streaming kernels (tb_stream.cu: *_pipe_kernel): same tiles, taller blocks
+  bool pipe_ok;     // the lattice / batch has a TMA-staged shape (whole tiles, chain runs of whole 16-byte multiples)
   int tune_tt, tune_chunk, tune_solver;
   int resident_x_tmem;  // resident solver: keep x in tensor memory (1, default) or in an L2 workspace (0)
   int cluster_capacity; // cluster solver: co-resident clusters of this lattice's shape (-1 = not queried yet)

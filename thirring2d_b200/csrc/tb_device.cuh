@@ -170,7 +170,7 @@ __device__ __forceinline__ void reduce_finalize(double acc, const TbGeom &g, con
   }
   if (threadIdx.x == 0) s.ticket[b.ctile] = 0u;
   if (!SLAB) {
-    if (b.x_local == 0 && b.c < g.C) finalize_scalar<FIN>(red[b.c_local], b.c, b.ctile, s);
+    if (b.x_local == 0 && b.c < g.C) finalize_scalar<FIN>(red[b.c_local], b.c, b.c >> g.ta_shift, s);
   } else {
     const int seq = *sl.seq;
     if (b.x_local == 0) {

@@ -215,12 +215,27 @@ __device__ __forceinline__ void tmem_x_axpy(uint32_t xaddr, const double2 (&p)[8
 // The head's CTA has the lower block index, so it is dispatched no later than the CTA that waits for it.  The
 // arithmetic of a chain is unaffected (the state round-trips bit for bit): x, the iteration count and the status are
 // those of the one-CTA-per-chain launch.
+// The wait for a hand-over normally finds the flag set.  It can only last if blocks were not dispatched in index
+// order (the head's block has the lower index); after ~10 s the kernel traps rather than hang the device.
+#define TB_PLAN_SPIN_CYCLES 20000000000LL
 struct TbPlan {
   const int4 *segs;      // (chain, k_begin, k_end, -); k_begin == 1: fresh start; k_end == INT_MAX: to the end
   const int *seg_lo, *seg_hi;   // [gridDim.x] segment range of a CTA
   int *hand;             // [C] 0 = head not finished, k > 0 = state stored, resume at iteration k, -1 = chain finished
   double2 *sr, *sp, *sx; // stored state, [chain][16 tile sites][256 threads]
 };
+
+// one thread: wait until the head of a split chain has been stored (k > 0) or the chain has ended (-1).  Not inlined:
+// the solver kernels sit at 255 registers and the register allocation of their CG loop must not see this code.
+__device__ __noinline__ int plan_wait_hand(const int *hand) {
+  int h;
+  const long long t_spin = clock64();
+  while ((h = *(const volatile int *)hand) == 0) {
+    __nanosleep(200);
+    if (clock64() - t_spin > TB_PLAN_SPIN_CYCLES) __trap();   // a launch error instead of a hung device
+  }
+  return h;
+}
 
 
 // The schedule of a planned launch (one thread: C is a few hundred).  est = iteration counts of the context's previous

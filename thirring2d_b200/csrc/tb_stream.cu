@@ -16,6 +16,8 @@
 // (block, chain), and the LAST block of each chain tile (atomic ticket) sums the partials in slot order and
 // evaluates the CG scalar update, so alpha/beta/convergence never leave the device and no FP64 atomics in
 // arbitrary order are used.
+#include <cstdint>
+
 #include "tb_common.cuh"
 
 namespace {
@@ -248,6 +250,204 @@ dslash_axpy_norm_kernel(const double2 *__restrict__ in, const double2 *in_prev, 
   }
   reduce_finalize<FIN_RR, SLAB, TB_RED_RR>(acc, g, s, sl, b, red);
   if (SLAB) slab_signal_done(sl, TB_FLAG_MPDONE, -1, seq);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// TMA-staged variants of the two stencil passes of the fused iteration (single GPU, family A).
+//
+// The register-marching kernels above keep one row of loads in flight per thread (about 40 KB per SM), which is
+// at the edge of what 7 TB/s of HBM needs.  Here the rows of a block travel through a ring of NS shared-memory
+// stages filled by bulk asynchronous copies (cp.async.bulk, completion counted on an mbarrier per stage): NS - 1
+// rows of every resident block are in flight whatever the register budget, and the stencil reads its x-neighbours,
+// its links and the t+1 row from shared memory.  Same block tiling (BC chains x BX sites), same per-chain reduction
+// and last-block scalar update as dslash_kernel / dslash_axpy_norm_kernel; blocks are taller (gp.tt rows).
+//   FUSED = false : out = M in, |out|^2 -> alpha                               (hmc.c:366,368-371)
+//   FUSED = true  : q = M^dagger in on the fly; x += alpha p; r -= alpha q; ||r||^2 -> beta  (hmc.c:367,372-390)
+// A stage holds, for one row of the tile, [site][chain] with one halo site either side where the stencil needs it:
+//   P  (BX + 2) sites of the input field      W0  BX sites      W1  (BX + 1) sites (halo on the left)
+//   FUSED: PV (the CG direction p), X, RR: BX sites each
+constexpr int PIPE_NS_MAX = 4;   // stages per block; 3 when four of them would leave one block per SM
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <bool FUSED>
+struct PipeStage {
+  // offsets in double2 from the start of a stage, for a tile of bc chains x bx sites (bc * bx = 256)
+  __host__ __device__ static constexpr int p(int) { return 0; }
+  __host__ __device__ static int w0(int bc) { return 256 + 2 * bc; }
+  __host__ __device__ static int w1(int bc) { return 512 + 2 * bc; }
+  __host__ __device__ static int pv(int bc) { return 768 + 3 * bc; }
+  __host__ __device__ static int xx(int bc) { return 1024 + 3 * bc; }
+  __host__ __device__ static int rr(int bc) { return 1280 + 3 * bc; }
+  __host__ __device__ static int size(int bc) { return (FUSED ? 1536 : 768) + 3 * bc; }
+  static size_t smem_bytes(int bc, int ns) { return (size_t)ns * size(bc) * sizeof(double2) + ns * sizeof(unsigned long long); }
+};
+
+template <bool FUSED, int PIPE_NS>
+__global__ void __launch_bounds__(TB_MAX_BLOCK)
+dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ W0,
+                   const double2 *__restrict__ W1, const double *__restrict__ mass, const double *__restrict__ emu,
+                   const double *__restrict__ emmu, const double2 *__restrict__ pvec, double2 *__restrict__ x,
+                   double2 *__restrict__ r, const TbGeom g, const TbCgState s, const TbSlab sl) {
+  using St = PipeStage<FUSED>;
+  __shared__ double red[TB_MAX_BLOCK];
+  extern __shared__ __align__(128) unsigned char pipe_smem[];
+  const BlockPos b = block_pos(g);
+  {   // a tile of the staged geometry spans one or more of the chain tiles that tile_active counts in
+    const int c0 = b.ctile * g.bc;
+    int live = 0;
+    for (int q = c0 >> g.ta_shift; q <= (c0 + g.bc - 1) >> g.ta_shift; q++) live += s.tile_active[q];
+    if (live == 0) return;
+  }
+  const int bc = g.bc, bx = g.bx, TT = g.tt, tid = threadIdx.x;
+  const int ssize = St::size(bc);
+  double2 *stage0 = reinterpret_cast<double2 *>(pipe_smem);
+  const uint32_t stage0_addr = smem_u32(stage0);
+  const uint32_t bar0 = stage0_addr + (uint32_t)(PIPE_NS * ssize) * 16u;
+  if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < PIPE_NS; q++) mbar_init(bar0 + 8u * q, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+
+  const int t0 = b.ttile * TT;
+  const int c0 = b.ctile * bc, x0 = b.xtile * bx;
+  const bool contiguous = bc == g.C;   // the tile holds every chain: its sites are one contiguous run of a row
+  const int np = contiguous ? 1 : bx;                              // centre pieces per array and row
+  const uint32_t plen = (uint32_t)(contiguous ? bx * bc : bc) * 16u;   // bytes per centre piece
+  const uint32_t hlen = (uint32_t)bc * 16u;                        // bytes per halo site
+  const size_t pstride = contiguous ? 0 : (size_t)g.C;             // double2 between centre pieces in global memory
+  const int xm = x0 == 0 ? g.nx - 1 : x0 - 1, xp = x0 + bx == g.nx ? 0 : x0 + bx;
+
+  // row i of the block (-1 .. TT: one row of halo either side in t) -> stage (i + 1) % NS; issued by warp 0
+  auto fill = [&](int i) {
+    const int slot = (i + 1) % PIPE_NS;
+    const uint32_t bar = bar0 + 8u * slot;
+    const uint32_t dst0 = stage0_addr + (uint32_t)(slot * ssize) * 16u;
+    int t = t0 + i;
+    t = t < 0 ? t + g.nt : (t >= g.nt ? t - g.nt : t);
+    const size_t row = (size_t)t * g.R + c0;
+    const int lane = tid & 31;
+    const int kind = i < 0 ? 0 : (i >= TT ? 1 : 2);   // 0: P and W0 centres; 1: P centre; 2: everything
+    const int nseg = kind == 0 ? 2 * np : kind == 1 ? np : (FUSED ? 6 * np + 3 : 3 * np + 3);
+    if (lane == 0) {
+      const uint32_t bytes = kind == 0 ? 2 * np * plen : kind == 1 ? np * plen : (FUSED ? 6 : 3) * np * plen + 3 * hlen;
+      mbar_expect_tx(bar, bytes);
+    }
+    __syncwarp();
+    for (int sg = lane; sg < nseg; sg += 32) {
+      // decode: arrays in the order P, W0, W1, PV, X, RR; the centre pieces of an array first, then the halo sites
+      const double2 *src;
+      uint32_t dst, bytes = plen;
+      if (sg < np) { src = in + row + (size_t)x0 * g.C + sg * pstride; dst = (uint32_t)(St::p(bc) + bc) * 16u + sg * plen; }
+      else if (kind == 1) { continue; }
+      else if (sg < 2 * np) { const int k = sg - np; src = W0 + row + (size_t)x0 * g.C + k * pstride; dst = (uint32_t)St::w0(bc) * 16u + k * plen; }
+      else if (kind == 0) { continue; }
+      else if (sg < 3 * np) { const int k = sg - 2 * np; src = W1 + row + (size_t)x0 * g.C + k * pstride; dst = (uint32_t)(St::w1(bc) + bc) * 16u + k * plen; }
+      else if (sg == 3 * np) { src = in + row + (size_t)xm * g.C; dst = (uint32_t)St::p(bc) * 16u; bytes = hlen; }
+      else if (sg == 3 * np + 1) { src = in + row + (size_t)xp * g.C; dst = (uint32_t)(St::p(bc) + (bx + 1) * bc) * 16u; bytes = hlen; }
+      else if (sg == 3 * np + 2) { src = W1 + row + (size_t)xm * g.C; dst = (uint32_t)St::w1(bc) * 16u; bytes = hlen; }
+      else {
+        const int k = sg - (3 * np + 3), a = k / np, kk = k - a * np;
+        const double2 *base = a == 0 ? pvec : (a == 1 ? x : r);
+        src = base + row + (size_t)x0 * g.C + kk * pstride;
+        dst = (uint32_t)(a == 0 ? St::pv(bc) : (a == 1 ? St::xx(bc) : St::rr(bc))) * 16u + kk * plen;
+      }
+      bulk_g2s(dst0 + dst, src, bytes, bar);
+    }
+  };
+  auto stage_of = [&](int i) { return stage0 + ((i + 1) % PIPE_NS) * ssize; };
+  auto wait_row = [&](int i) { mbar_wait(bar0 + 8u * ((i + 1) % PIPE_NS), (uint32_t)(((i + 1) / PIPE_NS) & 1)); };
+
+  if (tid < 32)
+    for (int i = -1; i < PIPE_NS - 1 && i <= TT; i++) fill(i);
+
+  const bool act = s.active[b.c] != 0;
+  const double m = mass[b.c];
+  const double af = FUSED ? emmu[b.c] : emu[b.c];   // factor on the +t hop (M^dagger: e^{-mu})
+  const double ab = FUSED ? emu[b.c] : emmu[b.c];   // factor on the -t hop
+  const double a = FUSED ? s.alpha[b.c] : 0.0;
+  const size_t j = (size_t)b.x * g.C + b.c;
+  double acc = 0.0;
+
+  wait_row(-1);
+  double2 pm = stage_of(-1)[St::p(bc) + bc + tid];
+  double2 w0m = stage_of(-1)[St::w0(bc) + tid];
+  wait_row(0);
+  double2 pc = stage_of(0)[St::p(bc) + bc + tid];
+  __syncthreads();   // stage of row -1 is free
+  if (tid < 32 && PIPE_NS - 1 <= TT) fill(PIPE_NS - 1);
+
+  for (int i = 0; i < TT; i++) {
+    wait_row(i + 1);
+    const double2 *S = stage_of(i);
+    const double2 pp = stage_of(i + 1)[St::p(bc) + bc + tid];
+    const double2 pxm = S[St::p(bc) + tid], pxp = S[St::p(bc) + 2 * bc + tid];
+    const double2 w0c = S[St::w0(bc) + tid];
+    const double2 w1m = S[St::w1(bc) + tid], w1c = S[St::w1(bc) + bc + tid];
+    // hops: +af W0(n) psi(n+t) - ab conj(W0(n-t)) psi(n-t) + W1(n) psi(n+x) - conj(W1(n-x)) psi(n-x)
+    const double fr = w0c.x * af, fi = w0c.y * af;
+    const double br = w0m.x * ab, bi = w0m.y * ab;
+    double hr = fr * pp.x - fi * pp.y;
+    double hi = fr * pp.y + fi * pp.x;
+    hr -= br * pm.x + bi * pm.y;
+    hi -= br * pm.y - bi * pm.x;
+    hr += w1c.x * pxp.x - w1c.y * pxp.y;
+    hi += w1c.x * pxp.y + w1c.y * pxp.x;
+    hr -= w1m.x * pxm.x + w1m.y * pxm.y;
+    hi -= w1m.x * pxm.y - w1m.y * pxm.x;
+    const size_t k = (size_t)(t0 + i) * g.R + j;
+    if (FUSED) {
+      const double qx = m * pc.x - hr, qy = m * pc.y - hi;   // q = M^dagger Mp
+      const double2 pv = S[St::pv(bc) + tid];
+      double2 xv = S[St::xx(bc) + tid], rv = S[St::rr(bc) + tid];
+      xv.x += a * pv.x;
+      xv.y += a * pv.y;
+      rv.x -= a * qx;
+      rv.y -= a * qy;
+      if (act) {
+        x[k] = xv;
+        r[k] = rv;
+        acc += rv.x * rv.x + rv.y * rv.y;
+      }
+    } else {
+      double2 o;
+      o.x = m * pc.x + hr;
+      o.y = m * pc.y + hi;
+      if (act) {
+        out[k] = o;
+        acc += o.x * o.x + o.y * o.y;   // <p, M^dagger M p> = |M p|^2
+      }
+    }
+    pm = pc;
+    pc = pp;
+    w0m = w0c;
+    __syncthreads();   // every thread has read the stage of row i
+    if (tid < 32 && i + PIPE_NS <= TT) fill(i + PIPE_NS);
+  }
+  reduce_finalize<FUSED ? FIN_RR : FIN_PQ, false, FUSED ? TB_RED_RR : TB_RED_PQ>(acc, g, s, sl, b, red);
 }
 
 // p = r + beta p (hmc.c:391-392).  SLAB: p is an exchange vector: wait until the neighbours have finished
@@ -543,6 +743,59 @@ int tb_choose_geom(tb_ctx *ctx) {
   g.tt = tt;
   g.nttiles = (ctx->nt + tt - 1) / tt;
   g.nslots = g.nxtiles * g.nttiles;
+  g.ta_shift = g.bc_shift;
+  // TMA-staged kernels: a tile holds EVERY chain of its sites, so the sites of a tile are one contiguous run of a row
+  // and a row of the tile is one bulk copy per array (4 KB) plus three halo sites.  Measured per CG iteration against
+  // the marching kernels (B200, gpurun_out/probe_pipe_r01n.txt): 2048^2 x 1 chain 189 -> 167 us, 1024^2 x 4 188 -> 171,
+  // 512^2 x 16 191 -> 169; 256^2 x 32 equal; 256^2 x 64 (4 sites per tile: the halo sites are a quarter of the
+  // traffic into shared memory) 191 -> 196; 256^2 x 128 360 -> 389.  Tiles of 32 out of 64 chains (a 512-byte copy per
+  // site) were 1.5x SLOWER: the copy engine of an SM retires a small copy every ~65 cycles.  So: batches of up to 16
+  // chains (tiles at least 16 sites wide), blocks at least 16 rows tall (a ring of stages has a fill latency) with
+  // >= 2.5 blocks per SM; everything else keeps the marching kernels.
+  ctx->gp = g;
+  ctx->pipe_ok = false;
+  const char *et = getenv("TB_PIPE_TEST");   // tests: stage every shape the kernels can handle
+  const int max_chains = et ? 128 : 16, min_rows = et ? 4 : 16;
+  if (ctx->nranks == 1 && ctx->C <= max_chains && (ctx->C & (ctx->C - 1)) == 0 && ctx->nx % (TB_MAX_BLOCK / ctx->C) == 0) {
+    TbGeom &p = ctx->gp;
+    p.bc = ctx->C;
+    p.bx = TB_MAX_BLOCK / ctx->C;
+    p.bc_shift = 0;
+    while ((1 << p.bc_shift) < p.bc) p.bc_shift++;
+    p.nctiles = 1;
+    p.nxtiles = ctx->nx / p.bx;
+    p.Cpad = ctx->C;
+    const long min_blocks = et ? 1 : 370;
+    for (int ttp = 64; ttp >= min_rows; ttp--) {
+      if (ctx->nt % ttp != 0 || (long)p.nxtiles * (ctx->nt / ttp) < min_blocks) continue;
+      if ((size_t)p.nxtiles * (ctx->nt / ttp) * p.Cpad > (size_t)g.nxtiles * ctx->nt * g.Cpad) continue;   // partial sums buffer
+      p.tt = ttp;
+      p.nttiles = ctx->nt / ttp;
+      p.nslots = p.nxtiles * p.nttiles;
+      ctx->pipe_ok = true;
+      break;
+    }
+  }
+  return TB_OK;
+}
+
+static bool use_pipe(const tb_ctx *ctx) {
+  return ctx->pipe_ok && !ctx->msite && ctx->tune_tt == 0 && getenv("TB_NO_PIPE") == nullptr;
+}
+
+template <bool FUSED>
+static int launch_pipe(tb_ctx *ctx, const double2 *in, double2 *out, double2 *x) {
+  const TbGeom &g = ctx->gp;
+  int ns = PIPE_NS_MAX;
+  while (ns > 2 && 2 * (PipeStage<FUSED>::smem_bytes(g.bc, ns) + 4096) > 227 * 1024) ns--;   // two blocks per SM at least
+  if (ns < 3) ns = 3;
+  const size_t smem = PipeStage<FUSED>::smem_bytes(g.bc, ns);
+  auto kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4> : dslash_pipe_kernel<FUSED, 3>;
+  TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid_of(g), TB_MAX_BLOCK, smem, ctx->stream>>>(in, out, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu,
+                                                         ctx->p, x, ctx->r, g, ctx->cg, ctx->slab);
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
   return TB_OK;
 }
 
@@ -712,11 +965,16 @@ static int cg_iteration_fused(tb_ctx *ctx, double2 *x) {
   const dim3 grid = grid_of(g);
   const int block = g.bc * g.bx;
   cudaStream_t st = ctx->stream;
-  DslashArgs k1 = {ctx->p, ctx->p, ctx->p, ctx->Mp, nullptr, false, true, true, 0, -1, 0, -1};
-  TB_CHECK(launch_dslash_t<false>(ctx, k1));
-  TB_DISPATCH_TT(g.tt, (dslash_axpy_norm_kernel<TT, false><<<grid, block, 0, st>>>(ctx->Mp, ctx->Mp, ctx->Mp, ctx->W0,
-      ctx->W0, ctx->W1, ctx->d_mass, ctx->msite, ctx->d_emu, ctx->d_emmu, ctx->p, x, ctx->r, g, ctx->cg, ctx->slab)))
-  ctx->launches++;
+  if (use_pipe(ctx)) {   // rows staged through shared memory by bulk asynchronous copies
+    TB_CHECK(launch_pipe<false>(ctx, ctx->p, ctx->Mp, nullptr));
+    TB_CHECK(launch_pipe<true>(ctx, ctx->Mp, nullptr, x));
+  } else {
+    DslashArgs k1 = {ctx->p, ctx->p, ctx->p, ctx->Mp, nullptr, false, true, true, 0, -1, 0, -1};
+    TB_CHECK(launch_dslash_t<false>(ctx, k1));
+    TB_DISPATCH_TT(g.tt, (dslash_axpy_norm_kernel<TT, false><<<grid, block, 0, st>>>(ctx->Mp, ctx->Mp, ctx->Mp, ctx->W0,
+        ctx->W0, ctx->W1, ctx->d_mass, ctx->msite, ctx->d_emu, ctx->d_emmu, ctx->p, x, ctx->r, g, ctx->cg, ctx->slab)))
+    ctx->launches++;
+  }
   TB_DISPATCH_TT(g.tt, (xpay_kernel<TT, false><<<grid, block, 0, st>>>(ctx->p, ctx->r, g, ctx->cg, ctx->slab)))
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
@@ -795,7 +1053,7 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
 
   int chunk = ctx->tune_chunk > 0 ? ctx->tune_chunk : 16;
   const bool use_graph = getenv("TB_NO_GRAPH") == nullptr;
-  if (use_graph && (ctx->cg_graph == nullptr || ctx->cg_graph_chunk != chunk * 8 + (fused ? 1 : 0))) {
+  if (use_graph && (ctx->cg_graph == nullptr || ctx->cg_graph_chunk != chunk * 8 + (fused ? 1 : 0) + (use_pipe(ctx) ? 2 : 0))) {
     if (ctx->cg_graph) { cudaGraphExecDestroy(ctx->cg_graph); ctx->cg_graph = nullptr; }
     cudaStream_t cap;
     TB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
@@ -816,7 +1074,7 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
     TB_CUDA(cudaGraphInstantiate(&ctx->cg_graph, graph, 0));
     cudaGraphDestroy(graph);
     cudaStreamDestroy(cap);
-    ctx->cg_graph_chunk = chunk * 8 + (fused ? 1 : 0);
+    ctx->cg_graph_chunk = chunk * 8 + (fused ? 1 : 0) + (use_pipe(ctx) ? 2 : 0);
   }
 
   const long max_chunks = ((long)ctx->cg.max_iter + chunk - 1) / chunk + 1;

@@ -23,8 +23,25 @@ echo "== ncu full: cluster kernel (128x128 x 33 chains = one wave of 4-CTA clust
 ncu --set full --clock-control none --import-source on -k regex:cluster_cg -s 1 -c 1 \
     -f -o $OUT/prof_${TAG}_cluster python tools/probe_cluster.py 128,128,33,0.1 > $OUT/ncu_full_cluster_$TAG.log 2>&1
 tail -1 $OUT/ncu_full_cluster_$TAG.log | cut -c1-200
+echo "== ncu full: planned cluster launch (256x256 x 8 chains on 7 co-resident clusters of 16 CTAs)"
+ncu --set full --clock-control none --import-source on -k regex:cluster_cg -s 1 -c 1 \
+    -f -o $OUT/prof_${TAG}_cluster_planned python tools/probe_cluster.py 256,256,8,0.05 > $OUT/ncu_full_cluster_planned_$TAG.log 2>&1
+tail -1 $OUT/ncu_full_cluster_planned_$TAG.log | cut -c1-200
+echo "== ncu full: TMA-staged streaming kernels (2048x2048 single lattice, 1.3 GB working set)"
+ncu --set full --clock-control none --import-source on -k regex:'dslash_pipe|xpay' -s 30 -c 6 \
+    -f -o $OUT/prof_${TAG}_staged python tools/probe.py --one 2048 2048 1 > $OUT/ncu_full_staged_$TAG.log 2>&1
+tail -1 $OUT/ncu_full_staged_$TAG.log | cut -c1-200
 echo "== ncu full: streaming kernels on a working set > L2 (256x256 x 64 chains)"
 ncu --set full --clock-control none --import-source on -k regex:'dslash_kernel|axpy_norm|xpay' -s 40 -c 8 \
     -f -o $OUT/prof_${TAG}_stream python tools/probe.py --one 256 256 64 > $OUT/ncu_full_stream_$TAG.log 2>&1
 tail -1 $OUT/ncu_full_stream_$TAG.log | cut -c1-200
+echo "== summaries of the captures (gpurun brings back at most 64 MiB: only the report of the bench's top kernel travels)"
+for k in resident cluster cluster_planned staged stream; do
+  python tools/ncu_summary.py full $OUT/prof_${TAG}_$k.ncu-rep > $OUT/ncu_full_${TAG}_$k.txt 2>&1
+  [ $k = resident ] || rm -f $OUT/prof_${TAG}_$k.ncu-rep
+done
+python tools/ncu_summary.py launches $OUT/launches_$TAG.csv > $OUT/launches_${TAG}_bench.txt 2>&1
+echo "== planned vs plain launches, staged vs marching kernels"
+python tools/probe_plan.py 2>&1 | tee $OUT/probe_plan_$TAG.txt | cut -c1-250
+python tools/probe_pipe.py 2048,2048,1,0.01 1024,1024,4,0.01 512,512,16,0.01 256,256,64,0.01 2>&1 | tee $OUT/probe_pipe_$TAG.txt | cut -c1-250
 ls -la $OUT | tail -15
