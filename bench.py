@@ -487,6 +487,14 @@ def other_configs(tb, torch, dist, dev, stream, rank, world, cpu=True):
     kind, in_flight = ctx.solver_info()
     ms, info = solve_once(ctx, ctx.vec_doubles, 0)
     ms_stream, _ = solve_once(ctx, ctx.vec_doubles, 1)
+    # trajectories/s of this configuration: update_gauge as coded (10 leapfrog steps, hmc.c:708), device-resident
+    ctx.set_tuning(0, 0, 0)
+    ctx.hmc_trajectory(10, 1.0, seed=310 + rank, traj_index=0)   # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    _, _, traj_its = ctx.hmc_trajectory(10, 1.0, seed=310 + rank, traj_index=1)
+    torch.cuda.synchronize()
+    traj_s = max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3
     ctx.close()
     ms = max_over_ranks(ms)
     applies = total_over_ranks(2 * int(info.iters.astype(np.int64).sum()))
@@ -495,7 +503,9 @@ def other_configs(tb, torch, dist, dev, stream, rank, world, cpu=True):
         "ms_per_batched_solve": ms, "cg_iters_mean": float(info.iters.mean()),
         "converged": bool(np.all(info.status == tb.CG_CONVERGED)),
         "solver": {0: "streaming", 1: "on-chip (CTA per chain)", 2: "on-chip (16-CTA cluster per chain)"}[kind],
-        "chains_in_flight": in_flight, "ms_streaming_solver": max_over_ranks(ms_stream)}
+        "chains_in_flight": in_flight, "ms_streaming_solver": max_over_ranks(ms_stream),
+        "hmc": {"traj_per_sec": world * chains / traj_s, "ms_per_batched_trajectory": 1e3 * traj_s, "nsteps": 10,
+                "cg_iters_per_solve": float(traj_its) / (chains * 11)}}
     if world == 1 and cpu:
         out["256x256_m0.01_g1_8_chains_per_gpu"]["cpu_baseline"] = cpu_port_apply_rate(256, 256, 0.01, 40)
 

@@ -92,3 +92,27 @@ def test_staged_kernels_are_the_default_on_a_large_lattice():
         assert np.all(is_.status == tb.CG_CONVERGED) and np.all(np.abs(is_.iters.astype(int) - im.iters.astype(int)) <= 1)
         for c in (0, 7, 15):
             assert_close(xs[c], xm[c], CG_SOL_TOL, f"chain {c}")
+
+
+@pytest.mark.parametrize("nt,nx,C,mu", [(32, 32, 64, 0.0), (64, 128, 8, 0.1), (128, 256, 1, 0.05), (16, 32, 128, 0.0),
+                                        (24, 64, 4, 0.2)])
+def test_staged_apply_matches_oracle(stage_small_lattices, oracle, nt, nx, C, mu):
+    """T1 for the staged plain apply (CG = false): M and M^dagger against the oracle to 1e-13, every tile shape."""
+    from tests.util import APPLY_TOL
+    rng = np.random.default_rng(nt + 3 * nx + C)
+    A = random_gauge(rng, C, nt, nx)
+    v = random_vector(rng, C, nt, nx)
+    m = rng.uniform(0.05, 1.0, size=C)
+    with tb.Context(nt, nx, C, tb.MODE_ADJOINT, m=m, mu=mu) as ctx:
+        ctx.set_gauge(A)
+        got_m, got_d = ctx.fm_mul(v), ctx.fm_dagger_mul(v)
+        os.environ["TB_NO_PIPE"] = "1"
+        try:
+            ref_m, ref_d = ctx.fm_mul(v), ctx.fm_dagger_mul(v)
+        finally:
+            os.environ.pop("TB_NO_PIPE", None)
+        for c in sorted({0, C // 2, C - 1}):
+            assert_close(got_m[c], oracle.fm_mul(v[c], A[c], float(m[c]), mu), 1e-13, f"staged M, chain {c}")
+            assert_close(got_d[c], oracle.fm_dagger_mul(v[c], A[c], float(m[c]), mu), 1e-13, f"staged M^dagger, chain {c}")
+        assert_close(got_m, ref_m, APPLY_TOL, "staged vs marching M")
+        assert_close(got_d, ref_d, APPLY_TOL, "staged vs marching M^dagger")

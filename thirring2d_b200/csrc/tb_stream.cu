@@ -263,6 +263,7 @@ dslash_axpy_norm_kernel(const double2 *__restrict__ in, const double2 *in_prev, 
 // and last-block scalar update as dslash_kernel / dslash_axpy_norm_kernel; blocks are taller (gp.tt rows).
 //   FUSED = false : out = M in, |out|^2 -> alpha                               (hmc.c:366,368-371)
 //   FUSED = true  : q = M^dagger in on the fly; x += alpha p; r -= alpha q; ||r||^2 -> beta  (hmc.c:367,372-390)
+//   CG = false    : a plain apply, out = M in or M^dagger in (`dagger`), no chain masks, no reduction (hmc.c:132-248)
 // A stage holds, for one row of the tile, [site][chain] with one halo site either side where the stencil needs it:
 //   P  (BX + 2) sites of the input field      W0  BX sites      W1  (BX + 1) sites (halo on the left)
 //   FUSED: PV (the CG direction p), X, RR: BX sites each
@@ -304,17 +305,17 @@ struct PipeStage {
   static size_t smem_bytes(int bc, int ns) { return (size_t)ns * size(bc) * sizeof(double2) + ns * sizeof(unsigned long long); }
 };
 
-template <bool FUSED, int PIPE_NS>
+template <bool FUSED, int PIPE_NS, bool CG>
 __global__ void __launch_bounds__(TB_MAX_BLOCK)
 dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ W0,
                    const double2 *__restrict__ W1, const double *__restrict__ mass, const double *__restrict__ emu,
                    const double *__restrict__ emmu, const double2 *__restrict__ pvec, double2 *__restrict__ x,
-                   double2 *__restrict__ r, const TbGeom g, const TbCgState s, const TbSlab sl) {
+                   double2 *__restrict__ r, const TbGeom g, const TbCgState s, const TbSlab sl, const int dagger) {
   using St = PipeStage<FUSED>;
   __shared__ double red[TB_MAX_BLOCK];
   extern __shared__ __align__(128) unsigned char pipe_smem[];
   const BlockPos b = block_pos(g);
-  {   // a tile of the staged geometry spans one or more of the chain tiles that tile_active counts in
+  if (CG) {   // a tile of the staged geometry spans one or more of the chain tiles that tile_active counts in
     const int c0 = b.ctile * g.bc;
     int live = 0;
     for (int q = c0 >> g.ta_shift; q <= (c0 + g.bc - 1) >> g.ta_shift; q++) live += s.tile_active[q];
@@ -384,10 +385,11 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
   if (tid < 32)
     for (int i = -1; i < PIPE_NS - 1 && i <= TT; i++) fill(i);
 
-  const bool act = s.active[b.c] != 0;
+  const bool act = CG ? s.active[b.c] != 0 : true;
+  const bool dag = FUSED || (!CG && dagger);
   const double m = mass[b.c];
-  const double af = FUSED ? emmu[b.c] : emu[b.c];   // factor on the +t hop (M^dagger: e^{-mu})
-  const double ab = FUSED ? emu[b.c] : emmu[b.c];   // factor on the -t hop
+  const double af = dag ? emmu[b.c] : emu[b.c];   // factor on the +t hop (M^dagger: e^{-mu})
+  const double ab = dag ? emu[b.c] : emmu[b.c];   // factor on the -t hop
   const double a = FUSED ? s.alpha[b.c] : 0.0;
   const size_t j = (size_t)b.x * g.C + b.c;
   double acc = 0.0;
@@ -434,8 +436,13 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
       }
     } else {
       double2 o;
-      o.x = m * pc.x + hr;
-      o.y = m * pc.y + hi;
+      if (!CG && dag) {
+        o.x = m * pc.x - hr;
+        o.y = m * pc.y - hi;
+      } else {
+        o.x = m * pc.x + hr;
+        o.y = m * pc.y + hi;
+      }
       if (act) {
         out[k] = o;
         acc += o.x * o.x + o.y * o.y;   // <p, M^dagger M p> = |M p|^2
@@ -447,7 +454,7 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
     __syncthreads();   // every thread has read the stage of row i
     if (tid < 32 && i + PIPE_NS <= TT) fill(i + PIPE_NS);
   }
-  reduce_finalize<FUSED ? FIN_RR : FIN_PQ, false, FUSED ? TB_RED_RR : TB_RED_PQ>(acc, g, s, sl, b, red);
+  if (CG) reduce_finalize<FUSED ? FIN_RR : FIN_PQ, false, FUSED ? TB_RED_RR : TB_RED_PQ>(acc, g, s, sl, b, red);
 }
 
 // p = r + beta p (hmc.c:391-392).  SLAB: p is an exchange vector: wait until the neighbours have finished
@@ -783,17 +790,17 @@ static bool use_pipe(const tb_ctx *ctx) {
   return ctx->pipe_ok && !ctx->msite && ctx->tune_tt == 0 && getenv("TB_NO_PIPE") == nullptr;
 }
 
-template <bool FUSED>
-static int launch_pipe(tb_ctx *ctx, const double2 *in, double2 *out, double2 *x) {
+template <bool FUSED, bool CG = true>
+static int launch_pipe(tb_ctx *ctx, const double2 *in, double2 *out, double2 *x, bool dagger = false) {
   const TbGeom &g = ctx->gp;
   int ns = PIPE_NS_MAX;
   while (ns > 2 && 2 * (PipeStage<FUSED>::smem_bytes(g.bc, ns) + 4096) > 227 * 1024) ns--;   // two blocks per SM at least
   if (ns < 3) ns = 3;
   const size_t smem = PipeStage<FUSED>::smem_bytes(g.bc, ns);
-  auto kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4> : dslash_pipe_kernel<FUSED, 3>;
+  auto kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4, CG> : dslash_pipe_kernel<FUSED, 3, CG>;
   TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid_of(g), TB_MAX_BLOCK, smem, ctx->stream>>>(in, out, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu,
-                                                         ctx->p, x, ctx->r, g, ctx->cg, ctx->slab);
+                                                         ctx->p, x, ctx->r, g, ctx->cg, ctx->slab, dagger ? 1 : 0);
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
   return TB_OK;
@@ -910,6 +917,7 @@ static int launch_dslash_t(tb_ctx *ctx, const DslashArgs &a) {
 }
 
 int tb_launch_dslash(tb_ctx *ctx, bool dagger, const double2 *in, double2 *out, bool masked) {
+  if (!masked && use_pipe(ctx)) return launch_pipe<false, false>(ctx, in, out, nullptr, dagger);
   DslashArgs a = {in, in, in, out, nullptr, dagger, false, masked, 0, -1, 0, -1};
   return launch_dslash_t<false>(ctx, a);
 }
