@@ -423,6 +423,15 @@ int tb_run_cg_any(tb_ctx *ctx, const double2 *b, double2 *x) {
   return TB_OK;
 }
 
+// The same solve without the event pair and the host synchronisation when an on-chip solver serves the context (one
+// or two launches, nothing for the host to poll): callers that queue more work behind the solve (the device-resident
+// trajectory) keep the GPU busy.  The streaming solver needs its host loop and stays synchronous.
+int tb_run_cg_async(tb_ctx *ctx, const double2 *b, double2 *x) {
+  const int onchip = onchip_solver(ctx);
+  if (!onchip || ctx->tune_solver == 2) return tb_run_cg_any(ctx, b, x);
+  return run_onchip_slice(ctx, onchip, b, x, 0, ctx->C, ctx->stream);
+}
+
 extern "C" int tb_solver_info(tb_ctx *ctx, int *kind, int *chains_in_flight) {
   if (!ctx) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));

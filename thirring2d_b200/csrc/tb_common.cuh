@@ -92,6 +92,7 @@ struct TbHmc {
   double2 *mom, *newA, *psi, *st, *chi, *phi, *gauss;
   double *sums, *obs, *u, *nf_over_g;
   int *accept, *failed;
+  unsigned long long *iter_sum;   // CG iterations of the trajectory, summed over chains and solves on the device
 };
 
 struct tb_ctx {

@@ -201,9 +201,16 @@ __global__ void commit_kernel(double2 *__restrict__ A, const double2 *__restrict
     if (accept[k % C]) A[k] = newA[k];
 }
 
-__global__ void or_failed_kernel(int *__restrict__ failed, const int *__restrict__ status, int C) {
+// after every solve of a trajectory: remember chains whose solve failed, add the iteration counts to the device-side
+// total (the host reads both once, at the end of the trajectory)
+__global__ void or_failed_kernel(int *__restrict__ failed, const int *__restrict__ status, const int *__restrict__ iters,
+                                 unsigned long long *__restrict__ iter_sum, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C && status[c] != TB_CG_CONVERGED && status[c] != TB_CG_ZERO_SOURCE) failed[c] |= 1 << status[c];
+  unsigned int n = c < C ? (unsigned int)iters[c] : 0u;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+  if ((threadIdx.x & 31) == 0 && n) atomicAdd(iter_sum, (unsigned long long)n);
 }
 
 // update_puregauge_hb (hmc.c:82-93): links decouple in the quenched action, so every link runs its own
@@ -282,6 +289,7 @@ int ew_blocks(size_t n) {
 
 // ---------------------------------------------------------------------------------------------------------
 int tb_run_cg_any(tb_ctx *ctx, const double2 *b, double2 *x);  // tb_api.cu: solver dispatch + timing
+int tb_run_cg_async(tb_ctx *ctx, const double2 *b, double2 *x);  // the same, no host synchronisation (on-chip solvers)
 
 static int hmc_alloc(tb_ctx *ctx) {
   if (ctx->hmc.mom) return TB_OK;
@@ -304,6 +312,7 @@ static int hmc_alloc(tb_ctx *ctx) {
   TB_CUDA(cudaMalloc((void **)&ctx->hmc.u, cp * sizeof(double)));
   TB_CUDA(cudaMalloc((void **)&ctx->hmc.accept, 2 * cp * sizeof(int)));
   ctx->hmc.failed = ctx->hmc.accept + cp;
+  TB_CUDA(cudaMalloc((void **)&ctx->hmc.iter_sum, sizeof(unsigned long long)));
   if (!ctx->hmc.nf_over_g) {
     TB_CUDA(cudaMalloc((void **)&ctx->hmc.nf_over_g, cp * sizeof(double)));
     double *h = (double *)malloc(cp * sizeof(double));
@@ -316,7 +325,7 @@ static int hmc_alloc(tb_ctx *ctx) {
 
 void tb_hmc_release(tb_ctx *ctx) {
   void *p[] = {ctx->hmc.mom, ctx->hmc.newA, ctx->hmc.psi, ctx->hmc.st, ctx->hmc.chi, ctx->hmc.phi, ctx->hmc.gauss,
-               ctx->hmc.sums, ctx->hmc.obs, ctx->hmc.u, ctx->hmc.accept, ctx->hmc.nf_over_g};
+               ctx->hmc.sums, ctx->hmc.obs, ctx->hmc.u, ctx->hmc.accept, ctx->hmc.nf_over_g, ctx->hmc.iter_sum};
   for (void *q : p)
     if (q) cudaFree(q);
 }
@@ -405,13 +414,15 @@ extern "C" int tb_hmc_trajectory(tb_ctx *ctx, int nsteps, double traj_length, un
     TB_CUDA(cudaMemcpyAsync(ctx->stage, host, n * sizeof(double2), cudaMemcpyHostToDevice, st));
     return tb_launch_pack(ctx, ctx->stage, dst);
   };
-  auto count_iters = [&]() -> int {
-    TB_CUDA(cudaMemcpyAsync(ctx->h_iters, ctx->cg.iters, C * sizeof(int), cudaMemcpyDeviceToHost, st));
-    TB_CUDA(cudaStreamSynchronize(st));
-    for (int c = 0; c < C; c++) cg_iters += ctx->h_iters[c];
+  // nothing in the trajectory waits for the host: failures and iteration counts are collected on the device
+  auto after_solve = [&]() -> int {
+    or_failed_kernel<<<(C + 255) / 256, 256, 0, st>>>(H.failed, ctx->cg.status, ctx->cg.iters, H.iter_sum, C);
+    ctx->launches++;
+    TB_CUDA(cudaGetLastError());
     return TB_OK;
   };
   TB_CUDA(cudaMemsetAsync(H.failed, 0, cp * sizeof(int), st));
+  TB_CUDA(cudaMemsetAsync(H.iter_sum, 0, sizeof(unsigned long long), st));
 
   // links of the current configuration (a previous rejected trajectory leaves them consistent, but be safe)
   TB_CHECK(links_from(ctx, ctx->Adev));
@@ -443,22 +454,19 @@ extern "C" int tb_hmc_trajectory(tb_ctx *ctx, int nsteps, double traj_length, un
                                                 ctx->t_off, ctx->nt_global);
     ctx->launches++;
     // momentum_step, hmc.c:504: chi = (M~M)^-1 psi, phi = M chi, forces
-    TB_CHECK(tb_run_cg_any(ctx, H.psi, H.chi));
-    or_failed_kernel<<<(C + 255) / 256, 256, 0, st>>>(H.failed, ctx->cg.status, C);
-    TB_CHECK(count_iters());
+    TB_CHECK(tb_run_cg_async(ctx, H.psi, H.chi));
+    TB_CHECK(after_solve());
     TB_CHECK(tb_launch_dslash(ctx, false, H.chi, H.phi, false));
     force_kernel<<<eb, 256, 0, st>>>(H.mom, H.newA, H.chi, H.phi, H.st, H.nf_over_g, ctx->d_emu, ctx->d_emmu, eps_p,
                                      ctx->nt, ctx->nx, C);
     gauge_step_links_kernel<<<eb, 256, 0, st>>>(H.newA, H.mom, ctx->W0, ctx->W1, 2.0 * eps_q, ctx->nt, ctx->nx, C,
                                                 ctx->t_off, ctx->nt_global);
-    ctx->launches += 3;
+    ctx->launches += 2;
     TB_CUDA(cudaGetLastError());
   }
   // pseudofermion_action on the proposed field, hmc.c:719
-  TB_CHECK(tb_run_cg_any(ctx, H.psi, H.chi));
-  or_failed_kernel<<<(C + 255) / 256, 256, 0, st>>>(H.failed, ctx->cg.status, C);
-  ctx->launches++;
-  TB_CHECK(count_iters());
+  TB_CHECK(tb_run_cg_async(ctx, H.psi, H.chi));
+  TB_CHECK(after_solve());
   TB_CHECK(dot_to(ctx, H.psi, H.chi, 5));
   TB_CHECK(dot_to(ctx, H.mom, H.mom, 7));               // hmc.c:721-724
   TB_CHECK(gauge_action_to(ctx, H.newA, 4));            // hmc.c:725
@@ -480,7 +488,11 @@ extern "C" int tb_hmc_trajectory(tb_ctx *ctx, int nsteps, double traj_length, un
   } else {
     TB_CUDA(cudaStreamSynchronize(st));
   }
-  if (cg_iters_host) *cg_iters_host = cg_iters;
+  if (cg_iters_host) {
+    unsigned long long total = 0;
+    TB_CUDA(cudaMemcpy(&total, H.iter_sum, sizeof(total), cudaMemcpyDeviceToHost));
+    *cg_iters_host = cg_iters + (long long)total;
+  }
   return TB_OK;
 }
 
