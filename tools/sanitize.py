@@ -10,6 +10,24 @@ CASES = [(16, 16, 3, tb.MODE_ADJOINT, 0.5, 0.1), (32, 32, 2, tb.MODE_ADJOINT, 0.
                                  (64, 64, 2, tb.MODE_ADJOINT, 0.5, 0.1), (64, 64, 1, tb.MODE_REF_COMPAT, 50.0, 0.1),
                                  (128, 128, 1, tb.MODE_ADJOINT, 0.6, 0.1), (128, 64, 1, tb.MODE_REF_COMPAT, 50.0, 0.0),
                                  (256, 256, 1, tb.MODE_ADJOINT, 1.0, 0.0), (48, 40, 2, tb.MODE_ADJOINT, 0.7, 0.1)]
+if only in ("new", "pipe"):
+    # planned launches (a second solve: the first one provides the iteration estimates) and the TMA-staged kernels
+    for (nt, nx, n, solver) in [(64, 64, 160, 0), (128, 128, 40, 0), (256, 256, 8, 0), (64, 128, 8, 1), (32, 32, 64, 1)]:
+        if only == "pipe" and solver != 1:
+            continue
+        A = rng.uniform(-np.pi, np.pi, size=(n, nt, nx, 2))
+        xi = rng.normal(size=(n, nt, nx)) + 1j * rng.normal(size=(n, nt, nx))
+        os.environ["TB_SUBBATCHES"] = "1"
+        os.environ["TB_PIPE_TEST"] = "1"
+        with tb.Context(nt, nx, n, tb.MODE_ADJOINT, m=np.linspace(1.5, 3.0, n), mu=0.1) as ctx:
+            ctx.set_tuning(solver=solver)
+            ctx.set_gauge(A)
+            b = ctx.fm_conjugate_mul(xi)
+            for rep in range(2):
+                x, info = ctx.fmdm_invert_cg(b)
+            print(nt, nx, n, ctx.solver_info(), int(info.iters.min()), int(info.iters.max()),
+                  np.bincount(info.status, minlength=4).tolist(), flush=True)
+    sys.exit(0)
 for (nt, nx, n, mode, m, mu) in CASES:
     if (only == "small" and nt * nx > 4096) or (only == "cluster" and nt * nx <= 4096):
         continue
