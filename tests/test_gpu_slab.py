@@ -50,15 +50,22 @@ def _worker(rank, world, port, nt, nx, nchains, m, mu, q):
     xi, infoi = ctx.fm_invert_cg(v[:, sl])
     ctx.set_tuning(solver=3)   # the 4-kernel iteration with separate scalar kernels (the form REF_COMPAT uses)
     x4, info4 = ctx.fmdm_invert_cg(b)
+    # the fused iteration as separate kernels (TB_NO_PERSIST), then the one-launch solve again: both protocols share
+    # the epoch counter and the neighbour flags
+    ctx.set_tuning(solver=0)
+    os.environ["TB_NO_PERSIST"] = "1"
+    xm, infom = ctx.fmdm_invert_cg(b)
+    del os.environ["TB_NO_PERSIST"]
+    x5, info5 = ctx.fmdm_invert_cg(b)
     out.update(b=b, x=x, x2=x2, xi=xi, x4=x4, iters=info.iters, status=info.status, iters2=info2.iters,
-               iters4=info4.iters)
+               iters4=info4.iters, xm=xm, itersm=infom.iters, x5=x5, iters5=info5.iters)
     q.put((rank, out))
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("nt,nx,nchains,m,mu", [(32, 32, 1, 0.2, 0.1), (64, 48, 3, 0.1, 0.0), (16, 16, 40, 0.5, 0.2)])
+@pytest.mark.parametrize("nt,nx,nchains,m,mu", [(32, 32, 1, 0.2, 0.1), (64, 48, 3, 0.1, 0.0), (16, 16, 40, 0.5, 0.2), (256, 512, 1, 0.1, 0.0)])
 def test_T7_slab_matches_single_gpu(nt, nx, nchains, m, mu):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -99,3 +106,6 @@ def test_T7_slab_matches_single_gpu(nt, nx, nchains, m, mu):
     assert np.all(np.abs(res[0]["iters4"].astype(int) - info.iters.astype(int)) <= 1)
     assert np.linalg.norm(xs - x) <= 1e-12 * np.linalg.norm(x)
     assert np.linalg.norm(cat("xi") - xi) <= 1e-12 * np.linalg.norm(xi)
+    assert np.linalg.norm(cat("xm") - x) <= 1e-12 * np.linalg.norm(x)
+    assert np.all(np.abs(res[0]["itersm"].astype(int) - info.iters.astype(int)) <= 1)
+    assert np.array_equal(cat("x5"), xs) and np.array_equal(res[0]["iters5"], res[0]["iters"])

@@ -85,6 +85,9 @@ struct TbSlab {
   int *seq;                    // device epoch counter = generation of the exchange vector p
   unsigned int *done_ticket;   // [TB_NFLAGS] completion counters of the signalling kernels
   int *err;                    // set when a flag wait timed out
+  // persistent solve (tb_stream.cu: slab_cg_persistent_kernel): grid barrier counter and block 0's broadcast flag
+  unsigned long long *gbar;
+  int *go;
 };
 
 // buffers of the device-resident HMC trajectory (tb_hmc.cu), allocated at first use

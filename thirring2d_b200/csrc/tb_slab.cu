@@ -36,15 +36,17 @@ int tb_slab_layout(tb_ctx *ctx) {
   ctx->Mp = (double2 *)(base + o.mp);
   ctx->W0 = (double2 *)(base + o.w0);
   int *local = nullptr;
-  e = cudaMalloc((void **)&local, (2 + TB_NFLAGS) * sizeof(int));
+  e = cudaMalloc((void **)&local, (2 + TB_NFLAGS + 6) * sizeof(int));
   if (e != cudaSuccess) {
     tb_set_error("cudaMalloc failed: %s", cudaGetErrorString(e));
     return TB_ENOMEM;
   }
-  TB_CUDA(cudaMemset(local, 0, (2 + TB_NFLAGS) * sizeof(int)));
+  TB_CUDA(cudaMemset(local, 0, (2 + TB_NFLAGS + 6) * sizeof(int)));
   ctx->slab.seq = local;
   ctx->slab.done_ticket = (unsigned int *)(local + 1);
   ctx->slab.err = local + 1 + TB_NFLAGS;
+  ctx->slab.gbar = (unsigned long long *)(local + 8);   // 8-byte aligned: ints 8, 9
+  ctx->slab.go = local + 10;
   ctx->slab.P = ctx->nranks;
   ctx->slab.rank = ctx->rank;
   return TB_OK;

@@ -592,6 +592,378 @@ slab_scalars_kernel(const TbGeom g, const TbCgState s, const TbSlab sl) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Slab mode, whole solve in ONE launch per GPU (fused ADJOINT iteration, up to 32 chains).
+//
+// The multi-kernel slab iteration spends most of its time between kernels: five launches and four cross-GPU
+// hand-shakes per iteration (2048^2 on 8 GPUs: 25 us of kernels in an 82 us iteration).  Here every GPU runs one
+// persistent cooperative kernel; a block owns a fixed set of tiles for the whole solve and the phases of an iteration
+// are separated by grid barriers (an atomic counter in L2) instead of kernel boundaries:
+//   A  Mp = M p, |Mp|^2        barrier   block 0: all-reduce over the GPUs -> alpha     (hmc.c:366,368-371)
+//   B  q = M^dagger Mp on the fly, x += alpha p, r -= alpha q, ||r||^2
+//                               barrier   block 0: all-reduce -> beta, convergence        (hmc.c:367,372-390)
+//   C  p = r + beta p           barrier   block 0: "generation k+1 of p is complete" to both neighbours (hmc.c:391-392)
+// The all-reduce is the one-shot peer-store exchange of the multi-kernel path (every rank stores its partial into
+// every rank's slot table, sums in rank order => bitwise identical scalars and decisions on all ranks).  It doubles
+// as the cross-GPU fence for the halo rows: a rank contributes to the |Mp|^2 sum only after its phase A, so whoever
+// holds the sum knows that (i) the neighbours' Mp rows are complete and (ii) nobody reads generation k of p any
+// more; likewise ||r||^2 for the Mp rows.  Only "p is complete" needs a flag of its own, and only tiles in the first
+// and last rows of the slab wait for it (they are scheduled last).  Fields that are rewritten during the launch are
+// loaded with ld.global.cg: L1 is not coherent across the phases of one kernel.
+// ranks enter the launch seconds apart when one of them is still busy on the host: ~20 s before a wait gives up
+#define TB_PERSIST_SPIN_CYCLES 40000000000LL
+struct SlabCgArgs {
+  const double2 *b;
+  double2 *x, *r, *p, *Mp;
+  const double2 *p_prev, *p_next, *mp_prev, *mp_next;
+  const double2 *W0, *W0_prev, *W1;
+  const double *mass, *emu, *emmu;
+};
+
+__device__ __forceinline__ void spin_until(volatile int *f, int need) {
+  const long long t0 = clock64();
+  while (*f < need) {
+    __nanosleep(64);
+    if (clock64() - t0 > TB_PERSIST_SPIN_CYCLES) __trap();   // a launch error on this rank instead of a hung box
+  }
+}
+
+__device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned long long &target) {
+  // device scope is enough for the halo rows too: a peer reads them out of THIS GPU's L2, after a flag that block 0
+  // stores behind a system-scope fence (a system-scope fence in every thread cost ~5 us per barrier)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    atomicAdd(bar, 1ULL);
+    const long long t0 = clock64();
+    while (*(volatile unsigned long long *)bar < target)
+      if (clock64() - t0 > TB_PERSIST_SPIN_CYCLES) __trap();
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// The barrier in front of a reduction: every block arrives; block 0 alone waits for the arrivals (it then runs the
+// all-reduce and releases the others through *sl.go, see block0_scalars / wait_go), so the other blocks poll one
+// flag instead of the counter and then the flag.
+__device__ __forceinline__ void grid_arrive(unsigned long long *bar, unsigned long long &target) {
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    atomicAdd(bar, 1ULL);
+    if (blockIdx.x == 0) {
+      const long long t0 = clock64();
+      while (*(volatile unsigned long long *)bar < target)
+        if (clock64() - t0 > TB_PERSIST_SPIN_CYCLES) __trap();
+      __threadfence();
+    }
+  }
+  if (blockIdx.x == 0) __syncthreads();
+}
+
+// tile `tile` of this rank's slab (one chain tile); rows at the two ends of the slab come last
+__device__ __forceinline__ BlockPos tile_pos(const TbGeom &g, int tile) {
+  BlockPos b;
+  b.ctile = 0;
+  b.xtile = tile % g.nxtiles;
+  b.ttile = (tile / g.nxtiles + 1) % g.nttiles;
+  b.c_local = threadIdx.x & (g.bc - 1);
+  b.x_local = threadIdx.x >> g.bc_shift;
+  b.c = b.c_local;
+  b.x = b.xtile * g.bx + b.x_local;
+  b.valid = (b.c < g.C) && (b.x < g.nx);
+  return b;
+}
+
+// per-chain sum of `acc` over the block -> partial[blockIdx.x][chain]
+__device__ __forceinline__ void block_partial(double acc, const TbGeom &g, const TbCgState &s, double *red) {
+  const int c_local = threadIdx.x & (g.bc - 1), x_local = threadIdx.x >> g.bc_shift;
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int st = g.bx >> 1; st > 0; st >>= 1) {
+    if (x_local < st) red[threadIdx.x] += red[threadIdx.x + st * g.bc];
+    __syncthreads();
+  }
+  if (x_local == 0) s.partial[(size_t)blockIdx.x * g.Cpad + c_local] = red[c_local];
+  __syncthreads();
+}
+
+// block 0, after the grid barrier: sum the block partials in block order, all-reduce over the ranks, evaluate the CG
+// scalars (finalize_scalar), then release the other blocks of this GPU through *sl.go = go_value
+template <int FIN, int RED>
+__device__ __forceinline__ void block0_scalars(const TbGeom &g, const TbCgState &s, const TbSlab &sl, double *red,
+                                               int seqv, int go_value) {
+  const int c_local = threadIdx.x & (g.bc - 1), x_local = threadIdx.x >> g.bc_shift;
+  double sum = 0.0;
+  for (int blk = x_local; blk < (int)gridDim.x; blk += g.bx) sum += __ldcg(&s.partial[(size_t)blk * g.Cpad + c_local]);
+  red[threadIdx.x] = sum;
+  __syncthreads();
+  for (int st = g.bx >> 1; st > 0; st >>= 1) {
+    if (x_local < st) red[threadIdx.x] += red[threadIdx.x + st * g.bc];
+    __syncthreads();
+  }
+  if (x_local == 0) {
+    const double total = red[c_local];
+    for (int q = 0; q < sl.P; q++) sl.peer_red[q][(size_t)(RED * sl.P + sl.rank) * g.Cpad + c_local] = total;
+    __threadfence_system();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int q = 0; q < sl.P; q++) *(volatile int *)(sl.peer_red_flag[q] + (RED * sl.P + sl.rank) * g.nctiles) = seqv;
+  }
+  if ((int)threadIdx.x < sl.P) spin_until(sl.red_flag + (RED * sl.P + threadIdx.x) * g.nctiles, seqv);
+  __syncthreads();
+  if (x_local == 0 && c_local < g.C) {
+    double total = 0.0;
+    for (int q = 0; q < sl.P; q++) total += __ldcv(&sl.red[(size_t)(RED * sl.P + q) * g.Cpad + c_local]);
+    finalize_scalar<FIN>(total, c_local, 0, s);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    *(volatile int *)sl.go = go_value;
+  }
+}
+
+__device__ __forceinline__ void wait_go(const TbSlab &sl, int go_value) {
+  if (threadIdx.x == 0) {
+    spin_until((volatile int *)sl.go, go_value);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+template <int TT>
+__global__ void __launch_bounds__(TB_MAX_BLOCK)
+slab_cg_persistent_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, const TbSlab sl) {
+  __shared__ double red[TB_MAX_BLOCK];
+  const int ntiles = g.nxtiles * g.nttiles;
+  const size_t R = (size_t)g.R;
+  unsigned long long bar_target = 0;
+  const int E0 = *(volatile int *)sl.seq;   // block 0 rewrites it only after the last grid barrier
+  const int c = threadIdx.x & (g.bc - 1);
+  const bool chain = c < g.C;
+  const double m = chain ? a.mass[c] : 0.0;
+  const double e_p = chain ? a.emu[c] : 1.0, e_m = chain ? a.emmu[c] : 1.0;
+
+  // the neighbours may still read the previous generation of p (an apply queued before this solve)
+  auto wait_ends = [&](const BlockPos &b, int kind, int need) {
+    if (b.ttile == 0 || b.ttile == g.nttiles - 1) {
+      if (threadIdx.x == 0) {
+        if (b.ttile == 0) spin_until(sl.flags + kind * 2 + 0, need);
+        if (b.ttile == g.nttiles - 1) spin_until(sl.flags + kind * 2 + 1, need);
+        __threadfence_system();
+      }
+      __syncthreads();
+    }
+  };
+
+  // ---- x = 0, r = p = b, ||b||^2 (hmc.c:349-361): generation E0 + 1 of p
+  double acc = 0.0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const BlockPos b = tile_pos(g, tile);
+    wait_ends(b, TB_FLAG_PDONE, E0);
+    if (b.valid) {
+      const size_t j = (size_t)b.x * g.C + b.c;
+      const int t0 = b.ttile * TT;
+#pragma unroll
+      for (int i = 0; i < TT; i++) {
+        const int t = t0 + i;
+        if (t < g.nt) {
+          const size_t k = t * R + j;
+          const double2 v = a.b[k];
+          a.x[k] = make_double2(0.0, 0.0);
+          a.r[k] = v;
+          a.p[k] = v;
+          acc += v.x * v.x + v.y * v.y;
+        }
+      }
+    }
+  }
+  block_partial(acc, g, s, red);
+  grid_arrive(sl.gbar, bar_target);
+  int gen = E0 + 1;   // generation of p
+  if (blockIdx.x == 0) {
+    block0_scalars<FIN_INIT, TB_RED_INIT>(g, s, sl, red, gen, 3 * gen);
+    if (threadIdx.x == 0) {
+      __threadfence_system();
+      *(volatile int *)(sl.sig_prev + TB_FLAG_PREADY * 2) = gen;
+      *(volatile int *)(sl.sig_next + TB_FLAG_PREADY * 2) = gen;
+    }
+  }
+  wait_go(sl, 3 * gen);
+
+  while (*(volatile int *)s.n_active > 0) {
+    const bool act = chain && __ldcg(&s.active[c]) != 0;
+    // ---- A: Mp = M p, |Mp|^2
+    acc = 0.0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const BlockPos b = tile_pos(g, tile);
+      wait_ends(b, TB_FLAG_PREADY, gen);
+      if (b.valid && act) {
+        const size_t j = (size_t)b.x * g.C + b.c;
+        const size_t jp = (size_t)((b.x + 1 == g.nx) ? 0 : b.x + 1) * g.C + b.c;
+        const size_t jm = (size_t)((b.x == 0) ? g.nx - 1 : b.x - 1) * g.C + b.c;
+        const int t0 = b.ttile * TT;
+        double2 pm, w0m;
+        if (t0 == 0) {
+          pm = __ldcv(&a.p_prev[(size_t)(g.nt - 1) * R + j]);
+          w0m = __ldcv(&a.W0_prev[(size_t)(g.nt - 1) * R + j]);
+        } else {
+          pm = __ldcg(&a.p[(size_t)(t0 - 1) * R + j]);
+          w0m = a.W0[(size_t)(t0 - 1) * R + j];
+        }
+        double2 pc = __ldcg(&a.p[t0 * R + j]);
+#pragma unroll
+        for (int i = 0; i < TT; i++) {
+          const int t = t0 + i;
+          if (t < g.nt) {
+            const size_t row = t * R;
+            const double2 pp = (t + 1 == g.nt) ? __ldcv(&a.p_next[j]) : __ldcg(&a.p[row + R + j]);
+            const double2 pxp = __ldcg(&a.p[row + jp]);
+            const double2 pxm = __ldcg(&a.p[row + jm]);
+            const double2 w0c = a.W0[row + j];
+            const double2 w1c = a.W1[row + j];
+            const double2 w1m = a.W1[row + jm];
+            const double fr = w0c.x * e_p, fi = w0c.y * e_p;
+            const double br = w0m.x * e_m, bi = w0m.y * e_m;
+            double hr = fr * pp.x - fi * pp.y;
+            double hi = fr * pp.y + fi * pp.x;
+            hr -= br * pm.x + bi * pm.y;
+            hi -= br * pm.y - bi * pm.x;
+            hr += w1c.x * pxp.x - w1c.y * pxp.y;
+            hi += w1c.x * pxp.y + w1c.y * pxp.x;
+            hr -= w1m.x * pxm.x + w1m.y * pxm.y;
+            hi -= w1m.x * pxm.y - w1m.y * pxm.x;
+            double2 o;
+            o.x = m * pc.x + hr;
+            o.y = m * pc.y + hi;
+            a.Mp[row + j] = o;
+            acc += o.x * o.x + o.y * o.y;   // <p, M^dagger M p> = |M p|^2
+            pm = pc;
+            pc = pp;
+            w0m = w0c;
+          }
+        }
+      }
+    }
+    block_partial(acc, g, s, red);
+    grid_arrive(sl.gbar, bar_target);
+    if (blockIdx.x == 0) block0_scalars<FIN_PQ, TB_RED_PQ>(g, s, sl, red, gen, 3 * gen + 1);
+    wait_go(sl, 3 * gen + 1);
+
+    // ---- B: q = M^dagger Mp on the fly, x += alpha p, r -= alpha q, ||r||^2
+    acc = 0.0;
+    const double al = chain ? __ldcg(&s.alpha[c]) : 0.0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const BlockPos b = tile_pos(g, tile);
+      if (b.valid && act) {
+        const size_t j = (size_t)b.x * g.C + b.c;
+        const size_t jp = (size_t)((b.x + 1 == g.nx) ? 0 : b.x + 1) * g.C + b.c;
+        const size_t jm = (size_t)((b.x == 0) ? g.nx - 1 : b.x - 1) * g.C + b.c;
+        const int t0 = b.ttile * TT;
+        double2 pm, w0m;
+        if (t0 == 0) {
+          pm = __ldcv(&a.mp_prev[(size_t)(g.nt - 1) * R + j]);
+          w0m = __ldcv(&a.W0_prev[(size_t)(g.nt - 1) * R + j]);
+        } else {
+          pm = __ldcg(&a.Mp[(size_t)(t0 - 1) * R + j]);
+          w0m = a.W0[(size_t)(t0 - 1) * R + j];
+        }
+        double2 pc = __ldcg(&a.Mp[t0 * R + j]);
+#pragma unroll
+        for (int i = 0; i < TT; i++) {
+          const int t = t0 + i;
+          if (t < g.nt) {
+            const size_t row = t * R;
+            const double2 pp = (t + 1 == g.nt) ? __ldcv(&a.mp_next[j]) : __ldcg(&a.Mp[row + R + j]);
+            const double2 pxp = __ldcg(&a.Mp[row + jp]);
+            const double2 pxm = __ldcg(&a.Mp[row + jm]);
+            const double2 w0c = a.W0[row + j];
+            const double2 w1c = a.W1[row + j];
+            const double2 w1m = a.W1[row + jm];
+            const double2 pv = __ldcg(&a.p[row + j]);
+            double2 xv = __ldcg(&a.x[row + j]), rv = __ldcg(&a.r[row + j]);
+            const double fr = w0c.x * e_m, fi = w0c.y * e_m;   // M^dagger: e^{-mu} on the +t hop
+            const double br = w0m.x * e_p, bi = w0m.y * e_p;
+            double hr = fr * pp.x - fi * pp.y;
+            double hi = fr * pp.y + fi * pp.x;
+            hr -= br * pm.x + bi * pm.y;
+            hi -= br * pm.y - bi * pm.x;
+            hr += w1c.x * pxp.x - w1c.y * pxp.y;
+            hi += w1c.x * pxp.y + w1c.y * pxp.x;
+            hr -= w1m.x * pxm.x + w1m.y * pxm.y;
+            hi -= w1m.x * pxm.y - w1m.y * pxm.x;
+            const double qx = m * pc.x - hr, qy = m * pc.y - hi;
+            xv.x += al * pv.x;
+            xv.y += al * pv.y;
+            rv.x -= al * qx;
+            rv.y -= al * qy;
+            a.x[row + j] = xv;
+            a.r[row + j] = rv;
+            acc += rv.x * rv.x + rv.y * rv.y;
+            pm = pc;
+            pc = pp;
+            w0m = w0c;
+          }
+        }
+      }
+    }
+    block_partial(acc, g, s, red);
+    grid_arrive(sl.gbar, bar_target);
+    if (blockIdx.x == 0) block0_scalars<FIN_RR, TB_RED_RR>(g, s, sl, red, gen, 3 * gen + 2);
+    wait_go(sl, 3 * gen + 2);
+    if (*(volatile int *)s.n_active == 0) break;
+
+    // ---- C: p = r + beta p for the chains that go on: generation gen + 1
+    if (chain && __ldcg(&s.active[c]) != 0) {
+      const double be = __ldcg(&s.beta[c]);
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const BlockPos b = tile_pos(g, tile);
+        if (b.valid) {
+          const size_t j = (size_t)b.x * g.C + b.c;
+          const int t0 = b.ttile * TT;
+#pragma unroll
+          for (int i = 0; i < TT; i++) {
+            const int t = t0 + i;
+            if (t < g.nt) {
+              const size_t k = t * R + j;
+              const double2 rv = __ldcg(&a.r[k]);
+              double2 pv = __ldcg(&a.p[k]);
+              pv.x = rv.x + be * pv.x;
+              pv.y = rv.y + be * pv.y;
+              a.p[k] = pv;
+            }
+          }
+        }
+      }
+    }
+    grid_barrier(sl.gbar, bar_target);
+    gen++;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      __threadfence_system();
+      *(volatile int *)(sl.sig_prev + TB_FLAG_PREADY * 2) = gen;
+      *(volatile int *)(sl.sig_next + TB_FLAG_PREADY * 2) = gen;
+    }
+  }
+  // every rank leaves in the same iteration (identical scalars).  Leave the epoch and the flags as the multi-kernel
+  // protocol expects them: nobody reads p or Mp of this solve any more.
+  grid_barrier(sl.gbar, bar_target);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *sl.seq = gen;
+    __threadfence_system();
+    for (int kind = 0; kind < TB_NFLAGS; kind++) {
+      *(volatile int *)(sl.sig_prev + kind * 2) = gen;
+      *(volatile int *)(sl.sig_next + kind * 2) = gen;
+    }
+    __threadfence_system();
+  }
+}
+
 // plain per-chain Re<a,b>
 template <int TT>
 __global__ void __launch_bounds__(TB_MAX_BLOCK)
@@ -1036,6 +1408,43 @@ int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out) {
   return launch_dslash_t<true>(ctx, k);
 }
 
+// slab mode: the whole solve as one persistent cooperative launch per GPU (slab_cg_persistent_kernel)
+// Measured on 2 GPUs (us per CG iteration, multi-kernel -> one launch): 2048^2 142.6 -> 134.9; 1024^2 (the per-GPU size
+// of 2048^2 on 8 GPUs) 78.4 -> 42.1; 512^2 68.0 -> 39.0.  Slabs of more than 4M sites are HBM-bound, where the
+// multi-kernel path (L1-cached neighbour loads, four blocks per SM) is at 0.85 of the HBM peak: it keeps those.
+static bool use_persistent_slab(const tb_ctx *ctx) {
+  return ctx->nranks > 1 && ctx->g.nctiles == 1 && !ctx->msite && tb_conj_is_dagger(ctx) && ctx->cg_variant != 4 &&
+         ctx->nsite <= ((size_t)4 << 20) && getenv("TB_NO_PERSIST") == nullptr;
+}
+
+template <int TT>
+static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int *nblocks_out) {
+  TbGeom g = ctx->g;   // same tiles, TT rows each (8: 80 registers, three blocks per SM)
+  g.tt = TT;
+  g.nttiles = (ctx->nt + TT - 1) / TT;
+  g.nslots = g.nxtiles * g.nttiles;
+  const TbSlab &sl = ctx->slab;
+  SlabCgArgs a = {b, ctx->xw, ctx->r, ctx->p, ctx->Mp, sl.p_prev, sl.p_next, sl.mp_prev, sl.mp_next,
+                  ctx->W0, sl.W0_prev, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu};
+  auto kern = slab_cg_persistent_kernel<TT>;
+  int per_sm = 0, nsm = TB_NUM_SMS_B200, coop = 0;
+  TB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+  TB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
+  TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g.bc * g.bx, 0));
+  if (!coop || per_sm < 1) { *nblocks_out = 0; return TB_OK; }
+  int nblocks = g.nxtiles * g.nttiles;
+  if (nblocks > per_sm * nsm) nblocks = per_sm * nsm;
+  TB_CUDA(cudaMemsetAsync(sl.gbar, 0, sizeof(unsigned long long), ctx->stream));
+  TbGeom gg = g;
+  TbCgState ss = ctx->cg;
+  TbSlab sls = sl;
+  void *args[] = {&a, &gg, &ss, &sls};
+  TB_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(nblocks), dim3(g.bc * g.bx), args, 0, ctx->stream));
+  ctx->launches++;
+  *nblocks_out = nblocks;
+  return TB_OK;
+}
+
 // Streaming CG driver: the whole solve stays on the device; the host only polls the number of chains
 // still iterating, one graph launch (tune_chunk iterations) behind the device.
 int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
@@ -1048,6 +1457,14 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
   const bool fused = tb_conj_is_dagger(ctx) && ctx->cg_variant != 4;
   cg_reset_kernel<<<(g.Cpad + 255) / 256, 256, 0, st>>>(g, ctx->cg);
   ctx->launches++;
+  if (use_persistent_slab(ctx)) {
+    int nblocks = 0;
+    TB_CHECK(launch_persistent_slab<8>(ctx, b, &nblocks));
+    if (nblocks > 0) {
+      TB_CUDA(cudaMemcpyAsync(x, ctx->xw, ctx->nsite * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+      return TB_OK;
+    }
+  }
   if (slab) {
     slab_bump_kernel<<<1, 1, 0, st>>>(ctx->slab);
     TB_DISPATCH_TT(g.tt, (cg_init_kernel<TT, true><<<grid, block, 0, st>>>(b, ctx->xw, ctx->r, ctx->p, g, ctx->cg, ctx->slab)))
