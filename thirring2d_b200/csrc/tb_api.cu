@@ -129,10 +129,10 @@ int tb_create_common(tb_ctx **out, int nt, int nx, int nchains, int mode, int de
   if (nranks > 1) {  // p, Mp and W0 live in the IPC-exported exchange block
     if (rc == TB_OK) rc = tb_slab_layout(ctx);
   } else {
-    A_(ctx->W0, n) A_(ctx->p, n) A_(ctx->Mp, n)
+    A_(ctx->W0, n) A_(ctx->p, n) A_(ctx->Mp, n) A_(ctx->r, n)
   }
   A_(ctx->W1, n) A_(ctx->Adev, n)
-  A_(ctx->r, n) A_(ctx->q, n) A_(ctx->xw, n) A_(ctx->tmp, n)
+  A_(ctx->q, n) A_(ctx->xw, n) A_(ctx->tmp, n)
   A_(ctx->vin, n) A_(ctx->vout, n)
   A_(ctx->stage, 2 * n)
   A_(ctx->stage_x, n)
@@ -190,7 +190,7 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
   const bool slab = ctx->nranks > 1;
   tb_slab_release(ctx);
   tb_hmc_release(ctx);
-  void *dev[] = {ctx->d_mass, ctx->d_emu, ctx->d_emmu, slab ? nullptr : (void *)ctx->W0, ctx->W1, ctx->Adev, ctx->r,
+  void *dev[] = {ctx->d_mass, ctx->d_emu, ctx->d_emmu, slab ? nullptr : (void *)ctx->W0, ctx->W1, ctx->Adev, slab ? nullptr : (void *)ctx->r,
                  slab ? nullptr : (void *)ctx->p, slab ? nullptr : (void *)ctx->Mp, ctx->q, ctx->xw, ctx->tmp, ctx->vin, ctx->vout, ctx->stage, ctx->stage_x, ctx->cg.rr_old, ctx->cg.active,
                  ctx->cg.partial, ctx->cg.ticket};
   for (void *p : dev)

@@ -73,6 +73,8 @@ struct TbSlab {
   int P, rank;
   // peer views of the two exchange vectors and of the t-links
   const double2 *p_prev, *p_next, *mp_prev, *mp_next, *W0_prev;
+  // one-launch solve: the neighbours' residual and second direction buffer (p is double-buffered there)
+  const double2 *r_prev, *r_next, *p1_prev, *p1_next;
   // my flags: flags[kind*2 + side], side 0 = written by the previous rank, 1 = by the next rank
   volatile int *flags;
   int *sig_prev;  // previous rank's flags + 1 (its "from next" side):  sig_prev[kind*2]
@@ -123,6 +125,7 @@ struct tb_ctx {
   int *occ_dev, *occ_stage;
   // work vectors (device layout)
   double2 *r, *p, *Mp, *q, *xw, *tmp, *vin, *vout;
+  double2 *p1;    // slab mode: second direction buffer of the one-launch solve (in the exchange block, like p, Mp, r)
   double2 *Adev;  // angles (A0,A1) in device layout
   double *stage;  // canonical-layout device staging buffer (2*nsite doubles)
   double *h_pinned;  // pinned host staging (2*nsite doubles)

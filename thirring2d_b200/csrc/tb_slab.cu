@@ -5,7 +5,7 @@
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SlabOffsets {
-  size_t p, mp, w0, red, red_flag, flags, total;
+  size_t p, mp, w0, r, p1, red, red_flag, flags, total;
 };
 
 static SlabOffsets slab_offsets(const tb_ctx *ctx) {
@@ -14,7 +14,9 @@ static SlabOffsets slab_offsets(const tb_ctx *ctx) {
   o.p = 0;
   o.mp = vec;
   o.w0 = 2 * vec;
-  o.red = 3 * vec;
+  o.r = 3 * vec;
+  o.p1 = 4 * vec;
+  o.red = 5 * vec;
   o.red_flag = o.red + align_up((size_t)TB_NRED * ctx->nranks * ctx->g.Cpad * sizeof(double), 256);
   o.flags = o.red_flag + align_up((size_t)TB_NRED * ctx->nranks * ctx->g.nctiles * sizeof(int), 256);
   o.total = o.flags + 256;
@@ -35,6 +37,8 @@ int tb_slab_layout(tb_ctx *ctx) {
   ctx->p = (double2 *)(base + o.p);
   ctx->Mp = (double2 *)(base + o.mp);
   ctx->W0 = (double2 *)(base + o.w0);
+  ctx->r = (double2 *)(base + o.r);
+  ctx->p1 = (double2 *)(base + o.p1);
   int *local = nullptr;
   e = cudaMalloc((void **)&local, (2 + TB_NFLAGS + 6) * sizeof(int));
   if (e != cudaSuccess) {
@@ -104,6 +108,10 @@ extern "C" int tb_slab_connect(tb_ctx *ctx, const void *all_handles) {
   sl.mp_prev = (const double2 *)(pv + o.mp);
   sl.mp_next = (const double2 *)(nx + o.mp);
   sl.W0_prev = (const double2 *)(pv + o.w0);
+  sl.r_prev = (const double2 *)(pv + o.r);
+  sl.r_next = (const double2 *)(nx + o.r);
+  sl.p1_prev = (const double2 *)(pv + o.p1);
+  sl.p1_next = (const double2 *)(nx + o.p1);
   sl.flags = (volatile int *)(me + o.flags);
   sl.sig_prev = (int *)(pv + o.flags) + 1;  // the previous rank sees me as its "next" neighbour
   sl.sig_next = (int *)(nx + o.flags) + 0;  // the next rank sees me as its "previous" neighbour

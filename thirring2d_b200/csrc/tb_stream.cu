@@ -599,23 +599,25 @@ slab_scalars_kernel(const TbGeom g, const TbCgState s, const TbSlab sl) {
 // hand-shakes per iteration (2048^2 on 8 GPUs: 25 us of kernels in an 82 us iteration).  Here every GPU runs one
 // persistent cooperative kernel; a block owns a fixed set of tiles for the whole solve and the phases of an iteration
 // are separated by grid barriers (an atomic counter in L2) instead of kernel boundaries:
-//   A  Mp = M p, |Mp|^2        barrier   block 0: all-reduce over the GPUs -> alpha     (hmc.c:366,368-371)
+//   A  p = r + beta p on the fly (hmc.c:391-392), Mp = M p, |Mp|^2
+//                               barrier   block 0: all-reduce over the GPUs -> alpha     (hmc.c:366,368-371)
 //   B  q = M^dagger Mp on the fly, x += alpha p, r -= alpha q, ||r||^2
 //                               barrier   block 0: all-reduce -> beta, convergence        (hmc.c:367,372-390)
-//   C  p = r + beta p           barrier   block 0: "generation k+1 of p is complete" to both neighbours (hmc.c:391-392)
-// The all-reduce is the one-shot peer-store exchange of the multi-kernel path (every rank stores its partial into
-// every rank's slot table, sums in rank order => bitwise identical scalars and decisions on all ranks).  It doubles
-// as the cross-GPU fence for the halo rows: a rank contributes to the |Mp|^2 sum only after its phase A, so whoever
-// holds the sum knows that (i) the neighbours' Mp rows are complete and (ii) nobody reads generation k of p any
-// more; likewise ||r||^2 for the Mp rows.  Only "p is complete" needs a flag of its own, and only tiles in the first
-// and last rows of the slab wait for it (they are scheduled last).  Fields that are rewritten during the launch are
-// loaded with ld.global.cg: L1 is not coherent across the phases of one kernel.
+// Two synchronisation points per iteration.  p is double-buffered and never exchanged: phase A recomputes
+// p = r + beta p_old at the five points of its stencil (the same fma everywhere, so the copies agree to the bit with
+// the stored one), reading the neighbours' rows of r and p_old.  The all-reduce is the one-shot peer-store exchange of
+// the multi-kernel path (every rank stores its partial into every rank's slot table, sums in rank order => bitwise
+// identical scalars and decisions on all ranks), and it doubles as the cross-GPU fence for the halo rows: a rank
+// contributes to the |Mp|^2 sum only after its phase A, so whoever holds the sum knows that the neighbours' Mp rows
+// are complete and that nobody reads r or p_old of this iteration any more; likewise ||r||^2 for r, the new p and the
+// Mp rows.  No neighbour flag is left inside the solve.  Fields that are rewritten during the launch are loaded with
+// ld.global.cg: L1 is not coherent across the phases of one kernel.
 // ranks enter the launch seconds apart when one of them is still busy on the host: ~20 s before a wait gives up
 #define TB_PERSIST_SPIN_CYCLES 40000000000LL
 struct SlabCgArgs {
   const double2 *b;
-  double2 *x, *r, *p, *Mp;
-  const double2 *p_prev, *p_next, *mp_prev, *mp_next;
+  double2 *x, *r, *p, *p1, *Mp;
+  const double2 *p_prev, *p_next, *p1_prev, *p1_next, *r_prev, *r_next, *mp_prev, *mp_next;
   const double2 *W0, *W0_prev, *W1;
   const double *mass, *emu, *emmu;
 };
@@ -738,7 +740,7 @@ __device__ __forceinline__ void wait_go(const TbSlab &sl, int go_value) {
 }
 
 template <int TT>
-__global__ void __launch_bounds__(TB_MAX_BLOCK)
+__global__ void __launch_bounds__(TB_MAX_BLOCK, 3)
 slab_cg_persistent_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, const TbSlab sl) {
   __shared__ double red[TB_MAX_BLOCK];
   const int ntiles = g.nxtiles * g.nttiles;
@@ -787,23 +789,27 @@ slab_cg_persistent_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s,
   block_partial(acc, g, s, red);
   grid_arrive(sl.gbar, bar_target);
   int gen = E0 + 1;   // generation of p
-  if (blockIdx.x == 0) {
-    block0_scalars<FIN_INIT, TB_RED_INIT>(g, s, sl, red, gen, 3 * gen);
-    if (threadIdx.x == 0) {
-      __threadfence_system();
-      *(volatile int *)(sl.sig_prev + TB_FLAG_PREADY * 2) = gen;
-      *(volatile int *)(sl.sig_next + TB_FLAG_PREADY * 2) = gen;
-    }
-  }
+  if (blockIdx.x == 0) block0_scalars<FIN_INIT, TB_RED_INIT>(g, s, sl, red, gen, 3 * gen);
   wait_go(sl, 3 * gen);
 
-  while (*(volatile int *)s.n_active > 0) {
+  // p is double-buffered: odd iterations read p_old from a.p and write p_new into a.p1, even ones the other way round
+  int n_act = *(volatile int *)s.n_active;
+  for (int k = 1; n_act > 0; k++) {
     const bool act = chain && __ldcg(&s.active[c]) != 0;
-    // ---- A: Mp = M p, |Mp|^2
+    const double be = chain ? __ldcg(&s.beta[c]) : 0.0;   // 0 in the first iteration: p = r (hmc.c:352-353)
+    const bool odd = k & 1;   // p_old of iteration 1 is a.p (= b, times beta = 0)
+    const double2 *po = odd ? a.p : a.p1, *po_prev = odd ? a.p_prev : a.p1_prev, *po_next = odd ? a.p_next : a.p1_next;
+    double2 *pn = odd ? a.p1 : a.p;
+    // p = r + beta p (hmc.c:391-392) wherever the stencil needs it; the same fma everywhere, so the five copies of a
+    // site's p agree to the bit with the one that is stored
+    auto pnew = [&](const double2 rv, const double2 pv) {
+      return make_double2(fma(be, pv.x, rv.x), fma(be, pv.y, rv.y));
+    };
+    // ---- A: p = r + beta p on the fly, Mp = M p, |Mp|^2.  The neighbours' rows of r and of the old p are complete:
+    // their owners passed the ||r||^2 all-reduce of the previous iteration.
     acc = 0.0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
       const BlockPos b = tile_pos(g, tile);
-      wait_ends(b, TB_FLAG_PREADY, gen);
       if (b.valid && act) {
         const size_t j = (size_t)b.x * g.C + b.c;
         const size_t jp = (size_t)((b.x + 1 == g.nx) ? 0 : b.x + 1) * g.C + b.c;
@@ -811,21 +817,24 @@ slab_cg_persistent_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s,
         const int t0 = b.ttile * TT;
         double2 pm, w0m;
         if (t0 == 0) {
-          pm = __ldcv(&a.p_prev[(size_t)(g.nt - 1) * R + j]);
-          w0m = __ldcv(&a.W0_prev[(size_t)(g.nt - 1) * R + j]);
+          const size_t kk = (size_t)(g.nt - 1) * R + j;
+          pm = pnew(__ldcv(&a.r_prev[kk]), __ldcv(&po_prev[kk]));
+          w0m = __ldcv(&a.W0_prev[kk]);
         } else {
-          pm = __ldcg(&a.p[(size_t)(t0 - 1) * R + j]);
-          w0m = a.W0[(size_t)(t0 - 1) * R + j];
+          const size_t kk = (size_t)(t0 - 1) * R + j;
+          pm = pnew(__ldcg(&a.r[kk]), __ldcg(&po[kk]));
+          w0m = a.W0[kk];
         }
-        double2 pc = __ldcg(&a.p[t0 * R + j]);
+        double2 pc = pnew(__ldcg(&a.r[t0 * R + j]), __ldcg(&po[t0 * R + j]));
 #pragma unroll
         for (int i = 0; i < TT; i++) {
           const int t = t0 + i;
           if (t < g.nt) {
             const size_t row = t * R;
-            const double2 pp = (t + 1 == g.nt) ? __ldcv(&a.p_next[j]) : __ldcg(&a.p[row + R + j]);
-            const double2 pxp = __ldcg(&a.p[row + jp]);
-            const double2 pxm = __ldcg(&a.p[row + jm]);
+            const double2 pp = (t + 1 == g.nt) ? pnew(__ldcv(&a.r_next[j]), __ldcv(&po_next[j]))
+                                               : pnew(__ldcg(&a.r[row + R + j]), __ldcg(&po[row + R + j]));
+            const double2 pxp = pnew(__ldcg(&a.r[row + jp]), __ldcg(&po[row + jp]));
+            const double2 pxm = pnew(__ldcg(&a.r[row + jm]), __ldcg(&po[row + jm]));
             const double2 w0c = a.W0[row + j];
             const double2 w1c = a.W1[row + j];
             const double2 w1m = a.W1[row + jm];
@@ -842,6 +851,7 @@ slab_cg_persistent_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s,
             double2 o;
             o.x = m * pc.x + hr;
             o.y = m * pc.y + hi;
+            pn[row + j] = pc;
             a.Mp[row + j] = o;
             acc += o.x * o.x + o.y * o.y;   // <p, M^dagger M p> = |M p|^2
             pm = pc;
@@ -856,7 +866,8 @@ slab_cg_persistent_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s,
     if (blockIdx.x == 0) block0_scalars<FIN_PQ, TB_RED_PQ>(g, s, sl, red, gen, 3 * gen + 1);
     wait_go(sl, 3 * gen + 1);
 
-    // ---- B: q = M^dagger Mp on the fly, x += alpha p, r -= alpha q, ||r||^2
+    // ---- B: q = M^dagger Mp on the fly, x += alpha p, r -= alpha q, ||r||^2.  The neighbours' Mp rows are complete:
+    // their owners contributed to the |Mp|^2 sum.
     acc = 0.0;
     const double al = chain ? __ldcg(&s.alpha[c]) : 0.0;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -886,7 +897,7 @@ slab_cg_persistent_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s,
             const double2 w0c = a.W0[row + j];
             const double2 w1c = a.W1[row + j];
             const double2 w1m = a.W1[row + jm];
-            const double2 pv = __ldcg(&a.p[row + j]);
+            const double2 pv = __ldcg(&pn[row + j]);
             double2 xv = __ldcg(&a.x[row + j]), rv = __ldcg(&a.r[row + j]);
             const double fr = w0c.x * e_m, fi = w0c.y * e_m;   // M^dagger: e^{-mu} on the +t hop
             const double br = w0m.x * e_p, bi = w0m.y * e_p;
@@ -917,38 +928,8 @@ slab_cg_persistent_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s,
     grid_arrive(sl.gbar, bar_target);
     if (blockIdx.x == 0) block0_scalars<FIN_RR, TB_RED_RR>(g, s, sl, red, gen, 3 * gen + 2);
     wait_go(sl, 3 * gen + 2);
-    if (*(volatile int *)s.n_active == 0) break;
-
-    // ---- C: p = r + beta p for the chains that go on: generation gen + 1
-    if (chain && __ldcg(&s.active[c]) != 0) {
-      const double be = __ldcg(&s.beta[c]);
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const BlockPos b = tile_pos(g, tile);
-        if (b.valid) {
-          const size_t j = (size_t)b.x * g.C + b.c;
-          const int t0 = b.ttile * TT;
-#pragma unroll
-          for (int i = 0; i < TT; i++) {
-            const int t = t0 + i;
-            if (t < g.nt) {
-              const size_t k = t * R + j;
-              const double2 rv = __ldcg(&a.r[k]);
-              double2 pv = __ldcg(&a.p[k]);
-              pv.x = rv.x + be * pv.x;
-              pv.y = rv.y + be * pv.y;
-              a.p[k] = pv;
-            }
-          }
-        }
-      }
-    }
-    grid_barrier(sl.gbar, bar_target);
+    n_act = *(volatile int *)s.n_active;
     gen++;
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-      __threadfence_system();
-      *(volatile int *)(sl.sig_prev + TB_FLAG_PREADY * 2) = gen;
-      *(volatile int *)(sl.sig_next + TB_FLAG_PREADY * 2) = gen;
-    }
   }
   // every rank leaves in the same iteration (identical scalars).  Leave the epoch and the flags as the multi-kernel
   // protocol expects them: nobody reads p or Mp of this solve any more.
@@ -1409,8 +1390,8 @@ int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out) {
 }
 
 // slab mode: the whole solve as one persistent cooperative launch per GPU (slab_cg_persistent_kernel)
-// Measured on 2 GPUs (us per CG iteration, multi-kernel -> one launch): 2048^2 142.6 -> 134.9; 1024^2 (the per-GPU size
-// of 2048^2 on 8 GPUs) 78.4 -> 42.1; 512^2 68.0 -> 39.0.  Slabs of more than 4M sites are HBM-bound, where the
+// Measured on 2 GPUs (us per CG iteration, multi-kernel -> one launch): 2048^2 142.6 -> 122.8; 1024^2 (the per-GPU size
+// of 2048^2 on 8 GPUs) 78.4 -> 37.0; 512^2 68.0 -> 32.7.  Slabs of more than 4M sites are HBM-bound, where the
 // multi-kernel path (L1-cached neighbour loads, four blocks per SM) is at 0.85 of the HBM peak: it keeps those.
 static bool use_persistent_slab(const tb_ctx *ctx) {
   return ctx->nranks > 1 && ctx->g.nctiles == 1 && !ctx->msite && tb_conj_is_dagger(ctx) && ctx->cg_variant != 4 &&
@@ -1424,7 +1405,8 @@ static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int *nblocks_ou
   g.nttiles = (ctx->nt + TT - 1) / TT;
   g.nslots = g.nxtiles * g.nttiles;
   const TbSlab &sl = ctx->slab;
-  SlabCgArgs a = {b, ctx->xw, ctx->r, ctx->p, ctx->Mp, sl.p_prev, sl.p_next, sl.mp_prev, sl.mp_next,
+  SlabCgArgs a = {b, ctx->xw, ctx->r, ctx->p, ctx->p1, ctx->Mp, sl.p_prev, sl.p_next, sl.p1_prev, sl.p1_next,
+                  sl.r_prev, sl.r_next, sl.mp_prev, sl.mp_next,
                   ctx->W0, sl.W0_prev, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu};
   auto kern = slab_cg_persistent_kernel<TT>;
   int per_sm = 0, nsm = TB_NUM_SMS_B200, coop = 0;
