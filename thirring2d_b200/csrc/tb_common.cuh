@@ -90,6 +90,9 @@ struct TbSlab {
   // persistent solve (tb_stream.cu: slab_cg_persistent_kernel): grid barrier counter and block 0's broadcast flag
   unsigned long long *gbar;
   int *go;
+  // one-launch solve: all-reduce slots {partial, tag} written by one 16-byte store, [(kind*P + q)*Cpad + c] in MY memory
+  double2 *red2;
+  double2 *peer_red2[TB_SLAB_MAX_RANKS];
 };
 
 // buffers of the device-resident HMC trajectory (tb_hmc.cu), allocated at first use

@@ -5,7 +5,7 @@
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SlabOffsets {
-  size_t p, mp, w0, r, p1, red, red_flag, flags, total;
+  size_t p, mp, w0, r, p1, red, red_flag, flags, red2, total;
 };
 
 static SlabOffsets slab_offsets(const tb_ctx *ctx) {
@@ -19,7 +19,8 @@ static SlabOffsets slab_offsets(const tb_ctx *ctx) {
   o.red = 5 * vec;
   o.red_flag = o.red + align_up((size_t)TB_NRED * ctx->nranks * ctx->g.Cpad * sizeof(double), 256);
   o.flags = o.red_flag + align_up((size_t)TB_NRED * ctx->nranks * ctx->g.nctiles * sizeof(int), 256);
-  o.total = o.flags + 256;
+  o.red2 = o.flags + 256;
+  o.total = o.red2 + align_up((size_t)TB_NRED * ctx->nranks * ctx->g.Cpad * sizeof(double2), 256);
   return o;
 }
 
@@ -117,9 +118,11 @@ extern "C" int tb_slab_connect(tb_ctx *ctx, const void *all_handles) {
   sl.sig_next = (int *)(nx + o.flags) + 0;  // the next rank sees me as its "previous" neighbour
   sl.red = (double *)(me + o.red);
   sl.red_flag = (volatile int *)(me + o.red_flag);
+  sl.red2 = (double2 *)(me + o.red2);
   for (int q = 0; q < P; q++) {
     sl.peer_red[q] = (double *)((char *)ctx->peer_block[q] + o.red);
     sl.peer_red_flag[q] = (int *)((char *)ctx->peer_block[q] + o.red_flag);
+    sl.peer_red2[q] = (double2 *)((char *)ctx->peer_block[q] + o.red2);
   }
   ctx->slab_connected = true;
   return TB_OK;

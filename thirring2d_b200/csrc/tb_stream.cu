@@ -679,54 +679,80 @@ __device__ __forceinline__ BlockPos tile_pos(const TbGeom &g, int tile) {
   return b;
 }
 
+// per-chain sum of `v` over the block (thread = x_local * bc + chain, bc <= 32): xor-shuffles between the lanes of a
+// warp that hold the same chain, then the eight warp partials in warp order; valid in threads tid < bc.  Fixed shape:
+// deterministic.
+__device__ __forceinline__ double block_sum_chains(double v, const TbGeom &g, double *red) {
+  for (int o = 16; o >= g.bc; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  __syncthreads();   // red may still be read by the previous call
+  if (lane < g.bc) red[warp * g.bc + lane] = v;
+  __syncthreads();
+  double t = 0.0;
+  if ((int)threadIdx.x < g.bc)
+    for (int w = 0; w < nwarp; w++) t += red[w * g.bc + threadIdx.x];
+  return t;
+}
+
 // per-chain sum of `acc` over the block -> partial[blockIdx.x][chain]
 __device__ __forceinline__ void block_partial(double acc, const TbGeom &g, const TbCgState &s, double *red) {
-  const int c_local = threadIdx.x & (g.bc - 1), x_local = threadIdx.x >> g.bc_shift;
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  for (int st = g.bx >> 1; st > 0; st >>= 1) {
-    if (x_local < st) red[threadIdx.x] += red[threadIdx.x + st * g.bc];
-    __syncthreads();
-  }
-  if (x_local == 0) s.partial[(size_t)blockIdx.x * g.Cpad + c_local] = red[c_local];
-  __syncthreads();
+  const double t = block_sum_chains(acc, g, red);
+  if ((int)threadIdx.x < g.bc) s.partial[(size_t)blockIdx.x * g.Cpad + threadIdx.x] = t;
+}
+
+__device__ __forceinline__ void st_volatile_v2(double2 *p, long long x, long long y) {
+  asm volatile("st.volatile.global.v2.b64 [%0], {%1, %2};\n" ::"l"(p), "l"(x), "l"(y) : "memory");
+}
+__device__ __forceinline__ void ld_volatile_v2(const double2 *p, long long &x, long long &y) {
+  asm volatile("ld.volatile.global.v2.b64 {%0, %1}, [%2];\n" : "=l"(x), "=l"(y) : "l"(p) : "memory");
 }
 
 // block 0, after the grid barrier: sum the block partials in block order, all-reduce over the ranks, evaluate the CG
-// scalars (finalize_scalar), then release the other blocks of this GPU through *sl.go = go_value
+// scalars (finalize_scalar), then release the other blocks of this GPU through *sl.go = go_value.
+// The exchange is one 16-byte store per (peer, chain): {bits of the partial, the same bits xor a tag of the sequence
+// number}.  Value and tag travel together, so no fence (an NVLink round trip) separates them, and a reader that caught
+// the two halves of different generations sees a tag that matches nothing and polls again; thread (q, chain) polls the
+// slot that rank q writes into this GPU's memory.
 template <int FIN, int RED>
 __device__ __forceinline__ void block0_scalars(const TbGeom &g, const TbCgState &s, const TbSlab &sl, double *red,
                                                int seqv, int go_value) {
   const int c_local = threadIdx.x & (g.bc - 1), x_local = threadIdx.x >> g.bc_shift;
   double sum = 0.0;
   for (int blk = x_local; blk < (int)gridDim.x; blk += g.bx) sum += __ldcg(&s.partial[(size_t)blk * g.Cpad + c_local]);
-  red[threadIdx.x] = sum;
+  const double mine = block_sum_chains(sum, g, red);   // threads < bc
   __syncthreads();
-  for (int st = g.bx >> 1; st > 0; st >>= 1) {
-    if (x_local < st) red[threadIdx.x] += red[threadIdx.x + st * g.bc];
-    __syncthreads();
-  }
-  if (x_local == 0) {
-    const double total = red[c_local];
-    for (int q = 0; q < sl.P; q++) sl.peer_red[q][(size_t)(RED * sl.P + sl.rank) * g.Cpad + c_local] = total;
-    __threadfence_system();
+  if ((int)threadIdx.x < g.bc) red[threadIdx.x] = mine;
+  __syncthreads();
+  const bool io = (int)threadIdx.x < sl.P * g.bc;   // thread (q, chain)
+  const int q = threadIdx.x >> g.bc_shift;
+  const size_t slot = (size_t)(RED * sl.P) * g.Cpad + c_local;
+  double theirs = 0.0;
+  if (io) {
+    const double v = red[c_local];
+    __threadfence_system();   // this GPU's halo rows (visible device-wide since the grid barrier) before the tag
+    const long long tag = (long long)((unsigned long long)seqv * 0x9E3779B97F4A7C15ULL);
+    st_volatile_v2(sl.peer_red2[q] + slot + (size_t)sl.rank * g.Cpad, __double_as_longlong(v), __double_as_longlong(v) ^ tag);
+    const double2 *in = sl.red2 + slot + (size_t)q * g.Cpad;
+    const long long t0 = clock64();
+    for (;;) {
+      long long wx, wy;
+      ld_volatile_v2(in, wx, wy);
+      if ((wx ^ wy) == tag) { theirs = __longlong_as_double(wx); break; }
+      if (clock64() - t0 > TB_PERSIST_SPIN_CYCLES) __trap();
+    }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    for (int q = 0; q < sl.P; q++) *(volatile int *)(sl.peer_red_flag[q] + (RED * sl.P + sl.rank) * g.nctiles) = seqv;
-  }
-  if ((int)threadIdx.x < sl.P) spin_until(sl.red_flag + (RED * sl.P + threadIdx.x) * g.nctiles, seqv);
+  if (io) red[threadIdx.x] = theirs;   // [q][chain]
   __syncthreads();
   if (x_local == 0 && c_local < g.C) {
     double total = 0.0;
-    for (int q = 0; q < sl.P; q++) total += __ldcv(&sl.red[(size_t)(RED * sl.P + q) * g.Cpad + c_local]);
+    for (int r = 0; r < sl.P; r++) total += red[r * g.bc + c_local];   // rank order: the same bits on every rank
     finalize_scalar<FIN>(total, c_local, 0, s);
   }
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    __threadfence_system();   // acquire side of the exchange: the neighbours' rows, for the blocks that wait on go
     *(volatile int *)sl.go = go_value;
   }
 }
@@ -1390,8 +1416,8 @@ int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out) {
 }
 
 // slab mode: the whole solve as one persistent cooperative launch per GPU (slab_cg_persistent_kernel)
-// Measured on 2 GPUs (us per CG iteration, multi-kernel -> one launch): 2048^2 142.6 -> 122.8; 1024^2 (the per-GPU size
-// of 2048^2 on 8 GPUs) 78.4 -> 37.0; 512^2 68.0 -> 32.7.  Slabs of more than 4M sites are HBM-bound, where the
+// Measured on 2 GPUs (us per CG iteration, multi-kernel -> one launch): 2048^2 142.6 -> 120.5; 1024^2 (the per-GPU size
+// of 2048^2 on 8 GPUs) 78.4 -> 33.5; 512^2 68.0 -> 29.0.  Slabs of more than 4M sites are HBM-bound, where the
 // multi-kernel path (L1-cached neighbour loads, four blocks per SM) is at 0.85 of the HBM peak: it keeps those.
 static bool use_persistent_slab(const tb_ctx *ctx) {
   return ctx->nranks > 1 && ctx->g.nctiles == 1 && !ctx->msite && tb_conj_is_dagger(ctx) && ctx->cg_variant != 4 &&
