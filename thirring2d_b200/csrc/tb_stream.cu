@@ -1132,7 +1132,7 @@ int tb_choose_geom(tb_ctx *ctx) {
   g.ta_shift = g.bc_shift;
   // TMA-staged kernels: a tile holds EVERY chain of its sites, so the sites of a tile are one contiguous run of a row
   // and a row of the tile is one bulk copy per array (4 KB) plus three halo sites.  Measured per CG iteration against
-  // the marching kernels (B200, gpurun_out/probe_pipe_r01n.txt): 2048^2 x 1 chain 189 -> 167 us, 1024^2 x 4 188 -> 171,
+  // the marching kernels (B200, gpurun_out/probe_pipe_r01s.txt): 2048^2 x 1 chain 189 -> 167 us, 1024^2 x 4 188 -> 171,
   // 512^2 x 16 191 -> 169; 256^2 x 32 equal; 256^2 x 64 (4 sites per tile: the halo sites are a quarter of the
   // traffic into shared memory) 191 -> 196; 256^2 x 128 360 -> 389.  Tiles of 32 out of 64 chains (a 512-byte copy per
   // site) were 1.5x SLOWER: the copy engine of an SM retires a small copy every ~65 cycles.  So: batches of up to 16
