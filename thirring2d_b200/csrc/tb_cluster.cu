@@ -454,7 +454,7 @@ struct ClusterLaunch {
   static int config(Kern kern, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, int nclusters, cudaStream_t st) {
     TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Slab<NX>::SMEM));
     if (CS > 8) TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-    memset(cfg, 0, sizeof(*cfg));
+    *cfg = cudaLaunchConfig_t{};
     cfg->gridDim = dim3((unsigned)(nclusters * CS), 1, 1);
     cfg->blockDim = dim3(NTHREADS, 1, 1);
     cfg->dynamicSmemBytes = Slab<NX>::SMEM;

@@ -363,7 +363,7 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
                    const double *__restrict__ emu, const double *__restrict__ emmu, const TbCgState s, const int C,
                    const int c_first, const TbPlan plan) {
   using Cfg = ResidentWtCfg<NT, NX>;
-  constexpr int V = Cfg::V, NWARPS = Cfg::NWARPS, TX = 2, TT = 8, NG = NX / TX;
+  constexpr int V = Cfg::V, TX = 2, TT = 8, NG = NX / TX;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *Fp = reinterpret_cast<double2 *>(smem_raw);   // p, as the stencil neighbours read it
   double2 *Fm = Fp + V;                                  // Mp
