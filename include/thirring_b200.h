@@ -83,6 +83,16 @@ int tb_set_tuning(tb_ctx *ctx, int rows_per_thread, int iters_per_launch, int so
  * runs concurrently on this device (0 for streaming).  Either pointer may be NULL. */
 int tb_solver_info(tb_ctx *ctx, int *kind, int *chains_in_flight);
 
+/* Diagnostics, host only (no GPU involved): the schedule of a planned launch of the on-chip solvers.  A batch that
+ * fills its last wave of SMs (or of co-resident clusters) badly is cut into one equal share of CG iterations per
+ * machine; est[c] / status[c] are the iteration count and the TB_CG_* status of chain c in the previous solve.
+ * Output: segs4[4*s .. 4*s+3] = (chain, first iteration, end iteration, 0) for up to nchains + machines - 1
+ * segments; machine b runs segments [seg_lo[b], seg_hi[b]) in order.  first iteration > 1: the tail of a split
+ * chain (it waits for the head, which is the FIRST segment of a machine with a lower index); end iteration
+ * 0x7fffffff: until the chain ends.  The same code runs inside the library's plan_kernel. */
+int tb_plan_schedule(const int *est, const int *status, int nchains, int machines, int *segs4, int *seg_lo,
+                     int *seg_hi);
+
 /* ---- host-buffer entry points (copies inside; this is what the reference-facing shim calls) ---------- */
 
 /* Upload angles A and build the link fields W_mu = s * 1/2 * eta_mu * exp(iA_mu) once (replaces the

@@ -244,6 +244,61 @@ __device__ __noinline__ int plan_wait_hand(const int *hand) {
 // j + 1, tail [1 + first, end) LAST on machine j.  Machine j is CTA M - 1 - j, so the head's CTA has the lower index.
 // Without usable estimates (first solve of a context, or a chain that did not converge) chains are dealt out whole,
 // round-robin, which is what the hardware does with one CTA per chain.
+// Host and device: tb_plan_schedule (tb_resident.cu) runs the same code on the CPU for tests/test_plan_schedule.py.
+__host__ __device__ inline void plan_fill(const int *est, int C, int M, long long W, int mx, int4 *segs, int *seg_lo,
+                                          int *seg_hi) {
+  // A hand-over is not worth fewer than MINS iterations on either side.  A machine may therefore run over its share by
+  // up to MINS iterations (a short tail is stretched to MINS, a chain that overshoots by less stays whole) but is never
+  // left under it, and the share of the machines still to fill is recomputed from the work still to place: nothing
+  // piles up on the last machine (149 equal chains on 148 machines: 285 iterations on the busiest one, not 554).
+  const int INF = 0x7fffffff, MINS = 8;
+  long long left = W;   // iterations not placed yet
+  int nseg = 0, j = 0;
+  auto share = [&](int jj) {
+    const long long t = (left + (M - jj) - 1) / (M - jj);
+    return t < mx ? (long long)mx : t;   // >= the longest chain: a head always ends before its tail's turn comes
+  };
+  long long rem = share(0);
+  seg_lo[M - 1] = 0;
+  for (int c = 0; c < C; c++) {
+    const int n = est[c];
+    if (rem <= 0 && j < M - 1) {   // machine j is full
+      seg_hi[M - 1 - j] = nseg;
+      j++;
+      seg_lo[M - 1 - j] = nseg;
+      rem = share(j);
+    }
+    if (j == M - 1 || n <= rem + MINS || n < 2 * MINS) {   // whole
+      segs[nseg++] = make_int4(c, 1, INF, 0);
+      rem -= n;
+      left -= n;
+    } else {
+      const long long piece = rem > MINS ? rem : MINS;   // iterations of c that machine j runs: the tail, its last job
+      const int first = (int)(n - piece);                // >= MINS; the head: first job of machine j + 1
+      segs[nseg++] = make_int4(c, 1 + first, INF, 0);
+      left -= piece;
+      seg_hi[M - 1 - j] = nseg;
+      j++;
+      seg_lo[M - 1 - j] = nseg;
+      rem = share(j);
+      segs[nseg++] = make_int4(c, 1, 1 + first, 0);
+      rem -= first;
+      left -= first;
+    }
+  }
+  seg_hi[M - 1 - j] = nseg;
+  for (j++; j < M; j++) seg_lo[M - 1 - j] = seg_hi[M - 1 - j] = nseg;
+}
+
+// chains dealt out whole: CTA b gets chains b, b + M, ...
+__host__ __device__ inline void plan_deal(int b, int C, int M, int4 *segs, int *seg_lo, int *seg_hi) {
+  const int per = C / M, extra = C % M;
+  const int lo = b * per + (b < extra ? b : extra), cnt = per + (b < extra ? 1 : 0);
+  seg_lo[b] = lo;
+  seg_hi[b] = lo + cnt;
+  for (int i = 0; i < cnt; i++) segs[lo + i] = make_int4(b + i * M, 1, 0x7fffffff, 0);
+}
+
 __global__ void plan_kernel(const int *__restrict__ est, const int *__restrict__ status, int C, int M, int4 *segs,
                             int *seg_lo, int *seg_hi, int *hand) {
   extern __shared__ int est_s[];   // [C]: one thread walks the chains, out of shared memory
@@ -265,46 +320,11 @@ __global__ void plan_kernel(const int *__restrict__ est, const int *__restrict__
   atomicMax(&mx_s, mx);
   if (bad) atomicOr(&bad_s, 1);
   __syncthreads();
-  if (bad_s) {   // chains dealt out whole, round-robin
-    for (int b = threadIdx.x; b < M; b += blockDim.x) {
-      const int per = C / M, extra = C % M;   // CTA b gets chains b, b + M, ...
-      const int lo = b * per + (b < extra ? b : extra), cnt = per + (b < extra ? 1 : 0);
-      seg_lo[b] = lo;
-      seg_hi[b] = lo + cnt;
-      for (int i = 0; i < cnt; i++) segs[lo + i] = make_int4(b + i * M, 1, 0x7fffffff, 0);
-    }
+  if (bad_s) {
+    for (int b = threadIdx.x; b < M; b += blockDim.x) plan_deal(b, C, M, segs, seg_lo, seg_hi);
     return;
   }
-  if (threadIdx.x != 0) return;
-  const int INF = 0x7fffffff, MINS = 8;
-  long long T = (W_s + M - 1) / M;
-  if (T < mx_s) T = mx_s;
-  int nseg = 0, j = 0;
-  long long rem = T;
-  seg_lo[M - 1] = 0;
-  for (int c = 0; c < C; c++) {
-    const int n = est_s[c];
-    if (rem < MINS && j < M - 1) {   // machine j is full
-      seg_hi[M - 1 - j] = nseg;
-      j++;
-      seg_lo[M - 1 - j] = nseg;
-      rem = T;
-    }
-    const long long first = n - rem;   // iterations that do not fit machine j
-    if (j == M - 1 || first < MINS) {  // whole (a few iterations over the share are cheaper than a hand-over)
-      segs[nseg++] = make_int4(c, 1, INF, 0);
-      rem = first > 0 ? 0 : rem - n;
-    } else {
-      segs[nseg++] = make_int4(c, 1 + (int)first, INF, 0);   // tail: last job of machine j
-      seg_hi[M - 1 - j] = nseg;
-      j++;
-      seg_lo[M - 1 - j] = nseg;
-      segs[nseg++] = make_int4(c, 1, 1 + (int)first, 0);     // head: first job of machine j + 1
-      rem = T - first;
-    }
-  }
-  seg_hi[M - 1 - j] = nseg;
-  for (j++; j < M; j++) seg_lo[M - 1 - j] = seg_hi[M - 1 - j] = nseg;
+  if (threadIdx.x == 0) plan_fill(est_s, C, M, W_s, mx_s, segs, seg_lo, seg_hi);
 }
 
 

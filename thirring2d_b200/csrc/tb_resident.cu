@@ -714,3 +714,29 @@ int tb_run_cg_resident_slice(tb_ctx *ctx, const double2 *b, double2 *x, int c0, 
 int tb_run_cg_resident(tb_ctx *ctx, const double2 *b, double2 *x) {
   return tb_run_cg_resident_slice(ctx, b, x, 0, ctx->C, ctx->stream);
 }
+
+// The schedule plan_kernel would write for these iteration estimates, computed on the host by the same code (no GPU
+// involved): segs4[4 * s] = (chain, first iteration, end iteration, 0), CTA b owns segments [seg_lo[b], seg_hi[b]).
+// segs4 holds up to C + M - 1 segments.  For tests and for inspecting a plan.
+extern "C" int tb_plan_schedule(const int *est, const int *status, int nchains, int machines, int *segs4, int *seg_lo,
+                                int *seg_hi) {
+  if (!est || !status || !segs4 || !seg_lo || !seg_hi || nchains < 1 || machines < 1) {
+    tb_set_error("tb_plan_schedule: invalid arguments");
+    return TB_EINVAL;
+  }
+  long long W = 0;
+  int mx = 0;
+  bool bad = false;
+  for (int c = 0; c < nchains; c++) {
+    if (est[c] <= 0 || status[c] != TB_CG_CONVERGED) bad = true;
+    W += est[c];
+    mx = est[c] > mx ? est[c] : mx;
+  }
+  int4 *segs = reinterpret_cast<int4 *>(segs4);
+  if (bad) {
+    for (int b = 0; b < machines; b++) plan_deal(b, nchains, machines, segs, seg_lo, seg_hi);
+  } else {
+    plan_fill(est, nchains, machines, W, mx, segs, seg_lo, seg_hi);
+  }
+  return TB_OK;
+}
