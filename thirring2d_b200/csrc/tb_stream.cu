@@ -1421,6 +1421,7 @@ int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out) {
 // multi-kernel path (L1-cached neighbour loads, four blocks per SM) is at 0.85 of the HBM peak: it keeps those.
 static bool use_persistent_slab(const tb_ctx *ctx) {
   return ctx->nranks > 1 && ctx->g.nctiles == 1 && !ctx->msite && tb_conj_is_dagger(ctx) && ctx->cg_variant != 4 &&
+         ctx->g.bx >= ctx->nranks &&   // block 0 exchanges with thread (rank, chain): needs nranks * bc threads
          ctx->nsite <= ((size_t)4 << 20) && getenv("TB_NO_PERSIST") == nullptr;
 }
 
