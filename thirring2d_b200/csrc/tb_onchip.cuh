@@ -248,9 +248,10 @@ __device__ __noinline__ int plan_wait_hand(const int *hand) {
 __host__ __device__ inline void plan_fill(const int *est, int C, int M, long long W, int mx, int4 *segs, int *seg_lo,
                                           int *seg_hi) {
   // A hand-over is not worth fewer than MINS iterations on either side.  A machine may therefore run over its share by
-  // up to MINS iterations (a short tail is stretched to MINS, a chain that overshoots by less stays whole) but is never
-  // left under it, and the share of the machines still to fill is recomputed from the work still to place: nothing
-  // piles up on the last machine (149 equal chains on 148 machines: 285 iterations on the busiest one, not 554).
+  // a few iterations (a chain that overshoots by less than MINS stays whole; a tail of MINS/2 .. MINS iterations is
+  // stretched to MINS) or stay up to MINS/2 - 1 under it, and the share of the machines still to fill is recomputed from
+  // the work still to place: nothing piles up on the last machine (149 equal chains on 148 machines: 285 iterations on
+  // the busiest one, not 554).
   const int INF = 0x7fffffff, MINS = 8;
   long long left = W;   // iterations not placed yet
   int nseg = 0, j = 0;
@@ -262,13 +263,13 @@ __host__ __device__ inline void plan_fill(const int *est, int C, int M, long lon
   seg_lo[M - 1] = 0;
   for (int c = 0; c < C; c++) {
     const int n = est[c];
-    if (rem <= 0 && j < M - 1) {   // machine j is full
+    if (rem < MINS / 2 && j < M - 1) {   // machine j is full (up to 3 iterations short: the later shares absorb them)
       seg_hi[M - 1 - j] = nseg;
       j++;
       seg_lo[M - 1 - j] = nseg;
       rem = share(j);
     }
-    if (j == M - 1 || n <= rem + MINS || n < 2 * MINS) {   // whole
+    if (j == M - 1 || n - rem < MINS || n < 2 * MINS) {   // whole
       segs[nseg++] = make_int4(c, 1, INF, 0);
       rem -= n;
       left -= n;
