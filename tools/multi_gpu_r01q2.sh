@@ -1,3 +1,4 @@
+# 2-GPU visit: slab_bench at three sizes, multi-kernel form (TB_NO_PERSIST=1) and one-launch solve, plus rows-per-thread variants
 for size in 1024 512; do
 for np_ in 1 0; do
   if [ $np_ = 1 ]; then export TB_NO_PERSIST=1; else unset TB_NO_PERSIST; fi
