@@ -123,3 +123,47 @@ def test_no_usable_estimate_deals_the_chains_out_whole():
 def test_rejects_bad_arguments():
     lib = load_library()
     assert lib.tb_plan_schedule(None, None, 4, 2, None, None, None) != 0
+
+
+def simulate(est, machines, resident):
+    """Event simulation of a planned launch: blocks are dispatched in index order onto `resident` slots, a block runs its
+    segments in order, a tail cannot start before its chain's head has finished (it spins, holding its slot).  Returns
+    the makespan in iterations; raises if the launch cannot finish."""
+    est = np.asarray(est, dtype=np.int64)
+    segs, lo, hi = schedule(est, np.zeros(len(est)), machines)
+    head_done = {}                      # chain -> time its head finished
+    need_head = {int(segs[s][0]) for b in range(machines) for s in range(lo[b], hi[b]) if segs[s][1] > 1}
+    free_at = [0] * resident            # when each slot becomes free
+    finish = 0
+    for b in range(machines):           # index order: the hardware's dispatch order
+        slot = int(np.argmin(free_at))
+        t = free_at[slot]
+        for s in range(lo[b], hi[b]):
+            c, k0, k1, _ = (int(v) for v in segs[s])
+            if k0 > 1:
+                if c not in head_done:
+                    raise AssertionError(f"block {b} waits for the head of chain {c}, which no earlier block runs")
+                t = max(t, head_done[c])
+                t += est[c] - (k0 - 1)
+            elif k1 != INF:
+                t += k1 - 1
+                head_done[c] = t
+            else:
+                t += est[c]
+        free_at[slot] = t
+        finish = max(finish, t)
+    assert need_head <= set(head_done)
+    return finish
+
+
+@pytest.mark.parametrize("n,machines", [(256, 148), (149, 148), (211, 148), (8, 7), (40, 33), (600, 148)])
+def test_planned_launch_finishes_whatever_the_residency(n, machines):
+    """A tail only ever waits for a block with a lower index whose FIRST job is the head: the launch finishes with all
+    blocks resident (the real case: one block per SM) and also if only some of them were (dispatch in index order)."""
+    rng = np.random.default_rng(n)
+    est = rng.integers(250, 300, size=n)
+    ideal = est.sum() / machines
+    full = simulate(est, machines, machines)
+    assert full <= max(ideal, est.max()) + 16 + 1, (full, ideal)          # nobody waits when every block is resident
+    for resident in (1, 2, max(1, machines // 3), machines - 1):
+        simulate(est, machines, resident)                                 # slower, but it ends
