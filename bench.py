@@ -430,6 +430,85 @@ def streaming_roofline(tb, torch, dev, stream):
             "us_per_iteration": t * 1e6 / it}
 
 
+def slab_config(tb, torch, dist, dev, stream, rank, world, n, peak, iters=200, m=0.05):
+    """One n x n lattice, `iters` CG iterations of fmdm_invert_cg, on `world` GPUs as t-slabs (world == 1: the
+    streaming solver).  Device time of the solve by CUDA events, max over ranks, best of 3 after one warm-up."""
+    local = dev.index or 0
+    gen = torch.Generator(device=dev).manual_seed(5)   # the same stream on every rank: every rank draws the global field
+    A = ((torch.rand(n * n * 2, dtype=torch.float64, device=dev, generator=gen) - 0.5) * (2 * np.pi)).view(n, n, 2)
+    b = torch.randn(n * n * 2, dtype=torch.float64, device=dev, generator=gen).view(n, n, 2)
+
+    def single():
+        ctx = tb.Context(n, n, 1, tb.MODE_ADJOINT, device=local, m=m, mu=0.0, stream=stream.cuda_stream)
+        ctx.set_cg(1e-30, iters + 1)
+        ctx.set_tuning(0, 0, 1)
+        ctx.set_gauge_dev(A.data_ptr())
+        x = torch.empty_like(b)
+        ms = []
+        for _ in range(4):
+            ctx.cg_dev(b.data_ptr(), x.data_ptr())
+            ms.append(ctx.last_solve_ms)
+        it = int(ctx.cg_result().iters.max())
+        ctx.close()
+        return min(ms[1:]), it, float((x * x).sum())
+
+    if world == 1:
+        ms, it, _ = single()
+        return {"us_per_cg_iteration": ms * 1e3 / it, "dirac_applies_per_sec": 2 * it / (ms * 1e-3),
+                "site_applies_per_sec": 2 * it * n * n / (ms * 1e-3), "iterations": it, "gpus": 1,
+                "hbm_frac_288B_definition": BYTES_PER_SITE_ITER * n * n * it / (ms * 1e-3) / 1e9 / peak,
+                "hbm_frac_real_traffic_240B": 240 * n * n * it / (ms * 1e-3) / 1e9 / peak}
+
+    ntl = n // world
+    A_l = A[rank * ntl:(rank + 1) * ntl].contiguous()
+    b_l = b[rank * ntl:(rank + 1) * ntl].contiguous()
+    x_l = torch.empty_like(b_l)
+    ctx = tb.Context(n, n, 1, tb.MODE_ADJOINT, device=local, m=m, mu=0.0, stream=stream.cuda_stream,
+                     slab_rank=rank, slab_nranks=world)
+    ctx.slab_setup(dist)
+    ctx.set_cg(1e-30, iters + 1)
+    ctx.set_gauge_dev(A_l.data_ptr())
+    ctx.synchronize()
+    dist.barrier()
+
+    def timed(env=None):
+        if env:
+            os.environ[env] = "1"
+        ms = []
+        for _ in range(4):
+            dist.barrier()
+            ctx.cg_dev(b_l.data_ptr(), x_l.data_ptr())
+            ms.append(ctx.last_solve_ms)
+        if env:
+            del os.environ[env]
+        t = torch.tensor([min(ms[1:])], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_multi = timed("TB_NO_PERSIST")   # one kernel per pass, flags between kernels
+    ms = timed()                        # default: the whole solve in one launch per GPU where the slab allows it
+    it = int(ctx.cg_result().iters.max())
+    chk = torch.tensor([float((x_l * x_l).sum())], dtype=torch.float64, device=dev)
+    dist.all_reduce(chk, op=dist.ReduceOp.SUM)
+    ctx.close()
+    one = torch.zeros(3, dtype=torch.float64, device=dev)
+    if rank == 0:   # the same problem on one GPU, in this run
+        ms1, it1, chk1 = single()
+        one = torch.tensor([ms1, it1, chk1], dtype=torch.float64, device=dev)
+    dist.broadcast(one, 0)
+    ms1, it1, chk1 = one.tolist()
+    best = min(ms, ms_multi)
+    return {"us_per_cg_iteration": best * 1e3 / it, "gpus": world, "iterations": it,
+            "us_per_cg_iteration_one_launch_solve": ms * 1e3 / it,
+            "us_per_cg_iteration_multi_kernel": ms_multi * 1e3 / it,
+            "us_per_cg_iteration_1_gpu": ms1 * 1e3 / it1, "speedup_vs_1_gpu": (ms1 / it1) / (best / it),
+            "dirac_applies_per_sec": 2 * it / (best * 1e-3), "site_applies_per_sec": 2 * it * n * n / (best * 1e-3),
+            "x_norm2_rel_diff_vs_1_gpu": abs(chk.item() - chk1) / chk1,
+            "rows_per_gpu": ntl, "hbm_frac_real_traffic_240B_per_gpu": 240 * n * n / world * it / (best * 1e-3) / 1e9 / peak,
+            "note": "strong scaling of ONE lattice: t-slabs, peer-memory halos and all-reduces (no NCCL on the data "
+                    "path); device time, max over ranks"}
+
+
 def cpu_port_apply_rate(nt, nx, m, iters):
     """Dirac applies/s of the CPU path on ONE host core at a lattice size where a full reference solve would take
     minutes to hours (SURVEY 8(c) caveat 4): `iters` CG iterations of the oracle port of fmdm_invert_cg (bit-identical
@@ -626,26 +705,20 @@ def other_configs(tb, torch, dist, dev, stream, rank, world, cpu=True):
         if drop:
             out["unmodified_reference_driver_single_chain"] = drop
 
-    # configs[3] at N = 1: 2048x2048 single lattice, streaming CG, fixed 200 iterations (the slab-decomposed
-    # multi-GPU figures come from tools/slab_bench.py, profiles/scaling_*.txt)
-    if world == 1:
-        nt = nx = 2048
-        peak, _ = measured_peak()
-        ctx = tb.Context(nt, nx, 1, tb.MODE_ADJOINT, device=local, m=0.05, mu=0.0, stream=stream.cuda_stream)
-        ctx.set_cg(1e-30, 201)
-        g = torch.Generator(device=dev).manual_seed(5)
-        A = (torch.rand(nt * nx * 2, dtype=torch.float64, device=dev, generator=g) - 0.5) * (2 * np.pi)
-        ctx.set_gauge_dev(A.data_ptr())
-        ms, info = solve_once(ctx, ctx.vec_doubles, 1)
-        it = int(info.iters.max())
-        ctx.close()
-        out["2048x2048_single_lattice_1_gpu"] = {
-            "us_per_cg_iteration": ms * 1e3 / it, "dirac_applies_per_sec": 2 * it / (ms * 1e-3),
-            "site_applies_per_sec": 2 * it * nt * nx / (ms * 1e-3),
-            "hbm_frac_288B_definition": BYTES_PER_SITE_ITER * nt * nx * it / (ms * 1e-3) / 1e9 / peak,
-            "hbm_frac_real_traffic_240B": 240 * nt * nx * it / (ms * 1e-3) / 1e9 / peak, "iterations": it}
-        if cpu:
-            out["2048x2048_single_lattice_1_gpu"]["cpu_baseline"] = cpu_port_apply_rate(2048, 2048, 0.05, 2)
+    # configs[3]: 2048x2048 (and 4096x4096) single lattice, CG with a fixed 200 iterations (hmc.c:364-395).  N = 1: the
+    # streaming solver.  N > 1: the lattice is cut into N t-slabs, one per rank (tb_create_slab): halo rows are peer
+    # loads over NVLink, the two dot products per iteration one-shot peer-store all-reduces; the same global field and
+    # source on every N, and rank 0 also solves the whole lattice alone so that the speed-up is measured in this run.
+    peak, _ = measured_peak()
+    for n in (2048, 4096):
+        key = f"{n}x{n}_single_lattice" + ("_1_gpu" if world == 1 else "_slab")
+        try:
+            out[key] = slab_config(tb, torch, dist, dev, stream, rank, world, n, peak)
+        except Exception as e:   # a dead peer or a launch error must not cost the headline line
+            out[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
+            break
+    if world == 1 and cpu and "error" not in out["2048x2048_single_lattice_1_gpu"]:
+        out["2048x2048_single_lattice_1_gpu"]["cpu_baseline"] = cpu_port_apply_rate(2048, 2048, 0.05, 2)
     return out
 
 

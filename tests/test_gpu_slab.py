@@ -1,4 +1,4 @@
-"""T7: slab decomposition over 2 GPUs against the single-GPU path (needs >= 2 GPUs; `gpurun --gpus 2`).
+"""T7: slab decomposition over 2, 4 and 8 GPUs against the single-GPU path (needs that many GPUs; `gpurun --gpus N`).
 One process per GPU; halos are peer reads over NVLink, dot products one-shot peer all-reduces."""
 import os
 import socket
@@ -57,21 +57,33 @@ def _worker(rank, world, port, nt, nx, nchains, m, mu, q):
     xm, infom = ctx.fmdm_invert_cg(b)
     del os.environ["TB_NO_PERSIST"]
     x5, info5 = ctx.fmdm_invert_cg(b)
+    # the one-launch solve in its block-0 form (TB_SLAB_SYNC=0), with a single slot replica, and with 8-row tiles
+    os.environ["TB_SLAB_SYNC"] = "0"
+    x6, info6 = ctx.fmdm_invert_cg(b)
+    del os.environ["TB_SLAB_SYNC"]
+    os.environ["TB_SLAB_NREP"] = "1"
+    os.environ["TB_SLAB_ROWS"] = "8"
+    x7, info7 = ctx.fmdm_invert_cg(b)
+    del os.environ["TB_SLAB_NREP"], os.environ["TB_SLAB_ROWS"]
+    x8, info8 = ctx.fmdm_invert_cg(b)
     out.update(b=b, x=x, x2=x2, xi=xi, x4=x4, iters=info.iters, status=info.status, iters2=info2.iters,
-               iters4=info4.iters, xm=xm, itersm=infom.iters, x5=x5, iters5=info5.iters)
+               iters4=info4.iters, xm=xm, itersm=infom.iters, x5=x5, iters5=info5.iters, x6=x6, iters6=info6.iters,
+               x7=x7, iters7=info7.iters, x8=x8, iters8=info8.iters)
     q.put((rank, out))
     dist.barrier()
     ctx.close()
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("nt,nx,nchains,m,mu", [(32, 32, 1, 0.2, 0.1), (64, 48, 3, 0.1, 0.0), (16, 16, 40, 0.5, 0.2), (256, 512, 1, 0.1, 0.0)])
-def test_T7_slab_matches_single_gpu(nt, nx, nchains, m, mu):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+def test_T7_slab_matches_single_gpu(nt, nx, nchains, m, mu, world):
+    """Rank-order sums, the wrap link between rank P-1 and rank 0, and both forms of the one-launch solve at every
+    rank count the box offers (hmc.c:364-395 is the loop all of them restate)."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
 
-    world = 2
     mpctx = mp.get_context("spawn")
     q = mpctx.Queue()
     port = _free_port()
@@ -109,3 +121,9 @@ def test_T7_slab_matches_single_gpu(nt, nx, nchains, m, mu):
     assert np.linalg.norm(cat("xm") - x) <= 1e-12 * np.linalg.norm(x)
     assert np.all(np.abs(res[0]["itersm"].astype(int) - info.iters.astype(int)) <= 1)
     assert np.array_equal(cat("x5"), xs) and np.array_equal(res[0]["iters5"], res[0]["iters"])
+    for k in ("6", "7"):   # other summation orders of the block partials: same solve to rounding
+        assert np.linalg.norm(cat("x" + k) - x) <= 1e-12 * np.linalg.norm(x)
+        assert np.all(np.abs(res[0]["iters" + k].astype(int) - info.iters.astype(int)) <= 1)
+        for r in range(world):
+            assert np.array_equal(res[r]["iters" + k], res[0]["iters" + k])
+    assert np.array_equal(cat("x8"), xs) and np.array_equal(res[0]["iters8"], res[0]["iters"])

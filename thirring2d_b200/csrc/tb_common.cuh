@@ -93,7 +93,17 @@ struct TbSlab {
   // one-launch solve: all-reduce slots {partial, tag} written by one 16-byte store, [(kind*P + q)*Cpad + c] in MY memory
   double2 *red2;
   double2 *peer_red2[TB_SLAB_MAX_RANKS];
+  // one-launch solve, every block polls (slab_cg_onelaunch_kernel): the same {partial, tag} slots, replicated NREP times
+  // on separate L2 lines so that the pollers of one GPU spread over the replicas:
+  //   red3[rep * rep_stride + (kind*P + q)*Cpad + c]
+  double2 *red3;
+  double2 *peer_red3[TB_SLAB_MAX_RANKS];
+  int nrep, rep_stride;
+  unsigned long long *timeline;   // optional: globaltimer stamps of the first iterations (TB_SLAB_TIMELINE), else nullptr
 };
+#define TB_SLAB_NREP_MAX 8
+#define TB_SLAB_TL_ITERS 64   /* iterations the timeline records */
+#define TB_SLAB_TL_WORDS 8    /* stamps per iteration: phase A first start, last end, stores issued, last total seen; same for B */
 
 // buffers of the device-resident HMC trajectory (tb_hmc.cu), allocated at first use
 struct TbHmc {

@@ -5,7 +5,8 @@
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SlabOffsets {
-  size_t p, mp, w0, r, p1, red, red_flag, flags, red2, total;
+  size_t p, mp, w0, r, p1, red, red_flag, flags, red2, red3, total;
+  int rep_stride;
 };
 
 static SlabOffsets slab_offsets(const tb_ctx *ctx) {
@@ -20,7 +21,9 @@ static SlabOffsets slab_offsets(const tb_ctx *ctx) {
   o.red_flag = o.red + align_up((size_t)TB_NRED * ctx->nranks * ctx->g.Cpad * sizeof(double), 256);
   o.flags = o.red_flag + align_up((size_t)TB_NRED * ctx->nranks * ctx->g.nctiles * sizeof(int), 256);
   o.red2 = o.flags + 256;
-  o.total = o.red2 + align_up((size_t)TB_NRED * ctx->nranks * ctx->g.Cpad * sizeof(double2), 256);
+  o.red3 = o.red2 + align_up((size_t)TB_NRED * ctx->nranks * ctx->g.Cpad * sizeof(double2), 256);
+  o.rep_stride = (int)align_up((size_t)TB_NRED * ctx->nranks * ctx->g.Cpad, 16);   // double2 elements: whole 256-byte blocks
+  o.total = o.red3 + (size_t)TB_SLAB_NREP_MAX * o.rep_stride * sizeof(double2);
   return o;
 }
 
@@ -119,10 +122,14 @@ extern "C" int tb_slab_connect(tb_ctx *ctx, const void *all_handles) {
   sl.red = (double *)(me + o.red);
   sl.red_flag = (volatile int *)(me + o.red_flag);
   sl.red2 = (double2 *)(me + o.red2);
+  sl.red3 = (double2 *)(me + o.red3);
+  sl.rep_stride = o.rep_stride;
+  sl.nrep = TB_SLAB_NREP_MAX;
   for (int q = 0; q < P; q++) {
     sl.peer_red[q] = (double *)((char *)ctx->peer_block[q] + o.red);
     sl.peer_red_flag[q] = (int *)((char *)ctx->peer_block[q] + o.red_flag);
     sl.peer_red2[q] = (double2 *)((char *)ctx->peer_block[q] + o.red2);
+    sl.peer_red3[q] = (double2 *)((char *)ctx->peer_block[q] + o.red3);
   }
   ctx->slab_connected = true;
   return TB_OK;
@@ -133,5 +140,6 @@ void tb_slab_release(tb_ctx *ctx) {
   for (int q = 0; q < ctx->nranks; q++)
     if (q != ctx->rank && ctx->peer_block[q]) cudaIpcCloseMemHandle(ctx->peer_block[q]);
   if (ctx->slab.seq) cudaFree(ctx->slab.seq);
+  if (ctx->slab.timeline) cudaFree(ctx->slab.timeline);
   if (ctx->slab_block) cudaFree(ctx->slab_block);
 }

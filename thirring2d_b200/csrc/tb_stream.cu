@@ -971,6 +971,349 @@ slab_cg_persistent_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s,
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// One-launch slab solve, second form: EVERY block takes part in the all-reduce (default; TB_SLAB_SYNC=0 selects the
+// block-0 form above).  A synchronisation point of the form above is a chain of six hand-overs: block partials ->
+// counter -> block 0 (which first has to notice the last arrival) -> peer stores -> block 0's scalar update in global
+// memory -> go flag -> every block reloads the scalars; ~14 us at 2048^2.  Here:
+//   * the block whose ticket is the LAST one of the grid gathers the block partials at once (nobody polls the counter)
+//     and stores {partial, partial xor tag} into every rank's slot table, NREP replicas on separate L2 lines;
+//   * every block polls the P slots of ITS replica in its own GPU's memory (one warp, one 128-byte line at C = 1), adds
+//     them in rank order and evaluates alpha / beta / convergence itself, in registers: the CG scalars are bitwise
+//     identical in every block of every rank, so there is neither a go flag nor a scalar reload, and the decisions
+//     (stop, iterate) are taken everywhere in the same iteration.
+// The all-reduce still doubles as the cross-GPU fence for the halo rows (a rank's partial is stored only after all its
+// blocks have arrived behind a device-scope fence, and behind a system-scope fence of the storing threads).  A slot
+// of kind K and generation g is overwritten at generation g + 1 of kind K only after the owner passed the reduction of
+// the other kind in between, which needs every block of every rank to have arrived there, i.e. to have read slot g.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+
+struct ChainScalars {   // CG scalars of the thread's chain (c = threadIdx.x & (bc - 1)), identical in every block
+  double rr_old, rr_init, rr, alpha, beta;
+  int active, iters, status;
+};
+
+template <int FIN>
+__device__ __forceinline__ void update_scalars(double total, ChainScalars &cs, const TbCgState &s) {
+  if (FIN == FIN_INIT) {
+    cs.rr = cs.rr_old = cs.rr_init = total;
+    if (total < s.accuracy) {   // hmc.c:359-361, x is already zero
+      cs.status = TB_CG_ZERO_SOURCE;
+      cs.active = 0;
+    }
+  } else if (FIN == FIN_PQ) {
+    if (cs.active) cs.alpha = cs.rr_old / total;   // hmc.c:371
+  } else if (FIN == FIN_RR) {
+    if (cs.active) {
+      const int it = ++cs.iters;
+      cs.rr = total;
+      int st = -1;
+      if (total < s.accuracy) st = TB_CG_CONVERGED;                                                   // hmc.c:381
+      else if (!(total == total) || total / cs.rr_init > TB_DIVERGENCE_RATIO) st = TB_CG_DIVERGED;   // hmc.c:383
+      else if (it >= s.max_iter - 1) st = TB_CG_MAXITER;                                              // hmc.c:364
+      if (st >= 0) {
+        cs.status = st;
+        cs.active = 0;
+      } else {
+        cs.beta = total / cs.rr_old;   // hmc.c:390
+        cs.rr_old = total;             // hmc.c:394
+      }
+    }
+  }
+}
+
+// Per-chain sum of `acc` over all blocks of all ranks; returns the total of the thread's chain (valid in every thread).
+// tl: optional time stamps of this synchronisation point (4 words: see TB_SLAB_TL_WORDS), nullptr when not recording.
+template <int RED>
+__device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, const TbCgState &s, const TbSlab &sl,
+                                                 double *red, unsigned long long &target, int gen,
+                                                 unsigned long long *tl) {
+  __shared__ int s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = (blockDim.x + 31) >> 5;
+  const int c_local = tid & (g.bc - 1), x_local = tid >> g.bc_shift;
+  for (int o = 16; o >= g.bc; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __syncthreads();   // red may still be read by the previous call
+  if (lane < g.bc) red[warp * g.bc + lane] = acc;
+  __threadfence();   // this thread's field stores are visible device-wide before the block's arrival is counted
+  __syncthreads();
+  if (tl && tid == 0) atomicMax(&tl[1], global_ns());
+  if (warp == 0) {
+    if (lane < g.bc) {
+      double t = 0.0;
+      for (int w = 0; w < nwarp; w++) t += red[w * g.bc + lane];
+      __stcg(&s.partial[(size_t)blockIdx.x * g.Cpad + lane], t);
+      __threadfence();
+    }
+    __syncwarp();
+    if (lane == 0) {
+      target += gridDim.x;
+      s_last = atomicAdd(sl.gbar, 1ULL) == target - 1;
+    }
+  }
+  __syncthreads();
+  if (s_last) {   // block-uniform: this block arrived last, every other block's partial and field rows are visible
+    __threadfence();
+    double sum = 0.0;
+    for (int blk = x_local; blk < (int)gridDim.x; blk += g.bx) sum += __ldcg(&s.partial[(size_t)blk * g.Cpad + c_local]);
+    const double mine = block_sum_chains(sum, g, red);   // threads < bc
+    __syncthreads();
+    if (tid < g.bc) red[tid] = mine;
+    __syncthreads();
+    const long long tag = (long long)((unsigned long long)gen * 0x9E3779B97F4A7C15ULL);
+    const int nst = sl.P * sl.nrep * g.bc;
+    if (tid < nst) __threadfence_system();   // this GPU's halo rows before the tag, for the peers
+    for (int i = tid; i < nst; i += blockDim.x) {
+      const int c = i & (g.bc - 1), k = i >> g.bc_shift, rep = k % sl.nrep, q = k / sl.nrep;
+      const double v = red[c];
+      st_volatile_v2(sl.peer_red3[q] + (size_t)rep * sl.rep_stride + (size_t)(RED * sl.P + sl.rank) * g.Cpad + c,
+                     __double_as_longlong(v), __double_as_longlong(v) ^ tag);
+    }
+    if (tl && tid == 0) tl[2] = global_ns();
+    __syncthreads();   // red is rewritten below
+  }
+  const bool io = tid < sl.P * g.bc;   // thread (q, chain) polls the slot rank q writes into this GPU's memory
+  double theirs = 0.0;
+  if (io) {
+    const long long tag = (long long)((unsigned long long)gen * 0x9E3779B97F4A7C15ULL);
+    const int q = tid >> g.bc_shift;
+    const double2 *in = sl.red3 + (size_t)(blockIdx.x % sl.nrep) * sl.rep_stride + (size_t)(RED * sl.P + q) * g.Cpad + c_local;
+    const long long t0 = clock64();
+    for (;;) {
+      long long wx, wy;
+      ld_volatile_v2(in, wx, wy);
+      if ((wx ^ wy) == tag) { theirs = __longlong_as_double(wx); break; }
+      __nanosleep(20);
+      if (clock64() - t0 > TB_PERSIST_SPIN_CYCLES) __trap();   // a launch error on this rank instead of a hung box
+    }
+    __threadfence_system();   // acquire side: the neighbours' rows behind their tags
+    red[tid] = theirs;        // [q][chain]
+  }
+  __syncthreads();
+  double total = 0.0;
+  for (int r = 0; r < sl.P; r++) total += red[r * g.bc + c_local];   // rank order: the same bits on every rank
+  if (tl && tid == 0) atomicMax(&tl[3], global_ns());
+  return total;
+}
+
+template <int TT>
+__global__ void __launch_bounds__(TB_MAX_BLOCK, 3)
+slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, const TbSlab sl) {
+  __shared__ double red[TB_MAX_BLOCK];
+  const int ntiles = g.nxtiles * g.nttiles;
+  const size_t R = (size_t)g.R;
+  unsigned long long bar_target = 0;
+  const int E0 = *(volatile int *)sl.seq;   // rewritten only after the last grid barrier
+  const int c = threadIdx.x & (g.bc - 1);
+  const bool chain = c < g.C;
+  const double m = chain ? a.mass[c] : 0.0;
+  const double e_p = chain ? a.emu[c] : 1.0, e_m = chain ? a.emmu[c] : 1.0;
+  ChainScalars cs = {0.0, 0.0, 0.0, 0.0, 0.0, chain ? 1 : 0, 0, TB_CG_MAXITER};
+  auto stamps = [&](int k, int half) -> unsigned long long * {
+    return (sl.timeline && k < TB_SLAB_TL_ITERS) ? sl.timeline + ((size_t)k * 2 + half) * 4 : nullptr;
+  };
+
+  // the neighbours may still read the previous generation of p (an apply queued before this solve)
+  auto wait_ends = [&](const BlockPos &b, int kind, int need) {
+    if (b.ttile == 0 || b.ttile == g.nttiles - 1) {
+      if (threadIdx.x == 0) {
+        if (b.ttile == 0) spin_until(sl.flags + kind * 2 + 0, need);
+        if (b.ttile == g.nttiles - 1) spin_until(sl.flags + kind * 2 + 1, need);
+        __threadfence_system();
+      }
+      __syncthreads();
+    }
+  };
+
+  // ---- x = 0, r = p = b, ||b||^2 (hmc.c:349-361): generation E0 + 1 of p
+  double acc = 0.0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const BlockPos b = tile_pos(g, tile);
+    wait_ends(b, TB_FLAG_PDONE, E0);
+    if (b.valid) {
+      const size_t j = (size_t)b.x * g.C + b.c;
+      const int t0 = b.ttile * TT;
+#pragma unroll
+      for (int i = 0; i < TT; i++) {
+        const int t = t0 + i;
+        if (t < g.nt) {
+          const size_t k = t * R + j;
+          const double2 v = a.b[k];
+          a.x[k] = make_double2(0.0, 0.0);
+          a.r[k] = v;
+          a.p[k] = v;
+          acc += v.x * v.x + v.y * v.y;
+        }
+      }
+    }
+  }
+  int gen = E0 + 1;   // generation of p
+  update_scalars<FIN_INIT>(slab_allreduce<TB_RED_INIT>(acc, g, s, sl, red, bar_target, gen, nullptr), cs, s);
+
+  // p is double-buffered: odd iterations read p_old from a.p and write p_new into a.p1, even ones the other way round
+  auto n_active = [&] { return __popc(__ballot_sync(0xffffffffu, (int)(threadIdx.x & 31) < g.bc && cs.active)); };
+  for (int k = 1; n_active() > 0; k++) {
+    const bool act = cs.active != 0;
+    const double be = cs.beta;   // 0 in the first iteration: p = r (hmc.c:352-353)
+    const bool odd = k & 1;      // p_old of iteration 1 is a.p (= b, times beta = 0)
+    const double2 *po = odd ? a.p : a.p1, *po_prev = odd ? a.p_prev : a.p1_prev, *po_next = odd ? a.p_next : a.p1_next;
+    double2 *pn = odd ? a.p1 : a.p;
+    // p = r + beta p (hmc.c:391-392) wherever the stencil needs it; the same fma everywhere, so the five copies of a
+    // site's p agree to the bit with the one that is stored
+    auto pnew = [&](const double2 rv, const double2 pv) {
+      return make_double2(fma(be, pv.x, rv.x), fma(be, pv.y, rv.y));
+    };
+    unsigned long long *tlA = stamps(k - 1, 0), *tlB = stamps(k - 1, 1);
+    if (tlA && threadIdx.x == 0) atomicMin(&tlA[0], global_ns());
+    // ---- A: p = r + beta p on the fly, Mp = M p, |Mp|^2.  The neighbours' rows of r and of the old p are complete:
+    // their owners passed the ||r||^2 all-reduce of the previous iteration.
+    acc = 0.0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const BlockPos b = tile_pos(g, tile);
+      if (b.valid && act) {
+        const size_t j = (size_t)b.x * g.C + b.c;
+        const size_t jp = (size_t)((b.x + 1 == g.nx) ? 0 : b.x + 1) * g.C + b.c;
+        const size_t jm = (size_t)((b.x == 0) ? g.nx - 1 : b.x - 1) * g.C + b.c;
+        const int t0 = b.ttile * TT;
+        double2 pm, w0m;
+        if (t0 == 0) {
+          const size_t kk = (size_t)(g.nt - 1) * R + j;
+          pm = pnew(__ldcv(&a.r_prev[kk]), __ldcv(&po_prev[kk]));
+          w0m = __ldcv(&a.W0_prev[kk]);
+        } else {
+          const size_t kk = (size_t)(t0 - 1) * R + j;
+          pm = pnew(__ldcg(&a.r[kk]), __ldcg(&po[kk]));
+          w0m = a.W0[kk];
+        }
+        double2 pc = pnew(__ldcg(&a.r[t0 * R + j]), __ldcg(&po[t0 * R + j]));
+#pragma unroll
+        for (int i = 0; i < TT; i++) {
+          const int t = t0 + i;
+          if (t < g.nt) {
+            const size_t row = t * R;
+            const double2 pp = (t + 1 == g.nt) ? pnew(__ldcv(&a.r_next[j]), __ldcv(&po_next[j]))
+                                               : pnew(__ldcg(&a.r[row + R + j]), __ldcg(&po[row + R + j]));
+            const double2 pxp = pnew(__ldcg(&a.r[row + jp]), __ldcg(&po[row + jp]));
+            const double2 pxm = pnew(__ldcg(&a.r[row + jm]), __ldcg(&po[row + jm]));
+            const double2 w0c = a.W0[row + j];
+            const double2 w1c = a.W1[row + j];
+            const double2 w1m = a.W1[row + jm];
+            const double fr = w0c.x * e_p, fi = w0c.y * e_p;
+            const double br = w0m.x * e_m, bi = w0m.y * e_m;
+            double hr = fr * pp.x - fi * pp.y;
+            double hi = fr * pp.y + fi * pp.x;
+            hr -= br * pm.x + bi * pm.y;
+            hi -= br * pm.y - bi * pm.x;
+            hr += w1c.x * pxp.x - w1c.y * pxp.y;
+            hi += w1c.x * pxp.y + w1c.y * pxp.x;
+            hr -= w1m.x * pxm.x + w1m.y * pxm.y;
+            hi -= w1m.x * pxm.y - w1m.y * pxm.x;
+            double2 o;
+            o.x = m * pc.x + hr;
+            o.y = m * pc.y + hi;
+            pn[row + j] = pc;
+            a.Mp[row + j] = o;
+            acc += o.x * o.x + o.y * o.y;   // <p, M^dagger M p> = |M p|^2
+            pm = pc;
+            pc = pp;
+            w0m = w0c;
+          }
+        }
+      }
+    }
+    update_scalars<FIN_PQ>(slab_allreduce<TB_RED_PQ>(acc, g, s, sl, red, bar_target, gen, tlA), cs, s);
+
+    // ---- B: q = M^dagger Mp on the fly, x += alpha p, r -= alpha q, ||r||^2.  The neighbours' Mp rows are complete:
+    // their owners contributed to the |Mp|^2 sum.
+    if (tlB && threadIdx.x == 0) atomicMin(&tlB[0], global_ns());
+    acc = 0.0;
+    const double al = cs.alpha;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const BlockPos b = tile_pos(g, tile);
+      if (b.valid && act) {
+        const size_t j = (size_t)b.x * g.C + b.c;
+        const size_t jp = (size_t)((b.x + 1 == g.nx) ? 0 : b.x + 1) * g.C + b.c;
+        const size_t jm = (size_t)((b.x == 0) ? g.nx - 1 : b.x - 1) * g.C + b.c;
+        const int t0 = b.ttile * TT;
+        double2 pm, w0m;
+        if (t0 == 0) {
+          pm = __ldcv(&a.mp_prev[(size_t)(g.nt - 1) * R + j]);
+          w0m = __ldcv(&a.W0_prev[(size_t)(g.nt - 1) * R + j]);
+        } else {
+          pm = __ldcg(&a.Mp[(size_t)(t0 - 1) * R + j]);
+          w0m = a.W0[(size_t)(t0 - 1) * R + j];
+        }
+        double2 pc = __ldcg(&a.Mp[t0 * R + j]);
+#pragma unroll
+        for (int i = 0; i < TT; i++) {
+          const int t = t0 + i;
+          if (t < g.nt) {
+            const size_t row = t * R;
+            const double2 pp = (t + 1 == g.nt) ? __ldcv(&a.mp_next[j]) : __ldcg(&a.Mp[row + R + j]);
+            const double2 pxp = __ldcg(&a.Mp[row + jp]);
+            const double2 pxm = __ldcg(&a.Mp[row + jm]);
+            const double2 w0c = a.W0[row + j];
+            const double2 w1c = a.W1[row + j];
+            const double2 w1m = a.W1[row + jm];
+            const double2 pv = __ldcg(&pn[row + j]);
+            double2 xv = __ldcg(&a.x[row + j]), rv = __ldcg(&a.r[row + j]);
+            const double fr = w0c.x * e_m, fi = w0c.y * e_m;   // M^dagger: e^{-mu} on the +t hop
+            const double br = w0m.x * e_p, bi = w0m.y * e_p;
+            double hr = fr * pp.x - fi * pp.y;
+            double hi = fr * pp.y + fi * pp.x;
+            hr -= br * pm.x + bi * pm.y;
+            hi -= br * pm.y - bi * pm.x;
+            hr += w1c.x * pxp.x - w1c.y * pxp.y;
+            hi += w1c.x * pxp.y + w1c.y * pxp.x;
+            hr -= w1m.x * pxm.x + w1m.y * pxm.y;
+            hi -= w1m.x * pxm.y - w1m.y * pxm.x;
+            const double qx = m * pc.x - hr, qy = m * pc.y - hi;
+            xv.x += al * pv.x;
+            xv.y += al * pv.y;
+            rv.x -= al * qx;
+            rv.y -= al * qy;
+            a.x[row + j] = xv;
+            a.r[row + j] = rv;
+            acc += rv.x * rv.x + rv.y * rv.y;
+            pm = pc;
+            pc = pp;
+            w0m = w0c;
+          }
+        }
+      }
+    }
+    update_scalars<FIN_RR>(slab_allreduce<TB_RED_RR>(acc, g, s, sl, red, bar_target, gen, tlB), cs, s);
+    gen++;
+  }
+  // every block of every rank leaves in the same iteration (identical scalars).  Block 0 writes the outcome; then leave
+  // the epoch and the flags as the multi-kernel protocol expects them: nobody reads p or Mp of this solve any more.
+  if (blockIdx.x == 0 && (int)threadIdx.x < g.bc && chain) {
+    s.status[c] = cs.status;
+    s.iters[c] = cs.iters;
+    s.rr[c] = cs.rr;
+    s.rr_init[c] = cs.rr_init;
+    s.rr_old[c] = cs.rr_old;
+    s.alpha[c] = cs.alpha;
+    s.beta[c] = cs.beta;
+    s.active[c] = 0;
+  }
+  grid_barrier(sl.gbar, bar_target);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    *s.n_active = 0;
+    s.tile_active[0] = 0;
+    *sl.seq = gen;
+    __threadfence_system();
+    for (int kind = 0; kind < TB_NFLAGS; kind++) {
+      *(volatile int *)(sl.sig_prev + kind * 2) = gen;
+      *(volatile int *)(sl.sig_next + kind * 2) = gen;
+    }
+    __threadfence_system();
+  }
+}
+
 // plain per-chain Re<a,b>
 template <int TT>
 __global__ void __launch_bounds__(TB_MAX_BLOCK)
@@ -1425,17 +1768,17 @@ static bool use_persistent_slab(const tb_ctx *ctx) {
          ctx->nsite <= ((size_t)4 << 20) && getenv("TB_NO_PERSIST") == nullptr;
 }
 
-template <int TT>
+template <int TT, bool ALLPOLL>
 static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int *nblocks_out) {
   TbGeom g = ctx->g;   // same tiles, TT rows each (8: 80 registers, three blocks per SM)
   g.tt = TT;
   g.nttiles = (ctx->nt + TT - 1) / TT;
   g.nslots = g.nxtiles * g.nttiles;
-  const TbSlab &sl = ctx->slab;
+  TbSlab &sl = ctx->slab;
   SlabCgArgs a = {b, ctx->xw, ctx->r, ctx->p, ctx->p1, ctx->Mp, sl.p_prev, sl.p_next, sl.p1_prev, sl.p1_next,
                   sl.r_prev, sl.r_next, sl.mp_prev, sl.mp_next,
                   ctx->W0, sl.W0_prev, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu};
-  auto kern = slab_cg_persistent_kernel<TT>;
+  auto kern = ALLPOLL ? slab_cg_onelaunch_kernel<TT> : slab_cg_persistent_kernel<TT>;
   int per_sm = 0, nsm = TB_NUM_SMS_B200, coop = 0;
   TB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
   TB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -1443,15 +1786,69 @@ static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int *nblocks_ou
   if (!coop || per_sm < 1) { *nblocks_out = 0; return TB_OK; }
   int nblocks = g.nxtiles * g.nttiles;
   if (nblocks > per_sm * nsm) nblocks = per_sm * nsm;
+  if ((size_t)nblocks * g.Cpad > (size_t)ctx->g.nxtiles * ctx->nt * ctx->g.Cpad) { *nblocks_out = 0; return TB_OK; }   // partial[]
   TB_CUDA(cudaMemsetAsync(sl.gbar, 0, sizeof(unsigned long long), ctx->stream));
+  sl.nrep = TB_SLAB_NREP_MAX;   // the same on every rank: a rank polls the replicas its peers write
+  if (const char *e = getenv("TB_SLAB_NREP")) {
+    const int n = atoi(e);
+    sl.nrep = n < 1 ? 1 : (n > TB_SLAB_NREP_MAX ? TB_SLAB_NREP_MAX : n);
+  }
+  // optional timeline of the first TB_SLAB_TL_ITERS iterations (TB_SLAB_TIMELINE=<file prefix>): per synchronisation
+  // point {first block starts the phase, last block finishes it, partial stored to the peers, last block holds the total}
+  const char *tlpath = ALLPOLL ? getenv("TB_SLAB_TIMELINE") : nullptr;
+  const size_t tlwords = (size_t)TB_SLAB_TL_ITERS * TB_SLAB_TL_WORDS;
+  unsigned long long *tl_host = nullptr;
+  if (tlpath) {
+    if (!sl.timeline) TB_CUDA(cudaMalloc((void **)&sl.timeline, tlwords * sizeof(unsigned long long)));
+    tl_host = (unsigned long long *)malloc(tlwords * sizeof(unsigned long long));
+    for (size_t i = 0; i < tlwords; i++) tl_host[i] = (i % 4 == 0) ? ~0ULL : 0ULL;
+    TB_CUDA(cudaMemcpyAsync(sl.timeline, tl_host, tlwords * sizeof(unsigned long long), cudaMemcpyHostToDevice, ctx->stream));
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
   TbGeom gg = g;
   TbCgState ss = ctx->cg;
   TbSlab sls = sl;
+  if (!tlpath) sls.timeline = nullptr;
   void *args[] = {&a, &gg, &ss, &sls};
   TB_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(nblocks), dim3(g.bc * g.bx), args, 0, ctx->stream));
   ctx->launches++;
   *nblocks_out = nblocks;
+  if (tlpath) {
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    TB_CUDA(cudaMemcpy(tl_host, sl.timeline, tlwords * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    char name[512];
+    snprintf(name, sizeof(name), "%s.rank%d.txt", tlpath, ctx->rank);
+    if (FILE *f = fopen(name, "w")) {
+      fprintf(f, "# globaltimer ns since the first stamp of this rank; per CG iteration and phase (A: Mp = M p, B: M^dagger + "
+                 "update): start = first block enters, end = last block has its partial, stored = partial sent to the peers, "
+                 "total = last block holds the all-reduced sum\n# iter A_start A_end A_stored A_total B_start B_end B_stored B_total\n");
+      unsigned long long t0 = tl_host[0];
+      for (int k = 0; k < TB_SLAB_TL_ITERS; k++) {
+        if (tl_host[(size_t)k * 8] == ~0ULL) break;
+        fprintf(f, "%d", k + 1);
+        for (int w = 0; w < 8; w++) fprintf(f, " %lld", (long long)(tl_host[(size_t)k * 8 + w] - t0));
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+    free(tl_host);
+  }
   return TB_OK;
+}
+
+// rows per tile of the one-launch solve: the largest of 8, 4, 2 that still gives every SM about two tiles (small
+// slabs are latency-bound: more, shorter marches; 2048^2 on 8 GPUs is 256 tiles of 8 rows for 148 SMs)
+static int launch_persistent_slab_auto(tb_ctx *ctx, const double2 *b, int *nblocks_out) {
+  const bool allpoll = !(getenv("TB_SLAB_SYNC") && atoi(getenv("TB_SLAB_SYNC")) == 0);
+  int tt = 8;
+  if (allpoll) {
+    while (tt > 2 && (long)ctx->g.nxtiles * ((ctx->nt + tt - 1) / tt) < 2L * TB_NUM_SMS_B200) tt >>= 1;
+    if (const char *e = getenv("TB_SLAB_ROWS")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) tt = v; }
+  }
+  if (!allpoll) return launch_persistent_slab<8, false>(ctx, b, nblocks_out);
+  if (tt == 8) return launch_persistent_slab<8, true>(ctx, b, nblocks_out);
+  if (tt == 4) return launch_persistent_slab<4, true>(ctx, b, nblocks_out);
+  return launch_persistent_slab<2, true>(ctx, b, nblocks_out);
 }
 
 // Streaming CG driver: the whole solve stays on the device; the host only polls the number of chains
@@ -1468,7 +1865,7 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
   ctx->launches++;
   if (use_persistent_slab(ctx)) {
     int nblocks = 0;
-    TB_CHECK(launch_persistent_slab<8>(ctx, b, &nblocks));
+    TB_CHECK(launch_persistent_slab_auto(ctx, b, &nblocks));
     if (nblocks > 0) {
       TB_CUDA(cudaMemcpyAsync(x, ctx->xw, ctx->nsite * sizeof(double2), cudaMemcpyDeviceToDevice, st));
       return TB_OK;

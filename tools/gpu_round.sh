@@ -45,7 +45,7 @@ echo "== planned vs plain launches, staged vs marching kernels"
 python tools/probe_plan.py 2>&1 | tee $OUT/probe_plan_$TAG.txt | cut -c1-250
 python tools/probe_pipe.py 2048,2048,1,0.01 1024,1024,4,0.01 512,512,16,0.01 256,256,64,0.01 2>&1 | tee $OUT/probe_pipe_$TAG.txt | cut -c1-250
 if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
-  echo "== 2+ GPUs: slab parity tests and the one-launch slab solve (tools/multi_gpu_r01q3.sh)"
-  bash tools/multi_gpu_r01q3.sh 2>&1 | tee $OUT/slab_$TAG.txt | cut -c1-250
+  echo "== 2+ GPUs: slab parity tests and the one-launch slab solve (tools/multi_gpu.sh)"
+  bash tools/multi_gpu.sh $TAG quick 2>&1 | tee $OUT/slab_$TAG.txt | cut -c1-250
 fi
 ls -la $OUT | tail -15
