@@ -104,7 +104,8 @@ int tb_set_gauge(tb_ctx *ctx, const double *A_host);
  * of an occupied site is dropped, vec_ops.c:110-128) and occupied sites become identity rows (vec_ops.c:130).
  * With it, TB_OP_M is fM (vec_ops.c:96), TB_OP_MDAG is fM_transpose (vec_ops.c:135), tb_cg is cg_MdM
  * (vec_ops.c:261) and tb_invert is cg_propagator (vec_ops.c:311) on vectors whose imaginary parts are zero.
- * Call tb_set_params first: the masses are baked into the per-site mass field. */
+ * The masses of tb_set_params are baked into the per-site mass field; a later tb_set_params re-bakes it from the
+ * stored occupation field.  tb_set_gauge* switches the context back to family A. */
 int tb_set_occupancy(tb_ctx *ctx, const int *field_host);
 
 /* out = Op in, Op one of TB_OP_* (fm_mul hmc.c:123, fm_conjugate_mul hmc.c:188, fmdm_mul hmc.c:259). */
@@ -210,9 +211,16 @@ int tb_hmc_condensate(tb_ctx *ctx, int nsrc, unsigned long long seed, unsigned i
 int tb_get_gauge(tb_ctx *ctx, double *A_host);
 
 /* Gauge-field checkpoint (hmc.c has none; mirrors the raw dump of fermionbag.c:125-161): 64-byte header
- * ("THIRRING2D-A-V1", NT, NX, nchains, mode) + raw FP64 A[chain][t][x][dir]. */
+ * ("THIRRING2D-A-V1", NT, NX, nchains, mode, index of the next trajectory) + raw FP64 A[chain][t][x][dir]. */
 int tb_checkpoint_write(tb_ctx *ctx, const char *path);
 int tb_checkpoint_read(tb_ctx *ctx, const char *path);
+
+/* The trajectory counter that travels in the checkpoint header.  The device random stream is keyed by (seed, chain,
+ * trajectory index): a resumed run that restarted the index at 1 would replay the momenta, the pseudofermion noise,
+ * the Metropolis uniforms and the measurement sources of its first leg.  Set it before tb_checkpoint_write (the index
+ * the NEXT trajectory will use); tb_checkpoint_read restores it (0: the file does not record it). */
+int tb_checkpoint_set_next_trajectory(tb_ctx *ctx, unsigned int next_traj);
+int tb_checkpoint_next_trajectory(const tb_ctx *ctx, unsigned int *next_traj);
 
 /* Counters for bench.py: kernels launched by this context since creation / since the last reset. */
 long long tb_launch_count(const tb_ctx *ctx);

@@ -77,3 +77,59 @@ def test_vec_ops_replacement_object_under_reference_code():
                        cwd=ROOT, timeout=600)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "vecops child ok" in p.stdout
+
+
+def test_one_context_switches_between_family_a_and_b(oracle):
+    """tb_set_occupancy replaces the gauge field and tb_set_gauge switches back: a 48x48 context (streaming solver
+    with its cached CUDA graph, no TMA-staged shape) solves A -> B -> A -> B and every result equals a fresh context's.
+    The graph holds the per-site mass pointer by value, so the switch must rebuild it."""
+    nt = nx = 48
+    n, m, mu = 2, 0.25, 0.1
+    rng = np.random.default_rng(48)
+    A = rng.uniform(-np.pi, np.pi, size=(n, nt, nx, 2))
+    field = (rng.random((n, nt, nx)) < 0.15).astype(np.int32)
+    v = rng.normal(size=(n, nt, nx)) + 1j * rng.normal(size=(n, nt, nx))
+    vr = v.real.astype(np.complex128)
+
+    def fresh(kind):
+        with tb.Context(nt, nx, n, tb.MODE_ADJOINT, m=m, mu=mu) as ctx:
+            if kind == "A":
+                ctx.set_gauge(A)
+                return ctx.fmdm_invert_cg(ctx.fm_conjugate_mul(v))
+            ctx.set_occupancy(field)
+            return ctx.fmdm_invert_cg(vr)
+
+    xa, ia = fresh("A")
+    xb, ib = fresh("B")
+    with tb.Context(nt, nx, n, tb.MODE_ADJOINT, m=m, mu=mu) as ctx:
+        assert ctx.solver_info()[0] == 0   # the streaming solver serves this shape
+        for _ in range(2):
+            ctx.set_gauge(A)
+            x, info = ctx.fmdm_invert_cg(ctx.fm_conjugate_mul(v))
+            assert np.array_equal(x, xa) and np.array_equal(info.iters, ia.iters)
+            ctx.set_occupancy(field)
+            x, info = ctx.fmdm_invert_cg(vr)
+            assert np.array_equal(x, xb) and np.array_equal(info.iters, ib.iters)
+    for c in range(n):
+        xo, st, it, rr = oracle.cg_MdM(v[c].real, field[c], m, mu)
+        assert_close(xb[c].real, xo, CG_SOL_TOL, "cg_MdM after the switch")
+
+
+@pytest.mark.parametrize("nt", [24, 64])
+def test_set_params_after_set_occupancy_rebakes_the_site_masses(oracle, nt):
+    """The per-site mass field of family B is built from the masses: changing them afterwards must rebuild it (streaming
+    24^2 and the on-chip 64^2 kernel, which finds its occupied sites through that field)."""
+    nx, n = nt, 3
+    rng = np.random.default_rng(nt)
+    field = (rng.random((n, nt, nx)) < 0.2).astype(np.int32)
+    psi = rng.normal(size=(n, nt, nx))
+    with tb.Context(nt, nx, n, tb.MODE_ADJOINT, m=0.9, mu=0.0) as ctx:
+        ctx.set_occupancy(field)
+        ctx.set_params(0.2, 0.05)
+        chi = ctx.fM(psi)
+        x, info = ctx.cg_MdM(psi)
+    for c in range(n):
+        assert_close(chi[c], oracle.fM(psi[c], field[c], 0.2, 0.05), APPLY_TOL, "fM after set_params")
+        xo, st, it, rr = oracle.cg_MdM(psi[c], field[c], 0.2, 0.05)
+        assert abs(int(info.iters[c]) - it) <= 1
+        assert_close(x[c], xo, CG_SOL_TOL, "cg_MdM after set_params")

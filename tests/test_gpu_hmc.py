@@ -150,10 +150,10 @@ def test_checkpoint_round_trip_and_batched_driver(tmp_path):
         ctx.hmc_set_coupling(0.3)
         ctx.hmc_heatbath(20, seed=3)
         A = ctx.get_gauge()
-        ctx.checkpoint_write(ck)
+        ctx.checkpoint_write(ck, next_trajectory=3)
     assert os.path.getsize(ck) == 64 + A.nbytes
     with tb.Context(nt, nx, 6, tb.MODE_ADJOINT, m=0.5) as ctx:
-        ctx.checkpoint_read(ck)
+        assert ctx.checkpoint_read(ck) == 3   # the trajectory counter travels in the header
         assert np.array_equal(ctx.get_gauge(), A)
     with tb.Context(nt, nx, 5, tb.MODE_ADJOINT, m=0.5) as ctx:
         with pytest.raises(tb.TBError, match="holds 6 chains"):
@@ -173,6 +173,44 @@ def test_checkpoint_round_trip_and_batched_driver(tmp_path):
     # the first printed gauge action is the action of the checkpointed field: (Nf/g) sum (1 - cos A)
     sg0 = float(re.search(r"^\[chain 0\] Start HMC: Sg (\S+),", out, re.M).group(1))
     assert abs(sg0 - (2 / 0.3) * np.sum(1 - np.cos(A[0]))) <= 6e-6 * sg0
+
+
+def test_resumed_run_continues_the_random_stream(tmp_path):
+    """A run of 4 trajectories and a run of 2 + a resumed run of 2 print the same trajectories 3 and 4: the checkpoint
+    carries the trajectory index that keys the device random stream, so the second leg does not replay the momenta,
+    noise and Metropolis uniforms of the first.  A file without the index is refused unless --traj-offset is given."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    base = [sys.executable, "-m", "thirring2d_b200.hmc_driver", "--nt", "16", "--nx", "16", "--chains", "3",
+            "--mode", "adjoint", "--nsteps", "10", "--condensate", "2"]
+
+    def run(extra, n_loops):
+        return subprocess.run(base + extra, input=f"{n_loops}\n1\n0.5\n0.3\n0.0\n77\n", capture_output=True, text=True,
+                              cwd=root, timeout=300)
+
+    ck = str(tmp_path / "leg1.ckpt")
+    full = run([], 4)
+    leg1 = run(["--checkpoint", ck], 2)
+    leg2 = run(["--resume", ck], 2)
+    assert full.returncode == 0 and leg1.returncode == 0 and leg2.returncode == 0, (full.stderr, leg1.stderr, leg2.stderr)
+
+    def chain_lines(out):
+        return [ln for ln in out.splitlines() if ln.startswith("[chain")]
+
+    per_traj = len(chain_lines(full.stdout)) // 4
+    assert chain_lines(leg1.stdout) == chain_lines(full.stdout)[:2 * per_traj]
+    assert chain_lines(leg2.stdout) == chain_lines(full.stdout)[2 * per_traj:]
+    # a checkpoint that does not record the index (written by the bare C call without the counter set)
+    old = str(tmp_path / "old.ckpt")
+    with tb.Context(16, 16, 3, tb.MODE_ADJOINT, m=0.5) as ctx:
+        ctx.checkpoint_read(ck)
+        ctx.checkpoint_write(old, next_trajectory=0)
+    refused = run(["--resume", old], 1)
+    assert refused.returncode != 0 and "--traj-offset" in (refused.stderr + refused.stdout)
+    ok = run(["--resume", old, "--traj-offset", "3"], 2)
+    assert ok.returncode == 0 and chain_lines(ok.stdout) == chain_lines(leg2.stdout)
 
 
 def free_field_condensate(L, m):

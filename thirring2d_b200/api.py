@@ -332,11 +332,19 @@ class Context:
                                          C.byref(its)), "tb_hmc_condensate")
         return cond, its.value
 
-    def checkpoint_write(self, path):
+    def checkpoint_write(self, path, next_trajectory=None):
+        """next_trajectory: index the next trajectory will use (keys the device random stream); stored in the header."""
+        if next_trajectory is not None:
+            check(self.lib.tb_checkpoint_set_next_trajectory(self._h, int(next_trajectory)),
+                  "tb_checkpoint_set_next_trajectory")
         check(self.lib.tb_checkpoint_write(self._h, os.fsencode(path)), "tb_checkpoint_write")
 
     def checkpoint_read(self, path):
+        """Returns the index of the next trajectory recorded in the file (0: not recorded)."""
         check(self.lib.tb_checkpoint_read(self._h, os.fsencode(path)), "tb_checkpoint_read")
+        n = C.c_uint(0)
+        check(self.lib.tb_checkpoint_next_trajectory(self._h, C.byref(n)), "tb_checkpoint_next_trajectory")
+        return n.value
 
     @property
     def launch_count(self):

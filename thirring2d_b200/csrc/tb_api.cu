@@ -293,6 +293,8 @@ extern "C" int tb_set_params(tb_ctx *ctx, const double *m, const double *mu, int
   if (e == cudaSuccess) e = cudaMemcpy(ctx->d_emmu, buf + 2 * cp, cp * sizeof(double), cudaMemcpyHostToDevice);
   free(buf);
   TB_CUDA(e);
+  // family B: the site masses (m on free sites, 1 on occupied ones) were built from the old masses
+  if (ctx->msite) TB_CHECK(tb_launch_occupancy(ctx, ctx->occ_stage));
   return TB_OK;
 }
 
@@ -572,6 +574,7 @@ extern "C" int tb_set_occupancy(tb_ctx *ctx, const int *field_host) {
   TB_CHECK(tb_launch_occupancy(ctx, ctx->occ_stage));
   ctx->msite = ctx->msite_buf;
   ctx->have_gauge = true;
+  invalidate_graph(ctx);
   return TB_OK;
 }
 

@@ -170,6 +170,7 @@ struct tb_ctx {
   int slab_graph_chunk;
   TbHmc hmc;
   unsigned int hmc_chain_offset;  // global index of chain 0 (RNG key), tb_hmc_set_chain_offset
+  unsigned int ckpt_next_traj;    // index of the next trajectory, stored in / restored from the checkpoint header
 };
 
 int tb_choose_geom(tb_ctx *ctx);

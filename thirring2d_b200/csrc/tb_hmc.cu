@@ -18,7 +18,10 @@ namespace {
 
 #define TB_NF 2.0  /* "#define Nf 2", hmc.c:28 */
 
-// ---- Philox4x32-10: counter (site index, draw slot, trajectory, stream), key (seed lo, seed hi ^ chain) ----
+// ---- Philox4x32-10: counter (site index, global chain index, trajectory | sweep, stream), key (seed lo, seed hi) ----
+// Every consumer has its own range of the stream word (TB_RNG_*): trajectory fields 1..4, heat bath, measure() sources
+// and condensate sources cannot collide whatever nsrc is; the chain sits in the counter, not in the key, so two
+// (seed, chain) pairs never share a stream.
 __device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key) {
 #pragma unroll
   for (int r = 0; r < 10; r++) {
@@ -35,6 +38,12 @@ __device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key) {
 // offset keeps log() finite (the reference has a 2^-32 chance of log(0))
 __device__ __forceinline__ double u01(unsigned int r) { return ((double)r + 0.5) * 2.3283064365386963e-10; }
 
+// stream word: consumer in the top byte, source index below (nsrc < 2^24)
+#define TB_RNG_MEASURE 0x01000000u
+#define TB_RNG_CONDENSATE 0x02000000u
+#define TB_RNG_HEATBATH 0x03000000u
+#define TB_RNG_MAX_SOURCES 0x01000000
+
 struct RngKey {
   unsigned long long seed;
   unsigned int traj, stream;
@@ -43,8 +52,8 @@ struct RngKey {
 
 // (sqrt(-2 ln x1) cos(2 pi x2), sqrt(-2 ln x1) sin(2 pi x2)), hmc.c:425-426 / 490-491
 __device__ __forceinline__ double2 box_muller(size_t site, int c, const RngKey k) {
-  const uint4 r = philox(make_uint4((unsigned int)site, (unsigned int)(site >> 32), k.traj, k.stream),
-                         make_uint2((unsigned int)k.seed, (unsigned int)(k.seed >> 32) ^ ((unsigned int)c + k.chain0)));
+  const uint4 r = philox(make_uint4((unsigned int)site, (unsigned int)c + k.chain0, k.traj, k.stream),
+                         make_uint2((unsigned int)k.seed, (unsigned int)(k.seed >> 32)));
   const double x1 = u01(r.x), x2 = u01(r.y);
   const double rad = sqrt(-2.0 * log(x1));
   double s, co;
@@ -60,8 +69,8 @@ __global__ void fill_gauss_kernel(double2 *__restrict__ v, size_t nsite_total, i
 __global__ void fill_uniform_kernel(double *__restrict__ u, int C, RngKey k) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) {
-    const uint4 r = philox(make_uint4(0u, 0u, k.traj, k.stream),
-                           make_uint2((unsigned int)k.seed, (unsigned int)(k.seed >> 32) ^ ((unsigned int)c + k.chain0)));
+    const uint4 r = philox(make_uint4(0u, (unsigned int)c + k.chain0, k.traj, k.stream),
+                           make_uint2((unsigned int)k.seed, (unsigned int)(k.seed >> 32)));
     u[c] = u01(r.x);
   }
 }
@@ -223,8 +232,8 @@ __global__ void heatbath_kernel(double2 *__restrict__ A, const double *__restric
     const double nfg = nf_over_g[c];
     double2 a = A[i];
     for (int s = 0; s < sweeps; s++) {
-      const uint4 r = philox(make_uint4((unsigned int)site, (unsigned int)(site >> 32), (unsigned int)s, k.stream),
-                             make_uint2((unsigned int)k.seed, (unsigned int)(k.seed >> 32) ^ ((unsigned int)c + k.chain0)));
+      const uint4 r = philox(make_uint4((unsigned int)site, (unsigned int)c + k.chain0, (unsigned int)s, k.stream),
+                             make_uint2((unsigned int)k.seed, (unsigned int)(k.seed >> 32)));
       const double n0 = 2.0 * M_PI * u01(r.x) - M_PI, n1 = 2.0 * M_PI * u01(r.z) - M_PI;
       if (u01(r.y) < exp(nfg * (cos(n0) - cos(a.x)))) a.x = n0;
       if (u01(r.w) < exp(nfg * (cos(n1) - cos(a.y)))) a.y = n1;
@@ -376,7 +385,7 @@ extern "C" int tb_hmc_heatbath(tb_ctx *ctx, int sweeps, unsigned long long seed)
   TB_CUDA(cudaSetDevice(ctx->device));
   TB_CHECK(hmc_alloc(ctx));
   if (!ctx->have_gauge) TB_CUDA(cudaMemsetAsync(ctx->Adev, 0, ctx->nsite * sizeof(double2), ctx->stream));  // hmc.c:915
-  const RngKey k = {seed, 0u, 7u, ctx->hmc_chain_offset};
+  const RngKey k = {seed, 0u, TB_RNG_HEATBATH, ctx->hmc_chain_offset};
   heatbath_kernel<<<ew_blocks(ctx->nsite), 256, 0, ctx->stream>>>(ctx->Adev, ctx->hmc.nf_over_g, sweeps, ctx->nsite,
                                                                  ctx->C, k);
   ctx->launches++;
@@ -522,7 +531,7 @@ extern "C" int tb_get_gauge(tb_ctx *ctx, double *A_host) {
 // sources_host (optional, parity tests): complex [nsrc][chain][t][x].
 extern "C" int tb_hmc_measure(tb_ctx *ctx, int nsrc, unsigned long long seed, unsigned int meas_index,
                               const double *sources_host, double *magnetisation_host, double *phase_host) {
-  if (!ctx || nsrc < 0) return TB_EINVAL;
+  if (!ctx || nsrc < 0 || nsrc >= TB_RNG_MAX_SOURCES) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->have_gauge) { tb_set_error("tb_hmc_measure: no gauge field"); return TB_EINVAL; }
   TB_CHECK(hmc_alloc(ctx));
@@ -548,7 +557,7 @@ extern "C" int tb_hmc_measure(tb_ctx *ctx, int nsrc, unsigned long long seed, un
       TB_CUDA(cudaMemcpyAsync(ctx->stage, sources_host + (size_t)i * 2 * n, n * sizeof(double2), cudaMemcpyHostToDevice, st));
       TB_CHECK(tb_launch_pack(ctx, ctx->stage, H.gauss));
     } else {
-      fill_gauss_kernel<<<ew_blocks(n), 256, 0, st>>>(H.gauss, n, C, RngKey{seed, meas_index, 16u + (unsigned int)i, ctx->hmc_chain_offset});
+      fill_gauss_kernel<<<ew_blocks(n), 256, 0, st>>>(H.gauss, n, C, RngKey{seed, meas_index, TB_RNG_MEASURE + (unsigned int)i, ctx->hmc_chain_offset});
       ctx->launches++;
     }
     TB_CHECK(tb_launch_dslash(ctx, tb_conj_is_dagger(ctx), H.gauss, ctx->tmp, false));
@@ -574,7 +583,7 @@ extern "C" int tb_hmc_measure(tb_ctx *ctx, int nsrc, unsigned long long seed, un
 // cg_iters_host (optional): CG iterations summed over chains and sources.
 extern "C" int tb_hmc_condensate(tb_ctx *ctx, int nsrc, unsigned long long seed, unsigned int meas_index,
                                  const double *sources_host, double *condensate_host, long long *cg_iters_host) {
-  if (!ctx || nsrc < 1 || !condensate_host) return TB_EINVAL;
+  if (!ctx || nsrc < 1 || nsrc >= TB_RNG_MAX_SOURCES || !condensate_host) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
   if (!ctx->have_gauge) { tb_set_error("tb_hmc_condensate: no gauge field"); return TB_EINVAL; }
   TB_CHECK(hmc_alloc(ctx));
@@ -593,7 +602,7 @@ extern "C" int tb_hmc_condensate(tb_ctx *ctx, int nsrc, unsigned long long seed,
         TB_CUDA(cudaMemcpyAsync(ctx->stage, sources_host + (size_t)i * 2 * n, n * sizeof(double2), cudaMemcpyHostToDevice, st));
         TB_CHECK(tb_launch_pack(ctx, ctx->stage, H.gauss));
       } else {
-        fill_gauss_kernel<<<ew_blocks(n), 256, 0, st>>>(H.gauss, n, C, RngKey{seed, meas_index, 64u + (unsigned int)i, ctx->hmc_chain_offset});
+        fill_gauss_kernel<<<ew_blocks(n), 256, 0, st>>>(H.gauss, n, C, RngKey{seed, meas_index, TB_RNG_CONDENSATE + (unsigned int)i, ctx->hmc_chain_offset});
         ctx->launches++;
       }
       TB_CHECK(tb_launch_dslash(ctx, tb_conj_is_dagger(ctx), H.gauss, ctx->tmp, false));   // hmc.c:410
@@ -623,12 +632,28 @@ extern "C" int tb_hmc_condensate(tb_ctx *ctx, int nsrc, unsigned long long seed,
 
 // ---- on-disk format -----------------------------------------------------------------------
 // hmc.c never writes its configuration; the checkpoint mirrors fermionbag's raw dump idea (fermionbag.c:125-161):
-// a 64-byte header (magic, NT, NX, nchains, mode) followed by the raw FP64 angles A[chain][t][x][dir].
+// a 64-byte header (magic, NT, NX, nchains, mode, index of the next trajectory) followed by the raw FP64 angles
+// A[chain][t][x][dir].  The trajectory index keys the device random stream (momenta, pseudofermion noise, Metropolis
+// uniforms, measurement sources): a resumed run must continue it, or it replays the noise of its first leg.
 struct TbCkptHeader {
   char magic[16];
   int nt, nx, nchains, mode;
-  char pad[32];
+  unsigned int next_traj;   // 0 = not recorded (files written before the field existed)
+  char pad[28];
 };
+static_assert(sizeof(TbCkptHeader) == 64, "checkpoint header is 64 bytes");
+
+extern "C" int tb_checkpoint_set_next_trajectory(tb_ctx *ctx, unsigned int next_traj) {
+  if (!ctx) return TB_EINVAL;
+  ctx->ckpt_next_traj = next_traj;
+  return TB_OK;
+}
+
+extern "C" int tb_checkpoint_next_trajectory(const tb_ctx *ctx, unsigned int *next_traj) {
+  if (!ctx || !next_traj) return TB_EINVAL;
+  *next_traj = ctx->ckpt_next_traj;
+  return TB_OK;
+}
 
 extern "C" int tb_checkpoint_write(tb_ctx *ctx, const char *path) {
   if (!ctx || !path) return TB_EINVAL;
@@ -644,6 +669,7 @@ extern "C" int tb_checkpoint_write(tb_ctx *ctx, const char *path) {
       memset(&h, 0, sizeof(h));
       memcpy(h.magic, "THIRRING2D-A-V1", 15);
       h.nt = ctx->nt; h.nx = ctx->nx; h.nchains = ctx->C; h.mode = ctx->mode;
+      h.next_traj = ctx->ckpt_next_traj;
       if (fwrite(&h, sizeof(h), 1, f) != 1 || fwrite(A, sizeof(double), ctx->nsite * 2, f) != ctx->nsite * 2) {
         tb_set_error("tb_checkpoint_write: short write to %s", path);
         rc = TB_EINVAL;
@@ -680,6 +706,7 @@ extern "C" int tb_checkpoint_read(tb_ctx *ctx, const char *path) {
   fclose(f);
   if (rc == TB_OK) rc = tb_set_gauge(ctx, A);
   if (rc == TB_OK) rc = tb_synchronize(ctx);
+  if (rc == TB_OK) ctx->ckpt_next_traj = h.next_traj;
   free(A);
   return rc;
 }

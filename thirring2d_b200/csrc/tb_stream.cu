@@ -1884,7 +1884,10 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
 
   int chunk = ctx->tune_chunk > 0 ? ctx->tune_chunk : 16;
   const bool use_graph = getenv("TB_NO_GRAPH") == nullptr;
-  if (use_graph && (ctx->cg_graph == nullptr || ctx->cg_graph_chunk != chunk * 8 + (fused ? 1 : 0) + (use_pipe(ctx) ? 2 : 0))) {
+  // the graph holds its kernel arguments by value: everything a later call may change is part of the key (the per-site
+  // mass pointer of family B is one of them; CG tolerances and tile shapes invalidate the graph where they are set)
+  const int graph_key = chunk * 8 + (fused ? 1 : 0) + (use_pipe(ctx) ? 2 : 0) + (ctx->msite ? 4 : 0);
+  if (use_graph && (ctx->cg_graph == nullptr || ctx->cg_graph_chunk != graph_key)) {
     if (ctx->cg_graph) { cudaGraphExecDestroy(ctx->cg_graph); ctx->cg_graph = nullptr; }
     cudaStream_t cap;
     TB_CUDA(cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
@@ -1905,7 +1908,7 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
     TB_CUDA(cudaGraphInstantiate(&ctx->cg_graph, graph, 0));
     cudaGraphDestroy(graph);
     cudaStreamDestroy(cap);
-    ctx->cg_graph_chunk = chunk * 8 + (fused ? 1 : 0) + (use_pipe(ctx) ? 2 : 0);
+    ctx->cg_graph_chunk = graph_key;
   }
 
   const long max_chunks = ((long)ctx->cg.max_iter + chunk - 1) / chunk + 1;

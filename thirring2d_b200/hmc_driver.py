@@ -82,7 +82,10 @@ def main(argv=None):
     ap.add_argument("--backend", default=None, help="torch.distributed backend when launched by torchrun (default nccl)")
     ap.add_argument("--device", type=int, default=None, help="CUDA device (default: LOCAL_RANK modulo the device count)")
     ap.add_argument("--checkpoint", default=None, help="write the gauge fields here at the end (one file per rank)")
-    ap.add_argument("--resume", default=None, help="start from this checkpoint instead of the heat bath")
+    ap.add_argument("--resume", default=None, help="start from this checkpoint instead of the heat bath; the trajectory "
+                    "index (it keys the random stream) continues from the one recorded in the file")
+    ap.add_argument("--traj-offset", type=int, default=None, help="index of the first trajectory of this run (default: 1, "
+                    "or the index recorded in the --resume file); needed to resume a file that does not record it")
     a = ap.parse_args(argv)
     import os
 
@@ -116,17 +119,25 @@ def main(argv=None):
     mode = tb.MODE_ADJOINT if a.mode == "adjoint" else tb.MODE_REF_COMPAT
     names = ["acceptance", "Magnetisation", "Phase"] + (["Condensate"] if a.condensate > 0 else [])
     acc_sum = np.zeros(nloc)
-    last = np.zeros((nloc, len(names)))
+    meas_sum = np.zeros((nloc, len(names)))   # per chain: sum over the measurements of the run
+    n_meas = 0
     if nloc > 0:
         with tb.Context(a.nt, a.nx, nloc, mode, device=device, m=1.0, mu=mu) as ctx:
             ctx.set_params(np.array([points[p][1] for p in gid]), mu)
             ctx.hmc_set_coupling(np.array([points[p][0] for p in gid]))
             ctx.hmc_set_chain_offset(first)
+            start = 1
             if a.resume:
-                ctx.checkpoint_read(a.resume if world == 1 else "%s.rank%d" % (a.resume, rank))
+                recorded = ctx.checkpoint_read(a.resume if world == 1 else "%s.rank%d" % (a.resume, rank))
+                if a.traj_offset is None and recorded == 0:
+                    raise SystemExit("--resume: %s does not record a trajectory index; pass --traj-offset (restarting "
+                                     "at 1 would replay the random numbers of the first leg)" % a.resume)
+                start = a.traj_offset if a.traj_offset is not None else recorded
             else:
                 ctx.hmc_heatbath(100, seed=seed)  # hmc.c:927-929
-            for i in range(1, n_loops + 1):
+                if a.traj_offset is not None:
+                    start = a.traj_offset
+            for i in range(start, start + n_loops):
                 obs, acc, _ = ctx.hmc_trajectory(a.nsteps, a.traj_length, seed=seed, traj_index=i)
                 acc_sum += acc
                 if not a.quiet:
@@ -134,21 +145,27 @@ def main(argv=None):
                         print("\n".join(trajectory_lines(obs[c], first + c)))
                 if i % n_measure == 0:
                     mag, ph = ctx.hmc_measure(20, seed=seed, meas_index=i)
-                    last[:, 1], last[:, 2] = mag, ph
+                    n_meas += 1
+                    meas_sum[:, 1] += mag
+                    meas_sum[:, 2] += ph
                     if not a.quiet:
                         for c in range(nloc):
                             print("\n".join(measurement_lines(mag[c], ph[c], first + c)))
                     if a.condensate > 0:
                         cond, _ = ctx.hmc_condensate(a.condensate, seed=seed, meas_index=i)
-                        last[:, 3] = cond
+                        meas_sum[:, 3] += cond
                         if not a.quiet:
                             for c in range(nloc):
                                 print("[chain %d] Condensate %s" % (first + c, fmt_g(cond[c])))
             if a.checkpoint:
-                ctx.checkpoint_write(a.checkpoint if world == 1 else "%s.rank%d" % (a.checkpoint, rank))
-    last[:, 0] = acc_sum / max(n_loops, 1)
+                ctx.checkpoint_write(a.checkpoint if world == 1 else "%s.rank%d" % (a.checkpoint, rank),
+                                     next_trajectory=start + n_loops)
+    # per chain: acceptance over the run and the measurements averaged over the run's trajectories (the summary's
+    # error bar is the spread of these chain averages over the chains of a point)
+    chain_avg = meas_sum / max(n_meas, 1)
+    chain_avg[:, 0] = acc_sum / max(n_loops, 1)
     sys.stdout.flush()
-    cnt, mean, err = reduce_observables(last, gid, len(points), dist=dist,
+    cnt, mean, err = reduce_observables(chain_avg, gid, len(points), dist=dist,
                                         device=("cuda:%d" % device) if (dist is not None and dist.get_backend() == "nccl") else None)
     if rank == 0:
         print("\n".join(summary_lines(points, cnt, mean, err, names)))

@@ -61,6 +61,8 @@ SIGNATURES = {
     "tb_get_gauge": (_i, [_vp, _vp]),
     "tb_checkpoint_write": (_i, [_vp, C.c_char_p]),
     "tb_checkpoint_read": (_i, [_vp, C.c_char_p]),
+    "tb_checkpoint_set_next_trajectory": (_i, [_vp, C.c_uint]),
+    "tb_checkpoint_next_trajectory": (_i, [_vp, C.POINTER(C.c_uint)]),
     "tb_launch_count": (C.c_longlong, [_vp]),
     "tb_reset_launch_count": (_i, [_vp]),
     "tb_last_solve_ms": (_d, [_vp]),
