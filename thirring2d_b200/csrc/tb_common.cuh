@@ -99,6 +99,9 @@ struct TbSlab {
   double2 *red3;
   double2 *peer_red3[TB_SLAB_MAX_RANKS];
   int nrep, rep_stride;
+  // the totals {total, tag} the last-arriving block of THIS GPU publishes to its other blocks: bcast[rep * bcast_stride + kind*Cpad + c]
+  double2 *bcast;
+  int bcast_stride;
   unsigned long long *timeline;   // optional: globaltimer stamps of the first iterations (TB_SLAB_TIMELINE), else nullptr
 };
 #define TB_SLAB_NREP_MAX 8

@@ -5,8 +5,8 @@
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct SlabOffsets {
-  size_t p, mp, w0, r, p1, red, red_flag, flags, red2, red3, total;
-  int rep_stride;
+  size_t p, mp, w0, r, p1, red, red_flag, flags, red2, red3, bcast, total;
+  int rep_stride, bcast_stride;
 };
 
 static SlabOffsets slab_offsets(const tb_ctx *ctx) {
@@ -23,7 +23,9 @@ static SlabOffsets slab_offsets(const tb_ctx *ctx) {
   o.red2 = o.flags + 256;
   o.red3 = o.red2 + align_up((size_t)TB_NRED * ctx->nranks * ctx->g.Cpad * sizeof(double2), 256);
   o.rep_stride = (int)align_up((size_t)TB_NRED * ctx->nranks * ctx->g.Cpad, 16);   // double2 elements: whole 256-byte blocks
-  o.total = o.red3 + (size_t)TB_SLAB_NREP_MAX * o.rep_stride * sizeof(double2);
+  o.bcast = o.red3 + (size_t)TB_SLAB_NREP_MAX * o.rep_stride * sizeof(double2);
+  o.bcast_stride = (int)align_up((size_t)TB_NRED * ctx->g.Cpad, 16);
+  o.total = o.bcast + (size_t)TB_SLAB_NREP_MAX * o.bcast_stride * sizeof(double2);
   return o;
 }
 
@@ -124,6 +126,8 @@ extern "C" int tb_slab_connect(tb_ctx *ctx, const void *all_handles) {
   sl.red2 = (double2 *)(me + o.red2);
   sl.red3 = (double2 *)(me + o.red3);
   sl.rep_stride = o.rep_stride;
+  sl.bcast = (double2 *)(me + o.bcast);
+  sl.bcast_stride = o.bcast_stride;
   sl.nrep = TB_SLAB_NREP_MAX;
   for (int q = 0; q < P; q++) {
     sl.peer_red[q] = (double *)((char *)ctx->peer_block[q] + o.red);

@@ -1027,20 +1027,25 @@ __device__ __forceinline__ void update_scalars(double total, ChainScalars &cs, c
 }
 
 // Per-chain sum of `acc` over all blocks of all ranks; returns the total of the thread's chain (valid in every thread).
+// mode 2: every block polls the peers' slots (NREP replicas).  mode 1: only the block that arrived last exchanges with
+// the peers (one quiet slot per peer: pollers on a line delay the NVLink store they wait for); it then publishes the
+// all-reduced totals {total, total xor tag} on NREP lines of its OWN GPU, which the other blocks poll.
 // tl: optional time stamps of this synchronisation point (4 words: see TB_SLAB_TL_WORDS), nullptr when not recording.
 template <int RED>
 __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, const TbCgState &s, const TbSlab &sl,
-                                                 double *red, unsigned long long &target, int gen,
+                                                 double *red, unsigned long long &target, int gen, int mode,
                                                  unsigned long long *tl) {
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = (blockDim.x + 31) >> 5;
   const int c_local = tid & (g.bc - 1), x_local = tid >> g.bc_shift;
+  const bool stamp = tl && tid == 0 && (blockIdx.x & 15) == 0;   // a sample of the blocks records
+  const long long tag = (long long)((unsigned long long)gen * 0x9E3779B97F4A7C15ULL);
   for (int o = 16; o >= g.bc; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   __syncthreads();   // red may still be read by the previous call
   if (lane < g.bc) red[warp * g.bc + lane] = acc;
   __threadfence();   // this thread's field stores are visible device-wide before the block's arrival is counted
   __syncthreads();
-  if (tl && tid == 0) atomicMax(&tl[1], global_ns());
+  if (stamp) atomicMax(&tl[1], global_ns());
   if (warp == 0) {
     if (lane < g.bc) {
       double t = 0.0;
@@ -1055,7 +1060,8 @@ __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, co
     }
   }
   __syncthreads();
-  if (s_last) {   // block-uniform: this block arrived last, every other block's partial and field rows are visible
+  const bool last = s_last != 0;   // block-uniform: this block arrived last, every other block's partial and rows are visible
+  if (last) {
     __threadfence();
     double sum = 0.0;
     for (int blk = x_local; blk < (int)gridDim.x; blk += g.bx) sum += __ldcg(&s.partial[(size_t)blk * g.Cpad + c_local]);
@@ -1063,11 +1069,11 @@ __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, co
     __syncthreads();
     if (tid < g.bc) red[tid] = mine;
     __syncthreads();
-    const long long tag = (long long)((unsigned long long)gen * 0x9E3779B97F4A7C15ULL);
-    const int nst = sl.P * sl.nrep * g.bc;
+    const int nrep_out = mode == 2 ? sl.nrep : 1;
+    const int nst = sl.P * nrep_out * g.bc;
     if (tid < nst) __threadfence_system();   // this GPU's halo rows before the tag, for the peers
     for (int i = tid; i < nst; i += blockDim.x) {
-      const int c = i & (g.bc - 1), k = i >> g.bc_shift, rep = k % sl.nrep, q = k / sl.nrep;
+      const int c = i & (g.bc - 1), k = i >> g.bc_shift, rep = k % nrep_out, q = k / nrep_out;
       const double v = red[c];
       st_volatile_v2(sl.peer_red3[q] + (size_t)rep * sl.rep_stride + (size_t)(RED * sl.P + sl.rank) * g.Cpad + c,
                      __double_as_longlong(v), __double_as_longlong(v) ^ tag);
@@ -1075,39 +1081,78 @@ __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, co
     if (tl && tid == 0) tl[2] = global_ns();
     __syncthreads();   // red is rewritten below
   }
-  const bool io = tid < sl.P * g.bc;   // thread (q, chain) polls the slot rank q writes into this GPU's memory
-  double theirs = 0.0;
-  if (io) {
-    const long long tag = (long long)((unsigned long long)gen * 0x9E3779B97F4A7C15ULL);
-    const int q = tid >> g.bc_shift;
-    const double2 *in = sl.red3 + (size_t)(blockIdx.x % sl.nrep) * sl.rep_stride + (size_t)(RED * sl.P + q) * g.Cpad + c_local;
-    const long long t0 = clock64();
-    for (;;) {
-      long long wx, wy;
-      ld_volatile_v2(in, wx, wy);
-      if ((wx ^ wy) == tag) { theirs = __longlong_as_double(wx); break; }
-      __nanosleep(20);
-      if (clock64() - t0 > TB_PERSIST_SPIN_CYCLES) __trap();   // a launch error on this rank instead of a hung box
+  double total;
+  if (mode == 2 || last) {
+    const bool io = tid < sl.P * g.bc;   // thread (q, chain) polls the slot rank q writes into this GPU's memory
+    if (io) {
+      const int q = tid >> g.bc_shift, rep = mode == 2 ? (int)(blockIdx.x % sl.nrep) : 0;
+      const double2 *in = sl.red3 + (size_t)rep * sl.rep_stride + (size_t)(RED * sl.P + q) * g.Cpad + c_local;
+      const long long t0 = clock64();
+      double theirs;
+      for (;;) {
+        long long wx, wy;
+        ld_volatile_v2(in, wx, wy);
+        if ((wx ^ wy) == tag) { theirs = __longlong_as_double(wx); break; }
+        if (mode == 2) __nanosleep(20);
+        if (clock64() - t0 > TB_PERSIST_SPIN_CYCLES) __trap();   // a launch error on this rank instead of a hung box
+      }
+      __threadfence_system();   // acquire side: the neighbours' rows behind their tags
+      red[tid] = theirs;        // [q][chain]
     }
-    __threadfence_system();   // acquire side: the neighbours' rows behind their tags
-    red[tid] = theirs;        // [q][chain]
+    __syncthreads();
+    total = 0.0;
+    for (int r = 0; r < sl.P; r++) total += red[r * g.bc + c_local];   // rank order: the same bits on every rank
+    if (mode != 2 && tid < sl.nrep * g.bc) {   // publish the totals to the other blocks of this GPU
+      __threadfence();
+      st_volatile_v2(sl.bcast + (size_t)(tid >> g.bc_shift) * sl.bcast_stride + (size_t)RED * g.Cpad + c_local,
+                     __double_as_longlong(total), __double_as_longlong(total) ^ tag);
+    }
+  } else {
+    if (tid < g.bc) {
+      const double2 *in = sl.bcast + (size_t)(blockIdx.x % sl.nrep) * sl.bcast_stride + (size_t)RED * g.Cpad + tid;
+      const long long t0 = clock64();
+      double v;
+      for (;;) {
+        long long wx, wy;
+        ld_volatile_v2(in, wx, wy);
+        if ((wx ^ wy) == tag) { v = __longlong_as_double(wx); break; }
+        __nanosleep(20);
+        if (clock64() - t0 > TB_PERSIST_SPIN_CYCLES) __trap();
+      }
+      __threadfence();   // acquire: this GPU's rows (the publisher saw every arrival) and, through it, the neighbours'
+      red[tid] = v;
+    }
+    __syncthreads();
+    total = red[c_local];
   }
-  __syncthreads();
-  double total = 0.0;
-  for (int r = 0; r < sl.P; r++) total += red[r * g.bc + c_local];   // rank order: the same bits on every rank
-  if (tl && tid == 0) atomicMax(&tl[3], global_ns());
+  if (stamp) atomicMax(&tl[3], global_ns());
   return total;
+}
+
+// Work of one block: column strip `xtile` (bx sites wide) and rows [t_begin, t_end) of the slab.  The nt rows of a strip
+// are cut into nseg segments as evenly as integer rows allow, nxtiles * nseg <= the number of co-resident blocks when the
+// slab allows it: every block has work and none has more than one row above the average (2048^2 on 8 GPUs: 440 blocks
+// of 4 or 5 rows instead of 256 tiles of 8 rows on 148 SMs).
+struct SlabSeg { int xtile, t_begin, t_end; };
+__device__ __forceinline__ SlabSeg slab_seg(const TbGeom &g, int w, int nseg) {
+  SlabSeg sg;
+  sg.xtile = w % g.nxtiles;
+  const int j = w / g.nxtiles;
+  sg.t_begin = (int)((long long)j * g.nt / nseg);
+  sg.t_end = (int)((long long)(j + 1) * g.nt / nseg);
+  return sg;
 }
 
 template <int TT>
 __global__ void __launch_bounds__(TB_MAX_BLOCK, 3)
-slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, const TbSlab sl) {
+slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, const TbSlab sl, const int nseg,
+                         const int mode) {
   __shared__ double red[TB_MAX_BLOCK];
-  const int ntiles = g.nxtiles * g.nttiles;
-  const size_t R = (size_t)g.R;
+  const int nwork = g.nxtiles * nseg;
+  const int R = g.R;   // 32-bit indices: a slab of the one-launch solve has at most 2^27 elements per field
   unsigned long long bar_target = 0;
   const int E0 = *(volatile int *)sl.seq;   // rewritten only after the last grid barrier
-  const int c = threadIdx.x & (g.bc - 1);
+  const int c = threadIdx.x & (g.bc - 1), x_local = threadIdx.x >> g.bc_shift;
   const bool chain = c < g.C;
   const double m = chain ? a.mass[c] : 0.0;
   const double e_p = chain ? a.emu[c] : 1.0, e_m = chain ? a.emmu[c] : 1.0;
@@ -1115,45 +1160,43 @@ slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, 
   auto stamps = [&](int k, int half) -> unsigned long long * {
     return (sl.timeline && k < TB_SLAB_TL_ITERS) ? sl.timeline + ((size_t)k * 2 + half) * 4 : nullptr;
   };
+  // rows [t0, t0 + nrows) of the chunks of a segment: at most TT rows each, as even as integer rows allow
+  auto chunks = [&](const SlabSeg &sg) { return (sg.t_end - sg.t_begin + TT - 1) / TT; };
+  auto chunk_lo = [&](const SlabSeg &sg, int nch, int ch) { return sg.t_begin + ch * (sg.t_end - sg.t_begin) / nch; };
 
-  // the neighbours may still read the previous generation of p (an apply queued before this solve)
-  auto wait_ends = [&](const BlockPos &b, int kind, int need) {
-    if (b.ttile == 0 || b.ttile == g.nttiles - 1) {
+  // ---- x = 0, r = p = b, ||b||^2 (hmc.c:349-361): generation E0 + 1 of p
+  double acc = 0.0;
+  for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+    const SlabSeg sg = slab_seg(g, w, nseg);
+    // the neighbours may still read the previous generation of p (an apply queued before this solve)
+    if (sg.t_begin == 0 || sg.t_end == g.nt) {
       if (threadIdx.x == 0) {
-        if (b.ttile == 0) spin_until(sl.flags + kind * 2 + 0, need);
-        if (b.ttile == g.nttiles - 1) spin_until(sl.flags + kind * 2 + 1, need);
+        if (sg.t_begin == 0) spin_until(sl.flags + TB_FLAG_PDONE * 2 + 0, E0);
+        if (sg.t_end == g.nt) spin_until(sl.flags + TB_FLAG_PDONE * 2 + 1, E0);
         __threadfence_system();
       }
       __syncthreads();
     }
-  };
-
-  // ---- x = 0, r = p = b, ||b||^2 (hmc.c:349-361): generation E0 + 1 of p
-  double acc = 0.0;
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    const BlockPos b = tile_pos(g, tile);
-    wait_ends(b, TB_FLAG_PDONE, E0);
-    if (b.valid) {
-      const size_t j = (size_t)b.x * g.C + b.c;
-      const int t0 = b.ttile * TT;
-#pragma unroll
-      for (int i = 0; i < TT; i++) {
-        const int t = t0 + i;
-        if (t < g.nt) {
-          const size_t k = t * R + j;
-          const double2 v = a.b[k];
-          a.x[k] = make_double2(0.0, 0.0);
-          a.r[k] = v;
-          a.p[k] = v;
-          acc += v.x * v.x + v.y * v.y;
-        }
+    const int x = sg.xtile * g.bx + x_local;
+    if (chain && x < g.nx) {
+      const int j = x * g.C + c;
+      for (int t = sg.t_begin; t < sg.t_end; t++) {
+        const int k = t * R + j;
+        const double2 v = a.b[k];
+        a.x[k] = make_double2(0.0, 0.0);
+        a.r[k] = v;
+        a.p[k] = v;
+        acc += v.x * v.x + v.y * v.y;
       }
     }
   }
   int gen = E0 + 1;   // generation of p
-  update_scalars<FIN_INIT>(slab_allreduce<TB_RED_INIT>(acc, g, s, sl, red, bar_target, gen, nullptr), cs, s);
+  update_scalars<FIN_INIT>(slab_allreduce<TB_RED_INIT>(acc, g, s, sl, red, bar_target, gen, mode, nullptr), cs, s);
 
-  // p is double-buffered: odd iterations read p_old from a.p and write p_new into a.p1, even ones the other way round
+  // p is double-buffered: odd iterations read p_old from a.p and write p_new into a.p1, even ones the other way round.
+  // Fields of this GPU that other blocks rewrite between the phases are read with ordinary (L1-cached) loads: every
+  // synchronisation point ends with an acquire fence and a CTA barrier in every block, which is what makes ordinary
+  // loads after a grid-wide barrier see the other blocks' stores; the neighbours' rows come over NVLink with ld.cv.
   auto n_active = [&] { return __popc(__ballot_sync(0xffffffffu, (int)(threadIdx.x & 31) < g.bc && cs.active)); };
   for (int k = 1; n_active() > 0; k++) {
     const bool act = cs.active != 0;
@@ -1167,37 +1210,40 @@ slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, 
       return make_double2(fma(be, pv.x, rv.x), fma(be, pv.y, rv.y));
     };
     unsigned long long *tlA = stamps(k - 1, 0), *tlB = stamps(k - 1, 1);
-    if (tlA && threadIdx.x == 0) atomicMin(&tlA[0], global_ns());
+    if (tlA && threadIdx.x == 0 && (blockIdx.x & 15) == 0) atomicMin(&tlA[0], global_ns());
     // ---- A: p = r + beta p on the fly, Mp = M p, |Mp|^2.  The neighbours' rows of r and of the old p are complete:
     // their owners passed the ||r||^2 all-reduce of the previous iteration.
     acc = 0.0;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const BlockPos b = tile_pos(g, tile);
-      if (b.valid && act) {
-        const size_t j = (size_t)b.x * g.C + b.c;
-        const size_t jp = (size_t)((b.x + 1 == g.nx) ? 0 : b.x + 1) * g.C + b.c;
-        const size_t jm = (size_t)((b.x == 0) ? g.nx - 1 : b.x - 1) * g.C + b.c;
-        const int t0 = b.ttile * TT;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+      const SlabSeg sg = slab_seg(g, w, nseg);
+      const int x = sg.xtile * g.bx + x_local;
+      if (!(chain && x < g.nx && act)) continue;
+      const int j = x * g.C + c;
+      const int jp = ((x + 1 == g.nx) ? 0 : x + 1) * g.C + c;
+      const int jm = ((x == 0) ? g.nx - 1 : x - 1) * g.C + c;
+      const int nch = chunks(sg);
+      for (int ch = 0; ch < nch; ch++) {
+        const int t0 = chunk_lo(sg, nch, ch), nrows = chunk_lo(sg, nch, ch + 1) - t0;
         double2 pm, w0m;
         if (t0 == 0) {
-          const size_t kk = (size_t)(g.nt - 1) * R + j;
+          const int kk = (g.nt - 1) * R + j;
           pm = pnew(__ldcv(&a.r_prev[kk]), __ldcv(&po_prev[kk]));
           w0m = __ldcv(&a.W0_prev[kk]);
         } else {
-          const size_t kk = (size_t)(t0 - 1) * R + j;
-          pm = pnew(__ldcg(&a.r[kk]), __ldcg(&po[kk]));
+          const int kk = (t0 - 1) * R + j;
+          pm = pnew(a.r[kk], po[kk]);
           w0m = a.W0[kk];
         }
-        double2 pc = pnew(__ldcg(&a.r[t0 * R + j]), __ldcg(&po[t0 * R + j]));
+        double2 pc = pnew(a.r[t0 * R + j], po[t0 * R + j]);
 #pragma unroll
         for (int i = 0; i < TT; i++) {
-          const int t = t0 + i;
-          if (t < g.nt) {
-            const size_t row = t * R;
+          if (i < nrows) {
+            const int t = t0 + i;
+            const int row = t * R;
             const double2 pp = (t + 1 == g.nt) ? pnew(__ldcv(&a.r_next[j]), __ldcv(&po_next[j]))
-                                               : pnew(__ldcg(&a.r[row + R + j]), __ldcg(&po[row + R + j]));
-            const double2 pxp = pnew(__ldcg(&a.r[row + jp]), __ldcg(&po[row + jp]));
-            const double2 pxm = pnew(__ldcg(&a.r[row + jm]), __ldcg(&po[row + jm]));
+                                               : pnew(a.r[row + R + j], po[row + R + j]);
+            const double2 pxp = pnew(a.r[row + jp], po[row + jp]);
+            const double2 pxm = pnew(a.r[row + jm], po[row + jm]);
             const double2 w0c = a.W0[row + j];
             const double2 w1c = a.W1[row + j];
             const double2 w1m = a.W1[row + jm];
@@ -1224,42 +1270,45 @@ slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, 
         }
       }
     }
-    update_scalars<FIN_PQ>(slab_allreduce<TB_RED_PQ>(acc, g, s, sl, red, bar_target, gen, tlA), cs, s);
+    update_scalars<FIN_PQ>(slab_allreduce<TB_RED_PQ>(acc, g, s, sl, red, bar_target, gen, mode, tlA), cs, s);
 
     // ---- B: q = M^dagger Mp on the fly, x += alpha p, r -= alpha q, ||r||^2.  The neighbours' Mp rows are complete:
     // their owners contributed to the |Mp|^2 sum.
-    if (tlB && threadIdx.x == 0) atomicMin(&tlB[0], global_ns());
+    if (tlB && threadIdx.x == 0 && (blockIdx.x & 15) == 0) atomicMin(&tlB[0], global_ns());
     acc = 0.0;
     const double al = cs.alpha;
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-      const BlockPos b = tile_pos(g, tile);
-      if (b.valid && act) {
-        const size_t j = (size_t)b.x * g.C + b.c;
-        const size_t jp = (size_t)((b.x + 1 == g.nx) ? 0 : b.x + 1) * g.C + b.c;
-        const size_t jm = (size_t)((b.x == 0) ? g.nx - 1 : b.x - 1) * g.C + b.c;
-        const int t0 = b.ttile * TT;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+      const SlabSeg sg = slab_seg(g, w, nseg);
+      const int x = sg.xtile * g.bx + x_local;
+      if (!(chain && x < g.nx && act)) continue;
+      const int j = x * g.C + c;
+      const int jp = ((x + 1 == g.nx) ? 0 : x + 1) * g.C + c;
+      const int jm = ((x == 0) ? g.nx - 1 : x - 1) * g.C + c;
+      const int nch = chunks(sg);
+      for (int ch = 0; ch < nch; ch++) {
+        const int t0 = chunk_lo(sg, nch, ch), nrows = chunk_lo(sg, nch, ch + 1) - t0;
         double2 pm, w0m;
         if (t0 == 0) {
-          pm = __ldcv(&a.mp_prev[(size_t)(g.nt - 1) * R + j]);
-          w0m = __ldcv(&a.W0_prev[(size_t)(g.nt - 1) * R + j]);
+          pm = __ldcv(&a.mp_prev[(g.nt - 1) * R + j]);
+          w0m = __ldcv(&a.W0_prev[(g.nt - 1) * R + j]);
         } else {
-          pm = __ldcg(&a.Mp[(size_t)(t0 - 1) * R + j]);
-          w0m = a.W0[(size_t)(t0 - 1) * R + j];
+          pm = a.Mp[(t0 - 1) * R + j];
+          w0m = a.W0[(t0 - 1) * R + j];
         }
-        double2 pc = __ldcg(&a.Mp[t0 * R + j]);
+        double2 pc = a.Mp[t0 * R + j];
 #pragma unroll
         for (int i = 0; i < TT; i++) {
-          const int t = t0 + i;
-          if (t < g.nt) {
-            const size_t row = t * R;
-            const double2 pp = (t + 1 == g.nt) ? __ldcv(&a.mp_next[j]) : __ldcg(&a.Mp[row + R + j]);
-            const double2 pxp = __ldcg(&a.Mp[row + jp]);
-            const double2 pxm = __ldcg(&a.Mp[row + jm]);
+          if (i < nrows) {
+            const int t = t0 + i;
+            const int row = t * R;
+            const double2 pp = (t + 1 == g.nt) ? __ldcv(&a.mp_next[j]) : a.Mp[row + R + j];
+            const double2 pxp = a.Mp[row + jp];
+            const double2 pxm = a.Mp[row + jm];
             const double2 w0c = a.W0[row + j];
             const double2 w1c = a.W1[row + j];
             const double2 w1m = a.W1[row + jm];
-            const double2 pv = __ldcg(&pn[row + j]);
-            double2 xv = __ldcg(&a.x[row + j]), rv = __ldcg(&a.r[row + j]);
+            const double2 pv = pn[row + j];
+            double2 xv = a.x[row + j], rv = a.r[row + j];
             const double fr = w0c.x * e_m, fi = w0c.y * e_m;   // M^dagger: e^{-mu} on the +t hop
             const double br = w0m.x * e_p, bi = w0m.y * e_p;
             double hr = fr * pp.x - fi * pp.y;
@@ -1285,7 +1334,7 @@ slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, 
         }
       }
     }
-    update_scalars<FIN_RR>(slab_allreduce<TB_RED_RR>(acc, g, s, sl, red, bar_target, gen, tlB), cs, s);
+    update_scalars<FIN_RR>(slab_allreduce<TB_RED_RR>(acc, g, s, sl, red, bar_target, gen, mode, tlB), cs, s);
     gen++;
   }
   // every block of every rank leaves in the same iteration (identical scalars).  Block 0 writes the outcome; then leave
@@ -1768,9 +1817,11 @@ static bool use_persistent_slab(const tb_ctx *ctx) {
          ctx->nsite <= ((size_t)4 << 20) && getenv("TB_NO_PERSIST") == nullptr;
 }
 
-template <int TT, bool ALLPOLL>
-static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int *nblocks_out) {
-  TbGeom g = ctx->g;   // same tiles, TT rows each (8: 80 registers, three blocks per SM)
+// mode 0: block 0 runs the all-reduce (slab_cg_persistent_kernel); 1: the last-arriving block exchanges with the peers
+// and publishes the totals locally; 2: every block polls the peers' slots (slab_cg_onelaunch_kernel, see slab_allreduce)
+static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int mode, int *nblocks_out) {
+  constexpr int TT = 8;
+  TbGeom g = ctx->g;   // same column strips; mode 0: tiles of TT rows, else balanced row segments (slab_seg)
   g.tt = TT;
   g.nttiles = (ctx->nt + TT - 1) / TT;
   g.nslots = g.nxtiles * g.nttiles;
@@ -1778,14 +1829,23 @@ static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int *nblocks_ou
   SlabCgArgs a = {b, ctx->xw, ctx->r, ctx->p, ctx->p1, ctx->Mp, sl.p_prev, sl.p_next, sl.p1_prev, sl.p1_next,
                   sl.r_prev, sl.r_next, sl.mp_prev, sl.mp_next,
                   ctx->W0, sl.W0_prev, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu};
-  auto kern = ALLPOLL ? slab_cg_onelaunch_kernel<TT> : slab_cg_persistent_kernel<TT>;
+  const void *kern = mode == 0 ? (const void *)slab_cg_persistent_kernel<TT> : (const void *)slab_cg_onelaunch_kernel<TT>;
   int per_sm = 0, nsm = TB_NUM_SMS_B200, coop = 0;
   TB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
   TB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
   TB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, g.bc * g.bx, 0));
   if (!coop || per_sm < 1) { *nblocks_out = 0; return TB_OK; }
-  int nblocks = g.nxtiles * g.nttiles;
-  if (nblocks > per_sm * nsm) nblocks = per_sm * nsm;
+  const int capacity = per_sm * nsm;
+  int nseg = 1, nblocks;
+  if (mode == 0) {
+    nblocks = g.nxtiles * g.nttiles;
+  } else {
+    nseg = capacity / g.nxtiles;
+    if (nseg > ctx->nt) nseg = ctx->nt;
+    if (nseg < 1) nseg = 1;
+    nblocks = g.nxtiles * nseg;
+  }
+  if (nblocks > capacity) nblocks = capacity;
   if ((size_t)nblocks * g.Cpad > (size_t)ctx->g.nxtiles * ctx->nt * ctx->g.Cpad) { *nblocks_out = 0; return TB_OK; }   // partial[]
   TB_CUDA(cudaMemsetAsync(sl.gbar, 0, sizeof(unsigned long long), ctx->stream));
   sl.nrep = TB_SLAB_NREP_MAX;   // the same on every rank: a rank polls the replicas its peers write
@@ -1793,9 +1853,10 @@ static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int *nblocks_ou
     const int n = atoi(e);
     sl.nrep = n < 1 ? 1 : (n > TB_SLAB_NREP_MAX ? TB_SLAB_NREP_MAX : n);
   }
+  if (sl.nrep > g.bx) sl.nrep = g.bx;   // a thread per (replica, chain) publishes the totals
   // optional timeline of the first TB_SLAB_TL_ITERS iterations (TB_SLAB_TIMELINE=<file prefix>): per synchronisation
   // point {first block starts the phase, last block finishes it, partial stored to the peers, last block holds the total}
-  const char *tlpath = ALLPOLL ? getenv("TB_SLAB_TIMELINE") : nullptr;
+  const char *tlpath = mode != 0 ? getenv("TB_SLAB_TIMELINE") : nullptr;
   const size_t tlwords = (size_t)TB_SLAB_TL_ITERS * TB_SLAB_TL_WORDS;
   unsigned long long *tl_host = nullptr;
   if (tlpath) {
@@ -1809,8 +1870,9 @@ static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int *nblocks_ou
   TbCgState ss = ctx->cg;
   TbSlab sls = sl;
   if (!tlpath) sls.timeline = nullptr;
-  void *args[] = {&a, &gg, &ss, &sls};
-  TB_CUDA(cudaLaunchCooperativeKernel((const void *)kern, dim3(nblocks), dim3(g.bc * g.bx), args, 0, ctx->stream));
+  int nseg_arg = nseg, mode_arg = mode;
+  void *args[] = {&a, &gg, &ss, &sls, &nseg_arg, &mode_arg};   // the block-0 kernel takes the first four
+  TB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(nblocks), dim3(g.bc * g.bx), args, 0, ctx->stream));
   ctx->launches++;
   *nblocks_out = nblocks;
   if (tlpath) {
@@ -1819,9 +1881,11 @@ static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int *nblocks_ou
     char name[512];
     snprintf(name, sizeof(name), "%s.rank%d.txt", tlpath, ctx->rank);
     if (FILE *f = fopen(name, "w")) {
+      fprintf(f, "# %d blocks, %d row segments per column strip, sync mode %d\n", nblocks, nseg, mode);
       fprintf(f, "# globaltimer ns since the first stamp of this rank; per CG iteration and phase (A: Mp = M p, B: M^dagger + "
                  "update): start = first block enters, end = last block has its partial, stored = partial sent to the peers, "
-                 "total = last block holds the all-reduced sum\n# iter A_start A_end A_stored A_total B_start B_end B_stored B_total\n");
+                 "total = last block holds the all-reduced sum (every 16th block records)\n"
+                 "# iter A_start A_end A_stored A_total B_start B_end B_stored B_total\n");
       unsigned long long t0 = tl_host[0];
       for (int k = 0; k < TB_SLAB_TL_ITERS; k++) {
         if (tl_host[(size_t)k * 8] == ~0ULL) break;
@@ -1836,19 +1900,10 @@ static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int *nblocks_ou
   return TB_OK;
 }
 
-// rows per tile of the one-launch solve: the largest of 8, 4, 2 that still gives every SM about two tiles (small
-// slabs are latency-bound: more, shorter marches; 2048^2 on 8 GPUs is 256 tiles of 8 rows for 148 SMs)
 static int launch_persistent_slab_auto(tb_ctx *ctx, const double2 *b, int *nblocks_out) {
-  const bool allpoll = !(getenv("TB_SLAB_SYNC") && atoi(getenv("TB_SLAB_SYNC")) == 0);
-  int tt = 8;
-  if (allpoll) {
-    while (tt > 2 && (long)ctx->g.nxtiles * ((ctx->nt + tt - 1) / tt) < 2L * TB_NUM_SMS_B200) tt >>= 1;
-    if (const char *e = getenv("TB_SLAB_ROWS")) { const int v = atoi(e); if (v == 2 || v == 4 || v == 8) tt = v; }
-  }
-  if (!allpoll) return launch_persistent_slab<8, false>(ctx, b, nblocks_out);
-  if (tt == 8) return launch_persistent_slab<8, true>(ctx, b, nblocks_out);
-  if (tt == 4) return launch_persistent_slab<4, true>(ctx, b, nblocks_out);
-  return launch_persistent_slab<2, true>(ctx, b, nblocks_out);
+  int mode = 1;
+  if (const char *e = getenv("TB_SLAB_SYNC")) { const int v = atoi(e); if (v >= 0 && v <= 2) mode = v; }
+  return launch_persistent_slab(ctx, b, mode, nblocks_out);
 }
 
 // Streaming CG driver: the whole solve stays on the device; the host only polls the number of chains

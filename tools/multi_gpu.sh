@@ -15,7 +15,7 @@ port=29540
 for P in 2 4 8; do
   [ $P -le $NG ] || continue
   for size in 2048 4096 1024; do
-    for variant in "default" "TB_SLAB_SYNC=0" "TB_NO_PERSIST=1" "TB_SLAB_NREP=1" "TB_SLAB_ROWS=8"; do
+    for variant in "default" "TB_SLAB_SYNC=0" "TB_SLAB_SYNC=2" "TB_NO_PERSIST=1" "TB_SLAB_NREP=1"; do
       [ -n "$QUICK" ] && [ "$variant" != "default" ] && [ "$variant" != "TB_SLAB_SYNC=0" ] && continue
       [ $size = 4096 ] && [ "$variant" != "default" ] && [ "$variant" != "TB_NO_PERSIST=1" ] && continue
       port=$((port + 1))
@@ -24,8 +24,12 @@ for P in 2 4 8; do
       echo "P=$P size=$size $variant: $line" | tee -a $OUT/slab_${TAG}_${NG}gpu.txt | cut -c1-220
     done
   done
-  port=$((port + 1))
-  TB_SLAB_TIMELINE=$OUT/timeline_${TAG}_P${P}_2048 timeout 120 $RUN --nproc-per-node $P --master-port $port tools/slab_bench.py --size 2048 --iters 60 2>&1 | tail -1 | cut -c1-200
+  for size in 2048 1024; do
+    for mode in 1 2; do
+      port=$((port + 1))
+      TB_SLAB_SYNC=$mode TB_SLAB_TIMELINE=$OUT/timeline_${TAG}_P${P}_${size}_mode${mode} timeout 120 $RUN --nproc-per-node $P --master-port $port tools/slab_bench.py --size $size --iters 60 2>&1 | tail -1 | cut -c1-200
+    done
+  done
 done
 echo "== bench.py under torch.distributed.run at every rank count"
 for P in 2 4 8; do
