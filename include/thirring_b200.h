@@ -74,7 +74,10 @@ int tb_set_cg(tb_ctx *ctx, double accuracy, int max_iter);
  * 18 = 1x8, 28 = 2x8, 24 = 2x4).  iters_per_launch: CG iterations per CUDA-graph launch (streaming).
  * solver: 0 auto (on-chip when the lattice has a resident or cluster shape, see tb_solver_info), 1 streaming
  * multi-kernel (3 fused kernels per iteration when M~ = M^dagger, else 4), 2 on-chip or fail, 3 streaming with
- * the 4-kernel iteration always. */
+ * the 4-kernel iteration always, 5 the strict solver: fmdm_invert_cg in the reference's own floating-point evaluation
+ * order (no FMA contraction, every lattice sum accumulated sequentially in (t, x) order as hmc.c:354-379 does) -- slow,
+ * for parity work: it lands on the reference's iteration count where the fast solvers' tree sums move the
+ * ||r||^2 < 1e-30 crossing of a 700+ iteration solve by 1-3 iterations. */
 int tb_set_tuning(tb_ctx *ctx, int rows_per_thread, int iters_per_launch, int solver);
 
 /* Which CG solver the context will use with the current tuning: kind 0 = streaming kernels, 1 = on-chip, one CTA
@@ -98,6 +101,12 @@ int tb_plan_schedule(const int *est, const int *status, int nchains, int machine
 /* Upload angles A and build the link fields W_mu = s * 1/2 * eta_mu * exp(iA_mu) once (replaces the
  * sin/cos re-evaluated inside every apply, hmc.c:140-141,152-153,163-164,173-174). */
 int tb_set_gauge(tb_ctx *ctx, const double *A_host);
+
+/* Links from cos / sin evaluated by the caller's libm: trig_t_host / trig_x_host = double[nchains][NT][NX][2] holding
+ * (cos A_t, sin A_t) and (cos A_x, sin A_x).  The links are then bit for bit what hmc.c:140-174 computes on the host
+ * (the device's sincos may differ from glibc's in the last bit), which together with the strict solver
+ * (tb_set_tuning solver = 5) reproduces fmdm_invert_cg's recursion exactly.  The stored angles are not updated. */
+int tb_set_links_trig(tb_ctx *ctx, const double *trig_t_host, const double *trig_x_host);
 
 /* Family B (vec_ops.c behind Thirring.h): occupation field int[nchains][NT][NX], 0 = free site (vec_ops.c:107).
  * Replaces the gauge field: the links become the real constants s*1/2*eta masked by the field (a hop into or out
@@ -225,6 +234,10 @@ int tb_checkpoint_next_trajectory(const tb_ctx *ctx, unsigned int *next_traj);
 /* Counters for bench.py: kernels launched by this context since creation / since the last reset. */
 long long tb_launch_count(const tb_ctx *ctx);
 int tb_reset_launch_count(tb_ctx *ctx);
+
+/* FP64 FMA issue rate of the context's device in TFLOP/s (a kernel of independent DFMA chains, best of `repeats`
+ * launches, CUDA events): the measured denominator for the on-chip solvers, which are bound by FP64 issue. */
+int tb_measure_fp64_peak(tb_ctx *ctx, int repeats, double *tflops_out);
 
 /* Milliseconds the device spent in the last tb_cg_dev/tb_invert_dev call (CUDA events on the context stream). */
 double tb_last_solve_ms(const tb_ctx *ctx);

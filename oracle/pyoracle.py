@@ -59,6 +59,8 @@ class Oracle:
         L.orc_fm_conjugate_mul.argtypes = [ii, ii, dd, dd, ii, _dp, _dp, _dp]
         L.orc_fmdm_invert_cg.argtypes = [ii, ii, dd, dd, ii, _dp, _dp, _dp, ii, C.POINTER(ii), _dp]
         L.orc_fmdm_invert_cg.restype = ii
+        L.orc_fmdm_invert_cg_treesum.argtypes = L.orc_fmdm_invert_cg.argtypes
+        L.orc_fmdm_invert_cg_treesum.restype = ii
         L.orc_fm_invert_cg.argtypes = L.orc_fmdm_invert_cg.argtypes
         L.orc_fm_invert_cg.restype = ii
         L.orc_fermion_matrix.argtypes = [ii, ii, dd, dd, _dp, _dp]
@@ -104,13 +106,14 @@ class Oracle:
         self.lib.orc_fm_conjugate_mul(nt, nx, m, mu, mode, _p(v), _p(out), _p(A))
         return out
 
-    def fmdm_invert_cg(self, b, A, m, mu, mode, max_iter=0):
-        """Returns (x, status, iterations, final rr)."""
+    def fmdm_invert_cg(self, b, A, m, mu, mode, max_iter=0, treesum=False):
+        """Returns (x, status, iterations, final rr).  treesum: NOT the reference's arithmetic; the loop's two dot
+        products are summed as a pairwise tree, to measure what the summation order alone does to the iteration count."""
         b, A, nt, nx = self._prep(b, A)
         x = np.empty_like(b)
         it, rr = C.c_int(0), C.c_double(0)
-        st = self.lib.orc_fmdm_invert_cg(nt, nx, m, mu, mode, _p(b), _p(x), _p(A), max_iter,
-                                         C.byref(it), C.byref(rr))
+        fn = self.lib.orc_fmdm_invert_cg_treesum if treesum else self.lib.orc_fmdm_invert_cg
+        st = fn(nt, nx, m, mu, mode, _p(b), _p(x), _p(A), max_iter, C.byref(it), C.byref(rr))
         return x, st, it.value, rr.value
 
     def fm_invert_cg(self, v, A, m, mu, mode, max_iter=0):

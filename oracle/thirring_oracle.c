@@ -108,14 +108,38 @@ void orc_fm_conjugate_mul(int nt, int nx, double m, double mu, int mode,
  * number of loop passes executed (k at exit; 0 for the zero-source early return) and the last ||r||^2.
  * The reference prints "Cannot invert fermion matrix" and exit(1)s on divergence (hmc.c:383-388); the
  * oracle returns ORC_CG_DIVERGED instead so a test can observe it. */
+/* Sum of n terms: sequentially in index order as the reference does (tree = 0), or as a balanced pairwise tree
+ * (tree = 1).  The tree is NOT the reference's arithmetic: it exists so that a test can attribute the 1-3 iterations
+ * by which a parallel reduction moves the ||r||^2 < 1e-30 crossing of a 700+ iteration solve to the summation order
+ * alone (same recursion, same per-site arithmetic, only the two dot products of the loop summed differently). */
+static double sum_terms(double *t, int n, int tree)
+{
+  if (!tree) { double s = 0; for (int i = 0; i < n; i++) s += t[i]; return s; }
+  for (; n > 1; n = (n + 1) / 2) for (int i = 0; i < n / 2; i++) t[i] = t[i] + t[i + (n + 1) / 2];
+  return t[0];
+}
+
+static int cg_impl(int nt, int nx, double m, double mu, int mode, const double *b_, double *x_,
+                   const double *A, int max_iter, int *iters, double *rr_final, int tree);
+
 int orc_fmdm_invert_cg(int nt, int nx, double m, double mu, int mode, const double *b_, double *x_,
                        const double *A, int max_iter, int *iters, double *rr_final)
+{ return cg_impl(nt, nx, m, mu, mode, b_, x_, A, max_iter, iters, rr_final, 0); }
+
+/* the same recursion with the loop's two dot products summed as a pairwise tree (see sum_terms) */
+int orc_fmdm_invert_cg_treesum(int nt, int nx, double m, double mu, int mode, const double *b_, double *x_,
+                               const double *A, int max_iter, int *iters, double *rr_final)
+{ return cg_impl(nt, nx, m, mu, mode, b_, x_, A, max_iter, iters, rr_final, 1); }
+
+static int cg_impl(int nt, int nx, double m, double mu, int mode, const double *b_, double *x_,
+                   const double *A, int max_iter, int *iters, double *rr_final, int tree)
 {
   const int V = nt * nx;
   const cplx *b = (const cplx *)b_;
   cplx *xo = (cplx *)x_;
   cplx *r = malloc(sizeof(cplx) * V), *p = malloc(sizeof(cplx) * V);
   cplx *Mp = malloc(sizeof(cplx) * V), *MMp = malloc(sizeof(cplx) * V);
+  double *term = malloc(sizeof(double) * V);
   double rr = 0, rr_old = 0, rr_init, pMp, a;
   int status = ORC_CG_MAXITER, k = 0;
   if (max_iter <= 0) max_iter = ORC_CG_MAX_ITER;
@@ -133,13 +157,13 @@ int orc_fmdm_invert_cg(int nt, int nx, double m, double mu, int mode, const doub
   for (k = 1; k < max_iter; k++) {                                 /* hmc.c:364 */
     apply(nt, nx, m, mu, 0, p, Mp, A);                             /* hmc.c:366 */
     apply(nt, nx, m, mu, mode == ORC_MODE_ADJOINT, Mp, MMp, A);    /* hmc.c:367 */
-    pMp = 0;
-    for (int i = 0; i < V; i++) pMp += p[i].re * MMp[i].re + p[i].im * MMp[i].im;   /* hmc.c:369-370 */
+    for (int i = 0; i < V; i++) term[i] = p[i].re * MMp[i].re + p[i].im * MMp[i].im;   /* hmc.c:369-370 */
+    pMp = sum_terms(term, V, tree);
     a = rr_old / pMp;
     for (int i = 0; i < V; i++) { xo[i].re += a * p[i].re; xo[i].im += a * p[i].im; }     /* :372-373 */
     for (int i = 0; i < V; i++) { r[i].re -= a * MMp[i].re; r[i].im -= a * MMp[i].im; }   /* :374-375 */
-    rr = 0;
-    for (int i = 0; i < V; i++) rr += r[i].re * r[i].re + r[i].im * r[i].im;              /* :377-379 */
+    for (int i = 0; i < V; i++) term[i] = r[i].re * r[i].re + r[i].im * r[i].im;          /* :377-379 */
+    rr = sum_terms(term, V, tree);
     if (rr < ORC_CG_ACCURACY) { status = ORC_CG_CONVERGED; break; }                       /* :381 */
     if (rr / rr_init > 1e10) { status = ORC_CG_DIVERGED; break; }                         /* :383 */
     double beta = rr / rr_old;                                                            /* :390 */
@@ -149,7 +173,7 @@ int orc_fmdm_invert_cg(int nt, int nx, double m, double mu, int mode, const doub
 done:
   if (iters) *iters = (status == ORC_CG_MAXITER) ? k - 1 : k;   /* loop passes executed */
   if (rr_final) *rr_final = rr;
-  free(r); free(p); free(Mp); free(MMp);
+  free(r); free(p); free(Mp); free(MMp); free(term);
   return status;
 }
 

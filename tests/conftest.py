@@ -10,6 +10,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: a full-size case (seconds of GPU time, tens of seconds of host time)")
 
 
 @pytest.fixture(scope="session")

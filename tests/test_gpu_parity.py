@@ -6,7 +6,8 @@ count within +-1 of the oracle and solution within 1e-12 l2-relative.
 import numpy as np
 import pytest
 
-from tests.util import APPLY_TOL, CG_SOL_TOL, assert_close, random_gauge, random_vector, smooth_gauge
+from tests.util import (APPLY_TOL, CG_SOL_TOL, assert_close, iteration_band, libm_cos_sin, random_gauge, random_vector,
+                        smooth_gauge)
 
 pytestmark = pytest.mark.gpu
 
@@ -120,6 +121,7 @@ def test_T4_cg_matches_oracle(oracle, nt, nx, nchains, mode, m, mu, width):
     A = random_gauge(rng, nchains, nt, nx) if width is None else smooth_gauge(rng, nchains, nt, nx, width)
     xi = random_vector(rng, nchains, nt, nx)
     ref = None
+    band = {}   # chain -> (shift of the reference's own recursion under tree summation, its count)
     with tb.Context(nt, nx, nchains, mode, m=m, mu=mu) as ctx:
         ctx.set_gauge(A)
         b = ctx.fm_conjugate_mul(xi)  # as random_pseudofermion does (hmc.c:418-436)
@@ -133,11 +135,15 @@ def test_T4_cg_matches_oracle(oracle, nt, nx, nchains, mode, m, mu, width):
             for c in range(nchains):
                 xo, st, it, rr = ref[c]
                 assert info.status[c] == st == tb.CG_CONVERGED
-                # +-1 (north_star) wherever the solve takes up to a few hundred iterations; at m = 0.01 (700-2600
-                # iterations, ||r||^2 falling ~2 % per iteration) 700+ iterations of differently rounded
-                # recursions (FMA contraction, tree sums) move the 1e-30 crossing by 1-3 iterations: 0.5 % there
-                tol_it = max(1, int(np.ceil(0.005 * it)))
-                assert abs(int(info.iters[c]) - it) <= tol_it, (solver, rows, c, info.iters[c], it)
+                # +-1 (north_star).  Where a solve takes 700+ iterations (m = 0.01) a tree-summed dot product moves the
+                # ||r||^2 < 1e-30 crossing of the REFERENCE'S OWN recursion by 1-3 iterations (measured per input by
+                # iteration_band with the oracle); a parallel solver gets +-1 on top of that shift, nothing else, and
+                # the strict solver must hit the reference's count exactly (test_gpu_strict.py)
+                d = abs(int(info.iters[c]) - it)
+                if d > 1:
+                    if c not in band:
+                        band[c] = iteration_band(oracle, b[c], A[c], m, mu, mode, it)
+                    assert d <= band[c][0] + 1, (solver, rows, c, int(info.iters[c]), it, band[c])
                 assert_close(x[c], xo, CG_SOL_TOL, f"solver {solver} rows {rows} chain {c}")
                 assert info.rr[c] < 1e-30
 

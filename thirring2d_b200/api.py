@@ -137,6 +137,15 @@ class Context:
         assert A.shape == (self.nchains, self.nt, self.nx, 2), A.shape
         check(self.lib.tb_set_gauge(self._h, A.ctypes.data), "tb_set_gauge")
 
+    def set_links_trig(self, trig_t, trig_x):
+        """Links from the caller's cos / sin: float64 (nchains, NT, NX, 2) = (cos A, sin A) per direction."""
+        tt = np.ascontiguousarray(trig_t, dtype=np.float64)
+        tx = np.ascontiguousarray(trig_x, dtype=np.float64)
+        if tt.ndim == 3:
+            tt, tx = tt[None], tx[None]
+        assert tt.shape == tx.shape == (self.nchains, self.nt, self.nx, 2), tt.shape
+        check(self.lib.tb_set_links_trig(self._h, tt.ctypes.data, tx.ctypes.data), "tb_set_links_trig")
+
     def set_occupancy(self, field):
         """Family B (vec_ops.c): occupation field (nchains, NT, NX) ints, 0 = free.  Call set_params first."""
         field = np.ascontiguousarray(field, dtype=np.int32)
@@ -352,6 +361,12 @@ class Context:
 
     def reset_launch_count(self):
         self.lib.tb_reset_launch_count(self._h)
+
+    def measure_fp64_peak(self, repeats=5):
+        """FP64 FMA rate of the device in TFLOP/s (independent DFMA chains): the on-chip solvers' roofline denominator."""
+        tf = C.c_double(0.0)
+        check(self.lib.tb_measure_fp64_peak(self._h, repeats, C.byref(tf)), "tb_measure_fp64_peak")
+        return tf.value
 
     @property
     def last_solve_ms(self):

@@ -397,7 +397,7 @@ extern "C" int tb_apply_dev(tb_ctx *ctx, int op, const double *d_in, double *d_o
 
 // 0 = streaming, 1 = one CTA per chain (tb_resident.cu), 2 = one thread-block cluster per chain (tb_cluster.cu)
 static int onchip_solver(tb_ctx *ctx) {
-  if (ctx->tune_solver == 1) return 0;
+  if (ctx->tune_solver == 1 || ctx->tune_solver == 5) return 0;
   if (tb_resident_supported(ctx)) return 1;
   if (tb_cluster_supported(ctx)) return 2;
   return 0;
@@ -416,6 +416,7 @@ int tb_run_cg_any(tb_ctx *ctx, const double2 *b, double2 *x) {
     return TB_EINVAL;
   }
   if (onchip) TB_CHECK(run_onchip_slice(ctx, onchip, b, x, 0, ctx->C, ctx->stream));
+  else if (ctx->tune_solver == 5) TB_CHECK(tb_run_cg_strict(ctx, b, x));   // the reference's own evaluation order
   else TB_CHECK(tb_run_cg_stream(ctx, b, x));
   TB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
   TB_CUDA(cudaEventSynchronize(ctx->ev1));
@@ -552,6 +553,24 @@ extern "C" int tb_set_gauge(tb_ctx *ctx, const double *A_host) {
     sub_range(ctx, s, &c0, &n);
     if (n) TB_CHECK(tb_launch_links_slice(ctx, ctx->Adev, c0, n, ctx->sub_stream[s]));
   }
+  ctx->msite = nullptr;
+  ctx->have_gauge = true;
+  return TB_OK;
+}
+
+// Links from cos / sin of the angles computed by the CALLER (its libm), canonical layout double[nchains][NT][NX][2] =
+// (cos A_mu, sin A_mu) per direction: the links are then bit for bit what hmc.c:140-174 evaluates on the host, which
+// with the strict solver (tb_set_tuning solver = 5) makes the whole CG recursion the reference's.  The stored angles
+// are not touched: use it for solves and applies, not in front of the device-resident trajectory.
+extern "C" int tb_set_links_trig(tb_ctx *ctx, const double *trig_t_host, const double *trig_x_host) {
+  if (!ctx || !trig_t_host || !trig_x_host) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(upload_vec(ctx, trig_t_host, ctx->vin));
+  TB_CHECK(join_subs(ctx));
+  TB_CUDA(cudaStreamSynchronize(ctx->stream));   // the staging buffer is reused by the second upload
+  TB_CHECK(upload_vec(ctx, trig_x_host, ctx->vout));
+  TB_CHECK(join_subs(ctx));
+  TB_CHECK(tb_launch_links_from_trig(ctx, ctx->vin, ctx->vout));
   ctx->msite = nullptr;
   ctx->have_gauge = true;
   return TB_OK;

@@ -198,6 +198,8 @@ int tb_launch_occupancy(tb_ctx *ctx, const int *d_field_canonical);
 int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out);
 int tb_slab_layout(tb_ctx *ctx);
 int tb_run_cg_any(tb_ctx *ctx, const double2 *b, double2 *x);
+int tb_run_cg_strict(tb_ctx *ctx, const double2 *b, double2 *x);   // tb_strict.cu: reference evaluation order
+int tb_launch_links_from_trig(tb_ctx *ctx, const double2 *T0, const double2 *T1);
 void tb_hmc_release(tb_ctx *ctx);
 int tb_create_common(tb_ctx **out, int nt_local, int nx, int nchains, int mode, int device, int rank, int nranks,
                      int nt_global);

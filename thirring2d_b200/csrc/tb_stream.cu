@@ -992,6 +992,12 @@ __device__ __forceinline__ unsigned long long global_ns() {
   return t;
 }
 
+// Release / acquire fences of the synchronisation points.  __threadfence() and __threadfence_system() are the
+// sequentially consistent fences (MEMBAR.SC); the hand-overs below are plain release -> acquire chains, for which
+// fence.acq_rel (MEMBAR.ALL) is what the PTX memory model asks for, and a synchronisation point is a chain of six of them.
+__device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;\n" ::: "memory"); }
+
 struct ChainScalars {   // CG scalars of the thread's chain (c = threadIdx.x & (bc - 1)), identical in every block
   double rr_old, rr_init, rr, alpha, beta;
   int active, iters, status;
@@ -1043,7 +1049,7 @@ __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, co
   for (int o = 16; o >= g.bc; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   __syncthreads();   // red may still be read by the previous call
   if (lane < g.bc) red[warp * g.bc + lane] = acc;
-  __threadfence();   // this thread's field stores are visible device-wide before the block's arrival is counted
+  fence_gpu();   // this thread's field stores are visible device-wide before the block's arrival is counted
   __syncthreads();
   if (stamp) atomicMax(&tl[1], global_ns());
   if (warp == 0) {
@@ -1051,7 +1057,7 @@ __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, co
       double t = 0.0;
       for (int w = 0; w < nwarp; w++) t += red[w * g.bc + lane];
       __stcg(&s.partial[(size_t)blockIdx.x * g.Cpad + lane], t);
-      __threadfence();
+      fence_gpu();
     }
     __syncwarp();
     if (lane == 0) {
@@ -1062,7 +1068,7 @@ __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, co
   __syncthreads();
   const bool last = s_last != 0;   // block-uniform: this block arrived last, every other block's partial and rows are visible
   if (last) {
-    __threadfence();
+    fence_gpu();
     double sum = 0.0;
     for (int blk = x_local; blk < (int)gridDim.x; blk += g.bx) sum += __ldcg(&s.partial[(size_t)blk * g.Cpad + c_local]);
     const double mine = block_sum_chains(sum, g, red);   // threads < bc
@@ -1071,7 +1077,7 @@ __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, co
     __syncthreads();
     const int nrep_out = mode == 2 ? sl.nrep : 1;
     const int nst = sl.P * nrep_out * g.bc;
-    if (tid < nst) __threadfence_system();   // this GPU's halo rows before the tag, for the peers
+    if (tid < nst) fence_sys();   // this GPU's halo rows before the tag, for the peers
     for (int i = tid; i < nst; i += blockDim.x) {
       const int c = i & (g.bc - 1), k = i >> g.bc_shift, rep = k % nrep_out, q = k / nrep_out;
       const double v = red[c];
@@ -1096,14 +1102,14 @@ __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, co
         if (mode == 2) __nanosleep(20);
         if (clock64() - t0 > TB_PERSIST_SPIN_CYCLES) __trap();   // a launch error on this rank instead of a hung box
       }
-      __threadfence_system();   // acquire side: the neighbours' rows behind their tags
+      fence_sys();   // acquire side: the neighbours' rows behind their tags
       red[tid] = theirs;        // [q][chain]
     }
     __syncthreads();
     total = 0.0;
     for (int r = 0; r < sl.P; r++) total += red[r * g.bc + c_local];   // rank order: the same bits on every rank
     if (mode != 2 && tid < sl.nrep * g.bc) {   // publish the totals to the other blocks of this GPU
-      __threadfence();
+      fence_gpu();
       st_volatile_v2(sl.bcast + (size_t)(tid >> g.bc_shift) * sl.bcast_stride + (size_t)RED * g.Cpad + c_local,
                      __double_as_longlong(total), __double_as_longlong(total) ^ tag);
     }
@@ -1119,7 +1125,7 @@ __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, co
         __nanosleep(20);
         if (clock64() - t0 > TB_PERSIST_SPIN_CYCLES) __trap();
       }
-      __threadfence();   // acquire: this GPU's rows (the publisher saw every arrival) and, through it, the neighbours'
+      fence_gpu();   // acquire: this GPU's rows (the publisher saw every arrival) and, through it, the neighbours'
       red[tid] = v;
     }
     __syncthreads();

@@ -32,6 +32,7 @@ SIGNATURES = {
     "tb_solver_info": (_i, [_vp, _ip, _ip]),
     "tb_plan_schedule": (_i, [_ip, _ip, _i, _i, _ip, _ip, _ip]),
     "tb_set_gauge": (_i, [_vp, _vp]),
+    "tb_set_links_trig": (_i, [_vp, _vp, _vp]),
     "tb_set_occupancy": (_i, [_vp, _vp]),
     "tb_apply": (_i, [_vp, _i, _vp, _vp]),
     "tb_cg": (_i, [_vp, _vp, _vp, _ip, _ip, _dp]),
@@ -66,6 +67,7 @@ SIGNATURES = {
     "tb_launch_count": (C.c_longlong, [_vp]),
     "tb_reset_launch_count": (_i, [_vp]),
     "tb_last_solve_ms": (_d, [_vp]),
+    "tb_measure_fp64_peak": (_i, [_vp, _i, _dp]),
 }
 
 
