@@ -250,6 +250,17 @@ def gpu_arm(args):
     barrier()
     launches = ctx.launch_count
     ms_total = e0.elapsed_time(e1)
+    # The timed steps re-solve the same sources, so the planned launch (tb_onchip.cuh: TbPlan) has exact iteration counts
+    # from the warm-up: its best case.  A first solve, or a solve after the field moved, has no or stale estimates; the
+    # plain launch (one CTA per chain, two waves) is what it costs then.
+    os.environ["TB_NO_PLAN"] = "1"
+    plain_ms = []
+    for _ in range(4):
+        plain_ms.append(step())
+    del os.environ["TB_NO_PLAN"]
+    plain_ms = float(np.mean(plain_ms[1:]))
+    step()   # planned again, so that x below is the timed solve's
+    fp64_peak = ctx.measure_fp64_peak(5)
 
     # e2e: the host-buffer C-ABI entry points a reference-side caller binds
     def e2e_step():   # new angles + solve, as at every leapfrog step of momentum_step (hmc.c:504-516)
@@ -297,12 +308,12 @@ def gpu_arm(args):
         hmc_s = time.perf_counter() - t0
         hmc = (hmc_s, acc_sum / args.traj, it_sum / (args.traj * chains * (HMC_NSTEPS + 1)))
 
-    t = torch.tensor([ms_total, e2e_s * 1e3, solve_ms, hmc[0] if hmc else 0.0], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_s * 1e3, solve_ms, hmc[0] if hmc else 0.0, plain_ms], dtype=torch.float64, device=dev)
     cnt = torch.tensor([applies_per_step, launches], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-    ms_total, e2e_ms, solve_ms, hmc_s = t.tolist()
+    ms_total, e2e_ms, solve_ms, hmc_s, plain_ms = t.tolist()
     applies_all, launches_all = cnt.tolist()
 
     stream_roof = None
@@ -330,14 +341,23 @@ def gpu_arm(args):
                        if resident else "CG iteration (dslash, dslash+dot, axpy+norm, xpay)")
         regime = ("cache-resident: state on chip, frac > 1 is expected; HBM traffic = `traffic`"
                   if resident else "streaming")
-        traffic = None
+        traffic, traffic_src = None, None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get("resident_cg_kernel" if resident else "streaming_iteration")
+            tj = json.load(open(tp))
+            traffic = tj.get("resident_cg_kernel" if resident else "streaming_iteration")
+            traffic_src = (tj.get(("resident_cg_kernel" if resident else "streaming_iteration") + "_source", "")
+                           + " -- from a committed ncu --set full capture, NOT measured in this run")
+        fp64_tflops = 88 * NT * NX * float(iters.sum()) * args.steps / (solve_ms * 1e-3) / 1e12
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": solve_ms / args.steps,
-            "ms_per_step_incl_l2_flush": ms_total / args.steps, "higher_is_better": True,
+            "ms_per_step_incl_l2_flush": ms_total / args.steps,
+            "ms_per_step_plain_launch": plain_ms,
+            "planner_note": "value / ms_per_step: planned launch with the iteration counts of the previous solve of the "
+                            "same sources (its best case); ms_per_step_plain_launch: one CTA per chain without a plan, "
+                            "what a first solve or a solve on a moved field costs; the hmc figure below has the real mix",
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(chains), "lattice": [NT, NX], "chains_per_gpu": chains,
                        "mode": "ADJOINT", "m": MASS, "mu": MU, "g": G, "cg_accuracy": 1e-30,
@@ -345,16 +365,21 @@ def gpu_arm(args):
                        "l2": "256 MiB flush buffer written before every timed step, outside the per-step CUDA-event pair"},
             "site_applies_per_sec": value * NT * NX,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "kernel": kernel_name, "regime": regime,
-                         "algorithmic_bytes_per_launch": alg_bytes_per_step / launches_per_step,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "kernel": kernel_name, "regime": regime,
+                         # the solver kernel runs once per step (the one-block plan_kernel in front of it moves no
+                         # lattice data); streaming: per launch of the 3 kernels of an iteration
+                         "algorithmic_bytes_per_launch": alg_bytes_per_step if resident
+                         else alg_bytes_per_step / launches_per_step,
                          "algorithmic_bytes_per_site_iteration": BYTES_PER_SITE_ITER,
                          "us_per_iteration": solve_ms * 1e3 / args.steps / max_it, "sites": sites,
                          # what actually bounds the on-chip kernel (ncu: FP64 pipe), for orientation only: 34
                          # useful flops per site and apply + 20 for the fused BLAS-1
-                         "fp64": {"achieved_tflops": 88 * NT * NX * float(iters.sum()) * args.steps
-                                  / (solve_ms * 1e-3) / 1e12,
-                                  "nominal_peak_tflops": 37.0, "peak_source": "B200 datasheet FP64 (not measured)"}},
+                         "fp64": {"achieved_tflops": fp64_tflops, "measured_peak_tflops": fp64_peak,
+                                  "frac_of_measured": fp64_tflops / fp64_peak if fp64_peak > 0 else None,
+                                  "flops_per_site_iteration": 88,
+                                  "peak_source": "tb_measure_fp64_peak: independent DFMA chains on every SM, best of 5 "
+                                                 "launches, in this run"}},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(A_host.nbytes + b_host.nbytes),
                     "d2h_bytes_per_step": int(x_host.nbytes), "ms_per_step": e2e_ms / args.steps,
                     "pinned_copy_rates_measured": pcie,
@@ -380,6 +405,7 @@ def gpu_arm(args):
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"{nch} chain solves of the same workload ({NT}x{NX}, m={MASS}), "
                                               f"{cores} single-threaded processes, {busy:.1f} s"}
+            line["parity_checked"] = parity_check(torch, tb, ctx, x, A_np, b_host, info, chains)
             # also one core, and the flags the reference ships with (Makefile:2, no optimisation)
             v1 = run_cpu_reference(4, 1)
             line["cpu_baseline"]["one_core"] = {"value": v1[0], "sample": f"{v1[4]} chain solves, -O3"}
@@ -397,6 +423,29 @@ def gpu_arm(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def parity_check(torch, tb, ctx, x, A_np, b_host, info, chains):
+    """Outside the timed region: three of the headline chains against the CPU checker (the oracle port, bit-identical
+    to the compiled reference) on the very inputs and solutions of the timed solves."""
+    from oracle.pyoracle import MODE_ADJOINT, Oracle   # the checker, never the thing measured
+
+    orc = Oracle()
+    xc = torch.empty_like(x)
+    ctx.unpack_dev(x.data_ptr(), xc.data_ptr())
+    xh = xc.cpu().numpy().view(np.complex128).reshape(chains, NT, NX)
+    bh = b_host.numpy().view(np.complex128).reshape(chains, NT, NX)
+    out = {"chains": [], "iters_gpu": [], "iters_reference": [], "solution_rel_l2": []}
+    for c in sorted({0, chains // 2, chains - 1}):
+        xo, st, it, rr = orc.fmdm_invert_cg(bh[c], A_np[c], MASS, MU, MODE_ADJOINT)
+        out["chains"].append(int(c))
+        out["iters_gpu"].append(int(info.iters[c]))
+        out["iters_reference"].append(int(it))
+        out["solution_rel_l2"].append(float(np.linalg.norm(xh[c] - xo) / np.linalg.norm(xo)))
+    out["ok"] = bool(all(abs(a - b) <= 1 for a, b in zip(out["iters_gpu"], out["iters_reference"]))
+                     and max(out["solution_rel_l2"]) <= 1e-12)
+    out["tolerance"] = "iterations +-1, solution 1e-12 l2-relative (north_star, SURVEY Appendix C)"
+    return out
 
 
 def streaming_roofline(tb, torch, dev, stream):
@@ -423,10 +472,14 @@ def streaming_roofline(tb, torch, dev, stream):
     it = int(info.iters.max())
     ctx.close()
     t = min(ms) * 1e-3
-    ach = BYTES_PER_SITE_ITER * nt * nx * chains * it / t / 1e9
-    return {"bound": "hbm", "kernel": "streaming CG iteration (dslash, dslash+dot, axpy+norm, xpay)",
+    # the fused ADJOINT iteration moves 240 B per site (K1 64 + the fused M^dagger / update pass 128 + K4 48): that is
+    # `achieved`; SURVEY 8(d)'s accounting of the unfused design (288 B) is reported beside it
+    ach = 240 * nt * nx * chains * it / t / 1e9
+    ach288 = BYTES_PER_SITE_ITER * nt * nx * chains * it / t / 1e9
+    return {"bound": "hbm", "kernel": "streaming CG iteration (dslash+|Mp|^2, dslash^dagger+axpy+norm, xpay)",
             "workload": f"{nt}x{nx} x {chains} chains, {it} iterations, working set 470 MB > L2",
-            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+            "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes_per_site_iteration": 240,
+            "achieved_288B_definition": ach288, "frac_288B_definition": ach288 / peak,
             "us_per_iteration": t * 1e6 / it}
 
 
@@ -509,21 +562,20 @@ def slab_config(tb, torch, dist, dev, stream, rank, world, n, peak, iters=200, m
                     "path); device time, max over ranks"}
 
 
-def cpu_port_apply_rate(nt, nx, m, iters):
-    """Dirac applies/s of the CPU path on ONE host core at a lattice size where a full reference solve would take
-    minutes to hours (SURVEY 8(c) caveat 4): `iters` CG iterations of the oracle port of fmdm_invert_cg (bit-identical
-    to the reference's, tests/test_oracle_pinned.py), which re-evaluates sin/cos in every apply like hmc.c:140-174."""
-    from oracle.pyoracle import MODE_ADJOINT, Oracle
-
-    orc = Oracle()
-    rng = np.random.default_rng(7)
-    A = rng.uniform(-np.pi, np.pi, size=(nt, nx, 2))
-    b = rng.normal(size=(nt, nx)) + 1j * rng.normal(size=(nt, nx))
-    t0 = time.perf_counter()
-    orc.fmdm_invert_cg(b, A, m, 0.0, MODE_ADJOINT, iters + 1)
-    dt = time.perf_counter() - t0
-    return {"dirac_applies_per_sec": 2 * iters / dt, "cores": 1, "kind": "port",
-            "sample": f"{iters} CG iterations of one {nt}x{nx} chain, {dt:.1f} s"}
+def cpu_apply_rate(nt, nx, m, g, iters):
+    """Dirac applies/s of the reference's CPU path on ONE host core at a lattice size where a full solve would take
+    minutes to hours (SURVEY 8(c) caveat 4): `iters` CG iterations of the reference's own fmdm_invert_cg, compiled from
+    the unmodified hmc.c with CG_MAX_ITER rewritten to iters + 1 (oracle/build_ref.sh, libhmcref_*_it<N>.so; max-iter is
+    silent, hmc.c:364); the oracle port (bit-identical, tests/test_oracle_pinned.py) when that object is absent."""
+    p = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", "--nt", str(nt), "--nx", str(nx), "--chains", "1",
+                        "--m", str(m), "--mu", "0.0", "--g", str(g), "--flavour", f"adjoint_it{iters + 1}",
+                        "--max-iter", str(iters + 1)], cwd=ROOT, capture_output=True, text=True)
+    try:
+        o = json.loads(p.stdout.strip().splitlines()[-1])
+    except Exception:
+        return {"error": (p.stderr or p.stdout)[-300:]}
+    return {"dirac_applies_per_sec": o["applies"] / o["seconds"], "cores": 1, "kind": o["kind"],
+            "sample": f"{o['iters']} CG iterations of one {nt}x{nx} chain, {o['seconds']:.1f} s"}
 
 
 def other_configs(tb, torch, dist, dev, stream, rank, world, cpu=True):
@@ -586,7 +638,7 @@ def other_configs(tb, torch, dist, dev, stream, rank, world, cpu=True):
         "hmc": {"traj_per_sec": world * chains / traj_s, "ms_per_batched_trajectory": 1e3 * traj_s, "nsteps": 10,
                 "cg_iters_per_solve": float(traj_its) / (chains * 11)}}
     if world == 1 and cpu:
-        out["256x256_m0.01_g1_8_chains_per_gpu"]["cpu_baseline"] = cpu_port_apply_rate(256, 256, 0.01, 40)
+        out["256x256_m0.01_g1_8_chains_per_gpu"]["cpu_baseline"] = cpu_apply_rate(256, 256, 0.01, 1.0, 40)
 
     # configs[4]: coupling/mass scan, 32 (g, m) points x 64 chains on 128x128, chiral condensate measurement.
     # 4 points (256 chains) per GPU; per-chain m and g; condensate from stochastic sources through fm_invert_cg.
@@ -718,7 +770,7 @@ def other_configs(tb, torch, dist, dev, stream, rank, world, cpu=True):
             out[key] = {"error": f"{type(e).__name__}: {e}"[:300]}
             break
     if world == 1 and cpu and "error" not in out["2048x2048_single_lattice_1_gpu"]:
-        out["2048x2048_single_lattice_1_gpu"]["cpu_baseline"] = cpu_port_apply_rate(2048, 2048, 0.05, 2)
+        out["2048x2048_single_lattice_1_gpu"]["cpu_baseline"] = cpu_apply_rate(2048, 2048, 0.05, 1.0, 2)
     return out
 
 

@@ -24,14 +24,18 @@ if [ ! -f "$REF/hmc.c" ]; then
   exit 0
 fi
 
-build_one() { # NT NX flavour [nsteps] [shipped]
-  local nt=$1 nx=$2 fl=$3 ns=${4:-10} opt=$OPT
+build_one() { # NT NX flavour [nsteps] [shipped|-] [CG_MAX_ITER]
+  local nt=$1 nx=$2 fl=$3 ns=${4:-10} opt=$OPT maxit=${6:-}
   local name="libhmcref_${nt}x${nx}_${fl}"
+  [ -n "$maxit" ] && name="${name}_it${maxit}"
   [ "$ns" != 10 ] && name="${name}_ns${ns}"
   # the reference's own CFLAGS (Makefile:5 "-march=native -std=c99 -g", i.e. no optimisation); x86-64-v3 instead of
   # native so that the object also runs on the GPU box's host CPU
   if [ "${5:-}" = shipped ]; then name="${name}_shipped"; opt="-march=x86-64-v3 -g"; fi
   local sedprog="s/^#define NT 32/#define NT ${nt}/; s/^#define NX 32/#define NX ${nx}/; s/int nsteps = 10;/int nsteps = ${ns};/"
+  # bounded CPU baselines at sizes where a full solve takes minutes to hours: "#define CG_MAX_ITER 100000" (hmc.c:35)
+  # rewritten, so the reference's own fmdm_invert_cg runs N - 1 iterations and returns (max-iter is silent, hmc.c:364)
+  [ -n "$maxit" ] && sedprog="$sedprog; s/^#define CG_MAX_ITER 100000/#define CG_MAX_ITER ${maxit}/"
   if [ "$fl" = adjoint ]; then
     sedprog="$sedprog; 197,248{s/v += 0\\.5/v @@ 0.5/; s/v -= 0\\.5/v += 0.5/; s/v @@ 0\\.5/v -= 0.5/; s/expmmu/EXPTMP/; s/expmu/expmmu/; s/EXPTMP/expmu/}"
   fi
@@ -51,6 +55,9 @@ build_one 32 32 adjoint 40
 build_one 64 64 adjoint 40
 # CPU baseline at the flags the reference ships with
 build_one 64 64 adjoint 10 shipped
+# bounded CPU baselines of the large configurations: 40 iterations at 256^2, 2 at 2048^2 (bench.py other_configs)
+build_one 256 256 adjoint 10 - 41
+build_one 2048 2048 adjoint 10 - 3
 # family B: vec_ops.c behind Thirring.h (sizes are unguarded #defines, Thirring.h:14-15).  The translation unit
 # is assembled on gcc's stdin: "#define MAIN" (so that the EXTERN globals of Thirring.h:54-76 are DEFINED here,
 # as the driver fermionbag.c does), the size-rewritten header, then vec_ops.c without its own #include.

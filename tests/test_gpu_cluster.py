@@ -122,9 +122,13 @@ def test_cluster_device_resident_invert_and_condensate():
         cond, iters = ctx.hmc_condensate(nsrc=4, seed=3)
     k = (2 * np.arange(nt) + 1) * np.pi / nt
     s = np.sin(k) ** 2
-    want = float((m / (m * m + s[:, None] + s[None, :])).mean())
-    err = cond.std(ddof=1) / np.sqrt(n)
-    assert abs(cond.mean() - want) < 5 * err + 1e-4, (cond.mean(), want, err)
+    h = m / (m * m + s[:, None] + s[None, :])   # eigenvalues of the Hermitian part of M^-1 on the free field
+    want = float(h.mean())
+    # variance of the estimator for circular Gaussian sources with E|eta|^2 = 2: tr(H^2) / (V^2 nsrc) per chain (the
+    # spread of six chains is too poor an estimate of it to gate on)
+    err = float(np.sqrt((h * h).mean() / (nt * nx * 4) / n))
+    assert abs(cond.mean() - want) < 4 * err, (cond.mean(), want, err)
+    assert 0.2 * err * np.sqrt(n) < cond.std(ddof=1) < 3 * err * np.sqrt(n)   # chains draw different sources
 
 
 @pytest.mark.parametrize("nt,nx", [(128, 64), (128, 128)])
