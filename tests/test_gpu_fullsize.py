@@ -1,6 +1,8 @@
 """Parity at BASELINE.json's full sizes through size-independent properties (the oracle would need minutes to
 hours there): adjointness, linearity, the CG residual checked by an independent apply, agreement of the two
 solvers, and a checksum of the batched result against single-chain solves of a few sampled chains."""
+import os
+
 import numpy as np
 import pytest
 
@@ -113,3 +115,53 @@ def test_T1_apply_matches_oracle_at_full_size(oracle, nt, nx, nchains):
     for c in range(nchains):
         assert_close(got_m[c], oracle.fm_mul(v[c], A[c], m[c], mu[c]), APPLY_TOL, "M")
         assert_close(got_d[c], oracle.fm_conjugate_mul(v[c], A[c], m[c], mu[c], tb.MODE_ADJOINT), APPLY_TOL, "M^dagger")
+
+
+@pytest.mark.parametrize("n,mode,mu", [(200, tb.MODE_ADJOINT, 0.0), (3, tb.MODE_ADJOINT, 0.1), (5, tb.MODE_REF_COMPAT, 0.05)])
+def test_host_buffer_path_through_the_canonical_layout_kernel(oracle, n, mode, mu):
+    """tb_cg and tb_cg_gauge on a 64^2 context go host buffer -> H2D -> ONE kernel (canonical layout in and out, links
+    built inside from the angles) -> D2H per sub-batch of chains.  The result must be bitwise the device-resident
+    path's (pack -> links kernel -> solver -> unpack), the context must be left as tb_set_gauge leaves it (links and
+    angles), and a sample of chains is checked against the oracle.  200 chains: two waves on 148 SMs (4 + 4 sub-batches)."""
+    import torch
+
+    nt = nx = 64
+    m = 100.0 if mode == tb.MODE_REF_COMPAT else 0.2
+    rng = np.random.default_rng(n)
+    A = rng.uniform(-np.pi, np.pi, size=(n, nt, nx, 2))
+    A2 = rng.uniform(-np.pi, np.pi, size=(n, nt, nx, 2))
+    xi = rng.normal(size=(n, nt, nx)) + 1j * rng.normal(size=(n, nt, nx))
+    dev = torch.device("cuda", 0)
+    with tb.Context(nt, nx, n, mode, m=m, mu=mu) as ctx:
+        # device-resident reference: explicit re-layout kernels and links_kernel
+        A_dev = torch.from_numpy(A).to(dev)
+        ctx.set_gauge_dev(A_dev.data_ptr())
+        v_canon = torch.from_numpy(xi.view(np.float64)).to(dev)
+        v, b, x = (torch.empty(ctx.vec_doubles, dtype=torch.float64, device=dev) for _ in range(3))
+        ctx.pack_dev(v_canon.data_ptr(), v.data_ptr())
+        ctx.apply_dev(tb.OP_MCONJ, v.data_ptr(), b.data_ptr())
+        os.environ["TB_NO_PLAN"] = "1"
+        ctx.cg_dev(b.data_ptr(), x.data_ptr())
+        del os.environ["TB_NO_PLAN"]
+        it_dev = ctx.cg_result().iters.copy()
+        out = torch.empty_like(v_canon)
+        ctx.unpack_dev(b.data_ptr(), out.data_ptr())
+        b_host = out.cpu().numpy().view(np.complex128).reshape(n, nt, nx)
+        ctx.unpack_dev(x.data_ptr(), out.data_ptr())
+        x_dev = out.cpu().numpy().view(np.complex128).reshape(n, nt, nx)
+        # host-buffer entry points
+        ctx.set_gauge(A2)                                  # something else, so that cg_gauge has to install A
+        x1, i1 = ctx.fmdm_invert_cg_with_gauge(A, b_host)   # tb_cg_gauge: links built inside the solver kernel
+        assert np.array_equal(x1, x_dev) and np.array_equal(i1.iters, it_dev)
+        assert np.array_equal(ctx.get_gauge(), A)           # the context's angles ...
+        assert np.array_equal(ctx.fm_conjugate_mul(xi), b_host)   # ... and links are the new field's
+        x2, i2 = ctx.fmdm_invert_cg(b_host)                 # tb_cg: links from the context
+        assert np.array_equal(x2, x_dev) and np.array_equal(i2.iters, it_dev)
+        os.environ["TB_NO_CANON"] = "1"                     # the re-layout path stays available and agrees
+        x3, i3 = ctx.fmdm_invert_cg_with_gauge(A, b_host)
+        del os.environ["TB_NO_CANON"]
+        assert np.array_equal(x3, x_dev)
+    for c in sorted({0, n // 2, n - 1}):
+        xo, st, it, rr = oracle.fmdm_invert_cg(b_host[c], A[c], m, mu, mode)
+        assert abs(int(it_dev[c]) - it) <= 1
+        assert np.linalg.norm(x1[c] - xo) <= 1e-12 * np.linalg.norm(xo)

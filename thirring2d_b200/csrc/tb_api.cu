@@ -154,13 +154,36 @@ int tb_create_common(tb_ctx **out, int nt, int nx, int nchains, int mode, int de
     cudaEventCreate(&ctx->ev1);
     cudaEventCreateWithFlags(&ctx->ev_flag[0], cudaEventDisableTiming);
     cudaEventCreateWithFlags(&ctx->ev_flag[1], cudaEventDisableTiming);
-    // host-buffer pipeline: chains are processed in nsub sub-batches on their own streams
+    // host-buffer pipeline: chains are processed in nsub sub-batches on their own streams.  Where one CTA per chain
+    // serves the context (64^2) a batch larger than the SM count runs in waves of nsm chains: every wave is cut into
+    // pieces of its own, so that the first wave's CTAs start as their inputs arrive (256 chains on 148 SMs: 4 x 37, then
+    // 4 x 27) instead of 4 x 64, of which at most 128 fit the first wave.
     const char *es = getenv("TB_SUBBATCHES");
-    ctx->nsub = es ? atoi(es) : (ctx->C >= 128 ? 4 : (ctx->C >= 32 ? 2 : 1));
-    if (nranks > 1) ctx->nsub = 1;
-    if (ctx->nsub < 1) ctx->nsub = 1;
-    if (ctx->nsub > TB_MAX_SUB) ctx->nsub = TB_MAX_SUB;
-    if (ctx->nsub > ctx->C) ctx->nsub = ctx->C;
+    int nsm = TB_NUM_SMS_B200;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    const bool cta_per_chain = nranks == 1 && nt == 64 && nx == 64;
+    int nb = 0;
+    if (!es && cta_per_chain && ctx->C > nsm) {
+      const int waves = (ctx->C + nsm - 1) / nsm;
+      const int pieces = waves >= TB_MAX_SUB ? 1 : TB_MAX_SUB / waves;
+      for (int w = 0; w < waves && nb < TB_MAX_SUB; w++) {
+        const int lo = w * nsm, hi = (w + 1) * nsm < ctx->C ? (w + 1) * nsm : ctx->C;
+        const bool last_slot = w == waves - 1 || nb + pieces >= TB_MAX_SUB;   // the last pieces take whatever is left
+        const int end = last_slot && w < waves - 1 ? ctx->C : hi;
+        for (int q = 0; q < pieces && nb < TB_MAX_SUB; q++) ctx->sub_c0[nb++] = lo + (int)((long long)(end - lo) * q / pieces);
+        if (end == ctx->C) break;
+      }
+    } else {
+      int k = es ? atoi(es) : (ctx->C >= 128 ? 4 : (ctx->C >= 32 ? 2 : 1));
+      if (nranks > 1) k = 1;
+      if (k < 1) k = 1;
+      if (k > TB_MAX_SUB) k = TB_MAX_SUB;
+      if (k > ctx->C) k = ctx->C;
+      const int per = (ctx->C + k - 1) / k;
+      for (int q = 0; q < k && q * per < ctx->C; q++) ctx->sub_c0[nb++] = q * per;
+    }
+    ctx->nsub = nb;
+    ctx->sub_c0[nb] = ctx->C;
     cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming);
     for (int s = 0; s < ctx->nsub; s++) {
       cudaStreamCreateWithFlags(&ctx->sub_stream[s], cudaStreamNonBlocking);
@@ -213,10 +236,8 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
 
 // ---- sub-batch streams (host-buffer pipeline) -----------------------------------------------------------
 static void sub_range(const tb_ctx *ctx, int s, int *c0, int *n) {
-  const int per = (ctx->C + ctx->nsub - 1) / ctx->nsub;
-  *c0 = s * per;
-  int m = ctx->C - *c0;
-  *n = m < 0 ? 0 : (m < per ? m : per);
+  *c0 = ctx->sub_c0[s];
+  *n = ctx->sub_c0[s + 1] - ctx->sub_c0[s];
 }
 
 // sub-streams start after everything already queued on the context stream
@@ -606,6 +627,34 @@ extern "C" int tb_apply(tb_ctx *ctx, int op, const double *in_host, double *out_
   return download_vec(ctx, ctx->vout, out_host);
 }
 
+// Host buffers straight through the 64^2 on-chip kernel (tb_resident.cu, CANON): per sub-batch of chains one H2D copy
+// of the source (and of the angles, when the call brings a new gauge field), ONE kernel that reads and writes the
+// canonical layout and builds its own links, one D2H copy of the solution.  No re-layout or link kernel has to find a
+// free SM between the solver CTAs of the other sub-batches.
+static int solve_host_canon(tb_ctx *ctx, const double *A_host, const double *b_host, double *x_host) {
+  TB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+  TB_CHECK(fork_subs(ctx));
+  double2 *Ac = (double2 *)ctx->stage, *bc = ctx->vin, *xc = ctx->stage_x;   // canonical device staging
+  for (int s = 0; s < ctx->nsub; s++) {
+    int c0, n;
+    sub_range(ctx, s, &c0, &n);
+    if (n == 0) continue;
+    const size_t off = (size_t)c0 * ctx->V, bytes = (size_t)n * ctx->V * sizeof(double2);
+    cudaStream_t st = ctx->sub_stream[s];
+    if (A_host) TB_CUDA(cudaMemcpyAsync(Ac + off, (const double2 *)A_host + off, bytes, cudaMemcpyHostToDevice, st));
+    TB_CUDA(cudaMemcpyAsync(bc + off, (const double2 *)b_host + off, bytes, cudaMemcpyHostToDevice, st));
+    TB_CHECK(tb_run_cg_resident_canon(ctx, bc, xc, A_host ? Ac : nullptr, c0, n, st));
+    TB_CUDA(cudaMemcpyAsync((double2 *)x_host + off, xc + off, bytes, cudaMemcpyDeviceToHost, st));
+  }
+  TB_CHECK(sync_all(ctx));
+  TB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+  TB_CUDA(cudaEventSynchronize(ctx->ev1));
+  float ms = 0.f;
+  TB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  ctx->last_solve_ms = ms;
+  return TB_OK;
+}
+
 // the solve of a sub-batch starts as soon as ITS links and sources are on the device
 static int solve_host(tb_ctx *ctx, bool with_conj, const double *b_host, double *x_host, int *status, int *iters,
                       double *rr) {
@@ -616,7 +665,9 @@ static int solve_host(tb_ctx *ctx, bool with_conj, const double *b_host, double 
     tb_set_error("on-chip solver requested but %dx%d is not supported", ctx->nt, ctx->nx);
     return TB_EINVAL;
   }
-  if (!onchip || with_conj) {
+  if (onchip == 1 && !with_conj && tb_resident_canon_supported(ctx)) {
+    TB_CHECK(solve_host_canon(ctx, nullptr, b_host, x_host));
+  } else if (!onchip || with_conj) {
     TB_CHECK(upload_vec(ctx, b_host, ctx->vin));
     if (with_conj) TB_CHECK(tb_invert_dev(ctx, (const double *)ctx->vin, (double *)ctx->vout));
     else TB_CHECK(tb_cg_dev(ctx, (const double *)ctx->vin, (double *)ctx->vout));
@@ -653,6 +704,11 @@ extern "C" int tb_cg_gauge(tb_ctx *ctx, const double *A_host, const double *b_ho
   if (!onchip) {   // the streaming solver works on the whole batch at once: nothing to interleave
     TB_CHECK(tb_set_gauge(ctx, A_host));
     return solve_host(ctx, false, b_host, x_host, status, iters, rr);
+  }
+  if (onchip == 1 && tb_resident_canon_supported(ctx)) {
+    TB_CHECK(solve_host_canon(ctx, A_host, b_host, x_host));
+    if (status || iters || rr) TB_CHECK(tb_cg_result(ctx, status, iters, rr));
+    return TB_OK;
   }
   TB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
   TB_CHECK(fork_subs(ctx));

@@ -156,6 +156,7 @@ struct tb_ctx {
   cudaStream_t sub_stream[TB_MAX_SUB];
   cudaEvent_t sub_done[TB_MAX_SUB], fork_ev;
   int nsub;
+  int sub_c0[TB_MAX_SUB + 1];   // sub-batch s holds chains [sub_c0[s], sub_c0[s + 1])
   bool sub_pending;  // work queued on the sub-streams that the context stream has not joined yet
   double2 *stage_x;  // second canonical staging buffer (results)
   double last_solve_ms;
@@ -190,6 +191,9 @@ int tb_launch_links_slice(tb_ctx *ctx, const double2 *d_A_dev_layout, int c0, in
 int tb_launch_pack_slice(tb_ctx *ctx, const double2 *d_canonical_slice, double2 *d_vec, int c0, int n, cudaStream_t st);
 int tb_launch_unpack_slice(tb_ctx *ctx, const double2 *d_vec, double2 *d_canonical_slice, int c0, int n, cudaStream_t st);
 bool tb_resident_supported(const tb_ctx *ctx);
+bool tb_resident_canon_supported(const tb_ctx *ctx);
+int tb_run_cg_resident_canon(tb_ctx *ctx, const double2 *b_canon, double2 *x_canon, const double2 *A_canon, int c0, int n,
+                             cudaStream_t st);
 bool tb_cluster_supported(tb_ctx *ctx);
 int tb_cluster_capacity(tb_ctx *ctx);
 int tb_run_cg_cluster_slice(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st);

@@ -356,12 +356,22 @@ struct ResidentWtCfg {
   static_assert(NWARPS == 8, "two warps per TMEM lane quarter; block_sum8");
 };
 
-template <int NT, int NX, bool DAG, bool HAS_MU, bool MASKED, bool PLAN>
+// CANON: the host-buffer path.  bsrc and xout are in the CANONICAL layout [chain][t][x] (what the reference's
+// row-pointer vectors flatten to), so a sub-batch of chains goes H2D copy -> this kernel -> D2H copy with no re-layout
+// kernel in between, and a chain's 64 KB are one contiguous, fully coalesced run.  With canon.A set the links are built
+// here too, from the canonical angles (the arithmetic of links_kernel, bit for bit), and written back in the device
+// layout together with the angles, so the context's W0 / W1 / Adev are what tb_set_gauge would have left.
+struct TbCanon {
+  const double2 *A;          // canonical angles [chain][t][x] = (A_t, A_x), or nullptr: links are read from W0g / W1g
+  double2 *W0, *W1, *Adev;   // device-layout outputs (only with A)
+};
+
+template <int NT, int NX, bool DAG, bool HAS_MU, bool MASKED, bool PLAN, bool CANON = false>
 __global__ void __launch_bounds__(ResidentWtCfg<NT, NX>::NTHREADS, 1)
 resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, const double2 *__restrict__ W0g,
                    const double2 *__restrict__ W1g, const double *__restrict__ mass, const double *__restrict__ msite,
                    const double *__restrict__ emu, const double *__restrict__ emmu, const TbCgState s, const int C,
-                   const int c_first, const TbPlan plan) {
+                   const int c_first, const TbPlan plan, const TbCanon canon) {
   using Cfg = ResidentWtCfg<NT, NX>;
   constexpr int V = Cfg::V, TX = 2, TT = 8, NG = NX / TX;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -417,6 +427,45 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
   const double m = mass[c];
   const double e_p = emu[c], e_m = emmu[c];
 
+  if (CANON && canon.A) {
+    // links from the canonical angles: W0 = s0(t) 1/2 eta0(x) e^{iA_t}, W1 = s1(x) 1/2 e^{iA_x} (links_kernel,
+    // hmc.c:140-174), for the tile and its backward halo; the tile's own links and angles also go to the context's
+    // device-layout arrays
+    const double2 *Ac = canon.A + (size_t)c * V;
+    const int xm = (g * TX + NX - 1) % NX, tmr = (t0 + NT - 1) % NT;
+    auto link0 = [&](double a, int t, int x) {
+      double sn, cs;
+      sincos(a, &sn, &cs);
+      double f0 = (x & 1) ? -0.5 : 0.5;
+      if (t == NT - 1) f0 = -f0;
+      return make_double2(f0 * cs, f0 * sn);
+    };
+    auto link1 = [&](double a, int x) {
+      double sn, cs;
+      sincos(a, &sn, &cs);
+      const double f1 = (x == NX - 1) ? -0.5 : 0.5;
+      return make_double2(f1 * cs, f1 * sn);
+    };
+#pragma unroll 1
+    for (int i = 0; i < TT; i++) {
+      const int t = t0 + i;
+#pragma unroll
+      for (int j = 0; j < TX; j++) {
+        const int x = g * TX + j, k = t * NX + x;
+        const double2 a = Ac[k];
+        const double2 w0 = link0(a.x, t, x), w1 = link1(a.y, x);
+        tmem_st_d2(xaddr + TM_ROW + 16 * i + 4 * j, w0);
+        tmem_st_d2(xaddr + TM_ROW + 16 * i + 8 + 4 * j, w1);
+        canon.W0[(size_t)k * C + c] = w0;
+        canon.W1[(size_t)k * C + c] = w1;
+        canon.Adev[(size_t)k * C + c] = a;
+      }
+      tmem_st_d2(xaddr + TM_W1M + 4 * i, link1(Ac[t * NX + xm].y, xm));
+    }
+#pragma unroll
+    for (int j = 0; j < TX; j++) tmem_st_d2(xaddr + TM_W0M + 4 * j, link0(Ac[tmr * NX + g * TX + j].x, tmr, g * TX + j));
+    tmem_wait_st();
+  } else
   // links of the tile and of its backward halo: device layout [site][chain] -> tensor memory
   {
     const int xm = (g * TX + NX - 1) % NX, tmr = (t0 + NT - 1) % NT;
@@ -461,7 +510,7 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
 #pragma unroll
     for (int j = 0; j < TX; j++) {
       const int k = (t0 + i) * NX + g * TX + j;
-      r[i][j] = bsrc[(size_t)k * C + c];
+      r[i][j] = CANON ? bsrc[(size_t)c * V + k] : bsrc[(size_t)k * C + c];
       p[i][j] = r[i][j];
       rr = fma(r[i][j].x, r[i][j].x, rr);
       rr = fma(r[i][j].y, r[i][j].y, rr);
@@ -591,9 +640,10 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
     for (int u = 0; u < 4; u++) {
       const int f = ch * 4 + u, i = f / TX, j = f % TX;
       const int kk = (t0 + i) * NX + g * TX + j;
-      xout[(size_t)kk * C + c] = (iters > 0) ? make_double2(__hiloint2double((int)v[4 * u + 1], (int)v[4 * u]),
-                                                             __hiloint2double((int)v[4 * u + 3], (int)v[4 * u + 2]))
-                                              : make_double2(0.0, 0.0);
+      xout[CANON ? (size_t)c * V + kk : (size_t)kk * C + c] =
+          (iters > 0) ? make_double2(__hiloint2double((int)v[4 * u + 1], (int)v[4 * u]),
+                                     __hiloint2double((int)v[4 * u + 3], (int)v[4 * u + 2]))
+                      : make_double2(0.0, 0.0);
     }
   }
   __syncthreads();   // every warp has read its columns
@@ -615,14 +665,15 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
 }
 
 template <int NT, int NX>
-int launch_resident_wt(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st) {
+int launch_resident_wt(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st, const TbCanon *canon) {
   using Cfg = ResidentWtCfg<NT, NX>;
   const bool dag = tb_conj_is_dagger(ctx);
   // whole batches larger than the SM count are balanced over the SMs (see TbPlan)
   int nsm = TB_NUM_SMS_B200;
   cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-  const bool plan = plan_pays(ctx, c0, n, nsm);
+  const bool plan = !canon && plan_pays(ctx, c0, n, nsm);
   TbPlan pl = {};
+  TbCanon cn = {};
   if (plan) {
     TB_CHECK(plan_prepare(ctx, nsm, st, &pl));
     auto kern = resident_wt_kernel<NT, NX, false, false, false, true>;
@@ -630,18 +681,22 @@ int launch_resident_wt(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n,
     else if (ctx->has_mu) kern = resident_wt_kernel<NT, NX, false, true, false, true>;
     TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     kern<<<nsm, Cfg::NTHREADS, Cfg::SMEM, st>>>(b, x, ctx->W0, ctx->W1, ctx->d_mass, ctx->msite, ctx->d_emu, ctx->d_emmu,
-                                                ctx->cg, ctx->C, 0, pl);
+                                                ctx->cg, ctx->C, 0, pl, cn);
     ctx->launches++;
     TB_CUDA(cudaGetLastError());
     return TB_OK;
   }
   auto kern = resident_wt_kernel<NT, NX, false, false, false, false>;
-  if (ctx->msite) kern = ctx->has_mu ? resident_wt_kernel<NT, NX, true, true, true, false> : resident_wt_kernel<NT, NX, true, false, true, false>;
+  if (canon) {   // host-buffer path: canonical source / solution (and angles), family A only
+    cn = *canon;
+    if (dag) kern = ctx->has_mu ? resident_wt_kernel<NT, NX, true, true, false, false, true> : resident_wt_kernel<NT, NX, true, false, false, false, true>;
+    else kern = ctx->has_mu ? resident_wt_kernel<NT, NX, false, true, false, false, true> : resident_wt_kernel<NT, NX, false, false, false, false, true>;
+  } else if (ctx->msite) kern = ctx->has_mu ? resident_wt_kernel<NT, NX, true, true, true, false> : resident_wt_kernel<NT, NX, true, false, true, false>;
   else if (dag) kern = ctx->has_mu ? resident_wt_kernel<NT, NX, true, true, false, false> : resident_wt_kernel<NT, NX, true, false, false, false>;
   else if (ctx->has_mu) kern = resident_wt_kernel<NT, NX, false, true, false, false>;
   TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
   kern<<<n, Cfg::NTHREADS, Cfg::SMEM, st>>>(b, x, ctx->W0, ctx->W1, ctx->d_mass, ctx->msite, ctx->d_emu, ctx->d_emmu,
-                                            ctx->cg, ctx->C, c0, pl);
+                                            ctx->cg, ctx->C, c0, pl, cn);
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
   return TB_OK;
@@ -706,9 +761,25 @@ int tb_run_cg_resident_slice(tb_ctx *ctx, const double2 *b, double2 *x, int c0, 
       if (shape == 44) return launch_resident<64, 64, 4, 4>(ctx, b, x, c0, n, st);
       if (shape == 24) return launch_resident<64, 64, 2, 4>(ctx, b, x, c0, n, st);
       if (shape == 28 || !ctx->resident_x_tmem) return launch_resident<64, 64, 2, 8>(ctx, b, x, c0, n, st);
-      return launch_resident_wt<64, 64>(ctx, b, x, c0, n, st);   // default: links and x in tensor memory
+      return launch_resident_wt<64, 64>(ctx, b, x, c0, n, st, nullptr);   // default: links and x in tensor memory
     default: tb_set_error("resident solver: unsupported lattice %dx%d", ctx->nt, ctx->nx); return TB_EINVAL;
   }
+}
+
+// Host-buffer path of the 64^2 kernel: chains [c0, c0 + n) with source and solution in the canonical layout
+// (b_canon / x_canon point at chain 0 of the context) and, when A_canon is not null, the links built inside the kernel
+// from the canonical angles.  Returns TB_EINVAL when the context is not served by that kernel (the caller falls back to
+// the re-layout kernels).
+bool tb_resident_canon_supported(const tb_ctx *ctx) {
+  return tb_resident_supported(ctx) && ctx->nt == 64 && !ctx->msite && ctx->resident_x_tmem && ctx->tune_tt == 0 &&
+         getenv("TB_NO_CANON") == nullptr;
+}
+
+int tb_run_cg_resident_canon(tb_ctx *ctx, const double2 *b_canon, double2 *x_canon, const double2 *A_canon, int c0, int n,
+                             cudaStream_t st) {
+  if (!tb_resident_canon_supported(ctx)) return TB_EINVAL;
+  TbCanon cn = {A_canon, ctx->W0, ctx->W1, ctx->Adev};
+  return launch_resident_wt<64, 64>(ctx, b_canon, x_canon, c0, n, st, &cn);
 }
 
 int tb_run_cg_resident(tb_ctx *ctx, const double2 *b, double2 *x) {
