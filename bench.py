@@ -640,35 +640,52 @@ def other_configs(tb, torch, dist, dev, stream, rank, world, cpu=True):
     if world == 1 and cpu:
         out["256x256_m0.01_g1_8_chains_per_gpu"]["cpu_baseline"] = cpu_apply_rate(256, 256, 0.01, 1.0, 40)
 
-    # configs[4]: coupling/mass scan, 32 (g, m) points x 64 chains on 128x128, chiral condensate measurement.
-    # 4 points (256 chains) per GPU; per-chain m and g; condensate from stochastic sources through fm_invert_cg.
+    # configs[4]: coupling/mass scan, 32 (g, m) points x 64 chains on 128x128, chiral condensate measurement with
+    # N_src = 20 stochastic sources per configuration (hmc.c:798) through fm_invert_cg (hmc.c:408-414).  The SAME 2 048
+    # chains at every N (strong scaling of the fixed scan).  A chain's cost goes like its CG iteration count (~ 1/m):
+    # chains are dealt to the ranks by expected cost (shard.deal_by_cost, longest first) and every rank runs its long
+    # solves first, so that the tail of a batched solve on the cluster solver is made of the cheap chains.
+    from thirring2d_b200.shard import deal_by_cost, reduce_observables
+
     nt = nx = 128
+    per_point = 64
     pts = [(g, m) for g in (0.2, 0.3, 0.4, 0.5, 0.6, 0.7, 0.8, 1.0) for m in (0.01, 0.03, 0.1, 0.3)]
-    mine = [pts[(4 * rank + k) % len(pts)] for k in range(4)]
-    chains = 64 * len(mine)
-    g_arr = np.repeat([p[0] for p in mine], 64)
-    m_arr = np.repeat([p[1] for p in mine], 64)
+    point_of = np.repeat(np.arange(len(pts)), per_point)            # global chain -> scan point
+    cost = np.array([30.0 / pts[p][1] for p in point_of])           # expected iterations (measured: 3 000 at m = 0.01)
+    mine = deal_by_cost(cost, world)[rank]
+    chains = int(mine.size)
+    g_arr = np.array([pts[point_of[c]][0] for c in mine])
+    m_arr = np.array([pts[point_of[c]][1] for c in mine])
     ctx = tb.Context(nt, nx, chains, tb.MODE_ADJOINT, device=local, stream=stream.cuda_stream)
     ctx.set_params(m_arr, 0.0)
     ctx.hmc_set_coupling(g_arr)
     ctx.hmc_heatbath(100, seed=500 + rank)
     kind, in_flight = ctx.solver_info()
-    nsrc = 2
+    nsrc = 20
     ctx.hmc_condensate(nsrc=1, seed=1, meas_index=0)  # warm-up
     torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
     t0 = time.perf_counter()
     cond, its = ctx.hmc_condensate(nsrc=nsrc, seed=1, meas_index=1)
     torch.cuda.synchronize()
-    sec = max_over_ranks((time.perf_counter() - t0) * 1e3) * 1e-3
+    my_sec = time.perf_counter() - t0
+    sec = max_over_ranks(my_sec * 1e3) * 1e-3
+    busy = total_over_ranks(my_sec) / world
     ctx.close()
     applies = total_over_ranks(2 * its + chains * nsrc)
-    out["128x128_scan_4_points_x_64_chains_per_gpu_condensate"] = {
-        "condensate_sources_per_sec": world * chains * nsrc / sec, "dirac_applies_per_sec": applies / sec,
-        "ms_per_source_batch": 1e3 * sec / nsrc, "points_on_rank0": mine, "nsrc": nsrc,
-        "condensate_rank0_by_point": [float(np.mean(cond[64 * k:64 * (k + 1)])) for k in range(len(mine))],
-        "finite": bool(np.all(np.isfinite(cond))),
+    cnt, mean, err = reduce_observables(cond[:, None], point_of[mine], len(pts), dist=dist, device=dev)
+    out["128x128_scan_32_points_x_64_chains_condensate"] = {
+        "condensate_sources_per_sec": len(point_of) * nsrc / sec, "dirac_applies_per_sec": applies / sec,
+        "seconds": sec, "mean_over_ranks_seconds": busy, "load_balance": busy / sec, "scaling": "strong",
+        "chains_total": int(len(point_of)), "chains_on_rank0": chains, "nsrc": nsrc,
+        "ms_per_source_batch": 1e3 * sec / nsrc,
+        "points": [{"g": pts[p][0], "m": pts[p][1], "chains": int(cnt[p]), "condensate": float(mean[p, 0]),
+                    "stderr": float(err[p, 0])} for p in range(len(pts))],
+        "finite": bool(np.all(np.isfinite(mean))),
         "solver": {0: "streaming", 1: "on-chip (CTA per chain)", 2: "on-chip (4-CTA cluster per chain)"}[kind],
-        "chains_in_flight": in_flight}
+        "chains_in_flight": in_flight,
+        "dealing": "shard.deal_by_cost: expected cost 1/m, longest-processing-time rule, long solves first on each rank"}
 
     # SURVEY 8(f) row 3, family B (vec_ops.c): measure_propagator's batch of point sources on one occupation mask
     # (fermionbag.c:389-435) through cg_propagator, host buffers in and out; reference = its own vec_ops.c on one core

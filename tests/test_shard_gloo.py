@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from thirring2d_b200.shard import chain_range, owner_of, reduce_observables
+from thirring2d_b200.shard import chain_range, deal_by_cost, owner_of, reduce_observables
 
 
 @pytest.mark.parametrize("world,total", [(1, 256), (2, 256), (8, 2048), (3, 10), (4, 3), (8, 64)])
@@ -22,6 +22,27 @@ def test_chain_ranges_partition_the_chains(world, total):
     assert seen == list(range(total))
     sizes = [chain_range(r, world, total)[1] for r in range(world)]
     assert max(sizes) - min(sizes) <= 1
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8, 3])
+def test_deal_by_cost_balances_a_mass_scan(world):
+    """BASELINE config 5: 32 (g, m) points x 64 chains; the cost of a chain goes like 1/m.  Every chain is dealt once,
+    no rank carries more than the average plus one chain's cost, and every rank runs its long chains first."""
+    ms = np.tile(np.repeat([0.01, 0.03, 0.1, 0.3], 64), 8)
+    costs = 30.0 / ms
+    deal = deal_by_cost(costs, world)
+    assert sorted(np.concatenate(deal).tolist()) == list(range(costs.size))
+    loads = np.array([costs[d].sum() for d in deal])
+    assert loads.max() <= costs.sum() / world + costs.max()
+    assert loads.max() / loads.mean() < 1.01
+    for d in deal:
+        assert np.all(np.diff(costs[d]) <= 0)
+    # for contrast: the same chains in mass-major order dealt in contiguous blocks (chain_range) leave one rank with
+    # far more than its share
+    if world > 1:
+        by_mass = np.sort(costs)[::-1]
+        blocks = [by_mass[f:f + n].sum() for f, n in (chain_range(r, world, costs.size) for r in range(world))]
+        assert max(blocks) / (costs.sum() / world) > 1.5
 
 
 def _free_port():

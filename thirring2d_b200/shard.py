@@ -29,6 +29,26 @@ def owner_of(chain: int, world: int, nchains_total: int) -> int:
     return extra + (chain - cut) // base
 
 
+def deal_by_cost(costs, world: int):
+    """Cost-balanced dealing of independent units (chains of a coupling/mass scan: the cost of a chain is its expected
+    CG iteration count, e.g. that of the previous solve, which grows like 1/m).  Longest-processing-time rule: units in
+    descending cost order, each to the rank with the least work so far (ties to the lowest rank).  Returns one index
+    array per rank, each in descending cost order -- which is also the order a rank should RUN them in: the on-chip
+    solvers start chains in index order, so the long solves start first and the tail of a batch is made of short ones.
+    Deterministic; every rank computes the same deal from the same costs."""
+    costs = np.asarray(costs, dtype=np.float64)
+    if world < 1 or costs.ndim != 1:
+        raise ValueError("bad world/costs")
+    order = np.argsort(-costs, kind="stable")
+    load = np.zeros(world)
+    mine = [[] for _ in range(world)]
+    for i in order:
+        r = int(np.argmin(load))
+        mine[r].append(int(i))
+        load[r] += costs[i]
+    return [np.asarray(m, dtype=np.int64) for m in mine]
+
+
 def reduce_observables(local_values, group_ids=None, ngroups=1, dist=None, device=None):
     """Final measurement reduction.  local_values: (nlocal, nobs) per-chain observables of this rank;
     group_ids: (nlocal,) parameter-point index of each local chain.  Returns per group
