@@ -61,14 +61,19 @@ build_one 2048 2048 adjoint 10 - 3
 # family B: vec_ops.c behind Thirring.h (sizes are unguarded #defines, Thirring.h:14-15).  The translation unit
 # is assembled on gcc's stdin: "#define MAIN" (so that the EXTERN globals of Thirring.h:54-76 are DEFINED here,
 # as the driver fermionbag.c does), the size-rewritten header, then vec_ops.c without its own #include.
-build_vecops() { # NT NX
-  local nt=$1 nx=$2
+build_vecops() { # NT NX [symmetric]: the boundary choice is a #define in Thirring.h:27-28
+  local nt=$1 nx=$2 suffix="" bcsed=""
+  if [ "${3:-}" = symmetric ]; then
+    suffix="_symmetric"
+    bcsed="; s|^#define ANTISYMMETRIC|//#define ANTISYMMETRIC|; s|^//#define SYMMETRIC|#define SYMMETRIC|"
+  fi
   ( echo '#define MAIN'
-    sed "s/^#define NT 64/#define NT ${nt}/; s/^#define NX 64/#define NX ${nx}/" "$REF/Thirring.h"
+    sed "s/^#define NT 64/#define NT ${nt}/; s/^#define NX 64/#define NX ${nx}/${bcsed}" "$REF/Thirring.h"
     sed '/#include "Thirring.h"/d' "$REF/vec_ops.c" ) | gcc $OPT -std=c99 -w -fPIC -shared \
-      -I"$HERE/shim" -I"$REF" -x c - -x none "$REF/mersenne_inline.c" -o "$OUT/libvecopsref_${nt}x${nx}.so" -lm
+      -I"$HERE/shim" -I"$REF" -x c - -x none "$REF/mersenne_inline.c" -o "$OUT/libvecopsref_${nt}x${nx}${suffix}.so" -lm
 }
 SIZES_B=${TB_REF_SIZES_B:-"16x16 32x32 64x64 16x32"}
 for s in $SIZES_B; do build_vecops "${s%x*}" "${s#*x}"; done
+for s in 16x32 64x64; do build_vecops "${s%x*}" "${s#*x}" symmetric; done
 gcc -O2 -o "$OUT/ref_hmc" "$HERE/ref_launcher.c" -ldl
 ls "$OUT" | sed 's/^/  built oracle\/_ref\//'

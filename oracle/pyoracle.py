@@ -27,6 +27,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF_DIR = os.path.join(HERE, "_ref")
 
 MODE_REF_COMPAT, MODE_ADJOINT = 0, 1
+BC_ANTISYMMETRIC, BC_SYMMETRIC, BC_OPENX = 0, 1, 2   # Thirring.h:27-29
 CG_CONVERGED, CG_MAXITER, CG_DIVERGED, CG_ZERO_SOURCE = 0, 1, 2, 3
 
 _dp = C.POINTER(C.c_double)
@@ -79,6 +80,11 @@ class Oracle:
         L.orc_action.restype = dd
         L.orc_cg_MdM_occupied.argtypes = [ii, ii, dd, ipp, _dp, _dp, ipp]
         L.orc_cg_MdM_occupied.restype = ii
+
+    def set_boundary(self, bc):
+        """Family B boundary variant (a compile-time choice in the reference, Thirring.h:27-29); applies to every
+        family-B call of this process until changed."""
+        self.lib.orc_set_boundary(int(bc))
 
     @staticmethod
     def _prep(v, A):
@@ -332,8 +338,8 @@ class _Gauge:
         return self.arr[:, : self.nx, :]
 
 
-def ref_b_available(nt, nx):
-    return os.path.exists(os.path.join(REF_DIR, f"libvecopsref_{nt}x{nx}.so"))
+def ref_b_available(nt, nx, bc=BC_ANTISYMMETRIC):
+    return os.path.exists(os.path.join(REF_DIR, f"libvecopsref_{nt}x{nx}" + ("_symmetric" if bc == BC_SYMMETRIC else "") + ".so"))
 
 
 class RefLibB:
@@ -341,8 +347,10 @@ class RefLibB:
     defined in the same object (oracle/build_ref.sh).  A private RTLD_DEEPBIND copy: its internal calls can
     never be interposed, so it stays a pure CPU checker even when the GPU shim is loaded globally."""
 
-    def __init__(self, nt, nx, m=1.0, mu=0.0, deepbind=True):
-        src = os.path.join(REF_DIR, f"libvecopsref_{nt}x{nx}.so")
+    def __init__(self, nt, nx, m=1.0, mu=0.0, deepbind=True, bc=BC_ANTISYMMETRIC):
+        # SYMMETRIC is another build (the #define of Thirring.h:27-28 swapped); OPENX is the ANTISYMMETRIC object with
+        # the neighbour tables and the phantom column the driver sets up for it (fermionbag.c:713-717,761-765)
+        src = os.path.join(REF_DIR, f"libvecopsref_{nt}x{nx}" + ("_symmetric" if bc == BC_SYMMETRIC else "") + ".so")
         if not os.path.exists(src):
             raise FileNotFoundError(src)
         fd, tmp = tempfile.mkstemp(prefix="vecopsref_", suffix=".so")
@@ -359,6 +367,10 @@ class RefLibB:
         self._tdn = np.array([(i - 1 + nt) % nt for i in range(nt)], dtype=np.int32)
         self._xup = np.array([(i + 1) % nx for i in range(nx + 1)], dtype=np.int32)
         self._xdn = np.array([(i - 1 + nx) % nx for i in range(nx + 1)], dtype=np.int32)
+        if bc == BC_OPENX:
+            self._xdn[0] = nx
+            self._xup[nx - 1] = nx
+            self._xup[nx] = nx
         for name, arr in (("tup", self._tup), ("tdn", self._tdn), ("xup", self._xup), ("xdn", self._xdn)):
             C.c_void_p.in_dll(L, name).value = arr.ctypes.data
         eta = np.zeros((nt, nx + 1, 2), dtype=np.int32)   # fermionbag.c:770-781
@@ -368,6 +380,8 @@ class RefLibB:
         self._eta, self._eta_rows, self._eta_top = RefLib._triple(eta)
         C.c_void_p.in_dll(L, "eta").value = self._eta_top.ctypes.data
         self.field = np.zeros((nt, nx + 1), dtype=np.int32)   # fermionbag.c:697,710-712
+        if bc == BC_OPENX:
+            self.field[:, nx] = -100   # EMPTY, Thirring.h:41
         self._field_rows = np.ascontiguousarray(
             self.field.ctypes.data + np.arange(nt, dtype=np.uint64) * ((nx + 1) * 4), dtype=np.uint64)
         C.c_void_p.in_dll(L, "field").value = self._field_rows.ctypes.data

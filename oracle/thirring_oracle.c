@@ -226,16 +226,24 @@ double orc_re_dot(int n, const double *a, const double *b)
 }
 
 /* ====================================================================================================
- * Family B: the real, occupation-masked operator of vec_ops.c behind Thirring.h (ANTISYMMETRIC boundaries,
- * Thirring.h:27).  Vectors are real FP64 flat [t][x]; field[t][x] != 0 marks an occupied site (identity row,
- * hops into it dropped).  Pinned bit-for-bit against oracle/_ref/libvecopsref_*.so (tests/test_oracle_pinned.py).
+ * Family B: the real, occupation-masked operator of vec_ops.c behind Thirring.h.  Vectors are real FP64 flat
+ * [t][x]; field[t][x] != 0 marks an occupied site (identity row, hops into it dropped).  Boundary variants
+ * (Thirring.h:27-29): ORC_BC_ANTISYMMETRIC (the default; vec_ops.c:95-172), ORC_BC_SYMMETRIC (periodic in x,
+ * vec_ops.c:175-249), ORC_BC_OPENX (the x hops across the boundary are dropped: the driver points xup[NX-1] and xdn[0]
+ * at a phantom column whose field is EMPTY, fermionbag.c:713-717,761-765).  t is antiperiodic in all three.
+ * Pinned bit-for-bit against oracle/_ref/libvecopsref_*.so (tests/test_oracle_pinned.py).
  * ==================================================================================================== */
 #define ORC_B_CG_MAX_ITER 10000   /* Thirring.h:43 */
 
 /* fM (transpose = 0, vec_ops.c:96-133) and fM_transpose (transpose = 1, vec_ops.c:135-172) */
+enum { ORC_BC_ANTISYMMETRIC = 0, ORC_BC_SYMMETRIC = 1, ORC_BC_OPENX = 2 };
+static int orc_bc = ORC_BC_ANTISYMMETRIC;   /* like the reference's compile-time choice: set once per run */
+void orc_set_boundary(int bc) { orc_bc = bc; }
+
 static void apply_b(int nt, int nx, double m, double mu, int transpose, const int *field,
                     const double *psi, double *chi)
 {
+  const int bc = orc_bc;
   const double expmu = exp(mu), expmmu = exp(-mu);                /* vec_ops.c:101-102 */
   const double e_up = transpose ? expmmu : expmu, e_dn = transpose ? expmu : expmmu;
   for (int t = 0; t < nt; t++) for (int x = 0; x < nx; x++) {
@@ -254,14 +262,16 @@ static void apply_b(int nt, int nx, double m, double mu, int transpose, const in
         if ((t2 > t) != transpose) c += h; else c -= h;
       }
       int x2 = (x + 1) % nx;
-      if (field[t * nx + x2] == 0) {
+      if (field[t * nx + x2] == 0 && !(bc == ORC_BC_OPENX && x2 < x)) {
         double h = 0.5 * 1 * psi[t * nx + x2];
-        if ((x2 > x) != transpose) c += h; else c -= h;
+        const int plus = bc == ORC_BC_SYMMETRIC ? 1 : (x2 > x);       /* vec_ops.c:203 vs :123-124 */
+        if (plus != transpose) c += h; else c -= h;
       }
       x2 = (x - 1 + nx) % nx;
-      if (field[t * nx + x2] == 0) {
+      if (field[t * nx + x2] == 0 && !(bc == ORC_BC_OPENX && x2 > x)) {
         double h = 0.5 * 1 * psi[t * nx + x2];
-        if ((x2 > x) != transpose) c += h; else c -= h;
+        const int plus = bc == ORC_BC_SYMMETRIC ? 0 : (x2 > x);       /* vec_ops.c:207 vs :128-129 */
+        if (plus != transpose) c += h; else c -= h;
       }
     } else {
       c = psi[k];                                                   /* vec_ops.c:130 */

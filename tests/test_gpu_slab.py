@@ -75,7 +75,7 @@ def _worker(rank, world, port, nt, nx, nchains, m, mu, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("world", [2, 4, 8], ids=["P2", "P4", "P8"])
 @pytest.mark.parametrize("nt,nx,nchains,m,mu", [(32, 32, 1, 0.2, 0.1), (64, 48, 3, 0.1, 0.0), (16, 16, 40, 0.5, 0.2), (256, 512, 1, 0.1, 0.0)])
 def test_T7_slab_matches_single_gpu(nt, nx, nchains, m, mu, world):
     """Rank-order sums, the wrap link between rank P-1 and rank 0, and both forms of the one-launch solve at every

@@ -135,6 +135,30 @@ def test_family_b_oracle_bitwise_vs_compiled_vec_ops(oracle, nt, nx, m, mu, occ)
     assert np.abs(oracle.fM(xp, field, m, mu) - psi).max() < 1e-12
 
 
+@pytest.mark.skipif(not ref_b_available(64, 64, 1), reason="oracle/_ref (SYMMETRIC build) not present")
+@pytest.mark.parametrize("nt,nx", [(16, 32), (64, 64)])
+@pytest.mark.parametrize("bc", [1, 2], ids=["SYMMETRIC", "OPENX"])
+@pytest.mark.parametrize("m,mu,occ", [(0.3, 0.1, 0.1), (0.2, 0.0, 0.0)])
+def test_family_b_boundary_variants_bitwise_vs_compiled_vec_ops(oracle, nt, nx, bc, m, mu, occ):
+    """Thirring.h:27-29.  SYMMETRIC: vec_ops.c:175-249 from a build with the #define swapped; OPENX: the ANTISYMMETRIC
+    object with the neighbour tables and the EMPTY phantom column fermionbag.c:713-717,761-765 sets up."""
+    rng = np.random.default_rng(nt * nx + bc)
+    ref = RefLibB(nt, nx, m=m, mu=mu, bc=bc)
+    field = (rng.random((nt, nx)) < occ).astype(np.int32)
+    ref.set_field(field)
+    psi = rng.normal(size=(nt, nx))
+    antisymmetric = oracle.fM(psi, field, m, mu)
+    oracle.set_boundary(bc)
+    try:
+        assert np.array_equal(ref.call("fM", psi), oracle.fM(psi, field, m, mu))
+        assert np.array_equal(ref.call("fM_transpose", psi), oracle.fM(psi, field, m, mu, transpose=True))
+        assert not np.array_equal(oracle.fM(psi, field, m, mu), antisymmetric)   # the variant does change the operator
+        xp, st, it, rr = oracle.cg_MdM(psi, field, m, mu, propagator=True)
+        assert st == CG_CONVERGED and np.array_equal(ref.call("cg_propagator", psi), xp)
+    finally:
+        oracle.set_boundary(0)
+
+
 def test_family_b_golden_fixture(oracle):
     d = np.load(os.path.join(GOLD, "refB_32x32_m0.2_mu0.1.npz"))
     field, psi, m, mu = d["field"], d["psi"], float(d["m"]), float(d["mu"])

@@ -1291,7 +1291,10 @@ slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, 
       const int jp = ((x + 1 == g.nx) ? 0 : x + 1) * g.C + c;
       const int jm = ((x == 0) ? g.nx - 1 : x - 1) * g.C + c;
       const int nch = chunks(sg);
-      for (int ch = 0; ch < nch; ch++) {
+      // chunks in DESCENDING order: phase A went up, so this phase starts on the rows A wrote last (Mp, the new p) and
+      // ends on chunk 0, where the next phase A starts with the r this phase just wrote: on slabs larger than L2 every
+      // phase begins with what is still cached
+      for (int ch = nch - 1; ch >= 0; ch--) {
         const int t0 = chunk_lo(sg, nch, ch), nrows = chunk_lo(sg, nch, ch + 1) - t0;
         double2 pm, w0m;
         if (t0 == 0) {
@@ -1817,10 +1820,15 @@ int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out) {
 // Measured on 2 GPUs (us per CG iteration, multi-kernel -> one launch): 2048^2 142.6 -> 120.5; 1024^2 (the per-GPU size
 // of 2048^2 on 8 GPUs) 78.4 -> 33.5; 512^2 68.0 -> 29.0.  Slabs of more than 4M sites are HBM-bound, where the
 // multi-kernel path (L1-cached neighbour loads, four blocks per SM) is at 0.85 of the HBM peak: it keeps those.
+static size_t persist_max_sites() {
+  if (const char *e = getenv("TB_PERSIST_MAX_SITES")) return (size_t)atoll(e);
+  return (size_t)4 << 20;
+}
+
 static bool use_persistent_slab(const tb_ctx *ctx) {
   return ctx->nranks > 1 && ctx->g.nctiles == 1 && !ctx->msite && tb_conj_is_dagger(ctx) && ctx->cg_variant != 4 &&
          ctx->g.bx >= ctx->nranks &&   // block 0 exchanges with thread (rank, chain): needs nranks * bc threads
-         ctx->nsite <= ((size_t)4 << 20) && getenv("TB_NO_PERSIST") == nullptr;
+         ctx->nsite <= persist_max_sites() && getenv("TB_NO_PERSIST") == nullptr;
 }
 
 // mode 0: block 0 runs the all-reduce (slab_cg_persistent_kernel); 1: the last-arriving block exchanges with the peers
