@@ -117,6 +117,32 @@ int tb_set_links_trig(tb_ctx *ctx, const double *trig_t_host, const double *trig
  * stored occupation field.  tb_set_gauge* switches the context back to family A. */
 int tb_set_occupancy(tb_ctx *ctx, const int *field_host);
 
+/* Boundary variants of family B, a compile-time choice in the reference (Thirring.h:27-29): t is antiperiodic in all
+ * three; in x ANTISYMMETRIC (the default, vec_ops.c:95-172), SYMMETRIC (periodic, vec_ops.c:175-249) or OPENX (no hop
+ * across the x boundary: the driver's phantom column, fermionbag.c:713-717,761-765). */
+#define TB_BC_ANTISYMMETRIC 0
+#define TB_BC_SYMMETRIC     1
+#define TB_BC_OPENX         2
+
+/* tb_set_occupancy with a boundary variant; shared != 0: field_host is ONE field int[NT][NX] used by every source of
+ * the batch (multi-RHS: the 2 NX point sources of measure_propagator, fermionbag.c:389-435, the V/2 of calc_Dinv_cg,
+ * fluctuation_determinant.c:973-1003). */
+int tb_set_occupancy_bc(tb_ctx *ctx, const int *field_host, int bc, int shared);
+
+/* Family B on REAL vectors, host layout double[nchains][NT][NX] (what the reference's double** rows flatten to):
+ * tb_apply_real: TB_OP_M = fM (vec_ops.c:96), TB_OP_MDAG = fM_transpose (vec_ops.c:135).
+ * tb_cg_real: cg_MdM (propagator = 0, vec_ops.c:261) or cg_propagator (1, vec_ops.c:311) for every source; a source
+ * whose solve diverges is returned filled with 1e50 (vec_ops.c:292-296).  8 bytes per site cross PCIe, and on
+ * lattices of whole 8-row tiles with at most 4096 sites (64 x 64, the size Thirring.h compiles in) the solve runs as
+ * one real-arithmetic on-chip kernel per sub-batch of sources (tb_real.cu). */
+int tb_apply_real(tb_ctx *ctx, int op, const double *in_host, double *out_host);
+int tb_cg_real(tb_ctx *ctx, const double *b_host, double *x_host, int propagator, int *status, int *iters, double *rr);
+
+/* Batched BLAS-1 of vec_ops.c on device-resident real vectors double[nchains][NT*NX]: vec_dot (vec_ops.c:56-62), one
+ * value per vector to the host, summed in a fixed order; vec_dmul_add (vec_ops.c:51-55), a = b + e[chain] * d. */
+int tb_vec_dot_real_dev(tb_ctx *ctx, const double *d_a, const double *d_b, double *out_host);
+int tb_vec_dmul_add_real_dev(tb_ctx *ctx, double *d_a, const double *d_b, const double *d_d, const double *e_host);
+
 /* out = Op in, Op one of TB_OP_* (fm_mul hmc.c:123, fm_conjugate_mul hmc.c:188, fmdm_mul hmc.c:259). */
 int tb_apply(tb_ctx *ctx, int op, const double *in_host, double *out_host);
 

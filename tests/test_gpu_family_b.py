@@ -133,3 +133,91 @@ def test_set_params_after_set_occupancy_rebakes_the_site_masses(oracle, nt):
         xo, st, it, rr = oracle.cg_MdM(psi[c], field[c], 0.2, 0.05)
         assert abs(int(info.iters[c]) - it) <= 1
         assert_close(x[c], xo, CG_SOL_TOL, "cg_MdM after set_params")
+
+
+@pytest.mark.parametrize("nt,nx,nsrc", [(64, 64, 40), (32, 32, 5), (16, 16, 3), (16, 32, 4), (24, 40, 2), (8, 64, 2)])
+@pytest.mark.parametrize("bc", [tb.BC_ANTISYMMETRIC, tb.BC_SYMMETRIC, tb.BC_OPENX], ids=["ANTISYMMETRIC", "SYMMETRIC", "OPENX"])
+def test_family_b_boundary_variants_and_real_kernels(oracle, nt, nx, nsrc, bc):
+    """Thirring.h:27-29: the three boundary variants on real 8-byte vectors, against the oracle (pinned bitwise to the
+    reference built with the #define swapped / the OPENX neighbour tables).  64^2, 32^2, 16^2, 16x32 and 8x64 run the
+    on-chip real CG kernel, 24x40 the complex kernels behind the same real interface."""
+    rng = np.random.default_rng(nt + nx + nsrc + 17 * bc)
+    m, mu = 0.2, 0.1
+    field = (rng.random((nsrc, nt, nx)) < 0.12).astype(np.int32)
+    psi = rng.normal(size=(nsrc, nt, nx))
+    with tb.Context(nt, nx, nsrc, tb.MODE_ADJOINT, m=m, mu=mu) as ctx:
+        ctx.set_occupancy(field, bc=bc)
+        chi, chit = ctx.fM(psi), ctx.fM_transpose(psi)
+        x, info = ctx.cg_MdM(psi)
+        xp, infop = ctx.cg_propagator(psi)
+        os.environ["TB_NO_REAL"] = "1"    # the complex kernels behind the same interface
+        xc, infoc = ctx.cg_propagator(psi)
+        del os.environ["TB_NO_REAL"]
+    oracle.set_boundary(bc)
+    try:
+        for c in range(nsrc):
+            assert_close(chi[c], oracle.fM(psi[c], field[c], m, mu), APPLY_TOL, "fM")
+            assert_close(chit[c], oracle.fM(psi[c], field[c], m, mu, transpose=True), APPLY_TOL, "fM_transpose")
+            xo, st, it, rr = oracle.cg_MdM(psi[c], field[c], m, mu)
+            assert info.status[c] == st == tb.CG_CONVERGED and abs(int(info.iters[c]) - it) <= 1
+            assert_close(x[c], xo, CG_SOL_TOL, "cg_MdM")
+            xo, st, it, rr = oracle.cg_MdM(psi[c], field[c], m, mu, propagator=True)
+            assert abs(int(infop.iters[c]) - it) <= 1 and abs(int(infoc.iters[c]) - it) <= 1
+            assert_close(xp[c], xo, CG_SOL_TOL, "cg_propagator")
+            assert_close(xc[c], xo, CG_SOL_TOL, "cg_propagator, complex kernels")
+    finally:
+        oracle.set_boundary(0)
+
+
+def test_shared_field_multi_rhs_and_zero_source(oracle):
+    """measure_propagator (fermionbag.c:389-435): 2 NX point sources on ONE field, passed once; a zero source comes back
+    zero without iterating (vec_ops.c:275-277)."""
+    nt = nx = 64
+    rng = np.random.default_rng(9)
+    field1 = (rng.random((nt, nx)) < 0.1).astype(np.int32)
+    sites = [(t1, x1) for t1 in (0, 1) for x1 in range(nx) if field1[t1, x1] == 0][:100]
+    src = np.zeros((len(sites) + 1, nt, nx))    # the last source stays zero
+    for i, (t1, x1) in enumerate(sites):
+        src[i, t1, x1] = 1.0
+    with tb.Context(nt, nx, src.shape[0], tb.MODE_ADJOINT, m=0.1, mu=0.05) as ctx:
+        ctx.set_occupancy(field1)               # (NT, NX): shared by every source
+        prop, info = ctx.cg_propagator(src)
+    assert info.status[-1] == tb.CG_ZERO_SOURCE and info.iters[-1] == 0 and not prop[-1].any()
+    for i in (0, len(sites) // 2, len(sites) - 1):
+        xo, st, it, rr = oracle.cg_MdM(src[i], field1, 0.1, 0.05, propagator=True)
+        assert abs(int(info.iters[i]) - it) <= 1
+        assert_close(prop[i], xo, CG_SOL_TOL, "point-source propagator")
+
+
+def test_real_cg_stops_silently_at_max_iter():
+    """CG_MAX_ITER passes without convergence are silent in the reference (vec_ops.c:280): the solution so far comes
+    back, the status says TB_CG_MAXITER.  (The 1e50 fill of vec_ops.c:292-296 needs the residual of a positive-definite
+    CG to grow by 1e10, which these operators do not produce; the kernel carries the branch.)"""
+    nt = nx = 16
+    rng = np.random.default_rng(2)
+    psi = rng.normal(size=(2, nt, nx))
+    with tb.Context(nt, nx, 2, tb.MODE_ADJOINT, m=0.01, mu=0.0) as ctx:
+        ctx.set_occupancy(np.zeros((2, nt, nx), dtype=np.int32))
+        ctx.set_cg(1e-30, 6)
+        x, info = ctx.cg_MdM(psi)
+    assert np.all(info.status == tb.CG_MAXITER) and np.all(info.iters == 5) and np.all(np.isfinite(x))
+
+
+def test_batched_device_blas1_of_vec_ops():
+    """vec_dot (vec_ops.c:56-62) and vec_dmul_add (vec_ops.c:51-55) on device-resident real batches."""
+    import torch
+
+    nt, nx, n = 64, 64, 37
+    rng = np.random.default_rng(5)
+    a, b, d = (rng.normal(size=(n, nt, nx)) for _ in range(3))
+    e = rng.normal(size=n)
+    dev = torch.device("cuda", 0)
+    ta, tb_, td = (torch.from_numpy(v).to(dev) for v in (a, b, d))
+    with tb.Context(nt, nx, n, tb.MODE_ADJOINT) as ctx:
+        dots = ctx.vec_dot_dev(ta.data_ptr(), tb_.data_ptr())
+        ctx.vec_dmul_add_dev(ta.data_ptr(), tb_.data_ptr(), td.data_ptr(), e)
+        ctx.synchronize()
+    want = np.array([np.dot(a[c].ravel(), b[c].ravel()) for c in range(n)])
+    assert np.allclose(dots, want, rtol=1e-13, atol=1e-11)
+    got = ta.cpu().numpy()
+    assert np.allclose(got, b + e[:, None, None] * d, rtol=1e-15, atol=1e-15)

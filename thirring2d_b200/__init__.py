@@ -19,6 +19,9 @@ from .api import (  # noqa: F401
     CG_MAXITER,
     CG_DIVERGED,
     CG_ZERO_SOURCE,
+    BC_ANTISYMMETRIC,
+    BC_SYMMETRIC,
+    BC_OPENX,
 )
 
 __all__ = ["Context", "load_library", "library_path", "TBError"]

@@ -23,6 +23,7 @@ from .lib import check, load_library
 MODE_REF_COMPAT, MODE_ADJOINT = 0, 1
 OP_M, OP_MDAG, OP_MCONJ, OP_MDM = 0, 1, 2, 3
 CG_CONVERGED, CG_MAXITER, CG_DIVERGED, CG_ZERO_SOURCE = 0, 1, 2, 3
+BC_ANTISYMMETRIC, BC_SYMMETRIC, BC_OPENX = 0, 1, 2   # family B boundary variants, Thirring.h:27-29
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)
@@ -146,28 +147,70 @@ class Context:
         assert tt.shape == tx.shape == (self.nchains, self.nt, self.nx, 2), tt.shape
         check(self.lib.tb_set_links_trig(self._h, tt.ctypes.data, tx.ctypes.data), "tb_set_links_trig")
 
-    def set_occupancy(self, field):
-        """Family B (vec_ops.c): occupation field (nchains, NT, NX) ints, 0 = free.  Call set_params first."""
+    def set_occupancy(self, field, bc=BC_ANTISYMMETRIC):
+        """Family B (vec_ops.c): occupation field, ints, 0 = free.  (nchains, NT, NX): one field per source; (NT, NX)
+        with nchains > 1: ONE field shared by every source of the batch (multi-RHS).  bc: boundary variant."""
         field = np.ascontiguousarray(field, dtype=np.int32)
-        if field.ndim == 2:
+        shared = field.ndim == 2 and self.nchains > 1
+        if field.ndim == 2 and not shared:
             field = field[None]
-        assert field.shape == (self.nchains, self.nt, self.nx), field.shape
-        check(self.lib.tb_set_occupancy(self._h, field.ctypes.data), "tb_set_occupancy")
+        assert field.shape == ((self.nt, self.nx) if shared else (self.nchains, self.nt, self.nx)), field.shape
+        check(self.lib.tb_set_occupancy_bc(self._h, field.ctypes.data, int(bc), 1 if shared else 0), "tb_set_occupancy_bc")
 
-    # family B names (vec_ops.c:96,135,261,311): real vectors in, real vectors out
+    # family B names (vec_ops.c:96,135,261,311): real vectors in, real vectors out, 8 bytes per site end to end
+    def _real(self, v):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        squeeze = v.ndim == 2
+        if squeeze:
+            v = v[None]
+        assert v.shape == (self.nchains, self.nt, self.nx), (v.shape, (self.nchains, self.nt, self.nx))
+        return v, squeeze
+
+    def _apply_real(self, op, psi):
+        psi, squeeze = self._real(psi)
+        out = np.empty_like(psi)
+        check(self.lib.tb_apply_real(self._h, op, psi.ctypes.data, out.ctypes.data), "tb_apply_real")
+        return out[0] if squeeze else out
+
     def fM(self, psi):
-        return self.apply(OP_M, np.asarray(psi, dtype=np.float64).astype(np.complex128)).real
+        return self._apply_real(OP_M, psi)
 
     def fM_transpose(self, psi):
-        return self.apply(OP_MDAG, np.asarray(psi, dtype=np.float64).astype(np.complex128)).real
+        return self._apply_real(OP_MDAG, psi)
+
+    def _solve_real(self, source, propagator):
+        b, squeeze = self._real(source)
+        x = np.empty_like(b)
+        st = np.empty(self.nchains, dtype=np.int32)
+        it = np.empty(self.nchains, dtype=np.int32)
+        rr = np.empty(self.nchains, dtype=np.float64)
+        check(self.lib.tb_cg_real(self._h, b.ctypes.data, x.ctypes.data, 1 if propagator else 0, st.ctypes.data_as(_ip),
+                                  it.ctypes.data_as(_ip), rr.ctypes.data_as(_dp)), "tb_cg_real")
+        return (x[0] if squeeze else x), CGInfo(st, it, rr)
 
     def cg_MdM(self, source):
-        x, info = self.fmdm_invert_cg(np.asarray(source, dtype=np.float64).astype(np.complex128))
-        return x.real, info
+        return self._solve_real(source, False)
 
     def cg_propagator(self, source):
-        x, info = self.fm_invert_cg(np.asarray(source, dtype=np.float64).astype(np.complex128))
-        return x.real, info
+        return self._solve_real(source, True)
+
+    def cg_real_host_ptr(self, b_ptr: int, x_ptr: int, propagator=True):
+        """Raw host pointers (e.g. pinned buffers) of real batches double[nchains][NT][NX]."""
+        check(self.lib.tb_cg_real(self._h, C.c_void_p(b_ptr), C.c_void_p(x_ptr), 1 if propagator else 0, None, None, None),
+              "tb_cg_real")
+
+    def vec_dot_dev(self, d_a: int, d_b: int):
+        """vec_dot (vec_ops.c:56) for every vector of a device-resident real batch."""
+        out = np.empty(self.nchains, dtype=np.float64)
+        check(self.lib.tb_vec_dot_real_dev(self._h, C.c_void_p(d_a), C.c_void_p(d_b), out.ctypes.data_as(_dp)),
+              "tb_vec_dot_real_dev")
+        return out
+
+    def vec_dmul_add_dev(self, d_a: int, d_b: int, d_d: int, e):
+        """vec_dmul_add (vec_ops.c:51): a = b + e[chain] * d on device-resident real batches."""
+        e = np.ascontiguousarray(np.broadcast_to(np.asarray(e, dtype=np.float64), (self.nchains,)))
+        check(self.lib.tb_vec_dmul_add_real_dev(self._h, C.c_void_p(d_a), C.c_void_p(d_b), C.c_void_p(d_d),
+                                                e.ctypes.data_as(_dp)), "tb_vec_dmul_add_real_dev")
 
     def apply(self, op, v):
         squeeze = np.ndim(v) == 2

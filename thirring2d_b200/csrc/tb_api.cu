@@ -601,7 +601,13 @@ extern "C" int tb_set_links_trig(tb_ctx *ctx, const double *trig_t_host, const d
 // int[nchains][NT][NX].  Replaces the gauge field: links become the real masked constants of fM / fM_transpose
 // and occupied sites identity rows.  The current tb_set_params masses are baked into the site masses.
 extern "C" int tb_set_occupancy(tb_ctx *ctx, const int *field_host) {
-  if (!ctx || !field_host) return TB_EINVAL;
+  return tb_set_occupancy_bc(ctx, field_host, TB_BC_ANTISYMMETRIC, 0);
+}
+
+// The same with the boundary variant of Thirring.h:27-29 and, for shared != 0, ONE field int[NT][NX] for every source
+// of the batch (the multi-RHS case: measure_propagator's 2 NX point sources on one configuration).
+extern "C" int tb_set_occupancy_bc(tb_ctx *ctx, const int *field_host, int bc, int shared) {
+  if (!ctx || !field_host || bc < TB_BC_ANTISYMMETRIC || bc > TB_BC_OPENX) return TB_EINVAL;
   if (ctx->nranks > 1) { tb_set_error("tb_set_occupancy: slab contexts are not supported"); return TB_EINVAL; }
   TB_CUDA(cudaSetDevice(ctx->device));
   TB_CHECK(sync_all(ctx));
@@ -610,12 +616,90 @@ extern "C" int tb_set_occupancy(tb_ctx *ctx, const int *field_host) {
     TB_CHECK(dev_alloc(&ctx->occ_dev, ctx->nsite));
     TB_CHECK(dev_alloc(&ctx->occ_stage, ctx->nsite));
   }
-  TB_CUDA(cudaMemcpyAsync(ctx->occ_stage, field_host, ctx->nsite * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->occ_bc = bc;
+  if (shared) {
+    for (int c = 0; c < ctx->C; c++)
+      TB_CUDA(cudaMemcpyAsync(ctx->occ_stage + (size_t)c * ctx->V, field_host, ctx->V * sizeof(int),
+                              cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    TB_CUDA(cudaMemcpyAsync(ctx->occ_stage, field_host, ctx->nsite * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  }
   TB_CHECK(tb_launch_occupancy(ctx, ctx->occ_stage));
   ctx->msite = ctx->msite_buf;
   ctx->have_gauge = true;
   invalidate_graph(ctx);
   return TB_OK;
+}
+
+// ---- family B on REAL host vectors double[nchains][NT][NX] (tb_real.cu) ------------------------------------------
+static int need_occupancy(tb_ctx *ctx) {
+  if (!ctx->msite) {
+    tb_set_error("family B entry point without an occupation field (call tb_set_occupancy first)");
+    return TB_EINVAL;
+  }
+  return TB_OK;
+}
+
+// fM (TB_OP_M, vec_ops.c:96) / fM_transpose (TB_OP_MDAG, vec_ops.c:135) on real vectors, any lattice shape
+extern "C" int tb_apply_real(tb_ctx *ctx, int op, const double *in_host, double *out_host) {
+  if (!ctx || !in_host || !out_host || (op != TB_OP_M && op != TB_OP_MDAG)) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(need_occupancy(ctx));
+  TB_CHECK(join_subs(ctx));
+  double *din = ctx->stage, *dout = ctx->stage + ctx->nsite;   // stage holds 2 * nsite doubles
+  TB_CUDA(cudaMemcpyAsync(din, in_host, ctx->nsite * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  TB_CHECK(tb_launch_real_apply(ctx, op == TB_OP_MDAG, din, dout));
+  TB_CUDA(cudaMemcpyAsync(out_host, dout, ctx->nsite * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  return sync_all(ctx);
+}
+
+// cg_MdM (propagator = 0, vec_ops.c:261) / cg_propagator (1, vec_ops.c:311) for every source of the batch.  A source
+// whose solve diverges comes back filled with 1e50 (vec_ops.c:292-296) and status TB_CG_DIVERGED.  Lattices the
+// on-chip real kernel serves (whole 8-row tiles, at most 4096 sites: 64 x 64, the size Thirring.h compiles in) run
+// host -> H2D -> one kernel -> D2H per sub-batch of sources; other shapes go through the complex kernels.
+extern "C" int tb_cg_real(tb_ctx *ctx, const double *b_host, double *x_host, int propagator, int *status, int *iters,
+                          double *rr) {
+  if (!ctx || !b_host || !x_host) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(need_occupancy(ctx));
+  if (ctx->tune_solver != 1 && ctx->tune_solver != 5 && tb_real_cg_supported(ctx)) {
+    TB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    TB_CHECK(fork_subs(ctx));
+    double *db = ctx->stage, *dx = ctx->stage + ctx->nsite;
+    for (int s = 0; s < ctx->nsub; s++) {
+      int c0, n;
+      sub_range(ctx, s, &c0, &n);
+      if (n == 0) continue;
+      const size_t off = (size_t)c0 * ctx->V, bytes = (size_t)n * ctx->V * sizeof(double);
+      cudaStream_t st = ctx->sub_stream[s];
+      TB_CUDA(cudaMemcpyAsync(db + off, b_host + off, bytes, cudaMemcpyHostToDevice, st));
+      TB_CHECK(tb_run_cg_real(ctx, db, dx, propagator != 0, c0, n, st));
+      TB_CUDA(cudaMemcpyAsync(x_host + off, dx + off, bytes, cudaMemcpyDeviceToHost, st));
+    }
+    TB_CHECK(sync_all(ctx));
+    TB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    TB_CUDA(cudaEventSynchronize(ctx->ev1));
+    float ms = 0.f;
+    TB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_solve_ms = ms;
+    if (status || iters || rr) TB_CHECK(tb_cg_result(ctx, status, iters, rr));
+    return TB_OK;
+  }
+  // other shapes: the complex kernels on vectors with zero imaginary parts
+  const size_t n = ctx->nsite;
+  double *cb = (double *)malloc(4 * n * sizeof(double));
+  if (!cb) return TB_ENOMEM;
+  double *cx = cb + 2 * n;
+  for (size_t i = 0; i < n; i++) { cb[2 * i] = b_host[i]; cb[2 * i + 1] = 0.0; }
+  int *st = (int *)malloc(ctx->C * sizeof(int));
+  int rc = propagator ? tb_invert(ctx, cb, cx, st, iters, rr) : tb_cg(ctx, cb, cx, st, iters, rr);
+  if (rc == TB_OK) {
+    for (size_t i = 0; i < n; i++) x_host[i] = st[i / ctx->V] == TB_CG_DIVERGED ? 1e50 : cx[2 * i];
+    if (status) memcpy(status, st, ctx->C * sizeof(int));
+  }
+  free(st);
+  free(cb);
+  return rc;
 }
 
 extern "C" int tb_apply(tb_ctx *ctx, int op, const double *in_host, double *out_host) {

@@ -139,6 +139,7 @@ struct tb_ctx {
   // family B (vec_ops.c): per-site mass (occupied site = identity row); msite == nullptr for family A
   double *msite, *msite_buf;
   int *occ_dev, *occ_stage;
+  int occ_bc;   // family B boundary variant (TB_BC_*), Thirring.h:27-29
   // work vectors (device layout)
   double2 *r, *p, *Mp, *q, *xw, *tmp, *vin, *vout;
   double2 *p1;    // slab mode: second direction buffer of the one-launch solve (in the exchange block, like p, Mp, r)
@@ -199,6 +200,9 @@ int tb_cluster_capacity(tb_ctx *ctx);
 int tb_run_cg_cluster_slice(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st);
 int tb_launch_dot(tb_ctx *ctx, const double2 *a, const double2 *b, double *d_out);
 int tb_launch_occupancy(tb_ctx *ctx, const int *d_field_canonical);
+bool tb_real_cg_supported(const tb_ctx *ctx);
+int tb_launch_real_apply(tb_ctx *ctx, bool transpose, const double *d_in, double *d_out);
+int tb_run_cg_real(tb_ctx *ctx, const double *d_b, double *d_x, bool propagator, int c0, int n, cudaStream_t st);
 int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out);
 int tb_slab_layout(tb_ctx *ctx);
 int tb_run_cg_any(tb_ctx *ctx, const double2 *b, double2 *x);

@@ -1443,7 +1443,7 @@ __global__ void links_kernel(const double2 *__restrict__ A, double2 *__restrict_
 // site mass is m on free sites and 1 on occupied ones (identity row, vec_ops.c:130).  occ: [t][x][c] ints.
 __global__ void occupancy_links_kernel(const int *__restrict__ occ, const double *__restrict__ mass,
                                        double2 *__restrict__ W0, double2 *__restrict__ W1,
-                                       double *__restrict__ msite, int nt, int nx, int C) {
+                                       double *__restrict__ msite, int nt, int nx, int C, int bc) {
   const size_t total = (size_t)nt * nx * C;
   const size_t R = (size_t)nx * C;
   for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
@@ -1456,7 +1456,9 @@ __global__ void occupancy_links_kernel(const int *__restrict__ occ, const double
     const bool free_n = occ[k] == 0;
     double f0 = (x & 1) ? -0.5 : 0.5;
     if (t == nt - 1) f0 = -f0;
-    const double f1 = (x == nx - 1) ? -0.5 : 0.5;
+    // the x link across the boundary: ANTISYMMETRIC -1/2, SYMMETRIC +1/2 (vec_ops.c:201-207), OPENX none
+    // (fermionbag.c:713-717,761-765)
+    const double f1 = (x == nx - 1) ? (bc == TB_BC_SYMMETRIC ? 0.5 : (bc == TB_BC_OPENX ? 0.0 : -0.5)) : 0.5;
     W0[k] = make_double2((free_n && occ[kt] == 0) ? f0 : 0.0, 0.0);
     W1[k] = make_double2((free_n && occ[kx] == 0) ? f1 : 0.0, 0.0);
     msite[k] = free_n ? mass[c] : 1.0;
@@ -1644,7 +1646,7 @@ int tb_launch_occupancy(tb_ctx *ctx, const int *d_field_canonical) {
   int blocks = (int)((ctx->nsite + 255) / 256);
   if (blocks > TB_NUM_SMS_B200 * 16) blocks = TB_NUM_SMS_B200 * 16;
   occupancy_links_kernel<<<blocks, 256, 0, st>>>(occ, ctx->d_mass, ctx->W0, ctx->W1, ctx->msite_buf, ctx->nt,
-                                                 ctx->nx, ctx->C);
+                                                 ctx->nx, ctx->C, ctx->occ_bc);
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
   return TB_OK;

@@ -14,9 +14,10 @@
 
 static struct {
   tb_ctx *ctx;
-  int nt, nx, device;
+  int nt, nx, device, bc;
   int *field_flat, *field_last;
-  double *cin, *cout;   /* complex staging (imaginary parts zero) */
+  double *cin, *cout;   /* complex staging of the flat-array family (imaginary parts stay zero) */
+  double *rin, *rout;   /* real staging: one flat vector each */
   int have_field, mu_frozen;
   double mu0, m_last;
   int ***p_field_dummy;
@@ -40,6 +41,9 @@ int tb_vecops_configure(int nt, int nx, int device) {
   if (S.ctx) tb_vecops_shutdown();
   memset(&S, 0, sizeof(S));
   S.nt = nt; S.nx = nx; S.device = device;
+  /* the boundary variant is a #define in the reference (Thirring.h:27-29): THIRRING_BC = antisymmetric | symmetric | openx */
+  const char *bcs = getenv("THIRRING_BC");
+  S.bc = (bcs && !strcmp(bcs, "symmetric")) ? TB_BC_SYMMETRIC : ((bcs && !strcmp(bcs, "openx")) ? TB_BC_OPENX : TB_BC_ANTISYMMETRIC);
   if (tb_create(&S.ctx, nt, nx, 1, TB_MODE_ADJOINT, device) != TB_OK) die("tb_create");
   if (tb_set_cg(S.ctx, 1e-30, VEC_CG_MAX_ITER) != TB_OK) die("tb_set_cg");  /* Thirring.h:42-43 */
   size_t v = (size_t)nt * nx;
@@ -47,13 +51,15 @@ int tb_vecops_configure(int nt, int nx, int device) {
   S.field_last = malloc(v * sizeof(int));
   S.cin = calloc(2 * v, sizeof(double));
   S.cout = calloc(2 * v, sizeof(double));
+  S.rin = calloc(v, sizeof(double));
+  S.rout = calloc(v, sizeof(double));
   return 0;
 }
 
 void tb_vecops_shutdown(void) {
   if (S.ctx) tb_destroy(S.ctx);
   if (S.ctx0) tb_destroy(S.ctx0);
-  free(S.field_flat); free(S.field_last); free(S.cin); free(S.cout); free(S.field0_last); free(S.inv0);
+  free(S.field_flat); free(S.field_last); free(S.cin); free(S.cout); free(S.rin); free(S.rout); free(S.field0_last); free(S.inv0);
   memset(&S, 0, sizeof(S));
 }
 
@@ -90,18 +96,11 @@ static void sync_state(void) {
   if (changed) {
     double m = *S.p_m, mu = S.mu0;
     if (tb_set_params(S.ctx, &m, &mu, 1) != TB_OK) die("tb_set_params");
-    if (tb_set_occupancy(S.ctx, S.field_flat) != TB_OK) die("tb_set_occupancy");
+    if (tb_set_occupancy_bc(S.ctx, S.field_flat, S.bc, 0) != TB_OK) die("tb_set_occupancy");
     memcpy(S.field_last, S.field_flat, bytes);
     S.m_last = m;
     S.have_field = 1;
   }
-}
-
-static void to_complex(double **v) {
-  for (int t = 0; t < S.nt; t++) for (int x = 0; x < S.nx; x++) S.cin[2 * ((size_t)t * S.nx + x)] = v[t][x];
-}
-static void from_complex(double **v) {
-  for (int t = 0; t < S.nt; t++) for (int x = 0; x < S.nx; x++) v[t][x] = S.cout[2 * ((size_t)t * S.nx + x)];
 }
 
 /* ---- element-wise helpers: host rows, as in the reference ------------------------------------------------ */
@@ -136,11 +135,19 @@ void vec_print_lat(double **a) {
 }
 
 /* ---- the hot path: GPU ------------------------------------------------------------------------------------ */
+/* real vectors straight through (tb_real.cu): the rows are gathered into / scattered from one flat double[NT*NX] */
+static void to_flat(double **v) {
+  for (int t = 0; t < S.nt; t++) memcpy(S.rin + (size_t)t * S.nx, v[t], (size_t)S.nx * sizeof(double));
+}
+static void from_flat(double **v) {
+  for (int t = 0; t < S.nt; t++) memcpy(v[t], S.rout + (size_t)t * S.nx, (size_t)S.nx * sizeof(double));
+}
+
 static void apply(int op, double **chi, double **psi) {
   sync_state();
-  to_complex(psi);
-  if (tb_apply(S.ctx, op, S.cin, S.cout) != TB_OK) die("tb_apply");
-  from_complex(chi);
+  to_flat(psi);
+  if (tb_apply_real(S.ctx, op, S.rin, S.rout) != TB_OK) die("tb_apply_real");
+  from_flat(chi);
   S.gpu_calls++;
 }
 
@@ -149,18 +156,12 @@ void fM_transpose(double **chi, double **psi) { apply(TB_OP_MDAG, chi, psi); }
 
 static void solve(int propagator, double **inv, double **source) {
   sync_state();
-  to_complex(source);
+  to_flat(source);
   int status = 0, iters = 0;
   double rr = 0;
-  int rc = propagator ? tb_invert(S.ctx, S.cin, S.cout, &status, &iters, &rr)
-                      : tb_cg(S.ctx, S.cin, S.cout, &status, &iters, &rr);
-  if (rc != TB_OK) die("tb_cg");
+  if (tb_cg_real(S.ctx, S.rin, S.rout, propagator, &status, &iters, &rr) != TB_OK) die("tb_cg_real");
   S.gpu_calls++;
-  if (status == TB_CG_DIVERGED) {   /* vec_ops.c:292-296 */
-    vec_set(inv, 1e50);
-    return;
-  }
-  from_complex(inv);
+  from_flat(inv);   /* a diverged solve comes back filled with 1e50 (vec_ops.c:292-296) */
 }
 
 void cg_MdM(double **inv, double **source) { solve(0, inv, source); }

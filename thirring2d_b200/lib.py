@@ -34,6 +34,11 @@ SIGNATURES = {
     "tb_set_gauge": (_i, [_vp, _vp]),
     "tb_set_links_trig": (_i, [_vp, _vp, _vp]),
     "tb_set_occupancy": (_i, [_vp, _vp]),
+    "tb_set_occupancy_bc": (_i, [_vp, _vp, _i, _i]),
+    "tb_apply_real": (_i, [_vp, _i, _vp, _vp]),
+    "tb_cg_real": (_i, [_vp, _vp, _vp, _i, _ip, _ip, _dp]),
+    "tb_vec_dot_real_dev": (_i, [_vp, _vp, _vp, _dp]),
+    "tb_vec_dmul_add_real_dev": (_i, [_vp, _vp, _vp, _vp, _dp]),
     "tb_apply": (_i, [_vp, _i, _vp, _vp]),
     "tb_cg": (_i, [_vp, _vp, _vp, _ip, _ip, _dp]),
     "tb_invert": (_i, [_vp, _vp, _vp, _ip, _ip, _dp]),
