@@ -57,10 +57,13 @@ def _worker(rank, world, port, nt, nx, nchains, m, mu, q):
     xm, infom = ctx.fmdm_invert_cg(b)
     del os.environ["TB_NO_PERSIST"]
     x5, info5 = ctx.fmdm_invert_cg(b)
-    # the other forms of the one-launch solve: block 0 runs the all-reduce (TB_SLAB_SYNC=0); every block polls the
-    # peers' slots (2), here with a single slot replica; then the default again
+    # every form of the one-launch solve explicitly (the default picks one by slab size): block 0 runs the all-reduce
+    # (TB_SLAB_SYNC=0); the last-arriving block exchanges with the peers and publishes the totals (1); every block polls
+    # the peers' slots (2), here with a single slot replica; then the default again
     os.environ["TB_SLAB_SYNC"] = "0"
     x6, info6 = ctx.fmdm_invert_cg(b)
+    os.environ["TB_SLAB_SYNC"] = "1"
+    x9, info9 = ctx.fmdm_invert_cg(b)
     os.environ["TB_SLAB_SYNC"] = "2"
     os.environ["TB_SLAB_NREP"] = "1"
     x7, info7 = ctx.fmdm_invert_cg(b)
@@ -68,7 +71,7 @@ def _worker(rank, world, port, nt, nx, nchains, m, mu, q):
     x8, info8 = ctx.fmdm_invert_cg(b)
     out.update(b=b, x=x, x2=x2, xi=xi, x4=x4, iters=info.iters, status=info.status, iters2=info2.iters,
                iters4=info4.iters, xm=xm, itersm=infom.iters, x5=x5, iters5=info5.iters, x6=x6, iters6=info6.iters,
-               x7=x7, iters7=info7.iters, x8=x8, iters8=info8.iters)
+               x7=x7, iters7=info7.iters, x8=x8, iters8=info8.iters, x9=x9, iters9=info9.iters)
     q.put((rank, out))
     dist.barrier()
     ctx.close()
@@ -121,11 +124,13 @@ def test_T7_slab_matches_single_gpu(nt, nx, nchains, m, mu, world):
     assert np.linalg.norm(cat("xm") - x) <= 1e-12 * np.linalg.norm(x)
     assert np.all(np.abs(res[0]["itersm"].astype(int) - info.iters.astype(int)) <= 1)
     assert np.array_equal(cat("x5"), xs) and np.array_equal(res[0]["iters5"], res[0]["iters"])
-    # block 0's form cuts the slab into other tiles (another summation order of the partials): same solve to rounding
-    assert np.linalg.norm(cat("x6") - x) <= 1e-12 * np.linalg.norm(x)
-    assert np.all(np.abs(res[0]["iters6"].astype(int) - info.iters.astype(int)) <= 1)
-    for r in range(world):
-        assert np.array_equal(res[r]["iters6"], res[0]["iters6"])
+    # block 0's form and the other two cut the slab differently (another summation order of the partials): the same
+    # solve to rounding, identical decisions on every rank
+    for k in ("6", "9"):
+        assert np.linalg.norm(cat("x" + k) - x) <= 1e-12 * np.linalg.norm(x)
+        assert np.all(np.abs(res[0]["iters" + k].astype(int) - info.iters.astype(int)) <= 1)
+        for r in range(world):
+            assert np.array_equal(res[r]["iters" + k], res[0]["iters" + k])
     # who polls does not change a bit of the arithmetic
-    assert np.array_equal(cat("x7"), xs) and np.array_equal(res[0]["iters7"], res[0]["iters"])
+    assert np.array_equal(cat("x7"), cat("x9")) and np.array_equal(res[0]["iters7"], res[0]["iters9"])
     assert np.array_equal(cat("x8"), xs) and np.array_equal(res[0]["iters8"], res[0]["iters"])

@@ -1822,9 +1822,12 @@ int tb_slab_apply(tb_ctx *ctx, int op, const double2 *in, double2 *out) {
 // Measured on 2 GPUs (us per CG iteration, multi-kernel -> one launch): 2048^2 142.6 -> 120.5; 1024^2 (the per-GPU size
 // of 2048^2 on 8 GPUs) 78.4 -> 33.5; 512^2 68.0 -> 29.0.  Slabs of more than 4M sites are HBM-bound, where the
 // multi-kernel path (L1-cached neighbour loads, four blocks per SM) is at 0.85 of the HBM peak: it keeps those.
+// Measured (profiles/slab_r02f_8gpu.txt): with 8M sites per GPU (4096^2 on 2 GPUs) the one-launch solve still beats the
+// multi-kernel form, 358 vs 435 us per iteration (phase B walks its chunks downwards, so every phase starts on what the
+// previous one left in L2); the 32-bit indices of the kernel hold up to 2^27 elements per field.
 static size_t persist_max_sites() {
   if (const char *e = getenv("TB_PERSIST_MAX_SITES")) return (size_t)atoll(e);
-  return (size_t)4 << 20;
+  return (size_t)16 << 20;
 }
 
 static bool use_persistent_slab(const tb_ctx *ctx) {
@@ -1916,8 +1919,12 @@ static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int mode, int *
   return TB_OK;
 }
 
+// Which form (measured, us per CG iteration, profiles/slab_r02*.txt): slabs that live in L2 are bound by the two
+// synchronisation points, and there block 0's form is as fast on 2 GPUs (1024^2: 32.1-33.8 vs 32.2-32.7) and faster on 8
+// (2048^2: 33.3 vs 35.0); larger slabs are bound by the passes over the slab, where the balanced row segments, cached
+// loads and the hybrid all-reduce win (2048^2 on 2 GPUs 110.5 vs 120.0, 4096^2 on 8 GPUs 109).
 static int launch_persistent_slab_auto(tb_ctx *ctx, const double2 *b, int *nblocks_out) {
-  int mode = 1;
+  int mode = ctx->nsite <= ((size_t)1 << 20) ? 0 : 1;
   if (const char *e = getenv("TB_SLAB_SYNC")) { const int v = atoi(e); if (v >= 0 && v <= 2) mode = v; }
   return launch_persistent_slab(ctx, b, mode, nblocks_out);
 }
