@@ -223,6 +223,13 @@ int tb_hmc_trajectory(tb_ctx *ctx, int nsteps, double traj_length, unsigned long
                       const double *st_host, const double *u_host, double *obs_host, int *accepted_host,
                       long long *cg_iters_host);
 
+/* dS/dA for every link of every chain on the current field: what one momentum_step subtracts, times eps, from the
+ * momenta (hmc.c:504-661): gauge force (Nf/g) sin A, pseudofermion force of Re<psi, (M~M)^-1 psi>, and the force of
+ * the stochastic Re<st, M~ st> term as coded (st_host NULL: no such term).  psi_host complex [chain][t][x], force_host
+ * real [chain][t][x][2].  The quantity the reference's disabled CHECK_FORCE block (hmc.c:502,535-559) compares with a
+ * finite difference of pseudofermion_action. */
+int tb_hmc_force(tb_ctx *ctx, const double *psi_host, const double *st_host, double *force_host);
+
 /* Per chain, how the CG solves of the last tb_hmc_trajectory ended: bit (1 << TB_CG_MAXITER) and / or
  * (1 << TB_CG_DIVERGED) set, 0 when every solve converged.  The reference exit(1)s on divergence (hmc.c:383-388)
  * and is silent at max-iter; a batched trajectory rejects such a chain and reports it here. */

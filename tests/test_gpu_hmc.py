@@ -213,6 +213,38 @@ def test_resumed_run_continues_the_random_stream(tmp_path):
     assert ok.returncode == 0 and chain_lines(ok.stdout) == chain_lines(leg2.stdout)
 
 
+def test_force_is_the_derivative_of_the_action_check_force():
+    """The reference's CHECK_FORCE (hmc.c:502,535-559, disabled in the shipped source) on the GPU, batched: the force
+    momentum_step applies must be the derivative of Sg + Re<psi, (M^dagger M)^-1 psi> with respect to every link angle.
+    One chain per probed link and sign (A +- h e_k): 2 x 96 perturbed fields solved as one batch; central differences
+    with h = 1e-4 against tb_hmc_force on the unperturbed field.  ADJOINT mode (the formula assumes the true M^dagger),
+    mu != 0, the wrap-around links included."""
+    nt = nx = 16
+    m, mu, g, h = 0.4, 0.15, 0.3, 1e-4
+    rng = np.random.default_rng(31)
+    A = rng.uniform(-np.pi, np.pi, size=(nt, nx, 2))
+    psi = rng.normal(size=(nt, nx)) + 1j * rng.normal(size=(nt, nx))
+    links = [(0, 0, 0), (nt - 1, 3, 0), (5, nx - 1, 1), (nt - 1, nx - 1, 1), (0, nx - 1, 0), (7, 0, 1)]
+    links += [(int(t), int(x), int(d)) for t, x, d in zip(rng.integers(0, nt, 90), rng.integers(0, nx, 90), rng.integers(0, 2, 90))]
+    n = 2 * len(links)
+    Ab = np.broadcast_to(A, (n, nt, nx, 2)).copy()
+    for k, (t, x, d) in enumerate(links):
+        Ab[2 * k, t, x, d] += h
+        Ab[2 * k + 1, t, x, d] -= h
+    with tb.Context(nt, nx, n, tb.MODE_ADJOINT, m=m, mu=mu) as ctx:
+        ctx.set_gauge(Ab)
+        xs, info = ctx.fmdm_invert_cg(np.broadcast_to(psi, (n, nt, nx)))
+        assert np.all(info.status == tb.CG_CONVERGED)
+    S = (2.0 / g) * (1.0 - np.cos(Ab)).reshape(n, -1).sum(axis=1) + np.array([np.vdot(psi, xs[c]).real for c in range(n)])
+    with tb.Context(nt, nx, 1, tb.MODE_ADJOINT, m=m, mu=mu) as ctx:
+        ctx.hmc_set_coupling(g)
+        ctx.set_gauge(A)
+        F = ctx.hmc_force(psi)[0]
+    for k, (t, x, d) in enumerate(links):
+        fd = (S[2 * k] - S[2 * k + 1]) / (2 * h)
+        assert abs(F[t, x, d] - fd) <= 1e-6 * max(1.0, abs(fd)), ((t, x, d), F[t, x, d], fd)
+
+
 def free_field_condensate(L, m):
     """(1/V) Tr M^-1 at A = 0, mu = 0: (1/V) sum_k m / (m^2 + sum_mu sin^2 k_mu), k antiperiodic."""
     k = (2 * np.arange(L) + 1) * np.pi / L

@@ -353,6 +353,17 @@ class Context:
               "tb_hmc_trajectory")
         return obs, acc, its.value
 
+    def hmc_force(self, psi, st=None):
+        """dS/dA of momentum_step (hmc.c:504-661) for every link: real (nchains, NT, NX, 2)."""
+        psi = self._vec(psi)
+        stp = None
+        if st is not None:
+            st = self._vec(st)
+            stp = st.ctypes.data
+        out = np.empty((self.nchains, self.nt, self.nx, 2), dtype=np.float64)
+        check(self.lib.tb_hmc_force(self._h, psi.ctypes.data, stp, out.ctypes.data), "tb_hmc_force")
+        return out
+
     def hmc_cg_failures(self):
         """Per chain: bit (1 << CG_MAXITER) / (1 << CG_DIVERGED) set if a solve of the last trajectory ended so."""
         mask = np.empty(self.nchains, dtype=np.int32)

@@ -505,6 +505,44 @@ extern "C" int tb_hmc_trajectory(tb_ctx *ctx, int nsteps, double traj_length, un
   return TB_OK;
 }
 
+// The force of one momentum step, exposed for checking: dS/dA for every link of every chain on the context's current
+// field, exactly what momentum_step subtracts (times eps) from the momenta (hmc.c:504-661): the gauge force
+// (Nf/g) sin A, the pseudofermion force of Re<psi, (M~M)^-1 psi> through chi = (M~M)^-1 psi and M chi, and the force
+// of the stochastic Re<st, M~ st> term as coded.  psi_host: complex [chain][t][x]; st_host may be NULL (no such term).
+// force_host: real [chain][t][x][2].  This is what the reference's disabled CHECK_FORCE block (hmc.c:502,535-559)
+// compares with a finite difference of pseudofermion_action.
+extern "C" int tb_hmc_force(tb_ctx *ctx, const double *psi_host, const double *st_host, double *force_host) {
+  if (!ctx || !psi_host || !force_host) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->have_gauge) { tb_set_error("tb_hmc_force: no gauge field"); return TB_EINVAL; }
+  TB_CHECK(hmc_alloc(ctx));
+  TB_CHECK(tb_synchronize(ctx));
+  cudaStream_t st = ctx->stream;
+  const size_t n = ctx->nsite;
+  auto &H = ctx->hmc;
+  auto upload = [&](const double *host, double2 *dst) -> int {
+    TB_CUDA(cudaMemcpyAsync(ctx->stage, host, n * sizeof(double2), cudaMemcpyHostToDevice, st));
+    return tb_launch_pack(ctx, ctx->stage, dst);
+  };
+  TB_CHECK(links_from(ctx, ctx->Adev));
+  TB_CHECK(upload(psi_host, H.psi));
+  if (st_host) TB_CHECK(upload(st_host, H.st));
+  else TB_CUDA(cudaMemsetAsync(H.st, 0, n * sizeof(double2), st));
+  TB_CUDA(cudaMemsetAsync(H.mom, 0, n * sizeof(double2), st));
+  TB_CUDA(cudaMemcpyAsync(H.newA, ctx->Adev, n * sizeof(double2), cudaMemcpyDeviceToDevice, st));
+  TB_CHECK(tb_run_cg_any(ctx, H.psi, H.chi));                          // hmc.c:515
+  TB_CHECK(tb_launch_dslash(ctx, false, H.chi, H.phi, false));         // hmc.c:516
+  force_kernel<<<ew_blocks(n), 256, 0, st>>>(H.mom, H.newA, H.chi, H.phi, H.st, H.nf_over_g, ctx->d_emu, ctx->d_emmu, 1.0,
+                                              ctx->nt, ctx->nx, ctx->C);   // mom = 0 - 1 * force
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  TB_CHECK(tb_launch_unpack(ctx, H.mom, (double *)ctx->stage_x));
+  TB_CUDA(cudaMemcpyAsync(force_host, ctx->stage_x, n * sizeof(double2), cudaMemcpyDeviceToHost, st));
+  TB_CUDA(cudaStreamSynchronize(st));
+  for (size_t i = 0; i < 2 * n; i++) force_host[i] = -force_host[i];
+  return TB_OK;
+}
+
 // per chain: bit TB_CG_MAXITER / TB_CG_DIVERGED set when a solve of the last trajectory ended that way
 extern "C" int tb_hmc_cg_failures(tb_ctx *ctx, int *mask_host) {
   if (!ctx || !mask_host) return TB_EINVAL;

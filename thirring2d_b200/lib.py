@@ -62,6 +62,7 @@ SIGNATURES = {
     "tb_hmc_trajectory": (_i, [_vp, _i, _d, C.c_ulonglong, C.c_uint, _vp, _vp, _vp, _vp, _vp, _ip,
                                C.POINTER(C.c_longlong)]),
     "tb_hmc_cg_failures": (_i, [_vp, _ip]),
+    "tb_hmc_force": (_i, [_vp, _vp, _vp, _vp]),
     "tb_hmc_measure": (_i, [_vp, _i, C.c_ulonglong, C.c_uint, _vp, _dp, _dp]),
     "tb_hmc_condensate": (_i, [_vp, _i, C.c_ulonglong, C.c_uint, _vp, _dp, C.POINTER(C.c_longlong)]),
     "tb_get_gauge": (_i, [_vp, _vp]),
