@@ -85,20 +85,23 @@ __device__ __forceinline__ RealCoef real_coef(int x, int t0, int nt, int nx, dou
   return k;
 }
 
-// o[i] = m f[i] + hops, i = 0..7, for the thread's column; F: the field with zeros on occupied sites (shared memory)
+// o[i] = m f[i] + hops, i = 0..7, for the thread's column; F: the field with zeros on occupied sites (shared memory).
+// base = t0 * nx + x; the row stride nx is a compile-time constant in the 64 x 64 instantiation (immediate offsets).
 template <typename Epi>
-__device__ __forceinline__ void real_tile_apply(const double (&f)[8], const double *F, int t0, int x, int nt, int nx,
-                                                double m, const RealCoef &k, unsigned occ, Epi epi) {
-  const int tm = t0 == 0 ? nt - 1 : t0 - 1, te = t0 + 8 == nt ? 0 : t0 + 8;
-  const int xp = x + 1 == nx ? 0 : x + 1, xm = x == 0 ? nx - 1 : x - 1;
-  const double below = F[tm * nx + x], above = F[te * nx + x];
+__device__ __forceinline__ void real_tile_apply(const double (&f)[8], const double *F, int base, int off_below,
+                                                int off_above, int dxm, int dxp, int nx, double m, const RealCoef &k,
+                                                unsigned occ, Epi epi) {
+  const double below = F[base + off_below], above = F[base + off_above];
+  // neighbours in t inside the tile come from registers: they must be the MASKED values the exchange field holds
+  double fz[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) fz[i] = ((occ >> i) & 1u) ? 0.0 : f[i];
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    const int row = (t0 + i) * nx;
-    const double l = F[row + xm], r = F[row + xp];
-    // neighbours in t inside the tile come from registers: they must be the MASKED values the exchange field holds
-    const double up = i == 7 ? above : (((occ >> (i + 1)) & 1u) ? 0.0 : f[(i + 1) & 7]);
-    const double dn = i == 0 ? below : (((occ >> (i - 1 + 8) % 8) & 1u) ? 0.0 : f[(i + 7) & 7]);
+    const int row = base + i * nx;
+    const double l = F[row + dxm], r = F[row + dxp];
+    const double up = i == 7 ? above : fz[(i + 1) & 7];
+    const double dn = i == 0 ? below : fz[(i + 7) & 7];
     double o = m * f[i];
     o = fma(i == 7 ? k.up_top : k.up, up, o);
     o = fma(i == 0 ? k.dn_bot : k.dn, dn, o);
@@ -109,15 +112,21 @@ __device__ __forceinline__ void real_tile_apply(const double (&f)[8], const doub
   }
 }
 
-template <bool PROP>
+// NTT, NXT: compile-time lattice shape (64 x 64, the size Thirring.h compiles in), or 0, 0: the shape of the arguments
+template <bool PROP, int NTT, int NXT>
 __global__ void __launch_bounds__(512, 1)
 real_cg_kernel(const double *__restrict__ bsrc, double *__restrict__ xout, const int *__restrict__ field,
                const double *__restrict__ mass, const double *__restrict__ emu, const double *__restrict__ emmu,
-               const TbCgState s, const int nt, const int nx, const int bc) {
+               const TbCgState s, const int nt_rt, const int nx_rt, const int bc) {
   extern __shared__ __align__(16) unsigned char real_smem[];
+  const int nt = NTT ? NTT : nt_rt, nx = NXT ? NXT : nx_rt;
   const int V = nt * nx, c = blockIdx.x, tid = threadIdx.x, nwarps = blockDim.x >> 5;
   double *Fp = reinterpret_cast<double *>(real_smem), *Fm = Fp + V, *scrA = Fm + V, *scrB = scrA + 32;
-  const int x = tid % nx, t0 = (tid / nx) * 8;
+  const int x = tid % nx, t0 = (tid / nx) * 8, base = t0 * nx + x;
+  // offsets of the four halo neighbours relative to a site of the tile (periodic indices; the boundary rules are in
+  // the coefficients)
+  const int off_below = (t0 == 0 ? nt - 1 : -1) * nx, off_above = (t0 + 8 == nt ? 8 - nt : 8) * nx;
+  const int dxm = x == 0 ? nx - 1 : -1, dxp = x + 1 == nx ? 1 - nx : 1;
   const double m = mass[c];
   const RealCoef kM = real_coef(x, t0, nt, nx, emu[c], emmu[c], bc, false);
   const RealCoef kT = real_coef(x, t0, nt, nx, emu[c], emmu[c], bc, true);
@@ -127,17 +136,17 @@ real_cg_kernel(const double *__restrict__ bsrc, double *__restrict__ xout, const
   double r[8], p[8], xv[8];
 #pragma unroll
   for (int i = 0; i < 8; i++) {
-    const int k = (t0 + i) * nx + x;
+    const int k = base + i * nx;
     if (fc[k] != 0) occ |= 1u << i;
     r[i] = bc_[k];
     xv[i] = 0.0;   // vec_zero(inv), vec_ops.c:268
   }
   if (PROP) {   // cg_propagator: the source is M^T source (vec_ops.c:316)
 #pragma unroll
-    for (int i = 0; i < 8; i++) Fp[(t0 + i) * nx + x] = ((occ >> i) & 1u) ? 0.0 : r[i];
+    for (int i = 0; i < 8; i++) Fp[base + i * nx] = ((occ >> i) & 1u) ? 0.0 : r[i];
     __syncthreads();
     double tsrc[8];
-    real_tile_apply(r, Fp, t0, x, nt, nx, m, kT, occ, [&](int i, double o) { tsrc[i] = o; });
+    real_tile_apply(r, Fp, base, off_below, off_above, dxm, dxp, nx, m, kT, occ, [&](int i, double o) { tsrc[i] = o; });
     __syncthreads();   // every thread has read Fp
 #pragma unroll
     for (int i = 0; i < 8; i++) r[i] = tsrc[i];
@@ -147,7 +156,7 @@ real_cg_kernel(const double *__restrict__ bsrc, double *__restrict__ xout, const
   for (int i = 0; i < 8; i++) {
     p[i] = r[i];
     rr = fma(r[i], r[i], rr);
-    Fp[(t0 + i) * nx + x] = ((occ >> i) & 1u) ? 0.0 : p[i];
+    Fp[base + i * nx] = ((occ >> i) & 1u) ? 0.0 : p[i];
   }
   rr = real_block_sum<0>(rr, scrA, nwarps);   // its barrier publishes p
   const double rr_init = rr;
@@ -159,16 +168,16 @@ real_cg_kernel(const double *__restrict__ bsrc, double *__restrict__ xout, const
     for (int k = 1; k < s.max_iter; k++) {   // vec_ops.c:280
       double mp[8], pq = 0.0;
       // M p (vec_ops.c:282), published masked as it is produced; <p, M^T M p> = |M p|^2
-      real_tile_apply(p, Fp, t0, x, nt, nx, m, kM, occ, [&](int i, double o) {
+      real_tile_apply(p, Fp, base, off_below, off_above, dxm, dxp, nx, m, kM, occ, [&](int i, double o) {
         mp[i] = o;
-        Fm[(t0 + i) * nx + x] = ((occ >> i) & 1u) ? 0.0 : o;
+        Fm[base + i * nx] = ((occ >> i) & 1u) ? 0.0 : o;
         pq = fma(o, o, pq);
       });
       pq = real_block_sum<1>(pq, scrB, nwarps);   // its barrier publishes M p
       const double a = rr_old / pq;                // vec_ops.c:285
       rr = 0.0;
       // q = M^T M p consumed on the fly: r -= a q (vec_ops.c:287), ||r||^2
-      real_tile_apply(mp, Fm, t0, x, nt, nx, m, kT, occ, [&](int i, double o) {
+      real_tile_apply(mp, Fm, base, off_below, off_above, dxm, dxp, nx, m, kT, occ, [&](int i, double o) {
         r[i] = fma(-a, o, r[i]);
         rr = fma(r[i], r[i], rr);
       });
@@ -182,7 +191,7 @@ real_cg_kernel(const double *__restrict__ bsrc, double *__restrict__ xout, const
 #pragma unroll
       for (int i = 0; i < 8; i++) {
         p[i] = fma(be, p[i], r[i]);    // vec_ops.c:299
-        Fp[(t0 + i) * nx + x] = ((occ >> i) & 1u) ? 0.0 : p[i];   // the last readers of Fp passed the |Mp|^2 barrier
+        Fp[base + i * nx] = ((occ >> i) & 1u) ? 0.0 : p[i];   // the last readers of Fp passed the |Mp|^2 barrier
       }
       rr_old = rr;
       __syncthreads();
@@ -190,7 +199,7 @@ real_cg_kernel(const double *__restrict__ bsrc, double *__restrict__ xout, const
   }
   double *xc = xout + (size_t)c * V;
 #pragma unroll
-  for (int i = 0; i < 8; i++) xc[(t0 + i) * nx + x] = status == TB_CG_DIVERGED ? 1e50 : xv[i];   // vec_ops.c:294
+  for (int i = 0; i < 8; i++) xc[base + i * nx] = status == TB_CG_DIVERGED ? 1e50 : xv[i];   // vec_ops.c:294
   if (tid == 0) {
     s.status[c] = status;
     s.iters[c] = iters;
@@ -241,7 +250,9 @@ int tb_launch_real_apply(tb_ctx *ctx, bool transpose, const double *d_in, double
 int tb_run_cg_real(tb_ctx *ctx, const double *d_b, double *d_x, bool propagator, int c0, int n, cudaStream_t st) {
   const int V = (int)ctx->V, threads = ctx->nt / 8 * ctx->nx;
   const size_t smem = (size_t)(2 * V + 64) * sizeof(double);
-  auto kern = propagator ? real_cg_kernel<true> : real_cg_kernel<false>;
+  const bool fixed = ctx->nt == 64 && ctx->nx == 64;
+  auto kern = fixed ? (propagator ? real_cg_kernel<true, 64, 64> : real_cg_kernel<false, 64, 64>)
+                    : (propagator ? real_cg_kernel<true, 0, 0> : real_cg_kernel<false, 0, 0>);
   TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   TbCgState s = ctx->cg;   // per-chain outputs of sources c0.. land at their own index
   s.status += c0; s.iters += c0; s.rr += c0; s.rr_init += c0; s.active += c0;
