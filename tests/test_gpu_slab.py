@@ -67,14 +67,11 @@ def _worker(rank, world, port, nt, nx, nchains, m, mu, q):
     os.environ["TB_SLAB_SYNC"] = "2"
     os.environ["TB_SLAB_NREP"] = "1"
     x7, info7 = ctx.fmdm_invert_cg(b)
-    del os.environ["TB_SLAB_NREP"]
-    os.environ["TB_SLAB_SYNC"] = "3"   # a dedicated exchange block gathers the workers' slots
-    xa, infoa = ctx.fmdm_invert_cg(b)
-    del os.environ["TB_SLAB_SYNC"]
+    del os.environ["TB_SLAB_NREP"], os.environ["TB_SLAB_SYNC"]
     x8, info8 = ctx.fmdm_invert_cg(b)
     out.update(b=b, x=x, x2=x2, xi=xi, x4=x4, iters=info.iters, status=info.status, iters2=info2.iters,
                iters4=info4.iters, xm=xm, itersm=infom.iters, x5=x5, iters5=info5.iters, x6=x6, iters6=info6.iters,
-               x7=x7, iters7=info7.iters, x8=x8, iters8=info8.iters, x9=x9, iters9=info9.iters, xa=xa, itersa=infoa.iters)
+               x7=x7, iters7=info7.iters, x8=x8, iters8=info8.iters, x9=x9, iters9=info9.iters)
     q.put((rank, out))
     dist.barrier()
     ctx.close()
@@ -129,7 +126,7 @@ def test_T7_slab_matches_single_gpu(nt, nx, nchains, m, mu, world):
     assert np.array_equal(cat("x5"), xs) and np.array_equal(res[0]["iters5"], res[0]["iters"])
     # block 0's form and the other two cut the slab differently (another summation order of the partials): the same
     # solve to rounding, identical decisions on every rank
-    for k in ("6", "9", "a"):
+    for k in ("6", "9"):
         assert np.linalg.norm(cat("x" + k) - x) <= 1e-12 * np.linalg.norm(x)
         assert np.all(np.abs(res[0]["iters" + k].astype(int) - info.iters.astype(int)) <= 1)
         for r in range(world):

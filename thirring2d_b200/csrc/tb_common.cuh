@@ -102,12 +102,9 @@ struct TbSlab {
   // the totals {total, tag} the last-arriving block of THIS GPU publishes to its other blocks: bcast[rep * bcast_stride + kind*Cpad + c]
   double2 *bcast;
   int bcast_stride;
-  // exchange-block form: one slot {partial, tag} per worker block, slots[block * Cpad + c], in this GPU's memory
-  double2 *slots;
   unsigned long long *timeline;   // optional: globaltimer stamps of the first iterations (TB_SLAB_TIMELINE), else nullptr
 };
 #define TB_SLAB_NREP_MAX 8
-#define TB_SLAB_MAX_SLOTS 2048   /* worker blocks of the exchange-block form */
 #define TB_SLAB_TL_ITERS 64   /* iterations the timeline records */
 #define TB_SLAB_TL_WORDS 8    /* stamps per iteration: phase A first start, last end, stores issued, last total seen; same for B */
 

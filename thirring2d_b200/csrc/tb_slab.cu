@@ -57,12 +57,6 @@ int tb_slab_layout(tb_ctx *ctx) {
   ctx->slab.err = local + 1 + TB_NFLAGS;
   ctx->slab.gbar = (unsigned long long *)(local + 8);   // 8-byte aligned: ints 8, 9
   ctx->slab.go = local + 10;
-  e = cudaMalloc((void **)&ctx->slab.slots, (size_t)TB_SLAB_MAX_SLOTS * ctx->g.Cpad * sizeof(double2));
-  if (e != cudaSuccess) {
-    tb_set_error("cudaMalloc failed: %s", cudaGetErrorString(e));
-    return TB_ENOMEM;
-  }
-  TB_CUDA(cudaMemset(ctx->slab.slots, 0, (size_t)TB_SLAB_MAX_SLOTS * ctx->g.Cpad * sizeof(double2)));
   ctx->slab.P = ctx->nranks;
   ctx->slab.rank = ctx->rank;
   return TB_OK;
@@ -151,6 +145,5 @@ void tb_slab_release(tb_ctx *ctx) {
     if (q != ctx->rank && ctx->peer_block[q]) cudaIpcCloseMemHandle(ctx->peer_block[q]);
   if (ctx->slab.seq) cudaFree(ctx->slab.seq);
   if (ctx->slab.timeline) cudaFree(ctx->slab.timeline);
-  if (ctx->slab.slots) cudaFree(ctx->slab.slots);
   if (ctx->slab_block) cudaFree(ctx->slab_block);
 }

@@ -1032,84 +1032,6 @@ __device__ __forceinline__ void update_scalars(double total, ChainScalars &cs, c
   }
 }
 
-// mode 3: a DEDICATED exchange block (the last block of the grid; it owns no rows).  A worker block stores its partial
-// as {partial, partial xor tag} into its own slot -- value and tag travel together, so nothing separates them: no
-// partial -> fence -> ticket -> gather chain -- and goes to poll the published totals.  The exchange block spins on the
-// workers' slots from the start of the pass (its polls ARE the gather: the moment the last worker's slot turns, the sum
-// is complete), exchanges with the peers and publishes the totals.  Per synchronisation point the critical path is
-// store -> poll -> tree -> system fence -> NVLink -> poll -> publish -> poll.
-template <int RED>
-__device__ __forceinline__ double slab_allreduce_xblock(double acc, const TbGeom &g, const TbCgState &s, const TbSlab &sl,
-                                                        double *red, int gen, unsigned long long *tl) {
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = (blockDim.x + 31) >> 5;
-  const int c_local = tid & (g.bc - 1), x_local = tid >> g.bc_shift;
-  const int nworkers = (int)gridDim.x - 1;
-  const bool stamp = tl && tid == 0 && (blockIdx.x & 15) == 0;
-  // slots are shared by the three kinds of reduction: the tag tells kind and generation
-  const long long tag = (long long)((unsigned long long)(3 * gen + RED) * 0x9E3779B97F4A7C15ULL);
-  auto spin_tagged = [&](const double2 *in, bool nap) {
-    const long long t0 = clock64();
-    for (;;) {
-      long long wx, wy;
-      ld_volatile_v2(in, wx, wy);
-      if ((wx ^ wy) == tag) return __longlong_as_double(wx);
-      if (nap) __nanosleep(20);
-      if (clock64() - t0 > TB_PERSIST_SPIN_CYCLES) __trap();   // a launch error on this rank instead of a hung box
-    }
-  };
-  double total;
-  if ((int)blockIdx.x < nworkers) {
-    for (int o = 16; o >= g.bc; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    __syncthreads();   // red may still be read by the previous call
-    if (lane < g.bc) red[warp * g.bc + lane] = acc;
-    fence_gpu();   // this thread's field stores are visible device-wide before the block's slot turns
-    __syncthreads();
-    if (stamp) atomicMax(&tl[1], global_ns());
-    if (warp == 0 && lane < g.bc) {
-      double t = 0.0;
-      for (int w = 0; w < nwarp; w++) t += red[w * g.bc + lane];
-      st_volatile_v2(sl.slots + (size_t)blockIdx.x * g.Cpad + lane, __double_as_longlong(t), __double_as_longlong(t) ^ tag);
-      const double v = spin_tagged(sl.bcast + (size_t)(blockIdx.x % sl.nrep) * sl.bcast_stride + (size_t)RED * g.Cpad + lane, true);
-      fence_gpu();   // acquire: this GPU's rows (the exchange block saw every slot) and, through it, the neighbours'
-      red[lane] = v;
-    }
-    __syncthreads();
-    total = red[c_local];
-  } else {
-    double sum = 0.0;
-    for (int blk = x_local; blk < nworkers; blk += g.bx) sum += spin_tagged(sl.slots + (size_t)blk * g.Cpad + c_local, false);
-    fence_gpu();   // acquire: the workers' rows behind their slots
-    const double mine = block_sum_chains(sum, g, red);   // threads < bc
-    __syncthreads();
-    if (tid < g.bc) red[tid] = mine;
-    __syncthreads();
-    const bool io = tid < sl.P * g.bc;   // thread (q, chain): store to rank q, poll the slot rank q writes here
-    double theirs = 0.0;
-    if (io) {
-      const int q = tid >> g.bc_shift;
-      const double v = red[c_local];
-      fence_sys();   // this GPU's halo rows before the tag, for the peers
-      st_volatile_v2(sl.peer_red3[q] + (size_t)(RED * sl.P + sl.rank) * g.Cpad + c_local, __double_as_longlong(v),
-                     __double_as_longlong(v) ^ tag);
-      if (tl && tid == 0) tl[2] = global_ns();
-      theirs = spin_tagged(sl.red3 + (size_t)(RED * sl.P + q) * g.Cpad + c_local, false);
-      fence_sys();   // acquire side: the neighbours' rows behind their tags
-    }
-    __syncthreads();   // every storing thread has read red[c]
-    if (io) red[tid] = theirs;   // [q][chain]
-    __syncthreads();
-    total = 0.0;
-    for (int r = 0; r < sl.P; r++) total += red[r * g.bc + c_local];   // rank order: the same bits on every rank
-    if (tid < sl.nrep * g.bc) {   // publish the totals to the workers
-      fence_gpu();
-      st_volatile_v2(sl.bcast + (size_t)(tid >> g.bc_shift) * sl.bcast_stride + (size_t)RED * g.Cpad + c_local,
-                     __double_as_longlong(total), __double_as_longlong(total) ^ tag);
-    }
-  }
-  if (stamp) atomicMax(&tl[3], global_ns());
-  return total;
-}
-
 // Per-chain sum of `acc` over all blocks of all ranks; returns the total of the thread's chain (valid in every thread).
 // mode 2: every block polls the peers' slots (NREP replicas).  mode 1: only the block that arrived last exchanges with
 // the peers (one quiet slot per peer: pollers on a line delay the NVLink store they wait for); it then publishes the
@@ -1123,7 +1045,6 @@ __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, co
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = (blockDim.x + 31) >> 5;
   const int c_local = tid & (g.bc - 1), x_local = tid >> g.bc_shift;
   const bool stamp = tl && tid == 0 && (blockIdx.x & 15) == 0;   // a sample of the blocks records
-  if (mode == 3) return slab_allreduce_xblock<RED>(acc, g, s, sl, red, gen, tl);
   const long long tag = (long long)((unsigned long long)gen * 0x9E3779B97F4A7C15ULL);
   for (int o = 16; o >= g.bc; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   __syncthreads();   // red may still be read by the previous call
@@ -1234,9 +1155,6 @@ slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, 
                          const int mode) {
   __shared__ double red[TB_MAX_BLOCK];
   const int nwork = g.nxtiles * nseg;
-  // mode 3: the last block of the grid is the exchange block and owns no rows
-  const int nworkers = mode == 3 ? (int)gridDim.x - 1 : (int)gridDim.x;
-  const int w_first = (int)blockIdx.x < nworkers ? (int)blockIdx.x : nwork;
   const int R = g.R;   // 32-bit indices: a slab of the one-launch solve has at most 2^27 elements per field
   unsigned long long bar_target = 0;
   const int E0 = *(volatile int *)sl.seq;   // rewritten only after the last grid barrier
@@ -1254,7 +1172,7 @@ slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, 
 
   // ---- x = 0, r = p = b, ||b||^2 (hmc.c:349-361): generation E0 + 1 of p
   double acc = 0.0;
-  for (int w = w_first; w < nwork; w += nworkers) {
+  for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
     const SlabSeg sg = slab_seg(g, w, nseg);
     // the neighbours may still read the previous generation of p (an apply queued before this solve)
     if (sg.t_begin == 0 || sg.t_end == g.nt) {
@@ -1302,7 +1220,7 @@ slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, 
     // ---- A: p = r + beta p on the fly, Mp = M p, |Mp|^2.  The neighbours' rows of r and of the old p are complete:
     // their owners passed the ||r||^2 all-reduce of the previous iteration.
     acc = 0.0;
-    for (int w = w_first; w < nwork; w += nworkers) {
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
       const SlabSeg sg = slab_seg(g, w, nseg);
       const int x = sg.xtile * g.bx + x_local;
       if (!(chain && x < g.nx && act)) continue;
@@ -1365,7 +1283,7 @@ slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, 
     if (tlB && threadIdx.x == 0 && (blockIdx.x & 15) == 0) atomicMin(&tlB[0], global_ns());
     acc = 0.0;
     const double al = cs.alpha;
-    for (int w = w_first; w < nwork; w += nworkers) {
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
       const SlabSeg sg = slab_seg(g, w, nseg);
       const int x = sg.xtile * g.bx + x_local;
       if (!(chain && x < g.nx && act)) continue;
@@ -1941,16 +1859,12 @@ static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int mode, int *
   if (mode == 0) {
     nblocks = g.nxtiles * g.nttiles;
   } else {
-    const int workers = mode == 3 ? capacity - 1 : capacity;
-    nseg = workers / g.nxtiles;
+    nseg = capacity / g.nxtiles;
     if (nseg > ctx->nt) nseg = ctx->nt;
     if (nseg < 1) nseg = 1;
     nblocks = g.nxtiles * nseg;
-    if (nblocks > workers) nblocks = workers;
-    if (mode == 3) nblocks++;   // the exchange block
   }
   if (nblocks > capacity) nblocks = capacity;
-  if (mode == 3 && nblocks - 1 > TB_SLAB_MAX_SLOTS) { *nblocks_out = 0; return TB_OK; }
   if ((size_t)nblocks * g.Cpad > (size_t)ctx->g.nxtiles * ctx->nt * ctx->g.Cpad) { *nblocks_out = 0; return TB_OK; }   // partial[]
   TB_CUDA(cudaMemsetAsync(sl.gbar, 0, sizeof(unsigned long long), ctx->stream));
   sl.nrep = TB_SLAB_NREP_MAX;   // the same on every rank: a rank polls the replicas its peers write
@@ -2011,7 +1925,7 @@ static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int mode, int *
 // loads and the hybrid all-reduce win (2048^2 on 2 GPUs 110.5 vs 120.0, 4096^2 on 8 GPUs 109).
 static int launch_persistent_slab_auto(tb_ctx *ctx, const double2 *b, int *nblocks_out) {
   int mode = ctx->nsite <= ((size_t)1 << 20) ? 0 : 1;
-  if (const char *e = getenv("TB_SLAB_SYNC")) { const int v = atoi(e); if (v >= 0 && v <= 3) mode = v; }
+  if (const char *e = getenv("TB_SLAB_SYNC")) { const int v = atoi(e); if (v >= 0 && v <= 2) mode = v; }
   return launch_persistent_slab(ctx, b, mode, nblocks_out);
 }
 
