@@ -1922,9 +1922,9 @@ static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int mode, int *
 // Which form (measured, us per CG iteration, profiles/slab_r02*.txt): slabs that live in L2 are bound by the two
 // synchronisation points, and there block 0's form is as fast on 2 GPUs (1024^2: 32.1-33.8 vs 32.2-32.7) and faster on 8
 // (2048^2: 33.3 vs 35.0); larger slabs are bound by the passes over the slab, where the balanced row segments, cached
-// loads and the hybrid all-reduce win (2048^2 on 2 GPUs 110.5 vs 120.0, 4096^2 on 8 GPUs 109).
+// loads and the hybrid all-reduce win (2048^2 on 2 GPUs 104.3 vs 117.7, on 4 GPUs 57.5, 4096^2 on 8 GPUs 109).
 static int launch_persistent_slab_auto(tb_ctx *ctx, const double2 *b, int *nblocks_out) {
-  int mode = ctx->nsite <= ((size_t)1 << 20) ? 0 : 1;
+  int mode = ctx->nsite <= ((size_t)3 << 18) ? 0 : 1;   // 768K sites: 2048^2 on 8 GPUs -> block 0's form, on 4 -> hybrid
   if (const char *e = getenv("TB_SLAB_SYNC")) { const int v = atoi(e); if (v >= 0 && v <= 2) mode = v; }
   return launch_persistent_slab(ctx, b, mode, nblocks_out);
 }
