@@ -157,16 +157,6 @@ def test_host_buffer_path_through_the_canonical_layout_kernel(oracle, n, mode, m
         assert np.array_equal(ctx.fm_conjugate_mul(xi), b_host)   # ... and links are the new field's
         x2, i2 = ctx.fmdm_invert_cg(b_host)                 # tb_cg: links from the context
         assert np.array_equal(x2, x_dev) and np.array_equal(i2.iters, it_dev)
-        # more chains than SMs: by now the context has iteration counts, so these run as ONE planned launch that
-        # starts chains as their sub-batch arrives and splits chains between SMs -- still bitwise the same solve
-        ctx.set_gauge(A2)
-        x4, i4 = ctx.fmdm_invert_cg_with_gauge(A, b_host)
-        assert np.array_equal(x4, x_dev) and np.array_equal(i4.iters, it_dev)
-        assert np.array_equal(ctx.get_gauge(), A) and np.array_equal(ctx.fm_conjugate_mul(xi), b_host)
-        os.environ["TB_NO_E2E_PLAN"] = "1"                  # one launch per sub-batch, whole chains
-        x5, i5 = ctx.fmdm_invert_cg_with_gauge(A, b_host)
-        del os.environ["TB_NO_E2E_PLAN"]
-        assert np.array_equal(x5, x_dev)
         os.environ["TB_NO_CANON"] = "1"                     # the re-layout path stays available and agrees
         x3, i3 = ctx.fmdm_invert_cg_with_gauge(A, b_host)
         del os.environ["TB_NO_CANON"]

@@ -219,15 +219,6 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
   for (void *p : dev)
     if (p) cudaFree(p);
   if (ctx->plan_buf) cudaFree(ctx->plan_buf);
-  if (ctx->e2e_arrived) {
-    cudaFree(ctx->e2e_arrived);
-    cudaFree(ctx->e2e_ids_dev);
-    cudaFreeHost(ctx->e2e_done_host);
-    cudaFreeHost(ctx->e2e_epoch_host);
-    cudaFreeHost(ctx->e2e_ids_host);
-    cudaStreamDestroy(ctx->e2e_up);
-    cudaStreamDestroy(ctx->e2e_down);
-  }
   if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   if (ctx->h_iters) cudaFreeHost(ctx->h_iters);
@@ -748,105 +739,6 @@ static int solve_host_canon(tb_ctx *ctx, const double *A_host, const double *b_h
   return TB_OK;
 }
 
-// The same as ONE planned launch (tb_resident.cu: tb_run_cg_resident_canon_planned) for batches of more chains than
-// SMs in ADJOINT mode.  The sub-batch launches above cannot split a chain, so 256 chains on 148 SMs cost two waves of a
-// whole solve; here every SM gets an equal share of CG iterations, starts its first chain when that chain's sub-batch
-// has arrived (a 4-byte flag copied behind the data), and the host issues the D2H copy of a sub-batch when the kernel
-// has counted all its chains finished (system-scope atomics into mapped host memory).  Uploads use one stream, the
-// kernel another, downloads a third; the kernel needs no SM-side helper, so nothing can starve behind its 148 CTAs.
-static int e2e_resources(tb_ctx *ctx) {
-  if (ctx->e2e_arrived) return TB_OK;
-  TB_CUDA(cudaMalloc((void **)&ctx->e2e_arrived, TB_MAX_SUB * sizeof(int)));
-  TB_CUDA(cudaMemset(ctx->e2e_arrived, 0, TB_MAX_SUB * sizeof(int)));
-  TB_CUDA(cudaHostAlloc((void **)&ctx->e2e_done_host, TB_MAX_SUB * sizeof(int), cudaHostAllocMapped));
-  TB_CUDA(cudaHostGetDevicePointer((void **)&ctx->e2e_done_dev, ctx->e2e_done_host, 0));
-  TB_CUDA(cudaHostAlloc((void **)&ctx->e2e_epoch_host, sizeof(int), cudaHostAllocDefault));
-  TB_CUDA(cudaHostAlloc((void **)&ctx->e2e_ids_host, ctx->C * sizeof(int), cudaHostAllocDefault));
-  TB_CUDA(cudaMalloc((void **)&ctx->e2e_ids_dev, ctx->C * sizeof(int)));
-  TB_CUDA(cudaStreamCreateWithFlags(&ctx->e2e_up, cudaStreamNonBlocking));
-  TB_CUDA(cudaStreamCreateWithFlags(&ctx->e2e_down, cudaStreamNonBlocking));
-  // the scheduler's walk order: position floor(j C / M) is the first job of SM j and gets chain j (the first M chains
-  // are the first to arrive); the other positions take the later chains in order
-  int nsm = TB_NUM_SMS_B200;
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-  const int C = ctx->C, M = nsm < C ? nsm : C;
-  int early = 0, late = M, next_first = 0, j = 0;
-  for (int p = 0; p < C; p++) {
-    if (j < M && p == next_first) {
-      ctx->e2e_ids_host[p] = early++;
-      j++;
-      next_first = (int)((long long)j * C / M);
-    } else {
-      ctx->e2e_ids_host[p] = late++;
-    }
-  }
-  TB_CUDA(cudaMemcpy(ctx->e2e_ids_dev, ctx->e2e_ids_host, C * sizeof(int), cudaMemcpyHostToDevice));
-  return TB_OK;
-}
-
-static bool e2e_planned_pays(const tb_ctx *ctx) {
-  int nsm = TB_NUM_SMS_B200;
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-  return ctx->C > nsm && ctx->C <= 40000 && tb_conj_is_dagger(ctx) && getenv("TB_NO_PLAN") == nullptr &&
-         getenv("TB_NO_E2E_PLAN") == nullptr;
-}
-
-static int solve_host_canon_planned(tb_ctx *ctx, const double *A_host, const double *b_host, double *x_host) {
-  TB_CHECK(e2e_resources(ctx));
-  TB_CHECK(join_subs(ctx));
-  const int epoch = ++ctx->e2e_epoch;
-  *ctx->e2e_epoch_host = epoch;
-  for (int s = 0; s < TB_MAX_SUB; s++) ctx->e2e_done_host[s] = 0;
-  cudaStream_t up = ctx->e2e_up, down = ctx->e2e_down, run = ctx->sub_stream[0];
-  TB_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
-  TB_CUDA(cudaEventRecord(ctx->fork_ev, ctx->stream));   // everything queued on the context stream comes first
-  TB_CUDA(cudaStreamWaitEvent(up, ctx->fork_ev, 0));
-  TB_CUDA(cudaStreamWaitEvent(run, ctx->fork_ev, 0));
-  TB_CUDA(cudaStreamWaitEvent(down, ctx->fork_ev, 0));
-  double2 *Ac = (double2 *)ctx->stage, *bc = ctx->vin, *xc = ctx->stage_x;   // canonical device staging
-  TB_CHECK(tb_run_cg_resident_canon_planned(ctx, bc, xc, A_host ? Ac : nullptr, ctx->e2e_arrived, ctx->e2e_done_dev, epoch,
-                                            ctx->e2e_ids_dev, run));
-  for (int s = 0; s < ctx->nsub; s++) {
-    int c0, n;
-    sub_range(ctx, s, &c0, &n);
-    if (n == 0) continue;
-    const size_t off = (size_t)c0 * ctx->V, bytes = (size_t)n * ctx->V * sizeof(double2);
-    if (A_host) TB_CUDA(cudaMemcpyAsync(Ac + off, (const double2 *)A_host + off, bytes, cudaMemcpyHostToDevice, up));
-    TB_CUDA(cudaMemcpyAsync(bc + off, (const double2 *)b_host + off, bytes, cudaMemcpyHostToDevice, up));
-    TB_CUDA(cudaMemcpyAsync(ctx->e2e_arrived + s, ctx->e2e_epoch_host, sizeof(int), cudaMemcpyHostToDevice, up));
-  }
-  // downloads as the sub-batches complete; a kernel that died must not leave the host spinning
-  for (int s = 0; s < ctx->nsub; s++) {
-    int c0, n;
-    sub_range(ctx, s, &c0, &n);
-    if (n == 0) continue;
-    long spins = 0;
-    while (*(volatile int *)&ctx->e2e_done_host[s] < n) {
-      if ((++spins & 0xfff) == 0) {
-        const cudaError_t q = cudaStreamQuery(run);
-        if (q != cudaErrorNotReady && *(volatile int *)&ctx->e2e_done_host[s] < n) {
-          tb_set_error("planned host-buffer solve: the kernel ended (%s) with sub-batch %d incomplete", cudaGetErrorString(q), s);
-          return TB_ECUDA;
-        }
-      }
-    }
-    const size_t off = (size_t)c0 * ctx->V, bytes = (size_t)n * ctx->V * sizeof(double2);
-    TB_CUDA(cudaMemcpyAsync((double2 *)x_host + off, xc + off, bytes, cudaMemcpyDeviceToHost, down));
-  }
-  // the context stream continues behind all three
-  cudaStream_t all[3] = {up, run, down};
-  for (int k = 0; k < 3; k++) {
-    TB_CUDA(cudaEventRecord(ctx->sub_done[k % TB_MAX_SUB], all[k]));
-    TB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->sub_done[k % TB_MAX_SUB], 0));
-  }
-  TB_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
-  TB_CUDA(cudaEventSynchronize(ctx->ev1));
-  float ms = 0.f;
-  TB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-  ctx->last_solve_ms = ms;
-  return TB_OK;
-}
-
 // the solve of a sub-batch starts as soon as ITS links and sources are on the device
 static int solve_host(tb_ctx *ctx, bool with_conj, const double *b_host, double *x_host, int *status, int *iters,
                       double *rr) {
@@ -858,8 +750,7 @@ static int solve_host(tb_ctx *ctx, bool with_conj, const double *b_host, double 
     return TB_EINVAL;
   }
   if (onchip == 1 && !with_conj && tb_resident_canon_supported(ctx)) {
-    if (e2e_planned_pays(ctx)) TB_CHECK(solve_host_canon_planned(ctx, nullptr, b_host, x_host));
-    else TB_CHECK(solve_host_canon(ctx, nullptr, b_host, x_host));
+    TB_CHECK(solve_host_canon(ctx, nullptr, b_host, x_host));
   } else if (!onchip || with_conj) {
     TB_CHECK(upload_vec(ctx, b_host, ctx->vin));
     if (with_conj) TB_CHECK(tb_invert_dev(ctx, (const double *)ctx->vin, (double *)ctx->vout));
@@ -899,8 +790,7 @@ extern "C" int tb_cg_gauge(tb_ctx *ctx, const double *A_host, const double *b_ho
     return solve_host(ctx, false, b_host, x_host, status, iters, rr);
   }
   if (onchip == 1 && tb_resident_canon_supported(ctx)) {
-    if (e2e_planned_pays(ctx)) TB_CHECK(solve_host_canon_planned(ctx, A_host, b_host, x_host));
-    else TB_CHECK(solve_host_canon(ctx, A_host, b_host, x_host));
+    TB_CHECK(solve_host_canon(ctx, A_host, b_host, x_host));
     if (status || iters || rr) TB_CHECK(tb_cg_result(ctx, status, iters, rr));
     return TB_OK;
   }

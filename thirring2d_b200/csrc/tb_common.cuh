@@ -158,12 +158,6 @@ struct tb_ctx {
   cudaEvent_t sub_done[TB_MAX_SUB], fork_ev;
   int nsub;
   int sub_c0[TB_MAX_SUB + 1];   // sub-batch s holds chains [sub_c0[s], sub_c0[s + 1])
-  // planned launch over arriving host buffers (solve_host_canon_planned): arrival flags (device), completion counters
-  // (pinned host memory mapped into the device), the epoch value, the scheduler's walk order
-  int *e2e_arrived, *e2e_done_host, *e2e_done_dev, *e2e_epoch_host, *e2e_ids_dev, *e2e_ids_host;
-  int e2e_epoch;
-  cudaStream_t e2e_up, e2e_down;
-  bool e2e_have_estimates;   // the previous solve of the context left iteration counts for every chain
   bool sub_pending;  // work queued on the sub-streams that the context stream has not joined yet
   double2 *stage_x;  // second canonical staging buffer (results)
   double last_solve_ms;
@@ -201,8 +195,6 @@ bool tb_resident_supported(const tb_ctx *ctx);
 bool tb_resident_canon_supported(const tb_ctx *ctx);
 int tb_run_cg_resident_canon(tb_ctx *ctx, const double2 *b_canon, double2 *x_canon, const double2 *A_canon, int c0, int n,
                              cudaStream_t st);
-int tb_run_cg_resident_canon_planned(tb_ctx *ctx, const double2 *b_canon, double2 *x_canon, const double2 *A_canon,
-                                     const int *d_arrived, int *d_done, int epoch, const int *d_ids, cudaStream_t st);
 bool tb_cluster_supported(tb_ctx *ctx);
 int tb_cluster_capacity(tb_ctx *ctx);
 int tb_run_cg_cluster_slice(tb_ctx *ctx, const double2 *b, double2 *x, int c0, int n, cudaStream_t st);

@@ -238,16 +238,6 @@ __device__ __noinline__ int plan_wait_hand(const int *hand) {
 }
 
 
-// one thread: wait until the inputs of a sub-batch of chains have arrived (the flag is written by a copy on the upload
-// stream, behind the data)
-__device__ __noinline__ void plan_wait_arrival(const int *flag, int epoch) {
-  const long long t_spin = clock64();
-  while (*(const volatile int *)flag != epoch) {
-    __nanosleep(500);
-    if (clock64() - t_spin > TB_PLAN_SPIN_CYCLES) __trap();
-  }
-}
-
 // The schedule of a planned launch (one thread: C is a few hundred).  est = iteration counts of the context's previous
 // solve.  Machines are filled one after the other with T = ceil(sum est / M) iterations each; the chain that straddles
 // the boundary between machine j (its end) and j + 1 (its start) is split: head [1, 1 + first) FIRST on machine
@@ -255,9 +245,8 @@ __device__ __noinline__ void plan_wait_arrival(const int *flag, int epoch) {
 // Without usable estimates (first solve of a context, or a chain that did not converge) chains are dealt out whole,
 // round-robin, which is what the hardware does with one CTA per chain.
 // Host and device: tb_plan_schedule (tb_resident.cu) runs the same code on the CPU for tests/test_plan_schedule.py.
-// ids (optional): the chain behind position c of the walk (est is indexed by position); nullptr = chain c itself
 __host__ __device__ inline void plan_fill(const int *est, int C, int M, long long W, int mx, int4 *segs, int *seg_lo,
-                                          int *seg_hi, const int *ids = nullptr) {
+                                          int *seg_hi) {
   // A hand-over is not worth fewer than MINS iterations on either side.  A machine may therefore run over its share by
   // a few iterations (a chain that overshoots by less than MINS stays whole; a tail of MINS/2 .. MINS iterations is
   // stretched to MINS) or stay up to MINS/2 - 1 under it, and the share of the machines still to fill is recomputed from
@@ -281,19 +270,19 @@ __host__ __device__ inline void plan_fill(const int *est, int C, int M, long lon
       rem = share(j);
     }
     if (j == M - 1 || n - rem < MINS || n < 2 * MINS) {   // whole
-      segs[nseg++] = make_int4(ids ? ids[c] : c, 1, INF, 0);
+      segs[nseg++] = make_int4(c, 1, INF, 0);
       rem -= n;
       left -= n;
     } else {
       const long long piece = rem > MINS ? rem : MINS;   // iterations of c that machine j runs: the tail, its last job
       const int first = (int)(n - piece);                // >= MINS; the head: first job of machine j + 1
-      segs[nseg++] = make_int4(ids ? ids[c] : c, 1 + first, INF, 0);
+      segs[nseg++] = make_int4(c, 1 + first, INF, 0);
       left -= piece;
       seg_hi[M - 1 - j] = nseg;
       j++;
       seg_lo[M - 1 - j] = nseg;
       rem = share(j);
-      segs[nseg++] = make_int4(ids ? ids[c] : c, 1, 1 + first, 0);
+      segs[nseg++] = make_int4(c, 1, 1 + first, 0);
       rem -= first;
       left -= first;
     }
@@ -312,7 +301,7 @@ __host__ __device__ inline void plan_deal(int b, int C, int M, int4 *segs, int *
 }
 
 __global__ void plan_kernel(const int *__restrict__ est, const int *__restrict__ status, int C, int M, int4 *segs,
-                            int *seg_lo, int *seg_hi, int *hand, const int *__restrict__ ids) {
+                            int *seg_lo, int *seg_hi, int *hand) {
   extern __shared__ int est_s[];   // [C]: one thread walks the chains, out of shared memory
   __shared__ long long W_s;
   __shared__ int mx_s, bad_s;
@@ -322,9 +311,9 @@ __global__ void plan_kernel(const int *__restrict__ est, const int *__restrict__
   int mx = 0, bad = 0;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     hand[c] = 0;
-    const int n = est[ids ? ids[c] : c];   // position c of the walk
+    const int n = est[c];
     est_s[c] = n;
-    if (n <= 0 || status[ids ? ids[c] : c] != TB_CG_CONVERGED) bad = 1;
+    if (n <= 0 || status[c] != TB_CG_CONVERGED) bad = 1;
     w += n;
     mx = n > mx ? n : mx;
   }
@@ -336,12 +325,12 @@ __global__ void plan_kernel(const int *__restrict__ est, const int *__restrict__
     for (int b = threadIdx.x; b < M; b += blockDim.x) plan_deal(b, C, M, segs, seg_lo, seg_hi);
     return;
   }
-  if (threadIdx.x == 0) plan_fill(est_s, C, M, W_s, mx_s, segs, seg_lo, seg_hi, ids);
+  if (threadIdx.x == 0) plan_fill(est_s, C, M, W_s, mx_s, segs, seg_lo, seg_hi);
 }
 
 
 // plan_kernel on the context's stream; M = CTAs (64^2) or clusters (128^2, 256^2) of the planned launch
-static int plan_prepare(tb_ctx *ctx, int M, cudaStream_t st, TbPlan *pl, const int *d_ids = nullptr) {
+static int plan_prepare(tb_ctx *ctx, int M, cudaStream_t st, TbPlan *pl) {
   const int C = ctx->C;
   if (!ctx->plan_buf) {
     const int mmax = TB_NUM_SMS_B200 > M ? TB_NUM_SMS_B200 : M;
@@ -352,7 +341,7 @@ static int plan_prepare(tb_ctx *ctx, int M, cudaStream_t st, TbPlan *pl, const i
   int4 *segs = (int4 *)ctx->plan_buf;
   int *lo = ctx->plan_buf + (size_t)(C + ctx->plan_m) * 4, *hi = lo + ctx->plan_m, *hand = hi + ctx->plan_m;
   if (C > 12000) TB_CUDA(cudaFuncSetAttribute(plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C * (int)sizeof(int)));
-  plan_kernel<<<1, 256, C * sizeof(int), st>>>(ctx->cg.iters, ctx->cg.status, C, M, segs, lo, hi, hand, d_ids);
+  plan_kernel<<<1, 256, C * sizeof(int), st>>>(ctx->cg.iters, ctx->cg.status, C, M, segs, lo, hi, hand);
   ctx->launches++;
   pl->segs = segs; pl->seg_lo = lo; pl->seg_hi = hi; pl->hand = hand;
   pl->sr = ctx->r; pl->sp = ctx->p; pl->sx = ctx->q;

@@ -364,21 +364,7 @@ struct ResidentWtCfg {
 struct TbCanon {
   const double2 *A;          // canonical angles [chain][t][x] = (A_t, A_x), or nullptr: links are read from W0g / W1g
   double2 *W0, *W1, *Adev;   // device-layout outputs (only with A)
-  // Planned launch over host buffers that are still arriving: the chains travel in nsub sub-batches (chains
-  // [sub_c0[s], sub_c0[s+1])); arrived[s] turns to `epoch` behind the H2D copies of sub-batch s (a 4-byte copy on the
-  // same stream), and a CTA waits for it before it starts a chain from its source.  done[s] (host memory, mapped)
-  // counts the finished chains of sub-batch s: the host issues the D2H copy of a sub-batch when its count is full.
-  const int *arrived;
-  int *done;
-  int epoch, nsub;
-  int sub_c0[TB_MAX_SUB + 1];
 };
-
-__device__ __forceinline__ int canon_sub_of(const TbCanon &cn, int c) {
-  int s = 0;
-  while (s + 1 < cn.nsub && c >= cn.sub_c0[s + 1]) s++;
-  return s;
-}
 
 template <int NT, int NX, bool DAG, bool HAS_MU, bool MASKED, bool PLAN, bool CANON = false>
 __global__ void __launch_bounds__(ResidentWtCfg<NT, NX>::NTHREADS, 1)
@@ -428,9 +414,6 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
           const int h = plan_wait_hand(&plan.hand[q.x]);
           __threadfence();
           if (h < 0) q.y = -1;   // the chain ended inside its head
-        } else if (CANON && canon.arrived && q.x >= 0) {   // a fresh start: the chain's inputs may still be crossing PCIe
-          plan_wait_arrival(&canon.arrived[canon_sub_of(canon, q.x)], canon.epoch);
-          __threadfence();
         }
       }
       sv[0] = q.x; sv[1] = q.y; sv[2] = q.z; sv[3] = sg + 1;
@@ -663,7 +646,7 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
                       : make_double2(0.0, 0.0);
     }
   }
-  __syncthreads();   // every warp has read its columns (and stored its part of x)
+  __syncthreads();   // every warp has read its columns
   if (tid == 0) {
     s.status[c] = status;
     s.iters[c] = iters;
@@ -673,10 +656,6 @@ resident_wt_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout,
     if (PLAN && sv[2] != 0x7fffffff) {   // the chain ended inside its head: the CTA that holds the tail skips it
       __threadfence();
       *(volatile int *)&plan.hand[c] = -1;
-    }
-    if (CANON && canon.done) {   // the solution of chain c is complete in device memory: tell the host
-      __threadfence_system();
-      atomicAdd_system(&canon.done[canon_sub_of(canon, c)], 1);
     }
   }
   }   // segments
@@ -799,33 +778,8 @@ bool tb_resident_canon_supported(const tb_ctx *ctx) {
 int tb_run_cg_resident_canon(tb_ctx *ctx, const double2 *b_canon, double2 *x_canon, const double2 *A_canon, int c0, int n,
                              cudaStream_t st) {
   if (!tb_resident_canon_supported(ctx)) return TB_EINVAL;
-  TbCanon cn = {A_canon, ctx->W0, ctx->W1, ctx->Adev, nullptr, nullptr, 0, 0, {0}};
+  TbCanon cn = {A_canon, ctx->W0, ctx->W1, ctx->Adev};
   return launch_resident_wt<64, 64>(ctx, b_canon, x_canon, c0, n, st, &cn);
-}
-
-// The same over host buffers that are still arriving, as ONE planned launch (one CTA per SM, equal shares of CG
-// iterations, chains paused and resumed): a CTA waits for the arrival flag of a chain's sub-batch before it starts
-// the chain and counts finished chains per sub-batch into host memory, so uploads, solves and downloads overlap
-// although a single kernel runs (tb_api.cu: solve_host_canon_planned).  d_ids: the order in which the scheduler walks
-// the chains (every SM's first job is a chain of the first wave of arrivals).  ADJOINT mode only.
-int tb_run_cg_resident_canon_planned(tb_ctx *ctx, const double2 *b_canon, double2 *x_canon, const double2 *A_canon,
-                                     const int *d_arrived, int *d_done, int epoch, const int *d_ids, cudaStream_t st) {
-  if (!tb_resident_canon_supported(ctx) || !tb_conj_is_dagger(ctx)) return TB_EINVAL;
-  using Cfg = ResidentWtCfg<64, 64>;
-  int nsm = TB_NUM_SMS_B200;
-  cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device);
-  TbPlan pl = {};
-  TB_CHECK(plan_prepare(ctx, nsm, st, &pl, d_ids));
-  TbCanon cn = {A_canon, ctx->W0, ctx->W1, ctx->Adev, d_arrived, d_done, epoch, ctx->nsub, {0}};
-  for (int s = 0; s <= ctx->nsub; s++) cn.sub_c0[s] = ctx->sub_c0[s];
-  auto kern = ctx->has_mu ? resident_wt_kernel<64, 64, true, true, false, true, true>
-                          : resident_wt_kernel<64, 64, true, false, false, true, true>;
-  TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
-  kern<<<nsm, Cfg::NTHREADS, Cfg::SMEM, st>>>(b_canon, x_canon, ctx->W0, ctx->W1, ctx->d_mass, ctx->msite, ctx->d_emu,
-                                              ctx->d_emmu, ctx->cg, ctx->C, 0, pl, cn);
-  ctx->launches++;
-  TB_CUDA(cudaGetLastError());
-  return TB_OK;
 }
 
 int tb_run_cg_resident(tb_ctx *ctx, const double2 *b, double2 *x) {
