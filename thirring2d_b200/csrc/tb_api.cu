@@ -702,10 +702,40 @@ extern "C" int tb_cg_real(tb_ctx *ctx, const double *b_host, double *x_host, int
   return rc;
 }
 
+// Small contexts (one sub-batch: fewer than 32 chains, e.g. the single chain of the interposed reference driver) run
+// a host-buffer call on the context's stream alone -- copy in, kernels, copy out, ONE synchronisation -- instead of
+// forking and joining sub-batch streams around every stage: an interposed fm_mul or fmdm_invert_cg is a handful of
+// driver calls instead of some twenty-five.
+static bool single_stream_path(const tb_ctx *ctx) { return ctx->nsub == 1 && ctx->nranks == 1 && !getenv("TB_NO_FASTPATH"); }
+
+static int h2d_vec(tb_ctx *ctx, const double *host, double2 *d_vec) {
+  if (ctx->C == 1) return cudaMemcpyAsync(d_vec, host, ctx->nsite * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess ? TB_OK : TB_ECUDA;
+  TB_CUDA(cudaMemcpyAsync(ctx->stage, host, ctx->nsite * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+  return tb_launch_pack(ctx, ctx->stage, d_vec);
+}
+
+static int d2h_vec(tb_ctx *ctx, const double2 *d_vec, double *host) {
+  const double2 *src = d_vec;
+  if (ctx->C > 1) {
+    TB_CHECK(tb_launch_unpack(ctx, d_vec, (double *)ctx->stage_x));
+    src = ctx->stage_x;
+  }
+  TB_CUDA(cudaMemcpyAsync(host, src, ctx->nsite * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+  return TB_OK;
+}
+
 extern "C" int tb_apply(tb_ctx *ctx, int op, const double *in_host, double *out_host) {
   if (!ctx || !in_host || !out_host) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
   TB_CHECK(need_gauge(ctx));
+  if (single_stream_path(ctx)) {
+    TB_CHECK(join_subs(ctx));
+    TB_CHECK(h2d_vec(ctx, in_host, ctx->vin));
+    TB_CHECK(tb_apply_dev(ctx, op, (const double *)ctx->vin, (double *)ctx->vout));
+    TB_CHECK(d2h_vec(ctx, ctx->vout, out_host));
+    TB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return TB_OK;
+  }
   TB_CHECK(upload_vec(ctx, in_host, ctx->vin));
   TB_CHECK(tb_apply_dev(ctx, op, (const double *)ctx->vin, (double *)ctx->vout));  // joins the sub-streams
   return download_vec(ctx, ctx->vout, out_host);
@@ -748,6 +778,32 @@ static int solve_host(tb_ctx *ctx, bool with_conj, const double *b_host, double 
   if (ctx->tune_solver == 2 && !onchip) {
     tb_set_error("on-chip solver requested but %dx%d is not supported", ctx->nt, ctx->nx);
     return TB_EINVAL;
+  }
+  if (single_stream_path(ctx) && onchip) {
+    cudaStream_t st = ctx->stream;
+    const size_t c = ctx->C;
+    TB_CHECK(join_subs(ctx));
+    TB_CUDA(cudaEventRecord(ctx->ev0, st));
+    TB_CHECK(h2d_vec(ctx, b_host, ctx->vin));
+    const double2 *src = ctx->vin;
+    if (with_conj) {   // fm_invert_cg, hmc.c:408-414
+      TB_CHECK(tb_launch_dslash(ctx, tb_conj_is_dagger(ctx), ctx->vin, ctx->tmp, false));
+      src = ctx->tmp;
+    }
+    TB_CHECK(run_onchip_slice(ctx, onchip, src, ctx->vout, 0, ctx->C, st));
+    TB_CHECK(d2h_vec(ctx, ctx->vout, x_host));
+    TB_CUDA(cudaMemcpyAsync(ctx->h_status, ctx->cg.status, c * sizeof(int), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaMemcpyAsync(ctx->h_iters, ctx->cg.iters, c * sizeof(int), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaMemcpyAsync(ctx->h_rr, ctx->cg.rr, c * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TB_CUDA(cudaEventRecord(ctx->ev1, st));
+    TB_CUDA(cudaStreamSynchronize(st));
+    float ms = 0.f;
+    TB_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_solve_ms = ms;
+    if (status) memcpy(status, ctx->h_status, c * sizeof(int));
+    if (iters) memcpy(iters, ctx->h_iters, c * sizeof(int));
+    if (rr) memcpy(rr, ctx->h_rr, c * sizeof(double));
+    return TB_OK;
   }
   if (onchip == 1 && !with_conj && tb_resident_canon_supported(ctx)) {
     TB_CHECK(solve_host_canon(ctx, nullptr, b_host, x_host));
