@@ -21,6 +21,8 @@ static struct {
   int have_A;
   int mu_frozen;
   double mu_at_first_call;
+  int params_set;       /* what the context holds: uploaded again only when the driver's m moved */
+  double m_set, mu_set;
   double *p_m, *p_mu;  /* the driver's globals, hmc.c:38,40 */
   long cg_calls, apply_calls, traj_calls;
   /* coarse override (update_gauge as one device-resident trajectory) */
@@ -84,7 +86,9 @@ static void sync_params(void) {
   }
   if (!S.mu_frozen) { S.mu_at_first_call = *S.p_mu; S.mu_frozen = 1; }
   double m = *S.p_m, mu = S.mu_at_first_call;
+  if (S.params_set && m == S.m_set && mu == S.mu_set) return;   /* read at every call, uploaded when it moved */
   if (tb_set_params(S.ctx, &m, &mu, 1) != TB_OK) die("tb_set_params");
+  S.params_set = 1; S.m_set = m; S.mu_set = mu;
 }
 
 static void sync_gauge(double ***A) {

@@ -565,9 +565,39 @@ static int download_vec(tb_ctx *ctx, const double2 *d_vec, double *host) {
   return sync_all(ctx);
 }
 
+// Small contexts (one sub-batch: fewer than 32 chains, e.g. the single chain of the interposed reference driver) run
+// a host-buffer call on the context's stream alone -- copy in, kernels, copy out, ONE synchronisation -- instead of
+// forking and joining sub-batch streams around every stage: an interposed fm_mul or fmdm_invert_cg is a handful of
+// driver calls instead of some twenty-five.
+static bool single_stream_path(const tb_ctx *ctx) { return ctx->nsub == 1 && ctx->nranks == 1 && !getenv("TB_NO_FASTPATH"); }
+
+static int h2d_vec(tb_ctx *ctx, const double *host, double2 *d_vec) {
+  if (ctx->C == 1) return cudaMemcpyAsync(d_vec, host, ctx->nsite * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess ? TB_OK : TB_ECUDA;
+  TB_CUDA(cudaMemcpyAsync(ctx->stage, host, ctx->nsite * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+  return tb_launch_pack(ctx, ctx->stage, d_vec);
+}
+
+static int d2h_vec(tb_ctx *ctx, const double2 *d_vec, double *host) {
+  const double2 *src = d_vec;
+  if (ctx->C > 1) {
+    TB_CHECK(tb_launch_unpack(ctx, d_vec, (double *)ctx->stage_x));
+    src = ctx->stage_x;
+  }
+  TB_CUDA(cudaMemcpyAsync(host, src, ctx->nsite * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
+  return TB_OK;
+}
+
 extern "C" int tb_set_gauge(tb_ctx *ctx, const double *A_host) {
   if (!ctx || !A_host) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
+  if (single_stream_path(ctx)) {
+    TB_CHECK(join_subs(ctx));
+    TB_CHECK(h2d_vec(ctx, A_host, ctx->Adev));
+    TB_CHECK(tb_launch_links(ctx, (const double *)ctx->Adev));
+    ctx->msite = nullptr;
+    ctx->have_gauge = true;
+    return TB_OK;
+  }
   TB_CHECK(upload_vec(ctx, A_host, ctx->Adev));
   for (int s = 0; s < ctx->nsub; s++) {
     int c0, n;
@@ -700,28 +730,6 @@ extern "C" int tb_cg_real(tb_ctx *ctx, const double *b_host, double *x_host, int
   free(st);
   free(cb);
   return rc;
-}
-
-// Small contexts (one sub-batch: fewer than 32 chains, e.g. the single chain of the interposed reference driver) run
-// a host-buffer call on the context's stream alone -- copy in, kernels, copy out, ONE synchronisation -- instead of
-// forking and joining sub-batch streams around every stage: an interposed fm_mul or fmdm_invert_cg is a handful of
-// driver calls instead of some twenty-five.
-static bool single_stream_path(const tb_ctx *ctx) { return ctx->nsub == 1 && ctx->nranks == 1 && !getenv("TB_NO_FASTPATH"); }
-
-static int h2d_vec(tb_ctx *ctx, const double *host, double2 *d_vec) {
-  if (ctx->C == 1) return cudaMemcpyAsync(d_vec, host, ctx->nsite * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess ? TB_OK : TB_ECUDA;
-  TB_CUDA(cudaMemcpyAsync(ctx->stage, host, ctx->nsite * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
-  return tb_launch_pack(ctx, ctx->stage, d_vec);
-}
-
-static int d2h_vec(tb_ctx *ctx, const double2 *d_vec, double *host) {
-  const double2 *src = d_vec;
-  if (ctx->C > 1) {
-    TB_CHECK(tb_launch_unpack(ctx, d_vec, (double *)ctx->stage_x));
-    src = ctx->stage_x;
-  }
-  TB_CUDA(cudaMemcpyAsync(host, src, ctx->nsite * sizeof(double2), cudaMemcpyDeviceToHost, ctx->stream));
-  return TB_OK;
 }
 
 extern "C" int tb_apply(tb_ctx *ctx, int op, const double *in_host, double *out_host) {
