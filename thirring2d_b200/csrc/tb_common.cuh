@@ -46,7 +46,6 @@ struct TbGeom {
   int tt;             // rows marched per thread
   int nslots;         // partial sums per chain = nxtiles*nttiles
   int Cpad;           // nctiles*bc
-  int pf;             // marching kernels: rows ahead that are prefetched into L2 (0 = none)
 };
 
 // Per-chain scalars of the batched CG (device arrays of length Cpad unless noted).

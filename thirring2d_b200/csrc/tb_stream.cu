@@ -32,10 +32,6 @@ namespace {
 //   SLAB protocol (epoch E = *sl.seq): wait flag `wait_ready` >= E on the sides this block touches, and
 //   `wait_done` >= E-1 before overwriting `out` rows a neighbour may still be reading; when the whole grid
 //   is done, publish `sig0`/`sig1` = E to both neighbours.
-// L2 prefetch of a row the march will reach g.pf rows from now: it costs no register and no scoreboard slot, so the
-// bytes a thread has in flight are no longer bounded by the one row of loads its registers can hold
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];\n" ::"l"(p)); }
-
 template <int TT, bool DAG, bool DOT, bool MASKED, bool SLAB>
 __global__ void __launch_bounds__(TB_MAX_BLOCK)
 dslash_kernel(const double2 *__restrict__ in, const double2 *in_prev, const double2 *in_next,
@@ -89,12 +85,6 @@ dslash_kernel(const double2 *__restrict__ in, const double2 *in_prev, const doub
       const int t = t0 + i;
       if (t < g.nt) {
         const size_t row = t * R;
-        if (g.pf > 0 && t + g.pf + 1 < g.nt) {
-          const size_t rp = (size_t)(t + g.pf) * R + j;
-          prefetch_l2(&in[rp + R]);
-          prefetch_l2(&W0[rp]);
-          prefetch_l2(&W1[rp]);
-        }
         const double2 pp = (t + 1 == g.nt) ? ld_halo<SLAB>(&in_next[j]) : in[row + R + j];
         const double2 pxp = in[row + jp];
         const double2 pxm = in[row + jm];
@@ -225,15 +215,6 @@ dslash_axpy_norm_kernel(const double2 *__restrict__ in, const double2 *in_prev, 
       const int t = t0 + i;
       if (t < g.nt) {
         const size_t row = t * R;
-        if (g.pf > 0 && t + g.pf + 1 < g.nt) {
-          const size_t rp = (size_t)(t + g.pf) * R + j;
-          prefetch_l2(&in[rp + R]);
-          prefetch_l2(&W0[rp]);
-          prefetch_l2(&W1[rp]);
-          prefetch_l2(&p[rp]);
-          prefetch_l2(&x[rp]);
-          prefetch_l2(&r[rp]);
-        }
         const double2 pp = (t + 1 == g.nt) ? ld_halo<SLAB>(&in_next[j]) : in[row + R + j];
         const double2 pxp = in[row + jp];
         const double2 pxm = in[row + jm];
@@ -1548,8 +1529,6 @@ int tb_choose_geom(tb_ctx *ctx) {
     const long nb1 = (long)g.nctiles * g.nxtiles;
     while (tt > 1 && nb1 * ((ctx->nt + tt - 1) / tt) < 6L * TB_NUM_SMS_B200) tt >>= 1;
   }
-  g.pf = 0;
-  if (const char *e = getenv("TB_PREFETCH")) g.pf = atoi(e);
   g.tt = tt;
   g.nttiles = (ctx->nt + tt - 1) / tt;
   g.nslots = g.nxtiles * g.nttiles;
