@@ -69,9 +69,12 @@ def _worker(rank, world, port, nt, nx, nchains, m, mu, q):
     x7, info7 = ctx.fmdm_invert_cg(b)
     del os.environ["TB_SLAB_NREP"], os.environ["TB_SLAB_SYNC"]
     x8, info8 = ctx.fmdm_invert_cg(b)
+    os.environ["TB_SLAB_SYSFENCE"] = "1"   # system-scope instead of device-scope fences around the peer exchange
+    xf, infof = ctx.fmdm_invert_cg(b)
+    del os.environ["TB_SLAB_SYSFENCE"]
     out.update(b=b, x=x, x2=x2, xi=xi, x4=x4, iters=info.iters, status=info.status, iters2=info2.iters,
                iters4=info4.iters, xm=xm, itersm=infom.iters, x5=x5, iters5=info5.iters, x6=x6, iters6=info6.iters,
-               x7=x7, iters7=info7.iters, x8=x8, iters8=info8.iters, x9=x9, iters9=info9.iters)
+               x7=x7, iters7=info7.iters, x8=x8, iters8=info8.iters, x9=x9, iters9=info9.iters, xf=xf, itersf=infof.iters)
     q.put((rank, out))
     dist.barrier()
     ctx.close()
@@ -134,3 +137,4 @@ def test_T7_slab_matches_single_gpu(nt, nx, nchains, m, mu, world):
     # who polls does not change a bit of the arithmetic
     assert np.array_equal(cat("x7"), cat("x9")) and np.array_equal(res[0]["iters7"], res[0]["iters9"])
     assert np.array_equal(cat("x8"), xs) and np.array_equal(res[0]["iters8"], res[0]["iters"])
+    assert np.array_equal(cat("xf"), xs) and np.array_equal(res[0]["itersf"], res[0]["iters"])   # the scope of a fence changes no bit

@@ -620,6 +620,7 @@ struct SlabCgArgs {
   const double2 *p_prev, *p_next, *p1_prev, *p1_next, *r_prev, *r_next, *mp_prev, *mp_next;
   const double2 *W0, *W0_prev, *W1;
   const double *mass, *emu, *emmu;
+  int sysfence;   // 1: system-scope fences around the peer exchange (TB_SLAB_SYSFENCE=1), 0: device scope (see xgpu_fence)
 };
 
 __device__ __forceinline__ void spin_until(volatile int *f, int need) {
@@ -715,7 +716,7 @@ __device__ __forceinline__ void ld_volatile_v2(const double2 *p, long long &x, l
 // slot that rank q writes into this GPU's memory.
 template <int FIN, int RED>
 __device__ __forceinline__ void block0_scalars(const TbGeom &g, const TbCgState &s, const TbSlab &sl, double *red,
-                                               int seqv, int go_value) {
+                                               int seqv, int go_value, int sysfence) {
   const int c_local = threadIdx.x & (g.bc - 1), x_local = threadIdx.x >> g.bc_shift;
   double sum = 0.0;
   for (int blk = x_local; blk < (int)gridDim.x; blk += g.bx) sum += __ldcg(&s.partial[(size_t)blk * g.Cpad + c_local]);
@@ -729,7 +730,7 @@ __device__ __forceinline__ void block0_scalars(const TbGeom &g, const TbCgState 
   double theirs = 0.0;
   if (io) {
     const double v = red[c_local];
-    __threadfence_system();   // this GPU's halo rows (visible device-wide since the grid barrier) before the tag
+    if (sysfence) __threadfence_system(); else __threadfence();   // this GPU's halo rows (visible device-wide since the grid barrier) before the tag
     const long long tag = (long long)((unsigned long long)seqv * 0x9E3779B97F4A7C15ULL);
     st_volatile_v2(sl.peer_red2[q] + slot + (size_t)sl.rank * g.Cpad, __double_as_longlong(v), __double_as_longlong(v) ^ tag);
     const double2 *in = sl.red2 + slot + (size_t)q * g.Cpad;
@@ -752,7 +753,7 @@ __device__ __forceinline__ void block0_scalars(const TbGeom &g, const TbCgState 
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence_system();   // acquire side of the exchange: the neighbours' rows, for the blocks that wait on go
+    if (sysfence) __threadfence_system(); else __threadfence();   // acquire side of the exchange: the neighbours' rows, for the blocks that wait on go
     *(volatile int *)sl.go = go_value;
   }
 }
@@ -815,7 +816,7 @@ slab_cg_persistent_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s,
   block_partial(acc, g, s, red);
   grid_arrive(sl.gbar, bar_target);
   int gen = E0 + 1;   // generation of p
-  if (blockIdx.x == 0) block0_scalars<FIN_INIT, TB_RED_INIT>(g, s, sl, red, gen, 3 * gen);
+  if (blockIdx.x == 0) block0_scalars<FIN_INIT, TB_RED_INIT>(g, s, sl, red, gen, 3 * gen, a.sysfence);
   wait_go(sl, 3 * gen);
 
   // p is double-buffered: odd iterations read p_old from a.p and write p_new into a.p1, even ones the other way round
@@ -889,7 +890,7 @@ slab_cg_persistent_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s,
     }
     block_partial(acc, g, s, red);
     grid_arrive(sl.gbar, bar_target);
-    if (blockIdx.x == 0) block0_scalars<FIN_PQ, TB_RED_PQ>(g, s, sl, red, gen, 3 * gen + 1);
+    if (blockIdx.x == 0) block0_scalars<FIN_PQ, TB_RED_PQ>(g, s, sl, red, gen, 3 * gen + 1, a.sysfence);
     wait_go(sl, 3 * gen + 1);
 
     // ---- B: q = M^dagger Mp on the fly, x += alpha p, r -= alpha q, ||r||^2.  The neighbours' Mp rows are complete:
@@ -952,7 +953,7 @@ slab_cg_persistent_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s,
     }
     block_partial(acc, g, s, red);
     grid_arrive(sl.gbar, bar_target);
-    if (blockIdx.x == 0) block0_scalars<FIN_RR, TB_RED_RR>(g, s, sl, red, gen, 3 * gen + 2);
+    if (blockIdx.x == 0) block0_scalars<FIN_RR, TB_RED_RR>(g, s, sl, red, gen, 3 * gen + 2, a.sysfence);
     wait_go(sl, 3 * gen + 2);
     n_act = *(volatile int *)s.n_active;
     gen++;
@@ -998,6 +999,19 @@ __device__ __forceinline__ unsigned long long global_ns() {
 __device__ __forceinline__ void fence_gpu() { asm volatile("fence.acq_rel.gpu;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_sys() { asm volatile("fence.acq_rel.sys;\n" ::: "memory"); }
 
+// The fences around the peer exchange.  Measured on this box (tools/nvlink_pingpong.cu, profiles/nvlink_pingpong_r02.txt):
+// a flag store is visible on the other GPU after 1.13 us; a device-scope fence costs 0.23 us, a SYSTEM-scope fence
+// 1.56 us -- two of them per all-reduce were a third of a synchronisation point.  Device scope is what the data path
+// needs: halo rows never travel, the peer reads them out of THIS GPU's L2 over NVLink with ld.cv (no cached copy on its
+// side), and every block's rows were ordered into that L2 by its own device-scope fence before its arrival was counted;
+// the tag leaves this GPU after the fence below, so a peer that has seen the tag and then asks this L2 for a row finds
+// it.  In the other direction value and tag travel in one 16-byte store.  (The PTX memory model asks for system scope
+// between threads of two GPUs; TB_SLAB_SYSFENCE=1 restores it.)
+__device__ __forceinline__ void xgpu_fence(int sysfence) {
+  if (sysfence) fence_sys();
+  else fence_gpu();
+}
+
 struct ChainScalars {   // CG scalars of the thread's chain (c = threadIdx.x & (bc - 1)), identical in every block
   double rr_old, rr_init, rr, alpha, beta;
   int active, iters, status;
@@ -1040,7 +1054,7 @@ __device__ __forceinline__ void update_scalars(double total, ChainScalars &cs, c
 template <int RED>
 __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, const TbCgState &s, const TbSlab &sl,
                                                  double *red, unsigned long long &target, int gen, int mode,
-                                                 unsigned long long *tl) {
+                                                 int sysfence, unsigned long long *tl) {
   __shared__ int s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = (blockDim.x + 31) >> 5;
   const int c_local = tid & (g.bc - 1), x_local = tid >> g.bc_shift;
@@ -1077,7 +1091,7 @@ __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, co
     __syncthreads();
     const int nrep_out = mode == 2 ? sl.nrep : 1;
     const int nst = sl.P * nrep_out * g.bc;
-    if (tid < nst) fence_sys();   // this GPU's halo rows before the tag, for the peers
+    if (tid < nst) xgpu_fence(sysfence);   // this GPU's halo rows before the tag, for the peers
     for (int i = tid; i < nst; i += blockDim.x) {
       const int c = i & (g.bc - 1), k = i >> g.bc_shift, rep = k % nrep_out, q = k / nrep_out;
       const double v = red[c];
@@ -1102,7 +1116,7 @@ __device__ __forceinline__ double slab_allreduce(double acc, const TbGeom &g, co
         if (mode == 2) __nanosleep(20);
         if (clock64() - t0 > TB_PERSIST_SPIN_CYCLES) __trap();   // a launch error on this rank instead of a hung box
       }
-      fence_sys();   // acquire side: the neighbours' rows behind their tags
+      xgpu_fence(sysfence);   // acquire side: the neighbours' rows behind their tags (and this SM's L1)
       red[tid] = theirs;        // [q][chain]
     }
     __syncthreads();
@@ -1197,7 +1211,7 @@ slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, 
     }
   }
   int gen = E0 + 1;   // generation of p
-  update_scalars<FIN_INIT>(slab_allreduce<TB_RED_INIT>(acc, g, s, sl, red, bar_target, gen, mode, nullptr), cs, s);
+  update_scalars<FIN_INIT>(slab_allreduce<TB_RED_INIT>(acc, g, s, sl, red, bar_target, gen, mode, a.sysfence, nullptr), cs, s);
 
   // p is double-buffered: odd iterations read p_old from a.p and write p_new into a.p1, even ones the other way round.
   // Fields of this GPU that other blocks rewrite between the phases are read with ordinary (L1-cached) loads: every
@@ -1276,7 +1290,7 @@ slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, 
         }
       }
     }
-    update_scalars<FIN_PQ>(slab_allreduce<TB_RED_PQ>(acc, g, s, sl, red, bar_target, gen, mode, tlA), cs, s);
+    update_scalars<FIN_PQ>(slab_allreduce<TB_RED_PQ>(acc, g, s, sl, red, bar_target, gen, mode, a.sysfence, tlA), cs, s);
 
     // ---- B: q = M^dagger Mp on the fly, x += alpha p, r -= alpha q, ||r||^2.  The neighbours' Mp rows are complete:
     // their owners contributed to the |Mp|^2 sum.
@@ -1343,7 +1357,7 @@ slab_cg_onelaunch_kernel(const SlabCgArgs a, const TbGeom g, const TbCgState s, 
         }
       }
     }
-    update_scalars<FIN_RR>(slab_allreduce<TB_RED_RR>(acc, g, s, sl, red, bar_target, gen, mode, tlB), cs, s);
+    update_scalars<FIN_RR>(slab_allreduce<TB_RED_RR>(acc, g, s, sl, red, bar_target, gen, mode, a.sysfence, tlB), cs, s);
     gen++;
   }
   // every block of every rank leaves in the same iteration (identical scalars).  Block 0 writes the outcome; then leave
@@ -1847,7 +1861,8 @@ static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int mode, int *
   TbSlab &sl = ctx->slab;
   SlabCgArgs a = {b, ctx->xw, ctx->r, ctx->p, ctx->p1, ctx->Mp, sl.p_prev, sl.p_next, sl.p1_prev, sl.p1_next,
                   sl.r_prev, sl.r_next, sl.mp_prev, sl.mp_next,
-                  ctx->W0, sl.W0_prev, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu};
+                  ctx->W0, sl.W0_prev, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu,
+                  (getenv("TB_SLAB_SYSFENCE") && atoi(getenv("TB_SLAB_SYSFENCE"))) ? 1 : 0};
   const void *kern = mode == 0 ? (const void *)slab_cg_persistent_kernel<TT> : (const void *)slab_cg_onelaunch_kernel<TT>;
   int per_sm = 0, nsm = TB_NUM_SMS_B200, coop = 0;
   TB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));

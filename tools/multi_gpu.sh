@@ -15,9 +15,8 @@ port=29540
 for P in 2 4 8; do
   [ $P -le $NG ] || continue
   for size in 2048 4096 1024; do
-    for variant in "default" "TB_SLAB_SYNC=0" "TB_SLAB_SYNC=2" "TB_NO_PERSIST=1" "TB_SLAB_NREP=1"; do
-      [ -n "$QUICK" ] && [ "$variant" != "default" ] && [ "$variant" != "TB_SLAB_SYNC=0" ] && continue
-      [ $size = 4096 ] && [ "$variant" != "default" ] && [ "$variant" != "TB_NO_PERSIST=1" ] && continue
+    for variant in "default" "TB_SLAB_SYNC=0" "TB_SLAB_SYNC=1" "TB_SLAB_SYSFENCE=1" "TB_NO_PERSIST=1"; do
+      [ -n "$QUICK" ] && [ "$variant" = "TB_NO_PERSIST=1" ] && continue
       port=$((port + 1))
       envs=""; [ "$variant" != "default" ] && envs="$variant"
       line=$(env $envs timeout 120 $RUN --nproc-per-node $P --master-port $port tools/slab_bench.py --size $size 2>&1 | tail -1)
@@ -31,6 +30,7 @@ for P in 2 4 8; do
     done
   done
 done
+[ -n "$QUICK" ] && exit 0
 echo "== bench.py under torch.distributed.run at every rank count"
 for P in 2 4 8; do
   [ $P -le $NG ] || continue
