@@ -1934,12 +1934,11 @@ static int launch_persistent_slab(tb_ctx *ctx, const double2 *b, int mode, int *
   return TB_OK;
 }
 
-// Which form (measured, us per CG iteration, profiles/slab_r02*.txt): slabs that live in L2 are bound by the two
-// synchronisation points, and there block 0's form is as fast on 2 GPUs (1024^2: 32.1-33.8 vs 32.2-32.7) and faster on 8
-// (2048^2: 33.3 vs 35.0); larger slabs are bound by the passes over the slab, where the balanced row segments, cached
-// loads and the hybrid all-reduce win (2048^2 on 2 GPUs 104.3 vs 117.7, on 4 GPUs 57.5, 4096^2 on 8 GPUs 109).
+// Which form (measured, us per CG iteration, profiles/slab_r02*.txt): with device-scope fences around the peer exchange
+// the hybrid form wins at every size on 2 GPUs (1024^2: 29.7 vs 32.2 for block 0's form, 2048^2: 100.8 vs 116.8,
+// 4096^2: 352 vs 367); TB_SLAB_SYNC=0 / 2 select the other forms.
 static int launch_persistent_slab_auto(tb_ctx *ctx, const double2 *b, int *nblocks_out) {
-  int mode = ctx->nsite <= ((size_t)3 << 18) ? 0 : 1;   // 768K sites: 2048^2 on 8 GPUs -> block 0's form, on 4 -> hybrid
+  int mode = 1;
   if (const char *e = getenv("TB_SLAB_SYNC")) { const int v = atoi(e); if (v >= 0 && v <= 2) mode = v; }
   return launch_persistent_slab(ctx, b, mode, nblocks_out);
 }
