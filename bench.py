@@ -383,8 +383,10 @@ def gpu_arm(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(A_host.nbytes + b_host.nbytes),
                     "d2h_bytes_per_step": int(x_host.nbytes), "ms_per_step": e2e_ms / args.steps,
                     "pinned_copy_rates_measured": pcie,
-                    "note": "PCIe-bound: the last chain of the second wave (256 chains on 148 SMs) starts one solve "
-                            "after the data of chain 108 have arrived"},
+                    "note": "per sub-batch of chains: H2D of angles and sources -> ONE kernel that reads and writes the host's "
+                            "layout and builds its links -> D2H; chains are not split on this path, so 256 chains on 148 SMs "
+                            "cost two waves of a 0.9 ms solve behind the arrival of the 108th chain (floor 2.05 ms per step); at "
+                            "N = 8 the ranks share one host memory system (pinned_copy_rates_measured falls from 55 to 20 GB/s)"},
             "gpu_launches": int(launches_all),
             "clocks": clocks,
         }
