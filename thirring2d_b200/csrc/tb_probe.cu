@@ -27,14 +27,14 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
 }  // namespace
 
 // FP64 FMA throughput of the context's device in TFLOP/s (2 flops per FMA), best of `repeats` launches of about a
-// millisecond each, CUDA events on the context's stream.
+// half a millisecond each, CUDA events on the context's stream.
 extern "C" int tb_measure_fp64_peak(tb_ctx *ctx, int repeats, double *tflops_out) {
   if (!ctx || !tflops_out || repeats < 1) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
   constexpr int ILP = 8;
   int nsm = TB_NUM_SMS_B200;
   TB_CUDA(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, ctx->device));
-  const int blocks = nsm * 8, threads = 256, iters = 4096;
+  const int blocks = nsm * 8, threads = 256, iters = 1024;   // ~0.6 ms per launch
   double *d = nullptr;
   TB_CUDA(cudaMalloc((void **)&d, sizeof(double)));
   cudaEvent_t e0, e1;
