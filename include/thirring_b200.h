@@ -86,6 +86,13 @@ int tb_set_tuning(tb_ctx *ctx, int rows_per_thread, int iters_per_launch, int so
  * runs concurrently on this device (0 for streaming).  Either pointer may be NULL. */
 int tb_solver_info(tb_ctx *ctx, int *kind, int *chains_in_flight);
 
+/* Which streaming kernels an apply / a CG iteration of the streaming solver runs on a family-A field with the current
+ * tuning and environment: kernels 0 = register-marching, 1 = TMA-staged, every chain of the batch in a tile (bulk
+ * copies, batches of up to 16 chains), 2 = TMA-staged, tiles of 16 chains x 16 sites moved as 2-D boxes through tensor
+ * maps (batches of a multiple of 16 chains).  tile_chains x tile_sites threads per block, rows_per_block rows of the
+ * lattice per block.  Any pointer may be NULL. */
+int tb_streaming_info(tb_ctx *ctx, int *kernels, int *tile_chains, int *tile_sites, int *rows_per_block);
+
 /* Diagnostics, host only (no GPU involved): the schedule of a planned launch of the on-chip solvers.  A batch that
  * fills its last wave of SMs (or of co-resident clusters) badly is cut into one equal share of CG iterations per
  * machine; est[c] / status[c] are the iteration count and the TB_CG_* status of chain c in the previous solve.

@@ -116,3 +116,95 @@ def test_staged_apply_matches_oracle(stage_small_lattices, oracle, nt, nx, C, mu
             assert_close(got_d[c], oracle.fm_dagger_mul(v[c], A[c], float(m[c]), mu), 1e-13, f"staged M^dagger, chain {c}")
         assert_close(got_m, ref_m, APPLY_TOL, "staged vs marching M")
         assert_close(got_d, ref_d, APPLY_TOL, "staged vs marching M^dagger")
+
+
+# ---- tiles of 16 chains moved as 2-D boxes through tensor maps (batches of more than 16 chains) -------------------------
+@pytest.fixture
+def stage_tiled(monkeypatch):
+    monkeypatch.setenv("TB_PIPE_TEST", "1")
+    monkeypatch.setenv("TB_PIPE_TILED", "1")   # read when the context is created
+    monkeypatch.delenv("TB_NO_PIPE", raising=False)
+    monkeypatch.delenv("TB_PIPE_XPAY", raising=False)
+
+
+TILED_CASES = [
+    (32, 32, 64, 0.3, 0.0, (0, 17, 63)),     # 4 chain tiles x 2 site tiles; the marching kernels count in tiles of 32 chains
+    (64, 64, 32, 0.2, 0.1, (0, 31)),         # 2 chain tiles, mu != 0
+    (16, 48, 48, 0.4, 0.0, (0, 47)),         # 3 chain tiles x 3 site tiles, neither a power of two
+    (24, 32, 128, 0.5, 0.05, (5, 127)),      # 8 chain tiles, 24 rows per block
+]
+
+
+@pytest.mark.parametrize("nt,nx,C,m,mu,check", TILED_CASES)
+def test_tiled_staged_kernels_match_the_oracle_and_the_marching_kernels(stage_tiled, oracle, nt, nx, C, m, mu, check):
+    rng = np.random.default_rng(nt * 11 + nx + C)
+    A = random_gauge(rng, C, nt, nx)
+    xi = random_vector(rng, C, nt, nx)
+    xi[C // 2] = 0.0                                    # a zero source: its chain is masked from the start
+    masses = np.full(C, m)
+    masses[3] = 4 * m                                   # a chain that finishes long before the others
+    masses[16:32] = 3 * m                               # a whole 16-chain tile that finishes early
+    with tb.Context(nt, nx, C, tb.MODE_ADJOINT, m=masses, mu=mu) as ctx:
+        ctx.set_tuning(solver=1)
+        assert ctx.streaming_info()[:3] == (2, 16, 16), ctx.streaming_info()
+        ctx.set_gauge(A)
+        # T1 for the tiled plain apply
+        v = random_vector(rng, C, nt, nx)
+        got_m, got_d = ctx.fm_mul(v), ctx.fm_dagger_mul(v)
+        for c in check:
+            assert_close(got_m[c], oracle.fm_mul(v[c], A[c], float(masses[c]), mu), 1e-13, f"tiled M, chain {c}")
+            assert_close(got_d[c], oracle.fm_dagger_mul(v[c], A[c], float(masses[c]), mu), 1e-13, f"tiled M^dagger, chain {c}")
+        b = ctx.fm_conjugate_mul(xi)
+        xs, is_, ls = solve(ctx, b, staged=True)
+        xm, im, lm = solve(ctx, b, staged=False)
+        assert np.array_equal(is_.status, im.status)
+        assert np.all(np.abs(is_.iters.astype(int) - im.iters.astype(int)) <= 1), (is_.iters, im.iters)
+        for c in range(C):
+            if is_.status[c] == tb.CG_CONVERGED:
+                assert_close(xs[c], xm[c], CG_SOL_TOL, f"tiled vs marching, chain {c}")
+            else:
+                assert is_.status[c] == tb.CG_ZERO_SOURCE and not xs[c].any()
+        for c in check:
+            xo, st, it, rr = oracle.fmdm_invert_cg(b[c], A[c], float(masses[c]), mu, tb.MODE_ADJOINT)
+            assert st == is_.status[c] and abs(it - int(is_.iters[c])) <= 1, (c, it, is_.iters[c])
+            assert_close(xs[c], xo, CG_SOL_TOL, f"tiled kernels vs oracle, chain {c}")
+        xs2, is2, _ = solve(ctx, b, staged=True)
+        assert np.array_equal(xs, xs2) and np.array_equal(is_.iters, is2.iters)
+
+
+# ---- the direction update folded into the first staged pass: two launches per iteration ---------------------------------
+@pytest.mark.parametrize("nt,nx,C,m,mu,tiled", [(64, 128, 8, 0.2, 0.0, False), (128, 256, 1, 0.3, 0.05, False),
+                                                (24, 64, 4, 0.4, 0.0, False), (16, 32, 128, 0.5, 0.0, False),
+                                                (32, 32, 64, 0.3, 0.0, True), (16, 48, 48, 0.4, 0.1, True)])
+def test_two_launch_iteration_is_bitwise_the_three_launch_one(monkeypatch, nt, nx, C, m, mu, tiled):
+    """p = r + beta p formed inside the first pass is the same fma the xpay kernel does and the sums run over the same
+    blocks: solution, iteration counts and residuals are bit for bit those of the three-launch staged iteration."""
+    monkeypatch.setenv("TB_PIPE_TEST", "1")
+    monkeypatch.setenv("TB_PIPE_TILED", "1" if tiled else "0")
+    monkeypatch.delenv("TB_NO_PIPE", raising=False)
+    rng = np.random.default_rng(nt + nx + C)
+    A = random_gauge(rng, C, nt, nx)
+    xi = random_vector(rng, C, nt, nx)
+    masses = np.full(C, m)
+    if C >= 8:
+        masses[3] = 4 * m
+        xi[C // 2] = 0.0
+    with tb.Context(nt, nx, C, tb.MODE_ADJOINT, m=masses, mu=mu) as ctx:
+        ctx.set_tuning(solver=1)
+        assert ctx.streaming_info()[0] == (2 if tiled else 1)
+        ctx.set_gauge(A)
+        b = ctx.fm_conjugate_mul(xi)
+        res = {}
+        for xpay in ("0", "1"):
+            monkeypatch.setenv("TB_PIPE_XPAY", xpay)
+            n0 = ctx.launch_count
+            x, info = ctx.fmdm_invert_cg(b)
+            res[xpay] = (x, info, ctx.launch_count - n0)
+        (x3, i3, l3), (x2, i2, l2) = res["0"], res["1"]
+        assert np.array_equal(i3.iters, i2.iters) and np.array_equal(i3.status, i2.status)
+        assert np.array_equal(i3.rr, i2.rr)
+        assert np.array_equal(x3, x2)
+        assert l2 < l3 and (l3 - l2) * 3 >= (l3 - 4)   # a third of the iteration's launches is gone
+        # and again, starting from the other parity of the two direction buffers' history
+        x2b, i2b = ctx.fmdm_invert_cg(b)
+        assert np.array_equal(x2b, x2) and np.array_equal(i2b.iters, i2.iters)

@@ -123,6 +123,13 @@ class Context:
         check(self.lib.tb_solver_info(self._h, C.byref(k), C.byref(n)), "tb_solver_info")
         return k.value, n.value
 
+    def streaming_info(self):
+        """(kernels, tile_chains, tile_sites, rows_per_block) of the streaming solver: kernels 0 register-marching,
+        1 TMA-staged whole-batch tiles, 2 TMA-staged 16-chain tiles through tensor maps."""
+        v = [C.c_int(0) for _ in range(4)]
+        check(self.lib.tb_streaming_info(self._h, *[C.byref(q) for q in v]), "tb_streaming_info")
+        return tuple(q.value for q in v)
+
     # -- host-buffer path (reference-facing) -----------------------------------------------------------------
     def _vec(self, v):
         v = np.ascontiguousarray(v, dtype=np.complex128)

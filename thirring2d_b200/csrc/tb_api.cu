@@ -61,10 +61,10 @@ static int alloc_cg_state(tb_ctx *ctx) {
   s.tile_active = ints + 3 * cp;
   s.n_active = ints + 3 * cp + g.nctiles;
   TB_CHECK(dev_alloc(&s.partial, max_slots * cp));
-  TB_CHECK(dev_alloc(&s.ticket, (size_t)g.nctiles));
+  TB_CHECK(dev_alloc(&s.ticket, cp));   // one per chain tile of ANY geometry (the staged kernels' tiles can be narrower)
   TB_CUDA(cudaMemset(dbl, 0, 7 * cp * sizeof(double)));
   TB_CUDA(cudaMemset(ints, 0, (3 * cp + g.nctiles + 1) * sizeof(int)));
-  TB_CUDA(cudaMemset(s.ticket, 0, g.nctiles * sizeof(unsigned int)));
+  TB_CUDA(cudaMemset(s.ticket, 0, cp * sizeof(unsigned int)));
   s.accuracy = 1e-30;   // CG_ACCURACY, hmc.c:34
   s.max_iter = 100000;  // CG_MAX_ITER, hmc.c:35
   return TB_OK;
@@ -472,6 +472,13 @@ extern "C" int tb_solver_info(tb_ctx *ctx, int *kind, int *chains_in_flight) {
     }
     *chains_in_flight = n;
   }
+  return TB_OK;
+}
+
+extern "C" int tb_streaming_info(tb_ctx *ctx, int *kernels, int *tile_chains, int *tile_sites, int *rows_per_block) {
+  if (!ctx) return TB_EINVAL;
+  const int k = tb_stream_kernels(ctx, tile_chains, tile_sites, rows_per_block);
+  if (kernels) *kernels = k;
   return TB_OK;
 }
 

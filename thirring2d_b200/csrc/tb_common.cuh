@@ -116,6 +116,8 @@ struct TbHmc {
   unsigned long long *iter_sum;   // CG iterations of the trajectory, summed over chains and solves on the device
 };
 
+#define TB_TMAP_CACHE 12
+
 struct tb_ctx {
   int nt, nx, C, mode, device;
   size_t V;          // nt*nx
@@ -125,6 +127,12 @@ struct tb_ctx {
   TbGeom g;
   TbGeom gp;        // geometry of the TMA-staged streaming kernels (tb_stream.cu: *_pipe_kernel): same tiles, taller blocks
   bool pipe_ok;     // the lattice / batch has a TMA-staged shape (whole tiles, chain runs of whole 16-byte multiples)
+  bool pipe_tiled;  // the staged tiles hold 16 of MORE chains: their rows are 2-D boxes, copied through tensor maps
+  // tensor maps of the vectors the tiled staged kernels read (128-byte CUtensorMap objects, kept opaque here)
+  unsigned char tmap_store[TB_TMAP_CACHE][128];
+  const void *tmap_ptr[TB_TMAP_CACHE];
+  int tmap_next;
+  int xp_parity;    // two-launch staged iteration: which of the two direction buffers (p, q) holds the current direction
   int tune_tt, tune_chunk, tune_solver;
   int resident_x_tmem;  // resident solver: keep x in tensor memory (1, default) or in an L2 workspace (0)
   int cluster_capacity; // cluster solver: co-resident clusters of this lattice's shape (-1 = not queried yet)
@@ -179,6 +187,7 @@ struct tb_ctx {
 };
 
 int tb_choose_geom(tb_ctx *ctx);
+int tb_stream_kernels(const tb_ctx *ctx, int *tile_chains, int *tile_sites, int *rows_per_block);
 
 // kernels / launch wrappers (tb_dirac.cu, tb_cg.cu)
 int tb_launch_links(tb_ctx *ctx, const double *d_A_dev_layout);

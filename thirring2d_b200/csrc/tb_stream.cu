@@ -16,7 +16,9 @@
 // (block, chain), and the LAST block of each chain tile (atomic ticket) sums the partials in slot order and
 // evaluates the CG scalar update, so alpha/beta/convergence never leave the device and no FP64 atomics in
 // arbitrary order are used.
+#include <cuda.h>   // CUtensorMap and its enums only: the encoder is fetched through the runtime, libcuda is not linked
 #include <cstdint>
+#include <cstring>
 
 #include "tb_common.cuh"
 
@@ -292,6 +294,18 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+// one 2-D box of a [site][chain] array (tensor map: dimension 0 = 2 C doubles, dimension 1 = sites) -> shared memory
+__device__ __forceinline__ void tensor_g2s(uint32_t dst, const void *tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+// tensor maps of the six arrays a staged block reads, in the order of the stage: P, W0, W1, PV, X, RR (TILED only)
+struct PipeMaps {
+  CUtensorMap m[6];
+};
+
 template <bool FUSED>
 struct PipeStage {
   // offsets in double2 from the start of a stage, for a tile of bc chains x bx sites (bc * bx = 256)
@@ -304,14 +318,39 @@ struct PipeStage {
   __host__ __device__ static int size(int bc) { return (FUSED ? 1536 : 768) + 3 * bc; }
   static size_t smem_bytes(int bc, int ns) { return (size_t)ns * size(bc) * sizeof(double2) + ns * sizeof(unsigned long long); }
 };
+// XP (the direction update folded into the first pass): P and R with a halo site either side, then the links
+struct PipeStageXp {
+  __host__ __device__ static constexpr int p(int) { return 0; }
+  __host__ __device__ static int rx(int bc) { return 256 + 2 * bc; }
+  __host__ __device__ static int w0(int bc) { return 512 + 4 * bc; }
+  __host__ __device__ static int w1(int bc) { return 768 + 4 * bc; }
+  __host__ __device__ static int size(int bc) { return 1024 + 5 * bc; }
+  __host__ __device__ static constexpr int pv(int) { return 0; }   // second-pass regions: not in this stage
+  __host__ __device__ static constexpr int xx(int) { return 0; }
+  __host__ __device__ static constexpr int rr(int) { return 0; }
+  static size_t smem_bytes(int bc, int ns) { return (size_t)ns * size(bc) * sizeof(double2) + ns * sizeof(unsigned long long); }
+};
 
-template <bool FUSED, int PIPE_NS, bool CG>
+// TILED: the tile holds 16 of the batch's chains (batches of more than 16 chains), so a row of the tile is bx runs of
+// 256 bytes, one per site.  Issued as bx separate bulk copies they were 1.5x slower than the marching kernels (the copy
+// engine retires a small copy every ~65 cycles); as ONE 2-D box per array and row, described by a tensor map
+// (cp.async.bulk.tensor.2d), they cost the same instructions and bytes as the contiguous tiles of a 16-chain batch.
+//
+// XP (first pass of the CG iteration only): the direction update p = r + beta p (hmc.c:391-392) of the PREVIOUS iteration
+// is folded into this pass instead of being a kernel of its own.  `in` is the previous direction, `r` the residual; the
+// new direction is formed on the fly for every site the stencil touches (the tile, its halo rows and halo columns:
+// the same fma as xpay_kernel, so the values are bit for bit those the separate kernel stores), written to `x` (a
+// SECOND direction buffer: other blocks are still reading their halos from `in`), and M applied to it.  The iteration
+// moves 224 B per site instead of 240 (r 16 + p 16 + links 32 + new p 16 + Mp 16 in this pass) in two launches.
+template <bool FUSED, int PIPE_NS, bool CG, bool TILED = false, bool XP = false>
 __global__ void __launch_bounds__(TB_MAX_BLOCK)
 dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ W0,
                    const double2 *__restrict__ W1, const double *__restrict__ mass, const double *__restrict__ emu,
                    const double *__restrict__ emmu, const double2 *__restrict__ pvec, double2 *__restrict__ x,
-                   double2 *__restrict__ r, const TbGeom g, const TbCgState s, const TbSlab sl, const int dagger) {
-  using St = PipeStage<FUSED>;
+                   double2 *__restrict__ r, const TbGeom g, const TbCgState s, const TbSlab sl, const int dagger,
+                   const __grid_constant__ PipeMaps maps) {
+  using St = typename std::conditional<XP, PipeStageXp, PipeStage<FUSED>>::type;
+  static_assert(!XP || (CG && !FUSED), "XP is the first pass of the fused CG iteration");
   __shared__ double red[TB_MAX_BLOCK];
   extern __shared__ __align__(128) unsigned char pipe_smem[];
   const BlockPos b = block_pos(g);
@@ -335,7 +374,7 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
 
   const int t0 = b.ttile * TT;
   const int c0 = b.ctile * bc, x0 = b.xtile * bx;
-  const bool contiguous = bc == g.C;   // the tile holds every chain: its sites are one contiguous run of a row
+  const bool contiguous = TILED || bc == g.C;   // one copy per array and row: a contiguous run, or a 2-D box
   const int np = contiguous ? 1 : bx;                              // centre pieces per array and row
   const uint32_t plen = (uint32_t)(contiguous ? bx * bc : bc) * 16u;   // bytes per centre piece
   const uint32_t hlen = (uint32_t)bc * 16u;                        // bytes per halo site
@@ -352,6 +391,30 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
     const size_t row = (size_t)t * g.R + c0;
     const int lane = tid & 31;
     const int kind = i < 0 ? 0 : (i >= TT ? 1 : 2);   // 0: P and W0 centres; 1: P centre; 2: everything
+    if constexpr (XP) {
+      // pieces: 0 P, 1 R, 2 W0, 3 W1 (centres); 4, 5 P left / right; 6, 7 R left / right; 8 W1 left.  Row -1: 0..2, row TT: 0..1
+      const int npc = kind == 0 ? 3 : kind == 1 ? 2 : 9;
+      if (lane == 0) mbar_expect_tx(bar, kind == 0 ? 3 * plen : kind == 1 ? 2 * plen : 4 * plen + 5 * hlen);
+      __syncwarp();
+      if (lane < npc) {
+        const int pc_ = lane;
+        const int arr = pc_ < 4 ? pc_ : (pc_ < 6 ? 0 : (pc_ < 8 ? 1 : 3));     // 0 P, 1 R, 2 W0, 3 W1
+        const int side = pc_ < 4 ? 0 : ((pc_ == 4 || pc_ == 6 || pc_ == 8) ? 1 : 2);   // 0 centre, 1 left, 2 right
+        const double2 *base = arr == 0 ? in : (arr == 1 ? (const double2 *)r : (arr == 2 ? W0 : W1));
+        const int off = arr == 0 ? St::p(bc) : (arr == 1 ? St::rx(bc) : (arr == 2 ? St::w0(bc) : St::w1(bc)));
+        const bool halo_l = arr != 2;   // W0 has no halo site; P, R, W1 keep one on the left
+        if (side == 0) {
+          const uint32_t dst = dst0 + (uint32_t)(off + (halo_l ? bc : 0)) * 16u;
+          if (TILED) tensor_g2s(dst, &maps.m[arr == 0 ? 0 : (arr == 1 ? 5 : (arr == 2 ? 1 : 2))], 2 * c0, t * g.nx + x0, bar);
+          else bulk_g2s(dst, base + row + (size_t)x0 * g.C, plen, bar);
+        } else if (side == 1) {
+          bulk_g2s(dst0 + (uint32_t)off * 16u, base + row + (size_t)xm * g.C, hlen, bar);
+        } else {
+          bulk_g2s(dst0 + (uint32_t)(off + (bx + 1) * bc) * 16u, base + row + (size_t)xp * g.C, hlen, bar);
+        }
+      }
+      return;
+    }
     const int nseg = kind == 0 ? 2 * np : kind == 1 ? np : (FUSED ? 6 * np + 3 : 3 * np + 3);
     if (lane == 0) {
       const uint32_t bytes = kind == 0 ? 2 * np * plen : kind == 1 ? np * plen : (FUSED ? 6 : 3) * np * plen + 3 * hlen;
@@ -362,21 +425,24 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
       // decode: arrays in the order P, W0, W1, PV, X, RR; the centre pieces of an array first, then the halo sites
       const double2 *src;
       uint32_t dst, bytes = plen;
-      if (sg < np) { src = in + row + (size_t)x0 * g.C + sg * pstride; dst = (uint32_t)(St::p(bc) + bc) * 16u + sg * plen; }
+      int arr = -1;   // centre piece of array `arr`, or -1: a halo site
+      if (sg < np) { arr = 0; src = in + row + (size_t)x0 * g.C + sg * pstride; dst = (uint32_t)(St::p(bc) + bc) * 16u + sg * plen; }
       else if (kind == 1) { continue; }
-      else if (sg < 2 * np) { const int k = sg - np; src = W0 + row + (size_t)x0 * g.C + k * pstride; dst = (uint32_t)St::w0(bc) * 16u + k * plen; }
+      else if (sg < 2 * np) { arr = 1; const int k = sg - np; src = W0 + row + (size_t)x0 * g.C + k * pstride; dst = (uint32_t)St::w0(bc) * 16u + k * plen; }
       else if (kind == 0) { continue; }
-      else if (sg < 3 * np) { const int k = sg - 2 * np; src = W1 + row + (size_t)x0 * g.C + k * pstride; dst = (uint32_t)(St::w1(bc) + bc) * 16u + k * plen; }
+      else if (sg < 3 * np) { arr = 2; const int k = sg - 2 * np; src = W1 + row + (size_t)x0 * g.C + k * pstride; dst = (uint32_t)(St::w1(bc) + bc) * 16u + k * plen; }
       else if (sg == 3 * np) { src = in + row + (size_t)xm * g.C; dst = (uint32_t)St::p(bc) * 16u; bytes = hlen; }
       else if (sg == 3 * np + 1) { src = in + row + (size_t)xp * g.C; dst = (uint32_t)(St::p(bc) + (bx + 1) * bc) * 16u; bytes = hlen; }
       else if (sg == 3 * np + 2) { src = W1 + row + (size_t)xm * g.C; dst = (uint32_t)St::w1(bc) * 16u; bytes = hlen; }
       else {
         const int k = sg - (3 * np + 3), a = k / np, kk = k - a * np;
         const double2 *base = a == 0 ? pvec : (a == 1 ? x : r);
+        arr = 3 + a;
         src = base + row + (size_t)x0 * g.C + kk * pstride;
         dst = (uint32_t)(a == 0 ? St::pv(bc) : (a == 1 ? St::xx(bc) : St::rr(bc))) * 16u + kk * plen;
       }
-      bulk_g2s(dst0 + dst, src, bytes, bar);
+      if (TILED && arr >= 0) tensor_g2s(dst0 + dst, &maps.m[arr], 2 * c0, t * g.nx + x0, bar);
+      else bulk_g2s(dst0 + dst, src, bytes, bar);
     }
   };
   auto stage_of = [&](int i) { return stage0 + ((i + 1) % PIPE_NS) * ssize; };
@@ -391,22 +457,33 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
   const double af = dag ? emmu[b.c] : emu[b.c];   // factor on the +t hop (M^dagger: e^{-mu})
   const double ab = dag ? emu[b.c] : emmu[b.c];   // factor on the -t hop
   const double a = FUSED ? s.alpha[b.c] : 0.0;
+  const double be = XP ? s.beta[b.c] : 0.0;   // 0 in the first iteration (cg_reset_kernel): p = r = b
   const size_t j = (size_t)b.x * g.C + b.c;
   double acc = 0.0;
+  // the field the stencil reads at offset `off` of a stage: the staged vector, or (XP) the new direction r + beta p
+  auto field = [&](const double2 *S, int off) {
+    const double2 pv = S[St::p(bc) + off];
+    if constexpr (XP) {
+      const double2 rv = S[PipeStageXp::rx(bc) + off];
+      return make_double2(fma(be, pv.x, rv.x), fma(be, pv.y, rv.y));
+    } else {
+      return pv;
+    }
+  };
 
   wait_row(-1);
-  double2 pm = stage_of(-1)[St::p(bc) + bc + tid];
+  double2 pm = field(stage_of(-1), bc + tid);
   double2 w0m = stage_of(-1)[St::w0(bc) + tid];
   wait_row(0);
-  double2 pc = stage_of(0)[St::p(bc) + bc + tid];
+  double2 pc = field(stage_of(0), bc + tid);
   __syncthreads();   // stage of row -1 is free
   if (tid < 32 && PIPE_NS - 1 <= TT) fill(PIPE_NS - 1);
 
   for (int i = 0; i < TT; i++) {
     wait_row(i + 1);
     const double2 *S = stage_of(i);
-    const double2 pp = stage_of(i + 1)[St::p(bc) + bc + tid];
-    const double2 pxm = S[St::p(bc) + tid], pxp = S[St::p(bc) + 2 * bc + tid];
+    const double2 pp = field(stage_of(i + 1), bc + tid);
+    const double2 pxm = field(S, tid), pxp = field(S, 2 * bc + tid);
     const double2 w0c = S[St::w0(bc) + tid];
     const double2 w1m = S[St::w1(bc) + tid], w1c = S[St::w1(bc) + bc + tid];
     // hops: +af W0(n) psi(n+t) - ab conj(W0(n-t)) psi(n-t) + W1(n) psi(n+x) - conj(W1(n-x)) psi(n-x)
@@ -445,6 +522,7 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
       }
       if (act) {
         out[k] = o;
+        if (XP) x[k] = pc;              // the new direction, for the second pass and the next iteration
         acc += o.x * o.x + o.y * o.y;   // <p, M^dagger M p> = |M p|^2
       }
     }
@@ -1516,6 +1594,56 @@ __global__ void transpose_kernel(const double2 *__restrict__ src, double2 *__res
 // ---------------------------------------------------------------------------------------------------------
 // host-side launch wrappers
 
+#ifndef TB_PIPE_TILED_DEFAULT
+#define TB_PIPE_TILED_DEFAULT false
+#endif
+
+// cuTensorMapEncodeTiled, through the runtime's driver entry-point query (the library does not link libcuda)
+typedef CUresult (*TmapEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                 const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder() {
+  static TmapEncodeFn fn = [] {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+    }
+    return (TmapEncodeFn)p;
+  }();
+  return fn;
+}
+
+// Tensor map of one device-layout vector [t][x][chain] of the context for the tiled staged kernels: dimension 0 = the
+// 2 C doubles of a site, dimension 1 = the nt * nx sites, box = (16 chains, 16 sites).  Cached by base pointer.
+static int tmap_for(tb_ctx *ctx, const void *base, CUtensorMap *out) {
+  for (int i = 0; i < TB_TMAP_CACHE; i++)
+    if (ctx->tmap_ptr[i] == base) {
+      memcpy(out, ctx->tmap_store[i], sizeof(CUtensorMap));
+      return TB_OK;
+    }
+  static_assert(sizeof(CUtensorMap) == 128, "tb_ctx::tmap_store");
+  const TbGeom &g = ctx->gp;
+  const cuuint64_t dims[2] = {(cuuint64_t)2 * ctx->C, (cuuint64_t)ctx->nt * ctx->nx};
+  const cuuint64_t strides[1] = {(cuuint64_t)ctx->C * sizeof(double2)};
+  const cuuint32_t box[2] = {(cuuint32_t)2 * g.bc, (cuuint32_t)g.bx};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult rc = tmap_encoder()(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<void *>(base), dims, strides, box, estr,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (rc != CUDA_SUCCESS) {
+    tb_set_error("cuTensorMapEncodeTiled failed (%d) for a %d x %d lattice, %d chains", (int)rc, ctx->nt, ctx->nx, ctx->C);
+    return TB_ECUDA;
+  }
+  const int slot = ctx->tmap_next;
+  ctx->tmap_next = (slot + 1) % TB_TMAP_CACHE;
+  ctx->tmap_ptr[slot] = base;
+  memcpy(ctx->tmap_store[slot], out, sizeof(CUtensorMap));
+  return TB_OK;
+}
+
 int tb_choose_geom(tb_ctx *ctx) {
   TbGeom &g = ctx->g;
   g.nt = ctx->nt;
@@ -1557,25 +1685,38 @@ int tb_choose_geom(tb_ctx *ctx) {
   // >= 2.5 blocks per SM; everything else keeps the marching kernels.
   ctx->gp = g;
   ctx->pipe_ok = false;
+  ctx->pipe_tiled = false;
+  ctx->tmap_next = 0;
+  for (int i = 0; i < TB_TMAP_CACHE; i++) ctx->tmap_ptr[i] = nullptr;
   const char *et = getenv("TB_PIPE_TEST");   // tests: stage every shape the kernels can handle
   const int max_chains = et ? 128 : 16, min_rows = et ? 4 : 16;
-  if (ctx->nranks == 1 && ctx->C <= max_chains && (ctx->C & (ctx->C - 1)) == 0 && ctx->nx % (TB_MAX_BLOCK / ctx->C) == 0) {
+  // Batches of more than 16 chains: tiles of 16 chains x 16 sites whose rows are 2-D boxes of the [site][chain] arrays,
+  // one tensor-map copy per array and row (dslash_pipe_kernel<TILED>).  TB_PIPE_TILED=0 keeps the marching kernels,
+  // =1 tiles every batch of a multiple of 16 chains (tests).
+  const char *etl = getenv("TB_PIPE_TILED");
+  const bool tiled_on = etl ? atoi(etl) != 0 : TB_PIPE_TILED_DEFAULT;
+  const bool tiled = tiled_on && ctx->nranks == 1 && ctx->C > 16 && ctx->C % 16 == 0 && ctx->nx % 16 == 0 &&
+                     (size_t)ctx->nt * ctx->nx < (1ull << 31) && tmap_encoder() != nullptr;
+  const bool whole = ctx->nranks == 1 && ctx->C <= max_chains && (ctx->C & (ctx->C - 1)) == 0 &&
+                     ctx->nx % (TB_MAX_BLOCK / ctx->C) == 0;
+  if (tiled || whole) {
     TbGeom &p = ctx->gp;
-    p.bc = ctx->C;
-    p.bx = TB_MAX_BLOCK / ctx->C;
+    p.bc = tiled ? 16 : ctx->C;
+    p.bx = TB_MAX_BLOCK / p.bc;
     p.bc_shift = 0;
     while ((1 << p.bc_shift) < p.bc) p.bc_shift++;
-    p.nctiles = 1;
+    p.nctiles = ctx->C / p.bc;
     p.nxtiles = ctx->nx / p.bx;
     p.Cpad = ctx->C;
     const long min_blocks = et ? 1 : 370;
     for (int ttp = 64; ttp >= min_rows; ttp--) {
-      if (ctx->nt % ttp != 0 || (long)p.nxtiles * (ctx->nt / ttp) < min_blocks) continue;
+      if (ctx->nt % ttp != 0 || (long)p.nctiles * p.nxtiles * (ctx->nt / ttp) < min_blocks) continue;
       if ((size_t)p.nxtiles * (ctx->nt / ttp) * p.Cpad > (size_t)g.nxtiles * ctx->nt * g.Cpad) continue;   // partial sums buffer
       p.tt = ttp;
       p.nttiles = ctx->nt / ttp;
       p.nslots = p.nxtiles * p.nttiles;
       ctx->pipe_ok = true;
+      ctx->pipe_tiled = tiled;
       break;
     }
   }
@@ -1586,17 +1727,59 @@ static bool use_pipe(const tb_ctx *ctx) {
   return ctx->pipe_ok && !ctx->msite && ctx->tune_tt == 0 && getenv("TB_NO_PIPE") == nullptr;
 }
 
-template <bool FUSED, bool CG = true>
-static int launch_pipe(tb_ctx *ctx, const double2 *in, double2 *out, double2 *x, bool dagger = false) {
+// The two-launch iteration (direction update folded into the first staged pass).  TB_PIPE_XPAY=0 keeps the separate
+// xpay kernel.
+#ifndef TB_PIPE_XPAY_DEFAULT
+#define TB_PIPE_XPAY_DEFAULT false
+#endif
+static bool use_pipe_xp(const tb_ctx *ctx) {
+  if (!use_pipe(ctx) || ctx->nranks > 1) return false;
+  const char *e = getenv("TB_PIPE_XPAY");
+  return e ? atoi(e) != 0 : TB_PIPE_XPAY_DEFAULT;
+}
+
+// Which streaming kernels the next apply / CG iteration of a family-A field would use: 0 register-marching, 1 staged
+// with whole-batch tiles (bulk copies), 2 staged with 16-chain tiles (tensor-map copies); and the staged tile shape.
+int tb_stream_kernels(const tb_ctx *ctx, int *tile_chains, int *tile_sites, int *rows_per_block) {
+  const bool on = use_pipe(ctx);
+  const TbGeom &g = on ? ctx->gp : ctx->g;
+  if (tile_chains) *tile_chains = g.bc;
+  if (tile_sites) *tile_sites = g.bx;
+  if (rows_per_block) *rows_per_block = g.tt;
+  return on ? (ctx->pipe_tiled ? 2 : 1) : 0;
+}
+
+// in / out as in the kernel; x: the solution (FUSED) or the buffer the new direction goes to (XP); pcur: the direction
+// the second pass reads (FUSED; default the context's p)
+template <bool FUSED, bool CG = true, bool XP = false>
+static int launch_pipe(tb_ctx *ctx, const double2 *in, double2 *out, double2 *x, bool dagger = false,
+                       const double2 *pcur = nullptr) {
+  using St = typename std::conditional<XP, PipeStageXp, PipeStage<FUSED>>::type;
   const TbGeom &g = ctx->gp;
+  if (!pcur) pcur = ctx->p;
   int ns = PIPE_NS_MAX;
-  while (ns > 2 && 2 * (PipeStage<FUSED>::smem_bytes(g.bc, ns) + 4096) > 227 * 1024) ns--;   // two blocks per SM at least
+  while (ns > 2 && 2 * (St::smem_bytes(g.bc, ns) + 4096) > 227 * 1024) ns--;   // two blocks per SM at least
   if (ns < 3) ns = 3;
-  const size_t smem = PipeStage<FUSED>::smem_bytes(g.bc, ns);
-  auto kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4, CG> : dslash_pipe_kernel<FUSED, 3, CG>;
+  const size_t smem = St::smem_bytes(g.bc, ns);
+  PipeMaps maps;
+  auto kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4, CG, false, XP> : dslash_pipe_kernel<FUSED, 3, CG, false, XP>;
+  if (ctx->pipe_tiled) {
+    kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4, CG, true, XP> : dslash_pipe_kernel<FUSED, 3, CG, true, XP>;
+    TB_CHECK(tmap_for(ctx, in, &maps.m[0]));
+    TB_CHECK(tmap_for(ctx, ctx->W0, &maps.m[1]));
+    TB_CHECK(tmap_for(ctx, ctx->W1, &maps.m[2]));
+    maps.m[3] = maps.m[4] = maps.m[5] = maps.m[0];
+    if (FUSED) {
+      TB_CHECK(tmap_for(ctx, pcur, &maps.m[3]));
+      TB_CHECK(tmap_for(ctx, x, &maps.m[4]));
+    }
+    if (FUSED || XP) TB_CHECK(tmap_for(ctx, ctx->r, &maps.m[5]));
+  } else {
+    memset(&maps, 0, sizeof(maps));
+  }
   TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid_of(g), TB_MAX_BLOCK, smem, ctx->stream>>>(in, out, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu,
-                                                         ctx->p, x, ctx->r, g, ctx->cg, ctx->slab, dagger ? 1 : 0);
+                                                         pcur, x, ctx->r, g, ctx->cg, ctx->slab, dagger ? 1 : 0, maps);
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
   return TB_OK;
@@ -1769,6 +1952,15 @@ static int cg_iteration_fused(tb_ctx *ctx, double2 *x) {
   const dim3 grid = grid_of(g);
   const int block = g.bc * g.bx;
   cudaStream_t st = ctx->stream;
+  if (use_pipe_xp(ctx)) {
+    // two launches: the direction update of the previous iteration is part of the first pass, which reads the old
+    // direction from one buffer and leaves the new one in the other (p and q: the fused iteration never stores q)
+    double2 *pold = (ctx->xp_parity & 1) ? ctx->q : ctx->p, *pnew = (ctx->xp_parity & 1) ? ctx->p : ctx->q;
+    ctx->xp_parity ^= 1;
+    TB_CHECK((launch_pipe<false, true, true>(ctx, pold, ctx->Mp, pnew)));
+    TB_CHECK((launch_pipe<true>(ctx, ctx->Mp, nullptr, x, false, pnew)));
+    return TB_OK;
+  }
   if (use_pipe(ctx)) {   // rows staged through shared memory by bulk asynchronous copies
     TB_CHECK(launch_pipe<false>(ctx, ctx->p, ctx->Mp, nullptr));
     TB_CHECK(launch_pipe<true>(ctx, ctx->Mp, nullptr, x));
@@ -1975,10 +2167,14 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
   TB_CUDA(cudaGetLastError());
 
   int chunk = ctx->tune_chunk > 0 ? ctx->tune_chunk : 16;
+  // the two-launch iteration alternates between two direction buffers: a graph must hold an even number of iterations
+  const bool xp = fused && !slab && use_pipe_xp(ctx);
+  if (xp) chunk += chunk & 1;
+  ctx->xp_parity = 0;
   const bool use_graph = getenv("TB_NO_GRAPH") == nullptr;
   // the graph holds its kernel arguments by value: everything a later call may change is part of the key (the per-site
   // mass pointer of family B is one of them; CG tolerances and tile shapes invalidate the graph where they are set)
-  const int graph_key = chunk * 8 + (fused ? 1 : 0) + (use_pipe(ctx) ? 2 : 0) + (ctx->msite ? 4 : 0);
+  const int graph_key = chunk * 16 + (fused ? 1 : 0) + (use_pipe(ctx) ? 2 : 0) + (ctx->msite ? 4 : 0) + (xp ? 8 : 0);
   if (use_graph && (ctx->cg_graph == nullptr || ctx->cg_graph_chunk != graph_key)) {
     if (ctx->cg_graph) { cudaGraphExecDestroy(ctx->cg_graph); ctx->cg_graph = nullptr; }
     cudaStream_t cap;
@@ -2007,7 +2203,7 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
   for (long i = 0; i < max_chunks; i++) {
     if (use_graph) {
       TB_CUDA(cudaGraphLaunch(ctx->cg_graph, st));
-      ctx->launches += (slab ? (fused ? 5LL : 6LL) : (fused ? 3LL : 4LL)) * chunk;
+      ctx->launches += (slab ? (fused ? 5LL : 6LL) : (fused ? (xp ? 2LL : 3LL) : 4LL)) * chunk;
     } else {
       for (int k = 0; k < chunk; k++)
         TB_CHECK(slab ? (fused ? cg_iteration_fused_slab(ctx, ctx->xw) : cg_iteration<true>(ctx, ctx->xw))

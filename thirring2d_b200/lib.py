@@ -30,6 +30,7 @@ SIGNATURES = {
     "tb_set_cg": (_i, [_vp, _d, _i]),
     "tb_set_tuning": (_i, [_vp, _i, _i, _i]),
     "tb_solver_info": (_i, [_vp, _ip, _ip]),
+    "tb_streaming_info": (_i, [_vp, _ip, _ip, _ip, _ip]),
     "tb_plan_schedule": (_i, [_ip, _ip, _i, _i, _ip, _ip, _ip]),
     "tb_set_gauge": (_i, [_vp, _vp]),
     "tb_set_links_trig": (_i, [_vp, _vp, _vp]),
