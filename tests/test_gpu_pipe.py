@@ -172,6 +172,31 @@ def test_tiled_staged_kernels_match_the_oracle_and_the_marching_kernels(stage_ti
         assert np.array_equal(xs, xs2) and np.array_equal(is_.iters, is2.iters)
 
 
+def test_tiled_kernels_are_the_default_for_a_batch_of_more_than_16_chains(monkeypatch):
+    """256^2 x 32 chains, no switches set: the streaming solver stages 16-chain tiles by itself and agrees with the
+    marching kernels."""
+    for k in ("TB_PIPE_TEST", "TB_PIPE_TILED", "TB_NO_PIPE", "TB_PIPE_XPAY"):
+        monkeypatch.delenv(k, raising=False)
+    nt = nx = 256
+    C = 32
+    rng = np.random.default_rng(6)
+    A = smooth_gauge(rng, C, nt, nx, 0.5)
+    xi = random_vector(rng, C, nt, nx)
+    with tb.Context(nt, nx, C, tb.MODE_ADJOINT, m=0.3, mu=0.0) as ctx:
+        ctx.set_tuning(solver=1)
+        assert ctx.streaming_info()[:3] == (2, 16, 16), ctx.streaming_info()
+        ctx.set_gauge(A)
+        b = ctx.fm_conjugate_mul(xi)
+        xs, is_, _ = solve(ctx, b, staged=True)
+        xm, im, _ = solve(ctx, b, staged=False)
+        assert np.all(is_.status == tb.CG_CONVERGED) and np.all(np.abs(is_.iters.astype(int) - im.iters.astype(int)) <= 1)
+        for c in (0, 15, 16, 31):
+            assert_close(xs[c], xm[c], CG_SOL_TOL, f"chain {c}")
+    with tb.Context(nt, nx, 16, tb.MODE_ADJOINT, m=0.3, mu=0.0) as ctx:
+        ctx.set_tuning(solver=1)
+        assert ctx.streaming_info()[:3] == (1, 16, 16), ctx.streaming_info()
+
+
 # ---- the direction update folded into the first staged pass: two launches per iteration ---------------------------------
 @pytest.mark.parametrize("nt,nx,C,m,mu,tiled", [(64, 128, 8, 0.2, 0.0, False), (128, 256, 1, 0.3, 0.05, False),
                                                 (24, 64, 4, 0.4, 0.0, False), (16, 32, 128, 0.5, 0.0, False),
@@ -204,7 +229,7 @@ def test_two_launch_iteration_is_bitwise_the_three_launch_one(monkeypatch, nt, n
         assert np.array_equal(i3.iters, i2.iters) and np.array_equal(i3.status, i2.status)
         assert np.array_equal(i3.rr, i2.rr)
         assert np.array_equal(x3, x2)
-        assert l2 < l3 and (l3 - l2) * 3 >= (l3 - 4)   # a third of the iteration's launches is gone
+        assert l2 < l3 and (l3 - l2) * 4 >= l3   # two launches per iteration instead of three
         # and again, starting from the other parity of the two direction buffers' history
         x2b, i2b = ctx.fmdm_invert_cg(b)
         assert np.array_equal(x2b, x2) and np.array_equal(i2b.iters, i2.iters)

@@ -1595,7 +1595,7 @@ __global__ void transpose_kernel(const double2 *__restrict__ src, double2 *__res
 // host-side launch wrappers
 
 #ifndef TB_PIPE_TILED_DEFAULT
-#define TB_PIPE_TILED_DEFAULT false
+#define TB_PIPE_TILED_DEFAULT true
 #endif
 
 // cuTensorMapEncodeTiled, through the runtime's driver entry-point query (the library does not link libcuda)
@@ -1682,7 +1682,10 @@ int tb_choose_geom(tb_ctx *ctx) {
   // traffic into shared memory) 191 -> 196; 256^2 x 128 360 -> 389.  Tiles of 32 out of 64 chains (a 512-byte copy per
   // site) were 1.5x SLOWER: the copy engine of an SM retires a small copy every ~65 cycles.  So: batches of up to 16
   // chains (tiles at least 16 sites wide), blocks at least 16 rows tall (a ring of stages has a fill latency) with
-  // >= 2.5 blocks per SM; everything else keeps the marching kernels.
+  // >= 2.5 blocks per SM.  Larger batches (a multiple of 16 chains): tiles of 16 chains x 16 sites moved as 2-D boxes
+  // through tensor maps, which cost what the contiguous tiles of a 16-chain batch cost (profiles/pipe_r02n_probe.txt, per
+  // CG iteration): 256^2 x 64 191 -> 172 us, 128^2 x 2048 1353 -> 1259, 512^2 x 64 691 -> 653, 128^2 x 512 356 -> 325.
+  // Everything else keeps the marching kernels.
   ctx->gp = g;
   ctx->pipe_ok = false;
   ctx->pipe_tiled = false;
@@ -1727,15 +1730,16 @@ static bool use_pipe(const tb_ctx *ctx) {
   return ctx->pipe_ok && !ctx->msite && ctx->tune_tt == 0 && getenv("TB_NO_PIPE") == nullptr;
 }
 
-// The two-launch iteration (direction update folded into the first staged pass).  TB_PIPE_XPAY=0 keeps the separate
-// xpay kernel.
-#ifndef TB_PIPE_XPAY_DEFAULT
-#define TB_PIPE_XPAY_DEFAULT false
-#endif
+// The two-launch iteration (direction update folded into the first staged pass) saves 16 of 240 B per site and a launch,
+// but the separate xpay kernel finds r and the next pass finds p in the 126 MB L2 while a vector is not much larger than
+// that.  Measured per CG iteration (B200, profiles/pipe_r02o_probe.txt), three -> two launches: vectors of 134 MB
+// (2048^2 x 2, 1024^2 x 8, 128^2 x 512) 323 -> 333, 323 -> 330, 325 -> 343 us; 67 MB (2048^2) 166 -> 178; vectors of
+// 268 MB (4096^2, 1024^2 x 16, 512^2 x 64, 256^2 x 256) 646 -> 621, 648 -> 618, 653 -> 631, 657 -> 631; 537 MB
+// (128^2 x 2048) 1259 -> 1190.  So: from 200 MB per vector.  TB_PIPE_XPAY=0 / 1 overrides.
 static bool use_pipe_xp(const tb_ctx *ctx) {
   if (!use_pipe(ctx) || ctx->nranks > 1) return false;
   const char *e = getenv("TB_PIPE_XPAY");
-  return e ? atoi(e) != 0 : TB_PIPE_XPAY_DEFAULT;
+  return e ? atoi(e) != 0 : ctx->nsite * sizeof(double2) >= (200ull << 20);
 }
 
 // Which streaming kernels the next apply / CG iteration of a family-A field would use: 0 register-marching, 1 staged
