@@ -192,9 +192,12 @@ def test_tiled_kernels_are_the_default_for_a_batch_of_more_than_16_chains(monkey
         assert np.all(is_.status == tb.CG_CONVERGED) and np.all(np.abs(is_.iters.astype(int) - im.iters.astype(int)) <= 1)
         for c in (0, 15, 16, 31):
             assert_close(xs[c], xm[c], CG_SOL_TOL, f"chain {c}")
-    with tb.Context(nt, nx, 16, tb.MODE_ADJOINT, m=0.3, mu=0.0) as ctx:
+    with tb.Context(512, 512, 16, tb.MODE_ADJOINT, m=0.3, mu=0.0) as ctx:   # 16 chains: one tile holds the whole batch
         ctx.set_tuning(solver=1)
         assert ctx.streaming_info()[:3] == (1, 16, 16), ctx.streaming_info()
+    with tb.Context(nt, nx, 24, tb.MODE_ADJOINT, m=0.3, mu=0.0) as ctx:     # not a multiple of 16: marching kernels
+        ctx.set_tuning(solver=1)
+        assert ctx.streaming_info()[0] == 0, ctx.streaming_info()
 
 
 # ---- the direction update folded into the first staged pass: two launches per iteration ---------------------------------
