@@ -29,6 +29,10 @@ namespace {
 
 #include "tb_onchip.cuh"
 
+#ifndef TB_CLUSTER_P2P
+#define TB_CLUSTER_P2P 1   // 0: the three split cluster barriers per iteration of round 1 (kept for comparison builds)
+#endif
+constexpr bool P2P = TB_CLUSTER_P2P != 0;
 constexpr int TX = 2, TT = 8;              // sites per thread: TT rows (t) x TX columns (x)
 constexpr int VL = 4096;                   // sites per CTA
 constexpr int NTHREADS = VL / (TX * TT);   // 256
@@ -44,8 +48,9 @@ struct Slab {
   static constexpr int OFF_HM = OFF_HP + 2 * NX;     // halo rows of Mp
   static constexpr int OFF_END = OFF_HM + 2 * NX;
   static constexpr int H_DN = 0, H_UP = NX;
-  // doubles after OFF_END: warp partials A, B [NWARPS each], cluster slots A, B [16 each]
-  static constexpr size_t SMEM = (size_t)OFF_END * sizeof(double2) + (2 * NWARPS + 32) * sizeof(double);
+  // doubles after OFF_END: warp partials A, B [NWARPS each], cluster slots A, B [16 each], then four mbarriers
+  // (p halos, Mp halos, slots A, slots B)
+  static constexpr size_t SMEM = (size_t)OFF_END * sizeof(double2) + (2 * NWARPS + 32 + 4) * sizeof(double);
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -67,11 +72,57 @@ __device__ __forceinline__ void st_cluster(uint32_t addr, const double v) {
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory"); }
 
+// ---- point-to-point hand-overs inside the CG loop --------------------------------------------------------------------
+// A store into a peer's shared memory followed by barrier.cluster.arrive.release costs the PRODUCER the round trip of
+// its stores (ncu: 19 % of the 256^2 kernel's warp time in "membar" stalls, three times per iteration).  Here the data
+// travels with its own completion: halo rows as one bulk copy shared -> peer shared per row, reduction partials as 8-byte
+// st.async, both counted in bytes on an mbarrier of the CONSUMER, which waits for the bytes it expects (two rows; one
+// partial per CTA of the cluster) exactly where it used to wait for the cluster barrier.  Producers never wait.
+// Flow control needs nothing extra: both reductions are all-to-all, so no CTA can be a whole phase ahead of a peer
+// (the data of phase n + 1 of a barrier is only sent after every CTA has contributed to a reduction that it joins after
+// its own wait for phase n).
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+}
+// every thread; a wait that outlives ~1e7 polls (seconds: a protocol error) traps instead of hanging the device
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      ".reg .u32 n;\n"
+      "mov.u32 n, 0;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "add.u32 n, n, 1;\n"
+      "setp.gt.u32 p, n, 0x1000000;\n"
+      "@p trap;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// 8 bytes into a peer's shared memory, counted on the peer's mbarrier (both addresses shared::cluster)
+__device__ __forceinline__ void st_async(uint32_t addr, const double v, uint32_t bar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.f64 [%0], %1, [%2];\n" ::"r"(addr), "d"(v), "r"(bar)
+               : "memory");
+}
+// bytes of my shared memory -> a peer's (dst and bar shared::cluster, src shared::cta; multiples of 16)
+__device__ __forceinline__ void bulk_s2c(uint32_t dst, uint32_t src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+               "r"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
 // Block sum -> every CTA's slot table; ends with a CTA barrier BEFORE the remote stores, so the caller's shared-
 // memory writes that precede it are visible CTA-wide afterwards.  After the caller's cluster barrier,
 // cluster_total adds the CS slots in rank order.
+// bar_saddr != 0: the partial travels as st.async counted on the receiver's mbarrier (the CG loop); 0: a plain store,
+// to be followed by a cluster barrier (the prologue)
 template <int CS>
-__device__ __forceinline__ void cluster_sum_post(double v, double *wscr, uint32_t slots_saddr, uint32_t my_rank) {
+__device__ __forceinline__ void cluster_sum_post(double v, double *wscr, uint32_t slots_saddr, uint32_t my_rank,
+                                                 uint32_t bar_saddr = 0) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   if ((threadIdx.x & 31) == 0) wscr[threadIdx.x >> 5] = v;
@@ -80,7 +131,11 @@ __device__ __forceinline__ void cluster_sum_post(double v, double *wscr, uint32_
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < NWARPS; w++) s += wscr[w];   // warp order, like block_sum of tb_resident.cu
-    if (threadIdx.x < CS) st_cluster(mapa_shared(slots_saddr + my_rank * 8u, threadIdx.x), s);
+    if (threadIdx.x < CS) {
+      const uint32_t dst = mapa_shared(slots_saddr + my_rank * 8u, threadIdx.x);
+      if (bar_saddr) st_async(dst, s, mapa_shared(bar_saddr, threadIdx.x));
+      else st_cluster(dst, s);
+    }
   }
 }
 template <int CS>
@@ -109,6 +164,18 @@ __device__ __forceinline__ void push_rows(const double2 (&v)[TT][TX], int hset, 
   }
 }
 
+// The same two rows as bulk copies out of the exchange field (row 0 and row LT - 1 of F, already published inside the
+// CTA and laid out like the halo buffers), counted on the receivers' halo mbarrier.  One thread.
+template <int NX>
+__device__ __forceinline__ void push_rows_bulk(uint32_t f_saddr, int hset, uint32_t smem_base, uint32_t bar_saddr,
+                                               uint32_t rank_m, uint32_t rank_p) {
+  using G = Slab<NX>;
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // the rows were written through the generic proxy
+  bulk_s2c(mapa_shared(smem_base + (uint32_t)(hset + G::H_UP) * 16u, rank_m), f_saddr, NX * 16u, mapa_shared(bar_saddr, rank_m));
+  bulk_s2c(mapa_shared(smem_base + (uint32_t)(hset + G::H_DN) * 16u, rank_p), f_saddr + (uint32_t)((G::LT - 1) * NX) * 16u,
+           NX * 16u, mapa_shared(bar_saddr, rank_p));
+}
+
 // PLAN: the grid is one cluster per "machine" of a planned launch (tb_onchip.cuh: TbPlan) and every cluster works
 // through its list of segments; a chain that is split is stored by the cluster that ran its head (r, p, x of every
 // slab, the flag raised by rank 0 after a cluster barrier) and picked up by the cluster that runs its tail.  Every
@@ -133,12 +200,20 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
   const uint32_t slotA_addr = (uint32_t)__cvta_generic_to_shared(slotA);
   const uint32_t slotB_addr = (uint32_t)__cvta_generic_to_shared(slotB);
+  // mbarriers of the point-to-point hand-overs: p halos, Mp halos, slots A (||r||^2), slots B (|Mp|^2 or <p, q>)
+  const uint32_t barHP = slotB_addr + 16 * 8, barHM = barHP + 8, barA = barHP + 16, barB = barHP + 24;
+  const uint32_t fp_saddr = smem_base + (uint32_t)G::OFF_FP * 16u, fm_saddr = smem_base + (uint32_t)G::OFF_FM * 16u;
+  auto init_bars = [&] {   // one thread; made visible to the peers by the cluster barrier every solve starts with
+    mbar_init(barHP, 1); mbar_init(barHM, 1); mbar_init(barA, 1); mbar_init(barB, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  };
 
   if (threadIdx.x < 32) {
     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(&tmem_base_s);
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(dst), "r"(TM_COLS_WT) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
+  if (P2P && !PLAN && threadIdx.x == 0) init_bars();
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
@@ -167,6 +242,7 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   if (PLAN) {
     __syncthreads();
     if (tid == 0) {
+      if (P2P) init_bars();   // every phase of the previous segment was waited for: nothing is in flight
       const int sg = sv[3];
       int4 q = make_int4(-1, 1, 0, 0);
       if (sg < plan.seg_hi[blockIdx.x / CS]) {
@@ -228,7 +304,7 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
     // every CTA of the cluster has left its previous segment before anyone stores into a peer's shared memory
     cluster_arrive();
     cluster_wait();
-    push_rows<NX>(p, G::OFF_HP, smem_base, rank_m, rank_p, top, bot, g);
+    if (!P2P) push_rows<NX>(p, G::OFF_HP, smem_base, rank_m, rank_p, top, bot, g);
     __syncthreads();   // p is published inside the CTA
   } else {
 #pragma unroll
@@ -247,7 +323,7 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   // peer's shared memory
   cluster_arrive();
   cluster_wait();
-  push_rows<NX>(p, G::OFF_HP, smem_base, rank_m, rank_p, top, bot, g);
+  if (!P2P) push_rows<NX>(p, G::OFF_HP, smem_base, rank_m, rank_p, top, bot, g);
   cluster_sum_post<CS>(rr, wscrA, slotA_addr, rank);   // hmc.c:354-356; its CTA barrier publishes Fp
   cluster_arrive();
   cluster_wait();
@@ -260,8 +336,17 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
   if (rr_old < s.accuracy && k_begin == 1) {  // hmc.c:359-361
     status = TB_CG_ZERO_SOURCE;
   } else {
-    cluster_arrive();   // pairs with the wait inside the first stencil (p and its halos are already published)
-    if (k_begin >= s.max_iter || (PLAN && k_begin >= sv[2])) cluster_wait();   // no iteration will run: close the barrier
+    // parity of the mbarrier phase iteration k completes: every barrier completes one phase per iteration, from 0
+    auto par = [&](int k) { return (uint32_t)(k ^ (PLAN ? sv[1] : 1)) & 1u; };
+    if (P2P) {
+      // the halo rows of the first direction, if an iteration will read them (a hand-over nobody waits for would land
+      // in the barriers of the cluster's next segment)
+      if (tid == 32 && k_begin < s.max_iter && (!PLAN || k_begin < sv[2]))
+        push_rows_bulk<NX>(fp_saddr, G::OFF_HP, smem_base, barHP, rank_m, rank_p);
+    } else {
+      cluster_arrive();   // pairs with the wait inside the first stencil (p and its halos are already published)
+      if (k_begin >= s.max_iter || (PLAN && k_begin >= sv[2])) cluster_wait();   // no iteration will run: close the barrier
+    }
     for (int k = k_begin; k < s.max_iter && (!PLAN || k < sv[2]); k++) {  // hmc.c:364
       // ---- Mp = M p (hmc.c:366).  Finished sites go to Fm at once (its last readers passed the ||r||^2
       // barrier); the first row of the slab waits for its hop from the halo row.
@@ -279,7 +364,14 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
               }
             }
           },
-          [] { cluster_wait(); });   // the p halos of this iteration are in place
+          [&] {   // the p halos of this iteration are in place
+            if (P2P) {
+              if (tid == 0) mbar_expect_tx(barHP, 2u * NX * 16u);
+              mbar_wait(barHP, par(k));
+            } else {
+              cluster_wait();
+            }
+          });
       if (top) {
         tile_fixup_dn<NX, false, HAS_MU>(mp[0], p_dn, xaddr, g, e_m);
 #pragma unroll
@@ -291,10 +383,14 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
           }
         }
       }
-      push_rows<NX>(mp, G::OFF_HM, smem_base, rank_m, rank_p, top, bot, g);
-      if (DAG) cluster_sum_post<CS>(pq, wscrB, slotB_addr, rank);   // its CTA barrier publishes Fm inside the CTA
+      if (!P2P) push_rows<NX>(mp, G::OFF_HM, smem_base, rank_m, rank_p, top, bot, g);
+      if (DAG) cluster_sum_post<CS>(pq, wscrB, slotB_addr, rank, P2P ? barB : 0u);   // its CTA barrier publishes Fm inside the CTA
       else __syncthreads();
-      cluster_arrive();   // Mp halos and |Mp|^2 partials are on their way
+      if (P2P) {
+        if (tid == 32) push_rows_bulk<NX>(fm_saddr, G::OFF_HM, smem_base, barHM, rank_m, rank_p);
+      } else {
+        cluster_arrive();   // Mp halos and |Mp|^2 partials are on their way
+      }
       rr = 0.0;
       double a = 0.0;
       if (DAG) {
@@ -314,7 +410,16 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
               else consume(i, j, o);
             },
             [&] {
-              cluster_wait();
+              if (P2P) {
+                if (tid == 0) {
+                  mbar_expect_tx(barHM, 2u * NX * 16u);
+                  mbar_expect_tx(barB, CS * 8u);
+                }
+                mbar_wait(barHM, par(k));
+                mbar_wait(barB, par(k));
+              } else {
+                cluster_wait();
+              }
               a = rr_old / cluster_total<CS>(slotB);   // hmc.c:371
               if (top) tile_fixup_dn<NX, true, HAS_MU>(qh[0], m_dn, xaddr, g, e_p);
 #pragma unroll
@@ -327,7 +432,14 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
         double2 q[TT][TX];
         tile_apply_wt<NX, false, HAS_MU, MASKED>(
             mp, Fm, m_dn, m_up, top, xaddr, t0, g, m, occ, e_p, e_m, [&](int i, int j, const double2 o) { q[i][j] = o; },
-            [] { cluster_wait(); });
+            [&] {
+              if (P2P) {
+                if (tid == 0) mbar_expect_tx(barHM, 2u * NX * 16u);
+                mbar_wait(barHM, par(k));
+              } else {
+                cluster_wait();
+              }
+            });
         if (top) tile_fixup_dn<NX, false, HAS_MU>(q[0], m_dn, xaddr, g, e_m);
 #pragma unroll
         for (int i = 0; i < TT; i++)
@@ -336,9 +448,14 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
             pq = fma(p[i][j].x, q[i][j].x, pq);
             pq = fma(p[i][j].y, q[i][j].y, pq);
           }
-        cluster_sum_post<CS>(pq, wscrB, slotB_addr, rank);
-        cluster_arrive();
-        cluster_wait();
+        cluster_sum_post<CS>(pq, wscrB, slotB_addr, rank, P2P ? barB : 0u);
+        if (P2P) {
+          if (tid == 0) mbar_expect_tx(barB, CS * 8u);
+          mbar_wait(barB, par(k));
+        } else {
+          cluster_arrive();
+          cluster_wait();
+        }
         a = rr_old / cluster_total<CS>(slotB);   // hmc.c:371
 #pragma unroll
         for (int i = 0; i < TT; i++)
@@ -350,10 +467,15 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
             rr = fma(r[i][j].y, r[i][j].y, rr);
           }
       }
-      cluster_sum_post<CS>(rr, wscrA, slotA_addr, rank);   // its CTA barrier: every local read of Fm has finished
-      cluster_arrive();
+      cluster_sum_post<CS>(rr, wscrA, slotA_addr, rank, P2P ? barA : 0u);   // its CTA barrier: every local read of Fm has finished
+      if (!P2P) cluster_arrive();
       tmem_x_axpy(xaddr + TM_X, p, a, k == 1);   // x += a p (hmc.c:372-373) while the partials cross the cluster
-      cluster_wait();
+      if (P2P) {
+        if (tid == 0) mbar_expect_tx(barA, CS * 8u);
+        mbar_wait(barA, par(k));
+      } else {
+        cluster_wait();
+      }
       rr = cluster_total<CS>(slotA);
       iters = k;
       // identical rr on every CTA => the whole cluster leaves the loop together, no barrier half-open
@@ -368,11 +490,16 @@ cluster_cg_kernel(const double2 *__restrict__ bsrc, double2 *__restrict__ xout, 
           p[i][j].y = fma(be, p[i][j].y, r[i][j].y);
           Fp[(t0 + i) * NX + j * NGX + g] = p[i][j];   // the last readers of Fp passed the |Mp|^2 barrier
         }
-      push_rows<NX>(p, G::OFF_HP, smem_base, rank_m, rank_p, top, bot, g);
+      if (!P2P) push_rows<NX>(p, G::OFF_HP, smem_base, rank_m, rank_p, top, bot, g);
       rr_old = rr;
       __syncthreads();    // p is published inside the CTA
-      cluster_arrive();   // and its halos are on their way; the wait is in the middle of the next stencil
-      if (k + 1 >= s.max_iter || (PLAN && k + 1 >= sv[2])) cluster_wait();   // loop ends here: close the barrier
+      if (P2P) {          // its halo rows leave if another iteration will read them
+        if (tid == 32 && k + 1 < s.max_iter && (!PLAN || k + 1 < sv[2]))
+          push_rows_bulk<NX>(fp_saddr, G::OFF_HP, smem_base, barHP, rank_m, rank_p);
+      } else {
+        cluster_arrive();   // and its halos are on their way; the wait is in the middle of the next stencil
+        if (k + 1 >= s.max_iter || (PLAN && k + 1 >= sv[2])) cluster_wait();   // loop ends here: close the barrier
+      }
     }
   }
   if (PLAN) c = sv[0];
