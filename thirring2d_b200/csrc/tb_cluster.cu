@@ -11,16 +11,19 @@
 //   tensor memory  x and the links W0, W1 of the thread's tile, thread-private columns (tcgen05.ld/st 32x32b)
 //
 // Distributed shared memory carries everything that crosses a CTA boundary:
-//   * halos are PUSHED: the warps that produce the first / last row of p or Mp also store it into the neighbour
-//     CTA's halo buffer (st.shared::cluster, 512 contiguous bytes per warp); the stencil reads local memory only;
-//   * both CG reductions are all-to-all over the cluster: every CTA stores its block sum into every CTA's slot
-//     table, and all CTAs add the slots in rank order => bitwise identical alpha, beta and stopping decisions on
-//     every CTA with no further communication (and run-to-run deterministic);
-//   * barrier.cluster is split into arrive.release / wait.acquire and the latency is hidden: a stencil does the
-//     first four rows of every tile (which need only the CTA's own data, except one hop into the first row of the
-//     slab that is added afterwards), THEN waits, and finishes with the halo rows in place; the x += alpha p
-//     update in tensor memory runs inside the ||r||^2 barrier.
-// Three split cluster barriers per CG iteration.  HBM is touched once per solve.
+//   * halos are PUSHED: the first / last row of p or Mp of a slab goes into the neighbour CTA's halo buffer as one bulk
+//     copy shared -> peer shared out of the exchange field; the stencil reads local memory only;
+//   * both CG reductions are all-to-all over the cluster: every CTA sends its block sum into every CTA's slot table
+//     (8-byte st.async), and all CTAs add the slots with the same tree => bitwise identical alpha, beta and stopping
+//     decisions on every CTA with no further communication (and run-to-run deterministic);
+//   * every hand-over is counted in bytes on an mbarrier of the CONSUMER, which waits where the latency is hidden: a
+//     stencil does the first four rows of every tile (which need only the CTA's own data, except one hop into the first
+//     row of the slab that is added afterwards), THEN waits, and finishes with the halo rows in place; the x += alpha p
+//     update in tensor memory runs while the ||r||^2 partials travel.  Producers never wait (round 1's
+//     st.shared::cluster + barrier.cluster.arrive.release cost them the round trip of their stores, three times per
+//     iteration).
+// No cluster barrier inside the CG loop; they remain in the prologue and at the segment boundaries of a planned launch.
+// HBM is touched once per solve.
 #include <cstdint>
 
 #include "tb_common.cuh"
@@ -117,7 +120,21 @@ __device__ __forceinline__ void bulk_s2c(uint32_t dst, uint32_t src, uint32_t by
 
 // Block sum -> every CTA's slot table; ends with a CTA barrier BEFORE the remote stores, so the caller's shared-
 // memory writes that precede it are visible CTA-wide afterwards.  After the caller's cluster barrier,
-// cluster_total adds the CS slots in rank order.
+// cluster_total adds the CS slots with the same pairwise tree on every CTA.
+// The same pairwise tree on every CTA (=> bitwise identical totals everywhere): four dependent additions for 16 slots
+// instead of sixteen; every warp of every CTA walks this chain twice per iteration.
+template <int N>
+__device__ __forceinline__ double tree_sum(const double *v_in) {
+  static_assert((N & (N - 1)) == 0, "power of two");
+  double v[N];
+#pragma unroll
+  for (int q = 0; q < N; q++) v[q] = v_in[q];
+#pragma unroll
+  for (int w = 1; w < N; w <<= 1)
+#pragma unroll
+    for (int q = 0; q + w < N; q += 2 * w) v[q] += v[q + w];
+  return v[0];
+}
 // bar_saddr != 0: the partial travels as st.async counted on the receiver's mbarrier (the CG loop); 0: a plain store,
 // to be followed by a cluster barrier (the prologue)
 template <int CS>
@@ -128,9 +145,7 @@ __device__ __forceinline__ void cluster_sum_post(double v, double *wscr, uint32_
   if ((threadIdx.x & 31) == 0) wscr[threadIdx.x >> 5] = v;
   __syncthreads();
   if (threadIdx.x < 32) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < NWARPS; w++) s += wscr[w];   // warp order, like block_sum of tb_resident.cu
+    const double s = tree_sum<NWARPS>(wscr);
     if (threadIdx.x < CS) {
       const uint32_t dst = mapa_shared(slots_saddr + my_rank * 8u, threadIdx.x);
       if (bar_saddr) st_async(dst, s, mapa_shared(bar_saddr, threadIdx.x));
@@ -140,10 +155,7 @@ __device__ __forceinline__ void cluster_sum_post(double v, double *wscr, uint32_
 }
 template <int CS>
 __device__ __forceinline__ double cluster_total(const double *slots) {
-  double s = 0.0;
-#pragma unroll
-  for (int q = 0; q < CS; q++) s += slots[q];
-  return s;
+  return tree_sum<CS>(slots);
 }
 
 // first row of the slab -> the "up" halo of the CTA that owns the rows before mine; last row -> the "dn" halo of
