@@ -278,6 +278,10 @@ int tb_reset_launch_count(tb_ctx *ctx);
 /* FP64 FMA issue rate of the context's device in TFLOP/s (a kernel of independent DFMA chains, best of `repeats`
  * launches, CUDA events): the measured denominator for the on-chip solvers, which are bound by FP64 issue. */
 int tb_measure_fp64_peak(tb_ctx *ctx, int repeats, double *tflops_out);
+/* The same measurement with a choice of instruction mix: kind 0 = tb_measure_fp64_peak (two of the three source operands
+ * are shared by all FMAs), kind 1 = every source operand of every FMA in its own register, which is what the FMAs of a
+ * stencil look like to the register file. */
+int tb_measure_fp64_rate(tb_ctx *ctx, int kind, int repeats, double *tflops_out);
 
 /* Milliseconds the device spent in the last tb_cg_dev/tb_invert_dev call (CUDA events on the context stream). */
 double tb_last_solve_ms(const tb_ctx *ctx);

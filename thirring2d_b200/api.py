@@ -429,6 +429,13 @@ class Context:
         check(self.lib.tb_measure_fp64_peak(self._h, repeats, C.byref(tf)), "tb_measure_fp64_peak")
         return tf.value
 
+    def measure_fp64_rate(self, kind, repeats=5):
+        """FP64 FMA rate in TFLOP/s for an instruction mix: kind 0 = measure_fp64_peak, 1 = every source operand of every
+        FMA in its own register (a stencil's FMAs)."""
+        tf = C.c_double(0.0)
+        check(self.lib.tb_measure_fp64_rate(self._h, kind, repeats, C.byref(tf)), "tb_measure_fp64_rate")
+        return tf.value
+
     @property
     def last_solve_ms(self):
         return float(self.lib.tb_last_solve_ms(self._h))

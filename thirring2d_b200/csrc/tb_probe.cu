@@ -24,11 +24,43 @@ __global__ void __launch_bounds__(256) dfma_peak_kernel(double *out, int iters, 
   if (s == 123.456) out[0] = s;   // keeps the chains alive; never true for the arguments used
 }
 
+// The same with every source operand in its own register (8 accumulators, 8 + 8 multiplicands, rotated so that no two
+// consecutive FMAs share a source): what a stencil's FMAs look like to the register file.  `iters` rounds of 32 FMAs.
+__global__ void __launch_bounds__(256) dfma_distinct_kernel(double *out, int iters, double a0, double b0) {
+  double v[8], a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    v[i] = (double)(threadIdx.x + i) * 1e-3;
+    a[i] = a0 + 1e-7 * (double)(i + (threadIdx.x & 3));
+    b[i] = b0 * (double)(i + 1);
+  }
+  for (int k = 0; k < iters; k++) {
+#pragma unroll
+    for (int u = 0; u < 4; u++)
+#pragma unroll
+      for (int i = 0; i < 8; i++) v[i] = fma(a[(i + u) & 7], v[i], b[(i + 2 * u + 1) & 7]);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += v[i];
+  if (s == 123.456) out[0] = s;
+}
+
 }  // namespace
 
 // FP64 FMA throughput of the context's device in TFLOP/s (2 flops per FMA), best of `repeats` launches of about a
 // half a millisecond each, CUDA events on the context's stream.
-extern "C" int tb_measure_fp64_peak(tb_ctx *ctx, int repeats, double *tflops_out) {
+static int measure_fp64(tb_ctx *ctx, int kind, int repeats, double *tflops_out);
+
+extern "C" int tb_measure_fp64_peak(tb_ctx *ctx, int repeats, double *tflops_out) { return measure_fp64(ctx, 0, repeats, tflops_out); }
+
+// kind 0: the peak above (two of the three sources shared by all FMAs); kind 1: every source operand in its own register
+extern "C" int tb_measure_fp64_rate(tb_ctx *ctx, int kind, int repeats, double *tflops_out) {
+  if (kind != 0 && kind != 1) return TB_EINVAL;
+  return measure_fp64(ctx, kind, repeats, tflops_out);
+}
+
+static int measure_fp64(tb_ctx *ctx, int kind, int repeats, double *tflops_out) {
   if (!ctx || !tflops_out || repeats < 1) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
   constexpr int ILP = 8;
@@ -43,7 +75,8 @@ extern "C" int tb_measure_fp64_peak(tb_ctx *ctx, int repeats, double *tflops_out
   double best = 0.0;
   for (int r = 0; r < repeats + 1; r++) {   // the first launch is a warm-up
     TB_CUDA(cudaEventRecord(e0, ctx->stream));
-    dfma_peak_kernel<ILP><<<blocks, threads, 0, ctx->stream>>>(d, iters, 0.999999, 1e-9);
+    if (kind == 0) dfma_peak_kernel<ILP><<<blocks, threads, 0, ctx->stream>>>(d, iters, 0.999999, 1e-9);
+    else dfma_distinct_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters, 0.999999, 1e-9);
     TB_CUDA(cudaEventRecord(e1, ctx->stream));
     TB_CUDA(cudaEventSynchronize(e1));
     float ms = 0.f;

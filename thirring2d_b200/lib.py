@@ -75,6 +75,7 @@ SIGNATURES = {
     "tb_reset_launch_count": (_i, [_vp]),
     "tb_last_solve_ms": (_d, [_vp]),
     "tb_measure_fp64_peak": (_i, [_vp, _i, _dp]),
+    "tb_measure_fp64_rate": (_i, [_vp, _i, _i, _dp]),
 }
 
 
