@@ -261,6 +261,7 @@ def gpu_arm(args):
     plain_ms = float(np.mean(plain_ms[1:]))
     step()   # planned again, so that x below is the timed solve's
     fp64_peak = ctx.measure_fp64_peak(3)
+    fp64_distinct = ctx.measure_fp64_rate(1, 2)   # the same FMAs with every source operand in its own register
 
     # e2e: the host-buffer C-ABI entry points a reference-side caller binds
     def e2e_step():   # new angles + solve, as at every leapfrog step of momentum_step (hmc.c:504-516)
@@ -377,6 +378,7 @@ def gpu_arm(args):
                          # useful flops per site and apply + 20 for the fused BLAS-1
                          "fp64": {"achieved_tflops": fp64_tflops, "measured_peak_tflops": fp64_peak,
                                   "frac_of_measured": fp64_tflops / fp64_peak if fp64_peak > 0 else None,
+                                  "measured_rate_distinct_operands_tflops": fp64_distinct,
                                   "flops_per_site_iteration": 88,
                                   "peak_source": "tb_measure_fp64_peak: independent DFMA chains on every SM, best of 3 "
                                                  "launches, in this run"}},
@@ -451,8 +453,9 @@ def parity_check(torch, tb, ctx, x, A_np, b_host, info, chains):
 
 
 def streaming_roofline(tb, torch, dev, stream):
-    """HBM-bound evidence on a working set larger than L2: the streaming CG (4 fused kernels per iteration) on
-    256x256 x 64 chains (470 MB of CG state), fixed 150 iterations, device time by CUDA events."""
+    """HBM-bound evidence on a working set larger than L2: the streaming CG (3 fused kernels per iteration; the two stencil
+    passes TMA-staged, 16-chain tiles through tensor maps) on 256x256 x 64 chains (470 MB of CG state), fixed 150
+    iterations, device time by CUDA events."""
     nt = nx = 256
     chains, iters = 64, 150
     peak, _ = measured_peak()
@@ -472,6 +475,7 @@ def streaming_roofline(tb, torch, dev, stream):
         ms.append(ctx.last_solve_ms)
     info = ctx.cg_result()
     it = int(info.iters.max())
+    kernels = ctx.streaming_info()
     ctx.close()
     t = min(ms) * 1e-3
     # the fused ADJOINT iteration moves 240 B per site (K1 64 + the fused M^dagger / update pass 128 + K4 48): that is
@@ -479,6 +483,9 @@ def streaming_roofline(tb, torch, dev, stream):
     ach = 240 * nt * nx * chains * it / t / 1e9
     ach288 = BYTES_PER_SITE_ITER * nt * nx * chains * it / t / 1e9
     return {"bound": "hbm", "kernel": "streaming CG iteration (dslash+|Mp|^2, dslash^dagger+axpy+norm, xpay)",
+            "stencil_kernels": {0: "register-marching", 1: "TMA-staged, whole-batch tiles", 2: "TMA-staged, 16-chain tiles "
+                                "through tensor maps"}[kernels[0]] + f", tile {kernels[1]} chains x {kernels[2]} sites, "
+                               f"{kernels[3]} rows per block",
             "workload": f"{nt}x{nx} x {chains} chains, {it} iterations, working set 470 MB > L2",
             "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "bytes_per_site_iteration": 240,
             "achieved_288B_definition": ach288, "frac_288B_definition": ach288 / peak,
