@@ -132,6 +132,8 @@ TILED_CASES = [
     (64, 64, 32, 0.2, 0.1, (0, 31)),         # 2 chain tiles, mu != 0
     (16, 48, 48, 0.4, 0.0, (0, 47)),         # 3 chain tiles x 3 site tiles, neither a power of two
     (24, 32, 128, 0.5, 0.05, (5, 127)),      # 8 chain tiles, 24 rows per block
+    (32, 32, 20, 0.3, 0.0, (0, 15, 16, 19)),  # a ragged last tile: 4 of its 16 chains exist (20 sources on one field)
+    (16, 48, 40, 0.4, 0.1, (0, 31, 32, 39)),  # 2 full tiles + 8 chains
 ]
 
 
@@ -143,7 +145,7 @@ def test_tiled_staged_kernels_match_the_oracle_and_the_marching_kernels(stage_ti
     xi[C // 2] = 0.0                                    # a zero source: its chain is masked from the start
     masses = np.full(C, m)
     masses[3] = 4 * m                                   # a chain that finishes long before the others
-    masses[16:32] = 3 * m                               # a whole 16-chain tile that finishes early
+    masses[16:32] = 3 * m                               # a whole 16-chain tile (or what exists of it) that finishes early
     with tb.Context(nt, nx, C, tb.MODE_ADJOINT, m=masses, mu=mu) as ctx:
         ctx.set_tuning(solver=1)
         assert ctx.streaming_info()[:3] == (2, 16, 16), ctx.streaming_info()
@@ -195,7 +197,10 @@ def test_tiled_kernels_are_the_default_for_a_batch_of_more_than_16_chains(monkey
     with tb.Context(512, 512, 16, tb.MODE_ADJOINT, m=0.3, mu=0.0) as ctx:   # 16 chains: one tile holds the whole batch
         ctx.set_tuning(solver=1)
         assert ctx.streaming_info()[:3] == (1, 16, 16), ctx.streaming_info()
-    with tb.Context(nt, nx, 24, tb.MODE_ADJOINT, m=0.3, mu=0.0) as ctx:     # not a multiple of 16: marching kernels
+    with tb.Context(nt, nx, 24, tb.MODE_ADJOINT, m=0.3, mu=0.0) as ctx:     # not a multiple of 16: a ragged last tile
+        ctx.set_tuning(solver=1)
+        assert ctx.streaming_info()[:3] == (2, 16, 16), ctx.streaming_info()
+    with tb.Context(nt, nx, 12, tb.MODE_ADJOINT, m=0.3, mu=0.0) as ctx:     # fewer than 16, not a power of two: marching
         ctx.set_tuning(solver=1)
         assert ctx.streaming_info()[0] == 0, ctx.streaming_info()
 

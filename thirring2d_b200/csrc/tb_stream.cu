@@ -377,7 +377,8 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
   const bool contiguous = TILED || bc == g.C;   // one copy per array and row: a contiguous run, or a 2-D box
   const int np = contiguous ? 1 : bx;                              // centre pieces per array and row
   const uint32_t plen = (uint32_t)(contiguous ? bx * bc : bc) * 16u;   // bytes per centre piece
-  const uint32_t hlen = (uint32_t)bc * 16u;                        // bytes per halo site
+  // bytes per halo site (a plain copy: in a ragged last tile only the chains that exist)
+  const uint32_t hlen = (uint32_t)((TILED && c0 + bc > g.C) ? g.C - c0 : bc) * 16u;
   const size_t pstride = contiguous ? 0 : (size_t)g.C;             // double2 between centre pieces in global memory
   const int xm = x0 == 0 ? g.nx - 1 : x0 - 1, xp = x0 + bx == g.nx ? 0 : x0 + bx;
 
@@ -1694,11 +1695,12 @@ int tb_choose_geom(tb_ctx *ctx) {
   const char *et = getenv("TB_PIPE_TEST");   // tests: stage every shape the kernels can handle
   const int max_chains = et ? 128 : 16, min_rows = et ? 4 : 16;
   // Batches of more than 16 chains: tiles of 16 chains x 16 sites whose rows are 2-D boxes of the [site][chain] arrays,
-  // one tensor-map copy per array and row (dslash_pipe_kernel<TILED>).  TB_PIPE_TILED=0 keeps the marching kernels,
-  // =1 tiles every batch of a multiple of 16 chains (tests).
+  // one tensor-map copy per array and row (dslash_pipe_kernel<TILED>).  A batch that is not a multiple of 16 chains ends
+  // in a ragged tile: the tensor copy zero-fills the chains that do not exist, their threads are inactive.
+  // TB_PIPE_TILED=0 keeps the marching kernels.
   const char *etl = getenv("TB_PIPE_TILED");
   const bool tiled_on = etl ? atoi(etl) != 0 : TB_PIPE_TILED_DEFAULT;
-  const bool tiled = tiled_on && ctx->nranks == 1 && ctx->C > 16 && ctx->C % 16 == 0 && ctx->nx % 16 == 0 &&
+  const bool tiled = tiled_on && ctx->nranks == 1 && ctx->C > 16 && ctx->nx % 16 == 0 &&
                      (size_t)ctx->nt * ctx->nx < (1ull << 31) && tmap_encoder() != nullptr;
   const bool whole = ctx->nranks == 1 && ctx->C <= max_chains && (ctx->C & (ctx->C - 1)) == 0 &&
                      ctx->nx % (TB_MAX_BLOCK / ctx->C) == 0;
@@ -1708,9 +1710,9 @@ int tb_choose_geom(tb_ctx *ctx) {
     p.bx = TB_MAX_BLOCK / p.bc;
     p.bc_shift = 0;
     while ((1 << p.bc_shift) < p.bc) p.bc_shift++;
-    p.nctiles = ctx->C / p.bc;
+    p.nctiles = (ctx->C + p.bc - 1) / p.bc;   // tiled: the last tile may be ragged (its missing chains are zero-filled boxes)
     p.nxtiles = ctx->nx / p.bx;
-    p.Cpad = ctx->C;
+    p.Cpad = p.nctiles * p.bc;                // <= the marching geometry's Cpad, which sizes the per-chain arrays
     const long min_blocks = et ? 1 : 370;
     for (int ttp = 64; ttp >= min_rows; ttp--) {
       if (ctx->nt % ttp != 0 || (long)p.nctiles * p.nxtiles * (ctx->nt / ttp) < min_blocks) continue;
