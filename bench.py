@@ -808,7 +808,50 @@ def other_configs(tb, torch, dist, dev, stream, rank, world, cpu=True):
             break
     if world == 1 and cpu and "error" not in out["2048x2048_single_lattice_1_gpu"]:
         out["2048x2048_single_lattice_1_gpu"]["cpu_baseline"] = cpu_apply_rate(2048, 2048, 0.05, 1.0, 2)
+    if world == 1:
+        try:
+            out["1024x1024_16_sources_on_one_gauge_field"] = multi_rhs_config(tb, torch, dev, stream, peak)
+        except Exception as e:
+            out["1024x1024_16_sources_on_one_gauge_field"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     return out
+
+
+def multi_rhs_config(tb, torch, dev, stream, peak, n=1024, nsrc=16, iters=200):
+    """Multi-RHS CG on ONE gauge field (the sources of fermion_phase, hmc.c:794-815; SURVEY 8(d): 32 + 32 / N_src bytes of
+    links per site and apply): the field uploaded once per source (tb_set_gauge_dev) against tb_set_gauge_shared_dev, where
+    the staged kernels read one link per site.  Fixed number of iterations, device time."""
+    res = {}
+    g = torch.Generator(device=dev).manual_seed(11)
+    A1 = (torch.rand(n * n * 2, dtype=torch.float64, device=dev, generator=g) - 0.5) * (2 * np.pi)
+    for shared in (False, True):
+        ctx = tb.Context(n, n, nsrc, tb.MODE_ADJOINT, device=dev.index or 0, m=0.01, mu=0.0, stream=stream.cuda_stream)
+        ctx.set_tuning(0, 0, 1)
+        ctx.set_cg(1e-30, iters + 1)
+        if shared:
+            ctx.set_gauge_shared_dev(A1.data_ptr())
+        else:
+            A = A1.view(1, -1).expand(nsrc, -1).contiguous()
+            ctx.set_gauge_dev(A.data_ptr())
+            del A
+        b = torch.randn(ctx.vec_doubles, dtype=torch.float64, device=dev, generator=g)
+        x = torch.empty_like(b)
+        ctx.cg_dev(b.data_ptr(), x.data_ptr())
+        ms = []
+        for _ in range(3):
+            ctx.cg_dev(b.data_ptr(), x.data_ptr())
+            ms.append(ctx.last_solve_ms)
+        it = int(ctx.cg_result().iters.max())
+        kern = ctx.streaming_info()
+        ctx.close()
+        del b, x
+        res["shared" if shared else "per_source"] = (min(ms) * 1e3 / it, kern)
+    sites = n * n * nsrc
+    us_s, us_p = res["shared"][0], res["per_source"][0]
+    return {"workload": f"{n}x{n}, {nsrc} sources on one gauge field, {iters} CG iterations, streaming solver",
+            "us_per_iteration_field_per_source": us_p, "us_per_iteration_shared_field": us_s, "speedup": us_p / us_s,
+            "bytes_per_site_source_iteration": {"per_source": 224, "shared": 224 - 64 + 64 / nsrc},
+            "frac_of_hbm_peak_shared": (224 - 64 + 64 / nsrc) * sites / (us_s * 1e-6) / 1e9 / peak,
+            "rows_per_block": {"per_source": res["per_source"][1][3], "shared": res["shared"][1][3]}}
 
 
 def main():

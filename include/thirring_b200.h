@@ -109,6 +109,14 @@ int tb_plan_schedule(const int *est, const int *status, int nchains, int machine
  * sin/cos re-evaluated inside every apply, hmc.c:140-141,152-153,163-164,173-174). */
 int tb_set_gauge(tb_ctx *ctx, const double *A_host);
 
+/* One gauge field for EVERY chain of the context: the chains are then the right-hand sides of a multi-RHS solve on that
+ * field -- the N_src random sources of fermion_phase (hmc.c:794-815), the point sources of a propagator.  A_host:
+ * double[NT][NX][2].  Every kernel works as after tb_set_gauge with nchains copies of the field; the TMA-staged streaming
+ * kernels read the links once per site instead of once per site and chain (32 + 32 / N_src bytes per site
+ * and apply; a CG iteration moves 180 instead of 240 bytes per site and source).  Single-GPU contexts. */
+int tb_set_gauge_shared(tb_ctx *ctx, const double *A_host);
+int tb_set_gauge_shared_dev(tb_ctx *ctx, const double *d_A_one_field);
+
 /* Links from cos / sin evaluated by the caller's libm: trig_t_host / trig_x_host = double[nchains][NT][NX][2] holding
  * (cos A_t, sin A_t) and (cos A_x, sin A_x).  The links are then bit for bit what hmc.c:140-174 computes on the host
  * (the device's sincos may differ from glibc's in the last bit), which together with the strict solver

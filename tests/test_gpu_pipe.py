@@ -241,3 +241,78 @@ def test_two_launch_iteration_is_bitwise_the_three_launch_one(monkeypatch, nt, n
         # and again, starting from the other parity of the two direction buffers' history
         x2b, i2b = ctx.fmdm_invert_cg(b)
         assert np.array_equal(x2b, x2) and np.array_equal(i2b.iters, i2.iters)
+
+
+# ---- one gauge field shared by every chain of the batch (multi-RHS): compact links in the staged kernels ---------------
+@pytest.mark.parametrize("nt,nx,C,mu,tiled,xpay", [(64, 128, 8, 0.0, False, "0"), (64, 64, 16, 0.1, False, "1"),
+                                                   (32, 32, 64, 0.0, True, "0"), (16, 48, 40, 0.1, True, "1"),
+                                                   (32, 32, 20, 0.0, True, "0")])
+def test_shared_gauge_field_is_bitwise_the_replicated_one(monkeypatch, oracle, nt, nx, C, mu, tiled, xpay):
+    """tb_set_gauge_shared: the staged kernels read one link per site instead of one per site and chain; the arithmetic
+    per site is untouched, so applies are bit for bit those of the same field uploaded once per chain with tb_set_gauge,
+    and so is the solve on the marching kernels and on the on-chip solver (which use the per-chain copies the call also
+    leaves behind); the staged solve agrees to rounding (its blocks are shorter with a shared field)."""
+    monkeypatch.setenv("TB_PIPE_TEST", "1")
+    monkeypatch.setenv("TB_PIPE_TILED", "1" if tiled else "0")
+    monkeypatch.setenv("TB_PIPE_XPAY", xpay)
+    monkeypatch.delenv("TB_NO_PIPE", raising=False)
+    rng = np.random.default_rng(3 * nt + nx + C)
+    A1 = random_gauge(rng, 1, nt, nx)[0]
+    A = np.ascontiguousarray(np.broadcast_to(A1, (C, nt, nx, 2)))
+    xi = random_vector(rng, C, nt, nx)
+    masses = np.full(C, 0.3)
+    masses[3] = 1.2
+    with tb.Context(nt, nx, C, tb.MODE_ADJOINT, m=masses, mu=mu) as ctx:
+        ctx.set_tuning(solver=1)
+        assert ctx.streaming_info()[0] == (2 if tiled else 1)
+        res = {}
+        for name in ("shared", "replicated", "shared again"):
+            if name == "replicated":
+                ctx.set_gauge(A)
+            else:
+                ctx.set_gauge_shared(A1)
+            m_v, d_v = ctx.fm_mul(xi), ctx.fm_dagger_mul(xi)
+            b = ctx.fm_conjugate_mul(xi)
+            x, info = ctx.fmdm_invert_cg(b)
+            os.environ["TB_NO_PIPE"] = "1"
+            try:
+                xm, im = ctx.fmdm_invert_cg(b)
+            finally:
+                os.environ.pop("TB_NO_PIPE", None)
+            res[name] = (m_v, d_v, x, info, xm, im)
+        ref = res["replicated"]
+        for name in ("shared", "shared again"):
+            got = res[name]
+            for k in (0, 1, 4):          # the applies and the solve on the marching kernels: bit for bit
+                assert np.array_equal(got[k], ref[k]), (name, k)
+            assert np.array_equal(got[5].iters, ref[5].iters)
+            # the staged solve runs shorter blocks with a shared field (tb_gauge_sharing): same arithmetic per site,
+            # differently blocked sums
+            assert np.array_equal(got[3].status, ref[3].status)
+            assert np.all(np.abs(got[3].iters.astype(int) - ref[3].iters.astype(int)) <= 1)
+            assert_close(got[2], ref[2], CG_SOL_TOL, f"{name} vs replicated, staged solve")
+        assert np.array_equal(res["shared"][2], res["shared again"][2])
+        c = C - 1
+        b = ctx.fm_conjugate_mul(xi)
+        xo, st, it, rr = oracle.fmdm_invert_cg(b[c], A1, float(masses[c]), mu, tb.MODE_ADJOINT)
+        assert abs(it - int(res["shared"][3].iters[c])) <= 1
+        assert_close(res["shared"][2][c], xo, CG_SOL_TOL, "shared gauge field vs oracle")
+
+
+def test_shared_gauge_field_on_the_on_chip_solver(oracle):
+    """64^2 x 20 sources on one field through the default (on-chip) solver: the per-chain link copies are right."""
+    nt = nx = 64
+    C = 20
+    rng = np.random.default_rng(11)
+    A1 = random_gauge(rng, 1, nt, nx)[0]
+    xi = random_vector(rng, C, nt, nx)
+    with tb.Context(nt, nx, C, tb.MODE_ADJOINT, m=0.2, mu=0.0) as ctx:
+        ctx.set_gauge_shared(A1)
+        b = ctx.fm_conjugate_mul(xi)
+        x, info = ctx.fmdm_invert_cg(b)
+        ctx.set_gauge(np.ascontiguousarray(np.broadcast_to(A1, (C, nt, nx, 2))))
+        x2, info2 = ctx.fmdm_invert_cg(b)
+        assert np.array_equal(x, x2) and np.array_equal(info.iters, info2.iters)
+        xo, st, it, rr = oracle.fmdm_invert_cg(b[7], A1, 0.2, 0.0, tb.MODE_ADJOINT)
+        assert abs(it - int(info.iters[7])) <= 1
+        assert_close(x[7], xo, CG_SOL_TOL, "on-chip solver, shared gauge field")

@@ -145,6 +145,13 @@ class Context:
         assert A.shape == (self.nchains, self.nt, self.nx, 2), A.shape
         check(self.lib.tb_set_gauge(self._h, A.ctypes.data), "tb_set_gauge")
 
+    def set_gauge_shared(self, A):
+        """One gauge field (NT, NX, 2) for every chain of the context: the chains are the right-hand sides of a multi-RHS
+        solve on that field (fermion_phase's sources, hmc.c:794-815)."""
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        assert A.shape == (self.nt, self.nx, 2), A.shape
+        check(self.lib.tb_set_gauge_shared(self._h, A.ctypes.data), "tb_set_gauge_shared")
+
     def set_links_trig(self, trig_t, trig_x):
         """Links from the caller's cos / sin: float64 (nchains, NT, NX, 2) = (cos A, sin A) per direction."""
         tt = np.ascontiguousarray(trig_t, dtype=np.float64)
@@ -295,6 +302,9 @@ class Context:
 
     def set_gauge_dev(self, d_A_canonical: int):
         check(self.lib.tb_set_gauge_dev(self._h, C.c_void_p(d_A_canonical)), "tb_set_gauge_dev")
+
+    def set_gauge_shared_dev(self, d_A_one_field: int):
+        check(self.lib.tb_set_gauge_shared_dev(self._h, C.c_void_p(d_A_one_field)), "tb_set_gauge_shared_dev")
 
     def apply_dev(self, op, d_in: int, d_out: int):
         check(self.lib.tb_apply_dev(self._h, op, C.c_void_p(d_in), C.c_void_p(d_out)), "tb_apply_dev")

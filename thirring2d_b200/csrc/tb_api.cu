@@ -219,6 +219,7 @@ extern "C" int tb_destroy(tb_ctx *ctx) {
   for (void *p : dev)
     if (p) cudaFree(p);
   if (ctx->plan_buf) cudaFree(ctx->plan_buf);
+  if (ctx->Ws) cudaFree(ctx->Ws);
   if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   if (ctx->h_iters) cudaFreeHost(ctx->h_iters);
@@ -375,6 +376,28 @@ extern "C" int tb_set_gauge_dev(tb_ctx *ctx, const double *d_A_canonical) {
   TB_CHECK(tb_launch_pack(ctx, d_A_canonical, ctx->Adev));
   TB_CHECK(tb_launch_links(ctx, (const double *)ctx->Adev));
   ctx->msite = nullptr;
+  ctx->have_gauge = true;
+  return TB_OK;
+}
+
+// One gauge field for every chain of the context (the chains are then the right-hand sides of a multi-RHS solve on that
+// field: fermion_phase's sources, hmc.c:794-815).  A: [NT][NX][2] angles, device or host.
+extern "C" int tb_set_gauge_shared_dev(tb_ctx *ctx, const double *d_A_one_field) {
+  if (!ctx || !d_A_one_field) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(join_subs(ctx));
+  TB_CHECK(tb_launch_links_shared(ctx, (const double2 *)d_A_one_field));
+  ctx->have_gauge = true;
+  return TB_OK;
+}
+
+extern "C" int tb_set_gauge_shared(tb_ctx *ctx, const double *A_host) {
+  if (!ctx || !A_host) return TB_EINVAL;
+  TB_CUDA(cudaSetDevice(ctx->device));
+  TB_CHECK(join_subs(ctx));
+  TB_CUDA(cudaMemcpyAsync(ctx->stage, A_host, ctx->V * sizeof(double2), cudaMemcpyHostToDevice, ctx->stream));
+  TB_CHECK(tb_launch_links_shared(ctx, (const double2 *)ctx->stage));
+  TB_CUDA(cudaStreamSynchronize(ctx->stream));   // the staging buffer is free again
   ctx->have_gauge = true;
   return TB_OK;
 }

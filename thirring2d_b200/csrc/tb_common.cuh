@@ -144,6 +144,12 @@ struct tb_ctx {
   // links, device layout [t][x][c]
   double2 *W0, *W1;
   bool have_gauge;
+  // one gauge field shared by every chain of the batch (multi-RHS solves, tb_set_gauge_shared): W0 / W1 above hold it
+  // replicated per chain for every kernel that indexes links by chain; Ws holds it once, W0 [V] then W1 [V], for the
+  // staged streaming kernels, which then read 2 x 16 B of links per SITE instead of per site and chain
+  double2 *Ws;
+  bool gauge_shared;
+  int gp_tt0;       // rows per staged block as tb_choose_geom chose them (a shared gauge field runs shorter blocks)
   // family B (vec_ops.c): per-site mass (occupied site = identity row); msite == nullptr for family A
   double *msite, *msite_buf;
   int *occ_dev, *occ_stage;
@@ -217,6 +223,8 @@ int tb_slab_layout(tb_ctx *ctx);
 int tb_run_cg_any(tb_ctx *ctx, const double2 *b, double2 *x);
 int tb_run_cg_strict(tb_ctx *ctx, const double2 *b, double2 *x);   // tb_strict.cu: reference evaluation order
 int tb_launch_links_from_trig(tb_ctx *ctx, const double2 *T0, const double2 *T1);
+int tb_launch_links_shared(tb_ctx *ctx, const double2 *d_A_one_field);
+void tb_gauge_sharing(tb_ctx *ctx, bool shared);   // sets gauge_shared and the staged geometry that goes with it   // [t][x] angles -> Ws, W0 / W1 / Adev replicated
 void tb_hmc_release(tb_ctx *ctx);
 int tb_create_common(tb_ctx **out, int nt_local, int nx, int nchains, int mode, int device, int rank, int nranks,
                      int nt_global);

@@ -406,6 +406,7 @@ extern "C" int tb_hmc_trajectory(tb_ctx *ctx, int nsteps, double traj_length, un
                                  long long *cg_iters_host) {
   if (!ctx || nsteps < 1 || !(traj_length > 0)) return TB_EINVAL;
   TB_CUDA(cudaSetDevice(ctx->device));
+  tb_gauge_sharing(ctx, false);   // a trajectory evolves one field per chain (the per-chain copies are what it starts from)
   if (!ctx->have_gauge) {
     tb_set_error("tb_hmc_trajectory: no gauge field (tb_set_gauge / tb_hmc_heatbath first)");
     return TB_EINVAL;

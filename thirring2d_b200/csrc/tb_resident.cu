@@ -779,6 +779,7 @@ int tb_run_cg_resident_canon(tb_ctx *ctx, const double2 *b_canon, double2 *x_can
                              cudaStream_t st) {
   if (!tb_resident_canon_supported(ctx)) return TB_EINVAL;
   TbCanon cn = {A_canon, ctx->W0, ctx->W1, ctx->Adev};
+  if (A_canon) tb_gauge_sharing(ctx, false);   // the kernel writes per-chain links
   return launch_resident_wt<64, 64>(ctx, b_canon, x_canon, c0, n, st, &cn);
 }
 

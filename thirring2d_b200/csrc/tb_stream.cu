@@ -306,30 +306,28 @@ struct PipeMaps {
   CUtensorMap m[6];
 };
 
-template <bool FUSED>
-struct PipeStage {
-  // offsets in double2 from the start of a stage, for a tile of bc chains x bx sites (bc * bx = 256)
+// Offsets in double2 from the start of a stage, for a tile of bc chains x bx sites (bc * bx = 256).  Regions in the order
+//   P  (bx + 2) sites (one halo site either side)      [XP: then R, the same shape]
+//   W0 bx sites                                         W1 (bx + 1) sites (halo site on the left)
+//   [FUSED: PV, X, RR: bx sites each]
+// A site is bc values, except in the link regions of a SHARED gauge field (SHW), where it is one value.  Every region
+// that a tensor-map copy fills starts on a multiple of 8 double2 (128 bytes).
+template <bool FUSED, bool XP, bool SHW>
+struct PipeLay {
+  __host__ __device__ static constexpr int al(int v) { return (v + 7) & ~7; }
   __host__ __device__ static constexpr int p(int) { return 0; }
-  __host__ __device__ static int w0(int bc) { return 256 + 2 * bc; }
-  __host__ __device__ static int w1(int bc) { return 512 + 2 * bc; }
-  __host__ __device__ static int pv(int bc) { return 768 + 3 * bc; }
-  __host__ __device__ static int xx(int bc) { return 1024 + 3 * bc; }
-  __host__ __device__ static int rr(int bc) { return 1280 + 3 * bc; }
-  __host__ __device__ static int size(int bc) { return (FUSED ? 1536 : 768) + 3 * bc; }
+  __host__ __device__ static constexpr int rx(int bc) { return 256 + 2 * bc; }
+  __host__ __device__ static constexpr int w0(int bc) { return XP ? 512 + 4 * bc : 256 + 2 * bc; }
+  __host__ __device__ static constexpr int w1(int bc) { return w0(bc) + (SHW ? al(256 / bc) : 256); }
+  __host__ __device__ static constexpr int pv(int bc) { return w1(bc) + (SHW ? al(256 / bc + 1) : 256 + bc); }
+  __host__ __device__ static constexpr int xx(int bc) { return pv(bc) + 256; }
+  __host__ __device__ static constexpr int rr(int bc) { return pv(bc) + 512; }
+  __host__ __device__ static constexpr int size(int bc) { return pv(bc) + (FUSED ? 768 : 0); }
   static size_t smem_bytes(int bc, int ns) { return (size_t)ns * size(bc) * sizeof(double2) + ns * sizeof(unsigned long long); }
 };
-// XP (the direction update folded into the first pass): P and R with a halo site either side, then the links
-struct PipeStageXp {
-  __host__ __device__ static constexpr int p(int) { return 0; }
-  __host__ __device__ static int rx(int bc) { return 256 + 2 * bc; }
-  __host__ __device__ static int w0(int bc) { return 512 + 4 * bc; }
-  __host__ __device__ static int w1(int bc) { return 768 + 4 * bc; }
-  __host__ __device__ static int size(int bc) { return 1024 + 5 * bc; }
-  __host__ __device__ static constexpr int pv(int) { return 0; }   // second-pass regions: not in this stage
-  __host__ __device__ static constexpr int xx(int) { return 0; }
-  __host__ __device__ static constexpr int rr(int) { return 0; }
-  static size_t smem_bytes(int bc, int ns) { return (size_t)ns * size(bc) * sizeof(double2) + ns * sizeof(unsigned long long); }
-};
+static_assert(PipeLay<false, false, false>::size(16) == 768 + 48 && PipeLay<true, false, false>::rr(16) == 1280 + 48 &&
+                  PipeLay<false, true, false>::size(16) == 1024 + 80,
+              "the per-chain layouts of rounds 1 and 2");
 
 // TILED: the tile holds 16 of the batch's chains (batches of more than 16 chains), so a row of the tile is bx runs of
 // 256 bytes, one per site.  Issued as bx separate bulk copies they were 1.5x slower than the marching kernels (the copy
@@ -342,14 +340,18 @@ struct PipeStageXp {
 // the same fma as xpay_kernel, so the values are bit for bit those the separate kernel stores), written to `x` (a
 // SECOND direction buffer: other blocks are still reading their halos from `in`), and M applied to it.  The iteration
 // moves 224 B per site instead of 240 (r 16 + p 16 + links 32 + new p 16 + Mp 16 in this pass) in two launches.
-template <bool FUSED, int PIPE_NS, bool CG, bool TILED = false, bool XP = false>
+//
+// SHW: one gauge field shared by every chain of the batch (tb_set_gauge_shared: the sources of a multi-RHS solve).  W0 and
+// W1 point at the compact fields [t][x]; a row of a tile stages bx (+ 1) links per field instead of bx * bc, and the
+// threads of a site read them as shared-memory broadcasts: the iteration moves 180 B per site and chain instead of 240.
+template <bool FUSED, int PIPE_NS, bool CG, bool TILED = false, bool XP = false, bool SHW = false>
 __global__ void __launch_bounds__(TB_MAX_BLOCK)
 dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ W0,
                    const double2 *__restrict__ W1, const double *__restrict__ mass, const double *__restrict__ emu,
                    const double *__restrict__ emmu, const double2 *__restrict__ pvec, double2 *__restrict__ x,
                    double2 *__restrict__ r, const TbGeom g, const TbCgState s, const TbSlab sl, const int dagger,
                    const __grid_constant__ PipeMaps maps) {
-  using St = typename std::conditional<XP, PipeStageXp, PipeStage<FUSED>>::type;
+  using St = PipeLay<FUSED, XP, SHW>;
   static_assert(!XP || (CG && !FUSED), "XP is the first pass of the fused CG iteration");
   __shared__ double red[TB_MAX_BLOCK];
   extern __shared__ __align__(128) unsigned char pipe_smem[];
@@ -380,6 +382,8 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
   // bytes per halo site (a plain copy: in a ragged last tile only the chains that exist)
   const uint32_t hlen = (uint32_t)((TILED && c0 + bc > g.C) ? g.C - c0 : bc) * 16u;
   const size_t pstride = contiguous ? 0 : (size_t)g.C;             // double2 between centre pieces in global memory
+  const uint32_t wlen = SHW ? (uint32_t)bx * 16u : plen;           // bytes of a row of links of the tile
+  const uint32_t whalo = SHW ? 16u : hlen;                         // ... and of its left halo site
   const int xm = x0 == 0 ? g.nx - 1 : x0 - 1, xp = x0 + bx == g.nx ? 0 : x0 + bx;
 
   // row i of the block (-1 .. TT: one row of halo either side in t) -> stage (i + 1) % NS; issued by warp 0
@@ -395,7 +399,7 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
     if constexpr (XP) {
       // pieces: 0 P, 1 R, 2 W0, 3 W1 (centres); 4, 5 P left / right; 6, 7 R left / right; 8 W1 left.  Row -1: 0..2, row TT: 0..1
       const int npc = kind == 0 ? 3 : kind == 1 ? 2 : 9;
-      if (lane == 0) mbar_expect_tx(bar, kind == 0 ? 3 * plen : kind == 1 ? 2 * plen : 4 * plen + 5 * hlen);
+      if (lane == 0) mbar_expect_tx(bar, kind == 0 ? 2 * plen + wlen : kind == 1 ? 2 * plen : 2 * plen + 2 * wlen + 4 * hlen + whalo);
       __syncwarp();
       if (lane < npc) {
         const int pc_ = lane;
@@ -404,7 +408,11 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
         const double2 *base = arr == 0 ? in : (arr == 1 ? (const double2 *)r : (arr == 2 ? W0 : W1));
         const int off = arr == 0 ? St::p(bc) : (arr == 1 ? St::rx(bc) : (arr == 2 ? St::w0(bc) : St::w1(bc)));
         const bool halo_l = arr != 2;   // W0 has no halo site; P, R, W1 keep one on the left
-        if (side == 0) {
+        if (SHW && arr >= 2) {   // compact links: [site] of the row, W1 with its left halo site in front
+          const size_t rs = (size_t)t * g.nx;
+          if (side == 0) bulk_g2s(dst0 + (uint32_t)(off + (arr == 3 ? 1 : 0)) * 16u, base + rs + x0, wlen, bar);
+          else bulk_g2s(dst0 + (uint32_t)off * 16u, base + rs + xm, 16u, bar);
+        } else if (side == 0) {
           const uint32_t dst = dst0 + (uint32_t)(off + (halo_l ? bc : 0)) * 16u;
           if (TILED) tensor_g2s(dst, &maps.m[arr == 0 ? 0 : (arr == 1 ? 5 : (arr == 2 ? 1 : 2))], 2 * c0, t * g.nx + x0, bar);
           else bulk_g2s(dst, base + row + (size_t)x0 * g.C, plen, bar);
@@ -418,7 +426,8 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
     }
     const int nseg = kind == 0 ? 2 * np : kind == 1 ? np : (FUSED ? 6 * np + 3 : 3 * np + 3);
     if (lane == 0) {
-      const uint32_t bytes = kind == 0 ? 2 * np * plen : kind == 1 ? np * plen : (FUSED ? 6 : 3) * np * plen + 3 * hlen;
+      const uint32_t bytes = kind == 0 ? np * (plen + wlen) : kind == 1 ? np * plen
+                                                                          : np * ((FUSED ? 4 : 1) * plen + 2 * wlen) + 2 * hlen + whalo;
       mbar_expect_tx(bar, bytes);
     }
     __syncwarp();
@@ -442,8 +451,16 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
         src = base + row + (size_t)x0 * g.C + kk * pstride;
         dst = (uint32_t)(a == 0 ? St::pv(bc) : (a == 1 ? St::xx(bc) : St::rr(bc))) * 16u + kk * plen;
       }
-      if (TILED && arr >= 0) tensor_g2s(dst0 + dst, &maps.m[arr], 2 * c0, t * g.nx + x0, bar);
-      else bulk_g2s(dst0 + dst, src, bytes, bar);
+      if (SHW && (arr == 1 || arr == 2 || sg == 3 * np + 2)) {   // compact links (W0 / W1 point at [t][x] fields)
+        const size_t rs = (size_t)t * g.nx;
+        if (arr == 1) bulk_g2s(dst0 + (uint32_t)St::w0(bc) * 16u, W0 + rs + x0, wlen, bar);
+        else if (arr == 2) bulk_g2s(dst0 + (uint32_t)(St::w1(bc) + 1) * 16u, W1 + rs + x0, wlen, bar);
+        else bulk_g2s(dst0 + (uint32_t)St::w1(bc) * 16u, W1 + rs + xm, 16u, bar);
+      } else if (TILED && arr >= 0) {
+        tensor_g2s(dst0 + dst, &maps.m[arr], 2 * c0, t * g.nx + x0, bar);
+      } else {
+        bulk_g2s(dst0 + dst, src, bytes, bar);
+      }
     }
   };
   auto stage_of = [&](int i) { return stage0 + ((i + 1) % PIPE_NS) * ssize; };
@@ -452,7 +469,8 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
   if (tid < 32)
     for (int i = -1; i < PIPE_NS - 1 && i <= TT; i++) fill(i);
 
-  const bool act = CG ? s.active[b.c] != 0 : true;
+  // the missing chains of a ragged last tile compute on zero-filled boxes and store nothing
+  const bool act = (!TILED || b.c < g.C) && (CG ? s.active[b.c] != 0 : true);
   const bool dag = FUSED || (!CG && dagger);
   const double m = mass[b.c];
   const double af = dag ? emmu[b.c] : emu[b.c];   // factor on the +t hop (M^dagger: e^{-mu})
@@ -465,7 +483,7 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
   auto field = [&](const double2 *S, int off) {
     const double2 pv = S[St::p(bc) + off];
     if constexpr (XP) {
-      const double2 rv = S[PipeStageXp::rx(bc) + off];
+      const double2 rv = S[St::rx(bc) + off];
       return make_double2(fma(be, pv.x, rv.x), fma(be, pv.y, rv.y));
     } else {
       return pv;
@@ -474,7 +492,8 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
 
   wait_row(-1);
   double2 pm = field(stage_of(-1), bc + tid);
-  double2 w0m = stage_of(-1)[St::w0(bc) + tid];
+  const int wi = SHW ? b.x_local : tid;   // index of the thread's link in a stage row (compact: one per site)
+  double2 w0m = stage_of(-1)[St::w0(bc) + wi];
   wait_row(0);
   double2 pc = field(stage_of(0), bc + tid);
   __syncthreads();   // stage of row -1 is free
@@ -485,8 +504,8 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
     const double2 *S = stage_of(i);
     const double2 pp = field(stage_of(i + 1), bc + tid);
     const double2 pxm = field(S, tid), pxp = field(S, 2 * bc + tid);
-    const double2 w0c = S[St::w0(bc) + tid];
-    const double2 w1m = S[St::w1(bc) + tid], w1c = S[St::w1(bc) + bc + tid];
+    const double2 w0c = S[St::w0(bc) + wi];
+    const double2 w1m = S[St::w1(bc) + wi], w1c = S[St::w1(bc) + (SHW ? 1 : bc) + wi];
     // hops: +af W0(n) psi(n+t) - ab conj(W0(n-t)) psi(n-t) + W1(n) psi(n+x) - conj(W1(n-x)) psi(n-x)
     const double fr = w0c.x * af, fi = w0c.y * af;
     const double br = w0m.x * ab, bi = w0m.y * ab;
@@ -1531,6 +1550,34 @@ __global__ void links_kernel(const double2 *__restrict__ A, double2 *__restrict_
   }
 }
 
+// One field for the whole batch: A[t][x] -> the compact links Ws = (W0 [V], W1 [V]) and the per-chain arrays W0 / W1 /
+// Adev filled with copies (links_kernel's arithmetic: the same links bit for bit)
+__global__ void links_shared_kernel(const double2 *__restrict__ A, double2 *__restrict__ Ws, double2 *__restrict__ W0,
+                                    double2 *__restrict__ W1, double2 *__restrict__ Adev, int nt, int nx, int C) {
+  const size_t V = (size_t)nt * nx;
+  for (size_t site = (size_t)blockIdx.x * blockDim.y + threadIdx.y; site < V; site += (size_t)gridDim.x * blockDim.y) {
+    const int x = (int)(site % nx);
+    const int t = (int)(site / nx);
+    const double2 a = A[site];
+    double s0, c0v, s1, c1;
+    sincos(a.x, &s0, &c0v);
+    sincos(a.y, &s1, &c1);
+    double f0 = (x & 1) ? -0.5 : 0.5;
+    if (t == nt - 1) f0 = -f0;
+    const double f1 = (x == nx - 1) ? -0.5 : 0.5;
+    const double2 w0 = make_double2(f0 * c0v, f0 * s0), w1 = make_double2(f1 * c1, f1 * s1);
+    if (threadIdx.x == 0) {
+      Ws[site] = w0;
+      Ws[V + site] = w1;
+    }
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      W0[site * C + c] = w0;
+      W1[site * C + c] = w1;
+      Adev[site * C + c] = a;
+    }
+  }
+}
+
 // Family B (vec_ops.c:96-172): links are real constants masked by the occupation field, W_mu(n) = s 1/2 eta_mu
 // if both n and n+mu^ are free, else 0 (hops into or out of an occupied site are dropped, vec_ops.c:110-128); the
 // site mass is m on free sites and 1 on occupied ones (identity row, vec_ops.c:130).  occ: [t][x][c] ints.
@@ -1714,17 +1761,21 @@ int tb_choose_geom(tb_ctx *ctx) {
     p.nxtiles = ctx->nx / p.bx;
     p.Cpad = p.nctiles * p.bc;                // <= the marching geometry's Cpad, which sizes the per-chain arrays
     const long min_blocks = et ? 1 : 370;
+    const char *er = getenv("TB_PIPE_ROWS");   // development: rows per staged block
     for (int ttp = 64; ttp >= min_rows; ttp--) {
+      if (er && ttp != atoi(er)) continue;
       if (ctx->nt % ttp != 0 || (long)p.nctiles * p.nxtiles * (ctx->nt / ttp) < min_blocks) continue;
       if ((size_t)p.nxtiles * (ctx->nt / ttp) * p.Cpad > (size_t)g.nxtiles * ctx->nt * g.Cpad) continue;   // partial sums buffer
       p.tt = ttp;
       p.nttiles = ctx->nt / ttp;
       p.nslots = p.nxtiles * p.nttiles;
+      ctx->gp_tt0 = ttp;
       ctx->pipe_ok = true;
       ctx->pipe_tiled = tiled;
       break;
     }
   }
+  tb_gauge_sharing(ctx, ctx->gauge_shared);
   return TB_OK;
 }
 
@@ -1760,31 +1811,45 @@ int tb_stream_kernels(const tb_ctx *ctx, int *tile_chains, int *tile_sites, int 
 template <bool FUSED, bool CG = true, bool XP = false>
 static int launch_pipe(tb_ctx *ctx, const double2 *in, double2 *out, double2 *x, bool dagger = false,
                        const double2 *pcur = nullptr) {
-  using St = typename std::conditional<XP, PipeStageXp, PipeStage<FUSED>>::type;
   const TbGeom &g = ctx->gp;
   if (!pcur) pcur = ctx->p;
-  int ns = PIPE_NS_MAX;
-  while (ns > 2 && 2 * (St::smem_bytes(g.bc, ns) + 4096) > 227 * 1024) ns--;   // two blocks per SM at least
-  if (ns < 3) ns = 3;
-  const size_t smem = St::smem_bytes(g.bc, ns);
+  const bool shw = ctx->gauge_shared && ctx->Ws != nullptr;
+  const double2 *w0 = shw ? ctx->Ws : ctx->W0, *w1 = shw ? ctx->Ws + ctx->V : ctx->W1;
   PipeMaps maps;
-  auto kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4, CG, false, XP> : dslash_pipe_kernel<FUSED, 3, CG, false, XP>;
+  memset(&maps, 0, sizeof(maps));
   if (ctx->pipe_tiled) {
-    kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4, CG, true, XP> : dslash_pipe_kernel<FUSED, 3, CG, true, XP>;
     TB_CHECK(tmap_for(ctx, in, &maps.m[0]));
-    TB_CHECK(tmap_for(ctx, ctx->W0, &maps.m[1]));
-    TB_CHECK(tmap_for(ctx, ctx->W1, &maps.m[2]));
+    if (!shw) {
+      TB_CHECK(tmap_for(ctx, ctx->W0, &maps.m[1]));
+      TB_CHECK(tmap_for(ctx, ctx->W1, &maps.m[2]));
+    }
     maps.m[3] = maps.m[4] = maps.m[5] = maps.m[0];
     if (FUSED) {
       TB_CHECK(tmap_for(ctx, pcur, &maps.m[3]));
       TB_CHECK(tmap_for(ctx, x, &maps.m[4]));
     }
     if (FUSED || XP) TB_CHECK(tmap_for(ctx, ctx->r, &maps.m[5]));
+  }
+  size_t smem;
+  void (*kern)(const double2 *, double2 *, const double2 *, const double2 *, const double *, const double *, const double *,
+               const double2 *, double2 *, double2 *, const TbGeom, const TbCgState, const TbSlab, const int, const PipeMaps);
+  if (shw) {
+    // the stages of a shared field are small (a row of links is bx values): a ring of 8 keeps as many bytes in flight in
+    // the passes that stage one vector as a ring of 4 does with per-chain links
+    constexpr int NS = (FUSED || XP) ? 4 : 8;
+    smem = PipeLay<FUSED, XP, true>::smem_bytes(g.bc, NS);
+    kern = ctx->pipe_tiled ? dslash_pipe_kernel<FUSED, NS, CG, true, XP, true> : dslash_pipe_kernel<FUSED, NS, CG, false, XP, true>;
   } else {
-    memset(&maps, 0, sizeof(maps));
+    using St = PipeLay<FUSED, XP, false>;
+    int ns = PIPE_NS_MAX;
+    while (ns > 2 && 2 * (St::smem_bytes(g.bc, ns) + 4096) > 227 * 1024) ns--;   // two blocks per SM at least
+    if (ns < 3) ns = 3;
+    smem = St::smem_bytes(g.bc, ns);
+    if (ctx->pipe_tiled) kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4, CG, true, XP> : dslash_pipe_kernel<FUSED, 3, CG, true, XP>;
+    else kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4, CG, false, XP> : dslash_pipe_kernel<FUSED, 3, CG, false, XP>;
   }
   TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid_of(g), TB_MAX_BLOCK, smem, ctx->stream>>>(in, out, ctx->W0, ctx->W1, ctx->d_mass, ctx->d_emu, ctx->d_emmu,
+  kern<<<grid_of(g), TB_MAX_BLOCK, smem, ctx->stream>>>(in, out, w0, w1, ctx->d_mass, ctx->d_emu, ctx->d_emmu,
                                                          pcur, x, ctx->r, g, ctx->cg, ctx->slab, dagger ? 1 : 0, maps);
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
@@ -1795,6 +1860,7 @@ static int launch_pipe(tb_ctx *ctx, const double2 *in, double2 *out, double2 *x,
 // pipelines sub-batches of chains on separate streams).
 int tb_launch_links_slice(tb_ctx *ctx, const double2 *d_A_dev_layout, int c0, int n, cudaStream_t st) {
   ctx->msite = nullptr;  // complex U(1) links: family A, no occupation mask
+  tb_gauge_sharing(ctx, false);
   const size_t total = ctx->V * (size_t)n;
   int blocks = (int)((total + 255) / 256);
   if (blocks > TB_NUM_SMS_B200 * 16) blocks = TB_NUM_SMS_B200 * 16;
@@ -1838,6 +1904,7 @@ int tb_launch_unpack_slice(tb_ctx *ctx, const double2 *d_vec, double2 *d_canonic
 
 // occupation field in canonical layout [chain][t][x] (device ints) -> masked links + site masses
 int tb_launch_occupancy(tb_ctx *ctx, const int *d_field_canonical) {
+  tb_gauge_sharing(ctx, false);
   cudaStream_t st = ctx->stream;
   const int *occ = d_field_canonical;
   if (ctx->C > 1) {
@@ -1852,6 +1919,39 @@ int tb_launch_occupancy(tb_ctx *ctx, const int *d_field_canonical) {
                                                  ctx->nx, ctx->C, ctx->occ_bc);
   ctx->launches++;
   TB_CUDA(cudaGetLastError());
+  return TB_OK;
+}
+
+// With a shared field the second pass keeps three blocks per SM instead of two and the first pass a ring of 8 stages:
+// shorter blocks fill the waves better.  Measured per CG iteration, replicated -> shared (profiles/shared_r02x_probe.txt):
+// 1024^2 x 16: 64 rows 621 -> 504, 32 rows 598 -> 482, 16 rows 633 -> 512; 512^2 x 32 (16-chain tiles): 64 rows 318 ->
+// 313, 32 rows 334 -> 286, 16 rows 340 -> 282; 256^2 x 64: 32 rows 169 -> 169, 16 rows 177 -> 154.
+void tb_gauge_sharing(tb_ctx *ctx, bool shared) {
+  ctx->gauge_shared = shared;
+  if (!ctx->pipe_ok) return;
+  TbGeom &p = ctx->gp;
+  int tt = ctx->gp_tt0;
+  const int want = ctx->pipe_tiled ? 16 : 32;
+  if (shared && want < tt && ctx->nt % want == 0 &&
+      (size_t)p.nxtiles * (ctx->nt / want) * p.Cpad <= (size_t)ctx->g.nxtiles * ctx->nt * ctx->g.Cpad)
+    tt = want;
+  p.tt = tt;
+  p.nttiles = ctx->nt / tt;
+  p.nslots = p.nxtiles * p.nttiles;
+}
+
+int tb_launch_links_shared(tb_ctx *ctx, const double2 *d_A_one_field) {
+  if (ctx->nranks > 1) { tb_set_error("a shared gauge field is not available in slab mode"); return TB_EINVAL; }
+  if (!ctx->Ws) TB_CUDA(cudaMalloc((void **)&ctx->Ws, 2 * ctx->V * sizeof(double2)));
+  const dim3 block(32, 8);
+  int blocks = (int)((ctx->V + 7) / 8);
+  if (blocks > TB_NUM_SMS_B200 * 16) blocks = TB_NUM_SMS_B200 * 16;
+  links_shared_kernel<<<blocks, block, 0, ctx->stream>>>(d_A_one_field, ctx->Ws, ctx->W0, ctx->W1, ctx->Adev, ctx->nt, ctx->nx,
+                                                        ctx->C);
+  ctx->launches++;
+  TB_CUDA(cudaGetLastError());
+  ctx->msite = nullptr;
+  tb_gauge_sharing(ctx, true);
   return TB_OK;
 }
 
@@ -2180,7 +2280,8 @@ int tb_run_cg_stream(tb_ctx *ctx, const double2 *b, double2 *x) {
   const bool use_graph = getenv("TB_NO_GRAPH") == nullptr;
   // the graph holds its kernel arguments by value: everything a later call may change is part of the key (the per-site
   // mass pointer of family B is one of them; CG tolerances and tile shapes invalidate the graph where they are set)
-  const int graph_key = chunk * 16 + (fused ? 1 : 0) + (use_pipe(ctx) ? 2 : 0) + (ctx->msite ? 4 : 0) + (xp ? 8 : 0);
+  const int graph_key = chunk * 32 + (fused ? 1 : 0) + (use_pipe(ctx) ? 2 : 0) + (ctx->msite ? 4 : 0) + (xp ? 8 : 0) +
+                        (ctx->gauge_shared ? 16 : 0);
   if (use_graph && (ctx->cg_graph == nullptr || ctx->cg_graph_chunk != graph_key)) {
     if (ctx->cg_graph) { cudaGraphExecDestroy(ctx->cg_graph); ctx->cg_graph = nullptr; }
     cudaStream_t cap;

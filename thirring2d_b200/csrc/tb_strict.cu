@@ -194,6 +194,7 @@ int tb_run_cg_strict(tb_ctx *ctx, const double2 *b, double2 *x) {
 }
 
 int tb_launch_links_from_trig(tb_ctx *ctx, const double2 *T0, const double2 *T1) {
+  tb_gauge_sharing(ctx, false);
   int blocks = (int)((ctx->nsite + 255) / 256);
   if (blocks > TB_NUM_SMS_B200 * 16) blocks = TB_NUM_SMS_B200 * 16;
   links_from_trig_kernel<<<blocks, 256, 0, ctx->stream>>>(T0, T1, ctx->W0, ctx->W1, ctx->nt, ctx->nx, ctx->C,

@@ -34,6 +34,8 @@ SIGNATURES = {
     "tb_plan_schedule": (_i, [_ip, _ip, _i, _i, _ip, _ip, _ip]),
     "tb_set_gauge": (_i, [_vp, _vp]),
     "tb_set_links_trig": (_i, [_vp, _vp, _vp]),
+    "tb_set_gauge_shared": (_i, [_vp, _vp]),
+    "tb_set_gauge_shared_dev": (_i, [_vp, _vp]),
     "tb_set_occupancy": (_i, [_vp, _vp]),
     "tb_set_occupancy_bc": (_i, [_vp, _vp, _i, _i]),
     "tb_apply_real": (_i, [_vp, _i, _vp, _vp]),
