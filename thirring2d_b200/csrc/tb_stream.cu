@@ -344,13 +344,13 @@ static_assert(PipeLay<false, false, false>::size(16) == 768 + 48 && PipeLay<true
 // SHW: one gauge field shared by every chain of the batch (tb_set_gauge_shared: the sources of a multi-RHS solve).  W0 and
 // W1 point at the compact fields [t][x]; a row of a tile stages bx (+ 1) links per field instead of bx * bc, and the
 // threads of a site read them as shared-memory broadcasts: the iteration moves 180 B per site and chain instead of 240.
-template <bool FUSED, int PIPE_NS, bool CG, bool TILED = false, bool XP = false, bool SHW = false>
-__global__ void __launch_bounds__(TB_MAX_BLOCK)
-dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ W0,
-                   const double2 *__restrict__ W1, const double *__restrict__ mass, const double *__restrict__ emu,
-                   const double *__restrict__ emmu, const double2 *__restrict__ pvec, double2 *__restrict__ x,
-                   double2 *__restrict__ r, const TbGeom g, const TbCgState s, const TbSlab sl, const int dagger,
-                   const __grid_constant__ PipeMaps maps) {
+template <bool FUSED, int PIPE_NS, bool CG, bool TILED, bool XP, bool SHW>
+__device__ __forceinline__ void
+dslash_pipe_body(const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ W0,
+                 const double2 *__restrict__ W1, const double *__restrict__ mass, const double *__restrict__ emu,
+                 const double *__restrict__ emmu, const double2 *__restrict__ pvec, double2 *__restrict__ x,
+                 double2 *__restrict__ r, const TbGeom &g, const TbCgState &s, const TbSlab &sl, const int dagger,
+                 const PipeMaps &maps) {
   using St = PipeLay<FUSED, XP, SHW>;
   static_assert(!XP || (CG && !FUSED), "XP is the first pass of the fused CG iteration");
   __shared__ double red[TB_MAX_BLOCK];
@@ -553,6 +553,26 @@ dslash_pipe_kernel(const double2 *__restrict__ in, double2 *__restrict__ out, co
     if (tid < 32 && i + PIPE_NS <= TT) fill(i + PIPE_NS);
   }
   if (CG) reduce_finalize<FUSED ? FIN_RR : FIN_PQ, false, FUSED ? TB_RED_RR : TB_RED_PQ>(acc, g, s, sl, b, red);
+}
+
+#define TB_PIPE_PARAMS                                                                                                  \
+  const double2 *__restrict__ in, double2 *__restrict__ out, const double2 *__restrict__ W0, const double2 *__restrict__ W1, \
+      const double *__restrict__ mass, const double *__restrict__ emu, const double *__restrict__ emmu,                 \
+      const double2 *__restrict__ pvec, double2 *__restrict__ x, double2 *__restrict__ r, const TbGeom g, const TbCgState s, \
+      const TbSlab sl, const int dagger, const __grid_constant__ PipeMaps maps
+#define TB_PIPE_ARGS in, out, W0, W1, mass, emu, emmu, pvec, x, r, g, s, sl, dagger, maps
+
+template <bool FUSED, int PIPE_NS, bool CG, bool TILED = false, bool XP = false, bool SHW = false>
+__global__ void __launch_bounds__(TB_MAX_BLOCK) dslash_pipe_kernel(TB_PIPE_PARAMS) {
+  dslash_pipe_body<FUSED, PIPE_NS, CG, TILED, XP, SHW>(TB_PIPE_ARGS);
+}
+// The plain first pass with whole-batch tiles, held to 64 registers = four blocks per SM.  That is what ptxas chose by
+// itself until the body grew its variants; at the 70 registers it then took, 2048^2 ran at the marching kernels' 188 us
+// per iteration instead of 166.  (Bounding every variant moved the others the wrong way: their register counts are
+// ptxas's own.)
+template <int PIPE_NS, bool CG>
+__global__ void __launch_bounds__(TB_MAX_BLOCK, 4) dslash_pipe_plain_kernel(TB_PIPE_PARAMS) {
+  dslash_pipe_body<false, PIPE_NS, CG, false, false, false>(TB_PIPE_ARGS);
 }
 
 // p = r + beta p (hmc.c:391-392).  SLAB: p is an exchange vector: wait until the neighbours have finished
@@ -1845,8 +1865,13 @@ static int launch_pipe(tb_ctx *ctx, const double2 *in, double2 *out, double2 *x,
     while (ns > 2 && 2 * (St::smem_bytes(g.bc, ns) + 4096) > 227 * 1024) ns--;   // two blocks per SM at least
     if (ns < 3) ns = 3;
     smem = St::smem_bytes(g.bc, ns);
-    if (ctx->pipe_tiled) kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4, CG, true, XP> : dslash_pipe_kernel<FUSED, 3, CG, true, XP>;
-    else kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4, CG, false, XP> : dslash_pipe_kernel<FUSED, 3, CG, false, XP>;
+    if (ctx->pipe_tiled) {
+      kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4, CG, true, XP> : dslash_pipe_kernel<FUSED, 3, CG, true, XP>;
+    } else if constexpr (!FUSED && !XP) {
+      kern = ns == 4 ? dslash_pipe_plain_kernel<4, CG> : dslash_pipe_plain_kernel<3, CG>;
+    } else {
+      kern = ns == 4 ? dslash_pipe_kernel<FUSED, 4, CG, false, XP> : dslash_pipe_kernel<FUSED, 3, CG, false, XP>;
+    }
   }
   TB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid_of(g), TB_MAX_BLOCK, smem, ctx->stream>>>(in, out, w0, w1, ctx->d_mass, ctx->d_emu, ctx->d_emmu,
