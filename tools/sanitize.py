@@ -28,6 +28,36 @@ if only in ("new", "pipe"):
             print(nt, nx, n, ctx.solver_info(), int(info.iters.min()), int(info.iters.max()),
                   np.bincount(info.status, minlength=4).tolist(), flush=True)
     sys.exit(0)
+if only == "r2":
+    # round 2: 16-chain tiles (one ragged), the two-launch iteration, a shared gauge field, the point-to-point cluster
+    # hand-overs; few iterations (memcheck)
+    os.environ["TB_SUBBATCHES"] = "1"
+    os.environ["TB_PIPE_TEST"] = "1"
+    for (nt, nx, n, xpay, shared) in [(32, 32, 64, "0", False), (32, 32, 20, "1", False), (32, 64, 8, "1", True),
+                                      (32, 32, 40, "0", True), (16, 48, 48, "1", True)]:
+        os.environ["TB_PIPE_XPAY"] = xpay
+        A = rng.uniform(-np.pi, np.pi, size=(n, nt, nx, 2))
+        xi = rng.normal(size=(n, nt, nx)) + 1j * rng.normal(size=(n, nt, nx))
+        with tb.Context(nt, nx, n, tb.MODE_ADJOINT, m=0.5, mu=0.1) as ctx:
+            ctx.set_tuning(solver=1)
+            ctx.set_cg(1e-30, 12)
+            if shared:
+                ctx.set_gauge_shared(A[0])
+            else:
+                ctx.set_gauge(A)
+            b = ctx.fm_conjugate_mul(xi)
+            x, info = ctx.fmdm_invert_cg(b)
+            print(nt, nx, n, "xpay", xpay, "shared", shared, ctx.streaming_info(), int(info.iters.max()), flush=True)
+    for (nt, nx) in [(128, 128), (256, 256), (128, 64)]:
+        A = rng.uniform(-np.pi, np.pi, size=(2, nt, nx, 2))
+        xi = rng.normal(size=(2, nt, nx)) + 1j * rng.normal(size=(2, nt, nx))
+        with tb.Context(nt, nx, 2, tb.MODE_ADJOINT, m=0.5, mu=0.1) as ctx:
+            ctx.set_cg(1e-30, 12)
+            ctx.set_gauge(A)
+            b = ctx.fm_conjugate_mul(xi)
+            x, info = ctx.fmdm_invert_cg(b)
+            print(nt, nx, ctx.solver_info(), info.iters.tolist(), flush=True)
+    sys.exit(0)
 for (nt, nx, n, mode, m, mu) in CASES:
     if (only == "small" and nt * nx > 4096) or (only == "cluster" and nt * nx <= 4096):
         continue
