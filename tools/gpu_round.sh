@@ -43,7 +43,14 @@ done
 python tools/ncu_summary.py launches $OUT/launches_$TAG.csv > $OUT/launches_${TAG}_bench.txt 2>&1
 echo "== planned vs plain launches, staged vs marching kernels"
 python tools/probe_plan.py 2>&1 | tee $OUT/probe_plan_$TAG.txt | cut -c1-250
-python tools/probe_pipe.py 2048,2048,1,0.01 1024,1024,4,0.01 512,512,16,0.01 256,256,64,0.01 2>&1 | tee $OUT/probe_pipe_$TAG.txt | cut -c1-250
+python tools/probe_pipe.py 2048,2048,1,0.01 4096,4096,1,0.01 512,512,16,0.01 256,256,64,0.01 128,128,2048,0.01 2>&1 | tee $OUT/probe_pipe_$TAG.txt | cut -c1-250
+echo "== many sources on one gauge field (tb_set_gauge_shared), cluster solver"
+python tools/probe_shared.py 2>&1 | tee $OUT/probe_shared_$TAG.txt | cut -c1-250
+python tools/probe_cluster.py 256,256,8,0.01 256,256,7,0.05 128,128,33,0.1 2>&1 | grep "solver=2" | tee $OUT/probe_cluster_$TAG.txt | cut -c1-250
+echo "== compute-sanitizer over the round-2 kernels"
+for tool in memcheck racecheck synccheck; do
+  compute-sanitizer --tool $tool --print-limit 5 python tools/sanitize.py r2 2>&1 | tail -3 | tee $OUT/sanitize_${TAG}_$tool.txt
+done
 if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
   echo "== 2+ GPUs: slab parity tests and the one-launch slab solve (tools/multi_gpu.sh)"
   bash tools/multi_gpu.sh $TAG quick 2>&1 | tee $OUT/slab_$TAG.txt | cut -c1-250
